@@ -1,0 +1,44 @@
+"""The CPU oracle against the golden vectors produced by the reference's own code
+(tests/golden/make_golden.py).  This is what pins the oracle; the CUDA path is then
+compared with the oracle (tests/test_gpu_*.py)."""
+import numpy as np
+import pytest
+
+import util
+from arpeggio_b200 import abi
+from oracle import oracle
+
+CASES = util.golden_cases()
+
+
+def test_fixtures_present():
+    assert len(CASES) >= 5
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_pairs_match_reference(case):
+    g = util.Golden(case)
+    got = oracle.pairs(g.soa, g.params)
+    if g.meta['raises'] == 'AttributeError':
+        # utils.py:173: the reference dies on an xbond donor without a single-bond neighbour;
+        # the oracle reports the pair that would have raised
+        assert np.any(got['mask'] & np.uint32(abi.PAIR_FAULT_XBOND_NO_NBR))
+        return
+    assert not np.any(got['mask'] & np.uint32(abi.PAIR_FAULT_XBOND_NO_NBR))
+    util.assert_records_equal(got, g.exp_pairs, f'{case} atom-atom')
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_pairs_bruteforce_equals_grid(case):
+    g = util.Golden(case)
+    util.assert_records_equal(oracle.pairs(g.soa, g.params, bruteforce=True), oracle.pairs(g.soa, g.params),
+                              f'{case} grid vs brute force')
+
+
+@pytest.mark.parametrize('case', [c for c in CASES if c != 'xbond_fault'])
+def test_planes_match_reference(case):
+    g = util.Golden(case)
+    util.assert_records_equal(oracle.ring_ring(g.rings, g.params), g.exp_ring_ring, f'{case} ring-ring')
+    util.assert_records_equal(oracle.atom_ring(g.soa, g.rings, g.params), g.exp_atom_ring, f'{case} atom-ring')
+    util.assert_records_equal(oracle.amide_amide(g.amides, g.params), g.exp_amide_amide, f'{case} amide-amide')
+    util.assert_records_equal(oracle.amide_ring(g.amides, g.rings, g.params), g.exp_amide_ring, f'{case} amide-ring')

@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # ---- error codes ---------------------------------------------------------
 OK = 0
@@ -177,7 +177,7 @@ EXPORTED_SYMBOLS = (
     'arp_upload_atoms', 'arp_pairs_run', 'arp_pairs_fetch', 'arp_pairs_device_ptr',
     'arp_upload_planes', 'arp_ring_ring_run', 'arp_ring_ring_fetch', 'arp_atom_ring_run',
     'arp_atom_ring_fetch', 'arp_amide_amide_run', 'arp_amide_amide_fetch', 'arp_amide_ring_run',
-    'arp_amide_ring_fetch', 'arp_flag_within', 'arp_sync', 'arp_get_stats', 'arp_timing_iters',
+    'arp_amide_ring_fetch', 'arp_flag_within', 'arp_sync', 'arp_get_stats', 'arp_timing_iters', 'arp_launch_count',
 )
 
 

@@ -1,0 +1,482 @@
+/*
+ * arp_api.cu -- the C ABI of libarpeggio_cuda.so (include/arpeggio_cuda.h): life cycle,
+ * parameters, uploads, the atom-atom run/fetch calls and the benchmark hooks.
+ * The plane entry points live in arp_planes.cu.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <new>
+
+#include "arp_ctx.cuh"
+
+static char g_create_err[ARP_ERRLEN] = {0};
+
+/* ---- cosine images of the angle thresholds, from the C library's acos (see arp_params) ---- */
+namespace {
+
+inline long long ord64(double x) { long long b; memcpy(&b, &x, 8); return b < 0 ? -(b & 0x7fffffffffffffffLL) : b; }
+inline double unord64(long long k) { long long b = k >= 0 ? k : (long long)((unsigned long long)(-k) | 0x8000000000000000ULL); double x; memcpy(&x, &b, 8); return x; }
+inline long long ord32(float x) { int b; memcpy(&b, &x, 4); return b < 0 ? -(long long)(b & 0x7fffffff) : (long long)b; }
+inline float unord32(long long k) { unsigned b = k >= 0 ? (unsigned)k : ((unsigned)(-k) | 0x80000000u); float x; memcpy(&x, &b, 4); return x; }
+
+/* last argument on the True side of a monotone predicate over [lo, hi]; *constant set if it never switches */
+template <class Pred> double edge64(Pred pred, double lo, double hi, bool true_below, bool* constant)
+{
+    long long klo = ord64(lo), khi = ord64(hi);
+    bool plo = pred(unord64(klo)), phi = pred(unord64(khi));
+    *constant = plo == phi;
+    if (*constant) return 0.0;
+    while (khi - klo > 1) {
+        long long mid = klo + (khi - klo) / 2;
+        if (pred(unord64(mid)) == plo) klo = mid; else khi = mid;
+    }
+    return unord64(true_below ? klo : khi);
+}
+template <class Pred> float edge32(Pred pred, float lo, float hi, bool true_below, bool* constant)
+{
+    long long klo = ord32(lo), khi = ord32(hi);
+    bool plo = pred(unord32(klo)), phi = pred(unord32(khi));
+    *constant = plo == phi;
+    if (*constant) return 0.f;
+    while (khi - klo > 1) {
+        long long mid = klo + (khi - klo) / 2;
+        if (pred(unord32(mid)) == plo) klo = mid; else khi = mid;
+    }
+    return unord32(true_below ? klo : khi);
+}
+
+inline double fold_deg64(double c)
+{
+    double rad = acos(c);
+    if (rad > M_PI / 2) rad = rad - M_PI;
+    return fabs(rad * 180 / M_PI);
+}
+inline float fold_deg32(float c)
+{
+    float rad = acosf(c);
+    if (rad > (float)(M_PI / 2)) { volatile float t = rad - (float)M_PI; rad = t; }
+    volatile float deg = rad * 180.0f;
+    deg = deg / (float)M_PI;
+    return fabsf(deg);
+}
+
+void cosine_images(arp_params* p)
+{
+    bool k;
+    auto ge = [&](double thr) {
+        double e = edge64([&](double c) { return acos(c) >= thr; }, -1.0, 1.0, true, &k);
+        return k ? (acos(1.0) >= thr ? 2.0 : -2.0) : e;
+    };
+    p->cos_hbond = ge(p->hbond_angle);
+    p->cos_weak_hbond = ge(p->weak_hbond_angle);
+    p->cos_cx_min = ge(p->cx_angle_min);
+    {
+        double mx = p->cx_angle_max;
+        double e = edge64([&](double c) { return acos(c) <= mx; }, -1.0, 1.0, false, &k);
+        p->cos_cx_max = k ? (acos(-1.0) <= mx ? -2.0 : 2.0) : e;
+    }
+    {
+        float thr = (float)p->xbond_angle;
+        float e = edge32([&](float c) { return acosf(c) >= thr; }, -1.f, 1.f, true, &k);
+        p->cos_xbond_f32 = k ? (acosf(1.f) >= thr ? 2.f : -2.f) : e;
+    }
+    {
+        double split = edge64([&](double c) { return acos(c) > M_PI / 2; }, -1.0, 1.0, true, &k);
+        double nxt = unord64(ord64(split) + 1);
+        p->cos_split_f64 = split;
+        for (int i = 0; i < 3; ++i) {
+            double b = p->plane_bins_deg[i];
+            double e = edge64([&](double c) { return fold_deg64(c) <= b; }, nxt, 1.0, false, &k);
+            p->cos_pos_f64[i] = k ? (fold_deg64(1.0) <= b ? -2.0 : 2.0) : e;
+            e = edge64([&](double c) { return fold_deg64(c) <= b; }, -1.0, split, true, &k);
+            p->cos_neg_f64[i] = k ? (fold_deg64(-1.0) <= b ? 2.0 : -2.0) : e;
+        }
+    }
+    {
+        float split = edge32([&](float c) { return acosf(c) > (float)(M_PI / 2); }, -1.f, 1.f, true, &k);
+        float nxt = unord32(ord32(split) + 1);
+        p->cos_split_f32 = split;
+        for (int i = 0; i < 3; ++i) {
+            float b = (float)p->plane_bins_deg[i];
+            float e = edge32([&](float c) { return fold_deg32(c) <= b; }, nxt, 1.f, false, &k);
+            p->cos_pos_f32[i] = k ? (fold_deg32(1.f) <= b ? -2.f : 2.f) : e;
+            e = edge32([&](float c) { return fold_deg32(c) <= b; }, -1.f, split, true, &k);
+            p->cos_neg_f32[i] = k ? (fold_deg32(-1.f) <= b ? 2.f : -2.f) : e;
+        }
+    }
+}
+
+void derive_rule_params(const arp_params& p, ArpRuleParams* r)
+{
+    memset(r, 0, sizeof *r);
+    r->r2 = p.interacting_cutoff * p.interacting_cutoff;
+    r->vdw_comp = p.vdw_comp;
+    r->h_vdw = p.h_vdw;
+    r->dist_max = (float)p.dist_max;          /* NEP 50: np.float32 <op> python float compares in float32 */
+    r->hbond_polar = (float)p.hbond_polar_dist;
+    r->weak_polar = (float)p.weak_polar_dist;
+    r->ionic = (float)p.ionic_dist;
+    r->carbonyl = (float)p.carbonyl_dist;
+    r->aromatic = (float)p.aromatic_dist;
+    r->hydrophobic = (float)p.hydrophobic_dist;
+    r->metal = (float)p.metal_dist;
+    r->cos_hbond = p.cos_hbond;
+    r->cos_weak_hbond = p.cos_weak_hbond;
+    r->cos_cx_min = p.cos_cx_min;
+    r->cos_cx_max = p.cos_cx_max;
+    r->cos_xbond_f32 = p.cos_xbond_f32;
+    r->blas_fma = p.blas_fma;
+    r->include_seq_adjacent = p.include_sequence_adjacent;
+    r->pi_ge_hbond = M_PI >= p.hbond_angle;
+    r->pi_ge_weak_hbond = M_PI >= p.weak_hbond_angle;
+    r->pi_in_cx = p.cx_angle_min <= M_PI && M_PI <= p.cx_angle_max;
+    r->pi_ge_xbond = M_PI >= p.xbond_angle;
+}
+
+int upload(arp_ctx* c, DBuf& b, const void* src, size_t bytes)
+{
+    ARP_TRY(dbuf_reserve(c, b, bytes));
+    if (bytes) ARP_CUDA(c, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->input_bytes += bytes;
+    return ARP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int arp_abi_version(void) { return ARP_ABI_VERSION; }
+
+int arp_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) { (void)cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return ARP_E_CUDA; }
+    return n;
+}
+
+int arp_params_default(arp_params* p)
+{
+    if (!p) return ARP_E_INVALID_ARG;
+    memset(p, 0, sizeof *p);
+    p->interacting_cutoff = 5.0;         /* process_protein_cli.py -i default */
+    p->vdw_comp = 0.1;                   /* -co default */
+    p->include_sequence_adjacent = 0;
+    p->blas_fma = 1;
+    p->h_vdw = 1.2;                      /* config.py:23-25 */
+    p->dist_max = 4.5;                   /* config.py:592-660 */
+    p->hbond_polar_dist = 3.5;
+    p->weak_polar_dist = 3.5;
+    p->ionic_dist = 4.0;
+    p->carbonyl_dist = 3.6;
+    p->aromatic_dist = 4.0;
+    p->hydrophobic_dist = 4.5;
+    p->metal_dist = 2.8;
+    p->hbond_angle = 1.57;
+    p->weak_hbond_angle = 2.27;
+    p->cx_angle_min = 0.52;
+    p->cx_angle_max = 2.62;
+    p->xbond_angle = 2.09;
+    p->ring_centroid_dist = 6.0;
+    p->atom_ring_dist = 4.5;
+    p->met_sulphur_dist = 6.0;
+    p->amide_centroid_dist = 6.0;
+    p->plane_bins_deg[0] = 30.0; p->plane_bins_deg[1] = 60.0; p->plane_bins_deg[2] = 90.0;
+    cosine_images(p);
+    return ARP_OK;
+}
+
+int arp_create(int device, arp_ctx** out)
+{
+    if (!out) return ARP_E_INVALID_ARG;
+    *out = nullptr;
+    int n = arp_device_count();
+    if (n <= 0) {
+        snprintf(g_create_err, ARP_ERRLEN, "no CUDA device available (there is no CPU fallback)");
+        return n < 0 ? ARP_E_CUDA : ARP_E_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        snprintf(g_create_err, ARP_ERRLEN, "device %d out of range (0..%d)", device, n - 1);
+        return ARP_E_INVALID_ARG;
+    }
+    arp_ctx* c = new (std::nothrow) arp_ctx();
+    if (!c) return ARP_E_OOM;
+    c->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaEventCreate(&c->ev[k]);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_meta, sizeof(RunMeta));
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        snprintf(g_create_err, ARP_ERRLEN, "%s", cudaGetErrorString(e));
+        arp_destroy(c);
+        return ARP_E_CUDA;
+    }
+    memset(c->h_meta, 0, sizeof(RunMeta));
+    memset(&c->stats, 0, sizeof c->stats);
+    arp_params_default(&c->params);
+    derive_rule_params(c->params, &c->rp);
+    c->have_params = 1;
+    *out = c;
+    return ARP_OK;
+}
+
+void arp_destroy(arp_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DBuf* bufs[] = { &c->xyz, &c->feat, &c->res_id, &c->rad_class, &c->vdw, &c->cov, &c->res_prev, &c->res_next,
+                     &c->res_flags, &c->bond_off, &c->bond_nbr, &c->h_off, &c->h_xyz, &c->xnbr, &c->struct_off,
+                     &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->out,
+                     &c->sort_tmp, &c->sort_out, &c->sort_zero, &c->sort_off, &c->within, &c->flush };
+    for (DBuf* b : bufs) dbuf_free(*b);
+    arp_planes_release(c);
+    for (int k = 0; k < 4; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    if (c->h_meta) cudaFreeHost(c->h_meta);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    (void)cudaGetLastError();
+    delete c;
+}
+
+const char* arp_last_error(arp_ctx* c) { return c ? c->err : g_create_err; }
+
+int arp_set_params(arp_ctx* c, const arp_params* p)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_REQUIRE(c, p != nullptr, ARP_E_INVALID_ARG, "params is NULL");
+    ARP_REQUIRE(c, p->interacting_cutoff >= 0.0 && p->interacting_cutoff < 1e6 && p->vdw_comp == p->vdw_comp,
+                ARP_E_INVALID_ARG, "interacting_cutoff / vdw_comp out of range");
+    c->params = *p;
+    derive_rule_params(c->params, &c->rp);
+    c->have_params = 1;
+    c->pairs_valid = 0; c->sorted_valid = 0;
+    c->ring_ring.valid = c->atom_ring.valid = c->amide_amide.valid = c->amide_ring.valid = 0;
+    return ARP_OK;
+}
+
+int arp_host_alloc(void** ptr, uint64_t bytes)
+{
+    if (!ptr) return ARP_E_INVALID_ARG;
+    cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); *ptr = nullptr; return e == cudaErrorMemoryAllocation ? ARP_E_OOM : ARP_E_CUDA; }
+    return ARP_OK;
+}
+
+int arp_host_free(void* ptr)
+{
+    if (!ptr) return ARP_OK;
+    cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return ARP_E_CUDA; }
+    return ARP_OK;
+}
+
+int arp_upload_atoms(arp_ctx* c, const arp_atoms* a)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_REQUIRE(c, a != nullptr, ARP_E_INVALID_ARG, "atoms is NULL");
+    ARP_REQUIRE(c, a->n_atoms >= 0 && a->n_residues >= 0 && a->n_rad_classes >= 0, ARP_E_INVALID_ARG, "negative size");
+    ARP_REQUIRE(c, a->n_atoms <= 500000000, ARP_E_INVALID_ARG, "more than 5e8 atoms");
+    ARP_REQUIRE(c, a->n_rad_classes <= ARPK_MAX_RAD, ARP_E_INVALID_ARG, "more than 512 radius classes");
+    const int N = a->n_atoms;
+    const int S = a->n_structures > 0 ? a->n_structures : 1;
+    ARP_REQUIRE(c, S == 1 || a->struct_off != nullptr, ARP_E_INVALID_ARG, "struct_off required for a batch");
+    if (N > 0) {
+        ARP_REQUIRE(c, a->xyz && a->feat && a->res_id && a->rad_class && a->vdw && a->cov && a->res_prev &&
+                       a->res_next && a->res_flags, ARP_E_INVALID_ARG, "a required atom array is NULL");
+        ARP_REQUIRE(c, a->n_residues > 0 && a->n_rad_classes > 0, ARP_E_INVALID_ARG, "atoms without residues or radius classes");
+    }
+    ARP_REQUIRE(c, !a->bond_off || N == 0 || a->bond_off[0] == 0, ARP_E_INVALID_ARG, "bond_off[0] != 0");
+    ARP_REQUIRE(c, !a->h_off || N == 0 || a->h_off[0] == 0, ARP_E_INVALID_ARG, "h_off[0] != 0");
+    if (a->struct_off) {
+        ARP_REQUIRE(c, a->struct_off[0] == 0 && a->struct_off[S] == N, ARP_E_INVALID_ARG, "struct_off must span the atoms");
+        for (int s = 0; s < S; ++s)
+            ARP_REQUIRE(c, a->struct_off[s] <= a->struct_off[s + 1], ARP_E_INVALID_ARG, "struct_off must ascend");
+    }
+    ARP_TRY(arp_bind(c));
+    c->have_atoms = 0; c->pairs_valid = 0; c->sorted_valid = 0;
+    c->atom_ring.valid = 0;
+    c->input_bytes = 0;
+    c->N = N; c->Rs = a->n_residues; c->K = a->n_rad_classes; c->S = S;
+    c->has_bonds = a->bond_off != nullptr;
+    c->has_h = a->h_off != nullptr;
+    c->has_xnbr = a->xnbr_xyz != nullptr;
+    c->E = (a->bond_off && N > 0) ? a->bond_off[N] : 0;
+    c->H = (a->h_off && N > 0) ? a->h_off[N] : 0;
+    ARP_REQUIRE(c, c->E >= 0 && c->H >= 0, ARP_E_INVALID_ARG, "negative CSR size");
+    ARP_REQUIRE(c, c->E == 0 || a->bond_nbr, ARP_E_INVALID_ARG, "bond_nbr is NULL");
+    ARP_REQUIRE(c, c->H == 0 || a->h_xyz, ARP_E_INVALID_ARG, "h_xyz is NULL");
+    const size_t n = (size_t)N;
+    ARP_TRY(upload(c, c->xyz, a->xyz, n * 12));
+    ARP_TRY(upload(c, c->feat, a->feat, n * 4));
+    ARP_TRY(upload(c, c->res_id, a->res_id, n * 4));
+    ARP_TRY(upload(c, c->rad_class, a->rad_class, n * 2));
+    ARP_TRY(upload(c, c->vdw, a->vdw, (size_t)c->K * 8));
+    ARP_TRY(upload(c, c->cov, a->cov, (size_t)c->K * 8));
+    ARP_TRY(upload(c, c->res_prev, a->res_prev, (size_t)c->Rs * 4));
+    ARP_TRY(upload(c, c->res_next, a->res_next, (size_t)c->Rs * 4));
+    ARP_TRY(upload(c, c->res_flags, a->res_flags, (size_t)c->Rs));
+    if (c->has_bonds) {
+        ARP_TRY(upload(c, c->bond_off, a->bond_off, (n + 1) * 4));
+        ARP_TRY(upload(c, c->bond_nbr, a->bond_nbr, (size_t)c->E * 4));
+    }
+    if (c->has_h) {
+        ARP_TRY(upload(c, c->h_off, a->h_off, (n + 1) * 4));
+        ARP_TRY(upload(c, c->h_xyz, a->h_xyz, (size_t)c->H * 24));
+    }
+    if (c->has_xnbr) ARP_TRY(upload(c, c->xnbr, a->xnbr_xyz, n * 12));
+    if (S > 1) ARP_TRY(upload(c, c->struct_off, a->struct_off, (size_t)(S + 1) * 4));
+    ARP_TRY(arp_pairs_prepare(c));
+    c->have_atoms = 1;
+    return ARP_OK;
+}
+
+static int pairs_out_reserve(arp_ctx* c, uint64_t records)
+{
+    if (records <= c->out_cap && c->out.p) return ARP_OK;
+    ARP_TRY(dbuf_reserve(c, c->out, (size_t)records * sizeof(arp_pair)));
+    c->out_cap = c->out.cap / sizeof(arp_pair);
+    return ARP_OK;
+}
+
+static void fill_stats(arp_ctx* c, int with_events)
+{
+    arp_stats& s = c->stats;
+    s.n_pairs = c->h_meta->n_pairs;
+    s.n_candidates = c->h_meta->n_candidates;
+    s.n_cells = c->h_meta->n_cells;
+    s.n_cells_nonempty = c->h_meta->n_cells_nonempty;
+    s.input_bytes = c->input_bytes;
+    s.output_bytes = s.n_pairs * sizeof(arp_pair);
+    if (with_events) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
+        s.ms_grid = a; s.ms_search = b; s.ms_classify = 0.f; s.ms_total = a + b;
+    }
+}
+
+int arp_pairs_run(arp_ctx* c, uint64_t* n_pairs)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_REQUIRE(c, c->have_atoms, ARP_E_NOT_READY, "arp_pairs_run before arp_upload_atoms");
+    ARP_TRY(arp_bind(c));
+    c->pairs_valid = 0; c->sorted_valid = 0;
+    /* first guess of the stream length; an overflowing run still counts, then is repeated once */
+    uint64_t want = c->out_cap ? c->out_cap : (uint64_t)c->N * 16 + 4096;
+    ARP_TRY(pairs_out_reserve(c, want));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        ARP_TRY(arp_pairs_enqueue(c, 1));
+        ARP_CUDA(c, cudaStreamSynchronize(c->stream));
+        uint64_t n = c->h_meta->n_pairs;
+        if (n <= c->out_cap) break;
+        ARP_REQUIRE(c, attempt == 0, ARP_E_CAPACITY, "record stream overflowed twice");
+        ARP_TRY(pairs_out_reserve(c, n + n / 16 + 1024));
+    }
+    c->n_pairs = c->h_meta->n_pairs;
+    c->pairs_valid = 1;
+    fill_stats(c, 1);
+    if (n_pairs) *n_pairs = c->n_pairs;
+    return ARP_OK;
+}
+
+int arp_pairs_fetch(arp_ctx* c, arp_pair* dst, uint64_t cap, int sorted)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_REQUIRE(c, c->pairs_valid, ARP_E_NOT_READY, "arp_pairs_fetch before arp_pairs_run");
+    ARP_REQUIRE(c, cap >= c->n_pairs, ARP_E_CAPACITY, "destination holds fewer records than the run produced");
+    if (c->n_pairs == 0) return ARP_OK;
+    ARP_REQUIRE(c, dst != nullptr, ARP_E_INVALID_ARG, "dst is NULL");
+    ARP_TRY(arp_bind(c));
+    const arp_pair* src = c->out.as<arp_pair>();
+    if (sorted) {
+        ARP_TRY(arp_pairs_sorted_build(c));
+        src = c->sort_out.as<arp_pair>();
+    }
+    ARP_CUDA(c, cudaMemcpyAsync(dst, src, (size_t)c->n_pairs * sizeof(arp_pair), cudaMemcpyDeviceToHost, c->stream));
+    ARP_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ARP_OK;
+}
+
+int arp_pairs_device_ptr(arp_ctx* c, const arp_pair** dptr)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_REQUIRE(c, dptr != nullptr, ARP_E_INVALID_ARG, "dptr is NULL");
+    ARP_REQUIRE(c, c->pairs_valid, ARP_E_NOT_READY, "no record stream yet");
+    *dptr = c->out.as<arp_pair>();
+    return ARP_OK;
+}
+
+int arp_flag_within(arp_ctx* c, double radius, uint8_t* flags_out, uint64_t cap)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_REQUIRE(c, c->have_atoms, ARP_E_NOT_READY, "arp_flag_within before arp_upload_atoms");
+    ARP_REQUIRE(c, radius >= 0.0, ARP_E_INVALID_ARG, "negative radius");
+    ARP_REQUIRE(c, cap >= (uint64_t)c->N, ARP_E_CAPACITY, "flags_out too small");
+    if (c->N == 0) return ARP_OK;
+    ARP_REQUIRE(c, flags_out != nullptr, ARP_E_INVALID_ARG, "flags_out is NULL");
+    ARP_TRY(arp_bind(c));
+    ARP_TRY(arp_flag_within_run(c, radius));
+    const uint8_t* d = c->within.as<uint8_t>() + 16 + (size_t)c->N * 4;
+    ARP_CUDA(c, cudaMemcpyAsync(flags_out, d, (size_t)c->N, cudaMemcpyDeviceToHost, c->stream));
+    ARP_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ARP_OK;
+}
+
+int arp_sync(arp_ctx* c)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_TRY(arp_bind(c));
+    ARP_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ARP_OK;
+}
+
+int arp_get_stats(arp_ctx* c, arp_stats* out)
+{
+    if (!c || !out) return ARP_E_INVALID_ARG;
+    *out = c->stats;
+    return ARP_OK;
+}
+
+uint64_t arp_launch_count(arp_ctx* c) { return c ? c->launches : 0; }
+
+/*
+ * Benchmark hook: repeats the whole atom-atom job (memset + grid build + pair kernel) `iters`
+ * times on the resident inputs.  Every iteration is bracketed by CUDA events on the context's
+ * stream; with flush_l2 a buffer larger than L2 is overwritten between iterations, outside the
+ * brackets.  *ms_per_iter = mean whole-job time; arp_get_stats then reports the mean grid-build
+ * and pair-kernel times of the same iterations.
+ */
+int arp_timing_iters(arp_ctx* c, int iters, int flush_l2, float* ms_per_iter)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_REQUIRE(c, c->have_atoms, ARP_E_NOT_READY, "arp_timing_iters before arp_upload_atoms");
+    ARP_REQUIRE(c, iters > 0, ARP_E_INVALID_ARG, "iters must be positive");
+    ARP_TRY(arp_bind(c));
+    if (!c->pairs_valid) ARP_TRY(arp_pairs_run(c, nullptr));      /* sizes the record buffer */
+    const size_t flush_bytes = (size_t)384 << 20;
+    if (flush_l2) ARP_TRY(dbuf_reserve(c, c->flush, flush_bytes));
+    double tot = 0.0, grid = 0.0, search = 0.0;
+    for (int it = 0; it < iters; ++it) {
+        if (flush_l2) ARP_CUDA(c, cudaMemsetAsync(c->flush.p, it & 0xff, flush_bytes, c->stream));
+        ARP_TRY(arp_pairs_enqueue(c, 1));
+        ARP_CUDA(c, cudaStreamSynchronize(c->stream));
+        ARP_REQUIRE(c, c->h_meta->n_pairs == c->n_pairs, ARP_E_CUDA, "record count changed between iterations");
+        float a = 0.f, b = 0.f;
+        ARP_CUDA(c, cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
+        ARP_CUDA(c, cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
+        grid += a; search += b; tot += a + b;
+    }
+    fill_stats(c, 0);
+    c->stats.ms_grid = (float)(grid / iters);
+    c->stats.ms_search = (float)(search / iters);
+    c->stats.ms_classify = 0.f;
+    c->stats.ms_total = (float)(tot / iters);
+    c->sorted_valid = 0;
+    if (ms_per_iter) *ms_per_iter = (float)(tot / iters);
+    return ARP_OK;
+}
+
+}  /* extern "C" */

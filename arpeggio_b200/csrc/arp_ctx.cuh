@@ -1,0 +1,191 @@
+/*
+ * arp_ctx.cuh -- context object, device buffers and error plumbing shared by the
+ * translation units of libarpeggio_cuda.so (not part of the public ABI).
+ */
+#ifndef ARP_CTX_CUH
+#define ARP_CTX_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/arpeggio_cuda.h"
+#include "arp_rules.cuh"
+
+#define ARP_ERRLEN 512
+
+/* growable device allocation */
+struct DBuf {
+    void*  p = nullptr;
+    size_t cap = 0;
+    template <class T> T* as() const { return (T*)p; }
+};
+
+/* per-structure cell grid (device) */
+struct StructGeom {
+    double ox, oy, oz;      /* origin = bounding-box minimum */
+    double inv_w;           /* 1 / cell edge; edge >= cutoff * 1.0001 */
+    int    dx, dy, dz;      /* cells per axis */
+    int    ncell;           /* dx * dy * dz (0 for an empty structure) */
+    int    cell_base;       /* global id of cell (0,0,0) */
+    float  r2_lo, r2_hi;    /* float32 d^2 at or below r2_lo is certainly within the cutoff,
+                               above r2_hi certainly outside; in between the exact double
+                               test of Bio.PDB.kdtrees decides */
+    int    pad;
+};
+
+/* counters the kernels leave behind (device, copied to pinned host memory after a run) */
+struct RunMeta {
+    unsigned long long n_pairs;       /* record cursor: total records the run produced */
+    unsigned long long n_candidates;  /* distance tests performed */
+    unsigned int n_cells;
+    unsigned int n_cells_nonempty;
+    unsigned int ticket[4];           /* dynamic tile ids: [0] cell scan, [1] pair kernel, [2] sort scan */
+    unsigned int fault;               /* sticky device-side diagnostics */
+    unsigned int pad[5];
+};
+
+struct PlaneSet {
+    int n = 0, is_f32 = 0;
+    DBuf center, normal, res_id, flags;
+};
+
+struct PlaneResult {
+    DBuf rec;              /* arp_plane_pair / arp_atom_plane records, sorted */
+    DBuf tmp;              /* unsorted stream */
+    DBuf cnt;              /* record cursor (device) */
+    uint64_t n = 0;
+    uint64_t cap = 0;
+    int valid = 0;
+};
+
+struct arp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    char err[ARP_ERRLEN] = {0};
+    int sm_count = 148;
+
+    arp_params params;
+    ArpRuleParams rp;
+    int have_params = 0;
+
+    /* uploaded atoms (original order) */
+    int N = 0, Rs = 0, K = 0, S = 1, E = 0, H = 0;
+    int have_atoms = 0;
+    DBuf xyz, feat, res_id, rad_class, vdw, cov, res_prev, res_next, res_flags;
+    DBuf bond_off, bond_nbr, h_off, h_xyz, xnbr, struct_off;
+    int has_bonds = 0, has_h = 0, has_xnbr = 0;
+    uint64_t input_bytes = 0;
+
+    /* cell grid + cell-sorted atom records */
+    DBuf zero;                    /* one memset per run: RunMeta | bbox | cell_cnt | scan_state */
+    size_t zero_bytes = 0, off_bbox = 0, off_cnt = 0, off_state = 0;
+    size_t cell_bound = 0;        /* upper bound of the number of cells, all structures */
+    DBuf geom, cell_start, cell_of, rank, pos4, att4;
+    RunMeta* h_meta = nullptr;    /* pinned */
+
+    /* output stream */
+    DBuf out;                     /* arp_pair records */
+    uint64_t out_cap = 0;         /* records */
+    uint64_t n_pairs = 0;
+    int pairs_valid = 0;
+    DBuf sort_tmp, sort_out, sort_zero, sort_off;
+    int sorted_valid = 0;
+
+    /* planes */
+    PlaneSet rings, amides;
+    int have_planes = 0;
+    PlaneResult ring_ring, atom_ring, amide_amide, amide_ring;
+
+    /* binding-site flags */
+    DBuf within;
+
+    /* timing */
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    arp_stats stats;
+    DBuf flush;                   /* L2 flush buffer for arp_timing_iters */
+    unsigned long long launches = 0;   /* kernels launched by this context so far */
+};
+
+static inline int arp_fail(arp_ctx* c, int code, const char* what, const char* file, int line)
+{
+    if (c) snprintf(c->err, ARP_ERRLEN, "%s (%s:%d)", what, file, line);
+    return code;
+}
+
+#define ARP_CUDA(c, call)                                                                   \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            (void)cudaGetLastError();                                                       \
+            return arp_fail((c), e_ == cudaErrorMemoryAllocation ? ARP_E_OOM : ARP_E_CUDA,  \
+                            cudaGetErrorString(e_), __FILE__, __LINE__);                    \
+        }                                                                                   \
+    } while (0)
+
+#define ARP_TRY(expr)                     \
+    do {                                  \
+        int rc_ = (expr);                 \
+        if (rc_ != ARP_OK) return rc_;    \
+    } while (0)
+
+#define ARP_REQUIRE(c, cond, code, msg)                                   \
+    do {                                                                  \
+        if (!(cond)) return arp_fail((c), (code), (msg), __FILE__, __LINE__); \
+    } while (0)
+
+/* kernel launch check: configuration errors surface here, execution errors at the next sync */
+#define ARP_LAUNCHED(c)                                                   \
+    do {                                                                  \
+        (c)->launches++;                                                  \
+        ARP_CUDA((c), cudaGetLastError());                                \
+    } while (0)
+
+static inline int dbuf_reserve(arp_ctx* c, DBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap && b.p) return ARP_OK;
+    if (bytes == 0) bytes = 16;
+    size_t want = bytes + bytes / 8 + 256;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        e = cudaMalloc(&b.p, bytes);
+        want = bytes;
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            b.p = nullptr;
+            return arp_fail(c, ARP_E_OOM, "device allocation failed", __FILE__, __LINE__);
+        }
+    }
+    b.cap = want;
+    return ARP_OK;
+}
+
+static inline void dbuf_free(DBuf& b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+}
+
+static inline int arp_bind(arp_ctx* c)
+{
+    ARP_CUDA(c, cudaSetDevice(c->device));
+    return ARP_OK;
+}
+
+/* entry points implemented across translation units */
+int  arp_pairs_prepare(arp_ctx* c);                       /* arp_pairs.cu: size the grid buffers after an upload */
+int  arp_pairs_enqueue(arp_ctx* c, int with_events);      /* arp_pairs.cu: memset + grid build + pair kernel */
+int  arp_pairs_sorted_build(arp_ctx* c);                  /* arp_pairs.cu: (i, j)-ascending copy of the stream */
+int  arp_flag_within_run(arp_ctx* c, double radius);      /* arp_pairs.cu */
+void arp_planes_release(arp_ctx* c);                      /* arp_planes.cu */
+
+/* exclusive scan of n ints (n read from *n_dev + n_add when n_dev != null), single pass;
+   state must hold one zeroed 64-bit word per tile of ARP_SCAN_TILE items */
+#define ARP_SCAN_TILE 2048
+int  arp_scan_exclusive(arp_ctx* c, const int* in, int* out, unsigned long long* state, unsigned int* ticket,
+                        const unsigned int* n_dev, int n_add, size_t n_bound);
+
+#endif /* ARP_CTX_CUH */

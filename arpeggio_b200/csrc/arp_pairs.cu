@@ -1,0 +1,680 @@
+/*
+ * arp_pairs.cu -- atom-atom contacts on the GPU (sm_100a).
+ *
+ * Replaces, for one `selection_plus` atom list (or a batch of independent lists):
+ *   Bio.PDB.NeighborSearch(selection_plus).search_all(cutoff)   interactions.py:1442, :707
+ *   InteractionComplex._calculate_atom_contacts                 interactions.py:693-936
+ *
+ * Pipeline of one run (all on the context's stream, no host round trip):
+ *   memset     one zero region: counters | bounding boxes | cell counts | scan state
+ *   k_bbox     per-structure bounding box (ordered-int atomics)
+ *   k_geom     per-structure cell grid (edge >= cutoff), global cell numbering, prefilter band
+ *   k_cellid   cell of every atom + rank inside the cell
+ *   k_scan     exclusive scan of the cell counts (single pass, decoupled look-back)
+ *   k_scatter  atoms into cell order as two 16-byte records: pos4 (x, y, z, original index)
+ *              and att4 (packed feature word, residue, residue's prev/next link)
+ *   k_pairs    one warp per home cell (dynamic tickets): the 13 forward neighbour cells + the
+ *              home cell are 5 contiguous runs of the cell-sorted array; lane = candidate,
+ *              home atoms broadcast; float32 prefilter, exact double test inside the band;
+ *              filters; ballot compaction into a per-warp shared-memory queue; every 128
+ *              queued hits the warp classifies 32 hits per round (fused distance + angle +
+ *              bitmask rules, arp_rules.cuh) and stores 16-byte records coalesced behind one
+ *              cursor atomic.
+ */
+#include "arp_ctx.cuh"
+
+#define FULL 0xffffffffu
+
+/* ---- ordered-int encoding of float32 for atomic min/max ------------------------------ */
+__device__ __forceinline__ unsigned f2ord(float f)
+{
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+/* structure of atom i (struct_off ascending, S >= 1); null struct_off = one structure */
+__device__ __forceinline__ int struct_of(const int* __restrict__ struct_off, int S, int i)
+{
+    if (!struct_off || S == 1) return 0;
+    int lo = 0, hi = S;            /* invariant: struct_off[lo] <= i < struct_off[hi] */
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (struct_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+/* ---- k_bbox --------------------------------------------------------------------------
+ * bbox[s][0..2] = max over atoms of ~ord(coord)  (i.e. the minimum), [3..5] = max of ord(coord).
+ * Zero-initialised, so a structure without atoms keeps all zeros.                        */
+__global__ void __launch_bounds__(256) k_bbox(const float* __restrict__ xyz, const int* __restrict__ struct_off,
+                                              int S, int N, unsigned* __restrict__ bbox)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = i < N;
+    int s = -1;
+    unsigned v[6] = {0, 0, 0, 0, 0, 0};
+    if (live) {
+        s = struct_of(struct_off, S, i);
+        for (int k = 0; k < 3; ++k) {
+            unsigned o = f2ord(xyz[3 * (size_t)i + k]);
+            v[k] = ~o; v[3 + k] = o;
+        }
+    }
+    /* warp-uniform structure: reduce in the warp, one lane commits */
+    int s0 = __shfl_sync(FULL, s, 0);
+    bool uniform = __all_sync(FULL, s == s0 || !live);
+    if (uniform) {
+        s0 = __reduce_max_sync(FULL, s);
+        if (s0 < 0) return;
+        for (int k = 0; k < 6; ++k) {
+            unsigned m = __reduce_max_sync(FULL, v[k]);
+            if ((threadIdx.x & 31) == 0) atomicMax(&bbox[6 * (size_t)s0 + k], m);
+        }
+    } else if (live) {
+        for (int k = 0; k < 6; ++k) atomicMax(&bbox[6 * (size_t)s + k], v[k]);
+    }
+}
+
+/* ---- k_geom: one block ------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256) k_geom(const unsigned* __restrict__ bbox, const int* __restrict__ struct_off,
+                                              int S, int N, double cutoff, StructGeom* __restrict__ geom,
+                                              RunMeta* __restrict__ meta)
+{
+    __shared__ int s_sum[256];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int s0 = 0; s0 < S; s0 += blockDim.x) {
+        int s = s0 + threadIdx.x;
+        StructGeom g;
+        memset(&g, 0, sizeof g);
+        int ncell = 0;
+        if (s < S) {
+            int lo = struct_off ? struct_off[s] : 0, hi = struct_off ? struct_off[s + 1] : N;
+            int n = hi - lo;
+            if (n > 0) {
+                double mn[3], mx[3], amax = 0.0;
+                bool finite = true;
+                for (int k = 0; k < 3; ++k) {
+                    mn[k] = (double)ord2f(~bbox[6 * (size_t)s + k]);
+                    mx[k] = (double)ord2f(bbox[6 * (size_t)s + 3 + k]);
+                    if (!(fabs(mn[k]) <= 3.0e38) || !(fabs(mx[k]) <= 3.0e38)) finite = false;
+                    amax = fmax(amax, fmax(fabs(mn[k]), fabs(mx[k])));
+                }
+                if (!finite) {           /* NaN / Inf coordinates: one cell, every test exact */
+                    for (int k = 0; k < 3; ++k) { mn[k] = 0.0; mx[k] = 0.0; }
+                    atomicOr(&meta->fault, 1u);
+                }
+                double r = cutoff;
+                double w = r > 1e-3 ? r * 1.0001 + 1e-4 : 1e-3;
+                long long d[3];
+                for (;;) {
+                    for (int k = 0; k < 3; ++k) d[k] = (long long)floor((mx[k] - mn[k]) / w) + 1;
+                    /* at most 4 n + 64 cells per structure (host sizes the tables on that bound) */
+                    if ((double)d[0] * (double)d[1] * (double)d[2] <= 4.0 * (double)n + 64.0) break;
+                    w *= 1.5;
+                }
+                g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2];
+                g.inv_w = 1.0 / w;
+                g.dx = (int)d[0]; g.dy = (int)d[1]; g.dz = (int)d[2];
+                ncell = g.dx * g.dy * g.dz;
+                g.ncell = ncell;
+                /* float32 prefilter band around r^2: u bounds one ulp of any coordinate */
+                double u = amax * 1.1920928955078125e-07;
+                double r2 = r * r;
+                double band = 4.0 * r * u + 4.0 * u * u + r2 * 1.9073486328125e-06;
+                double lo2 = r2 - band, hi2 = r2 + band;
+                g.r2_lo = finite ? __double2float_rd(lo2) : -1.0f;
+                g.r2_hi = finite ? __double2float_ru(hi2) : 3.4e38f;
+                if (!(lo2 > 0.0)) g.r2_lo = -1.0f;
+            }
+        }
+        /* block exclusive scan of ncell */
+        s_sum[threadIdx.x] = ncell;
+        __syncthreads();
+        for (int off = 1; off < blockDim.x; off <<= 1) {
+            int t = threadIdx.x >= off ? s_sum[threadIdx.x - off] : 0;
+            __syncthreads();
+            s_sum[threadIdx.x] += t;
+            __syncthreads();
+        }
+        int incl = s_sum[threadIdx.x];
+        int carry = s_carry;
+        if (s < S) {
+            g.cell_base = carry + incl - ncell;
+            geom[s] = g;
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = carry + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) meta->n_cells = (unsigned)s_carry;
+}
+
+__device__ __forceinline__ int cell_coord(double v, double o, double inv_w, int dim)
+{
+    double t = floor((v - o) * inv_w);
+    t = fmin(fmax(t, 0.0), (double)(dim - 1));     /* NaN -> 0 */
+    return (int)t;
+}
+
+/* ---- k_cellid ------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256) k_cellid(const float* __restrict__ xyz, const int* __restrict__ struct_off,
+                                                int S, int N, const StructGeom* __restrict__ geom,
+                                                int* __restrict__ cell_cnt, int* __restrict__ cell_of,
+                                                int* __restrict__ rank)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int s = struct_of(struct_off, S, i);
+    const StructGeom* g = geom + s;
+    int cx = cell_coord((double)xyz[3 * (size_t)i + 0], g->ox, g->inv_w, g->dx);
+    int cy = cell_coord((double)xyz[3 * (size_t)i + 1], g->oy, g->inv_w, g->dy);
+    int cz = cell_coord((double)xyz[3 * (size_t)i + 2], g->oz, g->inv_w, g->dz);
+    int c = g->cell_base + (cz * g->dy + cy) * g->dx + cx;
+    cell_of[i] = c;
+    rank[i] = atomicAdd(&cell_cnt[c], 1);
+}
+
+/* ---- k_scan: single-pass exclusive scan (decoupled look-back) -------------------------- */
+#define SCAN_THREADS 256
+#define SCAN_ITEMS   (ARP_SCAN_TILE / SCAN_THREADS)
+#define ST_AGG  (1ull << 62)
+#define ST_INCL (2ull << 62)
+#define ST_MASK (3ull << 62)
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(const int* __restrict__ in, int* __restrict__ out,
+                                                       unsigned long long* state, unsigned int* ticket,
+                                                       const unsigned int* n_dev, int n_add)
+{
+    __shared__ int s_tile;
+    __shared__ int s_warp[SCAN_THREADS / 32];
+    __shared__ int s_prefix;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    const long long n = (long long)(n_dev ? *n_dev : 0u) + n_add;
+    const long long base = (long long)tile * ARP_SCAN_TILE;
+    if (base >= n) return;
+    const long long first = base + (long long)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (first + k < n) ? in[first + k] : 0;
+        sum += v[k];
+    }
+    /* block scan of the thread sums */
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int t = __shfl_up_sync(FULL, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < SCAN_THREADS / 32 ? s_warp[lane] : 0;
+#pragma unroll
+        for (int off = 1; off < SCAN_THREADS / 32; off <<= 1) {
+            int t = __shfl_up_sync(FULL, w, off);
+            if (lane >= off) w += t;
+        }
+        if (lane < SCAN_THREADS / 32) s_warp[lane] = w;       /* inclusive warp totals */
+    }
+    __syncthreads();
+    const int warp_excl = warp ? s_warp[warp - 1] : 0;
+    const int tile_total = s_warp[SCAN_THREADS / 32 - 1];
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* st = state;
+        int prefix = 0;
+        if (tile == 0) {
+            st[0] = ST_INCL | (unsigned long long)(unsigned)tile_total;
+        } else {
+            st[tile] = ST_AGG | (unsigned long long)(unsigned)tile_total;
+            int p = tile - 1;
+            for (;;) {
+                unsigned long long w = st[p];
+                unsigned long long f = w & ST_MASK;
+                if (f == 0) continue;                      /* predecessor not published yet */
+                prefix += (int)(unsigned)(w & 0xffffffffull);
+                if (f == ST_INCL) break;
+                --p;
+            }
+            st[tile] = ST_INCL | (unsigned long long)(unsigned)(prefix + tile_total);
+        }
+        s_prefix = prefix;
+    }
+    __syncthreads();
+    int run = s_prefix + warp_excl + incl - sum;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (first + k < n) out[first + k] = run;
+        run += v[k];
+    }
+}
+
+int arp_scan_exclusive(arp_ctx* c, const int* in, int* out, unsigned long long* state, unsigned int* ticket,
+                       const unsigned int* n_dev, int n_add, size_t n_bound)
+{
+    size_t tiles = (n_bound + ARP_SCAN_TILE - 1) / ARP_SCAN_TILE;
+    if (tiles == 0) tiles = 1;
+    k_scan<<<(unsigned)tiles, SCAN_THREADS, 0, c->stream>>>(in, out, state, ticket, n_dev, n_add);
+    ARP_LAUNCHED(c);
+    return ARP_OK;
+}
+
+/* ---- k_scatter ------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256) k_scatter(int N, const float* __restrict__ xyz, const uint32_t* __restrict__ feat,
+                                                 const int32_t* __restrict__ res_id, const uint16_t* __restrict__ rad_class,
+                                                 const int32_t* __restrict__ res_prev, const int32_t* __restrict__ res_next,
+                                                 const uint8_t* __restrict__ res_flags, const int32_t* __restrict__ bond_off,
+                                                 const int* __restrict__ cell_of, const int* __restrict__ rank,
+                                                 const int* __restrict__ cell_start,
+                                                 float4* __restrict__ pos4, uint4* __restrict__ att4)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int dst = cell_start[cell_of[i]] + rank[i];
+    int r = res_id[i];
+    uint32_t w = (feat[i] & 0xFFFFFu) | ((uint32_t)(res_flags[r] & 3u) << ARPK_RES_SHIFT) |
+                 ((uint32_t)rad_class[i] << ARPK_RAD_SHIFT);
+    if (bond_off && bond_off[i + 1] > bond_off[i]) w |= ARPK_HAS_BOND;
+    pos4[dst] = make_float4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], __int_as_float(i));
+    att4[dst] = make_uint4(w, (uint32_t)r, (uint32_t)res_prev[r], (uint32_t)res_next[r]);
+}
+
+/* ---- k_pairs ---------------------------------------------------------------------------------- */
+#define PAIR_WARPS   8
+#define PAIR_SLOTS   4                      /* candidates held per lane */
+#define PAIR_CHUNK   (32 * PAIR_SLOTS)
+#define PAIR_QCAP    256                    /* ring capacity per warp (power of two) */
+#define PAIR_DRAIN   128
+#define PAIR_CELLS_PER_TICKET 4
+
+struct PairArgs {
+    const float4* pos4;
+    const uint4*  att4;
+    const int*    cell_start;
+    const StructGeom* geom;
+    RunMeta*      meta;
+    arp_pair*     out;
+    unsigned long long out_cap;
+    ArpSide       side;
+};
+
+__device__ __forceinline__ void pairs_drain(const PairArgs& A, const ArpRuleParams& P, const uint2* q,
+                                            unsigned head, unsigned n, int lane)
+{
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&A.meta->n_pairs, (unsigned long long)n);
+    base = __shfl_sync(FULL, base, 0);
+    for (unsigned r = 0; r < n; r += 32) {
+        unsigned idx = r + lane;
+        if (idx < n) {
+            uint2 e = q[(head + idx) & (PAIR_QCAP - 1)];
+            float4 pb = A.pos4[e.x], pe = A.pos4[e.y];
+            uint32_t fb = A.att4[e.x].x, fe = A.att4[e.y].x;
+            uint32_t mask; float dist;
+            int ib = __float_as_int(pb.w), ie = __float_as_int(pe.w);
+            rule_classify(A.side, P, ib, ie, pb.x, pb.y, pb.z, pe.x, pe.y, pe.z, fb, fe, &mask, &dist);
+            unsigned long long o = base + idx;
+            if (o < A.out_cap) {
+                int4 rec = make_int4(ib, ie, (int)mask, __float_as_int(dist));
+                reinterpret_cast<int4*>(A.out)[o] = rec;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(PAIR_WARPS * 32, 2) k_pairs(PairArgs A, ArpRuleParams P)
+{
+    __shared__ uint2 s_queue[PAIR_WARPS][PAIR_QCAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint2* q = s_queue[warp];
+    unsigned qhead = 0, qcount = 0;
+    unsigned ncand = 0;
+    unsigned long long ncand_total = 0;
+    unsigned nonempty = 0;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    const int n_cells = (int)A.meta->n_cells;
+    int s = 0;
+    StructGeom G = A.geom[0];
+    int s_end = G.cell_base + G.ncell;
+
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = (int)atomicAdd(&A.meta->ticket[1], 1u);
+        t = __shfl_sync(FULL, t, 0);
+        long long c0l = (long long)t * PAIR_CELLS_PER_TICKET;
+        if (c0l >= n_cells) break;
+        int c0 = (int)c0l;
+        int c1 = min(c0 + PAIR_CELLS_PER_TICKET, n_cells);
+        for (int c = c0; c < c1; ++c) {
+            const int hb = A.cell_start[c];
+            const int nh = A.cell_start[c + 1] - hb;
+            if (nh == 0) continue;
+            ++nonempty;
+            while (c >= s_end) { ++s; G = A.geom[s]; s_end = G.cell_base + G.ncell; }
+            /* the five runs of the half stencil, lanes 0..4 */
+            const int lc = c - G.cell_base;
+            const int cx = lc % G.dx, t2 = lc / G.dx, cy = t2 % G.dy, cz = t2 / G.dy;
+            int rbeg = 0, rlen = 0;
+            if (lane < 5) {
+                int y = cy + (lane == 1 || lane == 4 ? 1 : (lane == 2 ? -1 : 0));
+                int z = cz + (lane >= 2 ? 1 : 0);
+                int x0 = lane == 0 ? cx : max(cx - 1, 0);
+                int x1 = min(cx + 1, G.dx - 1);
+                if (y >= 0 && y < G.dy && z < G.dz) {
+                    int row = G.cell_base + (z * G.dy + y) * G.dx;
+                    rbeg = A.cell_start[row + x0];
+                    rlen = A.cell_start[row + x1 + 1] - rbeg;
+                }
+            }
+            const int b0 = __shfl_sync(FULL, rbeg, 0), b1 = __shfl_sync(FULL, rbeg, 1), b2 = __shfl_sync(FULL, rbeg, 2),
+                      b3 = __shfl_sync(FULL, rbeg, 3), b4 = __shfl_sync(FULL, rbeg, 4);
+            const int p1 = __shfl_sync(FULL, rlen, 0);
+            const int p2 = p1 + __shfl_sync(FULL, rlen, 1);
+            const int p3 = p2 + __shfl_sync(FULL, rlen, 2);
+            const int p4 = p3 + __shfl_sync(FULL, rlen, 3);
+            const int total = p4 + __shfl_sync(FULL, rlen, 4);
+
+            for (int k0 = 0; k0 < total; k0 += PAIR_CHUNK) {
+                float cxs[PAIR_SLOTS], cys[PAIR_SLOTS], czs[PAIR_SLOTS];
+                int   cor[PAIR_SLOTS], cg[PAIR_SLOTS];
+                uint4 cat[PAIR_SLOTS];
+#pragma unroll
+                for (int sl = 0; sl < PAIR_SLOTS; ++sl) {
+                    int k = k0 + sl * 32 + lane;
+                    cg[sl] = -1;
+                    if (k < total) {
+                        int g = k < p1 ? b0 + k : k < p2 ? b1 + (k - p1) : k < p3 ? b2 + (k - p2)
+                              : k < p4 ? b3 + (k - p3) : b4 + (k - p4);
+                        float4 p = A.pos4[g];
+                        cxs[sl] = p.x; cys[sl] = p.y; czs[sl] = p.z; cor[sl] = __float_as_int(p.w);
+                        cat[sl] = A.att4[g];
+                        cg[sl] = g;
+                    } else {
+                        cxs[sl] = cys[sl] = czs[sl] = 0.f; cor[sl] = 0; cat[sl] = make_uint4(0, 0, 0, 0);
+                    }
+                }
+                /* home atoms that still have candidates in this chunk: k > h */
+                const int h_end = min(nh, k0 + PAIR_CHUNK - 1);
+                for (int h = 0; h < h_end; ++h) {
+                    const float4 hp = A.pos4[hb + h];
+                    const uint4  ha = A.att4[hb + h];
+                    const int    ho = __float_as_int(hp.w);
+#pragma unroll
+                    for (int sl = 0; sl < PAIR_SLOTS; ++sl) {
+                        const int k = k0 + sl * 32 + lane;
+                        if (k0 + sl * 32 >= total) break;                 /* warp-uniform */
+                        const bool ok = cg[sl] >= 0 && k > h;
+                        const float ddx = hp.x - cxs[sl], ddy = hp.y - cys[sl], ddz = hp.z - czs[sl];
+                        const float d2 = __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, __fmul_rn(ddx, ddx)));
+                        bool hit = ok && (d2 <= G.r2_hi);
+                        ncand += ok ? 1u : 0u;
+                        if (hit) {
+                            if (d2 > G.r2_lo) hit = kd_within(hp.x, hp.y, hp.z, cxs[sl], cys[sl], czs[sl], P.r2);
+                            if (hit) {
+                                const bool h_first = ho < cor[sl];        /* atom_bgn = lower list index */
+                                const uint4 ab = h_first ? ha : cat[sl];
+                                const uint4 ae = h_first ? cat[sl] : ha;
+                                hit = rule_pair_survives(ab.x, (int)ab.y, (int)ab.z, (int)ab.w,
+                                                         ae.x, (int)ae.y, (int)ae.z, (int)ae.w, P.include_seq_adjacent);
+                            }
+                        }
+                        const unsigned m = __ballot_sync(FULL, hit);
+                        if (m) {
+                            if (hit) {
+                                const bool h_first = ho < cor[sl];
+                                const unsigned pos = (qhead + qcount + __popc(m & lt_mask)) & (PAIR_QCAP - 1);
+                                q[pos] = h_first ? make_uint2((unsigned)(hb + h), (unsigned)cg[sl])
+                                                 : make_uint2((unsigned)cg[sl], (unsigned)(hb + h));
+                            }
+                            qcount += __popc(m);
+                        }
+                    }
+                    if (qcount >= PAIR_DRAIN) {
+                        __syncwarp();
+                        pairs_drain(A, P, q, qhead, PAIR_DRAIN, lane);
+                        qhead = (qhead + PAIR_DRAIN) & (PAIR_QCAP - 1);
+                        qcount -= PAIR_DRAIN;
+                    }
+                }
+            }
+        }
+        ncand_total += ncand; ncand = 0;
+    }
+    if (qcount) {
+        __syncwarp();
+        pairs_drain(A, P, q, qhead, qcount, lane);
+    }
+    /* statistics */
+    for (int off = 16; off; off >>= 1) ncand_total += __shfl_xor_sync(FULL, ncand_total, off);
+    if (lane == 0) {
+        if (ncand_total) atomicAdd(&A.meta->n_candidates, ncand_total);
+        if (nonempty) atomicAdd(&A.meta->n_cells_nonempty, nonempty);
+    }
+}
+
+/* ---- host side ------------------------------------------------------------------------------- */
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int arp_pairs_prepare(arp_ctx* c)
+{
+    const size_t N = (size_t)c->N, S = (size_t)c->S;
+    c->cell_bound = 4 * N + 64 * S;
+    size_t tiles = (c->cell_bound + 1 + ARP_SCAN_TILE - 1) / ARP_SCAN_TILE + 1;
+    c->off_bbox = align_up(sizeof(RunMeta), 256);
+    c->off_cnt = align_up(c->off_bbox + 6 * sizeof(unsigned) * S, 256);
+    c->off_state = align_up(c->off_cnt + sizeof(int) * (c->cell_bound + 2), 256);
+    c->zero_bytes = c->off_state + tiles * sizeof(unsigned long long);
+    ARP_TRY(dbuf_reserve(c, c->zero, c->zero_bytes));
+    ARP_TRY(dbuf_reserve(c, c->geom, sizeof(StructGeom) * S));
+    ARP_TRY(dbuf_reserve(c, c->cell_start, sizeof(int) * (c->cell_bound + 2)));
+    ARP_TRY(dbuf_reserve(c, c->cell_of, sizeof(int) * N));
+    ARP_TRY(dbuf_reserve(c, c->rank, sizeof(int) * N));
+    ARP_TRY(dbuf_reserve(c, c->pos4, sizeof(float4) * N));
+    ARP_TRY(dbuf_reserve(c, c->att4, sizeof(uint4) * N));
+    return ARP_OK;
+}
+
+int arp_pairs_enqueue(arp_ctx* c, int with_events)
+{
+    const int N = c->N, S = c->S;
+    char* z = c->zero.as<char>();
+    RunMeta* meta = (RunMeta*)z;
+    unsigned* bbox = (unsigned*)(z + c->off_bbox);
+    int* cell_cnt = (int*)(z + c->off_cnt);
+    unsigned long long* state = (unsigned long long*)(z + c->off_state);
+    const int* so = S > 1 ? c->struct_off.as<int>() : nullptr;
+    cudaStream_t st = c->stream;
+
+    if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[0], st));
+    ARP_CUDA(c, cudaMemsetAsync(z, 0, c->zero_bytes, st));
+    if (N > 0) {
+        unsigned blocks = (unsigned)((N + 255) / 256);
+        k_bbox<<<blocks, 256, 0, st>>>(c->xyz.as<float>(), so, S, N, bbox);
+        ARP_LAUNCHED(c);
+        k_geom<<<1, 256, 0, st>>>(bbox, so, S, N, c->params.interacting_cutoff, c->geom.as<StructGeom>(), meta);
+        ARP_LAUNCHED(c);
+        k_cellid<<<blocks, 256, 0, st>>>(c->xyz.as<float>(), so, S, N, c->geom.as<StructGeom>(), cell_cnt,
+                                         c->cell_of.as<int>(), c->rank.as<int>());
+        ARP_LAUNCHED(c);
+        ARP_TRY(arp_scan_exclusive(c, cell_cnt, c->cell_start.as<int>(), state, &meta->ticket[0], &meta->n_cells, 1,
+                                   c->cell_bound + 1));
+        k_scatter<<<blocks, 256, 0, st>>>(N, c->xyz.as<float>(), c->feat.as<uint32_t>(), c->res_id.as<int32_t>(),
+                                          c->rad_class.as<uint16_t>(), c->res_prev.as<int32_t>(), c->res_next.as<int32_t>(),
+                                          c->res_flags.as<uint8_t>(), c->has_bonds ? c->bond_off.as<int32_t>() : nullptr,
+                                          c->cell_of.as<int>(), c->rank.as<int>(), c->cell_start.as<int>(),
+                                          c->pos4.as<float4>(), c->att4.as<uint4>());
+        ARP_LAUNCHED(c);
+    }
+    if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[1], st));
+    if (N > 0) {
+        PairArgs A;
+        A.pos4 = c->pos4.as<float4>(); A.att4 = c->att4.as<uint4>(); A.cell_start = c->cell_start.as<int>();
+        A.geom = c->geom.as<StructGeom>(); A.meta = meta; A.out = c->out.as<arp_pair>(); A.out_cap = c->out_cap;
+        A.side.vdw = c->vdw.as<double>(); A.side.cov = c->cov.as<double>();
+        A.side.bond_off = c->has_bonds ? c->bond_off.as<int32_t>() : nullptr;
+        A.side.bond_nbr = c->has_bonds ? c->bond_nbr.as<int32_t>() : nullptr;
+        A.side.h_off = c->has_h ? c->h_off.as<int32_t>() : nullptr;
+        A.side.h_xyz = c->has_h ? c->h_xyz.as<double>() : nullptr;
+        A.side.xnbr = c->has_xnbr ? c->xnbr.as<float>() : nullptr;
+        unsigned grid = (unsigned)(c->sm_count * 2);
+        size_t want = ((size_t)N / 24) / PAIR_WARPS + 1;       /* about one warp per few cells on small inputs */
+        if (want < grid) grid = (unsigned)want;
+        k_pairs<<<grid, PAIR_WARPS * 32, 0, st>>>(A, c->rp);
+        ARP_LAUNCHED(c);
+    }
+    if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[2], st));
+    ARP_CUDA(c, cudaMemcpyAsync(c->h_meta, meta, sizeof(RunMeta), cudaMemcpyDeviceToHost, st));
+    return ARP_OK;
+}
+
+/* ---- canonical (i, j) order of the record stream ----------------------------------------- */
+__global__ void __launch_bounds__(256) k_sort_count(const arp_pair* __restrict__ rec, unsigned long long n,
+                                                    int* __restrict__ cnt)
+{
+    unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) atomicAdd(&cnt[rec[r].i], 1);
+}
+
+__global__ void __launch_bounds__(256) k_sort_scatter(const arp_pair* __restrict__ rec, unsigned long long n,
+                                                      const int* __restrict__ off, int* __restrict__ cur,
+                                                      arp_pair* __restrict__ tmp)
+{
+    unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int4 v = reinterpret_cast<const int4*>(rec)[r];
+    int pos = off[v.x] + atomicAdd(&cur[v.x], 1);
+    reinterpret_cast<int4*>(tmp)[pos] = v;
+}
+
+/* records of one i are contiguous in tmp; (i, j) is unique, so the rank of j inside the segment
+   is the final position */
+__global__ void __launch_bounds__(256) k_sort_place(const arp_pair* __restrict__ tmp, unsigned long long n,
+                                                    const int* __restrict__ off, arp_pair* __restrict__ out)
+{
+    unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int4 v = reinterpret_cast<const int4*>(tmp)[r];
+    int b = off[v.x], e = off[v.x + 1];
+    int rank = 0;
+    for (int k = b; k < e; ++k) rank += tmp[k].j < v.y ? 1 : 0;
+    reinterpret_cast<int4*>(out)[b + rank] = v;
+}
+
+int arp_pairs_sorted_build(arp_ctx* c)
+{
+    if (c->sorted_valid) return ARP_OK;
+    const unsigned long long n = c->n_pairs;
+    const size_t N = (size_t)c->N;
+    if (n >= (1ull << 31)) return arp_fail(c, ARP_E_CAPACITY, "too many records for the sorted view", __FILE__, __LINE__);
+    ARP_TRY(dbuf_reserve(c, c->sort_out, sizeof(arp_pair) * (size_t)n));
+    if (n == 0) { c->sorted_valid = 1; return ARP_OK; }
+    ARP_TRY(dbuf_reserve(c, c->sort_tmp, sizeof(arp_pair) * (size_t)n));
+    /* zero region: cnt[N+1] | cur[N+1] | ticket | scan state */
+    size_t tiles = (N + 1 + ARP_SCAN_TILE - 1) / ARP_SCAN_TILE + 1;
+    size_t o_cur = align_up(sizeof(int) * (N + 2), 256);
+    size_t o_tick = align_up(o_cur + sizeof(int) * (N + 2), 256);
+    size_t o_state = o_tick + 256;
+    size_t zb = o_state + tiles * sizeof(unsigned long long);
+    ARP_TRY(dbuf_reserve(c, c->sort_zero, zb));
+    ARP_TRY(dbuf_reserve(c, c->sort_off, sizeof(int) * (N + 2)));
+    char* z = c->sort_zero.as<char>();
+    int* cnt = (int*)z; int* cur = (int*)(z + o_cur);
+    unsigned* ticket = (unsigned*)(z + o_tick);
+    unsigned long long* state = (unsigned long long*)(z + o_state);
+    ARP_CUDA(c, cudaMemsetAsync(z, 0, zb, c->stream));
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    k_sort_count<<<blocks, 256, 0, c->stream>>>(c->out.as<arp_pair>(), n, cnt);
+    ARP_LAUNCHED(c);
+    ARP_TRY(arp_scan_exclusive(c, cnt, c->sort_off.as<int>(), state, ticket, nullptr, (int)(N + 1), N + 1));
+    k_sort_scatter<<<blocks, 256, 0, c->stream>>>(c->out.as<arp_pair>(), n, c->sort_off.as<int>(), cur,
+                                                  c->sort_tmp.as<arp_pair>());
+    ARP_LAUNCHED(c);
+    k_sort_place<<<blocks, 256, 0, c->stream>>>(c->sort_tmp.as<arp_pair>(), n, c->sort_off.as<int>(),
+                                                c->sort_out.as<arp_pair>());
+    ARP_LAUNCHED(c);
+    c->sorted_valid = 1;
+    return ARP_OK;
+}
+
+/* ---- binding-site expansion (interactions.py:1420-1424) ------------------------------------
+ * flag[i] = in selection, or within `radius` of a selected atom of the same structure
+ * (Bio.PDB.kdtrees test: double, d2 <= r*r).  Selected atoms are few (a ligand), so each
+ * block stages a tile of selected atoms in shared memory and every thread tests its atom. */
+__global__ void __launch_bounds__(256) k_within_collect(int N, const uint32_t* __restrict__ feat, int* __restrict__ n_sel,
+                                                        int* __restrict__ sel)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N && (feat[i] & ARP_F_IN_SELECTION)) sel[atomicAdd(n_sel, 1)] = i;
+}
+
+__global__ void __launch_bounds__(256) k_within(int N, int S, const float* __restrict__ xyz, const uint32_t* __restrict__ feat,
+                                                const int* __restrict__ struct_off, const int* __restrict__ n_sel_p,
+                                                const int* __restrict__ sel, double r2,
+                                                uint8_t* __restrict__ flags)
+{
+    __shared__ float4 s_sel[256];
+    __shared__ int s_struct[256];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_sel = *n_sel_p;
+    bool live = i < N;
+    float x = 0.f, y = 0.f, z = 0.f;
+    int s = 0;
+    bool flag = false;
+    if (live) {
+        x = xyz[3 * (size_t)i]; y = xyz[3 * (size_t)i + 1]; z = xyz[3 * (size_t)i + 2];
+        s = struct_of(struct_off, S, i);
+        flag = (feat[i] & ARP_F_IN_SELECTION) != 0;
+    }
+    for (int t0 = 0; t0 < n_sel; t0 += 256) {
+        int k = t0 + threadIdx.x;
+        __syncthreads();
+        if (k < n_sel) {
+            int a = sel[k];
+            s_sel[threadIdx.x] = make_float4(xyz[3 * (size_t)a], xyz[3 * (size_t)a + 1], xyz[3 * (size_t)a + 2], 0.f);
+            s_struct[threadIdx.x] = struct_of(struct_off, S, a);
+        }
+        __syncthreads();
+        int m = min(256, n_sel - t0);
+        if (live && !flag) {
+            for (int j = 0; j < m; ++j) {
+                float4 p = s_sel[j];
+                if (s_struct[j] == s && kd_within(p.x, p.y, p.z, x, y, z, r2)) { flag = true; break; }
+            }
+        }
+    }
+    if (live) flags[i] = flag ? 1 : 0;
+}
+
+int arp_flag_within_run(arp_ctx* c, double radius)
+{
+    const int N = c->N;
+    ARP_TRY(dbuf_reserve(c, c->within, (size_t)N * 5 + 64));
+    char* base = c->within.as<char>();
+    int* n_sel = (int*)base;
+    int* sel = (int*)(base + 16);
+    uint8_t* flags = (uint8_t*)(base + 16 + (size_t)N * 4);
+    ARP_CUDA(c, cudaMemsetAsync(n_sel, 0, 16, c->stream));
+    if (N == 0) return ARP_OK;
+    unsigned blocks = (unsigned)((N + 255) / 256);
+    k_within_collect<<<blocks, 256, 0, c->stream>>>(N, c->feat.as<uint32_t>(), n_sel, sel);
+    ARP_LAUNCHED(c);
+    double r2 = radius * radius;
+    k_within<<<blocks, 256, 0, c->stream>>>(N, c->S, c->xyz.as<float>(), c->feat.as<uint32_t>(),
+                                            c->S > 1 ? c->struct_off.as<int>() : nullptr, n_sel, sel, r2, flags);
+    ARP_LAUNCHED(c);
+    return ARP_OK;
+}

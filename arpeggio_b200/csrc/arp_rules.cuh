@@ -1,0 +1,402 @@
+/*
+ * arp_rules.cuh -- the per-pair CREDO rule evaluation, written once for the device.
+ *
+ * Everything here is a pure function of the two atoms' records and of the side arrays
+ * (hydrogens, bonds, halogen neighbours) addressed by ORIGINAL atom index.  The code is
+ * __host__ __device__ so that tests/ can also compile it for the host (tests/emu/) and
+ * check the rule logic in the GPU-less build container; the product only ever runs it
+ * inside the CUDA kernels of arp_pairs.cu.
+ *
+ * Arithmetic contract (measured against NumPy 2.3 / OpenBLAS):
+ *   - float32 distance (interactions.py:745): component differences rounded to float32,
+ *     squares rounded to float32, summed in double, rounded to float32, sqrtf.
+ *   - float64 norm/dot of 3-vectors through BLAS (utils.py:87, :147): FMA chain when
+ *     params.blas_fma, else sequential.
+ *   - utils.get_angle (utils.py:696-745): plain scalar arithmetic, one rounding per op,
+ *     in the dtype NumPy promotes to.  arccos is never evaluated: the angle tests are
+ *     comparisons of the cosine with the host-computed images in arp_params (cos_*).
+ * The translation unit must be compiled with -fmad=false (no implicit contraction);
+ * every fused multiply-add below is explicit.
+ */
+#ifndef ARP_RULES_CUH
+#define ARP_RULES_CUH
+
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/arpeggio_cuda.h"
+
+#if defined(__CUDACC__)
+#define ARP_HD __host__ __device__ __forceinline__
+#else
+#define ARP_HD static inline
+#endif
+
+/* ---- packed per-atom word (sorted-order attribute record, word 0) -------------------
+ * bits 0..19  ARP_F_* as uploaded
+ * bits 20..21 ARP_R_* of the atom's residue
+ * bit  22     atom has at least one entry in the bond CSR
+ * bits 23..31 radius class (K <= 512)                                                  */
+#define ARPK_RES_SHIFT   20
+#define ARPK_HAS_BOND    (1u << 22)
+#define ARPK_RAD_SHIFT   23
+#define ARPK_MAX_RAD     512
+
+struct ArpSide {               /* side arrays, original atom order (device pointers) */
+    const double*   vdw;       /* [K] */
+    const double*   cov;       /* [K] */
+    const int32_t*  bond_off;  /* [N+1] or null */
+    const int32_t*  bond_nbr;
+    const int32_t*  h_off;     /* [N+1] or null */
+    const double*   h_xyz;     /* [H][3] */
+    const float*    xnbr;      /* [N][3] or null */
+};
+
+struct ArpRuleParams {         /* arp_params narrowed the way NumPy (NEP 50) narrows it */
+    double r2;                 /* interacting_cutoff^2, double (Bio.PDB.kdtrees) */
+    float  r2_prefilter;       /* float32 upper bound used to skip the double test */
+    double vdw_comp;
+    double h_vdw;
+    float  dist_max, hbond_polar, weak_polar, ionic, carbonyl, aromatic, hydrophobic, metal;
+    double cos_hbond, cos_weak_hbond, cos_cx_min, cos_cx_max;
+    float  cos_xbond_f32;
+    int    blas_fma;
+    int    include_seq_adjacent;
+    /* what the comparisons give when get_angle() falls back to np.pi (utils.py:741-743) */
+    int    pi_ge_hbond, pi_ge_weak_hbond, pi_in_cx, pi_ge_xbond;
+};
+
+/* ---- exactly rounded primitives ------------------------------------------------------ */
+ARP_HD float f_sub(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fsub_rn(a, b);
+#else
+    volatile float r = a - b; return r;
+#endif
+}
+ARP_HD float f_add(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b; return r;
+#endif
+}
+ARP_HD float f_mul(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b; return r;
+#endif
+}
+ARP_HD float f_div(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fdiv_rn(a, b);
+#else
+    volatile float r = a / b; return r;
+#endif
+}
+ARP_HD float f_sqrt(float a) {
+#ifdef __CUDA_ARCH__
+    return __fsqrt_rn(a);
+#else
+    return sqrtf(a);
+#endif
+}
+ARP_HD double d_sub(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dsub_rn(a, b);
+#else
+    volatile double r = a - b; return r;
+#endif
+}
+ARP_HD double d_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b; return r;
+#endif
+}
+ARP_HD double d_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b; return r;
+#endif
+}
+ARP_HD double d_div(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __ddiv_rn(a, b);
+#else
+    volatile double r = a / b; return r;
+#endif
+}
+ARP_HD double d_sqrt(double a) {
+#ifdef __CUDA_ARCH__
+    return __dsqrt_rn(a);
+#else
+    return sqrt(a);
+#endif
+}
+ARP_HD double d_fma(double a, double b, double c) { return fma(a, b, c); }
+
+/* ---- NumPy / OpenBLAS models ------------------------------------------------------------ */
+
+/* np.dot of float64 3-vectors (OpenBLAS ddot tail loop) */
+ARP_HD double np_dot3_f64(double x0, double x1, double x2, double y0, double y1, double y2, int blas_fma)
+{
+    double d = d_mul(x0, y0);
+    if (blas_fma) { d = d_fma(x1, y1, d); d = d_fma(x2, y2, d); }
+    else          { d = d_add(d, d_mul(x1, y1)); d = d_add(d, d_mul(x2, y2)); }
+    return d;
+}
+ARP_HD double np_norm3_f64(double x, double y, double z, int blas_fma)
+{
+    return d_sqrt(np_dot3_f64(x, y, z, x, y, z, blas_fma));
+}
+/* np.dot of float32 3-vectors (OpenBLAS sdot: float products, double accumulator) */
+ARP_HD float np_dot3_f32(float x0, float x1, float x2, float y0, float y1, float y2)
+{
+    double d = (double)f_mul(x0, y0);
+    d = d_add(d, (double)f_mul(x1, y1));
+    d = d_add(d, (double)f_mul(x2, y2));
+    return (float)d;
+}
+ARP_HD float np_norm3_f32(float x, float y, float z) { return f_sqrt(np_dot3_f32(x, y, z, x, y, z)); }
+
+/* Bio.PDB.kdtrees radius test: double coordinates, sequential sum of squares <= r*r */
+ARP_HD bool kd_within(float ax, float ay, float az, float bx, float by, float bz, double r2)
+{
+    double dx = d_sub((double)ax, (double)bx);
+    double dy = d_sub((double)ay, (double)by);
+    double dz = d_sub((double)az, (double)bz);
+    double s = d_mul(dx, dx);
+    s = d_add(s, d_mul(dy, dy));
+    s = d_add(s, d_mul(dz, dz));
+    return s <= r2;
+}
+
+/* np.linalg.norm(bgn.coord - end.coord), float32 (interactions.py:745) */
+ARP_HD float np_dist_f32(float ax, float ay, float az, float bx, float by, float bz)
+{
+    return np_norm3_f32(f_sub(ax, bx), f_sub(ay, by), f_sub(az, bz));
+}
+
+/* ---- cosines of utils.get_angle in its three dtype flows ------------------------------ */
+
+/* a float32, b float64 (hydrogen), c float32: float64 throughout (utils.py:90, :113) */
+ARP_HD double cos_angle_fdf(const float* a, const double* b, const float* c)
+{
+    double v1x = d_sub((double)a[0], b[0]), v1y = d_sub((double)a[1], b[1]), v1z = d_sub((double)a[2], b[2]);
+    double v2x = d_sub((double)c[0], b[0]), v2y = d_sub((double)c[1], b[1]), v2z = d_sub((double)c[2], b[2]);
+    double m1 = d_sqrt(d_add(d_add(d_mul(v1x, v1x), d_mul(v1y, v1y)), d_mul(v1z, v1z)));
+    double m2 = d_sqrt(d_add(d_add(d_mul(v2x, v2x), d_mul(v2y, v2y)), d_mul(v2z, v2z)));
+    double n1x = d_div(v1x, m1), n1y = d_div(v1y, m1), n1z = d_div(v1z, m1);
+    double n2x = d_div(v2x, m2), n2y = d_div(v2y, m2), n2z = d_div(v2z, m2);
+    return d_add(d_add(d_mul(n1x, n2x), d_mul(n1y, n2y)), d_mul(n1z, n2z));
+}
+
+/* a, b float32 (v1 stays float32), c float64 (v2 float64): utils.py:151 */
+ARP_HD double cos_angle_ffd(const float* a, const float* b, const double* c)
+{
+    float v1x = f_sub(a[0], b[0]), v1y = f_sub(a[1], b[1]), v1z = f_sub(a[2], b[2]);
+    double v2x = d_sub(c[0], (double)b[0]), v2y = d_sub(c[1], (double)b[1]), v2z = d_sub(c[2], (double)b[2]);
+    float m1 = f_sqrt(f_add(f_add(f_mul(v1x, v1x), f_mul(v1y, v1y)), f_mul(v1z, v1z)));
+    float n1x = f_div(v1x, m1), n1y = f_div(v1y, m1), n1z = f_div(v1z, m1);
+    double m2 = d_sqrt(d_add(d_add(d_mul(v2x, v2x), d_mul(v2y, v2y)), d_mul(v2z, v2z)));
+    double n2x = d_div(v2x, m2), n2y = d_div(v2y, m2), n2z = d_div(v2z, m2);
+    return d_add(d_add(d_mul((double)n1x, n2x), d_mul((double)n1y, n2y)), d_mul((double)n1z, n2z));
+}
+
+/* all float32 (utils.py:174) */
+ARP_HD float cos_angle_fff(const float* a, const float* b, const float* c)
+{
+    float v1x = f_sub(a[0], b[0]), v1y = f_sub(a[1], b[1]), v1z = f_sub(a[2], b[2]);
+    float v2x = f_sub(c[0], b[0]), v2y = f_sub(c[1], b[1]), v2z = f_sub(c[2], b[2]);
+    float m1 = f_sqrt(f_add(f_add(f_mul(v1x, v1x), f_mul(v1y, v1y)), f_mul(v1z, v1z)));
+    float m2 = f_sqrt(f_add(f_add(f_mul(v2x, v2x), f_mul(v2y, v2y)), f_mul(v2z, v2z)));
+    float n1x = f_div(v1x, m1), n1y = f_div(v1y, m1), n1z = f_div(v1z, m1);
+    float n2x = f_div(v2x, m2), n2y = f_div(v2y, m2), n2z = f_div(v2z, m2);
+    return f_add(f_add(f_mul(n1x, n2x), f_mul(n1y, n2y)), f_mul(n1z, n2z));
+}
+
+/* arccos(c) is NaN (-> np.pi, utils.py:741-743) exactly when c is NaN or outside [-1, 1] */
+ARP_HD bool acos_is_nan(double c) { return !(c >= -1.0 && c <= 1.0); }
+ARP_HD bool acos_is_nan_f(float c) { return !(c >= -1.0f && c <= 1.0f); }
+
+/* ---- predicates ---------------------------------------------------------------------------- */
+
+/* utils.is_hbond (utils.py:73-93) / utils.is_weak_hbond (utils.py:96-116) */
+ARP_HD int rule_is_hbond(const ArpSide& S, const ArpRuleParams& P, int donor, const float* dc, const float* ac,
+                         double vdw_acc, double cos_thr, int pi_ge)
+{
+    if (!S.h_off) return 0;
+    int h0 = S.h_off[donor], h1 = S.h_off[donor + 1];
+    if (h0 == h1) return 0;
+    double lim = d_add(d_add(P.h_vdw, vdw_acc), P.vdw_comp);                       /* utils.py:89 */
+    for (int k = h0; k < h1; ++k) {
+        const double* h = S.h_xyz + 3 * (size_t)k;
+        double vx = d_sub(h[0], (double)ac[0]), vy = d_sub(h[1], (double)ac[1]), vz = d_sub(h[2], (double)ac[2]);
+        double h_dist = np_norm3_f64(vx, vy, vz, P.blas_fma);                      /* utils.py:87 */
+        if (h_dist <= lim) {
+            double c = cos_angle_fdf(dc, h, ac);
+            if (acos_is_nan(c) ? pi_ge : (c <= cos_thr)) return 1;                 /* utils.py:90 */
+        }
+    }
+    return 0;
+}
+
+/* utils.is_halogen_weak_hbond (utils.py:119-155) */
+ARP_HD int rule_is_halogen_weak_hbond(const ArpSide& S, const ArpRuleParams& P, int donor, int halogen,
+                                      const float* hc, uint32_t feat_hal, double vdw_hal)
+{
+    if (!(feat_hal & ARP_F_HAS_XNBR) || !S.xnbr || !S.h_off) return 0;            /* utils.py:139-141 */
+    int h0 = S.h_off[donor], h1 = S.h_off[donor + 1];
+    if (h0 == h1) return 0;
+    const float* nb = S.xnbr + 3 * (size_t)halogen;
+    double lim = d_add(d_add(P.h_vdw, vdw_hal), P.vdw_comp);                       /* utils.py:149 */
+    for (int k = h0; k < h1; ++k) {
+        const double* h = S.h_xyz + 3 * (size_t)k;
+        double vx = d_sub((double)hc[0], h[0]), vy = d_sub((double)hc[1], h[1]), vz = d_sub((double)hc[2], h[2]);
+        double h_dist = np_norm3_f64(vx, vy, vz, P.blas_fma);                      /* utils.py:147 */
+        if (h_dist <= lim) {
+            double c = cos_angle_ffd(nb, hc, h);
+            if (acos_is_nan(c) ? P.pi_in_cx : (c <= P.cos_cx_min && c >= P.cos_cx_max)) return 1;  /* utils.py:151 */
+        }
+    }
+    return 0;
+}
+
+#define ARPK_FAULT_XBOND_NO_NBR (1u << 31)
+
+/* utils.is_xbond (utils.py:158-179); a donor without single-bond neighbour makes the reference
+   raise (utils.py:173): reported through the fault bit, like the oracle */
+ARP_HD int rule_is_xbond(const ArpSide& S, const ArpRuleParams& P, int donor, const float* dc, const float* ac,
+                         uint32_t feat_donor, uint32_t* fault)
+{
+    if (!(feat_donor & ARP_F_HAS_XNBR) || !S.xnbr) { *fault |= ARPK_FAULT_XBOND_NO_NBR; return 0; }
+    float c = cos_angle_fff(S.xnbr + 3 * (size_t)donor, dc, ac);
+    if (acos_is_nan_f(c)) return P.pi_ge_xbond;
+    return c <= P.cos_xbond_f32;
+}
+
+/* InteractionComplex.__get_contact_type (interactions.py:643-691): six ifs, last true wins */
+ARP_HD uint32_t rule_entity_class(uint32_t fb, uint32_t fe)
+{
+    bool sb = (fb & ARP_F_IN_SELECTION) != 0, se = (fe & ARP_F_IN_SELECTION) != 0;
+    bool wb = (fb & ARP_F_IS_WATER) != 0,     we = (fe & ARP_F_IS_WATER) != 0;
+    uint32_t c = 7;
+    if (!sb && !se) c = ARP_CLASS_INTRA_NON_SELECTION;
+    if (sb && se) c = ARP_CLASS_INTRA_SELECTION;
+    if (sb != se) c = ARP_CLASS_INTER;
+    if ((sb && we) || (se && wb)) c = ARP_CLASS_SELECTION_WATER;
+    if ((!sb && we) || (!se && wb)) c = ARP_CLASS_NON_SELECTION_WATER;
+    if (wb && we) c = ARP_CLASS_WATER_WATER;
+    return c;
+}
+
+/*
+ * The filters that make _calculate_atom_contacts `continue` (interactions.py:712-741).
+ * (fb, rb, pb, nb) belong to the atom with the LOWER list index (atom_bgn), e to atom_end.
+ * f* are packed words (ARPK_*), r* residue index, p and n the residue's prev/next links.
+ */
+ARP_HD bool rule_pair_survives(uint32_t fb, int rb, int pb, int nb, uint32_t fe, int re, int pe, int ne,
+                               int include_seq_adjacent)
+{
+    if ((fb | fe) & ARP_F_ELEM_H) return false;                                    /* :712-713 */
+    if (rb == re) return false;                                                    /* :729-730 */
+    if (!include_seq_adjacent) {                                                   /* :733 */
+        uint32_t flb = fb >> ARPK_RES_SHIFT, fle = fe >> ARPK_RES_SHIFT;
+        if ((fle & ARP_R_IS_POLYPEPTIDE) &&                                        /* :734, res_end twice */
+            (flb & ARP_R_HAS_LINKS) && (fle & ARP_R_HAS_LINKS) &&                  /* :736-737 */
+            (nb == re || pb == re || ne == rb || pe == rb))                        /* :739-740 */
+            return false;
+    }
+    return true;
+}
+
+/*
+ * Loop body of _calculate_atom_contacts after the filters (interactions.py:743-936).
+ * b = atom_bgn (lower list index), e = atom_end; coordinates and packed words are passed
+ * in registers, rare branches read the side arrays by original index.
+ */
+ARP_HD void rule_classify(const ArpSide& S, const ArpRuleParams& P, int b, int e,
+                          float bx, float by, float bz, float ex, float ey, float ez,
+                          uint32_t fb, uint32_t fe, uint32_t* mask_out, float* dist_out)
+{
+    const float pb[3] = { bx, by, bz }, pe[3] = { ex, ey, ez };
+    const double vdw_b = S.vdw[fb >> ARPK_RAD_SHIFT], vdw_e = S.vdw[fe >> ARPK_RAD_SHIFT];
+    const double cov_b = S.cov[fb >> ARPK_RAD_SHIFT], cov_e = S.cov[fe >> ARPK_RAD_SHIFT];
+    const double sum_cov = d_add(cov_b, cov_e);                                    /* :717 */
+    const double sum_vdw = d_add(vdw_b, vdw_e);                                    /* :718 */
+    const float d = np_dist_f32(bx, by, bz, ex, ey, ez);                           /* :745 */
+    const float vdwc = (float)d_add(sum_vdw, P.vdw_comp);
+    uint32_t m = 0, fault = 0;
+
+    bool bonded = false;                                                           /* :750-754 */
+    if (fb & ARPK_HAS_BOND) {           /* only atom_bgn's neighbour list is consulted */
+        for (int k = S.bond_off[b]; k < S.bond_off[b + 1]; ++k)
+            if (S.bond_nbr[k] == e) { bonded = true; break; }
+    }
+    if (bonded)                  m |= 1u << ARP_SIFT_COVALENT;                     /* :756-757 */
+    else if (d < (float)sum_cov) m |= 1u << ARP_SIFT_CLASH;                        /* :760 */
+    else if (d < (float)sum_vdw) m |= 1u << ARP_SIFT_VDW_CLASH;                    /* :764 */
+    else if (d <= vdwc)          m |= 1u << ARP_SIFT_VDW;                          /* :768 */
+    else                         m |= 1u << ARP_SIFT_PROXIMAL;                     /* :772 */
+
+    if (d <= P.metal) {                                                            /* :777-783 */
+        if (((fb & ARP_F_HBOND_ACCEPTOR) && (fe & ARP_F_IS_METAL)) ||
+            ((fe & ARP_F_HBOND_ACCEPTOR) && (fb & ARP_F_IS_METAL))) m |= 1u << ARP_SIFT_METAL;
+    }
+
+    if (!(m & (1u << ARP_SIFT_CLASH)) && d <= P.dist_max) {                        /* :786 */
+        /* hbond / polar :791-819 */
+        if ((fb & ARP_F_IS_WATER) && d <= vdwc) {
+            if (fe & (ARP_F_HBOND_ACCEPTOR | ARP_F_HBOND_DONOR)) m |= (1u << ARP_SIFT_HBOND) | (1u << ARP_SIFT_POLAR);
+        } else if ((fe & ARP_F_IS_WATER) && d <= vdwc) {
+            if (fb & (ARP_F_HBOND_ACCEPTOR | ARP_F_HBOND_DONOR)) m |= (1u << ARP_SIFT_HBOND) | (1u << ARP_SIFT_POLAR);
+        } else if ((fb & ARP_F_HBOND_DONOR) && (fe & ARP_F_HBOND_ACCEPTOR)) {
+            if (rule_is_hbond(S, P, b, pb, pe, vdw_e, P.cos_hbond, P.pi_ge_hbond)) m |= 1u << ARP_SIFT_HBOND;
+            if (d <= P.hbond_polar) m |= 1u << ARP_SIFT_POLAR;
+        } else if ((fe & ARP_F_HBOND_DONOR) && (fb & ARP_F_HBOND_ACCEPTOR)) {
+            if (rule_is_hbond(S, P, e, pe, pb, vdw_b, P.cos_hbond, P.pi_ge_hbond)) m |= 1u << ARP_SIFT_HBOND;
+            if (d <= P.hbond_polar) m |= 1u << ARP_SIFT_POLAR;
+        }
+        /* weak hbond / weak polar: four independent ifs, each ASSIGNS SIFt[6] :857-886 */
+        int weak = 0; bool wp = false;
+        if ((fb & ARP_F_HBOND_ACCEPTOR) && (fe & ARP_F_WEAK_HBOND_DONOR)) {
+            weak = rule_is_hbond(S, P, e, pe, pb, vdw_b, P.cos_weak_hbond, P.pi_ge_weak_hbond); wp = true;
+        }
+        if ((fb & ARP_F_WEAK_HBOND_DONOR) && (fe & ARP_F_HBOND_ACCEPTOR)) {
+            weak = rule_is_hbond(S, P, b, pb, pe, vdw_e, P.cos_weak_hbond, P.pi_ge_weak_hbond); wp = true;
+        }
+        if ((fb & ARP_F_WEAK_HBOND_ACCEPTOR) && (fb & ARP_F_IS_HALOGEN) &&
+            (fe & (ARP_F_HBOND_DONOR | ARP_F_WEAK_HBOND_DONOR))) {
+            weak = rule_is_halogen_weak_hbond(S, P, e, b, pb, fb, vdw_b); wp = true;
+        }
+        if ((fe & ARP_F_WEAK_HBOND_ACCEPTOR) && (fe & ARP_F_IS_HALOGEN) &&
+            (fb & (ARP_F_HBOND_DONOR | ARP_F_WEAK_HBOND_DONOR))) {
+            weak = rule_is_halogen_weak_hbond(S, P, b, e, pe, fe, vdw_e); wp = true;
+        }
+        if (weak) m |= 1u << ARP_SIFT_WEAK_HBOND;
+        if (wp && d <= P.weak_polar) m |= 1u << ARP_SIFT_WEAK_POLAR;
+        /* xbond :889-895 */
+        if (d <= vdwc) {
+            if ((fb & ARP_F_XBOND_DONOR) && (fe & ARP_F_XBOND_ACCEPTOR)) {
+                if (rule_is_xbond(S, P, b, pb, pe, fb, &fault)) m |= 1u << ARP_SIFT_XBOND;
+            } else if ((fe & ARP_F_XBOND_DONOR) && (fb & ARP_F_XBOND_ACCEPTOR)) {
+                if (rule_is_xbond(S, P, e, pe, pb, fe, &fault)) m |= 1u << ARP_SIFT_XBOND;
+            }
+        }
+        /* ionic :898-904, carbonyl :907-913, aromatic :916-917, hydrophobic :920-921 */
+        if (d <= P.ionic && (((fb & ARP_F_POS_IONISABLE) && (fe & ARP_F_NEG_IONISABLE)) ||
+                             ((fb & ARP_F_NEG_IONISABLE) && (fe & ARP_F_POS_IONISABLE)))) m |= 1u << ARP_SIFT_IONIC;
+        if (d <= P.carbonyl && (((fb & ARP_F_CARBONYL_OXYGEN) && (fe & ARP_F_CARBONYL_CARBON)) ||
+                                ((fe & ARP_F_CARBONYL_OXYGEN) && (fb & ARP_F_CARBONYL_CARBON)))) m |= 1u << ARP_SIFT_CARBONYL;
+        if ((fb & fe & ARP_F_AROMATIC) && d <= P.aromatic) m |= 1u << ARP_SIFT_AROMATIC;
+        if ((fb & fe & ARP_F_HYDROPHOBE) && d <= P.hydrophobic) m |= 1u << ARP_SIFT_HYDROPHOBIC;
+    }
+    *mask_out = m | (rule_entity_class(fb, fe) << ARP_CLASS_SHIFT) | fault;
+    *dist_out = d;
+}
+
+#endif /* ARP_RULES_CUH */

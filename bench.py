@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Benchmark of the interatomic-contact hot path (BASELINE.json metric: classified atom-pairs/s on a
+100k-atom synthetic structure).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--atoms A]
+
+One step = one pass of the whole atom-atom job (cell-grid build + pair kernel: neighbour search,
+filters, fused 15-bit CREDO classifier, record emission) over the configs[2] structure.
+  value     pairs/s with the inputs resident in HBM; every step is bracketed by CUDA events on the
+            library's stream and L2 is flushed (384 MiB memset) between steps, outside the brackets
+  e2e       the same metric through the public API (ContactEngine.pairs) with HOST buffers: pinned
+            H2D of the step's arrays + kernels + D2H of the record stream inside the timed region
+  roofline  the pair kernel's algorithmic bytes (sum of input array bytes + 16 B per record) over its
+            mean CUDA-event duration in the same timed steps, against MEASURED_PEAKS.json (HBM copy)
+  cpu_baseline / --impl reference
+            the CPU oracle (oracle/arp_oracle.c, a C port of the reference's Python loop -- the
+            reference itself needs BioPython/OpenBabel/gemmi, which are not installable here) on the
+            host cores, one structure per thread
+Multi-GPU (torchrun, one rank per GPU): structures are independent, so each rank runs its own
+100k-atom structure (weak scaling, no collective on the data path; gloo only carries the barrier and
+the max/sum of the per-rank results).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'classified atom-pairs/s'
+UNIT = 'pairs/s'
+
+
+def workload_name(atoms):
+    return f'synthetic {atoms // 1000}k-atom cloud with SIFt feature masks, full 15-bit CREDO classifier (configs[2])'
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (burst copy)'
+    except Exception:
+        return 6650.0, 'fallback 6.65 TB/s (B200_PROFILING.md)'
+
+
+def ncu_traffic(atoms):
+    """dram bytes per k_pairs launch from the committed ncu --set full capture, if one was summarised."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'k_pairs_traffic.json')) as fh:
+            t = json.load(fh)
+        return float(t['dram_bytes_per_launch']) if int(t.get('atoms', 0)) == atoms else None
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={device}', f'--query-gpu={self.QUERY}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(',')]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.15 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        sm = [float(r[1]) for r in rows if r[1].replace('.', '').isdigit()]
+        reasons = set()
+        for r in rows:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': float(rows[0][2]) if rows[0][2].replace('.', '').isdigit() else None,
+                'reasons': sorted(reasons), 'samples': len(rows)}
+
+
+# ---------------------------------------------------------------------------------------------
+class CpuPort:
+    """The CPU oracle (C port of the reference loop) on `threads` host threads, one structure per thread
+    (ctypes releases the GIL; the oracle keeps no global state).  A few distinct clouds are shared
+    read-only by the threads."""
+
+    def __init__(self, atoms_per_thread, threads, seed=2):
+        from arpeggio_b200 import params as arp_params, synth
+        from oracle import oracle
+        self.oracle = oracle
+        oracle.lib()
+        self.p = arp_params.make_params()
+        self.threads = threads
+        distinct = [synth.cloud_featured(atoms_per_thread, seed=seed + 100 * t) for t in range(min(threads, 8))]
+        self.soas = [distinct[t % len(distinct)] for t in range(threads)]
+
+    def step(self, reps=1):
+        """every thread classifies its structure `reps` times; returns (pairs, seconds)"""
+        counts = [0] * self.threads
+
+        def work(t):
+            n = 0
+            for _ in range(reps):
+                n += self.oracle.pairs(self.soas[t], self.p).shape[0]
+            counts[t] = n
+
+        t0 = time.perf_counter()
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(self.threads)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        return sum(counts), time.perf_counter() - t0
+
+
+def dist_env():
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    return rank, world, local
+
+
+def run_reference(args):
+    """The reference arm: the CPU port of the reference's loop on all host cores (rank 0 only)."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 10_000 if args.steps <= 400 else 4_000
+    port = CpuPort(sample, cores)
+    for _ in range(max(args.warmup, 1)):
+        port.step()
+    t_tot, pairs = 0.0, 0
+    for _ in range(args.steps):
+        n, dt = port.step()
+        pairs += n
+        t_tot += dt
+    value = pairs / t_tot
+    desc = f'{cores} threads x one {sample}-atom cloud of the configs[2] recipe per step (C port of the reference loop)'
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * t_tot / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32 distance / f64 angles / u32 masks', 'data': 'synthetic',
+        'config': {'workload': workload_name(args.atoms), 'sample': desc},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    rank, world, local = dist_env()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist   # plumbing only: barrier + max/sum of per-rank scalars
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+
+    from arpeggio_b200 import abi, params as arp_params, synth
+    from arpeggio_b200.engine import ContactEngine, PinnedBuffer
+    from arpeggio_b200.soa import AtomSoA
+
+    p = arp_params.make_params()
+    soa = synth.cloud_featured(args.atoms, seed=2 + rank)
+    eng = ContactEngine(device=local, params=p)
+
+    # ---- inputs resident in HBM ------------------------------------------------------------
+    eng.upload_atoms(soa)
+    n_pairs = eng.run_pairs()
+    in_bytes = soa.input_bytes()
+    alg_bytes = in_bytes + 16 * n_pairs
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    eng.time_pairs(max(args.warmup, 3), flush_l2=True)
+    if dist:
+        dist.barrier()
+    eng.sync()
+    t_begin = time.time()
+    l0 = eng.launch_count()
+    ms_step = eng.time_pairs(args.steps, flush_l2=True)          # mean per-step CUDA-event time
+    eng.sync()
+    launches = eng.launch_count() - l0
+    st = eng.stats()
+    if dist:
+        dist.barrier()
+
+    # ---- end to end through the public API, host buffers -----------------------------------
+    pins = []
+
+    def pinned_like(a):
+        if a is None:
+            return None
+        pb = PinnedBuffer(max(a.nbytes, 16))
+        pins.append(pb)
+        v = pb.array(a.dtype, a.size).reshape(a.shape)
+        v[...] = a
+        return v
+
+    host = AtomSoA(**{k: pinned_like(getattr(soa, k)) for k in
+                      ('xyz', 'feat', 'res_id', 'rad_class', 'vdw', 'cov', 'res_prev', 'res_next', 'res_flags',
+                       'bond_off', 'bond_nbr', 'h_off', 'h_xyz', 'xnbr_xyz')})
+    out_pin = PinnedBuffer(16 * (n_pairs + 1024))
+    out = out_pin.array(abi.PAIR_DTYPE)
+    e2e_steps = max(3, min(args.steps, 200))
+
+    def e2e_step():
+        eng.upload_atoms(host)
+        n = eng.run_pairs()
+        return eng.fetch_pairs(n, sorted=False, out=out)
+
+    for _ in range(3):
+        got = e2e_step()
+    assert got.shape[0] == n_pairs
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    eng.sync()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
+
+    # ---- aggregate over ranks: slowest rank's time, total pairs ------------------------------
+    tot_pairs, ms_max, e2e_max, ms_kernel = float(n_pairs), ms_step, e2e_s, st['ms_search']
+    if dist:
+        import torch
+        t = torch.tensor([ms_step, e2e_s, st['ms_search']], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        s = torch.tensor([float(n_pairs)], dtype=torch.float64)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        ms_max, e2e_max, ms_kernel, tot_pairs = float(t[0]), float(t[1]), float(t[2]), float(s[0])
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = alg_bytes / (st['ms_search'] * 1e-3) / 1e9
+        line = {
+            'metric': METRIC, 'value': tot_pairs / (ms_max * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_max, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32 distance / f64 angles / u32 masks', 'data': 'synthetic',
+            'config': {'workload': workload_name(args.atoms), 'atoms_per_gpu': args.atoms, 'pairs_per_structure': n_pairs,
+                       'cutoff': 5.0, 'l2': 'flushed between steps (384 MiB memset outside the event brackets)',
+                       'timing': 'sum of per-step CUDA-event brackets on the library stream, max over ranks',
+                       'sharding': 'one independent structure per GPU, no collective'},
+            'e2e': {'value': tot_pairs / e2e_max, 'unit': UNIT, 'h2d_bytes_per_step': int(in_bytes),
+                    'd2h_bytes_per_step': int(16 * n_pairs + 64), 'steps': e2e_steps, 'ms_per_step': e2e_max * 1e3},
+            'gpu_launches': int(launches),
+            'kernels_per_step': int(launches // max(args.steps, 1)),
+            'roofline': {'bound': 'hbm', 'kernel': 'k_pairs', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': achieved / peak, 'traffic': ncu_traffic(args.atoms), 'algorithmic_bytes': int(alg_bytes),
+                         'kernel_ms': st['ms_search'], 'grid_build_ms': st['ms_grid'], 'peak_source': peak_src},
+            'clocks': clocks,
+            'candidate_tests_per_step': int(st['n_candidates']),
+        }
+        if not args.no_cpu:
+            cores = os.cpu_count() or 1
+            reps = 2
+            port = CpuPort(args.atoms // 4, cores)
+            port.step()
+            n_cpu, dt = port.step(reps)
+            rate = n_cpu / dt
+            line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                    'sample': f'{cores} threads x {reps} passes over a {args.atoms // 4}-atom cloud of the same '
+                                              f'recipe ({dt:.1f} s of wall time); C port of the reference loop'}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    for pb in pins:
+        pb.free()
+    out_pin.free()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=300)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', choices=('ours', 'reference'), default='ours')
+    ap.add_argument('--atoms', type=int, default=100_000)
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ARP_ABI_VERSION 3
+#define ARP_ABI_VERSION 4
 
 /* ---- error codes -------------------------------------------------------- */
 #define ARP_OK              0
@@ -236,8 +236,8 @@ typedef struct arp_stats {
     uint64_t output_bytes;      /* 16 * n_pairs */
     float    ms_total;          /* CUDA-event time of the last run, first to last kernel */
     float    ms_grid;           /* cell build part   */
-    float    ms_search;         /* pass 1: distance + filters -> hit masks */
-    float    ms_classify;       /* pass 2: classifier + emit */
+    float    ms_search;         /* the pair kernel: search + filters + classifier + emit */
+    float    ms_classify;       /* reserved (0): the classifier is fused into the pair kernel */
 } arp_stats;
 
 /* ---- life cycle ---------------------------------------------------------- */
@@ -294,7 +294,12 @@ int  arp_flag_within(arp_ctx* ctx, double radius, uint8_t* flags_out, uint64_t c
 /* ---- misc ------------------------------------------------------------------ */
 int  arp_sync(arp_ctx* ctx);
 int  arp_get_stats(arp_ctx* ctx, arp_stats* out);
-int  arp_timing_iters(arp_ctx* ctx, int iters, int flush_l2, float* ms_per_iter); /* bench hook: re-runs the pair kernels on resident inputs */
+/* bench hook: repeats the whole atom-atom job (grid build + pair kernel) `iters` times on the
+   resident inputs, each iteration bracketed by CUDA events on the context's stream; flush_l2 != 0
+   overwrites a buffer larger than L2 between iterations, outside the brackets.  *ms_per_iter is the
+   mean whole-job time; arp_get_stats then holds the mean grid-build / pair-kernel split. */
+int  arp_timing_iters(arp_ctx* ctx, int iters, int flush_l2, float* ms_per_iter);
+uint64_t arp_launch_count(arp_ctx* ctx);           /* kernels this context has launched so far */
 
 #ifdef __cplusplus
 }

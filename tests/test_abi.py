@@ -1,0 +1,118 @@
+"""The C ABI boundary without a GPU: the ctypes mirror matches include/arpeggio_cuda.h, the built
+library exports every declared symbol, and the product fails loudly when no device is present."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from arpeggio_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'arpeggio_cuda.h')
+
+
+def _probe(tmp_path, structs):
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
+    for cname, cls in structs:
+        lines.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')
+        for f, _ in cls._fields_:
+            lines.append(f'printf("{cname} {f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ['return 0;}']
+    src = tmp_path / 'probe.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'probe'
+    subprocess.check_call(['gcc', '-std=c11', '-o', str(exe), str(src)])
+    out = subprocess.check_output([str(exe)], text=True)
+    return {tuple(l.split()[:2]): int(l.split()[2]) for l in out.splitlines()}
+
+
+def test_struct_layouts_match_header(tmp_path):
+    structs = [('arp_params', abi.ArpParams), ('arp_atoms', abi.ArpAtoms), ('arp_planes', abi.ArpPlanes),
+               ('arp_stats', abi.ArpStats)]
+    got = _probe(tmp_path, structs)
+    for cname, cls in structs:
+        assert got[(cname, 'size')] == C.sizeof(cls), cname
+        for f, _ in cls._fields_:
+            assert got[(cname, f)] == getattr(cls, f).offset, (cname, f)
+
+
+def test_record_layouts_match_header(tmp_path):
+    class Pair(C.Structure):
+        _fields_ = [('i', C.c_int32), ('j', C.c_int32), ('mask', C.c_uint32), ('dist', C.c_float)]
+
+    class PlanePair(C.Structure):
+        _fields_ = [('a', C.c_int32), ('b', C.c_int32), ('code', C.c_uint32), ('_pad', C.c_uint32), ('dist', C.c_double)]
+
+    class AtomPlane(C.Structure):
+        _fields_ = [('atom', C.c_int32), ('ring', C.c_int32), ('code', C.c_uint32), ('_pad', C.c_uint32), ('dist', C.c_double)]
+
+    got = _probe(tmp_path, [('arp_pair', Pair), ('arp_plane_pair', PlanePair), ('arp_atom_plane', AtomPlane)])
+    for cname, cls, dt in (('arp_pair', Pair, abi.PAIR_DTYPE), ('arp_plane_pair', PlanePair, abi.PLANE_PAIR_DTYPE),
+                           ('arp_atom_plane', AtomPlane, abi.ATOM_PLANE_DTYPE)):
+        assert got[(cname, 'size')] == dt.itemsize
+        for f, _ in cls._fields_:
+            assert got[(cname, f)] == dt.fields[f][1], (cname, f)
+
+
+def test_constants_match_header():
+    text = open(HEADER).read()
+    defs = dict(re.findall(r'#define\s+(ARP_\w+)\s+\(?(-?\w+)', text))
+    assert int(defs['ARP_ABI_VERSION']) == abi.ABI_VERSION
+    for k, name in enumerate(abi.SIFT_NAMES):
+        key = {'metal_complex': 'METAL'}.get(name, name.upper())
+        assert int(defs['ARP_SIFT_' + key]) == k
+    for name in ('OK', 'E_INVALID_ARG', 'E_CUDA', 'E_OOM', 'E_CAPACITY', 'E_NOT_READY', 'E_NO_DEVICE'):
+        assert int(defs['ARP_' + name]) == getattr(abi, name)
+    bits = dict(re.findall(r'#define\s+(ARP_[FRP]_\w+)\s+\(1u << (\d+)\)', text))
+    for name, sh in bits.items():
+        assert getattr(abi, name[4:]) == 1 << int(sh), name
+    for k, name in enumerate(abi.CLASS_NAMES):
+        assert int(defs['ARP_CLASS_' + name]) == k
+
+
+def test_header_declares_what_python_binds():
+    text = open(HEADER).read()
+    declared = set(re.findall(r'\b(arp_[a-z_0-9]+)\s*\(', text))
+    assert declared == set(abi.EXPORTED_SYMBOLS)
+
+
+def test_library_loads_and_exports_every_symbol():
+    from arpeggio_b200 import _lib
+    L = _lib.lib()
+    for name in abi.EXPORTED_SYMBOLS:
+        assert hasattr(L, name), name
+    assert L.arp_abi_version() == abi.ABI_VERSION
+
+
+def test_no_device_means_error_not_fallback():
+    from arpeggio_b200 import _lib
+    from arpeggio_b200.engine import ContactEngine
+    L = _lib.lib()
+    if L.arp_device_count() > 0:
+        pytest.skip('a CUDA device is present')
+    with pytest.raises(_lib.ArpeggioCudaError) as ei:
+        ContactEngine(0)
+    assert ei.value.code == abi.E_NO_DEVICE
+    assert 'no CPU fallback' in str(ei.value)
+
+
+def test_default_params_from_c_match_python_thresholds():
+    """arp_params_default (C library acos) and params.make_params (host NumPy arccos) hold the same
+    thresholds; the cosine images may differ in the last ulps (different arccos implementations)."""
+    from arpeggio_b200 import _lib, params
+    p = abi.ArpParams()
+    assert _lib.lib().arp_params_default(C.byref(p)) == 0
+    q = params.make_params()
+    for f, _ in abi.ArpParams._fields_:
+        a, b = getattr(p, f), getattr(q, f)
+        if f.startswith('cos_'):
+            a = np.array(list(a) if hasattr(a, '__len__') else [a], dtype=np.float64)
+            b = np.array(list(b) if hasattr(b, '__len__') else [b], dtype=np.float64)
+            assert np.allclose(a, b, rtol=0, atol=3e-7), f
+        elif hasattr(a, '__len__'):
+            assert list(a) == list(b), f
+        else:
+            assert a == b, f

@@ -1,0 +1,203 @@
+"""GPU parity of the atom-atom path: libarpeggio_cuda.so (through the C ABI) against the CPU oracle
+and against the golden records produced by the reference's own code.  Bit-exact: pair set, (i < j)
+orientation, 15-bit mask + entity class, float32 distance bits."""
+import numpy as np
+import pytest
+
+import util
+from arpeggio_b200 import abi, params as arp_params, synth
+from arpeggio_b200.soa import AtomSoA
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+CASES = util.golden_cases()
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_golden_pairs(engine, case):
+    g = util.Golden(case)
+    engine.set_params(g.params)
+    got = engine.pairs(g.soa)
+    if g.meta['raises'] == 'AttributeError':
+        assert np.any(got['mask'] & np.uint32(abi.PAIR_FAULT_XBOND_NO_NBR))
+        util.assert_records_equal(got, oracle.pairs(g.soa, g.params), f'{case} vs oracle')
+        return
+    util.assert_records_equal(got, g.exp_pairs, f'{case} atom-atom vs reference records')
+
+
+def _check_vs_oracle(engine, soa, p, what):
+    engine.set_params(p)
+    got = engine.pairs(soa)
+    exp, n_within = oracle.pairs(soa, p, with_counts=True)
+    util.assert_records_equal(got, exp, what)
+    st = engine.stats()
+    assert st['n_pairs'] == exp.shape[0]
+    assert st['n_candidates'] >= n_within
+    # the unsorted stream is a permutation of the sorted one
+    raw = engine.fetch_pairs(got.shape[0], sorted=False)
+    util.assert_records_equal(util.sort_pairs(raw), got, what + ' (unsorted stream)')
+    return got
+
+
+def test_config2_uniform_cloud(engine):
+    soa = synth.cloud_uniform(10_000, seed=1)
+    got = _check_vs_oracle(engine, soa, arp_params.make_params(), 'config 2')
+    assert got.shape[0] > 100_000
+    assert not np.any(got['mask'] & np.uint32(0x7FE0))        # bits 5..14 need feature masks
+
+
+def test_config3_featured_cloud_full_size(engine):
+    soa = synth.cloud_featured(100_000, seed=2)
+    got = _check_vs_oracle(engine, soa, arp_params.make_params(), 'config 3')
+    assert got.shape[0] > 1_000_000
+    seen = np.bitwise_or.reduce(got['mask'])
+    assert seen & 0x7FFF == 0x7FFF, 'every SIFt bit occurs in the 100k cloud'
+    assert not np.any(got['mask'] & np.uint32(abi.PAIR_FAULT_XBOND_NO_NBR))
+
+
+@pytest.mark.parametrize('cutoff,comp,adj', [(3.0, 0.1, False), (5.0, 0.0, True), (8.0, 0.35, False), (0.5, 0.1, False)])
+def test_parameter_sweep(engine, cutoff, comp, adj):
+    soa = synth.cloud_featured(6_000, seed=7)
+    _check_vs_oracle(engine, soa, arp_params.make_params(cutoff, comp, adj), f'cutoff={cutoff}')
+
+
+def test_far_from_origin(engine):
+    soa = synth.cloud_featured(5_000, seed=8)
+    soa.xyz += np.float32(9000.0)          # large coordinates widen the float32 prefilter band
+    soa.h_xyz += 9000.0
+    soa.xnbr_xyz += np.float32(9000.0)
+    _check_vs_oracle(engine, soa, arp_params.make_params(), 'offset cloud')
+
+
+def test_degenerate_single_cell(engine):
+    """Hundreds of atoms inside one cell (candidate chunks > 128, long home lists)."""
+    rng = np.random.default_rng(5)
+    n = 700
+    soa = synth.cloud_featured(n, seed=9)
+    soa.xyz[:] = np.round(rng.uniform(0, 4.0, size=(n, 3)), 3).astype(np.float32)
+    soa.xyz[:40] = soa.xyz[0]               # coincident atoms (distance 0)
+    _check_vs_oracle(engine, soa, arp_params.make_params(), 'degenerate')
+
+
+def test_line_and_plane_shapes(engine):
+    """Elongated bounding boxes: the cell bound (4 n + 64) forces wider cells."""
+    rng = np.random.default_rng(6)
+    n = 3000
+    soa = synth.cloud_featured(n, seed=10)
+    soa.xyz[:, 0] = np.round(rng.uniform(0, 30000.0, n), 3)
+    soa.xyz[:, 1:] = np.round(rng.uniform(0, 3.0, (n, 2)), 3)
+    _check_vs_oracle(engine, soa, arp_params.make_params(), 'line')
+    soa.xyz[:, 0] = np.round(rng.uniform(0, 150.0, n), 3)
+    _check_vs_oracle(engine, soa, arp_params.make_params(), 'rod')
+
+
+def test_knife_edge_distances(engine):
+    """Pairs whose float32 distance sits exactly on, one ulp below and one ulp above each threshold."""
+    p = arp_params.make_params()
+    thr = [5.0, 4.5, 4.0, 3.9, 3.6, 3.5, 3.4, 3.3, 2.8, 1.52, 1.42]
+    xs, feats = [], []
+    x0 = 0.0
+    for t in thr:
+        f = np.float32(t)
+        for d in (np.nextafter(f, np.float32(0)), f, np.nextafter(f, np.float32(10))):
+            xs += [x0, x0 + float(d)]
+            x0 += 40.0
+    n = len(xs)
+    xyz = np.zeros((n, 3), np.float32)
+    xyz[:, 0] = np.array(xs, dtype=np.float64).astype(np.float32)
+    all_types = np.uint32(0xFFF) | abi.F_IS_METAL
+    soa = AtomSoA(xyz=xyz, feat=np.full(n, all_types, np.uint32), res_id=np.arange(n, dtype=np.int32),
+                  rad_class=(np.arange(n) % 2).astype(np.uint16), vdw=np.array([1.7, 1.6]), cov=np.array([0.76, 0.66]),
+                  res_prev=np.full(n, -1, np.int32), res_next=np.full(n, -1, np.int32), res_flags=np.zeros(n, np.uint8))
+    got = _check_vs_oracle(engine, soa, p, 'knife edge')
+    assert got.shape[0] >= 2 * len(thr)
+
+
+def test_empty_and_tiny(engine):
+    p = arp_params.make_params()
+    engine.set_params(p)
+    for n in (0, 1, 2):
+        soa = synth.cloud_featured(8, seed=3)
+        sub = AtomSoA(xyz=soa.xyz[:n], feat=soa.feat[:n], res_id=np.arange(n, dtype=np.int32), rad_class=soa.rad_class[:n],
+                      vdw=soa.vdw, cov=soa.cov, res_prev=np.full(max(n, 1), -1, np.int32),
+                      res_next=np.full(max(n, 1), -1, np.int32), res_flags=np.zeros(max(n, 1), np.uint8))
+        got = engine.pairs(sub)
+        util.assert_records_equal(got, oracle.pairs(sub, p), f'n={n}')
+
+
+def test_batch_equals_per_structure(engine):
+    """A batch (struct_off) gives exactly the union of the per-structure streams; no pair spans two structures."""
+    p = arp_params.make_params()
+    engine.set_params(p)
+    parts = [synth.cloud_featured(n, seed=20 + k) for k, n in enumerate((1500, 1, 0, 3000, 700))]
+    parts[2] = AtomSoA(xyz=np.zeros((0, 3), np.float32), feat=np.zeros(0, np.uint32), res_id=np.zeros(0, np.int32),
+                       rad_class=np.zeros(0, np.uint16), vdw=parts[0].vdw, cov=parts[0].cov,
+                       res_prev=np.zeros(0, np.int32), res_next=np.zeros(0, np.int32), res_flags=np.zeros(0, np.uint8))
+    batch = AtomSoA.concat(parts)
+    got = engine.pairs(batch)
+    util.assert_records_equal(got, oracle.pairs(batch, p), 'batch vs oracle')
+    off = batch.struct_off
+    s_i = np.searchsorted(off, got['i'], side='right')
+    s_j = np.searchsorted(off, got['j'], side='right')
+    assert np.array_equal(s_i, s_j)
+    pieces = []
+    for k, part in enumerate(parts):
+        if part.n_atoms == 0:
+            continue
+        r = engine.pairs(part).copy()
+        r['i'] += off[k]
+        r['j'] += off[k]
+        pieces.append(r)
+    util.assert_records_equal(got, util.sort_pairs(np.concatenate(pieces)), 'batch vs per-structure runs')
+
+
+def test_rerun_is_stable_and_overflow_regrows(engine):
+    """A sparse structure sizes the record buffer small; a dense one must regrow it (overflow path)."""
+    p = arp_params.make_params()
+    engine.set_params(p)
+    from arpeggio_b200.engine import ContactEngine
+    with ContactEngine(engine.device, p) as e2:
+        sparse = synth.cloud_uniform(200, seed=4)
+        sparse.xyz *= np.float32(10.0)
+        assert e2.pairs(sparse).shape[0] < 50
+        rng = np.random.default_rng(1)
+        dense = synth.cloud_uniform(2000, seed=5)
+        dense.xyz[:] = np.round(rng.uniform(0, 12.0, size=(2000, 3)), 3).astype(np.float32)
+        got = e2.pairs(dense)
+        assert got.shape[0] > 2000 * 16 + 4096
+        util.assert_records_equal(got, oracle.pairs(dense, p), 'dense after sparse')
+        util.assert_records_equal(e2.pairs(), got, 'second run on resident inputs')
+
+
+def test_flag_within(engine):
+    soa = synth.cloud_featured(20_000, seed=11)
+    soa.feat &= ~np.uint32(abi.F_IN_SELECTION)
+    soa.feat[100:160] |= abi.F_IN_SELECTION
+    engine.upload_atoms(soa)
+    for radius in (6.0, 0.0, 12.5):
+        assert np.array_equal(engine.flag_within(radius), oracle.flag_within(soa, radius)), radius
+
+
+def test_errors_are_reported(engine):
+    from arpeggio_b200._lib import ArpeggioCudaError
+    from arpeggio_b200.engine import ContactEngine
+    with ContactEngine(engine.device) as e2:
+        with pytest.raises(ArpeggioCudaError) as ei:
+            e2.run_pairs()
+        assert ei.value.code == abi.E_NOT_READY
+        soa = synth.cloud_uniform(10, seed=1)
+        bad = AtomSoA(xyz=soa.xyz.copy(), feat=soa.feat, res_id=soa.res_id, rad_class=soa.rad_class, vdw=soa.vdw, cov=soa.cov,
+                      res_prev=soa.res_prev, res_next=soa.res_next, res_flags=soa.res_flags)
+        bad.xyz[3, 1] = np.nan
+        with pytest.raises(ValueError):
+            e2.upload_atoms(bad)
+        e2.upload_atoms(soa)
+        n = e2.run_pairs()
+        small = np.empty(max(n - 1, 0), dtype=abi.PAIR_DTYPE)
+        if n:
+            with pytest.raises(ArpeggioCudaError) as ei:
+                e2._check(e2._L.arp_pairs_fetch(e2._ctx, small.ctypes.data, small.shape[0], 1))
+            assert ei.value.code == abi.E_CAPACITY
+    with pytest.raises(ArpeggioCudaError):
+        ContactEngine(device=4096)

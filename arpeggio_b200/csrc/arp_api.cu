@@ -106,32 +106,7 @@ void cosine_images(arp_params* p)
     }
 }
 
-void derive_rule_params(const arp_params& p, ArpRuleParams* r)
-{
-    memset(r, 0, sizeof *r);
-    r->r2 = p.interacting_cutoff * p.interacting_cutoff;
-    r->vdw_comp = p.vdw_comp;
-    r->h_vdw = p.h_vdw;
-    r->dist_max = (float)p.dist_max;          /* NEP 50: np.float32 <op> python float compares in float32 */
-    r->hbond_polar = (float)p.hbond_polar_dist;
-    r->weak_polar = (float)p.weak_polar_dist;
-    r->ionic = (float)p.ionic_dist;
-    r->carbonyl = (float)p.carbonyl_dist;
-    r->aromatic = (float)p.aromatic_dist;
-    r->hydrophobic = (float)p.hydrophobic_dist;
-    r->metal = (float)p.metal_dist;
-    r->cos_hbond = p.cos_hbond;
-    r->cos_weak_hbond = p.cos_weak_hbond;
-    r->cos_cx_min = p.cos_cx_min;
-    r->cos_cx_max = p.cos_cx_max;
-    r->cos_xbond_f32 = p.cos_xbond_f32;
-    r->blas_fma = p.blas_fma;
-    r->include_seq_adjacent = p.include_sequence_adjacent;
-    r->pi_ge_hbond = M_PI >= p.hbond_angle;
-    r->pi_ge_weak_hbond = M_PI >= p.weak_hbond_angle;
-    r->pi_in_cx = p.cx_angle_min <= M_PI && M_PI <= p.cx_angle_max;
-    r->pi_ge_xbond = M_PI >= p.xbond_angle;
-}
+void derive_rule_params(const arp_params& p, ArpRuleParams* r) { arp_derive_rule_params(&p, r); }
 
 int upload(arp_ctx* c, DBuf& b, const void* src, size_t bytes)
 {
@@ -231,7 +206,7 @@ void arp_destroy(arp_ctx* c)
     DBuf* bufs[] = { &c->xyz, &c->feat, &c->res_id, &c->rad_class, &c->vdw, &c->cov, &c->res_prev, &c->res_next,
                      &c->res_flags, &c->bond_off, &c->bond_nbr, &c->h_off, &c->h_xyz, &c->xnbr, &c->struct_off,
                      &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->out,
-                     &c->sort_tmp, &c->sort_out, &c->sort_zero, &c->sort_off, &c->within, &c->flush };
+                     &c->radtab, &c->sort_tmp, &c->sort_out, &c->sort_zero, &c->sort_off, &c->within, &c->flush };
     for (DBuf* b : bufs) dbuf_free(*b);
     arp_planes_release(c);
     for (int k = 0; k < 4; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
@@ -252,6 +227,7 @@ int arp_set_params(arp_ctx* c, const arp_params* p)
     c->params = *p;
     derive_rule_params(c->params, &c->rp);
     c->have_params = 1;
+    c->radtab_valid = 0;
     c->pairs_valid = 0; c->sorted_valid = 0;
     c->ring_ring.valid = c->atom_ring.valid = c->amide_amide.valid = c->amide_ring.valid = 0;
     return ARP_OK;
@@ -296,7 +272,7 @@ int arp_upload_atoms(arp_ctx* c, const arp_atoms* a)
             ARP_REQUIRE(c, a->struct_off[s] <= a->struct_off[s + 1], ARP_E_INVALID_ARG, "struct_off must ascend");
     }
     ARP_TRY(arp_bind(c));
-    c->have_atoms = 0; c->pairs_valid = 0; c->sorted_valid = 0;
+    c->have_atoms = 0; c->pairs_valid = 0; c->sorted_valid = 0; c->radtab_valid = 0;
     c->atom_ring.valid = 0;
     c->input_bytes = 0;
     c->N = N; c->Rs = a->n_residues; c->K = a->n_rad_classes; c->S = S;

@@ -83,6 +83,8 @@ struct arp_ctx {
     size_t zero_bytes = 0, off_bbox = 0, off_cnt = 0, off_state = 0;
     size_t cell_bound = 0;        /* upper bound of the number of cells, all structures */
     DBuf geom, cell_start, cell_of, rank, pos4, att4;
+    DBuf radtab;                  /* K x K float32 proximity thresholds */
+    int radtab_valid = 0;
     RunMeta* h_meta = nullptr;    /* pinned */
 
     /* output stream */

@@ -54,29 +54,57 @@ __device__ __forceinline__ int struct_of(const int* __restrict__ struct_off, int
 __global__ void __launch_bounds__(256) k_bbox(const float* __restrict__ xyz, const int* __restrict__ struct_off,
                                               int S, int N, unsigned* __restrict__ bbox)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = i < N;
-    int s = -1;
+    __shared__ unsigned s_v[8][6];
+    __shared__ int s_s[8];
+    const int ATOMS_PER_THREAD = 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int base = blockIdx.x * (256 * ATOMS_PER_THREAD);
+    int s = -1;                       /* structure of this thread's atoms; -2 = mixed */
     unsigned v[6] = {0, 0, 0, 0, 0, 0};
-    if (live) {
-        s = struct_of(struct_off, S, i);
+    for (int t = 0; t < ATOMS_PER_THREAD; ++t) {
+        int i = base + t * 256 + threadIdx.x;
+        if (i >= N) break;
+        int si = struct_of(struct_off, S, i);
+        if (s == -1) s = si;
+        if (si != s) {                /* rare: a structure boundary inside the thread's atoms */
+            for (int k = 0; k < 3; ++k) {
+                unsigned o = f2ord(xyz[3 * (size_t)i + k]);
+                atomicMax(&bbox[6 * (size_t)si + k], ~o);
+                atomicMax(&bbox[6 * (size_t)si + 3 + k], o);
+            }
+            continue;
+        }
         for (int k = 0; k < 3; ++k) {
             unsigned o = f2ord(xyz[3 * (size_t)i + k]);
-            v[k] = ~o; v[3 + k] = o;
+            v[k] = max(v[k], ~o); v[3 + k] = max(v[3 + k], o);
         }
     }
-    /* warp-uniform structure: reduce in the warp, one lane commits */
-    int s0 = __shfl_sync(FULL, s, 0);
-    bool uniform = __all_sync(FULL, s == s0 || !live);
+    /* warp: reduce when every live lane sees the same structure, else commit per lane */
+    int smax = __reduce_max_sync(FULL, s);
+    bool uniform = __all_sync(FULL, s == smax || s == -1);
     if (uniform) {
-        s0 = __reduce_max_sync(FULL, s);
-        if (s0 < 0) return;
-        for (int k = 0; k < 6; ++k) {
-            unsigned m = __reduce_max_sync(FULL, v[k]);
-            if ((threadIdx.x & 31) == 0) atomicMax(&bbox[6 * (size_t)s0 + k], m);
-        }
-    } else if (live) {
+        for (int k = 0; k < 6; ++k) v[k] = __reduce_max_sync(FULL, v[k]);
+    } else if (s >= 0) {
         for (int k = 0; k < 6; ++k) atomicMax(&bbox[6 * (size_t)s + k], v[k]);
+    }
+    if (lane == 0) {
+        s_s[warp] = uniform ? smax : -1;
+        for (int k = 0; k < 6; ++k) s_v[warp][k] = v[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int ws = lane < 8 ? s_s[lane] : -1;
+        int bs = __reduce_max_sync(FULL, ws);
+        bool buni = __all_sync(FULL, ws == bs || ws == -1);
+        if (buni) {
+            if (bs >= 0 && lane < 6) {
+                unsigned m = 0;
+                for (int w = 0; w < 8; ++w) if (s_s[w] >= 0) m = max(m, s_v[w][lane]);
+                atomicMax(&bbox[6 * (size_t)bs + lane], m);
+            }
+        } else if (lane < 8 && ws >= 0) {
+            for (int k = 0; k < 6; ++k) atomicMax(&bbox[6 * (size_t)ws + k], s_v[lane][k]);
+        }
     }
 }
 
@@ -309,26 +337,43 @@ struct PairArgs {
     ArpSide       side;
 };
 
-__device__ __forceinline__ void pairs_drain(const PairArgs& A, const ArpRuleParams& P, const uint2* q,
+/* One batch of queued distance hits: (1) the reference's `continue` filters, 32 hits per round, survivors
+   compacted in place; (2) one cursor atomic for the survivors; (3) classifier + coalesced 16-byte stores. */
+__device__ __forceinline__ void pairs_drain(const PairArgs& A, const ArpRuleParams& P, uint2* q,
                                             unsigned head, unsigned n, int lane)
 {
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&A.meta->n_pairs, (unsigned long long)n);
-    base = __shfl_sync(FULL, base, 0);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned ns = 0;
     for (unsigned r = 0; r < n; r += 32) {
-        unsigned idx = r + lane;
+        const unsigned idx = r + lane;
+        bool keep = false;
+        uint2 e = make_uint2(0, 0);
         if (idx < n) {
-            uint2 e = q[(head + idx) & (PAIR_QCAP - 1)];
-            float4 pb = A.pos4[e.x], pe = A.pos4[e.y];
-            uint32_t fb = A.att4[e.x].x, fe = A.att4[e.y].x;
+            e = q[(head + idx) & (PAIR_QCAP - 1)];
+            const uint4 ab = A.att4[e.x], ae = A.att4[e.y];
+            keep = rule_pair_survives(ab.x, (int)ab.y, (int)ab.z, (int)ab.w, ae.x, (int)ae.y, (int)ae.z, (int)ae.w,
+                                      P.include_seq_adjacent);
+        }
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (keep) q[(head + ns + __popc(m & lt_mask)) & (PAIR_QCAP - 1)] = e;     /* ns <= r: never ahead of the reads */
+        ns += __popc(m);
+    }
+    if (ns == 0) return;
+    __syncwarp();
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&A.meta->n_pairs, (unsigned long long)ns);
+    base = __shfl_sync(FULL, base, 0);
+    for (unsigned r = 0; r < ns; r += 32) {
+        const unsigned idx = r + lane;
+        if (idx < ns) {
+            const uint2 e = q[(head + idx) & (PAIR_QCAP - 1)];
+            const float4 pb = A.pos4[e.x], pe = A.pos4[e.y];
+            const uint32_t fb = A.att4[e.x].x, fe = A.att4[e.y].x;
             uint32_t mask; float dist;
-            int ib = __float_as_int(pb.w), ie = __float_as_int(pe.w);
+            const int ib = __float_as_int(pb.w), ie = __float_as_int(pe.w);
             rule_classify(A.side, P, ib, ie, pb.x, pb.y, pb.z, pe.x, pe.y, pe.z, fb, fe, &mask, &dist);
-            unsigned long long o = base + idx;
-            if (o < A.out_cap) {
-                int4 rec = make_int4(ib, ie, (int)mask, __float_as_int(dist));
-                reinterpret_cast<int4*>(A.out)[o] = rec;
-            }
+            const unsigned long long o = base + idx;
+            if (o < A.out_cap) reinterpret_cast<int4*>(A.out)[o] = make_int4(ib, ie, (int)mask, __float_as_int(dist));
         }
     }
     __syncwarp();
@@ -390,51 +435,44 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 2) k_pairs(PairArgs A, ArpRul
             for (int k0 = 0; k0 < total; k0 += PAIR_CHUNK) {
                 float cxs[PAIR_SLOTS], cys[PAIR_SLOTS], czs[PAIR_SLOTS];
                 int   cor[PAIR_SLOTS], cg[PAIR_SLOTS];
-                uint4 cat[PAIR_SLOTS];
 #pragma unroll
                 for (int sl = 0; sl < PAIR_SLOTS; ++sl) {
                     int k = k0 + sl * 32 + lane;
                     cg[sl] = -1;
+                    cxs[sl] = cys[sl] = czs[sl] = 0.f; cor[sl] = 0;
                     if (k < total) {
                         int g = k < p1 ? b0 + k : k < p2 ? b1 + (k - p1) : k < p3 ? b2 + (k - p2)
                               : k < p4 ? b3 + (k - p3) : b4 + (k - p4);
                         float4 p = A.pos4[g];
                         cxs[sl] = p.x; cys[sl] = p.y; czs[sl] = p.z; cor[sl] = __float_as_int(p.w);
-                        cat[sl] = A.att4[g];
                         cg[sl] = g;
-                    } else {
-                        cxs[sl] = cys[sl] = czs[sl] = 0.f; cor[sl] = 0; cat[sl] = make_uint4(0, 0, 0, 0);
                     }
                 }
                 /* home atoms that still have candidates in this chunk: k > h */
                 const int h_end = min(nh, k0 + PAIR_CHUNK - 1);
                 for (int h = 0; h < h_end; ++h) {
-                    const float4 hp = A.pos4[hb + h];
-                    const uint4  ha = A.att4[hb + h];
-                    const int    ho = __float_as_int(hp.w);
+                    float hx, hy, hz; int ho;
+                    if (k0 == 0 && h < 32) {       /* candidate k = h of run 0 is home atom h */
+                        hx = __shfl_sync(FULL, cxs[0], h); hy = __shfl_sync(FULL, cys[0], h);
+                        hz = __shfl_sync(FULL, czs[0], h); ho = __shfl_sync(FULL, cor[0], h);
+                    } else {
+                        const float4 hp = A.pos4[hb + h];
+                        hx = hp.x; hy = hp.y; hz = hp.z; ho = __float_as_int(hp.w);
+                    }
 #pragma unroll
                     for (int sl = 0; sl < PAIR_SLOTS; ++sl) {
                         const int k = k0 + sl * 32 + lane;
                         if (k0 + sl * 32 >= total) break;                 /* warp-uniform */
                         const bool ok = cg[sl] >= 0 && k > h;
-                        const float ddx = hp.x - cxs[sl], ddy = hp.y - cys[sl], ddz = hp.z - czs[sl];
+                        const float ddx = hx - cxs[sl], ddy = hy - cys[sl], ddz = hz - czs[sl];
                         const float d2 = __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, __fmul_rn(ddx, ddx)));
                         bool hit = ok && (d2 <= G.r2_hi);
                         ncand += ok ? 1u : 0u;
-                        if (hit) {
-                            if (d2 > G.r2_lo) hit = kd_within(hp.x, hp.y, hp.z, cxs[sl], cys[sl], czs[sl], P.r2);
-                            if (hit) {
-                                const bool h_first = ho < cor[sl];        /* atom_bgn = lower list index */
-                                const uint4 ab = h_first ? ha : cat[sl];
-                                const uint4 ae = h_first ? cat[sl] : ha;
-                                hit = rule_pair_survives(ab.x, (int)ab.y, (int)ab.z, (int)ab.w,
-                                                         ae.x, (int)ae.y, (int)ae.z, (int)ae.w, P.include_seq_adjacent);
-                            }
-                        }
+                        if (hit && d2 > G.r2_lo) hit = kd_within(hx, hy, hz, cxs[sl], cys[sl], czs[sl], P.r2);
                         const unsigned m = __ballot_sync(FULL, hit);
                         if (m) {
                             if (hit) {
-                                const bool h_first = ho < cor[sl];
+                                const bool h_first = ho < cor[sl];        /* atom_bgn = lower list index */
                                 const unsigned pos = (qhead + qcount + __popc(m & lt_mask)) & (PAIR_QCAP - 1);
                                 q[pos] = h_first ? make_uint2((unsigned)(hb + h), (unsigned)cg[sl])
                                                  : make_uint2((unsigned)cg[sl], (unsigned)(hb + h));
@@ -463,6 +501,19 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 2) k_pairs(PairArgs A, ArpRul
         if (ncand_total) atomicAdd(&A.meta->n_candidates, ncand_total);
         if (nonempty) atomicAdd(&A.meta->n_cells_nonempty, nonempty);
     }
+}
+
+/* K x K table of the float32 proximity thresholds (interactions.py:717-718, :760-768): NumPy narrows
+   the python-float sums to float32 before comparing with the float32 distance (NEP 50) */
+__global__ void k_radtab(int K, const double* __restrict__ vdw, const double* __restrict__ cov, double comp,
+                         float4* __restrict__ tab)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= K * K) return;
+    int a = t / K, b = t % K;
+    double sum_cov = d_add(cov[a], cov[b]);
+    double sum_vdw = d_add(vdw[a], vdw[b]);
+    tab[t] = make_float4((float)sum_cov, (float)sum_vdw, (float)d_add(sum_vdw, comp), 0.f);
 }
 
 /* ---- host side ------------------------------------------------------------------------------- */
@@ -503,7 +554,7 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
     ARP_CUDA(c, cudaMemsetAsync(z, 0, c->zero_bytes, st));
     if (N > 0) {
         unsigned blocks = (unsigned)((N + 255) / 256);
-        k_bbox<<<blocks, 256, 0, st>>>(c->xyz.as<float>(), so, S, N, bbox);
+        k_bbox<<<(unsigned)((N + 1023) / 1024), 256, 0, st>>>(c->xyz.as<float>(), so, S, N, bbox);
         ARP_LAUNCHED(c);
         k_geom<<<1, 256, 0, st>>>(bbox, so, S, N, c->params.interacting_cutoff, c->geom.as<StructGeom>(), meta);
         ARP_LAUNCHED(c);
@@ -525,6 +576,18 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         A.pos4 = c->pos4.as<float4>(); A.att4 = c->att4.as<uint4>(); A.cell_start = c->cell_start.as<int>();
         A.geom = c->geom.as<StructGeom>(); A.meta = meta; A.out = c->out.as<arp_pair>(); A.out_cap = c->out_cap;
         A.side.vdw = c->vdw.as<double>(); A.side.cov = c->cov.as<double>();
+        A.side.K = c->K;
+        A.side.radtab = nullptr;
+        if (c->K <= 64) {                   /* larger tables stop being cache resident: compute on the fly */
+            if (!c->radtab_valid) {
+                ARP_TRY(dbuf_reserve(c, c->radtab, sizeof(float4) * (size_t)c->K * c->K));
+                k_radtab<<<(unsigned)((c->K * c->K + 127) / 128), 128, 0, st>>>(c->K, c->vdw.as<double>(), c->cov.as<double>(),
+                                                                               c->params.vdw_comp, c->radtab.as<float4>());
+                ARP_LAUNCHED(c);
+                c->radtab_valid = 1;
+            }
+            A.side.radtab = c->radtab.as<float4>();
+        }
         A.side.bond_off = c->has_bonds ? c->bond_off.as<int32_t>() : nullptr;
         A.side.bond_nbr = c->has_bonds ? c->bond_nbr.as<int32_t>() : nullptr;
         A.side.h_off = c->has_h ? c->h_off.as<int32_t>() : nullptr;

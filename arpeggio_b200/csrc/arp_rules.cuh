@@ -3,9 +3,9 @@
  *
  * Everything here is a pure function of the two atoms' records and of the side arrays
  * (hydrogens, bonds, halogen neighbours) addressed by ORIGINAL atom index.  The code is
- * __host__ __device__ so that tests/ can also compile it for the host (tests/emu/) and
- * check the rule logic in the GPU-less build container; the product only ever runs it
- * inside the CUDA kernels of arp_pairs.cu.
+ * __host__ __device__ so that tests/emu can also compile it for the host and check the rule
+ * logic in the GPU-less build container; the product only ever runs it inside the CUDA
+ * kernels of arp_pairs.cu.
  *
  * Arithmetic contract (measured against NumPy 2.3 / OpenBLAS):
  *   - float32 distance (interactions.py:745): component differences rounded to float32,
@@ -17,22 +17,33 @@
  *     comparisons of the cosine with the host-computed images in arp_params (cos_*).
  * The translation unit must be compiled with -fmad=false (no implicit contraction);
  * every fused multiply-add below is explicit.
+ *
+ * Speed without changing a bit: the expensive exactly-rounded chains (float64 sqrt and six
+ * divisions per hydrogen) sit behind cheap certainly-true / certainly-false screens
+ *   - squared hydrogen distance against lim^2 (1 +- 4 ulp) before the float64 sqrt,
+ *   - a float32 estimate of the cosine against the threshold +- 2e-5 before get_angle's chain,
+ * and only the undecided sliver (and every NaN-prone degenerate geometry) runs the exact code,
+ * which is kept out of line so that the hot loop stays small.
  */
 #ifndef ARP_RULES_CUH
 #define ARP_RULES_CUH
 
 #include <stdint.h>
+#include <string.h>
 #include <math.h>
 
 #include "../../include/arpeggio_cuda.h"
 
 #if defined(__CUDACC__)
 #define ARP_HD __host__ __device__ __forceinline__
+#define ARP_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define ARP_HD static inline
+#define ARP_HD_NOINLINE static __attribute__((noinline))
+struct float4 { float x, y, z, w; };      /* host build of the rules (tests/emu) */
 #endif
 
-/* ---- packed per-atom word (sorted-order attribute record, word 0) -------------------
+/* ---- packed per-atom word (cell-sorted attribute record, word 0) ---------------------
  * bits 0..19  ARP_F_* as uploaded
  * bits 20..21 ARP_R_* of the atom's residue
  * bit  22     atom has at least one entry in the bond CSR
@@ -45,6 +56,8 @@
 struct ArpSide {               /* side arrays, original atom order (device pointers) */
     const double*   vdw;       /* [K] */
     const double*   cov;       /* [K] */
+    const float4*   radtab;    /* [K][K] (f32(cov_a+cov_b), f32(vdw_a+vdw_b), f32((vdw_a+vdw_b)+comp), -) or null */
+    int             K;
     const int32_t*  bond_off;  /* [N+1] or null */
     const int32_t*  bond_nbr;
     const int32_t*  h_off;     /* [N+1] or null */
@@ -54,7 +67,6 @@ struct ArpSide {               /* side arrays, original atom order (device point
 
 struct ArpRuleParams {         /* arp_params narrowed the way NumPy (NEP 50) narrows it */
     double r2;                 /* interacting_cutoff^2, double (Bio.PDB.kdtrees) */
-    float  r2_prefilter;       /* float32 upper bound used to skip the double test */
     double vdw_comp;
     double h_vdw;
     float  dist_max, hbond_polar, weak_polar, ionic, carbonyl, aromatic, hydrophobic, metal;
@@ -65,6 +77,35 @@ struct ArpRuleParams {         /* arp_params narrowed the way NumPy (NEP 50) nar
     /* what the comparisons give when get_angle() falls back to np.pi (utils.py:741-743) */
     int    pi_ge_hbond, pi_ge_weak_hbond, pi_in_cx, pi_ge_xbond;
 };
+
+/* arp_params -> ArpRuleParams (host) */
+static inline void arp_derive_rule_params(const arp_params* p, ArpRuleParams* r)
+{
+    const double pi = 3.141592653589793;      /* np.pi */
+    memset(r, 0, sizeof *r);
+    r->r2 = p->interacting_cutoff * p->interacting_cutoff;
+    r->vdw_comp = p->vdw_comp;
+    r->h_vdw = p->h_vdw;
+    r->dist_max = (float)p->dist_max;         /* NEP 50: np.float32 <op> python float compares in float32 */
+    r->hbond_polar = (float)p->hbond_polar_dist;
+    r->weak_polar = (float)p->weak_polar_dist;
+    r->ionic = (float)p->ionic_dist;
+    r->carbonyl = (float)p->carbonyl_dist;
+    r->aromatic = (float)p->aromatic_dist;
+    r->hydrophobic = (float)p->hydrophobic_dist;
+    r->metal = (float)p->metal_dist;
+    r->cos_hbond = p->cos_hbond;
+    r->cos_weak_hbond = p->cos_weak_hbond;
+    r->cos_cx_min = p->cos_cx_min;
+    r->cos_cx_max = p->cos_cx_max;
+    r->cos_xbond_f32 = p->cos_xbond_f32;
+    r->blas_fma = p->blas_fma;
+    r->include_seq_adjacent = p->include_sequence_adjacent;
+    r->pi_ge_hbond = pi >= p->hbond_angle;
+    r->pi_ge_weak_hbond = pi >= p->weak_hbond_angle;
+    r->pi_in_cx = p->cx_angle_min <= pi && pi <= p->cx_angle_max;
+    r->pi_ge_xbond = pi >= p->xbond_angle;
+}
 
 /* ---- exactly rounded primitives ------------------------------------------------------ */
 ARP_HD float f_sub(float a, float b) {
@@ -138,6 +179,13 @@ ARP_HD double d_sqrt(double a) {
 #endif
 }
 ARP_HD double d_fma(double a, double b, double c) { return fma(a, b, c); }
+ARP_HD float fast_rsqrt(float a) {
+#ifdef __CUDA_ARCH__
+    return rsqrtf(a);
+#else
+    return 1.0f / sqrtf(a);
+#endif
+}
 
 /* ---- NumPy / OpenBLAS models ------------------------------------------------------------ */
 
@@ -181,13 +229,16 @@ ARP_HD float np_dist_f32(float ax, float ay, float az, float bx, float by, float
     return np_norm3_f32(f_sub(ax, bx), f_sub(ay, by), f_sub(az, bz));
 }
 
-/* ---- cosines of utils.get_angle in its three dtype flows ------------------------------ */
+/* arccos(c) is NaN (-> np.pi, utils.py:741-743) exactly when c is NaN or outside [-1, 1] */
+ARP_HD bool acos_is_nan(double c) { return !(c >= -1.0 && c <= 1.0); }
+ARP_HD bool acos_is_nan_f(float c) { return !(c >= -1.0f && c <= 1.0f); }
 
-/* a float32, b float64 (hydrogen), c float32: float64 throughout (utils.py:90, :113) */
-ARP_HD double cos_angle_fdf(const float* a, const double* b, const float* c)
+/* ---- cosines of utils.get_angle in its three dtype flows (exact chains, out of line) ---- */
+
+/* v1 = a - b, v2 = c - b already formed in float64 (a, c float32, b = hydrogen float64):
+   float64 throughout (utils.py:90, :113) */
+ARP_HD_NOINLINE double cos_angle_dd_exact(double v1x, double v1y, double v1z, double v2x, double v2y, double v2z)
 {
-    double v1x = d_sub((double)a[0], b[0]), v1y = d_sub((double)a[1], b[1]), v1z = d_sub((double)a[2], b[2]);
-    double v2x = d_sub((double)c[0], b[0]), v2y = d_sub((double)c[1], b[1]), v2z = d_sub((double)c[2], b[2]);
     double m1 = d_sqrt(d_add(d_add(d_mul(v1x, v1x), d_mul(v1y, v1y)), d_mul(v1z, v1z)));
     double m2 = d_sqrt(d_add(d_add(d_mul(v2x, v2x), d_mul(v2y, v2y)), d_mul(v2z, v2z)));
     double n1x = d_div(v1x, m1), n1y = d_div(v1y, m1), n1z = d_div(v1z, m1);
@@ -196,7 +247,7 @@ ARP_HD double cos_angle_fdf(const float* a, const double* b, const float* c)
 }
 
 /* a, b float32 (v1 stays float32), c float64 (v2 float64): utils.py:151 */
-ARP_HD double cos_angle_ffd(const float* a, const float* b, const double* c)
+ARP_HD_NOINLINE double cos_angle_ffd(const float* a, const float* b, const double* c)
 {
     float v1x = f_sub(a[0], b[0]), v1y = f_sub(a[1], b[1]), v1z = f_sub(a[2], b[2]);
     double v2x = d_sub(c[0], (double)b[0]), v2y = d_sub(c[1], (double)b[1]), v2z = d_sub(c[2], (double)b[2]);
@@ -208,10 +259,10 @@ ARP_HD double cos_angle_ffd(const float* a, const float* b, const double* c)
 }
 
 /* all float32 (utils.py:174) */
-ARP_HD float cos_angle_fff(const float* a, const float* b, const float* c)
+ARP_HD_NOINLINE float cos_angle_fff(const float* a, float bx, float by, float bz, float cx, float cy, float cz)
 {
-    float v1x = f_sub(a[0], b[0]), v1y = f_sub(a[1], b[1]), v1z = f_sub(a[2], b[2]);
-    float v2x = f_sub(c[0], b[0]), v2y = f_sub(c[1], b[1]), v2z = f_sub(c[2], b[2]);
+    float v1x = f_sub(a[0], bx), v1y = f_sub(a[1], by), v1z = f_sub(a[2], bz);
+    float v2x = f_sub(cx, bx), v2y = f_sub(cy, by), v2z = f_sub(cz, bz);
     float m1 = f_sqrt(f_add(f_add(f_mul(v1x, v1x), f_mul(v1y, v1y)), f_mul(v1z, v1z)));
     float m2 = f_sqrt(f_add(f_add(f_mul(v2x, v2x), f_mul(v2y, v2y)), f_mul(v2z, v2z)));
     float n1x = f_div(v1x, m1), n1y = f_div(v1y, m1), n1z = f_div(v1z, m1);
@@ -219,44 +270,82 @@ ARP_HD float cos_angle_fff(const float* a, const float* b, const float* c)
     return f_add(f_add(f_mul(n1x, n2x), f_mul(n1y, n2y)), f_mul(n1z, n2z));
 }
 
-/* arccos(c) is NaN (-> np.pi, utils.py:741-743) exactly when c is NaN or outside [-1, 1] */
-ARP_HD bool acos_is_nan(double c) { return !(c >= -1.0 && c <= 1.0); }
-ARP_HD bool acos_is_nan_f(float c) { return !(c >= -1.0f && c <= 1.0f); }
-
 /* ---- predicates ---------------------------------------------------------------------------- */
 
-/* utils.is_hbond (utils.py:73-93) / utils.is_weak_hbond (utils.py:96-116) */
-ARP_HD int rule_is_hbond(const ArpSide& S, const ArpRuleParams& P, int donor, const float* dc, const float* ac,
-                         double vdw_acc, double cos_thr, int pi_ge)
+#define ARP_HB_NEED_H 1        /* utils.is_hbond      threshold (utils.py:73-93)  */
+#define ARP_HB_NEED_W 2        /* utils.is_weak_hbond threshold (utils.py:96-116) */
+
+/*
+ * One pass over the donor's hydrogens for utils.is_hbond and/or utils.is_weak_hbond: the two
+ * differ only in the angle threshold, so hydrogen distance and cosine are shared.
+ * Returns the subset of `need` whose predicate is true.
+ */
+ARP_HD int rule_hbond_scan(const ArpSide& S, const ArpRuleParams& P, int donor, float dcx, float dcy, float dcz,
+                           float acx, float acy, float acz, double vdw_acc, int need)
 {
     if (!S.h_off) return 0;
-    int h0 = S.h_off[donor], h1 = S.h_off[donor + 1];
+    const int h0 = S.h_off[donor], h1 = S.h_off[donor + 1];
     if (h0 == h1) return 0;
-    double lim = d_add(d_add(P.h_vdw, vdw_acc), P.vdw_comp);                       /* utils.py:89 */
+    const double lim = d_add(d_add(P.h_vdw, vdw_acc), P.vdw_comp);                  /* utils.py:89 */
+    const double lim2 = lim * lim;
+    const double lim2_lo = lim2 * (1.0 - 1e-15), lim2_hi = lim2 * (1.0 + 1e-15);
+    int got = 0;
+#pragma unroll 1
     for (int k = h0; k < h1; ++k) {
-        const double* h = S.h_xyz + 3 * (size_t)k;
-        double vx = d_sub(h[0], (double)ac[0]), vy = d_sub(h[1], (double)ac[1]), vz = d_sub(h[2], (double)ac[2]);
-        double h_dist = np_norm3_f64(vx, vy, vz, P.blas_fma);                      /* utils.py:87 */
-        if (h_dist <= lim) {
-            double c = cos_angle_fdf(dc, h, ac);
-            if (acos_is_nan(c) ? pi_ge : (c <= cos_thr)) return 1;                 /* utils.py:90 */
+        const double hx = S.h_xyz[3 * (size_t)k], hy = S.h_xyz[3 * (size_t)k + 1], hz = S.h_xyz[3 * (size_t)k + 2];
+        /* h_dist = np.linalg.norm(h_coord - acceptor.coord) (utils.py:87) */
+        const double ux = d_sub(hx, (double)acx), uy = d_sub(hy, (double)acy), uz = d_sub(hz, (double)acz);
+        const double s = np_dot3_f64(ux, uy, uz, ux, uy, uz, P.blas_fma);
+        bool within;
+        if (s < lim2_lo) within = true;
+        else if (s > lim2_hi) within = false;
+        else within = d_sqrt(s) <= lim;                     /* also takes NaN */
+        if (!within) continue;
+        /* get_angle(donor.coord, h_coord, acceptor.coord) (utils.py:90): v1 = donor - h, v2 = acceptor - h */
+        const double v1x = d_sub((double)dcx, hx), v1y = d_sub((double)dcy, hy), v1z = d_sub((double)dcz, hz);
+        const double v2x = d_sub((double)acx, hx), v2y = d_sub((double)acy, hy), v2z = d_sub((double)acz, hz);
+        /* float32 estimate of the cosine; |estimate - exact chain| < 2e-6 for non-degenerate vectors */
+        const float q1 = (float)(v1x * v1x + v1y * v1y + v1z * v1z);
+        const float q2 = (float)(v2x * v2x + v2y * v2y + v2z * v2z);
+        const float dt = (float)(v1x * v2x + v1y * v2y + v1z * v2z);
+        const float ce = dt * fast_rsqrt(q1 * q2);
+        const float tol = 2e-5f;
+        int sure_true = 0, sure_false = 0;
+        if (q1 > 1e-12f && q2 > 1e-12f && q1 < 1e12f && q2 < 1e12f && ce > -0.9999f && ce < 0.9999f) {
+            if (need & ARP_HB_NEED_H) {
+                if (ce < (float)P.cos_hbond - tol) sure_true |= ARP_HB_NEED_H;
+                else if (ce > (float)P.cos_hbond + tol) sure_false |= ARP_HB_NEED_H;
+            }
+            if (need & ARP_HB_NEED_W) {
+                if (ce < (float)P.cos_weak_hbond - tol) sure_true |= ARP_HB_NEED_W;
+                else if (ce > (float)P.cos_weak_hbond + tol) sure_false |= ARP_HB_NEED_W;
+            }
         }
+        got |= sure_true;
+        if ((need & ~got & ~sure_false) != 0) {              /* something still undecided for this hydrogen */
+            const double c = cos_angle_dd_exact(v1x, v1y, v1z, v2x, v2y, v2z);
+            const bool nan = acos_is_nan(c);
+            if ((need & ARP_HB_NEED_H) && (nan ? P.pi_ge_hbond : (c <= P.cos_hbond))) got |= ARP_HB_NEED_H;
+            if ((need & ARP_HB_NEED_W) && (nan ? P.pi_ge_weak_hbond : (c <= P.cos_weak_hbond))) got |= ARP_HB_NEED_W;
+        }
+        if ((need & ~got) == 0) break;                       /* the reference returns at the first success */
     }
-    return 0;
+    return got & need;
 }
 
 /* utils.is_halogen_weak_hbond (utils.py:119-155) */
-ARP_HD int rule_is_halogen_weak_hbond(const ArpSide& S, const ArpRuleParams& P, int donor, int halogen,
-                                      const float* hc, uint32_t feat_hal, double vdw_hal)
+ARP_HD_NOINLINE int rule_is_halogen_weak_hbond(const ArpSide& S, const ArpRuleParams& P, int donor, int halogen,
+                                               float hcx, float hcy, float hcz, uint32_t feat_hal, double vdw_hal)
 {
     if (!(feat_hal & ARP_F_HAS_XNBR) || !S.xnbr || !S.h_off) return 0;            /* utils.py:139-141 */
     int h0 = S.h_off[donor], h1 = S.h_off[donor + 1];
     if (h0 == h1) return 0;
     const float* nb = S.xnbr + 3 * (size_t)halogen;
+    const float hc[3] = { hcx, hcy, hcz };
     double lim = d_add(d_add(P.h_vdw, vdw_hal), P.vdw_comp);                       /* utils.py:149 */
     for (int k = h0; k < h1; ++k) {
         const double* h = S.h_xyz + 3 * (size_t)k;
-        double vx = d_sub((double)hc[0], h[0]), vy = d_sub((double)hc[1], h[1]), vz = d_sub((double)hc[2], h[2]);
+        double vx = d_sub((double)hcx, h[0]), vy = d_sub((double)hcy, h[1]), vz = d_sub((double)hcz, h[2]);
         double h_dist = np_norm3_f64(vx, vy, vz, P.blas_fma);                      /* utils.py:147 */
         if (h_dist <= lim) {
             double c = cos_angle_ffd(nb, hc, h);
@@ -270,11 +359,11 @@ ARP_HD int rule_is_halogen_weak_hbond(const ArpSide& S, const ArpRuleParams& P, 
 
 /* utils.is_xbond (utils.py:158-179); a donor without single-bond neighbour makes the reference
    raise (utils.py:173): reported through the fault bit, like the oracle */
-ARP_HD int rule_is_xbond(const ArpSide& S, const ArpRuleParams& P, int donor, const float* dc, const float* ac,
-                         uint32_t feat_donor, uint32_t* fault)
+ARP_HD_NOINLINE int rule_is_xbond(const ArpSide& S, const ArpRuleParams& P, int donor, float dcx, float dcy, float dcz,
+                                  float acx, float acy, float acz, uint32_t feat_donor, uint32_t* fault)
 {
     if (!(feat_donor & ARP_F_HAS_XNBR) || !S.xnbr) { *fault |= ARPK_FAULT_XBOND_NO_NBR; return 0; }
-    float c = cos_angle_fff(S.xnbr + 3 * (size_t)donor, dc, ac);
+    float c = cos_angle_fff(S.xnbr + 3 * (size_t)donor, dcx, dcy, dcz, acx, acy, acz);
     if (acos_is_nan_f(c)) return P.pi_ge_xbond;
     return c <= P.cos_xbond_f32;
 }
@@ -323,13 +412,17 @@ ARP_HD void rule_classify(const ArpSide& S, const ArpRuleParams& P, int b, int e
                           float bx, float by, float bz, float ex, float ey, float ez,
                           uint32_t fb, uint32_t fe, uint32_t* mask_out, float* dist_out)
 {
-    const float pb[3] = { bx, by, bz }, pe[3] = { ex, ey, ez };
-    const double vdw_b = S.vdw[fb >> ARPK_RAD_SHIFT], vdw_e = S.vdw[fe >> ARPK_RAD_SHIFT];
-    const double cov_b = S.cov[fb >> ARPK_RAD_SHIFT], cov_e = S.cov[fe >> ARPK_RAD_SHIFT];
-    const double sum_cov = d_add(cov_b, cov_e);                                    /* :717 */
-    const double sum_vdw = d_add(vdw_b, vdw_e);                                    /* :718 */
+    const uint32_t kb = fb >> ARPK_RAD_SHIFT, ke = fe >> ARPK_RAD_SHIFT;
+    float t_cov, t_vdw, vdwc;
+    if (S.radtab) {
+        const float4 t = S.radtab[kb * (uint32_t)S.K + ke];
+        t_cov = t.x; t_vdw = t.y; vdwc = t.z;
+    } else {
+        const double sum_cov = d_add(S.cov[kb], S.cov[ke]);                        /* :717 */
+        const double sum_vdw = d_add(S.vdw[kb], S.vdw[ke]);                        /* :718 */
+        t_cov = (float)sum_cov; t_vdw = (float)sum_vdw; vdwc = (float)d_add(sum_vdw, P.vdw_comp);
+    }
     const float d = np_dist_f32(bx, by, bz, ex, ey, ez);                           /* :745 */
-    const float vdwc = (float)d_add(sum_vdw, P.vdw_comp);
     uint32_t m = 0, fault = 0;
 
     bool bonded = false;                                                           /* :750-754 */
@@ -337,11 +430,11 @@ ARP_HD void rule_classify(const ArpSide& S, const ArpRuleParams& P, int b, int e
         for (int k = S.bond_off[b]; k < S.bond_off[b + 1]; ++k)
             if (S.bond_nbr[k] == e) { bonded = true; break; }
     }
-    if (bonded)                  m |= 1u << ARP_SIFT_COVALENT;                     /* :756-757 */
-    else if (d < (float)sum_cov) m |= 1u << ARP_SIFT_CLASH;                        /* :760 */
-    else if (d < (float)sum_vdw) m |= 1u << ARP_SIFT_VDW_CLASH;                    /* :764 */
-    else if (d <= vdwc)          m |= 1u << ARP_SIFT_VDW;                          /* :768 */
-    else                         m |= 1u << ARP_SIFT_PROXIMAL;                     /* :772 */
+    if (bonded)          m |= 1u << ARP_SIFT_COVALENT;                             /* :756-757 */
+    else if (d < t_cov)  m |= 1u << ARP_SIFT_CLASH;                                /* :760 */
+    else if (d < t_vdw)  m |= 1u << ARP_SIFT_VDW_CLASH;                            /* :764 */
+    else if (d <= vdwc)  m |= 1u << ARP_SIFT_VDW;                                  /* :768 */
+    else                 m |= 1u << ARP_SIFT_PROXIMAL;                             /* :772 */
 
     if (d <= P.metal) {                                                            /* :777-783 */
         if (((fb & ARP_F_HBOND_ACCEPTOR) && (fe & ARP_F_IS_METAL)) ||
@@ -349,42 +442,50 @@ ARP_HD void rule_classify(const ArpSide& S, const ArpRuleParams& P, int b, int e
     }
 
     if (!(m & (1u << ARP_SIFT_CLASH)) && d <= P.dist_max) {                        /* :786 */
-        /* hbond / polar :791-819 */
+        /* hbond / polar :791-819 -- which direction, if any, needs utils.is_hbond */
+        int need0 = 0, need1 = 0;        /* direction 0: donor = bgn, acceptor = end; 1: the reverse */
         if ((fb & ARP_F_IS_WATER) && d <= vdwc) {
             if (fe & (ARP_F_HBOND_ACCEPTOR | ARP_F_HBOND_DONOR)) m |= (1u << ARP_SIFT_HBOND) | (1u << ARP_SIFT_POLAR);
         } else if ((fe & ARP_F_IS_WATER) && d <= vdwc) {
             if (fb & (ARP_F_HBOND_ACCEPTOR | ARP_F_HBOND_DONOR)) m |= (1u << ARP_SIFT_HBOND) | (1u << ARP_SIFT_POLAR);
         } else if ((fb & ARP_F_HBOND_DONOR) && (fe & ARP_F_HBOND_ACCEPTOR)) {
-            if (rule_is_hbond(S, P, b, pb, pe, vdw_e, P.cos_hbond, P.pi_ge_hbond)) m |= 1u << ARP_SIFT_HBOND;
+            need0 |= ARP_HB_NEED_H;
             if (d <= P.hbond_polar) m |= 1u << ARP_SIFT_POLAR;
         } else if ((fe & ARP_F_HBOND_DONOR) && (fb & ARP_F_HBOND_ACCEPTOR)) {
-            if (rule_is_hbond(S, P, e, pe, pb, vdw_b, P.cos_hbond, P.pi_ge_hbond)) m |= 1u << ARP_SIFT_HBOND;
+            need1 |= ARP_HB_NEED_H;
             if (d <= P.hbond_polar) m |= 1u << ARP_SIFT_POLAR;
         }
-        /* weak hbond / weak polar: four independent ifs, each ASSIGNS SIFt[6] :857-886 */
-        int weak = 0; bool wp = false;
-        if ((fb & ARP_F_HBOND_ACCEPTOR) && (fe & ARP_F_WEAK_HBOND_DONOR)) {
-            weak = rule_is_hbond(S, P, e, pe, pb, vdw_b, P.cos_weak_hbond, P.pi_ge_weak_hbond); wp = true;
+        /* weak hbond / weak polar: four independent ifs, each ASSIGNS SIFt[6] (:857-886), so only the
+           last applicable one decides the bit; any applicable one enables weak polar */
+        const bool w1 = (fb & ARP_F_HBOND_ACCEPTOR) && (fe & ARP_F_WEAK_HBOND_DONOR);          /* is_weak_hbond(e, b) */
+        const bool w2 = (fb & ARP_F_WEAK_HBOND_DONOR) && (fe & ARP_F_HBOND_ACCEPTOR);          /* is_weak_hbond(b, e) */
+        const bool w3 = (fb & ARP_F_WEAK_HBOND_ACCEPTOR) && (fb & ARP_F_IS_HALOGEN) &&
+                        (fe & (ARP_F_HBOND_DONOR | ARP_F_WEAK_HBOND_DONOR));                   /* halogen b, donor e */
+        const bool w4 = (fe & ARP_F_WEAK_HBOND_ACCEPTOR) && (fe & ARP_F_IS_HALOGEN) &&
+                        (fb & (ARP_F_HBOND_DONOR | ARP_F_WEAK_HBOND_DONOR));                   /* halogen e, donor b */
+        int weak = 0;
+        if (w4)      weak = rule_is_halogen_weak_hbond(S, P, b, e, ex, ey, ez, fe, S.vdw[ke]);
+        else if (w3) weak = rule_is_halogen_weak_hbond(S, P, e, b, bx, by, bz, fb, S.vdw[kb]);
+        else if (w2) need0 |= ARP_HB_NEED_W;
+        else if (w1) need1 |= ARP_HB_NEED_W;
+        if ((w1 || w2 || w3 || w4) && d <= P.weak_polar) m |= 1u << ARP_SIFT_WEAK_POLAR;
+        /* one shared pass per direction */
+        int got = 0;
+#pragma unroll 1
+        for (int dir = 0; dir < 2; ++dir) {
+            const int need = dir ? need1 : need0;
+            if (!need) continue;
+            if (dir == 0) got |= rule_hbond_scan(S, P, b, bx, by, bz, ex, ey, ez, S.vdw[ke], need);
+            else          got |= rule_hbond_scan(S, P, e, ex, ey, ez, bx, by, bz, S.vdw[kb], need);
         }
-        if ((fb & ARP_F_WEAK_HBOND_DONOR) && (fe & ARP_F_HBOND_ACCEPTOR)) {
-            weak = rule_is_hbond(S, P, b, pb, pe, vdw_e, P.cos_weak_hbond, P.pi_ge_weak_hbond); wp = true;
-        }
-        if ((fb & ARP_F_WEAK_HBOND_ACCEPTOR) && (fb & ARP_F_IS_HALOGEN) &&
-            (fe & (ARP_F_HBOND_DONOR | ARP_F_WEAK_HBOND_DONOR))) {
-            weak = rule_is_halogen_weak_hbond(S, P, e, b, pb, fb, vdw_b); wp = true;
-        }
-        if ((fe & ARP_F_WEAK_HBOND_ACCEPTOR) && (fe & ARP_F_IS_HALOGEN) &&
-            (fb & (ARP_F_HBOND_DONOR | ARP_F_WEAK_HBOND_DONOR))) {
-            weak = rule_is_halogen_weak_hbond(S, P, b, e, pe, fe, vdw_e); wp = true;
-        }
-        if (weak) m |= 1u << ARP_SIFT_WEAK_HBOND;
-        if (wp && d <= P.weak_polar) m |= 1u << ARP_SIFT_WEAK_POLAR;
+        if (got & ARP_HB_NEED_H) m |= 1u << ARP_SIFT_HBOND;
+        if ((got & ARP_HB_NEED_W) || weak) m |= 1u << ARP_SIFT_WEAK_HBOND;
         /* xbond :889-895 */
         if (d <= vdwc) {
             if ((fb & ARP_F_XBOND_DONOR) && (fe & ARP_F_XBOND_ACCEPTOR)) {
-                if (rule_is_xbond(S, P, b, pb, pe, fb, &fault)) m |= 1u << ARP_SIFT_XBOND;
+                if (rule_is_xbond(S, P, b, bx, by, bz, ex, ey, ez, fb, &fault)) m |= 1u << ARP_SIFT_XBOND;
             } else if ((fe & ARP_F_XBOND_DONOR) && (fb & ARP_F_XBOND_ACCEPTOR)) {
-                if (rule_is_xbond(S, P, e, pe, pb, fe, &fault)) m |= 1u << ARP_SIFT_XBOND;
+                if (rule_is_xbond(S, P, e, ex, ey, ez, bx, by, bz, fe, &fault)) m |= 1u << ARP_SIFT_XBOND;
             }
         }
         /* ionic :898-904, carbonyl :907-913, aromatic :916-917, hydrophobic :920-921 */

@@ -205,7 +205,7 @@ void arp_destroy(arp_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     DBuf* bufs[] = { &c->xyz, &c->feat, &c->res_id, &c->rad_class, &c->vdw, &c->cov, &c->res_prev, &c->res_next,
                      &c->res_flags, &c->bond_off, &c->bond_nbr, &c->h_off, &c->h_xyz, &c->xnbr, &c->struct_off,
-                     &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->out,
+                     &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->out, &c->hits,
                      &c->radtab, &c->sort_tmp, &c->sort_out, &c->sort_zero, &c->sort_off, &c->within, &c->flush };
     for (DBuf* b : bufs) dbuf_free(*b);
     arp_planes_release(c);
@@ -314,6 +314,7 @@ static int pairs_out_reserve(arp_ctx* c, uint64_t records)
     if (records <= c->out_cap && c->out.p) return ARP_OK;
     ARP_TRY(dbuf_reserve(c, c->out, (size_t)records * sizeof(arp_pair)));
     c->out_cap = c->out.cap / sizeof(arp_pair);
+    ARP_TRY(dbuf_reserve(c, c->hits, (size_t)c->out_cap * sizeof(uint2)));
     return ARP_OK;
 }
 
@@ -327,10 +328,11 @@ static void fill_stats(arp_ctx* c, int with_events)
     s.input_bytes = c->input_bytes;
     s.output_bytes = s.n_pairs * sizeof(arp_pair);
     if (with_events) {
-        float a = 0.f, b = 0.f;
+        float a = 0.f, b = 0.f, d = 0.f;
         cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
         cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
-        s.ms_grid = a; s.ms_search = b; s.ms_classify = 0.f; s.ms_total = a + b;
+        cudaEventElapsedTime(&d, c->ev[2], c->ev[3]);
+        s.ms_grid = a; s.ms_search = b; s.ms_classify = d; s.ms_total = a + b + d;
     }
 }
 
@@ -434,21 +436,23 @@ int arp_timing_iters(arp_ctx* c, int iters, int flush_l2, float* ms_per_iter)
     if (!c->pairs_valid) ARP_TRY(arp_pairs_run(c, nullptr));      /* sizes the record buffer */
     const size_t flush_bytes = (size_t)384 << 20;
     if (flush_l2) ARP_TRY(dbuf_reserve(c, c->flush, flush_bytes));
-    double tot = 0.0, grid = 0.0, search = 0.0;
+    double tot = 0.0, grid = 0.0, search = 0.0, classify = 0.0;
     for (int it = 0; it < iters; ++it) {
         if (flush_l2) ARP_CUDA(c, cudaMemsetAsync(c->flush.p, it & 0xff, flush_bytes, c->stream));
         ARP_TRY(arp_pairs_enqueue(c, 1));
         ARP_CUDA(c, cudaStreamSynchronize(c->stream));
         ARP_REQUIRE(c, c->h_meta->n_pairs == c->n_pairs, ARP_E_CUDA, "record count changed between iterations");
-        float a = 0.f, b = 0.f;
+        float a = 0.f, b = 0.f, d = 0.f, w = 0.f;
         ARP_CUDA(c, cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
         ARP_CUDA(c, cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
-        grid += a; search += b; tot += a + b;
+        ARP_CUDA(c, cudaEventElapsedTime(&d, c->ev[2], c->ev[3]));
+        ARP_CUDA(c, cudaEventElapsedTime(&w, c->ev[0], c->ev[3]));
+        grid += a; search += b; classify += d; tot += w;
     }
     fill_stats(c, 0);
     c->stats.ms_grid = (float)(grid / iters);
     c->stats.ms_search = (float)(search / iters);
-    c->stats.ms_classify = 0.f;
+    c->stats.ms_classify = (float)(classify / iters);
     c->stats.ms_total = (float)(tot / iters);
     c->sorted_valid = 0;
     if (ms_per_iter) *ms_per_iter = (float)(tot / iters);

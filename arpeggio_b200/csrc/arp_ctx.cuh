@@ -89,6 +89,7 @@ struct arp_ctx {
 
     /* output stream */
     DBuf out;                     /* arp_pair records */
+    DBuf hits;                    /* uint2 hit list of the search kernel, same capacity as out */
     uint64_t out_cap = 0;         /* records */
     uint64_t n_pairs = 0;
     int pairs_valid = 0;

@@ -13,13 +13,14 @@
  *   k_scan     exclusive scan of the cell counts (single pass, decoupled look-back)
  *   k_scatter  atoms into cell order as two 16-byte records: pos4 (x, y, z, original index)
  *              and att4 (packed feature word, residue, residue's prev/next link)
- *   k_pairs    one warp per home cell (dynamic tickets): the 13 forward neighbour cells + the
+ *   k_search   one warp per home cell (dynamic tickets): the 13 forward neighbour cells + the
  *              home cell are 5 contiguous runs of the cell-sorted array; lane = candidate,
  *              home atoms broadcast; float32 prefilter, exact double test inside the band;
- *              filters; ballot compaction into a per-warp shared-memory queue; every 128
- *              queued hits the warp classifies 32 hits per round (fused distance + angle +
- *              bitmask rules, arp_rules.cuh) and stores 16-byte records coalesced behind one
- *              cursor atomic.
+ *              ballot compaction into a per-warp shared-memory ring; dense filters; survivors
+ *              appended to the hit list (8 B per pair, L2 resident) behind one cursor atomic
+ *   k_classify one thread per hit: fused float32 distance + 15-bit mask rules (arp_rules.cuh),
+ *              hydrogen scans and rare exact predicates compacted and run densely, records
+ *              staged in shared memory and stored tile by tile with cp.async.bulk
  */
 #include "arp_ctx.cuh"
 
@@ -318,29 +319,34 @@ __global__ void __launch_bounds__(256) k_scatter(int N, const float* __restrict_
     att4[dst] = make_uint4(w, (uint32_t)r, (uint32_t)res_prev[r], (uint32_t)res_next[r]);
 }
 
-/* ---- k_pairs ---------------------------------------------------------------------------------- */
-#define PAIR_WARPS   8
-#define PAIR_SLOTS   4                      /* candidates held per lane */
-#define PAIR_CHUNK   (32 * PAIR_SLOTS)
-#define PAIR_QCAP    256                    /* ring capacity per warp (power of two) */
-#define PAIR_DRAIN   128
-#define PAIR_CELLS_PER_TICKET 4
+/* ---- k_search ---------------------------------------------------------------------------------
+ * Neighbour search + the reference's `continue` filters.  One warp per home cell (dynamic tickets of
+ * SEARCH_CELLS cells): the home cell and its 13 forward neighbours are 5 contiguous runs of the
+ * cell-sorted array; lane = candidate (held in registers), home atoms broadcast by shuffle; float32
+ * prefilter with the exact double test of Bio.PDB.kdtrees inside the band; ballot compaction into a
+ * per-warp shared-memory ring.  Every 128 queued hits the warp orients (bgn = lower list index) and
+ * filters them 32 at a time and appends the survivors to the global hit list behind one cursor atomic.
+ * The kernel is small on purpose (no rule code): 4 CTAs of 8 warps per SM hide the load latency.   */
+#define SEARCH_WARPS  8
+#define SEARCH_SLOTS  4                     /* candidates held per lane */
+#define SEARCH_CHUNK  (32 * SEARCH_SLOTS)
+#define SEARCH_QCAP   256                   /* ring capacity per warp (power of two) */
+#define SEARCH_DRAIN  128
+#define SEARCH_CELLS  4                     /* cells per ticket; 8 lanes describe one cell's runs */
 
-struct PairArgs {
+struct SearchArgs {
     const float4* pos4;
     const uint4*  att4;
     const int*    cell_start;
     const StructGeom* geom;
     RunMeta*      meta;
-    arp_pair*     out;
-    unsigned long long out_cap;
-    ArpSide       side;
+    uint2*        hits;                     /* (bgn, end) cell-sorted indices of the surviving pairs */
+    unsigned long long hit_cap;
+    double        r2;
+    int           include_seq_adjacent;
 };
 
-/* One batch of queued distance hits: (1) the reference's `continue` filters, 32 hits per round, survivors
-   compacted in place; (2) one cursor atomic for the survivors; (3) classifier + coalesced 16-byte stores. */
-__device__ __forceinline__ void pairs_drain(const PairArgs& A, const ArpRuleParams& P, uint2* q,
-                                            unsigned head, unsigned n, int lane)
+__device__ __forceinline__ void search_drain(const SearchArgs& A, uint2* q, unsigned head, unsigned n, int lane)
 {
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned ns = 0;
@@ -349,13 +355,15 @@ __device__ __forceinline__ void pairs_drain(const PairArgs& A, const ArpRulePara
         bool keep = false;
         uint2 e = make_uint2(0, 0);
         if (idx < n) {
-            e = q[(head + idx) & (PAIR_QCAP - 1)];
+            e = q[(head + idx) & (SEARCH_QCAP - 1)];
+            const int oa = __float_as_int(A.pos4[e.x].w), ob = __float_as_int(A.pos4[e.y].w);
+            if (ob < oa) { unsigned t = e.x; e.x = e.y; e.y = t; }                 /* atom_bgn = lower list index */
             const uint4 ab = A.att4[e.x], ae = A.att4[e.y];
             keep = rule_pair_survives(ab.x, (int)ab.y, (int)ab.z, (int)ab.w, ae.x, (int)ae.y, (int)ae.z, (int)ae.w,
-                                      P.include_seq_adjacent);
+                                      A.include_seq_adjacent);
         }
         const unsigned m = __ballot_sync(FULL, keep);
-        if (keep) q[(head + ns + __popc(m & lt_mask)) & (PAIR_QCAP - 1)] = e;     /* ns <= r: never ahead of the reads */
+        if (keep) q[(head + ns + __popc(m & lt_mask)) & (SEARCH_QCAP - 1)] = e;   /* ns <= r: never ahead of the reads */
         ns += __popc(m);
     }
     if (ns == 0) return;
@@ -365,142 +373,291 @@ __device__ __forceinline__ void pairs_drain(const PairArgs& A, const ArpRulePara
     base = __shfl_sync(FULL, base, 0);
     for (unsigned r = 0; r < ns; r += 32) {
         const unsigned idx = r + lane;
-        if (idx < ns) {
-            const uint2 e = q[(head + idx) & (PAIR_QCAP - 1)];
-            const float4 pb = A.pos4[e.x], pe = A.pos4[e.y];
-            const uint32_t fb = A.att4[e.x].x, fe = A.att4[e.y].x;
-            uint32_t mask; float dist;
-            const int ib = __float_as_int(pb.w), ie = __float_as_int(pe.w);
-            rule_classify(A.side, P, ib, ie, pb.x, pb.y, pb.z, pe.x, pe.y, pe.z, fb, fe, &mask, &dist);
-            const unsigned long long o = base + idx;
-            if (o < A.out_cap) reinterpret_cast<int4*>(A.out)[o] = make_int4(ib, ie, (int)mask, __float_as_int(dist));
-        }
+        if (idx < ns && base + idx < A.hit_cap) A.hits[base + idx] = q[(head + idx) & (SEARCH_QCAP - 1)];
     }
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(PAIR_WARPS * 32, 2) k_pairs(PairArgs A, ArpRuleParams P)
+__global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) k_search(SearchArgs A)
 {
-    __shared__ uint2 s_queue[PAIR_WARPS][PAIR_QCAP];
+    __shared__ uint2 s_queue[SEARCH_WARPS][SEARCH_QCAP];
+    __shared__ int2  s_runs[SEARCH_WARPS][SEARCH_CELLS][8];      /* per cell: 5 x (first index, prefix); [5] = (total, nh); [6] = band */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint2* q = s_queue[warp];
     unsigned qhead = 0, qcount = 0;
-    unsigned ncand = 0;
-    unsigned long long ncand_total = 0;
+    unsigned long long ncand = 0;
     unsigned nonempty = 0;
     const unsigned lt_mask = (1u << lane) - 1u;
 
     const int n_cells = (int)A.meta->n_cells;
-    int s = 0;
-    StructGeom G = A.geom[0];
-    int s_end = G.cell_base + G.ncell;
+    int s = 0;                                  /* warp-uniform: structure of the ticket's first cell */
+    int s_end = A.geom[0].cell_base + A.geom[0].ncell;
 
     for (;;) {
         int t = 0;
         if (lane == 0) t = (int)atomicAdd(&A.meta->ticket[1], 1u);
         t = __shfl_sync(FULL, t, 0);
-        long long c0l = (long long)t * PAIR_CELLS_PER_TICKET;
+        const long long c0l = (long long)t * SEARCH_CELLS;
         if (c0l >= n_cells) break;
-        int c0 = (int)c0l;
-        int c1 = min(c0 + PAIR_CELLS_PER_TICKET, n_cells);
-        for (int c = c0; c < c1; ++c) {
-            const int hb = A.cell_start[c];
-            const int nh = A.cell_start[c + 1] - hb;
-            if (nh == 0) continue;
-            ++nonempty;
-            while (c >= s_end) { ++s; G = A.geom[s]; s_end = G.cell_base + G.ncell; }
-            /* the five runs of the half stencil, lanes 0..4 */
-            const int lc = c - G.cell_base;
-            const int cx = lc % G.dx, t2 = lc / G.dx, cy = t2 % G.dy, cz = t2 / G.dy;
-            int rbeg = 0, rlen = 0;
-            if (lane < 5) {
-                int y = cy + (lane == 1 || lane == 4 ? 1 : (lane == 2 ? -1 : 0));
-                int z = cz + (lane >= 2 ? 1 : 0);
-                int x0 = lane == 0 ? cx : max(cx - 1, 0);
-                int x1 = min(cx + 1, G.dx - 1);
-                if (y >= 0 && y < G.dy && z < G.dz) {
-                    int row = G.cell_base + (z * G.dy + y) * G.dx;
-                    rbeg = A.cell_start[row + x0];
-                    rlen = A.cell_start[row + x1 + 1] - rbeg;
+        const int c0 = (int)c0l;
+        while (c0 >= s_end) { ++s; s_end = A.geom[s].cell_base + A.geom[s].ncell; }   /* tickets ascend */
+        /* ---- run tables of the ticket's cells: lane = (cell q, run r) ---- */
+        {
+            const int qc = lane >> 3, r = lane & 7;
+            const int c = c0 + qc;
+            int rbeg = 0, rlen = 0, nh = 0;
+            float band_lo = 0.f, band_hi = 0.f;
+            if (c < n_cells) {
+                const StructGeom* gp = A.geom + s;
+                while (c >= gp->cell_base + gp->ncell) ++gp;                  /* the cell may lie in a later structure */
+                band_lo = gp->r2_lo; band_hi = gp->r2_hi;
+                if (r < 5) {
+                    const int gdx = gp->dx, gdy = gp->dy, gdz = gp->dz, gbase = gp->cell_base;
+                    const int lc = c - gbase;
+                    const int cx = lc % gdx, t2 = lc / gdx, cy = t2 % gdy, cz = t2 / gdy;
+                    const int y = cy + (r == 1 || r == 4 ? 1 : (r == 2 ? -1 : 0));
+                    const int z = cz + (r >= 2 ? 1 : 0);
+                    const int x0 = r == 0 ? cx : max(cx - 1, 0);
+                    const int x1 = min(cx + 1, gdx - 1);
+                    if (y >= 0 && y < gdy && z < gdz) {
+                        const int row = gbase + (z * gdy + y) * gdx;
+                        rbeg = A.cell_start[row + x0];
+                        rlen = A.cell_start[row + x1 + 1] - rbeg;
+                    }
+                    if (r == 0) nh = A.cell_start[c + 1] - rbeg;
                 }
             }
-            const int b0 = __shfl_sync(FULL, rbeg, 0), b1 = __shfl_sync(FULL, rbeg, 1), b2 = __shfl_sync(FULL, rbeg, 2),
-                      b3 = __shfl_sync(FULL, rbeg, 3), b4 = __shfl_sync(FULL, rbeg, 4);
-            const int p1 = __shfl_sync(FULL, rlen, 0);
-            const int p2 = p1 + __shfl_sync(FULL, rlen, 1);
-            const int p3 = p2 + __shfl_sync(FULL, rlen, 2);
-            const int p4 = p3 + __shfl_sync(FULL, rlen, 3);
-            const int total = p4 + __shfl_sync(FULL, rlen, 4);
-
-            for (int k0 = 0; k0 < total; k0 += PAIR_CHUNK) {
-                float cxs[PAIR_SLOTS], cys[PAIR_SLOTS], czs[PAIR_SLOTS];
-                int   cor[PAIR_SLOTS], cg[PAIR_SLOTS];
+            /* exclusive prefix of the run lengths inside each group of 8 lanes */
+            int incl = rlen;
 #pragma unroll
-                for (int sl = 0; sl < PAIR_SLOTS; ++sl) {
-                    int k = k0 + sl * 32 + lane;
-                    cg[sl] = -1;
-                    cxs[sl] = cys[sl] = czs[sl] = 0.f; cor[sl] = 0;
+            for (int off = 1; off < 8; off <<= 1) {
+                int v = __shfl_up_sync(FULL, incl, off, 8);
+                if (r >= off) incl += v;
+            }
+            const int total = __shfl_sync(FULL, incl, 7, 8);
+            nh = __shfl_sync(FULL, nh, 0, 8);
+            __syncwarp();
+            if (r < 5) s_runs[warp][qc][r] = make_int2(rbeg, incl - rlen);
+            else if (r == 5) s_runs[warp][qc][5] = make_int2(total, nh);
+            else if (r == 6) s_runs[warp][qc][6] = make_int2(__float_as_int(band_lo), __float_as_int(band_hi));
+            __syncwarp();
+        }
+        for (int qc = 0; qc < SEARCH_CELLS; ++qc) {
+            const int2 tn = s_runs[warp][qc][5];
+            const int total = tn.x, nh = tn.y;
+            if (nh == 0) continue;
+            ++nonempty;
+            const int2 r0 = s_runs[warp][qc][0], r1 = s_runs[warp][qc][1], r2 = s_runs[warp][qc][2],
+                       r3 = s_runs[warp][qc][3], r4 = s_runs[warp][qc][4];
+            const int hb = r0.x;
+            const float r2_lo = __int_as_float(s_runs[warp][qc][6].x), r2_hi = __int_as_float(s_runs[warp][qc][6].y);
+            /* tests of this cell: home atom h meets candidates k > h */
+            ncand += (unsigned long long)nh * (unsigned)total - (unsigned long long)nh * (unsigned)(nh + 1) / 2;
+
+            for (int k0 = 0; k0 < total; k0 += SEARCH_CHUNK) {
+                float cxs[SEARCH_SLOTS], cys[SEARCH_SLOTS], czs[SEARCH_SLOTS];
+                int   cg[SEARCH_SLOTS], ck[SEARCH_SLOTS];
+#pragma unroll
+                for (int sl = 0; sl < SEARCH_SLOTS; ++sl) {
+                    const int k = k0 + sl * 32 + lane;
+                    cg[sl] = 0; ck[sl] = -1;
+                    cxs[sl] = cys[sl] = czs[sl] = 0.f;
                     if (k < total) {
-                        int g = k < p1 ? b0 + k : k < p2 ? b1 + (k - p1) : k < p3 ? b2 + (k - p2)
-                              : k < p4 ? b3 + (k - p3) : b4 + (k - p4);
-                        float4 p = A.pos4[g];
-                        cxs[sl] = p.x; cys[sl] = p.y; czs[sl] = p.z; cor[sl] = __float_as_int(p.w);
-                        cg[sl] = g;
+                        const int g = k < r1.y ? r0.x + k : k < r2.y ? r1.x + (k - r1.y) : k < r3.y ? r2.x + (k - r2.y)
+                                    : k < r4.y ? r3.x + (k - r3.y) : r4.x + (k - r4.y);
+                        const float4 p = A.pos4[g];
+                        cxs[sl] = p.x; cys[sl] = p.y; czs[sl] = p.z;
+                        cg[sl] = g; ck[sl] = k;
                     }
                 }
                 /* home atoms that still have candidates in this chunk: k > h */
-                const int h_end = min(nh, k0 + PAIR_CHUNK - 1);
+                const int h_end = min(nh, k0 + SEARCH_CHUNK - 1);
                 for (int h = 0; h < h_end; ++h) {
-                    float hx, hy, hz; int ho;
+                    float hx, hy, hz;
                     if (k0 == 0 && h < 32) {       /* candidate k = h of run 0 is home atom h */
-                        hx = __shfl_sync(FULL, cxs[0], h); hy = __shfl_sync(FULL, cys[0], h);
-                        hz = __shfl_sync(FULL, czs[0], h); ho = __shfl_sync(FULL, cor[0], h);
+                        hx = __shfl_sync(FULL, cxs[0], h); hy = __shfl_sync(FULL, cys[0], h); hz = __shfl_sync(FULL, czs[0], h);
                     } else {
                         const float4 hp = A.pos4[hb + h];
-                        hx = hp.x; hy = hp.y; hz = hp.z; ho = __float_as_int(hp.w);
+                        hx = hp.x; hy = hp.y; hz = hp.z;
                     }
 #pragma unroll
-                    for (int sl = 0; sl < PAIR_SLOTS; ++sl) {
-                        const int k = k0 + sl * 32 + lane;
+                    for (int sl = 0; sl < SEARCH_SLOTS; ++sl) {
                         if (k0 + sl * 32 >= total) break;                 /* warp-uniform */
-                        const bool ok = cg[sl] >= 0 && k > h;
                         const float ddx = hx - cxs[sl], ddy = hy - cys[sl], ddz = hz - czs[sl];
                         const float d2 = __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, __fmul_rn(ddx, ddx)));
-                        bool hit = ok && (d2 <= G.r2_hi);
-                        ncand += ok ? 1u : 0u;
-                        if (hit && d2 > G.r2_lo) hit = kd_within(hx, hy, hz, cxs[sl], cys[sl], czs[sl], P.r2);
+                        bool hit = (ck[sl] > h) && (d2 <= r2_hi);
+                        if (__builtin_expect(hit && d2 > r2_lo, 0))
+                            hit = kd_within(hx, hy, hz, cxs[sl], cys[sl], czs[sl], A.r2);
                         const unsigned m = __ballot_sync(FULL, hit);
                         if (m) {
-                            if (hit) {
-                                const bool h_first = ho < cor[sl];        /* atom_bgn = lower list index */
-                                const unsigned pos = (qhead + qcount + __popc(m & lt_mask)) & (PAIR_QCAP - 1);
-                                q[pos] = h_first ? make_uint2((unsigned)(hb + h), (unsigned)cg[sl])
-                                                 : make_uint2((unsigned)cg[sl], (unsigned)(hb + h));
-                            }
+                            if (hit) q[(qhead + qcount + __popc(m & lt_mask)) & (SEARCH_QCAP - 1)] =
+                                         make_uint2((unsigned)(hb + h), (unsigned)cg[sl]);
                             qcount += __popc(m);
                         }
                     }
-                    if (qcount >= PAIR_DRAIN) {
+                    if (qcount >= SEARCH_DRAIN) {
                         __syncwarp();
-                        pairs_drain(A, P, q, qhead, PAIR_DRAIN, lane);
-                        qhead = (qhead + PAIR_DRAIN) & (PAIR_QCAP - 1);
-                        qcount -= PAIR_DRAIN;
+                        search_drain(A, q, qhead, SEARCH_DRAIN, lane);
+                        qhead = (qhead + SEARCH_DRAIN) & (SEARCH_QCAP - 1);
+                        qcount -= SEARCH_DRAIN;
                     }
                 }
             }
         }
-        ncand_total += ncand; ncand = 0;
     }
     if (qcount) {
         __syncwarp();
-        pairs_drain(A, P, q, qhead, qcount, lane);
+        search_drain(A, q, qhead, qcount, lane);
     }
-    /* statistics */
-    for (int off = 16; off; off >>= 1) ncand_total += __shfl_xor_sync(FULL, ncand_total, off);
     if (lane == 0) {
-        if (ncand_total) atomicAdd(&A.meta->n_candidates, ncand_total);
+        if (ncand) atomicAdd(&A.meta->n_candidates, ncand);
         if (nonempty) atomicAdd(&A.meta->n_cells_nonempty, nonempty);
     }
+}
+
+/* ---- k_classify ---------------------------------------------------------------------------------
+ * The loop body of _calculate_atom_contacts (interactions.py:743-936) over the hit list, one thread per
+ * pair, in tiles of CLS_TILE pairs per CTA:
+ *   stage 1  every thread: exact float32 distance, proximity bit, metal, feature bits that need no angle
+ *            (rule_classify_core); the record goes to a shared-memory staging tile; pairs that need a
+ *            hydrogen scan (is_hbond / is_weak_hbond) or a rare exact predicate (halogen weak hbond, xbond)
+ *            push a 32-bit work item into one of two shared-memory lists (ballot compaction)
+ *   stage 2  the lists are processed densely -- every lane runs the same predicate -- and OR their bit into
+ *            the staged record
+ *   stage 3  the finished tile (CLS_TILE x 16 B, contiguous in the output stream) leaves with one bulk
+ *            asynchronous copy shared -> global (cp.async.bulk, TMA engine), double buffered so that the
+ *            store of tile t overlaps the arithmetic of tile t + 1.                                      */
+#define CLS_THREADS 256
+#define CLS_TILE    512
+
+struct ClassifyArgs {
+    const float4* pos4;
+    const uint4*  att4;
+    const uint2*  hits;
+    const RunMeta* meta;
+    arp_pair*     out;
+    unsigned long long out_cap;
+    ArpSide       side;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_store_tile(void* gdst, const void* ssrc, uint32_t bytes)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read_all()
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read_1()
+{
+    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(CLS_THREADS, 3) k_classify(ClassifyArgs A, ArpRuleParams P)
+{
+    __shared__ __align__(128) int4 s_rec[2][CLS_TILE];          /* staged records, double buffered */
+    __shared__ uint32_t s_scan[2 * CLS_TILE];                   /* hydrogen-scan items: idx << 3 | dir << 2 | need */
+    __shared__ uint32_t s_rare[2 * CLS_TILE];                   /* rare items: idx << 3 | dir << 2 | kind */
+    __shared__ unsigned s_nscan, s_nrare;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned long long n = A.meta->n_pairs;
+    if (n > A.out_cap) n = A.out_cap;                           /* overflowing run: host repeats it with a larger buffer */
+    const unsigned long long n_tiles = (n + CLS_TILE - 1) / CLS_TILE;
+    int buf = 0;
+    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+        const unsigned long long base = tile * CLS_TILE;
+        const unsigned cnt = (unsigned)min((unsigned long long)CLS_TILE, n - base);
+        if (threadIdx.x == 0) {
+            s_nscan = 0; s_nrare = 0;
+            bulk_store_wait_read_1();                            /* the store that last used s_rec[buf] has read it */
+        }
+        __syncthreads();
+        /* ---- stage 1 ---- */
+        for (unsigned i0 = 0; i0 < cnt; i0 += CLS_THREADS) {
+            const unsigned idx = i0 + threadIdx.x;
+            int n_scan = 0, n_rare = 0;
+            uint32_t it_scan[2], it_rare[2];
+            if (idx < cnt) {
+                const uint2 e = A.hits[base + idx];
+                const float4 pb = A.pos4[e.x], pe = A.pos4[e.y];
+                const uint32_t fb = A.att4[e.x].x, fe = A.att4[e.y].x;
+                const int ib = __float_as_int(pb.w), ie = __float_as_int(pe.w);
+                uint32_t mask, work; float dist;
+                rule_classify_core(A.side, P, ib, ie, pb.x, pb.y, pb.z, pe.x, pe.y, pe.z, fb, fe, &mask, &dist, &work);
+                s_rec[buf][idx] = make_int4(ib, ie, (int)mask, __float_as_int(dist));
+                if (work & ARP_WORK_SCAN0) it_scan[n_scan++] = (idx << 3) | (work & 3u);
+                if (work & ARP_WORK_SCAN1) it_scan[n_scan++] = (idx << 3) | 4u | ((work >> 2) & 3u);
+                if (work & ARP_WORK_HAL0) it_rare[n_rare++] = (idx << 3) | ARP_RARE_HAL;
+                if (work & ARP_WORK_HAL1) it_rare[n_rare++] = (idx << 3) | 4u | ARP_RARE_HAL;
+                if (work & ARP_WORK_XB0) it_rare[n_rare++] = (idx << 3) | ARP_RARE_XBOND;
+                if (work & ARP_WORK_XB1) it_rare[n_rare++] = (idx << 3) | 4u | ARP_RARE_XBOND;
+            }
+            /* warp-aggregated append: one shared atomic per warp and list */
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const unsigned m = __ballot_sync(FULL, n_scan > pass);
+                if (m) {
+                    unsigned o = 0;
+                    if (lane == 0) o = atomicAdd(&s_nscan, (unsigned)__popc(m));
+                    o = __shfl_sync(FULL, o, 0);
+                    if (n_scan > pass) s_scan[o + __popc(m & lt_mask)] = it_scan[pass];
+                }
+                const unsigned mr = __ballot_sync(FULL, n_rare > pass);
+                if (mr) {
+                    unsigned o = 0;
+                    if (lane == 0) o = atomicAdd(&s_nrare, (unsigned)__popc(mr));
+                    o = __shfl_sync(FULL, o, 0);
+                    if (n_rare > pass) s_rare[o + __popc(mr & lt_mask)] = it_rare[pass];
+                }
+            }
+        }
+        __syncthreads();
+        /* ---- stage 2: dense hydrogen scans, then the rare exact predicates ---- */
+        const unsigned nscan = s_nscan, nrare = s_nrare;
+        for (unsigned w = threadIdx.x; w < nscan; w += CLS_THREADS) {
+            const uint32_t it = s_scan[w];
+            const unsigned idx = it >> 3;
+            const int need = (int)(it & 3u);
+            uint2 e = A.hits[base + idx];
+            if (it & 4u) { unsigned t = e.x; e.x = e.y; e.y = t; }       /* direction 1: donor = end, acceptor = bgn */
+            const float4 pd = A.pos4[e.x], pa = A.pos4[e.y];
+            const double vdw_acc = A.side.vdw[A.att4[e.y].x >> ARPK_RAD_SHIFT];
+            const int got = rule_hbond_scan(A.side, P, __float_as_int(pd.w), pd.x, pd.y, pd.z, pa.x, pa.y, pa.z, vdw_acc, need);
+            uint32_t bits = 0;
+            if (got & ARP_HB_NEED_H) bits |= 1u << ARP_SIFT_HBOND;
+            if (got & ARP_HB_NEED_W) bits |= 1u << ARP_SIFT_WEAK_HBOND;
+            if (bits) atomicOr(reinterpret_cast<unsigned*>(&s_rec[buf][idx].z), bits);
+        }
+        for (unsigned w = threadIdx.x; w < nrare; w += CLS_THREADS) {
+            const uint32_t it = s_rare[w];
+            const unsigned idx = it >> 3;
+            uint2 e = A.hits[base + idx];
+            if (it & 4u) { unsigned t = e.x; e.x = e.y; e.y = t; }       /* e.x = donor, e.y = halogen / acceptor */
+            const float4 pd = A.pos4[e.x], pa = A.pos4[e.y];
+            const uint32_t fd = A.att4[e.x].x, fa = A.att4[e.y].x;
+            uint32_t bits = 0;
+            if ((it & 3u) == ARP_RARE_HAL) {
+                if (rule_is_halogen_weak_hbond(A.side, P, __float_as_int(pd.w), __float_as_int(pa.w), pa.x, pa.y, pa.z, fa,
+                                               A.side.vdw[fa >> ARPK_RAD_SHIFT])) bits = 1u << ARP_SIFT_WEAK_HBOND;
+            } else {
+                uint32_t fault = 0;
+                if (rule_is_xbond(A.side, P, __float_as_int(pd.w), pd.x, pd.y, pd.z, pa.x, pa.y, pa.z, fd, &fault))
+                    bits = 1u << ARP_SIFT_XBOND;
+                bits |= fault;
+            }
+            if (bits) atomicOr(reinterpret_cast<unsigned*>(&s_rec[buf][idx].z), bits);
+        }
+        __syncthreads();
+        /* ---- stage 3: the tile leaves through the TMA engine ---- */
+        if (threadIdx.x == 0) bulk_store_tile(A.out + base, s_rec[buf], cnt * (uint32_t)sizeof(arp_pair));
+    }
+    if (threadIdx.x == 0) bulk_store_wait_read_all();            /* shared memory must outlive the copies */
 }
 
 /* K x K table of the float32 proximity thresholds (interactions.py:717-718, :760-768): NumPy narrows
@@ -572,12 +729,11 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
     }
     if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[1], st));
     if (N > 0) {
-        PairArgs A;
-        A.pos4 = c->pos4.as<float4>(); A.att4 = c->att4.as<uint4>(); A.cell_start = c->cell_start.as<int>();
-        A.geom = c->geom.as<StructGeom>(); A.meta = meta; A.out = c->out.as<arp_pair>(); A.out_cap = c->out_cap;
-        A.side.vdw = c->vdw.as<double>(); A.side.cov = c->cov.as<double>();
-        A.side.K = c->K;
-        A.side.radtab = nullptr;
+        ArpSide side;
+        memset(&side, 0, sizeof side);
+        side.vdw = c->vdw.as<double>(); side.cov = c->cov.as<double>();
+        side.K = c->K;
+        side.radtab = nullptr;
         if (c->K <= 64) {                   /* larger tables stop being cache resident: compute on the fly */
             if (!c->radtab_valid) {
                 ARP_TRY(dbuf_reserve(c, c->radtab, sizeof(float4) * (size_t)c->K * c->K));
@@ -586,20 +742,37 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
                 ARP_LAUNCHED(c);
                 c->radtab_valid = 1;
             }
-            A.side.radtab = c->radtab.as<float4>();
+            side.radtab = c->radtab.as<float4>();
         }
-        A.side.bond_off = c->has_bonds ? c->bond_off.as<int32_t>() : nullptr;
-        A.side.bond_nbr = c->has_bonds ? c->bond_nbr.as<int32_t>() : nullptr;
-        A.side.h_off = c->has_h ? c->h_off.as<int32_t>() : nullptr;
-        A.side.h_xyz = c->has_h ? c->h_xyz.as<double>() : nullptr;
-        A.side.xnbr = c->has_xnbr ? c->xnbr.as<float>() : nullptr;
-        unsigned grid = (unsigned)(c->sm_count * 2);
-        size_t want = ((size_t)N / 24) / PAIR_WARPS + 1;       /* about one warp per few cells on small inputs */
+        side.bond_off = c->has_bonds ? c->bond_off.as<int32_t>() : nullptr;
+        side.bond_nbr = c->has_bonds ? c->bond_nbr.as<int32_t>() : nullptr;
+        side.h_off = c->has_h ? c->h_off.as<int32_t>() : nullptr;
+        side.h_xyz = c->has_h ? c->h_xyz.as<double>() : nullptr;
+        side.xnbr = c->has_xnbr ? c->xnbr.as<float>() : nullptr;
+
+        SearchArgs SA;
+        SA.pos4 = c->pos4.as<float4>(); SA.att4 = c->att4.as<uint4>(); SA.cell_start = c->cell_start.as<int>();
+        SA.geom = c->geom.as<StructGeom>(); SA.meta = meta; SA.hits = c->hits.as<uint2>(); SA.hit_cap = c->out_cap;
+        SA.r2 = c->rp.r2; SA.include_seq_adjacent = c->rp.include_seq_adjacent;
+        unsigned grid = (unsigned)(c->sm_count * 4);
+        size_t want = ((size_t)N / 24) / SEARCH_WARPS + 1;     /* about one warp per few cells on small inputs */
         if (want < grid) grid = (unsigned)want;
-        k_pairs<<<grid, PAIR_WARPS * 32, 0, st>>>(A, c->rp);
+        k_search<<<grid, SEARCH_WARPS * 32, 0, st>>>(SA);
         ARP_LAUNCHED(c);
+        if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[2], st));
+
+        ClassifyArgs CA;
+        CA.pos4 = SA.pos4; CA.att4 = SA.att4; CA.hits = SA.hits; CA.meta = meta;
+        CA.out = c->out.as<arp_pair>(); CA.out_cap = c->out_cap; CA.side = side;
+        size_t tiles = (size_t)((c->out_cap + CLS_TILE - 1) / CLS_TILE);
+        unsigned cgrid = (unsigned)(c->sm_count * 3);
+        if (tiles < cgrid) cgrid = (unsigned)(tiles ? tiles : 1);
+        k_classify<<<cgrid, CLS_THREADS, 0, st>>>(CA, c->rp);
+        ARP_LAUNCHED(c);
+    } else if (with_events) {
+        ARP_CUDA(c, cudaEventRecord(c->ev[2], st));
     }
-    if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[2], st));
+    if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[3], st));
     ARP_CUDA(c, cudaMemcpyAsync(c->h_meta, meta, sizeof(RunMeta), cudaMemcpyDeviceToHost, st));
     return ARP_OK;
 }

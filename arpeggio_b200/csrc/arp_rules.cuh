@@ -403,14 +403,25 @@ ARP_HD bool rule_pair_survives(uint32_t fb, int rb, int pb, int nb, uint32_t fe,
     return true;
 }
 
+/* ---- deferred work of one pair (rule_classify_core -> the dense second stage) --------------------- */
+#define ARP_WORK_SCAN0  0x03u   /* bits 0..1: ARP_HB_NEED_* for direction 0 (donor = bgn, acceptor = end) */
+#define ARP_WORK_SCAN1  0x0Cu   /* bits 2..3: ARP_HB_NEED_* for direction 1 (donor = end, acceptor = bgn) */
+#define ARP_WORK_HAL0   0x10u   /* is_halogen_weak_hbond(donor = bgn, halogen = end) */
+#define ARP_WORK_HAL1   0x20u   /* is_halogen_weak_hbond(donor = end, halogen = bgn) */
+#define ARP_WORK_XB0    0x40u   /* is_xbond(donor = bgn, acceptor = end) */
+#define ARP_WORK_XB1    0x80u   /* is_xbond(donor = end, acceptor = bgn) */
+#define ARP_RARE_HAL    1u
+#define ARP_RARE_XBOND  2u
+
 /*
- * Loop body of _calculate_atom_contacts after the filters (interactions.py:743-936).
- * b = atom_bgn (lower list index), e = atom_end; coordinates and packed words are passed
- * in registers, rare branches read the side arrays by original index.
+ * Loop body of _calculate_atom_contacts after the filters (interactions.py:743-936), without the
+ * predicates that walk hydrogens or need an exact angle: those come back in *work and are OR-ed into
+ * the mask by the caller (bits hbond, weak_hbond, xbond).
+ * b = atom_bgn (lower list index), e = atom_end; coordinates and packed words are passed in registers.
  */
-ARP_HD void rule_classify(const ArpSide& S, const ArpRuleParams& P, int b, int e,
-                          float bx, float by, float bz, float ex, float ey, float ez,
-                          uint32_t fb, uint32_t fe, uint32_t* mask_out, float* dist_out)
+ARP_HD void rule_classify_core(const ArpSide& S, const ArpRuleParams& P, int b, int e,
+                               float bx, float by, float bz, float ex, float ey, float ez,
+                               uint32_t fb, uint32_t fe, uint32_t* mask_out, float* dist_out, uint32_t* work_out)
 {
     const uint32_t kb = fb >> ARPK_RAD_SHIFT, ke = fe >> ARPK_RAD_SHIFT;
     float t_cov, t_vdw, vdwc;
@@ -423,81 +434,91 @@ ARP_HD void rule_classify(const ArpSide& S, const ArpRuleParams& P, int b, int e
         t_cov = (float)sum_cov; t_vdw = (float)sum_vdw; vdwc = (float)d_add(sum_vdw, P.vdw_comp);
     }
     const float d = np_dist_f32(bx, by, bz, ex, ey, ez);                           /* :745 */
-    uint32_t m = 0, fault = 0;
+    uint32_t m = 0, work = 0;
 
     bool bonded = false;                                                           /* :750-754 */
     if (fb & ARPK_HAS_BOND) {           /* only atom_bgn's neighbour list is consulted */
         for (int k = S.bond_off[b]; k < S.bond_off[b + 1]; ++k)
             if (S.bond_nbr[k] == e) { bonded = true; break; }
     }
-    if (bonded)          m |= 1u << ARP_SIFT_COVALENT;                             /* :756-757 */
-    else if (d < t_cov)  m |= 1u << ARP_SIFT_CLASH;                                /* :760 */
-    else if (d < t_vdw)  m |= 1u << ARP_SIFT_VDW_CLASH;                            /* :764 */
-    else if (d <= vdwc)  m |= 1u << ARP_SIFT_VDW;                                  /* :768 */
-    else                 m |= 1u << ARP_SIFT_PROXIMAL;                             /* :772 */
+    const bool clash = !bonded && d < t_cov;
+    m |= bonded ? 1u << ARP_SIFT_COVALENT                                          /* :756-757 */
+       : clash ? 1u << ARP_SIFT_CLASH                                              /* :760 */
+       : d < t_vdw ? 1u << ARP_SIFT_VDW_CLASH                                      /* :764 */
+       : d <= vdwc ? 1u << ARP_SIFT_VDW                                            /* :768 */
+       : 1u << ARP_SIFT_PROXIMAL;                                                  /* :772 */
 
-    if (d <= P.metal) {                                                            /* :777-783 */
-        if (((fb & ARP_F_HBOND_ACCEPTOR) && (fe & ARP_F_IS_METAL)) ||
-            ((fe & ARP_F_HBOND_ACCEPTOR) && (fb & ARP_F_IS_METAL))) m |= 1u << ARP_SIFT_METAL;
-    }
+    const uint32_t x = fb | fe, a = fb & fe;
+    /* a feature pair "p on one atom, q on the other, either way round" */
+#define ARP_CROSS(p, q) ((((fb & (p)) != 0) & ((fe & (q)) != 0)) | (((fe & (p)) != 0) & ((fb & (q)) != 0)))
+    if ((d <= P.metal) & ARP_CROSS(ARP_F_HBOND_ACCEPTOR, ARP_F_IS_METAL)) m |= 1u << ARP_SIFT_METAL;   /* :777-783 */
 
-    if (!(m & (1u << ARP_SIFT_CLASH)) && d <= P.dist_max) {                        /* :786 */
-        /* hbond / polar :791-819 -- which direction, if any, needs utils.is_hbond */
-        int need0 = 0, need1 = 0;        /* direction 0: donor = bgn, acceptor = end; 1: the reverse */
-        if ((fb & ARP_F_IS_WATER) && d <= vdwc) {
-            if (fe & (ARP_F_HBOND_ACCEPTOR | ARP_F_HBOND_DONOR)) m |= (1u << ARP_SIFT_HBOND) | (1u << ARP_SIFT_POLAR);
-        } else if ((fe & ARP_F_IS_WATER) && d <= vdwc) {
-            if (fb & (ARP_F_HBOND_ACCEPTOR | ARP_F_HBOND_DONOR)) m |= (1u << ARP_SIFT_HBOND) | (1u << ARP_SIFT_POLAR);
-        } else if ((fb & ARP_F_HBOND_DONOR) && (fe & ARP_F_HBOND_ACCEPTOR)) {
-            need0 |= ARP_HB_NEED_H;
+    if (!clash && d <= P.dist_max) {                                               /* :786 */
+        const bool in_vdwc = d <= vdwc;
+        const bool don_b = fb & ARP_F_HBOND_DONOR, don_e = fe & ARP_F_HBOND_DONOR;
+        const bool acc_b = fb & ARP_F_HBOND_ACCEPTOR, acc_e = fe & ARP_F_HBOND_ACCEPTOR;
+        const bool wdon_b = fb & ARP_F_WEAK_HBOND_DONOR, wdon_e = fe & ARP_F_WEAK_HBOND_DONOR;
+        /* hbond / polar :791-819 */
+        if ((fb & ARP_F_IS_WATER) && in_vdwc) {
+            if (acc_e || don_e) m |= (1u << ARP_SIFT_HBOND) | (1u << ARP_SIFT_POLAR);
+        } else if ((fe & ARP_F_IS_WATER) && in_vdwc) {
+            if (acc_b || don_b) m |= (1u << ARP_SIFT_HBOND) | (1u << ARP_SIFT_POLAR);
+        } else if (don_b && acc_e) {
+            work |= ARP_HB_NEED_H;                                                 /* is_hbond(bgn, end) */
             if (d <= P.hbond_polar) m |= 1u << ARP_SIFT_POLAR;
-        } else if ((fe & ARP_F_HBOND_DONOR) && (fb & ARP_F_HBOND_ACCEPTOR)) {
-            need1 |= ARP_HB_NEED_H;
+        } else if (don_e && acc_b) {
+            work |= ARP_HB_NEED_H << 2;                                            /* is_hbond(end, bgn) */
             if (d <= P.hbond_polar) m |= 1u << ARP_SIFT_POLAR;
         }
         /* weak hbond / weak polar: four independent ifs, each ASSIGNS SIFt[6] (:857-886), so only the
            last applicable one decides the bit; any applicable one enables weak polar */
-        const bool w1 = (fb & ARP_F_HBOND_ACCEPTOR) && (fe & ARP_F_WEAK_HBOND_DONOR);          /* is_weak_hbond(e, b) */
-        const bool w2 = (fb & ARP_F_WEAK_HBOND_DONOR) && (fe & ARP_F_HBOND_ACCEPTOR);          /* is_weak_hbond(b, e) */
-        const bool w3 = (fb & ARP_F_WEAK_HBOND_ACCEPTOR) && (fb & ARP_F_IS_HALOGEN) &&
-                        (fe & (ARP_F_HBOND_DONOR | ARP_F_WEAK_HBOND_DONOR));                   /* halogen b, donor e */
-        const bool w4 = (fe & ARP_F_WEAK_HBOND_ACCEPTOR) && (fe & ARP_F_IS_HALOGEN) &&
-                        (fb & (ARP_F_HBOND_DONOR | ARP_F_WEAK_HBOND_DONOR));                   /* halogen e, donor b */
-        int weak = 0;
-        if (w4)      weak = rule_is_halogen_weak_hbond(S, P, b, e, ex, ey, ez, fe, S.vdw[ke]);
-        else if (w3) weak = rule_is_halogen_weak_hbond(S, P, e, b, bx, by, bz, fb, S.vdw[kb]);
-        else if (w2) need0 |= ARP_HB_NEED_W;
-        else if (w1) need1 |= ARP_HB_NEED_W;
+        const bool w1 = acc_b && wdon_e;                                           /* is_weak_hbond(end, bgn) */
+        const bool w2 = wdon_b && acc_e;                                           /* is_weak_hbond(bgn, end) */
+        const bool w3 = (fb & ARP_F_WEAK_HBOND_ACCEPTOR) && (fb & ARP_F_IS_HALOGEN) && (don_e || wdon_e);   /* halogen bgn */
+        const bool w4 = (fe & ARP_F_WEAK_HBOND_ACCEPTOR) && (fe & ARP_F_IS_HALOGEN) && (don_b || wdon_b);   /* halogen end */
+        if (w4)      work |= ARP_WORK_HAL0;
+        else if (w3) work |= ARP_WORK_HAL1;
+        else if (w2) work |= ARP_HB_NEED_W;
+        else if (w1) work |= ARP_HB_NEED_W << 2;
         if ((w1 || w2 || w3 || w4) && d <= P.weak_polar) m |= 1u << ARP_SIFT_WEAK_POLAR;
-        /* one shared pass per direction */
-        int got = 0;
-#pragma unroll 1
-        for (int dir = 0; dir < 2; ++dir) {
-            const int need = dir ? need1 : need0;
-            if (!need) continue;
-            if (dir == 0) got |= rule_hbond_scan(S, P, b, bx, by, bz, ex, ey, ez, S.vdw[ke], need);
-            else          got |= rule_hbond_scan(S, P, e, ex, ey, ez, bx, by, bz, S.vdw[kb], need);
-        }
-        if (got & ARP_HB_NEED_H) m |= 1u << ARP_SIFT_HBOND;
-        if ((got & ARP_HB_NEED_W) || weak) m |= 1u << ARP_SIFT_WEAK_HBOND;
         /* xbond :889-895 */
-        if (d <= vdwc) {
-            if ((fb & ARP_F_XBOND_DONOR) && (fe & ARP_F_XBOND_ACCEPTOR)) {
-                if (rule_is_xbond(S, P, b, bx, by, bz, ex, ey, ez, fb, &fault)) m |= 1u << ARP_SIFT_XBOND;
-            } else if ((fe & ARP_F_XBOND_DONOR) && (fb & ARP_F_XBOND_ACCEPTOR)) {
-                if (rule_is_xbond(S, P, e, ex, ey, ez, bx, by, bz, fe, &fault)) m |= 1u << ARP_SIFT_XBOND;
-            }
+        if (in_vdwc) {
+            if ((fb & ARP_F_XBOND_DONOR) && (fe & ARP_F_XBOND_ACCEPTOR)) work |= ARP_WORK_XB0;
+            else if ((fe & ARP_F_XBOND_DONOR) && (fb & ARP_F_XBOND_ACCEPTOR)) work |= ARP_WORK_XB1;
         }
         /* ionic :898-904, carbonyl :907-913, aromatic :916-917, hydrophobic :920-921 */
-        if (d <= P.ionic && (((fb & ARP_F_POS_IONISABLE) && (fe & ARP_F_NEG_IONISABLE)) ||
-                             ((fb & ARP_F_NEG_IONISABLE) && (fe & ARP_F_POS_IONISABLE)))) m |= 1u << ARP_SIFT_IONIC;
-        if (d <= P.carbonyl && (((fb & ARP_F_CARBONYL_OXYGEN) && (fe & ARP_F_CARBONYL_CARBON)) ||
-                                ((fe & ARP_F_CARBONYL_OXYGEN) && (fb & ARP_F_CARBONYL_CARBON)))) m |= 1u << ARP_SIFT_CARBONYL;
-        if ((fb & fe & ARP_F_AROMATIC) && d <= P.aromatic) m |= 1u << ARP_SIFT_AROMATIC;
-        if ((fb & fe & ARP_F_HYDROPHOBE) && d <= P.hydrophobic) m |= 1u << ARP_SIFT_HYDROPHOBIC;
+        if ((d <= P.ionic) & ARP_CROSS(ARP_F_POS_IONISABLE, ARP_F_NEG_IONISABLE)) m |= 1u << ARP_SIFT_IONIC;
+        if ((d <= P.carbonyl) & ARP_CROSS(ARP_F_CARBONYL_OXYGEN, ARP_F_CARBONYL_CARBON)) m |= 1u << ARP_SIFT_CARBONYL;
+        if ((a & ARP_F_AROMATIC) && d <= P.aromatic) m |= 1u << ARP_SIFT_AROMATIC;
+        if ((a & ARP_F_HYDROPHOBE) && d <= P.hydrophobic) m |= 1u << ARP_SIFT_HYDROPHOBIC;
     }
-    *mask_out = m | (rule_entity_class(fb, fe) << ARP_CLASS_SHIFT) | fault;
+#undef ARP_CROSS
+    (void)x;
+    *mask_out = m | (rule_entity_class(fb, fe) << ARP_CLASS_SHIFT);
     *dist_out = d;
+    *work_out = work;
+}
+
+/* the whole loop body for one pair: core + its deferred work, evaluated in place
+   (host emulation and single-pair uses; the kernels run the deferred work densely instead) */
+ARP_HD void rule_classify(const ArpSide& S, const ArpRuleParams& P, int b, int e,
+                          float bx, float by, float bz, float ex, float ey, float ez,
+                          uint32_t fb, uint32_t fe, uint32_t* mask_out, float* dist_out)
+{
+    uint32_t m, work;
+    rule_classify_core(S, P, b, e, bx, by, bz, ex, ey, ez, fb, fe, &m, dist_out, &work);
+    const double vdw_b = S.vdw[fb >> ARPK_RAD_SHIFT], vdw_e = S.vdw[fe >> ARPK_RAD_SHIFT];
+    int got = 0, weak = 0;
+    uint32_t fault = 0;
+    if (work & ARP_WORK_SCAN0) got |= rule_hbond_scan(S, P, b, bx, by, bz, ex, ey, ez, vdw_e, (int)(work & 3u));
+    if (work & ARP_WORK_SCAN1) got |= rule_hbond_scan(S, P, e, ex, ey, ez, bx, by, bz, vdw_b, (int)((work >> 2) & 3u));
+    if (work & ARP_WORK_HAL0) weak = rule_is_halogen_weak_hbond(S, P, b, e, ex, ey, ez, fe, vdw_e);
+    if (work & ARP_WORK_HAL1) weak = rule_is_halogen_weak_hbond(S, P, e, b, bx, by, bz, fb, vdw_b);
+    if (got & ARP_HB_NEED_H) m |= 1u << ARP_SIFT_HBOND;
+    if ((got & ARP_HB_NEED_W) || weak) m |= 1u << ARP_SIFT_WEAK_HBOND;
+    if ((work & ARP_WORK_XB0) && rule_is_xbond(S, P, b, bx, by, bz, ex, ey, ez, fb, &fault)) m |= 1u << ARP_SIFT_XBOND;
+    if ((work & ARP_WORK_XB1) && rule_is_xbond(S, P, e, ex, ey, ez, bx, by, bz, fe, &fault)) m |= 1u << ARP_SIFT_XBOND;
+    *mask_out = m | fault;
 }
 
 #endif /* ARP_RULES_CUH */

@@ -236,8 +236,8 @@ typedef struct arp_stats {
     uint64_t output_bytes;      /* 16 * n_pairs */
     float    ms_total;          /* CUDA-event time of the last run, first to last kernel */
     float    ms_grid;           /* cell build part   */
-    float    ms_search;         /* the pair kernel: search + filters + classifier + emit */
-    float    ms_classify;       /* reserved (0): the classifier is fused into the pair kernel */
+    float    ms_search;         /* search kernel: neighbour search + filters -> hit list */
+    float    ms_classify;       /* classify kernel: distance + angle + bitmask rules -> records */
 } arp_stats;
 
 /* ---- life cycle ---------------------------------------------------------- */

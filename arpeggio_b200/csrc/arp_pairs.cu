@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(256) k_scatter(int N, const float* __restrict_
 #define SEARCH_WARPS  8
 #define SEARCH_SLOTS  4                     /* candidates held per lane */
 #define SEARCH_CHUNK  (32 * SEARCH_SLOTS)
-#define SEARCH_QCAP   256                   /* ring capacity per warp (power of two) */
+#define SEARCH_QCAP   256                   /* queue capacity per warp: < DRAIN before a home atom, + <= CHUNK hits */
 #define SEARCH_DRAIN  128
 #define SEARCH_CELLS  4                     /* cells per ticket; 8 lanes describe one cell's runs */
 
@@ -346,7 +346,7 @@ struct SearchArgs {
     int           include_seq_adjacent;
 };
 
-__device__ __forceinline__ void search_drain(const SearchArgs& A, uint2* q, unsigned head, unsigned n, int lane)
+__device__ __forceinline__ void search_drain(const SearchArgs& A, uint2* q, unsigned n, int lane)
 {
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned ns = 0;
@@ -355,7 +355,7 @@ __device__ __forceinline__ void search_drain(const SearchArgs& A, uint2* q, unsi
         bool keep = false;
         uint2 e = make_uint2(0, 0);
         if (idx < n) {
-            e = q[(head + idx) & (SEARCH_QCAP - 1)];
+            e = q[idx];
             const int oa = __float_as_int(A.pos4[e.x].w), ob = __float_as_int(A.pos4[e.y].w);
             if (ob < oa) { unsigned t = e.x; e.x = e.y; e.y = t; }                 /* atom_bgn = lower list index */
             const uint4 ab = A.att4[e.x], ae = A.att4[e.y];
@@ -363,7 +363,7 @@ __device__ __forceinline__ void search_drain(const SearchArgs& A, uint2* q, unsi
                                       A.include_seq_adjacent);
         }
         const unsigned m = __ballot_sync(FULL, keep);
-        if (keep) q[(head + ns + __popc(m & lt_mask)) & (SEARCH_QCAP - 1)] = e;   /* ns <= r: never ahead of the reads */
+        if (keep) q[ns + __popc(m & lt_mask)] = e;                                 /* ns <= r: never ahead of the reads */
         ns += __popc(m);
     }
     if (ns == 0) return;
@@ -371,11 +371,20 @@ __device__ __forceinline__ void search_drain(const SearchArgs& A, uint2* q, unsi
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(&A.meta->n_pairs, (unsigned long long)ns);
     base = __shfl_sync(FULL, base, 0);
-    for (unsigned r = 0; r < ns; r += 32) {
-        const unsigned idx = r + lane;
-        if (idx < ns && base + idx < A.hit_cap) A.hits[base + idx] = q[(head + idx) & (SEARCH_QCAP - 1)];
-    }
+    for (unsigned r = lane; r < ns; r += 32)
+        if (base + r < A.hit_cap) A.hits[base + r] = q[r];
     __syncwarp();
+}
+
+/* n / d for 0 <= n < 2^24, d >= 1: float reciprocal estimate, then exact correction */
+__device__ __forceinline__ int fast_div(int n, int d)
+{
+    if (n >= (1 << 24)) return n / d;
+    int q = __float2int_rz(__fdividef((float)n, (float)d));
+    int r = n - q * d;
+    while (r < 0) { --q; r += d; }
+    while (r >= d) { ++q; r -= d; }
+    return q;
 }
 
 __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) k_search(SearchArgs A)
@@ -384,7 +393,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) k_search(SearchArgs A)
     __shared__ int2  s_runs[SEARCH_WARPS][SEARCH_CELLS][8];      /* per cell: 5 x (first index, prefix); [5] = (total, nh); [6] = band */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint2* q = s_queue[warp];
-    unsigned qhead = 0, qcount = 0;
+    unsigned qcount = 0;                        /* linear queue: drained completely once it holds >= SEARCH_DRAIN hits */
     unsigned long long ncand = 0;
     unsigned nonempty = 0;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -414,7 +423,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) k_search(SearchArgs A)
                 if (r < 5) {
                     const int gdx = gp->dx, gdy = gp->dy, gdz = gp->dz, gbase = gp->cell_base;
                     const int lc = c - gbase;
-                    const int cx = lc % gdx, t2 = lc / gdx, cy = t2 % gdy, cz = t2 / gdy;
+                    const int t2 = fast_div(lc, gdx), cx = lc - t2 * gdx;
+                    const int cz = fast_div(t2, gdy), cy = t2 - cz * gdy;
                     const int y = cy + (r == 1 || r == 4 ? 1 : (r == 2 ? -1 : 0));
                     const int z = cz + (r >= 2 ? 1 : 0);
                     const int x0 = r == 0 ? cx : max(cx - 1, 0);
@@ -480,26 +490,26 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) k_search(SearchArgs A)
                         const float4 hp = A.pos4[hb + h];
                         hx = hp.x; hy = hp.y; hz = hp.z;
                     }
+                    const unsigned home = (unsigned)(hb + h);
 #pragma unroll
                     for (int sl = 0; sl < SEARCH_SLOTS; ++sl) {
                         if (k0 + sl * 32 >= total) break;                 /* warp-uniform */
                         const float ddx = hx - cxs[sl], ddy = hy - cys[sl], ddz = hz - czs[sl];
                         const float d2 = __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, __fmul_rn(ddx, ddx)));
-                        bool hit = (ck[sl] > h) && (d2 <= r2_hi);
-                        if (__builtin_expect(hit && d2 > r2_lo, 0))
-                            hit = kd_within(hx, hy, hz, cxs[sl], cys[sl], czs[sl], A.r2);
-                        const unsigned m = __ballot_sync(FULL, hit);
-                        if (m) {
-                            if (hit) q[(qhead + qcount + __popc(m & lt_mask)) & (SEARCH_QCAP - 1)] =
-                                         make_uint2((unsigned)(hb + h), (unsigned)cg[sl]);
-                            qcount += __popc(m);
+                        const bool live = ck[sl] > h;
+                        bool hit = live && (d2 <= r2_lo);                 /* certainly within the cutoff */
+                        const bool maybe = live && !(d2 <= r2_lo) && (d2 <= r2_hi);
+                        if (__any_sync(FULL, maybe)) {                    /* rare: the exact test of Bio.PDB.kdtrees */
+                            if (maybe) hit = kd_within(hx, hy, hz, cxs[sl], cys[sl], czs[sl], A.r2);
                         }
+                        const unsigned m = __ballot_sync(FULL, hit);
+                        if (hit) q[qcount + __popc(m & lt_mask)] = make_uint2(home, (unsigned)cg[sl]);
+                        qcount += __popc(m);
                     }
                     if (qcount >= SEARCH_DRAIN) {
                         __syncwarp();
-                        search_drain(A, q, qhead, SEARCH_DRAIN, lane);
-                        qhead = (qhead + SEARCH_DRAIN) & (SEARCH_QCAP - 1);
-                        qcount -= SEARCH_DRAIN;
+                        search_drain(A, q, qcount, lane);
+                        qcount = 0;
                     }
                 }
             }
@@ -507,7 +517,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) k_search(SearchArgs A)
     }
     if (qcount) {
         __syncwarp();
-        search_drain(A, q, qhead, qcount, lane);
+        search_drain(A, q, qcount, lane);
     }
     if (lane == 0) {
         if (ncand) atomicAdd(&A.meta->n_candidates, ncand);
@@ -516,19 +526,20 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) k_search(SearchArgs A)
 }
 
 /* ---- k_classify ---------------------------------------------------------------------------------
- * The loop body of _calculate_atom_contacts (interactions.py:743-936) over the hit list, one thread per
- * pair, in tiles of CLS_TILE pairs per CTA:
- *   stage 1  every thread: exact float32 distance, proximity bit, metal, feature bits that need no angle
- *            (rule_classify_core); the record goes to a shared-memory staging tile; pairs that need a
- *            hydrogen scan (is_hbond / is_weak_hbond) or a rare exact predicate (halogen weak hbond, xbond)
- *            push a 32-bit work item into one of two shared-memory lists (ballot compaction)
- *   stage 2  the lists are processed densely -- every lane runs the same predicate -- and OR their bit into
- *            the staged record
+ * The loop body of _calculate_atom_contacts (interactions.py:743-936) over the hit list, one lane per
+ * pair.  Every WARP owns tiles of CLS_TILE consecutive pairs and runs them without any block barrier:
+ *   stage 1  32 pairs per round: exact float32 distance, proximity bit, metal, the feature bits that need
+ *            no angle (rule_classify_core); the record goes to the warp's shared-memory staging tile;
+ *            pairs that need a hydrogen scan (is_hbond / is_weak_hbond) or a rarer predicate (halogen weak
+ *            hbond, xbond) append a 32-bit work item to the warp's list (ballot compaction)
+ *   stage 2  the list is processed densely -- 32 items per round -- and each result bit is OR-ed into the
+ *            staged record
  *   stage 3  the finished tile (CLS_TILE x 16 B, contiguous in the output stream) leaves with one bulk
  *            asynchronous copy shared -> global (cp.async.bulk, TMA engine), double buffered so that the
- *            store of tile t overlaps the arithmetic of tile t + 1.                                      */
-#define CLS_THREADS 256
-#define CLS_TILE    512
+ *            store of one tile overlaps the arithmetic of the next.                                      */
+#define CLS_WARPS   8
+#define CLS_TILE    128
+#define CLS_ITEMS   (3 * CLS_TILE)          /* per pair at most: is_hbond scan + (is_weak_hbond scan | halogen) + xbond */
 
 struct ClassifyArgs {
     const float4* pos4;
@@ -558,106 +569,102 @@ __device__ __forceinline__ void bulk_store_wait_read_1()
     asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(CLS_THREADS, 3) k_classify(ClassifyArgs A, ArpRuleParams P)
+/* item = record index in the tile << 4 | direction << 3 | kind (bits 0..2):
+   kind 1..3 = ARP_HB_NEED_* of a hydrogen scan, 4 = halogen weak hbond, 5 = xbond;
+   direction 0: donor = bgn, 1: donor = end */
+#define CLS_KIND_HAL   4u
+#define CLS_KIND_XBOND 5u
+
+__global__ void __launch_bounds__(CLS_WARPS * 32, 3) k_classify(ClassifyArgs A, ArpRuleParams P)
 {
-    __shared__ __align__(128) int4 s_rec[2][CLS_TILE];          /* staged records, double buffered */
-    __shared__ uint32_t s_scan[2 * CLS_TILE];                   /* hydrogen-scan items: idx << 3 | dir << 2 | need */
-    __shared__ uint32_t s_rare[2 * CLS_TILE];                   /* rare items: idx << 3 | dir << 2 | kind */
-    __shared__ unsigned s_nscan, s_nrare;
-    const int lane = threadIdx.x & 31;
+    __shared__ __align__(128) int4 s_rec[CLS_WARPS][2][CLS_TILE];   /* staged records, per warp, double buffered */
+    __shared__ uint32_t s_item[CLS_WARPS][CLS_ITEMS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned long long n = A.meta->n_pairs;
     if (n > A.out_cap) n = A.out_cap;                           /* overflowing run: host repeats it with a larger buffer */
     const unsigned long long n_tiles = (n + CLS_TILE - 1) / CLS_TILE;
+    const unsigned long long warp_id = (unsigned long long)blockIdx.x * CLS_WARPS + warp;
+    const unsigned long long n_warps = (unsigned long long)gridDim.x * CLS_WARPS;
+    uint32_t* items = s_item[warp];
     int buf = 0;
-    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    for (unsigned long long tile = warp_id; tile < n_tiles; tile += n_warps, buf ^= 1) {
         const unsigned long long base = tile * CLS_TILE;
         const unsigned cnt = (unsigned)min((unsigned long long)CLS_TILE, n - base);
-        if (threadIdx.x == 0) {
-            s_nscan = 0; s_nrare = 0;
-            bulk_store_wait_read_1();                            /* the store that last used s_rec[buf] has read it */
-        }
-        __syncthreads();
+        int4* rec = s_rec[warp][buf];
+        if (lane == 0) bulk_store_wait_read_1();                 /* the store that last used this buffer has read it */
+        __syncwarp();
         /* ---- stage 1 ---- */
-        for (unsigned i0 = 0; i0 < cnt; i0 += CLS_THREADS) {
-            const unsigned idx = i0 + threadIdx.x;
-            int n_scan = 0, n_rare = 0;
-            uint32_t it_scan[2], it_rare[2];
+        unsigned n_items = 0;
+        for (unsigned i0 = 0; i0 < cnt; i0 += 32) {
+            const unsigned idx = i0 + lane;
+            uint32_t work = 0;
             if (idx < cnt) {
                 const uint2 e = A.hits[base + idx];
                 const float4 pb = A.pos4[e.x], pe = A.pos4[e.y];
                 const uint32_t fb = A.att4[e.x].x, fe = A.att4[e.y].x;
                 const int ib = __float_as_int(pb.w), ie = __float_as_int(pe.w);
-                uint32_t mask, work; float dist;
+                uint32_t mask; float dist;
                 rule_classify_core(A.side, P, ib, ie, pb.x, pb.y, pb.z, pe.x, pe.y, pe.z, fb, fe, &mask, &dist, &work);
-                s_rec[buf][idx] = make_int4(ib, ie, (int)mask, __float_as_int(dist));
-                if (work & ARP_WORK_SCAN0) it_scan[n_scan++] = (idx << 3) | (work & 3u);
-                if (work & ARP_WORK_SCAN1) it_scan[n_scan++] = (idx << 3) | 4u | ((work >> 2) & 3u);
-                if (work & ARP_WORK_HAL0) it_rare[n_rare++] = (idx << 3) | ARP_RARE_HAL;
-                if (work & ARP_WORK_HAL1) it_rare[n_rare++] = (idx << 3) | 4u | ARP_RARE_HAL;
-                if (work & ARP_WORK_XB0) it_rare[n_rare++] = (idx << 3) | ARP_RARE_XBOND;
-                if (work & ARP_WORK_XB1) it_rare[n_rare++] = (idx << 3) | 4u | ARP_RARE_XBOND;
+                rec[idx] = make_int4(ib, ie, (int)mask, __float_as_int(dist));
             }
-            /* warp-aggregated append: one shared atomic per warp and list */
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const unsigned m = __ballot_sync(FULL, n_scan > pass);
-                if (m) {
-                    unsigned o = 0;
-                    if (lane == 0) o = atomicAdd(&s_nscan, (unsigned)__popc(m));
-                    o = __shfl_sync(FULL, o, 0);
-                    if (n_scan > pass) s_scan[o + __popc(m & lt_mask)] = it_scan[pass];
-                }
-                const unsigned mr = __ballot_sync(FULL, n_rare > pass);
-                if (mr) {
-                    unsigned o = 0;
-                    if (lane == 0) o = atomicAdd(&s_nrare, (unsigned)__popc(mr));
-                    o = __shfl_sync(FULL, o, 0);
-                    if (n_rare > pass) s_rare[o + __popc(mr & lt_mask)] = it_rare[pass];
+            /* append the work items of this round, one kind of slot at a time (ballot compaction) */
+            {
+                unsigned m = __ballot_sync(FULL, (work & ARP_WORK_SCAN0) != 0);
+                if (work & ARP_WORK_SCAN0) items[n_items + __popc(m & lt_mask)] = (idx << 4) | (work & 3u);
+                n_items += __popc(m);
+                m = __ballot_sync(FULL, (work & ARP_WORK_SCAN1) != 0);
+                if (work & ARP_WORK_SCAN1) items[n_items + __popc(m & lt_mask)] = (idx << 4) | 8u | ((work >> 2) & 3u);
+                n_items += __popc(m);
+                const uint32_t rare = work & (ARP_WORK_HAL0 | ARP_WORK_HAL1 | ARP_WORK_XB0 | ARP_WORK_XB1);
+                if (__any_sync(FULL, rare != 0)) {
+                    m = __ballot_sync(FULL, (rare & (ARP_WORK_HAL0 | ARP_WORK_HAL1)) != 0);
+                    if (rare & (ARP_WORK_HAL0 | ARP_WORK_HAL1))
+                        items[n_items + __popc(m & lt_mask)] = (idx << 4) | ((rare & ARP_WORK_HAL1) ? 8u : 0u) | CLS_KIND_HAL;
+                    n_items += __popc(m);
+                    m = __ballot_sync(FULL, (rare & (ARP_WORK_XB0 | ARP_WORK_XB1)) != 0);
+                    if (rare & (ARP_WORK_XB0 | ARP_WORK_XB1))
+                        items[n_items + __popc(m & lt_mask)] = (idx << 4) | ((rare & ARP_WORK_XB1) ? 8u : 0u) | CLS_KIND_XBOND;
+                    n_items += __popc(m);
                 }
             }
         }
-        __syncthreads();
-        /* ---- stage 2: dense hydrogen scans, then the rare exact predicates ---- */
-        const unsigned nscan = s_nscan, nrare = s_nrare;
-        for (unsigned w = threadIdx.x; w < nscan; w += CLS_THREADS) {
-            const uint32_t it = s_scan[w];
-            const unsigned idx = it >> 3;
-            const int need = (int)(it & 3u);
-            uint2 e = A.hits[base + idx];
-            if (it & 4u) { unsigned t = e.x; e.x = e.y; e.y = t; }       /* direction 1: donor = end, acceptor = bgn */
-            const float4 pd = A.pos4[e.x], pa = A.pos4[e.y];
-            const double vdw_acc = A.side.vdw[A.att4[e.y].x >> ARPK_RAD_SHIFT];
-            const int got = rule_hbond_scan(A.side, P, __float_as_int(pd.w), pd.x, pd.y, pd.z, pa.x, pa.y, pa.z, vdw_acc, need);
-            uint32_t bits = 0;
-            if (got & ARP_HB_NEED_H) bits |= 1u << ARP_SIFT_HBOND;
-            if (got & ARP_HB_NEED_W) bits |= 1u << ARP_SIFT_WEAK_HBOND;
-            if (bits) atomicOr(reinterpret_cast<unsigned*>(&s_rec[buf][idx].z), bits);
-        }
-        for (unsigned w = threadIdx.x; w < nrare; w += CLS_THREADS) {
-            const uint32_t it = s_rare[w];
-            const unsigned idx = it >> 3;
-            uint2 e = A.hits[base + idx];
-            if (it & 4u) { unsigned t = e.x; e.x = e.y; e.y = t; }       /* e.x = donor, e.y = halogen / acceptor */
-            const float4 pd = A.pos4[e.x], pa = A.pos4[e.y];
-            const uint32_t fd = A.att4[e.x].x, fa = A.att4[e.y].x;
-            uint32_t bits = 0;
-            if ((it & 3u) == ARP_RARE_HAL) {
-                if (rule_is_halogen_weak_hbond(A.side, P, __float_as_int(pd.w), __float_as_int(pa.w), pa.x, pa.y, pa.z, fa,
-                                               A.side.vdw[fa >> ARPK_RAD_SHIFT])) bits = 1u << ARP_SIFT_WEAK_HBOND;
-            } else {
-                uint32_t fault = 0;
-                if (rule_is_xbond(A.side, P, __float_as_int(pd.w), pd.x, pd.y, pd.z, pa.x, pa.y, pa.z, fd, &fault))
-                    bits = 1u << ARP_SIFT_XBOND;
-                bits |= fault;
+        __syncwarp();
+        /* ---- stage 2: the deferred predicates, 32 items per round ---- */
+        for (unsigned w0 = 0; w0 < n_items; w0 += 32) {
+            const unsigned w = w0 + lane;
+            if (w < n_items) {
+                const uint32_t it = items[w];
+                const unsigned idx = it >> 4;
+                const uint32_t kind = it & 7u;
+                uint2 e = A.hits[base + idx];
+                if (it & 8u) { unsigned t = e.x; e.x = e.y; e.y = t; }   /* e.x = donor, e.y = acceptor / halogen */
+                const float4 pd = A.pos4[e.x], pa = A.pos4[e.y];
+                const uint32_t fa = A.att4[e.y].x;
+                const double vdw_a = A.side.vdw[fa >> ARPK_RAD_SHIFT];
+                uint32_t bits = 0;
+                if (kind <= 3u) {
+                    const int got = rule_hbond_scan(A.side, P, __float_as_int(pd.w), pd.x, pd.y, pd.z, pa.x, pa.y, pa.z,
+                                                    vdw_a, (int)kind);
+                    if (got & ARP_HB_NEED_H) bits |= 1u << ARP_SIFT_HBOND;
+                    if (got & ARP_HB_NEED_W) bits |= 1u << ARP_SIFT_WEAK_HBOND;
+                } else if (kind == CLS_KIND_HAL) {
+                    if (rule_is_halogen_weak_hbond(A.side, P, __float_as_int(pd.w), __float_as_int(pa.w), pa.x, pa.y, pa.z,
+                                                   fa, vdw_a)) bits = 1u << ARP_SIFT_WEAK_HBOND;
+                } else {
+                    uint32_t fault = 0;
+                    if (rule_is_xbond(A.side, P, __float_as_int(pd.w), pd.x, pd.y, pd.z, pa.x, pa.y, pa.z,
+                                      A.att4[e.x].x, &fault)) bits = 1u << ARP_SIFT_XBOND;
+                    bits |= fault;
+                }
+                if (bits) atomicOr(reinterpret_cast<unsigned*>(&rec[idx].z), bits);
             }
-            if (bits) atomicOr(reinterpret_cast<unsigned*>(&s_rec[buf][idx].z), bits);
         }
-        __syncthreads();
+        __syncwarp();
         /* ---- stage 3: the tile leaves through the TMA engine ---- */
-        if (threadIdx.x == 0) bulk_store_tile(A.out + base, s_rec[buf], cnt * (uint32_t)sizeof(arp_pair));
+        if (lane == 0) bulk_store_tile(A.out + base, rec, cnt * (uint32_t)sizeof(arp_pair));
     }
-    if (threadIdx.x == 0) bulk_store_wait_read_all();            /* shared memory must outlive the copies */
+    if (lane == 0) bulk_store_wait_read_all();                   /* shared memory must outlive the copies */
 }
 
 /* K x K table of the float32 proximity thresholds (interactions.py:717-718, :760-768): NumPy narrows
@@ -765,9 +772,10 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         CA.pos4 = SA.pos4; CA.att4 = SA.att4; CA.hits = SA.hits; CA.meta = meta;
         CA.out = c->out.as<arp_pair>(); CA.out_cap = c->out_cap; CA.side = side;
         size_t tiles = (size_t)((c->out_cap + CLS_TILE - 1) / CLS_TILE);
+        size_t blocks_needed = (tiles + CLS_WARPS - 1) / CLS_WARPS;
         unsigned cgrid = (unsigned)(c->sm_count * 3);
-        if (tiles < cgrid) cgrid = (unsigned)(tiles ? tiles : 1);
-        k_classify<<<cgrid, CLS_THREADS, 0, st>>>(CA, c->rp);
+        if (blocks_needed < cgrid) cgrid = (unsigned)(blocks_needed ? blocks_needed : 1);
+        k_classify<<<cgrid, CLS_WARPS * 32, 0, st>>>(CA, c->rp);
         ARP_LAUNCHED(c);
     } else if (with_events) {
         ARP_CUDA(c, cudaEventRecord(c->ev[2], st));

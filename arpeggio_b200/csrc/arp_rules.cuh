@@ -333,24 +333,41 @@ ARP_HD int rule_hbond_scan(const ArpSide& S, const ArpRuleParams& P, int donor, 
     return got & need;
 }
 
-/* utils.is_halogen_weak_hbond (utils.py:119-155) */
-ARP_HD_NOINLINE int rule_is_halogen_weak_hbond(const ArpSide& S, const ArpRuleParams& P, int donor, int halogen,
-                                               float hcx, float hcy, float hcz, uint32_t feat_hal, double vdw_hal)
+/* utils.is_halogen_weak_hbond (utils.py:119-155), screened like rule_hbond_scan */
+ARP_HD int rule_is_halogen_weak_hbond(const ArpSide& S, const ArpRuleParams& P, int donor, int halogen,
+                                      float hcx, float hcy, float hcz, uint32_t feat_hal, double vdw_hal)
 {
     if (!(feat_hal & ARP_F_HAS_XNBR) || !S.xnbr || !S.h_off) return 0;            /* utils.py:139-141 */
-    int h0 = S.h_off[donor], h1 = S.h_off[donor + 1];
+    const int h0 = S.h_off[donor], h1 = S.h_off[donor + 1];
     if (h0 == h1) return 0;
     const float* nb = S.xnbr + 3 * (size_t)halogen;
     const float hc[3] = { hcx, hcy, hcz };
-    double lim = d_add(d_add(P.h_vdw, vdw_hal), P.vdw_comp);                       /* utils.py:149 */
+    const double lim = d_add(d_add(P.h_vdw, vdw_hal), P.vdw_comp);                 /* utils.py:149 */
+    const double lim2 = lim * lim;
+    const double lim2_lo = lim2 * (1.0 - 1e-15), lim2_hi = lim2 * (1.0 + 1e-15);
+    const float w1x = nb[0] - hcx, w1y = nb[1] - hcy, w1z = nb[2] - hcz;           /* estimate of neighbour - halogen */
+    const float q1 = w1x * w1x + w1y * w1y + w1z * w1z;
+#pragma unroll 1
     for (int k = h0; k < h1; ++k) {
         const double* h = S.h_xyz + 3 * (size_t)k;
-        double vx = d_sub((double)hcx, h[0]), vy = d_sub((double)hcy, h[1]), vz = d_sub((double)hcz, h[2]);
-        double h_dist = np_norm3_f64(vx, vy, vz, P.blas_fma);                      /* utils.py:147 */
-        if (h_dist <= lim) {
-            double c = cos_angle_ffd(nb, hc, h);
-            if (acos_is_nan(c) ? P.pi_in_cx : (c <= P.cos_cx_min && c >= P.cos_cx_max)) return 1;  /* utils.py:151 */
+        const double vx = d_sub((double)hcx, h[0]), vy = d_sub((double)hcy, h[1]), vz = d_sub((double)hcz, h[2]);
+        const double s = np_dot3_f64(vx, vy, vz, vx, vy, vz, P.blas_fma);          /* h_dist^2, utils.py:147 */
+        bool within;
+        if (s < lim2_lo) within = true;
+        else if (s > lim2_hi) within = false;
+        else within = d_sqrt(s) <= lim;
+        if (!within) continue;
+        /* get_angle(neighbour, halogen, h): v2 = h - halogen = -(vx, vy, vz) */
+        const float q2 = (float)s;
+        const float dt = -(w1x * (float)vx + w1y * (float)vy + w1z * (float)vz);
+        const float ce = dt * fast_rsqrt(q1 * q2);
+        const float tol = 2e-5f;
+        if (q1 > 1e-12f && q2 > 1e-12f && q1 < 1e12f && q2 < 1e12f && ce > -0.9999f && ce < 0.9999f) {
+            if (ce < (float)P.cos_cx_min - tol && ce > (float)P.cos_cx_max + tol) return 1;
+            if (ce > (float)P.cos_cx_min + tol || ce < (float)P.cos_cx_max - tol) continue;
         }
+        const double c = cos_angle_ffd(nb, hc, h);
+        if (acos_is_nan(c) ? P.pi_in_cx : (c <= P.cos_cx_min && c >= P.cos_cx_max)) return 1;  /* utils.py:151 */
     }
     return 0;
 }

@@ -1,0 +1,112 @@
+"""Whole-batch runs: independent structures, one per stream slot, sharded over the GPUs of a box.
+
+The reference processes one structure per process invocation (process_protein_cli.py:153-198);
+structures share no state, so a batch shards with no collective on the data path:
+  - across GPUs: `shard_indices` gives every rank (one process per GPU) its part of the list,
+    greedy longest-first by atom count so that the ranks finish together;
+  - inside a GPU: `BatchRunner` keeps `slots` contexts (device buffers + stream each) busy from
+    `slots` host threads, so the H2D copy of one structure, the kernels of another and the D2H
+    copy of a third overlap (PCIe is full duplex; ctypes releases the GIL during the calls).
+"""
+import queue
+import threading
+import time
+
+import numpy as np
+
+from . import abi
+from .engine import ContactEngine, PinnedBuffer
+
+
+def shard_indices(sizes, world_size, rank):
+    """Indices of the structures rank `rank` of `world_size` processes.  sizes: atoms per structure.
+    Greedy longest-processing-time assignment (deterministic: ties by index), returned ascending."""
+    if not 0 <= rank < world_size:
+        raise ValueError('rank out of range')
+    sizes = np.asarray(sizes, dtype=np.int64)
+    order = np.lexsort((np.arange(sizes.shape[0]), -sizes))
+    load = [0] * world_size
+    mine = []
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        load[r] += int(sizes[i]) + 1
+        if r == rank:
+            mine.append(int(i))
+    return sorted(mine)
+
+
+class BatchRunner:
+    """`slots` ContactEngines on one device, driven by `slots` worker threads."""
+
+    def __init__(self, device=0, slots=3, params=None):
+        self.device = device
+        self.engines = [ContactEngine(device, params) for _ in range(max(1, slots))]
+        self._pins = [None] * len(self.engines)
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+        for p in self._pins:
+            if p is not None:
+                p.free()
+        self.engines, self._pins = [], []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_params(self, p):
+        for e in self.engines:
+            e.set_params(p)
+
+    def _out_buffer(self, slot, n):
+        pb = self._pins[slot]
+        if pb is None or pb.nbytes < 16 * n:
+            if pb is not None:
+                pb.free()
+            pb = self._pins[slot] = PinnedBuffer(16 * (n + n // 8 + 1024))
+        return pb.array(abi.PAIR_DTYPE)
+
+    def run(self, soas, consume=None, sorted=False, check_finite=True):
+        """Upload -> grid build + pair kernels -> fetch for every AtomSoA of `soas`.
+
+        consume(index, records): called in the worker thread with a view of the slot's pinned record
+        buffer (valid only during the call).  Returns (pairs_per_structure, seconds)."""
+        soas = list(soas)
+        counts = [0] * len(soas)
+        todo = queue.SimpleQueue()
+        for i in range(len(soas)):
+            todo.put(i)
+        errors = []
+
+        def work(slot):
+            eng = self.engines[slot]
+            try:
+                while True:
+                    try:
+                        i = todo.get_nowait()
+                    except queue.Empty:
+                        return
+                    eng.upload_atoms(soas[i], check_finite=check_finite)
+                    n = eng.run_pairs()
+                    rec = eng.fetch_pairs(n, sorted=sorted, out=self._out_buffer(slot, n))
+                    counts[i] = n
+                    if consume is not None:
+                        consume(i, rec)
+            except Exception as err:           # surface the first failure in the caller's thread
+                errors.append(err)
+
+        t0 = time.perf_counter()
+        threads = [threading.Thread(target=work, args=(s,)) for s in range(len(self.engines))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for e in self.engines:
+            e.sync()
+        dt = time.perf_counter() - t0
+        if errors:
+            raise errors[0]
+        return counts, dt

@@ -346,7 +346,10 @@ struct SearchArgs {
     int           include_seq_adjacent;
 };
 
-__device__ __forceinline__ void search_drain(const SearchArgs& A, uint2* q, unsigned n, int lane)
+/* Queued candidates of one warp: float32 d^2 <= r2_hi.  32 per round: the exact double test of
+   Bio.PDB.kdtrees inside the band, orientation (atom_bgn = lower list index), the reference's `continue`
+   filters; survivors are compacted in place and appended to the hit list behind one cursor atomic. */
+__device__ __forceinline__ void search_drain(const SearchArgs& A, uint2* q, unsigned n, float r2_lo, int lane)
 {
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned ns = 0;
@@ -356,11 +359,15 @@ __device__ __forceinline__ void search_drain(const SearchArgs& A, uint2* q, unsi
         uint2 e = make_uint2(0, 0);
         if (idx < n) {
             e = q[idx];
-            const int oa = __float_as_int(A.pos4[e.x].w), ob = __float_as_int(A.pos4[e.y].w);
-            if (ob < oa) { unsigned t = e.x; e.x = e.y; e.y = t; }                 /* atom_bgn = lower list index */
+            const float4 pa = A.pos4[e.x], pb = A.pos4[e.y];
+            const float ddx = pa.x - pb.x, ddy = pa.y - pb.y, ddz = pa.z - pb.z;
+            const float d2 = __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, __fmul_rn(ddx, ddx)));   /* as in the search loop */
+            keep = true;
+            if (!(d2 <= r2_lo)) keep = kd_within(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, A.r2);
+            if (__float_as_int(pb.w) < __float_as_int(pa.w)) { unsigned t = e.x; e.x = e.y; e.y = t; }
             const uint4 ab = A.att4[e.x], ae = A.att4[e.y];
-            keep = rule_pair_survives(ab.x, (int)ab.y, (int)ab.z, (int)ab.w, ae.x, (int)ae.y, (int)ae.z, (int)ae.w,
-                                      A.include_seq_adjacent);
+            keep = keep && rule_pair_survives(ab.x, (int)ab.y, (int)ab.z, (int)ab.w, ae.x, (int)ae.y, (int)ae.z, (int)ae.w,
+                                              A.include_seq_adjacent);
         }
         const unsigned m = __ballot_sync(FULL, keep);
         if (keep) q[ns + __popc(m & lt_mask)] = e;                                 /* ns <= r: never ahead of the reads */
@@ -387,16 +394,59 @@ __device__ __forceinline__ int fast_div(int n, int d)
     return q;
 }
 
-__global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) k_search(SearchArgs A)
+/* one chunk of <= 32 * NS candidates (registers) against the home atoms [0, h_end) of the cell */
+template <int NS>
+__device__ __forceinline__ void search_chunk(const SearchArgs& A, uint2* q, uint32_t q_addr, unsigned& qcount,
+                                             const float (&cxs)[SEARCH_SLOTS], const float (&cys)[SEARCH_SLOTS],
+                                             const float (&czs)[SEARCH_SLOTS], const int (&cg)[SEARCH_SLOTS],
+                                             int k_lane, bool first_chunk, int hb, int h_end, float r2_lo, float r2_hi,
+                                             int lane, unsigned lt_mask)
+{
+    for (int h = 0; h < h_end; ++h) {
+        float hx, hy, hz;
+        if (first_chunk && h < 32) {       /* candidate k = h of run 0 is home atom h */
+            hx = __shfl_sync(FULL, cxs[0], h); hy = __shfl_sync(FULL, cys[0], h); hz = __shfl_sync(FULL, czs[0], h);
+        } else {
+            const float4 hp = A.pos4[hb + h];
+            hx = hp.x; hy = hp.y; hz = hp.z;
+        }
+        const unsigned home = (unsigned)(hb + h);
+        const int hk = h - k_lane;         /* candidate k = k_lane + 32 sl is live iff 32 sl > hk */
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl) {
+            const float ddx = hx - cxs[sl], ddy = hy - cys[sl], ddz = hz - czs[sl];
+            const float d2 = __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, __fmul_rn(ddx, ddx)));
+            const bool hit = (d2 <= r2_hi) && (32 * sl > hk);          /* padding lanes sit at +inf */
+            const unsigned m = __ballot_sync(FULL, hit);
+            if (hit) {
+                const uint32_t addr = q_addr + 8u * (qcount + __popc(m & lt_mask));
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(addr), "r"(home), "r"((unsigned)cg[sl]) : "memory");
+            }
+            qcount += __popc(m);
+        }
+        if (qcount >= SEARCH_DRAIN) {
+            __syncwarp();
+            search_drain(A, q, qcount, r2_lo, lane);
+            qcount = 0;
+        }
+    }
+}
+
+#ifndef SEARCH_MINB
+#define SEARCH_MINB 3
+#endif
+__global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(SearchArgs A)
 {
     __shared__ uint2 s_queue[SEARCH_WARPS][SEARCH_QCAP];
     __shared__ int2  s_runs[SEARCH_WARPS][SEARCH_CELLS][8];      /* per cell: 5 x (first index, prefix); [5] = (total, nh); [6] = band */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint2* q = s_queue[warp];
+    const uint32_t q_addr = (uint32_t)__cvta_generic_to_shared(q);
     unsigned qcount = 0;                        /* linear queue: drained completely once it holds >= SEARCH_DRAIN hits */
     unsigned long long ncand = 0;
     unsigned nonempty = 0;
     const unsigned lt_mask = (1u << lane) - 1u;
+    float last_r2_lo = -1.f;
 
     const int n_cells = (int)A.meta->n_cells;
     int s = 0;                                  /* warp-uniform: structure of the ticket's first cell */
@@ -461,63 +511,42 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) k_search(SearchArgs A)
                        r3 = s_runs[warp][qc][3], r4 = s_runs[warp][qc][4];
             const int hb = r0.x;
             const float r2_lo = __int_as_float(s_runs[warp][qc][6].x), r2_hi = __int_as_float(s_runs[warp][qc][6].y);
+            if (r2_lo != last_r2_lo) {          /* structure boundary: queued candidates carry the previous band */
+                if (qcount) { __syncwarp(); search_drain(A, q, qcount, last_r2_lo, lane); qcount = 0; }
+                last_r2_lo = r2_lo;
+            }
             /* tests of this cell: home atom h meets candidates k > h */
-            ncand += (unsigned long long)nh * (unsigned)total - (unsigned long long)nh * (unsigned)(nh + 1) / 2;
+            ncand += (unsigned long long)((long long)nh * total - (long long)nh * (nh + 1) / 2);
 
             for (int k0 = 0; k0 < total; k0 += SEARCH_CHUNK) {
                 float cxs[SEARCH_SLOTS], cys[SEARCH_SLOTS], czs[SEARCH_SLOTS];
-                int   cg[SEARCH_SLOTS], ck[SEARCH_SLOTS];
+                int   cg[SEARCH_SLOTS];
 #pragma unroll
                 for (int sl = 0; sl < SEARCH_SLOTS; ++sl) {
                     const int k = k0 + sl * 32 + lane;
-                    cg[sl] = 0; ck[sl] = -1;
-                    cxs[sl] = cys[sl] = czs[sl] = 0.f;
+                    cg[sl] = 0;
+                    cxs[sl] = cys[sl] = czs[sl] = __int_as_float(0x7f800000);     /* +inf: never within any cutoff */
                     if (k < total) {
                         const int g = k < r1.y ? r0.x + k : k < r2.y ? r1.x + (k - r1.y) : k < r3.y ? r2.x + (k - r2.y)
                                     : k < r4.y ? r3.x + (k - r3.y) : r4.x + (k - r4.y);
                         const float4 p = A.pos4[g];
                         cxs[sl] = p.x; cys[sl] = p.y; czs[sl] = p.z;
-                        cg[sl] = g; ck[sl] = k;
+                        cg[sl] = g;
                     }
                 }
                 /* home atoms that still have candidates in this chunk: k > h */
                 const int h_end = min(nh, k0 + SEARCH_CHUNK - 1);
-                for (int h = 0; h < h_end; ++h) {
-                    float hx, hy, hz;
-                    if (k0 == 0 && h < 32) {       /* candidate k = h of run 0 is home atom h */
-                        hx = __shfl_sync(FULL, cxs[0], h); hy = __shfl_sync(FULL, cys[0], h); hz = __shfl_sync(FULL, czs[0], h);
-                    } else {
-                        const float4 hp = A.pos4[hb + h];
-                        hx = hp.x; hy = hp.y; hz = hp.z;
-                    }
-                    const unsigned home = (unsigned)(hb + h);
-#pragma unroll
-                    for (int sl = 0; sl < SEARCH_SLOTS; ++sl) {
-                        if (k0 + sl * 32 >= total) break;                 /* warp-uniform */
-                        const float ddx = hx - cxs[sl], ddy = hy - cys[sl], ddz = hz - czs[sl];
-                        const float d2 = __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, __fmul_rn(ddx, ddx)));
-                        const bool live = ck[sl] > h;
-                        bool hit = live && (d2 <= r2_lo);                 /* certainly within the cutoff */
-                        const bool maybe = live && !(d2 <= r2_lo) && (d2 <= r2_hi);
-                        if (__any_sync(FULL, maybe)) {                    /* rare: the exact test of Bio.PDB.kdtrees */
-                            if (maybe) hit = kd_within(hx, hy, hz, cxs[sl], cys[sl], czs[sl], A.r2);
-                        }
-                        const unsigned m = __ballot_sync(FULL, hit);
-                        if (hit) q[qcount + __popc(m & lt_mask)] = make_uint2(home, (unsigned)cg[sl]);
-                        qcount += __popc(m);
-                    }
-                    if (qcount >= SEARCH_DRAIN) {
-                        __syncwarp();
-                        search_drain(A, q, qcount, lane);
-                        qcount = 0;
-                    }
-                }
+                const int left = total - k0;
+                if (left > 96)      search_chunk<4>(A, q, q_addr, qcount, cxs, cys, czs, cg, k0 + lane, k0 == 0, hb, h_end, r2_lo, r2_hi, lane, lt_mask);
+                else if (left > 64) search_chunk<3>(A, q, q_addr, qcount, cxs, cys, czs, cg, k0 + lane, k0 == 0, hb, h_end, r2_lo, r2_hi, lane, lt_mask);
+                else if (left > 32) search_chunk<2>(A, q, q_addr, qcount, cxs, cys, czs, cg, k0 + lane, k0 == 0, hb, h_end, r2_lo, r2_hi, lane, lt_mask);
+                else                search_chunk<1>(A, q, q_addr, qcount, cxs, cys, czs, cg, k0 + lane, k0 == 0, hb, h_end, r2_lo, r2_hi, lane, lt_mask);
             }
         }
     }
     if (qcount) {
         __syncwarp();
-        search_drain(A, q, qcount, lane);
+        search_drain(A, q, qcount, last_r2_lo, lane);
     }
     if (lane == 0) {
         if (ncand) atomicAdd(&A.meta->n_candidates, ncand);
@@ -761,7 +790,7 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         SA.pos4 = c->pos4.as<float4>(); SA.att4 = c->att4.as<uint4>(); SA.cell_start = c->cell_start.as<int>();
         SA.geom = c->geom.as<StructGeom>(); SA.meta = meta; SA.hits = c->hits.as<uint2>(); SA.hit_cap = c->out_cap;
         SA.r2 = c->rp.r2; SA.include_seq_adjacent = c->rp.include_seq_adjacent;
-        unsigned grid = (unsigned)(c->sm_count * 4);
+        unsigned grid = (unsigned)(c->sm_count * SEARCH_MINB);
         size_t want = ((size_t)N / 24) / SEARCH_WARPS + 1;     /* about one warp per few cells on small inputs */
         if (want < grid) grid = (unsigned)want;
         k_search<<<grid, SEARCH_WARPS * 32, 0, st>>>(SA);

@@ -1,0 +1,193 @@
+"""Drop-in for the contact engine of ``arpeggio.core.InteractionComplex``.
+
+``CudaContactsMixin`` overrides the three protected methods through which
+``InteractionComplex.run_arpeggio`` (arpeggio/core/interactions.py:329-347) reaches the contact
+loops -- ``_calculate_atom_contacts`` (:693), ``_calculate_ring_contacts`` (:938) and
+``_calculate_group_contacts`` (:1208) -- and fills the same result bags (``atom_contacts``,
+``plane_plane_contacts``, ``atom_plane_contacts``, ``group_group_contacts``,
+``group_plane_contacts``, :84-88) with the reference's own namedtuples, so that
+``get_contacts()`` (:172-212) and everything downstream run unchanged.  Everything before the
+loops (file parsing, typing, ``_make_selection``) stays the reference's host code.
+
+    from arpeggio_b200.dropin import cuda_interaction_complex
+    InteractionComplex = cuda_interaction_complex()        # subclass of arpeggio.core.InteractionComplex
+    ic = InteractionComplex('1tqn_h.cif'); ic.structure_checks(); ic.initialize()
+    ic.run_arpeggio(['/A/508/'], 5.0, 0.1, False); contacts = ic.get_contacts()
+
+Not reproduced: the per-atom / per-residue SIFt counters the reference updates as a
+side effect inside the loops (interactions.py:822-852, :924-934, :1040-1057, :1171-1176); they
+feed only the CSV writers the reference CLI has disabled.  List order: the reference emits pairs in
+KD-tree traversal order; here records come out sorted by (bgn index, end index) of
+``selection_plus``.
+"""
+import collections
+
+import numpy as np
+
+from . import abi, params as arp_params
+from .engine import ContactEngine
+from .packing import pack_complex
+
+# the reference's record types (interactions.py:19-29); the real ones are used when importable
+AtomPlaneContact = collections.namedtuple('AtomPlaneContact',
+                                          ['bgn_atom', 'end_res', 'end_res_atoms', 'distance', 'sifts', 'text'])
+PlanePlaneContact = collections.namedtuple('PlanePlaneContact',
+                                           ['bgn_id', 'bgn_res', 'bgn_res_atoms', 'end_id', 'end_res', 'end_res_atoms',
+                                            'distance', 'contact_type', 'text'])
+AtomAtomContact = collections.namedtuple('AtomAtomContact', ['bgn_atom', 'end_atom', 'sifts', 'contact_type', 'distance'])
+
+_ENGINES = {}
+
+
+def shared_engine(device=0):
+    """One ContactEngine per device and process (a context is not re-entrant: callers that drive
+    several complexes from several threads should give every thread its own engine instead)."""
+    eng = _ENGINES.get(device)
+    if eng is None:
+        eng = _ENGINES[device] = ContactEngine(device)
+    return eng
+
+
+def _record_types(obj):
+    """The namedtuple classes of the module the host class comes from (so that isinstance / pickling
+    by reference users keep working), else the local mirrors."""
+    import sys
+    for klass in type(obj).__mro__:
+        mod = sys.modules.get(klass.__module__)
+        if mod is not None and all(hasattr(mod, n) for n in ('AtomAtomContact', 'PlanePlaneContact', 'AtomPlaneContact')):
+            return mod.AtomAtomContact, mod.PlanePlaneContact, mod.AtomPlaneContact
+    return AtomAtomContact, PlanePlaneContact, AtomPlaneContact
+
+
+def _contact_types_of(obj):
+    """config.CONTACT_TYPES of the reference the host class belongs to (single source of truth for the
+    thresholds, config.py:592-660), else the defaults mirrored in params.py."""
+    import sys
+    for klass in type(obj).__mro__:
+        mod = sys.modules.get(klass.__module__)
+        cfg = getattr(mod, 'config', None) if mod is not None else None
+        if cfg is not None and hasattr(cfg, 'CONTACT_TYPES'):
+            return cfg.CONTACT_TYPES, getattr(cfg, 'CONTACT_TYPES_DIST_MAX', arp_params.DEFAULT_DIST_MAX), \
+                getattr(cfg, 'VDW_RADII', {}).get('H', arp_params.DEFAULT_H_VDW)
+    return None, arp_params.DEFAULT_DIST_MAX, arp_params.DEFAULT_H_VDW
+
+
+class CudaContactsMixin:
+    """Mix in before ``arpeggio.core.InteractionComplex`` (or a duck-typed stand-in)."""
+
+    cuda_device = 0
+    cuda_engine = None          # set to a private ContactEngine to avoid the shared one
+
+    # ------------------------------------------------------------------
+    def _cuda_engine(self):
+        return self.cuda_engine if self.cuda_engine is not None else shared_engine(self.cuda_device)
+
+    def _cuda_packed(self):
+        """SoA image of the current selection (rebuilt whenever _make_selection produced new lists)."""
+        key = (id(self.selection_plus), len(self.selection_plus), id(self.selection), len(self.selection))
+        cached = getattr(self, '_cuda_pack_cache', None)
+        if cached is None or cached[0] != key:
+            cached = (key, pack_complex(self, ob=getattr(self, '_cuda_ob_module', None)))
+            self._cuda_pack_cache = cached
+        return cached[1]
+
+    def _cuda_params(self, interacting_cutoff=None, vdw_comp_factor=None, include_sequence_adjacent=None):
+        last = getattr(self, '_cuda_last_run', None)
+        if interacting_cutoff is None:
+            if last is None:
+                p = getattr(self, 'params', None)      # Parameters namedtuple of __init__ (interactions.py:41-43)
+                last = (getattr(p, 'interacting_threshold', 5.0), getattr(p, 'vdw_comp_factor', 0.1), False)
+            interacting_cutoff, vdw_comp_factor, include_sequence_adjacent = last
+        ct, dist_max, h_vdw = _contact_types_of(self)
+        return arp_params.make_params(interacting_cutoff, vdw_comp_factor, include_sequence_adjacent,
+                                      contact_types=ct, dist_max=dist_max, h_vdw=h_vdw)
+
+    # ------------------------------------------------------------------
+    def _calculate_atom_contacts(self, interacting_cutoff, vdw_comp_factor, include_sequence_adjacent):
+        """Replaces interactions.py:693-936 (neighbour search + per-pair rules) with the CUDA path."""
+        AAC, _, _ = _record_types(self)
+        self._cuda_last_run = (interacting_cutoff, vdw_comp_factor, include_sequence_adjacent)
+        packed = self._cuda_packed()
+        eng = self._cuda_engine()
+        eng.set_params(self._cuda_params(interacting_cutoff, vdw_comp_factor, include_sequence_adjacent))
+        rec = eng.pairs(packed.soa, sorted=True)
+        if rec.shape[0] and np.any(rec['mask'] & np.uint32(abi.PAIR_FAULT_XBOND_NO_NBR)):
+            # utils.is_xbond dereferences None when the donor has no single-bond neighbour (utils.py:173)
+            raise AttributeError("'NoneType' object has no attribute 'coord'")
+        atoms = packed.atoms
+        masks = rec['mask']
+        bits = ((masks[:, None] >> np.arange(abi.SIFT_NBITS, dtype=np.uint32)) & 1).astype(np.int64).tolist()
+        classes = ((masks >> abi.CLASS_SHIFT) & abi.CLASS_MASK).tolist()
+        dist = rec['dist']
+        out = []
+        for k, (i, j) in enumerate(zip(rec['i'].tolist(), rec['j'].tolist())):
+            out.append(AAC(atoms[i], atoms[j], bits[k], abi.CLASS_NAMES[classes[k]], dist[k]))
+        self.atom_contacts = out
+
+    def _calculate_ring_contacts(self):
+        """Replaces interactions.py:938-1194 (plane-plane and atom-plane)."""
+        _, PPC, APC = _record_types(self)
+        packed = self._cuda_packed()
+        eng = self._cuda_engine()
+        eng.set_params(self._cuda_params())
+        eng.upload_atoms(packed.soa)
+        eng.upload_planes(packed.rings, packed.amides)
+        rings = self.biopython_str.rings
+        names = {}
+
+        def ring_atoms(key):
+            v = names.get(key)
+            if v is None:
+                v = names[key] = sorted(a.get_id() for a in rings[key]['atoms'])
+            return v
+
+        self.plane_plane_contacts = []
+        for r in eng.ring_ring():
+            ka, kb = packed.ring_keys[int(r['a'])], packed.ring_keys[int(r['b'])]
+            code = int(r['code'])
+            labels = [abi.GEOM_NAMES[code & 0xF]]
+            if (code >> 4) & 0xF != 0xF:
+                labels.append(abi.GEOM_NAMES[(code >> 4) & 0xF])
+            self.plane_plane_contacts.append(PPC(ka, rings[ka]['residue'], list(ring_atoms(ka)), kb, rings[kb]['residue'],
+                                                 list(ring_atoms(kb)), np.float64(r['dist']), labels,
+                                                 abi.CLASS_NAMES[(code >> 8) & 7]))
+        self.atom_plane_contacts = []
+        for r in eng.atom_ring():
+            key = packed.ring_keys[int(r['ring'])]
+            code = int(r['code'])
+            labels = sorted(n for b, n in enumerate(abi.AP_NAMES) if code >> b & 1)
+            self.atom_plane_contacts.append(APC(packed.atoms[int(r['atom'])], rings[key]['residue'], list(ring_atoms(key)),
+                                                np.float64(r['dist']), labels, abi.CLASS_NAMES[(code >> 8) & 7]))
+
+    def _calculate_group_contacts(self):
+        """Replaces interactions.py:1208-1382 (amide-amide and amide-ring)."""
+        _, PPC, _ = _record_types(self)
+        packed = self._cuda_packed()
+        eng = self._cuda_engine()
+        eng.set_params(self._cuda_params())
+        eng.upload_planes(packed.rings, packed.amides)
+        rings, amides = self.biopython_str.rings, self.biopython_str.amides
+
+        def names(group):
+            return sorted(a.get_id() for a in group['atoms'])
+
+        self.group_group_contacts = []
+        for r in eng.amide_amide():
+            a, b = amides[packed.amide_keys[int(r['a'])]], amides[packed.amide_keys[int(r['b'])]]
+            self.group_group_contacts.append(PPC(a['amide_id'], a['residue'], names(a), b['amide_id'], b['residue'], names(b),
+                                                 np.float32(r['dist']), ['AMIDEAMIDE'],
+                                                 abi.CLASS_NAMES[(int(r['code']) >> 8) & 7]))
+        self.group_plane_contacts = []
+        for r in eng.amide_ring():
+            a, g = amides[packed.amide_keys[int(r['a'])]], rings[packed.ring_keys[int(r['b'])]]
+            self.group_plane_contacts.append(PPC(a['amide_id'], a['residue'], names(a), g['ring_id'], g['residue'], names(g),
+                                                 np.float64(r['dist']), ['AMIDERING'],
+                                                 abi.CLASS_NAMES[(int(r['code']) >> 8) & 7]))
+
+
+def cuda_interaction_complex(base_cls=None, device=0):
+    """A subclass of ``arpeggio.core.InteractionComplex`` (or of ``base_cls``) whose contact engine is
+    libarpeggio_cuda.so.  Importing the reference needs BioPython, OpenBabel and gemmi."""
+    if base_cls is None:
+        from arpeggio.core import InteractionComplex as base_cls   # noqa: N813
+    return type('CudaInteractionComplex', (CudaContactsMixin, base_cls), {'cuda_device': device})

@@ -97,9 +97,9 @@ class ContactEngine:
         self._check(self._L.arp_set_params(self._ctx, C.byref(p)))
         self.params = p
 
-    def upload_atoms(self, soa):
+    def upload_atoms(self, soa, check_finite=True):
         """soa: AtomSoA.  Coordinates must be finite (the reference would compare NaNs false)."""
-        if soa.n_atoms and not np.isfinite(soa.xyz).all():
+        if check_finite and soa.n_atoms and not np.isfinite(soa.xyz).all():
             raise ValueError('non-finite atom coordinates')
         a = soa.as_ctypes()
         self._check(self._L.arp_upload_atoms(self._ctx, C.byref(a)))

@@ -184,6 +184,7 @@ def run_ours(args):
         dist.init_process_group('gloo', rank=rank, world_size=world)
 
     from arpeggio_b200 import abi, params as arp_params, synth
+    from arpeggio_b200.batch import BatchRunner
     from arpeggio_b200.engine import ContactEngine, PinnedBuffer
     from arpeggio_b200.soa import AtomSoA
 
@@ -244,23 +245,35 @@ def run_ours(args):
     for _ in range(e2e_steps):
         e2e_step()
     eng.sync()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_serial_s = (time.perf_counter() - t0) / e2e_steps
+    # the batch API: the same steps through 3 stream slots, so that the H2D copy of one step, the kernels of
+    # another and the D2H copy of a third overlap; every step still moves its own inputs and results
+    runner = BatchRunner(device=local, slots=3, params=p)
+    checked = []
+    runner.run([host] * 6, consume=lambda i, rec: checked.append(int(rec.shape[0])))
+    assert checked and all(c == n_pairs for c in checked)
+    if dist:
+        dist.barrier()
+    _, dt = runner.run([host] * e2e_steps, check_finite=False)
+    e2e_s = dt / e2e_steps
+    runner.close()
     t_end = time.time()
     clocks = sampler.stop(t_begin, t_end) if sampler else None
 
     # ---- aggregate over ranks: slowest rank's time, total pairs ------------------------------
-    tot_pairs, ms_max, e2e_max, ms_kernel = float(n_pairs), ms_step, e2e_s, st['ms_search']
+    ms_pair = st['ms_search'] + st['ms_classify']
+    tot_pairs, ms_max, e2e_max, e2e_serial_max = float(n_pairs), ms_step, e2e_s, e2e_serial_s
     if dist:
         import torch
-        t = torch.tensor([ms_step, e2e_s, st['ms_search']], dtype=torch.float64)
+        t = torch.tensor([ms_step, e2e_s, e2e_serial_s], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         s = torch.tensor([float(n_pairs)], dtype=torch.float64)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        ms_max, e2e_max, ms_kernel, tot_pairs = float(t[0]), float(t[1]), float(t[2]), float(s[0])
+        ms_max, e2e_max, e2e_serial_max, tot_pairs = float(t[0]), float(t[1]), float(t[2]), float(s[0])
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        achieved = alg_bytes / (st['ms_search'] * 1e-3) / 1e9
+        achieved = alg_bytes / (ms_pair * 1e-3) / 1e9
         line = {
             'metric': METRIC, 'value': tot_pairs / (ms_max * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_max, 'higher_is_better': True, 'scaling': 'weak',
@@ -270,12 +283,17 @@ def run_ours(args):
                        'timing': 'sum of per-step CUDA-event brackets on the library stream, max over ranks',
                        'sharding': 'one independent structure per GPU, no collective'},
             'e2e': {'value': tot_pairs / e2e_max, 'unit': UNIT, 'h2d_bytes_per_step': int(in_bytes),
-                    'd2h_bytes_per_step': int(16 * n_pairs + 64), 'steps': e2e_steps, 'ms_per_step': e2e_max * 1e3},
+                    'd2h_bytes_per_step': int(16 * n_pairs + 64), 'steps': e2e_steps, 'ms_per_step': e2e_max * 1e3,
+                    'api': 'BatchRunner.run, 3 stream slots, pinned host buffers',
+                    'serial_value': tot_pairs / e2e_serial_max, 'serial_ms_per_step': e2e_serial_max * 1e3,
+                    'serial_api': 'ContactEngine.upload_atoms + run_pairs + fetch_pairs, one stream'},
             'gpu_launches': int(launches),
             'kernels_per_step': int(launches // max(args.steps, 1)),
-            'roofline': {'bound': 'hbm', 'kernel': 'k_pairs', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': ncu_traffic(args.atoms), 'algorithmic_bytes': int(alg_bytes),
-                         'kernel_ms': st['ms_search'], 'grid_build_ms': st['ms_grid'], 'peak_source': peak_src},
+            'roofline': {'bound': 'hbm', 'kernel': 'k_search + k_classify (the pair kernels, timed together)',
+                         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': ncu_traffic(args.atoms), 'algorithmic_bytes': int(alg_bytes), 'kernel_ms': ms_pair,
+                         'search_ms': st['ms_search'], 'classify_ms': st['ms_classify'], 'grid_build_ms': st['ms_grid'],
+                         'peak_source': peak_src},
             'clocks': clocks,
             'candidate_tests_per_step': int(st['n_candidates']),
         }

@@ -1,0 +1,64 @@
+"""Host-side logic of batch runs without a GPU: sharding of the structure list over ranks, and the
+world_size-2 reduction bench.py performs (gloo, CPU)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from arpeggio_b200.batch import shard_indices
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('world', [1, 2, 3, 8])
+def test_shards_partition_the_list(world):
+    rng = np.random.default_rng(world)
+    sizes = rng.integers(100, 50_000, size=257)
+    parts = [shard_indices(sizes, world, r) for r in range(world)]
+    flat = sorted(i for p in parts for i in p)
+    assert flat == list(range(257))
+    loads = [int(sizes[p].sum()) for p in parts]
+    assert max(loads) - min(loads) <= int(sizes.max())          # longest-first greedy bound
+    assert parts == [shard_indices(sizes, world, r) for r in range(world)]   # deterministic
+
+
+def test_shard_edge_cases():
+    assert shard_indices([], 4, 0) == []
+    assert shard_indices([10], 4, 0) == [0] and shard_indices([10], 4, 3) == []
+    with pytest.raises(ValueError):
+        shard_indices([1, 2], 2, 2)
+
+
+def test_world_size_2_gloo_reduction(tmp_path):
+    """Two CPU ranks shard a structure list, 'process' it, and reduce (max time, sum pairs) the way
+    bench.py does under torchrun."""
+    script = tmp_path / 'rank.py'
+    script.write_text(textwrap.dedent(f'''
+        import os, sys
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np, torch, torch.distributed as dist
+        from arpeggio_b200.batch import shard_indices
+        rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+        sizes = np.arange(1, 41) * 100
+        mine = shard_indices(sizes, world, rank)
+        pairs = float(sum(13 * sizes[i] for i in mine))       # stand-in for the per-structure record counts
+        secs = 1.0 + rank
+        t = torch.tensor([secs], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        s = torch.tensor([pairs, float(len(mine))], dtype=torch.float64); dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            print('RESULT', float(t[0]), float(s[0]), int(s[1]))
+        dist.barrier(); dist.destroy_process_group()
+    '''))
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29613')
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                          '--master-addr', '127.0.0.1', '--master-port', '29613', str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith('RESULT')][0].split()
+    assert float(line[1]) == 2.0
+    assert float(line[2]) == 13 * 100 * sum(range(1, 41))
+    assert int(line[3]) == 40

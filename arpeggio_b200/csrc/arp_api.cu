@@ -348,7 +348,7 @@ int arp_pairs_run(arp_ctx* c, uint64_t* n_pairs)
     for (int attempt = 0; attempt < 2; ++attempt) {
         ARP_TRY(arp_pairs_enqueue(c, 1));
         ARP_CUDA(c, cudaStreamSynchronize(c->stream));
-        uint64_t n = c->h_meta->n_pairs;
+        uint64_t n = c->h_meta->n_raw;          /* candidates >= records: both lists share the capacity */
         if (n <= c->out_cap) break;
         ARP_REQUIRE(c, attempt == 0, ARP_E_CAPACITY, "record stream overflowed twice");
         ARP_TRY(pairs_out_reserve(c, n + n / 16 + 1024));

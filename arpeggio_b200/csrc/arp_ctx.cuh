@@ -43,7 +43,9 @@ struct RunMeta {
     unsigned int n_cells_nonempty;
     unsigned int ticket[4];           /* dynamic tile ids: [0] cell scan, [1] pair kernel, [2] sort scan */
     unsigned int fault;               /* sticky device-side diagnostics */
-    unsigned int pad[5];
+    unsigned int r2_lo_inv;           /* 0x7f800000 - bits(min over structures of r2_lo); 0x7f800000 = no quick accept */
+    unsigned long long n_raw;         /* candidate cursor of k_search */
+    unsigned int pad[2];
 };
 
 struct PlaneSet {
@@ -85,11 +87,12 @@ struct arp_ctx {
     DBuf geom, cell_start, cell_of, rank, pos4, att4;
     DBuf radtab;                  /* K x K float32 proximity thresholds */
     int radtab_valid = 0;
+    int cls_smem_set = 0;
     RunMeta* h_meta = nullptr;    /* pinned */
 
     /* output stream */
     DBuf out;                     /* arp_pair records */
-    DBuf hits;                    /* uint2 hit list of the search kernel, same capacity as out */
+    DBuf hits;                    /* uint2 candidate list of the search kernel, same capacity as out */
     uint64_t out_cap = 0;         /* records */
     uint64_t n_pairs = 0;
     int pairs_valid = 0;

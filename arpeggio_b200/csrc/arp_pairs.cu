@@ -161,6 +161,8 @@ __global__ void __launch_bounds__(256) k_geom(const unsigned* __restrict__ bbox,
                 g.r2_lo = finite ? __double2float_rd(lo2) : -1.0f;
                 g.r2_hi = finite ? __double2float_ru(hi2) : 3.4e38f;
                 if (!(lo2 > 0.0)) g.r2_lo = -1.0f;
+                /* k_classify uses one conservative lower edge for all structures: the minimum */
+                atomicMax(&meta->r2_lo_inv, g.r2_lo > 0.f ? 0x7f800000u - __float_as_uint(g.r2_lo) : 0x7f800000u);
             }
         }
         /* block exclusive scan of ncell */
@@ -320,13 +322,12 @@ __global__ void __launch_bounds__(256) k_scatter(int N, const float* __restrict_
 }
 
 /* ---- k_search ---------------------------------------------------------------------------------
- * Neighbour search + the reference's `continue` filters.  One warp per home cell (dynamic tickets of
- * SEARCH_CELLS cells): the home cell and its 13 forward neighbours are 5 contiguous runs of the
- * cell-sorted array; lane = candidate (held in registers), home atoms broadcast by shuffle; float32
- * prefilter with the exact double test of Bio.PDB.kdtrees inside the band; ballot compaction into a
- * per-warp shared-memory ring.  Every 128 queued hits the warp orients (bgn = lower list index) and
- * filters them 32 at a time and appends the survivors to the global hit list behind one cursor atomic.
- * The kernel is small on purpose (no rule code): 4 CTAs of 8 warps per SM hide the load latency.   */
+ * Neighbour search.  One warp per home cell (dynamic tickets of SEARCH_CELLS cells): the home cell and
+ * its 13 forward neighbours are 5 contiguous runs of the cell-sorted array; lane = candidate (held in
+ * registers), home atoms broadcast by shuffle; float32 FMA d^2 against the upper edge of the band around
+ * r^2; ballot compaction into a per-warp shared-memory queue that is appended to the global candidate
+ * list behind one cursor atomic per >= 128 candidates.  The exact test, the orientation and the filters
+ * happen densely in k_classify.  The kernel is small on purpose: many warps in flight hide the loads. */
 #define SEARCH_WARPS  8
 #define SEARCH_SLOTS  4                     /* candidates held per lane */
 #define SEARCH_CHUNK  (32 * SEARCH_SLOTS)
@@ -336,50 +337,21 @@ __global__ void __launch_bounds__(256) k_scatter(int N, const float* __restrict_
 
 struct SearchArgs {
     const float4* pos4;
-    const uint4*  att4;
     const int*    cell_start;
     const StructGeom* geom;
     RunMeta*      meta;
-    uint2*        hits;                     /* (bgn, end) cell-sorted indices of the surviving pairs */
-    unsigned long long hit_cap;
-    double        r2;
-    int           include_seq_adjacent;
+    uint2*        raw;                      /* candidate pairs (cell-sorted indices), float32 d^2 <= r2_hi */
+    unsigned long long cap;
 };
 
-/* Queued candidates of one warp: float32 d^2 <= r2_hi.  32 per round: the exact double test of
-   Bio.PDB.kdtrees inside the band, orientation (atom_bgn = lower list index), the reference's `continue`
-   filters; survivors are compacted in place and appended to the hit list behind one cursor atomic. */
-__device__ __forceinline__ void search_drain(const SearchArgs& A, uint2* q, unsigned n, float r2_lo, int lane)
+/* the warp's queued candidates go to the global candidate list behind one cursor atomic */
+__device__ __forceinline__ void search_flush(const SearchArgs& A, const uint2* q, unsigned n, int lane)
 {
-    const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned ns = 0;
-    for (unsigned r = 0; r < n; r += 32) {
-        const unsigned idx = r + lane;
-        bool keep = false;
-        uint2 e = make_uint2(0, 0);
-        if (idx < n) {
-            e = q[idx];
-            const float4 pa = A.pos4[e.x], pb = A.pos4[e.y];
-            const float ddx = pa.x - pb.x, ddy = pa.y - pb.y, ddz = pa.z - pb.z;
-            const float d2 = __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, __fmul_rn(ddx, ddx)));   /* as in the search loop */
-            keep = true;
-            if (!(d2 <= r2_lo)) keep = kd_within(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, A.r2);
-            if (__float_as_int(pb.w) < __float_as_int(pa.w)) { unsigned t = e.x; e.x = e.y; e.y = t; }
-            const uint4 ab = A.att4[e.x], ae = A.att4[e.y];
-            keep = keep && rule_pair_survives(ab.x, (int)ab.y, (int)ab.z, (int)ab.w, ae.x, (int)ae.y, (int)ae.z, (int)ae.w,
-                                              A.include_seq_adjacent);
-        }
-        const unsigned m = __ballot_sync(FULL, keep);
-        if (keep) q[ns + __popc(m & lt_mask)] = e;                                 /* ns <= r: never ahead of the reads */
-        ns += __popc(m);
-    }
-    if (ns == 0) return;
-    __syncwarp();
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&A.meta->n_pairs, (unsigned long long)ns);
+    if (lane == 0) base = atomicAdd(&A.meta->n_raw, (unsigned long long)n);
     base = __shfl_sync(FULL, base, 0);
-    for (unsigned r = lane; r < ns; r += 32)
-        if (base + r < A.hit_cap) A.hits[base + r] = q[r];
+    for (unsigned r = lane; r < n; r += 32)
+        if (base + r < A.cap) A.raw[base + r] = q[r];
     __syncwarp();
 }
 
@@ -399,7 +371,7 @@ template <int NS>
 __device__ __forceinline__ void search_chunk(const SearchArgs& A, uint2* q, uint32_t q_addr, unsigned& qcount,
                                              const float (&cxs)[SEARCH_SLOTS], const float (&cys)[SEARCH_SLOTS],
                                              const float (&czs)[SEARCH_SLOTS], const int (&cg)[SEARCH_SLOTS],
-                                             int k_lane, bool first_chunk, int hb, int h_end, float r2_lo, float r2_hi,
+                                             int k_lane, bool first_chunk, int hb, int h_end, float r2_hi,
                                              int lane, unsigned lt_mask)
 {
     for (int h = 0; h < h_end; ++h) {
@@ -426,7 +398,7 @@ __device__ __forceinline__ void search_chunk(const SearchArgs& A, uint2* q, uint
         }
         if (qcount >= SEARCH_DRAIN) {
             __syncwarp();
-            search_drain(A, q, qcount, r2_lo, lane);
+            search_flush(A, q, qcount, lane);
             qcount = 0;
         }
     }
@@ -446,7 +418,6 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
     unsigned long long ncand = 0;
     unsigned nonempty = 0;
     const unsigned lt_mask = (1u << lane) - 1u;
-    float last_r2_lo = -1.f;
 
     const int n_cells = (int)A.meta->n_cells;
     int s = 0;                                  /* warp-uniform: structure of the ticket's first cell */
@@ -510,11 +481,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
             const int2 r0 = s_runs[warp][qc][0], r1 = s_runs[warp][qc][1], r2 = s_runs[warp][qc][2],
                        r3 = s_runs[warp][qc][3], r4 = s_runs[warp][qc][4];
             const int hb = r0.x;
-            const float r2_lo = __int_as_float(s_runs[warp][qc][6].x), r2_hi = __int_as_float(s_runs[warp][qc][6].y);
-            if (r2_lo != last_r2_lo) {          /* structure boundary: queued candidates carry the previous band */
-                if (qcount) { __syncwarp(); search_drain(A, q, qcount, last_r2_lo, lane); qcount = 0; }
-                last_r2_lo = r2_lo;
-            }
+            const float r2_hi = __int_as_float(s_runs[warp][qc][6].y);
             /* tests of this cell: home atom h meets candidates k > h */
             ncand += (unsigned long long)((long long)nh * total - (long long)nh * (nh + 1) / 2);
 
@@ -537,16 +504,16 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
                 /* home atoms that still have candidates in this chunk: k > h */
                 const int h_end = min(nh, k0 + SEARCH_CHUNK - 1);
                 const int left = total - k0;
-                if (left > 96)      search_chunk<4>(A, q, q_addr, qcount, cxs, cys, czs, cg, k0 + lane, k0 == 0, hb, h_end, r2_lo, r2_hi, lane, lt_mask);
-                else if (left > 64) search_chunk<3>(A, q, q_addr, qcount, cxs, cys, czs, cg, k0 + lane, k0 == 0, hb, h_end, r2_lo, r2_hi, lane, lt_mask);
-                else if (left > 32) search_chunk<2>(A, q, q_addr, qcount, cxs, cys, czs, cg, k0 + lane, k0 == 0, hb, h_end, r2_lo, r2_hi, lane, lt_mask);
-                else                search_chunk<1>(A, q, q_addr, qcount, cxs, cys, czs, cg, k0 + lane, k0 == 0, hb, h_end, r2_lo, r2_hi, lane, lt_mask);
+                if (left > 96)      search_chunk<4>(A, q, q_addr, qcount, cxs, cys, czs, cg, k0 + lane, k0 == 0, hb, h_end, r2_hi, lane, lt_mask);
+                else if (left > 64) search_chunk<3>(A, q, q_addr, qcount, cxs, cys, czs, cg, k0 + lane, k0 == 0, hb, h_end, r2_hi, lane, lt_mask);
+                else if (left > 32) search_chunk<2>(A, q, q_addr, qcount, cxs, cys, czs, cg, k0 + lane, k0 == 0, hb, h_end, r2_hi, lane, lt_mask);
+                else                search_chunk<1>(A, q, q_addr, qcount, cxs, cys, czs, cg, k0 + lane, k0 == 0, hb, h_end, r2_hi, lane, lt_mask);
             }
         }
     }
     if (qcount) {
         __syncwarp();
-        search_drain(A, q, qcount, last_r2_lo, lane);
+        search_flush(A, q, qcount, lane);
     }
     if (lane == 0) {
         if (ncand) atomicAdd(&A.meta->n_candidates, ncand);
@@ -555,28 +522,35 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
 }
 
 /* ---- k_classify ---------------------------------------------------------------------------------
- * The loop body of _calculate_atom_contacts (interactions.py:743-936) over the hit list, one lane per
- * pair.  Every WARP owns tiles of CLS_TILE consecutive pairs and runs them without any block barrier:
- *   stage 1  32 pairs per round: exact float32 distance, proximity bit, metal, the feature bits that need
- *            no angle (rule_classify_core); the record goes to the warp's shared-memory staging tile;
- *            pairs that need a hydrogen scan (is_hbond / is_weak_hbond) or a rarer predicate (halogen weak
- *            hbond, xbond) append a 32-bit work item to the warp's list (ballot compaction)
- *   stage 2  the list is processed densely -- 32 items per round -- and each result bit is OR-ed into the
- *            staged record
- *   stage 3  the finished tile (CLS_TILE x 16 B, contiguous in the output stream) leaves with one bulk
- *            asynchronous copy shared -> global (cp.async.bulk, TMA engine), double buffered so that the
- *            store of one tile overlaps the arithmetic of the next.                                      */
+ * Everything per pair, one lane per pair.  Every WARP owns tiles of CLS_TILE consecutive candidates and
+ * runs them without any block barrier:
+ *   stage 0  32 candidates per round: the exact double test of Bio.PDB.kdtrees inside the float32 band,
+ *            orientation (atom_bgn = lower list index), the reference's `continue` filters
+ *            (interactions.py:712-741); survivors are compacted into the warp's shared-memory list
+ *   stage 1  32 survivors per round: exact float32 distance, proximity bit, metal, the feature bits that
+ *            need no angle (rule_classify_core, interactions.py:743-936); the record goes to the warp's
+ *            staging tile; pairs that need a hydrogen scan (is_hbond / is_weak_hbond) or a rarer
+ *            predicate (halogen weak hbond, xbond) append a 32-bit work item to the warp's work list
+ *   stage 2  the work list is processed densely -- 32 items per round -- and each result bit is OR-ed
+ *            into the staged record
+ *   stage 3  the finished tile leaves with one bulk asynchronous copy shared -> global (cp.async.bulk,
+ *            TMA engine) behind one cursor atomic, double buffered so that the store of one tile overlaps
+ *            the arithmetic of the next.                                                              */
 #define CLS_WARPS   8
 #define CLS_TILE    128
 #define CLS_ITEMS   (3 * CLS_TILE)          /* per pair at most: is_hbond scan + (is_weak_hbond scan | halogen) + xbond */
+#define CLS_SMEM_PER_WARP (2 * CLS_TILE * 16 + CLS_ITEMS * 4 + CLS_TILE * 8)
+#define CLS_SMEM    (CLS_WARPS * CLS_SMEM_PER_WARP)
 
 struct ClassifyArgs {
     const float4* pos4;
     const uint4*  att4;
-    const uint2*  hits;
-    const RunMeta* meta;
+    const uint2*  raw;
+    RunMeta*      meta;
     arp_pair*     out;
-    unsigned long long out_cap;
+    unsigned long long cap;
+    double        r2;
+    int           include_seq_adjacent;
     ArpSide       side;
 };
 
@@ -604,32 +578,64 @@ __device__ __forceinline__ void bulk_store_wait_read_1()
 #define CLS_KIND_HAL   4u
 #define CLS_KIND_XBOND 5u
 
-__global__ void __launch_bounds__(CLS_WARPS * 32, 3) k_classify(ClassifyArgs A, ArpRuleParams P)
+#ifndef CLS_MINB
+#define CLS_MINB 3
+#endif
+__global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyArgs A, ArpRuleParams P)
 {
-    __shared__ __align__(128) int4 s_rec[CLS_WARPS][2][CLS_TILE];   /* staged records, per warp, double buffered */
-    __shared__ uint32_t s_item[CLS_WARPS][CLS_ITEMS];
+    extern __shared__ __align__(128) unsigned char s_dyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* mine = s_dyn + (size_t)warp * CLS_SMEM_PER_WARP;
+    int4* const rec0 = reinterpret_cast<int4*>(mine);                       /* 2 staging tiles */
+    uint32_t* const items = reinterpret_cast<uint32_t*>(mine + 2 * CLS_TILE * 16);
+    uint2* const surv = reinterpret_cast<uint2*>(mine + 2 * CLS_TILE * 16 + CLS_ITEMS * 4);
     const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned long long n = A.meta->n_pairs;
-    if (n > A.out_cap) n = A.out_cap;                           /* overflowing run: host repeats it with a larger buffer */
+    unsigned long long n = A.meta->n_raw;
+    if (n > A.cap) n = A.cap;                                    /* overflowing run: host repeats it with a larger buffer */
+    const float r2_lo = A.meta->r2_lo_inv == 0x7f800000u ? -1.0f : __uint_as_float(0x7f800000u - A.meta->r2_lo_inv);
     const unsigned long long n_tiles = (n + CLS_TILE - 1) / CLS_TILE;
     const unsigned long long warp_id = (unsigned long long)blockIdx.x * CLS_WARPS + warp;
     const unsigned long long n_warps = (unsigned long long)gridDim.x * CLS_WARPS;
-    uint32_t* items = s_item[warp];
     int buf = 0;
-    for (unsigned long long tile = warp_id; tile < n_tiles; tile += n_warps, buf ^= 1) {
+    for (unsigned long long tile = warp_id; tile < n_tiles; tile += n_warps) {
         const unsigned long long base = tile * CLS_TILE;
         const unsigned cnt = (unsigned)min((unsigned long long)CLS_TILE, n - base);
-        int4* rec = s_rec[warp][buf];
+        /* ---- stage 0: exact test, orientation, filters ---- */
+        unsigned nsurv = 0;
+        for (unsigned i0 = 0; i0 < cnt; i0 += 32) {
+            const unsigned idx = i0 + lane;
+            bool keep = false;
+            uint2 e = make_uint2(0, 0);
+            if (idx < cnt) {
+                e = A.raw[base + idx];
+                const float4 pa = A.pos4[e.x], pb = A.pos4[e.y];
+                uint4 ab = A.att4[e.x], ae = A.att4[e.y];
+                const float ddx = pa.x - pb.x, ddy = pa.y - pb.y, ddz = pa.z - pb.z;
+                const float d2 = __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, __fmul_rn(ddx, ddx)));   /* as in k_search */
+                keep = true;
+                if (!(d2 <= r2_lo)) keep = kd_within(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, A.r2);
+                if (__float_as_int(pb.w) < __float_as_int(pa.w)) {          /* atom_bgn = lower list index */
+                    const unsigned t = e.x; e.x = e.y; e.y = t;
+                    const uint4 tt = ab; ab = ae; ae = tt;
+                }
+                keep = keep && rule_pair_survives(ab.x, (int)ab.y, (int)ab.z, (int)ab.w, ae.x, (int)ae.y, (int)ae.z, (int)ae.w,
+                                                  A.include_seq_adjacent);
+            }
+            const unsigned m = __ballot_sync(FULL, keep);
+            if (keep) surv[nsurv + __popc(m & lt_mask)] = e;
+            nsurv += __popc(m);
+        }
+        if (nsurv == 0) continue;
+        int4* rec = rec0 + buf * CLS_TILE;
         if (lane == 0) bulk_store_wait_read_1();                 /* the store that last used this buffer has read it */
         __syncwarp();
         /* ---- stage 1 ---- */
         unsigned n_items = 0;
-        for (unsigned i0 = 0; i0 < cnt; i0 += 32) {
+        for (unsigned i0 = 0; i0 < nsurv; i0 += 32) {
             const unsigned idx = i0 + lane;
             uint32_t work = 0;
-            if (idx < cnt) {
-                const uint2 e = A.hits[base + idx];
+            if (idx < nsurv) {
+                const uint2 e = surv[idx];
                 const float4 pb = A.pos4[e.x], pe = A.pos4[e.y];
                 const uint32_t fb = A.att4[e.x].x, fe = A.att4[e.y].x;
                 const int ib = __float_as_int(pb.w), ie = __float_as_int(pe.w);
@@ -666,7 +672,7 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, 3) k_classify(ClassifyArgs A, 
                 const uint32_t it = items[w];
                 const unsigned idx = it >> 4;
                 const uint32_t kind = it & 7u;
-                uint2 e = A.hits[base + idx];
+                uint2 e = surv[idx];
                 if (it & 8u) { unsigned t = e.x; e.x = e.y; e.y = t; }   /* e.x = donor, e.y = acceptor / halogen */
                 const float4 pd = A.pos4[e.x], pa = A.pos4[e.y];
                 const uint32_t fa = A.att4[e.y].x;
@@ -691,7 +697,11 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, 3) k_classify(ClassifyArgs A, 
         }
         __syncwarp();
         /* ---- stage 3: the tile leaves through the TMA engine ---- */
-        if (lane == 0) bulk_store_tile(A.out + base, rec, cnt * (uint32_t)sizeof(arp_pair));
+        if (lane == 0) {
+            const unsigned long long o = atomicAdd(&A.meta->n_pairs, (unsigned long long)nsurv);
+            bulk_store_tile(A.out + o, rec, nsurv * (uint32_t)sizeof(arp_pair));
+        }
+        buf ^= 1;
     }
     if (lane == 0) bulk_store_wait_read_all();                   /* shared memory must outlive the copies */
 }
@@ -787,9 +797,8 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         side.xnbr = c->has_xnbr ? c->xnbr.as<float>() : nullptr;
 
         SearchArgs SA;
-        SA.pos4 = c->pos4.as<float4>(); SA.att4 = c->att4.as<uint4>(); SA.cell_start = c->cell_start.as<int>();
-        SA.geom = c->geom.as<StructGeom>(); SA.meta = meta; SA.hits = c->hits.as<uint2>(); SA.hit_cap = c->out_cap;
-        SA.r2 = c->rp.r2; SA.include_seq_adjacent = c->rp.include_seq_adjacent;
+        SA.pos4 = c->pos4.as<float4>(); SA.cell_start = c->cell_start.as<int>();
+        SA.geom = c->geom.as<StructGeom>(); SA.meta = meta; SA.raw = c->hits.as<uint2>(); SA.cap = c->out_cap;
         unsigned grid = (unsigned)(c->sm_count * SEARCH_MINB);
         size_t want = ((size_t)N / 24) / SEARCH_WARPS + 1;     /* about one warp per few cells on small inputs */
         if (want < grid) grid = (unsigned)want;
@@ -798,13 +807,18 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[2], st));
 
         ClassifyArgs CA;
-        CA.pos4 = SA.pos4; CA.att4 = SA.att4; CA.hits = SA.hits; CA.meta = meta;
-        CA.out = c->out.as<arp_pair>(); CA.out_cap = c->out_cap; CA.side = side;
+        CA.pos4 = SA.pos4; CA.att4 = c->att4.as<uint4>(); CA.raw = SA.raw; CA.meta = meta;
+        CA.out = c->out.as<arp_pair>(); CA.cap = c->out_cap; CA.side = side;
+        CA.r2 = c->rp.r2; CA.include_seq_adjacent = c->rp.include_seq_adjacent;
+        if (!c->cls_smem_set) {             /* per device: > 48 KB of dynamic shared memory is opt-in */
+            ARP_CUDA(c, cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, CLS_SMEM));
+            c->cls_smem_set = 1;
+        }
         size_t tiles = (size_t)((c->out_cap + CLS_TILE - 1) / CLS_TILE);
         size_t blocks_needed = (tiles + CLS_WARPS - 1) / CLS_WARPS;
-        unsigned cgrid = (unsigned)(c->sm_count * 3);
+        unsigned cgrid = (unsigned)(c->sm_count * CLS_MINB);
         if (blocks_needed < cgrid) cgrid = (unsigned)(blocks_needed ? blocks_needed : 1);
-        k_classify<<<cgrid, CLS_WARPS * 32, 0, st>>>(CA, c->rp);
+        k_classify<<<cgrid, CLS_WARPS * 32, CLS_SMEM, st>>>(CA, c->rp);
         ARP_LAUNCHED(c);
     } else if (with_events) {
         ARP_CUDA(c, cudaEventRecord(c->ev[2], st));

@@ -314,9 +314,7 @@ __global__ void __launch_bounds__(256) k_scatter(int N, const float* __restrict_
     if (i >= N) return;
     int dst = cell_start[cell_of[i]] + rank[i];
     int r = res_id[i];
-    uint32_t w = (feat[i] & 0xFFFFFu) | ((uint32_t)(res_flags[r] & 3u) << ARPK_RES_SHIFT) |
-                 ((uint32_t)rad_class[i] << ARPK_RAD_SHIFT);
-    if (bond_off && bond_off[i + 1] > bond_off[i]) w |= ARPK_HAS_BOND;
+    const uint32_t w = arp_pack_word(feat[i], res_flags[r], rad_class[i], bond_off && bond_off[i + 1] > bond_off[i]);
     pos4[dst] = make_float4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], __int_as_float(i));
     att4[dst] = make_uint4(w, (uint32_t)r, (uint32_t)res_prev[r], (uint32_t)res_next[r]);
 }
@@ -405,7 +403,7 @@ __device__ __forceinline__ void search_chunk(const SearchArgs& A, uint2* q, uint
 }
 
 #ifndef SEARCH_MINB
-#define SEARCH_MINB 3
+#define SEARCH_MINB 4
 #endif
 __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(SearchArgs A)
 {
@@ -676,7 +674,7 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
                 if (it & 8u) { unsigned t = e.x; e.x = e.y; e.y = t; }   /* e.x = donor, e.y = acceptor / halogen */
                 const float4 pd = A.pos4[e.x], pa = A.pos4[e.y];
                 const uint32_t fa = A.att4[e.y].x;
-                const double vdw_a = A.side.vdw[fa >> ARPK_RAD_SHIFT];
+                const double vdw_a = A.side.vdw[fa & ARPK_RAD_MASK];
                 uint32_t bits = 0;
                 if (kind <= 3u) {
                     const int got = rule_hbond_scan(A.side, P, __float_as_int(pd.w), pd.x, pd.y, pd.z, pa.x, pa.y, pa.z,
@@ -685,11 +683,11 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
                     if (got & ARP_HB_NEED_W) bits |= 1u << ARP_SIFT_WEAK_HBOND;
                 } else if (kind == CLS_KIND_HAL) {
                     if (rule_is_halogen_weak_hbond(A.side, P, __float_as_int(pd.w), __float_as_int(pa.w), pa.x, pa.y, pa.z,
-                                                   fa, vdw_a)) bits = 1u << ARP_SIFT_WEAK_HBOND;
+                                                   A.side.feat[__float_as_int(pa.w)], vdw_a)) bits = 1u << ARP_SIFT_WEAK_HBOND;
                 } else {
                     uint32_t fault = 0;
                     if (rule_is_xbond(A.side, P, __float_as_int(pd.w), pd.x, pd.y, pd.z, pa.x, pa.y, pa.z,
-                                      A.att4[e.x].x, &fault)) bits = 1u << ARP_SIFT_XBOND;
+                                      A.side.feat[__float_as_int(pd.w)], &fault)) bits = 1u << ARP_SIFT_XBOND;
                     bits |= fault;
                 }
                 if (bits) atomicOr(reinterpret_cast<unsigned*>(&rec[idx].z), bits);
@@ -779,8 +777,9 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         memset(&side, 0, sizeof side);
         side.vdw = c->vdw.as<double>(); side.cov = c->cov.as<double>();
         side.K = c->K;
+        side.feat = c->feat.as<uint32_t>();
         side.radtab = nullptr;
-        if (c->K <= 64) {                   /* larger tables stop being cache resident: compute on the fly */
+        {
             if (!c->radtab_valid) {
                 ARP_TRY(dbuf_reserve(c, c->radtab, sizeof(float4) * (size_t)c->K * c->K));
                 k_radtab<<<(unsigned)((c->K * c->K + 127) / 128), 128, 0, st>>>(c->K, c->vdw.as<double>(), c->cov.as<double>(),

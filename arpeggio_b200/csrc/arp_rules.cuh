@@ -44,20 +44,69 @@ struct float4 { float x, y, z, w; };      /* host build of the rules (tests/emu)
 #endif
 
 /* ---- packed per-atom word (cell-sorted attribute record, word 0) ---------------------
- * bits 0..19  ARP_F_* as uploaded
- * bits 20..21 ARP_R_* of the atom's residue
- * bit  22     atom has at least one entry in the bond CSR
- * bits 23..31 radius class (K <= 512)                                                  */
-#define ARPK_RES_SHIFT   20
-#define ARPK_HAS_BOND    (1u << 22)
-#define ARPK_RAD_SHIFT   23
+ * Internal layout, chosen so that every "p on one atom, q on the other" rule is one AND of the
+ * bgn word with the pair-swapped end word (arp_pack_word builds it from the uploaded arrays):
+ *   bits 0..8   radius class (K <= 512)
+ *   bit  9      element H                      bits 10..11 ARP_R_* of the atom's residue
+ *   bit  12     atom has bond CSR entries      bit  13 water      bit 14 in selection
+ *   bit  15     aromatic                       bit  16 hydrophobe (bit 17 unused)
+ *   pairs (even bit p, odd bit q):
+ *   18 hbond acceptor   | 19 hbond donor                     A: is_hbond directions
+ *   20 hbond acceptor   | 21 weak hbond donor                B: is_weak_hbond directions
+ *   22 xbond acceptor   | 23 xbond donor                     C: is_xbond directions
+ *   24 pos ionisable    | 25 neg ionisable                   D: ionic
+ *   26 carbonyl oxygen  | 27 carbonyl carbon                 E: carbonyl
+ *   28 hbond acceptor   | 29 is metal                        F: metal complex
+ *   30 weak hbond acceptor AND halogen | 31 hbond donor OR weak hbond donor   G: halogen weak hbond  */
+#define ARPK_RAD_MASK    0x1FFu
 #define ARPK_MAX_RAD     512
+#define ARPK_ELEM_H      (1u << 9)
+#define ARPK_RES_SHIFT   10
+#define ARPK_HAS_BOND    (1u << 12)
+#define ARPK_WATER       (1u << 13)
+#define ARPK_SELECTION   (1u << 14)
+#define ARPK_AROMATIC    (1u << 15)
+#define ARPK_HYDROPHOBE  (1u << 16)
+#define ARPK_PAIR_EVEN   0x55540000u     /* bits 18, 20, ..., 30 */
+#define ARPK_PAIR_ODD    0xAAA80000u     /* bits 19, 21, ..., 31 */
+#define ARPK_ACC         (1u << 18)
+#define ARPK_DON         (1u << 19)
+
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__
+#else
+static inline
+#endif
+uint32_t arp_pack_word(uint32_t feat, uint32_t res_flags, uint32_t rad_class, int has_bond)
+{
+    uint32_t w = (rad_class & ARPK_RAD_MASK) | ((res_flags & 3u) << ARPK_RES_SHIFT);
+    const uint32_t acc = (feat & ARP_F_HBOND_ACCEPTOR) != 0, don = (feat & ARP_F_HBOND_DONOR) != 0;
+    const uint32_t wdon = (feat & ARP_F_WEAK_HBOND_DONOR) != 0;
+    if (feat & ARP_F_ELEM_H) w |= ARPK_ELEM_H;
+    if (has_bond) w |= ARPK_HAS_BOND;
+    if (feat & ARP_F_IS_WATER) w |= ARPK_WATER;
+    if (feat & ARP_F_IN_SELECTION) w |= ARPK_SELECTION;
+    if (feat & ARP_F_AROMATIC) w |= ARPK_AROMATIC;
+    if (feat & ARP_F_HYDROPHOBE) w |= ARPK_HYDROPHOBE;
+    w |= acc << 18 | don << 19 | acc << 20 | wdon << 21 | acc << 28;
+    if (feat & ARP_F_XBOND_ACCEPTOR) w |= 1u << 22;
+    if (feat & ARP_F_XBOND_DONOR) w |= 1u << 23;
+    if (feat & ARP_F_POS_IONISABLE) w |= 1u << 24;
+    if (feat & ARP_F_NEG_IONISABLE) w |= 1u << 25;
+    if (feat & ARP_F_CARBONYL_OXYGEN) w |= 1u << 26;
+    if (feat & ARP_F_CARBONYL_CARBON) w |= 1u << 27;
+    if (feat & ARP_F_IS_METAL) w |= 1u << 29;
+    if ((feat & ARP_F_WEAK_HBOND_ACCEPTOR) && (feat & ARP_F_IS_HALOGEN)) w |= 1u << 30;
+    w |= (don | wdon) << 31;
+    return w;
+}
 
 struct ArpSide {               /* side arrays, original atom order (device pointers) */
     const double*   vdw;       /* [K] */
     const double*   cov;       /* [K] */
-    const float4*   radtab;    /* [K][K] (f32(cov_a+cov_b), f32(vdw_a+vdw_b), f32((vdw_a+vdw_b)+comp), -) or null */
+    const float4*   radtab;    /* [K][K] (f32(cov_a+cov_b), f32(vdw_a+vdw_b), f32((vdw_a+vdw_b)+comp), -) */
     int             K;
+    const uint32_t* feat;      /* [N] ARP_F_* as uploaded (rare predicates only) */
     const int32_t*  bond_off;  /* [N+1] or null */
     const int32_t*  bond_nbr;
     const int32_t*  h_off;     /* [N+1] or null */
@@ -305,9 +354,11 @@ ARP_HD int rule_hbond_scan(const ArpSide& S, const ArpRuleParams& P, int donor, 
         const double v1x = d_sub((double)dcx, hx), v1y = d_sub((double)dcy, hy), v1z = d_sub((double)dcz, hz);
         const double v2x = d_sub((double)acx, hx), v2y = d_sub((double)acy, hy), v2z = d_sub((double)acz, hz);
         /* float32 estimate of the cosine; |estimate - exact chain| < 2e-6 for non-degenerate vectors */
-        const float q1 = (float)(v1x * v1x + v1y * v1y + v1z * v1z);
-        const float q2 = (float)(v2x * v2x + v2y * v2y + v2z * v2z);
-        const float dt = (float)(v1x * v2x + v1y * v2y + v1z * v2z);
+        const float f1x = (float)v1x, f1y = (float)v1y, f1z = (float)v1z;
+        const float f2x = (float)v2x, f2y = (float)v2y, f2z = (float)v2z;
+        const float q1 = f1x * f1x + f1y * f1y + f1z * f1z;
+        const float q2 = (float)s;                         /* v2 = -(h - acceptor) */
+        const float dt = f1x * f2x + f1y * f2y + f1z * f2z;
         const float ce = dt * fast_rsqrt(q1 * q2);
         const float tol = 2e-5f;
         int sure_true = 0, sure_false = 0;
@@ -386,10 +437,8 @@ ARP_HD_NOINLINE int rule_is_xbond(const ArpSide& S, const ArpRuleParams& P, int 
 }
 
 /* InteractionComplex.__get_contact_type (interactions.py:643-691): six ifs, last true wins */
-ARP_HD uint32_t rule_entity_class(uint32_t fb, uint32_t fe)
+ARP_HD uint32_t rule_entity_class_bools(bool sb, bool se, bool wb, bool we)
 {
-    bool sb = (fb & ARP_F_IN_SELECTION) != 0, se = (fe & ARP_F_IN_SELECTION) != 0;
-    bool wb = (fb & ARP_F_IS_WATER) != 0,     we = (fe & ARP_F_IS_WATER) != 0;
     uint32_t c = 7;
     if (!sb && !se) c = ARP_CLASS_INTRA_NON_SELECTION;
     if (sb && se) c = ARP_CLASS_INTRA_SELECTION;
@@ -398,6 +447,17 @@ ARP_HD uint32_t rule_entity_class(uint32_t fb, uint32_t fe)
     if ((!sb && we) || (!se && wb)) c = ARP_CLASS_NON_SELECTION_WATER;
     if (wb && we) c = ARP_CLASS_WATER_WATER;
     return c;
+}
+/* the same as a 16 x 3-bit table indexed by sb | se << 1 | wb << 2 | we << 3 (built from the ifs above) */
+ARP_HD uint32_t rule_entity_class(uint32_t wb_word, uint32_t we_word)
+{
+    unsigned long long lut = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        lut |= (unsigned long long)rule_entity_class_bools(k & 1, (k >> 1) & 1, (k >> 2) & 1, (k >> 3) & 1) << (3 * k);
+    const uint32_t idx = ((wb_word >> 14) & 1u) | (((we_word >> 14) & 1u) << 1) | (((wb_word >> 13) & 1u) << 2) |
+                         (((we_word >> 13) & 1u) << 3);
+    return (uint32_t)(lut >> (3 * idx)) & 7u;
 }
 
 /*
@@ -408,7 +468,7 @@ ARP_HD uint32_t rule_entity_class(uint32_t fb, uint32_t fe)
 ARP_HD bool rule_pair_survives(uint32_t fb, int rb, int pb, int nb, uint32_t fe, int re, int pe, int ne,
                                int include_seq_adjacent)
 {
-    if ((fb | fe) & ARP_F_ELEM_H) return false;                                    /* :712-713 */
+    if ((fb | fe) & ARPK_ELEM_H) return false;                                     /* :712-713 */
     if (rb == re) return false;                                                    /* :729-730 */
     if (!include_seq_adjacent) {                                                   /* :733 */
         uint32_t flb = fb >> ARPK_RES_SHIFT, fle = fe >> ARPK_RES_SHIFT;
@@ -435,83 +495,66 @@ ARP_HD bool rule_pair_survives(uint32_t fb, int rb, int pb, int nb, uint32_t fe,
  * predicates that walk hydrogens or need an exact angle: those come back in *work and are OR-ed into
  * the mask by the caller (bits hbond, weak_hbond, xbond).
  * b = atom_bgn (lower list index), e = atom_end; coordinates and packed words are passed in registers.
+ * X = wb & pairswap(we): bit 2k = "p on bgn, q on end", bit 2k + 1 = "q on bgn, p on end".
  */
 ARP_HD void rule_classify_core(const ArpSide& S, const ArpRuleParams& P, int b, int e,
                                float bx, float by, float bz, float ex, float ey, float ez,
-                               uint32_t fb, uint32_t fe, uint32_t* mask_out, float* dist_out, uint32_t* work_out)
+                               uint32_t wb, uint32_t we, uint32_t* mask_out, float* dist_out, uint32_t* work_out)
 {
-    const uint32_t kb = fb >> ARPK_RAD_SHIFT, ke = fe >> ARPK_RAD_SHIFT;
-    float t_cov, t_vdw, vdwc;
-    if (S.radtab) {
-        const float4 t = S.radtab[kb * (uint32_t)S.K + ke];
-        t_cov = t.x; t_vdw = t.y; vdwc = t.z;
-    } else {
-        const double sum_cov = d_add(S.cov[kb], S.cov[ke]);                        /* :717 */
-        const double sum_vdw = d_add(S.vdw[kb], S.vdw[ke]);                        /* :718 */
-        t_cov = (float)sum_cov; t_vdw = (float)sum_vdw; vdwc = (float)d_add(sum_vdw, P.vdw_comp);
-    }
+    const float4 t = S.radtab[(wb & ARPK_RAD_MASK) * (uint32_t)S.K + (we & ARPK_RAD_MASK)];   /* :717-718 narrowed */
+    const float t_cov = t.x, t_vdw = t.y, vdwc = t.z;
     const float d = np_dist_f32(bx, by, bz, ex, ey, ez);                           /* :745 */
-    uint32_t m = 0, work = 0;
 
     bool bonded = false;                                                           /* :750-754 */
-    if (fb & ARPK_HAS_BOND) {           /* only atom_bgn's neighbour list is consulted */
+    if (wb & ARPK_HAS_BOND) {           /* only atom_bgn's neighbour list is consulted */
         for (int k = S.bond_off[b]; k < S.bond_off[b + 1]; ++k)
             if (S.bond_nbr[k] == e) { bonded = true; break; }
     }
     const bool clash = !bonded && d < t_cov;
-    m |= bonded ? 1u << ARP_SIFT_COVALENT                                          /* :756-757 */
-       : clash ? 1u << ARP_SIFT_CLASH                                              /* :760 */
-       : d < t_vdw ? 1u << ARP_SIFT_VDW_CLASH                                      /* :764 */
-       : d <= vdwc ? 1u << ARP_SIFT_VDW                                            /* :768 */
-       : 1u << ARP_SIFT_PROXIMAL;                                                  /* :772 */
+    uint32_t m = bonded ? 1u << ARP_SIFT_COVALENT                                  /* :756-757 */
+               : clash ? 1u << ARP_SIFT_CLASH                                      /* :760 */
+               : d < t_vdw ? 1u << ARP_SIFT_VDW_CLASH                              /* :764 */
+               : d <= vdwc ? 1u << ARP_SIFT_VDW                                    /* :768 */
+               : 1u << ARP_SIFT_PROXIMAL;                                          /* :772 */
 
-    const uint32_t x = fb | fe, a = fb & fe;
-    /* a feature pair "p on one atom, q on the other, either way round" */
-#define ARP_CROSS(p, q) ((((fb & (p)) != 0) & ((fe & (q)) != 0)) | (((fe & (p)) != 0) & ((fb & (q)) != 0)))
-    if ((d <= P.metal) & ARP_CROSS(ARP_F_HBOND_ACCEPTOR, ARP_F_IS_METAL)) m |= 1u << ARP_SIFT_METAL;   /* :777-783 */
+    const uint32_t sw = ((we & ARPK_PAIR_EVEN) << 1) | ((we & ARPK_PAIR_ODD) >> 1);
+    const uint32_t X = wb & sw, Y = wb & we;
+#define ARP_XB(n) ((X >> (n)) & 1u)
+    if (d <= P.metal) m |= (ARP_XB(28) | ARP_XB(29)) << ARP_SIFT_METAL;            /* :777-783 */
 
+    uint32_t work = 0;
     if (!clash && d <= P.dist_max) {                                               /* :786 */
         const bool in_vdwc = d <= vdwc;
-        const bool don_b = fb & ARP_F_HBOND_DONOR, don_e = fe & ARP_F_HBOND_DONOR;
-        const bool acc_b = fb & ARP_F_HBOND_ACCEPTOR, acc_e = fe & ARP_F_HBOND_ACCEPTOR;
-        const bool wdon_b = fb & ARP_F_WEAK_HBOND_DONOR, wdon_e = fe & ARP_F_WEAK_HBOND_DONOR;
         /* hbond / polar :791-819 */
-        if ((fb & ARP_F_IS_WATER) && in_vdwc) {
-            if (acc_e || don_e) m |= (1u << ARP_SIFT_HBOND) | (1u << ARP_SIFT_POLAR);
-        } else if ((fe & ARP_F_IS_WATER) && in_vdwc) {
-            if (acc_b || don_b) m |= (1u << ARP_SIFT_HBOND) | (1u << ARP_SIFT_POLAR);
-        } else if (don_b && acc_e) {
-            work |= ARP_HB_NEED_H;                                                 /* is_hbond(bgn, end) */
-            if (d <= P.hbond_polar) m |= 1u << ARP_SIFT_POLAR;
-        } else if (don_e && acc_b) {
-            work |= ARP_HB_NEED_H << 2;                                            /* is_hbond(end, bgn) */
+        const bool ws_b = (wb & ARPK_WATER) && in_vdwc;
+        const bool ws_e = !ws_b && (we & ARPK_WATER) && in_vdwc;
+        if (ws_b) {
+            if (we & (ARPK_ACC | ARPK_DON)) m |= (1u << ARP_SIFT_HBOND) | (1u << ARP_SIFT_POLAR);
+        } else if (ws_e) {
+            if (wb & (ARPK_ACC | ARPK_DON)) m |= (1u << ARP_SIFT_HBOND) | (1u << ARP_SIFT_POLAR);
+        } else if (X & (3u << 18)) {
+            work |= ARP_XB(19) ? ARP_HB_NEED_H : (ARP_HB_NEED_H << 2);             /* is_hbond(bgn, end) before (end, bgn) */
             if (d <= P.hbond_polar) m |= 1u << ARP_SIFT_POLAR;
         }
         /* weak hbond / weak polar: four independent ifs, each ASSIGNS SIFt[6] (:857-886), so only the
            last applicable one decides the bit; any applicable one enables weak polar */
-        const bool w1 = acc_b && wdon_e;                                           /* is_weak_hbond(end, bgn) */
-        const bool w2 = wdon_b && acc_e;                                           /* is_weak_hbond(bgn, end) */
-        const bool w3 = (fb & ARP_F_WEAK_HBOND_ACCEPTOR) && (fb & ARP_F_IS_HALOGEN) && (don_e || wdon_e);   /* halogen bgn */
-        const bool w4 = (fe & ARP_F_WEAK_HBOND_ACCEPTOR) && (fe & ARP_F_IS_HALOGEN) && (don_b || wdon_b);   /* halogen end */
-        if (w4)      work |= ARP_WORK_HAL0;
-        else if (w3) work |= ARP_WORK_HAL1;
-        else if (w2) work |= ARP_HB_NEED_W;
-        else if (w1) work |= ARP_HB_NEED_W << 2;
-        if ((w1 || w2 || w3 || w4) && d <= P.weak_polar) m |= 1u << ARP_SIFT_WEAK_POLAR;
-        /* xbond :889-895 */
-        if (in_vdwc) {
-            if ((fb & ARP_F_XBOND_DONOR) && (fe & ARP_F_XBOND_ACCEPTOR)) work |= ARP_WORK_XB0;
-            else if ((fe & ARP_F_XBOND_DONOR) && (fb & ARP_F_XBOND_ACCEPTOR)) work |= ARP_WORK_XB1;
+        if (X & ((3u << 20) | (3u << 30))) {
+            if (ARP_XB(31))      work |= ARP_WORK_HAL0;                            /* halogen end, donor bgn */
+            else if (ARP_XB(30)) work |= ARP_WORK_HAL1;                            /* halogen bgn, donor end */
+            else if (ARP_XB(21)) work |= ARP_HB_NEED_W;                            /* is_weak_hbond(bgn, end) */
+            else                 work |= ARP_HB_NEED_W << 2;                       /* is_weak_hbond(end, bgn) */
+            if (d <= P.weak_polar) m |= 1u << ARP_SIFT_WEAK_POLAR;
         }
+        /* xbond :889-895 */
+        if (in_vdwc && (X & (3u << 22))) work |= ARP_XB(23) ? ARP_WORK_XB0 : ARP_WORK_XB1;
         /* ionic :898-904, carbonyl :907-913, aromatic :916-917, hydrophobic :920-921 */
-        if ((d <= P.ionic) & ARP_CROSS(ARP_F_POS_IONISABLE, ARP_F_NEG_IONISABLE)) m |= 1u << ARP_SIFT_IONIC;
-        if ((d <= P.carbonyl) & ARP_CROSS(ARP_F_CARBONYL_OXYGEN, ARP_F_CARBONYL_CARBON)) m |= 1u << ARP_SIFT_CARBONYL;
-        if ((a & ARP_F_AROMATIC) && d <= P.aromatic) m |= 1u << ARP_SIFT_AROMATIC;
-        if ((a & ARP_F_HYDROPHOBE) && d <= P.hydrophobic) m |= 1u << ARP_SIFT_HYDROPHOBIC;
+        if (d <= P.ionic) m |= (ARP_XB(24) | ARP_XB(25)) << ARP_SIFT_IONIC;
+        if (d <= P.carbonyl) m |= (ARP_XB(26) | ARP_XB(27)) << ARP_SIFT_CARBONYL;
+        if (d <= P.aromatic) m |= ((Y >> 15) & 1u) << ARP_SIFT_AROMATIC;
+        if (d <= P.hydrophobic) m |= ((Y >> 16) & 1u) << ARP_SIFT_HYDROPHOBIC;
     }
-#undef ARP_CROSS
-    (void)x;
-    *mask_out = m | (rule_entity_class(fb, fe) << ARP_CLASS_SHIFT);
+#undef ARP_XB
+    *mask_out = m | (rule_entity_class(wb, we) << ARP_CLASS_SHIFT);
     *dist_out = d;
     *work_out = work;
 }
@@ -520,21 +563,21 @@ ARP_HD void rule_classify_core(const ArpSide& S, const ArpRuleParams& P, int b, 
    (host emulation and single-pair uses; the kernels run the deferred work densely instead) */
 ARP_HD void rule_classify(const ArpSide& S, const ArpRuleParams& P, int b, int e,
                           float bx, float by, float bz, float ex, float ey, float ez,
-                          uint32_t fb, uint32_t fe, uint32_t* mask_out, float* dist_out)
+                          uint32_t wb, uint32_t we, uint32_t* mask_out, float* dist_out)
 {
     uint32_t m, work;
-    rule_classify_core(S, P, b, e, bx, by, bz, ex, ey, ez, fb, fe, &m, dist_out, &work);
-    const double vdw_b = S.vdw[fb >> ARPK_RAD_SHIFT], vdw_e = S.vdw[fe >> ARPK_RAD_SHIFT];
+    rule_classify_core(S, P, b, e, bx, by, bz, ex, ey, ez, wb, we, &m, dist_out, &work);
+    const double vdw_b = S.vdw[wb & ARPK_RAD_MASK], vdw_e = S.vdw[we & ARPK_RAD_MASK];
     int got = 0, weak = 0;
     uint32_t fault = 0;
     if (work & ARP_WORK_SCAN0) got |= rule_hbond_scan(S, P, b, bx, by, bz, ex, ey, ez, vdw_e, (int)(work & 3u));
     if (work & ARP_WORK_SCAN1) got |= rule_hbond_scan(S, P, e, ex, ey, ez, bx, by, bz, vdw_b, (int)((work >> 2) & 3u));
-    if (work & ARP_WORK_HAL0) weak = rule_is_halogen_weak_hbond(S, P, b, e, ex, ey, ez, fe, vdw_e);
-    if (work & ARP_WORK_HAL1) weak = rule_is_halogen_weak_hbond(S, P, e, b, bx, by, bz, fb, vdw_b);
+    if (work & ARP_WORK_HAL0) weak = rule_is_halogen_weak_hbond(S, P, b, e, ex, ey, ez, S.feat[e], vdw_e);
+    if (work & ARP_WORK_HAL1) weak = rule_is_halogen_weak_hbond(S, P, e, b, bx, by, bz, S.feat[b], vdw_b);
     if (got & ARP_HB_NEED_H) m |= 1u << ARP_SIFT_HBOND;
     if ((got & ARP_HB_NEED_W) || weak) m |= 1u << ARP_SIFT_WEAK_HBOND;
-    if ((work & ARP_WORK_XB0) && rule_is_xbond(S, P, b, bx, by, bz, ex, ey, ez, fb, &fault)) m |= 1u << ARP_SIFT_XBOND;
-    if ((work & ARP_WORK_XB1) && rule_is_xbond(S, P, e, ex, ey, ez, bx, by, bz, fe, &fault)) m |= 1u << ARP_SIFT_XBOND;
+    if ((work & ARP_WORK_XB0) && rule_is_xbond(S, P, b, bx, by, bz, ex, ey, ez, S.feat[b], &fault)) m |= 1u << ARP_SIFT_XBOND;
+    if ((work & ARP_WORK_XB1) && rule_is_xbond(S, P, e, ex, ey, ez, bx, by, bz, S.feat[e], &fault)) m |= 1u << ARP_SIFT_XBOND;
     *mask_out = m | fault;
 }
 

@@ -14,9 +14,11 @@ extern "C" int emu_classify(const arp_atoms* A, const arp_params* P, const int32
     ArpSide S;
     memset(&S, 0, sizeof S);
     S.vdw = A->vdw; S.cov = A->cov; S.K = A->n_rad_classes;
+    S.feat = A->feat;
     S.bond_off = A->bond_off; S.bond_nbr = A->bond_nbr; S.h_off = A->h_off; S.h_xyz = A->h_xyz; S.xnbr = A->xnbr_xyz;
     float4* tab = 0;
-    if (use_table) {
+    (void)use_table;
+    {
         int K = S.K;
         tab = new float4[(size_t)K * K];
         for (int x = 0; x < K; ++x) for (int y = 0; y < K; ++y) {
@@ -28,11 +30,8 @@ extern "C" int emu_classify(const arp_atoms* A, const arp_params* P, const int32
     for (int64_t k = 0; k < n; ++k) {
         int i = b[k], j = e[k];
         auto word = [&](int a) {
-            int r = A->res_id[a];
-            uint32_t w = (A->feat[a] & 0xFFFFFu) | ((uint32_t)(A->res_flags[r] & 3u) << ARPK_RES_SHIFT) |
-                         ((uint32_t)A->rad_class[a] << ARPK_RAD_SHIFT);
-            if (A->bond_off && A->bond_off[a + 1] > A->bond_off[a]) w |= ARPK_HAS_BOND;
-            return w;
+            return arp_pack_word(A->feat[a], A->res_flags[A->res_id[a]], A->rad_class[a],
+                                 A->bond_off && A->bond_off[a + 1] > A->bond_off[a]);
         };
         uint32_t fb = word(i), fe = word(j);
         int rb = A->res_id[i], re = A->res_id[j];

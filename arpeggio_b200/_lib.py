@@ -10,7 +10,7 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libarpeggio_cuda.so')
+LIB_PATH = os.environ.get('ARPEGGIO_CUDA_LIB') or os.path.join(_HERE, 'libarpeggio_cuda.so')   # override: A/B builds
 _LIB = None
 
 

@@ -35,17 +35,30 @@ struct StructGeom {
     int    pad;
 };
 
-/* counters the kernels leave behind (device, copied to pinned host memory after a run) */
-struct RunMeta {
-    unsigned long long n_pairs;       /* record cursor: total records the run produced */
-    unsigned long long n_candidates;  /* distance tests performed */
+/* counters the kernels leave behind (device, copied to pinned host memory after a run).
+   Every counter that many warps hammer with atomics sits on its own 128-byte line. */
+struct alignas(128) RunMeta {
+    /* line 0: written once by k_geom, read by everybody */
     unsigned int n_cells;
-    unsigned int n_cells_nonempty;
-    unsigned int ticket[4];           /* dynamic tile ids: [0] cell scan, [1] pair kernel, [2] sort scan */
-    unsigned int fault;               /* sticky device-side diagnostics */
     unsigned int r2_lo_inv;           /* 0x7f800000 - bits(min over structures of r2_lo); 0x7f800000 = no quick accept */
+    unsigned int fault;               /* sticky device-side diagnostics */
+    unsigned int pad0[29];
+    /* line 1 */
     unsigned long long n_raw;         /* candidate cursor of k_search */
-    unsigned int pad[2];
+    unsigned int pad1[30];
+    /* line 2 */
+    unsigned long long n_pairs;       /* record cursor: total records the run produced */
+    unsigned int pad2[30];
+    /* line 3 */
+    unsigned int ticket_search;       /* dynamic cell tickets of k_search */
+    unsigned int pad3[31];
+    /* line 4 */
+    unsigned int ticket_scan;         /* dynamic tile ids of the cell scan */
+    unsigned int pad4[31];
+    /* line 5: end-of-kernel statistics */
+    unsigned long long n_candidates;  /* distance tests performed */
+    unsigned int n_cells_nonempty;
+    unsigned int pad5[29];
 };
 
 struct PlaneSet {

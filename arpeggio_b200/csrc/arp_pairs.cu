@@ -331,7 +331,10 @@ __global__ void __launch_bounds__(256) k_scatter(int N, const float* __restrict_
 #define SEARCH_CHUNK  (32 * SEARCH_SLOTS)
 #define SEARCH_QCAP   256                   /* queue capacity per warp: < DRAIN before a home atom, + <= CHUNK hits */
 #define SEARCH_DRAIN  128
-#define SEARCH_CELLS  4                     /* cells per ticket; 8 lanes describe one cell's runs */
+#ifndef SEARCH_CELLS
+#define SEARCH_CELLS  4
+#endif
+/* cells per ticket (<= 4); 8 lanes describe one cell's runs */
 
 struct SearchArgs {
     const float4* pos4;
@@ -405,6 +408,9 @@ __device__ __forceinline__ void search_chunk(const SearchArgs& A, uint2* q, uint
 #ifndef SEARCH_MINB
 #define SEARCH_MINB 4
 #endif
+#ifndef SEARCH_GRID_MULT
+#define SEARCH_GRID_MULT SEARCH_MINB
+#endif
 __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(SearchArgs A)
 {
     __shared__ uint2 s_queue[SEARCH_WARPS][SEARCH_QCAP];
@@ -421,12 +427,27 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
     int s = 0;                                  /* warp-uniform: structure of the ticket's first cell */
     int s_end = A.geom[0].cell_base + A.geom[0].ncell;
 
+    /* tickets: the first one is static (ticket = global warp id), the rest come from a shared counter that
+       starts at the number of warps; a plain read screens the counter so that late warps leave without
+       an atomic */
+    const unsigned n_warps_total = gridDim.x * SEARCH_WARPS;
+    const unsigned n_tickets = ((unsigned)n_cells + SEARCH_CELLS - 1) / SEARCH_CELLS;
+    bool first = true;
     for (;;) {
-        int t = 0;
-        if (lane == 0) t = (int)atomicAdd(&A.meta->ticket[1], 1u);
-        t = __shfl_sync(FULL, t, 0);
+        unsigned t = 0;
+        if (first) {
+            t = blockIdx.x * SEARCH_WARPS + warp;
+            first = false;
+        } else {
+            if (lane == 0) {
+                t = n_tickets;
+                if (*(volatile unsigned*)&A.meta->ticket_search + n_warps_total < n_tickets)
+                    t = atomicAdd(&A.meta->ticket_search, 1u) + n_warps_total;
+            }
+            t = __shfl_sync(FULL, t, 0);
+        }
+        if (t >= n_tickets) break;
         const long long c0l = (long long)t * SEARCH_CELLS;
-        if (c0l >= n_cells) break;
         const int c0 = (int)c0l;
         while (c0 >= s_end) { ++s; s_end = A.geom[s].cell_base + A.geom[s].ncell; }   /* tickets ascend */
         /* ---- run tables of the ticket's cells: lane = (cell q, run r) ---- */
@@ -435,7 +456,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
             const int c = c0 + qc;
             int rbeg = 0, rlen = 0, nh = 0;
             float band_lo = 0.f, band_hi = 0.f;
-            if (c < n_cells) {
+            if (qc < SEARCH_CELLS && c < n_cells) {
                 const StructGeom* gp = A.geom + s;
                 while (c >= gp->cell_base + gp->ncell) ++gp;                  /* the cell may lie in a later structure */
                 band_lo = gp->r2_lo; band_hi = gp->r2_hi;
@@ -466,9 +487,11 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
             const int total = __shfl_sync(FULL, incl, 7, 8);
             nh = __shfl_sync(FULL, nh, 0, 8);
             __syncwarp();
-            if (r < 5) s_runs[warp][qc][r] = make_int2(rbeg, incl - rlen);
-            else if (r == 5) s_runs[warp][qc][5] = make_int2(total, nh);
-            else if (r == 6) s_runs[warp][qc][6] = make_int2(__float_as_int(band_lo), __float_as_int(band_hi));
+            if (qc < SEARCH_CELLS) {
+                if (r < 5) s_runs[warp][qc][r] = make_int2(rbeg, incl - rlen);
+                else if (r == 5) s_runs[warp][qc][5] = make_int2(total, nh);
+                else if (r == 6) s_runs[warp][qc][6] = make_int2(__float_as_int(band_lo), __float_as_int(band_hi));
+            }
             __syncwarp();
         }
         for (int qc = 0; qc < SEARCH_CELLS; ++qc) {
@@ -524,11 +547,11 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
  * runs them without any block barrier:
  *   stage 0  32 candidates per round: the exact double test of Bio.PDB.kdtrees inside the float32 band,
  *            orientation (atom_bgn = lower list index), the reference's `continue` filters
- *            (interactions.py:712-741); survivors are compacted into the warp's shared-memory list
- *   stage 1  32 survivors per round: exact float32 distance, proximity bit, metal, the feature bits that
- *            need no angle (rule_classify_core, interactions.py:743-936); the record goes to the warp's
- *            staging tile; pairs that need a hydrogen scan (is_hbond / is_weak_hbond) or a rarer
- *            predicate (halogen weak hbond, xbond) append a 32-bit work item to the warp's work list
+ *            (interactions.py:712-741)
+ *   stage 1  the survivors, still in their lanes: exact float32 distance, proximity bit, metal, the
+ *            feature bits that need no angle (rule_classify_core, interactions.py:743-936); records are
+ *            compacted (ballot) into the warp's staging tile; pairs that need a hydrogen scan (is_hbond /
+ *            is_weak_hbond) or a rarer predicate (halogen weak hbond, xbond) append a 32-bit work item
  *   stage 2  the work list is processed densely -- 32 items per round -- and each result bit is OR-ed
  *            into the staged record
  *   stage 3  the finished tile leaves with one bulk asynchronous copy shared -> global (cp.async.bulk,
@@ -536,6 +559,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
  *            the arithmetic of the next.                                                              */
 #define CLS_WARPS   8
 #define CLS_TILE    128
+#define CLS_TAB_K   16                      /* radius tables up to K x K = 256 entries are staged in shared memory */
 #define CLS_ITEMS   (3 * CLS_TILE)          /* per pair at most: is_hbond scan + (is_weak_hbond scan | halogen) + xbond */
 #define CLS_SMEM_PER_WARP (2 * CLS_TILE * 16 + CLS_ITEMS * 4 + CLS_TILE * 8)
 #define CLS_SMEM    (CLS_WARPS * CLS_SMEM_PER_WARP)
@@ -588,6 +612,16 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
     uint32_t* const items = reinterpret_cast<uint32_t*>(mine + 2 * CLS_TILE * 16);
     uint2* const surv = reinterpret_cast<uint2*>(mine + 2 * CLS_TILE * 16 + CLS_ITEMS * 4);
     const unsigned lt_mask = (1u << lane) - 1u;
+    /* small radius tables live in shared memory: one dependent global load less per pair */
+    __shared__ float4 s_radtab[CLS_TAB_K * CLS_TAB_K];
+    __shared__ double s_vdw[CLS_TAB_K];
+    if (A.side.K <= CLS_TAB_K) {
+        for (int k = threadIdx.x; k < A.side.K * A.side.K; k += blockDim.x) s_radtab[k] = A.side.radtab[k];
+        for (int k = threadIdx.x; k < A.side.K; k += blockDim.x) s_vdw[k] = A.side.vdw[k];
+        __syncthreads();
+        A.side.radtab = s_radtab;
+        A.side.vdw = s_vdw;
+    }
     unsigned long long n = A.meta->n_raw;
     if (n > A.cap) n = A.cap;                                    /* overflowing run: host repeats it with a larger buffer */
     const float r2_lo = A.meta->r2_lo_inv == 0x7f800000u ? -1.0f : __uint_as_float(0x7f800000u - A.meta->r2_lo_inv);
@@ -598,16 +632,23 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
     for (unsigned long long tile = warp_id; tile < n_tiles; tile += n_warps) {
         const unsigned long long base = tile * CLS_TILE;
         const unsigned cnt = (unsigned)min((unsigned long long)CLS_TILE, n - base);
-        /* ---- stage 0: exact test, orientation, filters ---- */
-        unsigned nsurv = 0;
+        int4* rec = rec0 + buf * CLS_TILE;
+        if (lane == 0) bulk_store_wait_read_1();                 /* the store that last used this buffer has read it */
+        __syncwarp();
+        /* ---- stages 0 + 1, 32 candidates per round ---- */
+        unsigned nsurv = 0, n_items = 0;
+        uint2 e_next = lane < cnt ? A.raw[base + lane] : make_uint2(0, 0);   /* candidates are fetched one round ahead */
+#pragma unroll 1
         for (unsigned i0 = 0; i0 < cnt; i0 += 32) {
             const unsigned idx = i0 + lane;
             bool keep = false;
-            uint2 e = make_uint2(0, 0);
+            uint2 e = e_next;
+            if (idx + 32 < cnt) e_next = A.raw[base + idx + 32];
+            float4 pa, pb;
+            uint4 ab, ae;
             if (idx < cnt) {
-                e = A.raw[base + idx];
-                const float4 pa = A.pos4[e.x], pb = A.pos4[e.y];
-                uint4 ab = A.att4[e.x], ae = A.att4[e.y];
+                pa = A.pos4[e.x]; pb = A.pos4[e.y];
+                ab = A.att4[e.x]; ae = A.att4[e.y];
                 const float ddx = pa.x - pb.x, ddy = pa.y - pb.y, ddz = pa.z - pb.z;
                 const float d2 = __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, __fmul_rn(ddx, ddx)));   /* as in k_search */
                 keep = true;
@@ -615,53 +656,45 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
                 if (__float_as_int(pb.w) < __float_as_int(pa.w)) {          /* atom_bgn = lower list index */
                     const unsigned t = e.x; e.x = e.y; e.y = t;
                     const uint4 tt = ab; ab = ae; ae = tt;
+                    const float4 tp = pa; pa = pb; pb = tp;
                 }
                 keep = keep && rule_pair_survives(ab.x, (int)ab.y, (int)ab.z, (int)ab.w, ae.x, (int)ae.y, (int)ae.z, (int)ae.w,
                                                   A.include_seq_adjacent);
             }
-            const unsigned m = __ballot_sync(FULL, keep);
-            if (keep) surv[nsurv + __popc(m & lt_mask)] = e;
-            nsurv += __popc(m);
-        }
-        if (nsurv == 0) continue;
-        int4* rec = rec0 + buf * CLS_TILE;
-        if (lane == 0) bulk_store_wait_read_1();                 /* the store that last used this buffer has read it */
-        __syncwarp();
-        /* ---- stage 1 ---- */
-        unsigned n_items = 0;
-        for (unsigned i0 = 0; i0 < nsurv; i0 += 32) {
-            const unsigned idx = i0 + lane;
+            /* survivors keep their lane for the rules; their records are compacted into the staging tile */
+            const unsigned mk = __ballot_sync(FULL, keep);
+            const unsigned slot = nsurv + __popc(mk & lt_mask);
+            nsurv += __popc(mk);
             uint32_t work = 0;
-            if (idx < nsurv) {
-                const uint2 e = surv[idx];
-                const float4 pb = A.pos4[e.x], pe = A.pos4[e.y];
-                const uint32_t fb = A.att4[e.x].x, fe = A.att4[e.y].x;
-                const int ib = __float_as_int(pb.w), ie = __float_as_int(pe.w);
+            if (keep) {
+                const int ib = __float_as_int(pa.w), ie = __float_as_int(pb.w);
                 uint32_t mask; float dist;
-                rule_classify_core(A.side, P, ib, ie, pb.x, pb.y, pb.z, pe.x, pe.y, pe.z, fb, fe, &mask, &dist, &work);
-                rec[idx] = make_int4(ib, ie, (int)mask, __float_as_int(dist));
+                rule_classify_core(A.side, P, ib, ie, pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, ab.x, ae.x, &mask, &dist, &work);
+                rec[slot] = make_int4(ib, ie, (int)mask, __float_as_int(dist));
+                if (work) surv[slot] = e;                        /* stage 2 finds donor / acceptor through this */
             }
             /* append the work items of this round, one kind of slot at a time (ballot compaction) */
-            {
+            if (__any_sync(FULL, work != 0)) {
                 unsigned m = __ballot_sync(FULL, (work & ARP_WORK_SCAN0) != 0);
-                if (work & ARP_WORK_SCAN0) items[n_items + __popc(m & lt_mask)] = (idx << 4) | (work & 3u);
+                if (work & ARP_WORK_SCAN0) items[n_items + __popc(m & lt_mask)] = (slot << 4) | (work & 3u);
                 n_items += __popc(m);
                 m = __ballot_sync(FULL, (work & ARP_WORK_SCAN1) != 0);
-                if (work & ARP_WORK_SCAN1) items[n_items + __popc(m & lt_mask)] = (idx << 4) | 8u | ((work >> 2) & 3u);
+                if (work & ARP_WORK_SCAN1) items[n_items + __popc(m & lt_mask)] = (slot << 4) | 8u | ((work >> 2) & 3u);
                 n_items += __popc(m);
                 const uint32_t rare = work & (ARP_WORK_HAL0 | ARP_WORK_HAL1 | ARP_WORK_XB0 | ARP_WORK_XB1);
                 if (__any_sync(FULL, rare != 0)) {
                     m = __ballot_sync(FULL, (rare & (ARP_WORK_HAL0 | ARP_WORK_HAL1)) != 0);
                     if (rare & (ARP_WORK_HAL0 | ARP_WORK_HAL1))
-                        items[n_items + __popc(m & lt_mask)] = (idx << 4) | ((rare & ARP_WORK_HAL1) ? 8u : 0u) | CLS_KIND_HAL;
+                        items[n_items + __popc(m & lt_mask)] = (slot << 4) | ((rare & ARP_WORK_HAL1) ? 8u : 0u) | CLS_KIND_HAL;
                     n_items += __popc(m);
                     m = __ballot_sync(FULL, (rare & (ARP_WORK_XB0 | ARP_WORK_XB1)) != 0);
                     if (rare & (ARP_WORK_XB0 | ARP_WORK_XB1))
-                        items[n_items + __popc(m & lt_mask)] = (idx << 4) | ((rare & ARP_WORK_XB1) ? 8u : 0u) | CLS_KIND_XBOND;
+                        items[n_items + __popc(m & lt_mask)] = (slot << 4) | ((rare & ARP_WORK_XB1) ? 8u : 0u) | CLS_KIND_XBOND;
                     n_items += __popc(m);
                 }
             }
         }
+        if (nsurv == 0) continue;                                /* nothing staged: the buffer stays free */
         __syncwarp();
         /* ---- stage 2: the deferred predicates, 32 items per round ---- */
         for (unsigned w0 = 0; w0 < n_items; w0 += 32) {
@@ -762,7 +795,7 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         k_cellid<<<blocks, 256, 0, st>>>(c->xyz.as<float>(), so, S, N, c->geom.as<StructGeom>(), cell_cnt,
                                          c->cell_of.as<int>(), c->rank.as<int>());
         ARP_LAUNCHED(c);
-        ARP_TRY(arp_scan_exclusive(c, cell_cnt, c->cell_start.as<int>(), state, &meta->ticket[0], &meta->n_cells, 1,
+        ARP_TRY(arp_scan_exclusive(c, cell_cnt, c->cell_start.as<int>(), state, &meta->ticket_scan, &meta->n_cells, 1,
                                    c->cell_bound + 1));
         k_scatter<<<blocks, 256, 0, st>>>(N, c->xyz.as<float>(), c->feat.as<uint32_t>(), c->res_id.as<int32_t>(),
                                           c->rad_class.as<uint16_t>(), c->res_prev.as<int32_t>(), c->res_next.as<int32_t>(),
@@ -798,7 +831,7 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         SearchArgs SA;
         SA.pos4 = c->pos4.as<float4>(); SA.cell_start = c->cell_start.as<int>();
         SA.geom = c->geom.as<StructGeom>(); SA.meta = meta; SA.raw = c->hits.as<uint2>(); SA.cap = c->out_cap;
-        unsigned grid = (unsigned)(c->sm_count * SEARCH_MINB);
+        unsigned grid = (unsigned)(c->sm_count * SEARCH_GRID_MULT);
         size_t want = ((size_t)N / 24) / SEARCH_WARPS + 1;     /* about one warp per few cells on small inputs */
         if (want < grid) grid = (unsigned)want;
         k_search<<<grid, SEARCH_WARPS * 32, 0, st>>>(SA);

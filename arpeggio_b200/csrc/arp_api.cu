@@ -190,6 +190,7 @@ int arp_create(int device, arp_ctx** out)
         return ARP_E_CUDA;
     }
     memset(c->h_meta, 0, sizeof(RunMeta));
+    if (getenv("ARPEGGIO_NO_FUSED_GRID")) c->use_fused_grid = 0;     /* debugging / A-B knob: five-kernel grid build */
     memset(&c->stats, 0, sizeof c->stats);
     arp_params_default(&c->params);
     derive_rule_params(c->params, &c->rp);

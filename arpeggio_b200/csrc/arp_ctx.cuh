@@ -101,6 +101,8 @@ struct arp_ctx {
     DBuf radtab;                  /* K x K float32 proximity thresholds */
     int radtab_valid = 0;
     int cls_smem_set = 0;
+    int coop_blocks = -1;         /* co-resident blocks of k_grid_fused (0: not available, -1: not probed) */
+    int use_fused_grid = 1;
     RunMeta* h_meta = nullptr;    /* pinned */
 
     /* output stream */

@@ -22,7 +22,11 @@
  *              hydrogen scans and rare exact predicates compacted and run densely, records
  *              staged in shared memory and stored tile by tile with cp.async.bulk
  */
+#include <cooperative_groups.h>
+
 #include "arp_ctx.cuh"
+
+namespace cg = cooperative_groups;
 
 #define FULL 0xffffffffu
 
@@ -49,21 +53,29 @@ __device__ __forceinline__ int struct_of(const int* __restrict__ struct_off, int
     return lo;
 }
 
-/* ---- k_bbox --------------------------------------------------------------------------
+/* ======================================================================================
+ * Grid build.  Five phases, written as block-level device functions over a VIRTUAL block id so
+ * that they run either as five small kernels (batches of structures, very large inputs) or as
+ * one cooperative persistent kernel with grid-wide barriers in between (k_grid_fused: a single
+ * launch instead of five -- the phases are latency-, not throughput-bound at 10^5 atoms).
+ * ====================================================================================== */
+#define GRID_THREADS       256
+#define BBOX_ATOMS_PER_VB  (GRID_THREADS * 4)
+
+/* ---- phase 1: bounding boxes --------------------------------------------------------------
  * bbox[s][0..2] = max over atoms of ~ord(coord)  (i.e. the minimum), [3..5] = max of ord(coord).
  * Zero-initialised, so a structure without atoms keeps all zeros.                        */
-__global__ void __launch_bounds__(256) k_bbox(const float* __restrict__ xyz, const int* __restrict__ struct_off,
-                                              int S, int N, unsigned* __restrict__ bbox)
+__device__ __forceinline__ void dev_bbox(const float* __restrict__ xyz, const int* __restrict__ struct_off,
+                                         int S, int N, unsigned* __restrict__ bbox, int vb)
 {
     __shared__ unsigned s_v[8][6];
     __shared__ int s_s[8];
-    const int ATOMS_PER_THREAD = 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int base = blockIdx.x * (256 * ATOMS_PER_THREAD);
-    int s = -1;                       /* structure of this thread's atoms; -2 = mixed */
+    const int base = vb * BBOX_ATOMS_PER_VB;
+    int s = -1;                       /* structure of this thread's atoms */
     unsigned v[6] = {0, 0, 0, 0, 0, 0};
-    for (int t = 0; t < ATOMS_PER_THREAD; ++t) {
-        int i = base + t * 256 + threadIdx.x;
+    for (int t = 0; t < BBOX_ATOMS_PER_VB / GRID_THREADS; ++t) {
+        int i = base + t * GRID_THREADS + threadIdx.x;
         if (i >= N) break;
         int si = struct_of(struct_off, S, i);
         if (s == -1) s = si;
@@ -88,6 +100,7 @@ __global__ void __launch_bounds__(256) k_bbox(const float* __restrict__ xyz, con
     } else if (s >= 0) {
         for (int k = 0; k < 6; ++k) atomicMax(&bbox[6 * (size_t)s + k], v[k]);
     }
+    __syncthreads();                  /* the previous virtual block's readers are done with s_v / s_s */
     if (lane == 0) {
         s_s[warp] = uniform ? smax : -1;
         for (int k = 0; k < 6; ++k) s_v[warp][k] = v[k];
@@ -109,12 +122,12 @@ __global__ void __launch_bounds__(256) k_bbox(const float* __restrict__ xyz, con
     }
 }
 
-/* ---- k_geom: one block ------------------------------------------------------------------ */
-__global__ void __launch_bounds__(256) k_geom(const unsigned* __restrict__ bbox, const int* __restrict__ struct_off,
-                                              int S, int N, double cutoff, StructGeom* __restrict__ geom,
-                                              RunMeta* __restrict__ meta)
+/* ---- phase 2: per-structure grids, one block ---------------------------------------------- */
+__device__ __forceinline__ void dev_geom(const unsigned* __restrict__ bbox, const int* __restrict__ struct_off,
+                                         int S, int N, double cutoff, StructGeom* __restrict__ geom,
+                                         RunMeta* __restrict__ meta)
 {
-    __shared__ int s_sum[256];
+    __shared__ int s_sum[GRID_THREADS];
     __shared__ int s_carry;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
@@ -130,8 +143,8 @@ __global__ void __launch_bounds__(256) k_geom(const unsigned* __restrict__ bbox,
                 double mn[3], mx[3], amax = 0.0;
                 bool finite = true;
                 for (int k = 0; k < 3; ++k) {
-                    mn[k] = (double)ord2f(~bbox[6 * (size_t)s + k]);
-                    mx[k] = (double)ord2f(bbox[6 * (size_t)s + 3 + k]);
+                    mn[k] = (double)ord2f(~__ldcg(&bbox[6 * (size_t)s + k]));
+                    mx[k] = (double)ord2f(__ldcg(&bbox[6 * (size_t)s + 3 + k]));
                     if (!(fabs(mn[k]) <= 3.0e38) || !(fabs(mx[k]) <= 3.0e38)) finite = false;
                     amax = fmax(amax, fmax(fabs(mn[k]), fabs(mx[k])));
                 }
@@ -194,13 +207,12 @@ __device__ __forceinline__ int cell_coord(double v, double o, double inv_w, int 
     return (int)t;
 }
 
-/* ---- k_cellid ------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(256) k_cellid(const float* __restrict__ xyz, const int* __restrict__ struct_off,
-                                                int S, int N, const StructGeom* __restrict__ geom,
-                                                int* __restrict__ cell_cnt, int* __restrict__ cell_of,
-                                                int* __restrict__ rank)
+/* ---- phase 3: cell of every atom, rank inside the cell ---------------------------------------- */
+__device__ __forceinline__ void dev_cellid(const float* __restrict__ xyz, const int* __restrict__ struct_off,
+                                           int S, int N, const StructGeom* __restrict__ geom,
+                                           int* __restrict__ cell_cnt, int* __restrict__ cell_of,
+                                           int* __restrict__ rank, int i)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     int s = struct_of(struct_off, S, i);
     const StructGeom* g = geom + s;
@@ -212,32 +224,26 @@ __global__ void __launch_bounds__(256) k_cellid(const float* __restrict__ xyz, c
     rank[i] = atomicAdd(&cell_cnt[c], 1);
 }
 
-/* ---- k_scan: single-pass exclusive scan (decoupled look-back) -------------------------- */
-#define SCAN_THREADS 256
+/* ---- phase 4: single-pass exclusive scan (decoupled look-back) ------------------------------ */
+#define SCAN_THREADS GRID_THREADS
 #define SCAN_ITEMS   (ARP_SCAN_TILE / SCAN_THREADS)
 #define ST_AGG  (1ull << 62)
 #define ST_INCL (2ull << 62)
 #define ST_MASK (3ull << 62)
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(const int* __restrict__ in, int* __restrict__ out,
-                                                       unsigned long long* state, unsigned int* ticket,
-                                                       const unsigned int* n_dev, int n_add)
+/* one tile of ARP_SCAN_TILE items; every tile below `tile` has been started by a resident block */
+__device__ __forceinline__ void dev_scan_tile(const int* __restrict__ in, int* __restrict__ out,
+                                              unsigned long long* state, long long n, int tile)
 {
-    __shared__ int s_tile;
     __shared__ int s_warp[SCAN_THREADS / 32];
     __shared__ int s_prefix;
-    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
-    __syncthreads();
-    const int tile = s_tile;
-    const long long n = (long long)(n_dev ? *n_dev : 0u) + n_add;
     const long long base = (long long)tile * ARP_SCAN_TILE;
-    if (base >= n) return;
     const long long first = base + (long long)threadIdx.x * SCAN_ITEMS;
     int v[SCAN_ITEMS];
     int sum = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) {
-        v[k] = (first + k < n) ? in[first + k] : 0;
+        v[k] = (first + k < n) ? __ldcg(&in[first + k]) : 0;
         sum += v[k];
     }
     /* block scan of the thread sums */
@@ -248,6 +254,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const int* __restrict__ i
         int t = __shfl_up_sync(FULL, incl, off);
         if (lane >= off) incl += t;
     }
+    __syncthreads();                  /* readers of the previous tile are done with the shared words */
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
     if (warp == 0) {
@@ -291,6 +298,60 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const int* __restrict__ i
     }
 }
 
+/* ---- phase 5: atoms into cell order ------------------------------------------------------------ */
+struct ScatterArgs {
+    const float* xyz; const uint32_t* feat; const int32_t* res_id; const uint16_t* rad_class;
+    const int32_t* res_prev; const int32_t* res_next; const uint8_t* res_flags; const int32_t* bond_off;
+    const int* cell_of; const int* rank; const int* cell_start;
+    float4* pos4; uint4* att4;
+};
+
+__device__ __forceinline__ void dev_scatter(const ScatterArgs& A, int N, int i)
+{
+    if (i >= N) return;
+    int dst = __ldcg(&A.cell_start[A.cell_of[i]]) + A.rank[i];
+    int r = A.res_id[i];
+    const uint32_t w = arp_pack_word(A.feat[i], A.res_flags[r], A.rad_class[i],
+                                     A.bond_off && A.bond_off[i + 1] > A.bond_off[i]);
+    A.pos4[dst] = make_float4(A.xyz[3 * (size_t)i], A.xyz[3 * (size_t)i + 1], A.xyz[3 * (size_t)i + 2], __int_as_float(i));
+    A.att4[dst] = make_uint4(w, (uint32_t)r, (uint32_t)A.res_prev[r], (uint32_t)A.res_next[r]);
+}
+
+/* ---- the phases as separate kernels ------------------------------------------------------------- */
+__global__ void __launch_bounds__(GRID_THREADS) k_bbox(const float* __restrict__ xyz, const int* __restrict__ struct_off,
+                                                       int S, int N, unsigned* __restrict__ bbox)
+{
+    dev_bbox(xyz, struct_off, S, N, bbox, blockIdx.x);
+}
+
+__global__ void __launch_bounds__(GRID_THREADS) k_geom(const unsigned* __restrict__ bbox, const int* __restrict__ struct_off,
+                                                       int S, int N, double cutoff, StructGeom* __restrict__ geom,
+                                                       RunMeta* __restrict__ meta)
+{
+    dev_geom(bbox, struct_off, S, N, cutoff, geom, meta);
+}
+
+__global__ void __launch_bounds__(GRID_THREADS) k_cellid(const float* __restrict__ xyz, const int* __restrict__ struct_off,
+                                                         int S, int N, const StructGeom* __restrict__ geom,
+                                                         int* __restrict__ cell_cnt, int* __restrict__ cell_of,
+                                                         int* __restrict__ rank)
+{
+    dev_cellid(xyz, struct_off, S, N, geom, cell_cnt, cell_of, rank, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(const int* __restrict__ in, int* __restrict__ out,
+                                                       unsigned long long* state, unsigned int* ticket,
+                                                       const unsigned int* n_dev, int n_add)
+{
+    __shared__ int s_tile;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);   /* tiles in order of execution start */
+    __syncthreads();
+    const int tile = s_tile;
+    const long long n = (long long)(n_dev ? *n_dev : 0u) + n_add;
+    if ((long long)tile * ARP_SCAN_TILE >= n) return;
+    dev_scan_tile(in, out, state, n, tile);
+}
+
 int arp_scan_exclusive(arp_ctx* c, const int* in, int* out, unsigned long long* state, unsigned int* ticket,
                        const unsigned int* n_dev, int n_add, size_t n_bound)
 {
@@ -301,22 +362,51 @@ int arp_scan_exclusive(arp_ctx* c, const int* in, int* out, unsigned long long* 
     return ARP_OK;
 }
 
-/* ---- k_scatter ------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(256) k_scatter(int N, const float* __restrict__ xyz, const uint32_t* __restrict__ feat,
-                                                 const int32_t* __restrict__ res_id, const uint16_t* __restrict__ rad_class,
-                                                 const int32_t* __restrict__ res_prev, const int32_t* __restrict__ res_next,
-                                                 const uint8_t* __restrict__ res_flags, const int32_t* __restrict__ bond_off,
-                                                 const int* __restrict__ cell_of, const int* __restrict__ rank,
-                                                 const int* __restrict__ cell_start,
-                                                 float4* __restrict__ pos4, uint4* __restrict__ att4)
+__global__ void __launch_bounds__(GRID_THREADS) k_scatter(int N, ScatterArgs A)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    int dst = cell_start[cell_of[i]] + rank[i];
-    int r = res_id[i];
-    const uint32_t w = arp_pack_word(feat[i], res_flags[r], rad_class[i], bond_off && bond_off[i + 1] > bond_off[i]);
-    pos4[dst] = make_float4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], __int_as_float(i));
-    att4[dst] = make_uint4(w, (uint32_t)r, (uint32_t)res_prev[r], (uint32_t)res_next[r]);
+    dev_scatter(A, N, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+/* ---- the phases as one cooperative kernel ----------------------------------------------------- */
+struct GridArgs {
+    int N, S;
+    double cutoff;
+    const int* struct_off;
+    unsigned* bbox;
+    StructGeom* geom;
+    RunMeta* meta;
+    int* cell_cnt;
+    unsigned long long* scan_state;
+    ScatterArgs sc;                 /* sc.cell_of / rank / cell_start are written by earlier phases */
+    int* cell_of; int* rank; int* cell_start;
+};
+
+__global__ void __launch_bounds__(GRID_THREADS) k_grid_fused(GridArgs G)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int N = G.N;
+    const int vb_atoms = (N + GRID_THREADS - 1) / GRID_THREADS;
+    for (int vb = blockIdx.x; vb * BBOX_ATOMS_PER_VB < N; vb += gridDim.x)
+        dev_bbox(G.sc.xyz, G.struct_off, G.S, N, G.bbox, vb);
+    __threadfence();
+    grid.sync();
+    if (blockIdx.x == 0) dev_geom(G.bbox, G.struct_off, G.S, N, G.cutoff, G.geom, G.meta);
+    __threadfence();
+    grid.sync();
+    for (int vb = blockIdx.x; vb < vb_atoms; vb += gridDim.x)
+        dev_cellid(G.sc.xyz, G.struct_off, G.S, N, G.geom, G.cell_cnt, G.cell_of, G.rank, vb * GRID_THREADS + threadIdx.x);
+    __threadfence();
+    grid.sync();
+    {
+        const long long n = (long long)__ldcg(&G.meta->n_cells) + 1;
+        const int tiles = (int)((n + ARP_SCAN_TILE - 1) / ARP_SCAN_TILE);
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x)     /* ascending per block, blocks co-resident */
+            dev_scan_tile(G.cell_cnt, G.cell_start, G.scan_state, n, tile);
+    }
+    __threadfence();
+    grid.sync();
+    for (int vb = blockIdx.x; vb < vb_atoms; vb += gridDim.x)
+        dev_scatter(G.sc, N, vb * GRID_THREADS + threadIdx.x);
 }
 
 /* ---- k_search ---------------------------------------------------------------------------------
@@ -787,22 +877,45 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
     if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[0], st));
     ARP_CUDA(c, cudaMemsetAsync(z, 0, c->zero_bytes, st));
     if (N > 0) {
-        unsigned blocks = (unsigned)((N + 255) / 256);
-        k_bbox<<<(unsigned)((N + 1023) / 1024), 256, 0, st>>>(c->xyz.as<float>(), so, S, N, bbox);
-        ARP_LAUNCHED(c);
-        k_geom<<<1, 256, 0, st>>>(bbox, so, S, N, c->params.interacting_cutoff, c->geom.as<StructGeom>(), meta);
-        ARP_LAUNCHED(c);
-        k_cellid<<<blocks, 256, 0, st>>>(c->xyz.as<float>(), so, S, N, c->geom.as<StructGeom>(), cell_cnt,
-                                         c->cell_of.as<int>(), c->rank.as<int>());
-        ARP_LAUNCHED(c);
-        ARP_TRY(arp_scan_exclusive(c, cell_cnt, c->cell_start.as<int>(), state, &meta->ticket_scan, &meta->n_cells, 1,
-                                   c->cell_bound + 1));
-        k_scatter<<<blocks, 256, 0, st>>>(N, c->xyz.as<float>(), c->feat.as<uint32_t>(), c->res_id.as<int32_t>(),
-                                          c->rad_class.as<uint16_t>(), c->res_prev.as<int32_t>(), c->res_next.as<int32_t>(),
-                                          c->res_flags.as<uint8_t>(), c->has_bonds ? c->bond_off.as<int32_t>() : nullptr,
-                                          c->cell_of.as<int>(), c->rank.as<int>(), c->cell_start.as<int>(),
-                                          c->pos4.as<float4>(), c->att4.as<uint4>());
-        ARP_LAUNCHED(c);
+        ScatterArgs SC;
+        SC.xyz = c->xyz.as<float>(); SC.feat = c->feat.as<uint32_t>(); SC.res_id = c->res_id.as<int32_t>();
+        SC.rad_class = c->rad_class.as<uint16_t>(); SC.res_prev = c->res_prev.as<int32_t>();
+        SC.res_next = c->res_next.as<int32_t>(); SC.res_flags = c->res_flags.as<uint8_t>();
+        SC.bond_off = c->has_bonds ? c->bond_off.as<int32_t>() : nullptr;
+        SC.cell_of = c->cell_of.as<int>(); SC.rank = c->rank.as<int>(); SC.cell_start = c->cell_start.as<int>();
+        SC.pos4 = c->pos4.as<float4>(); SC.att4 = c->att4.as<uint4>();
+        unsigned blocks = (unsigned)((N + GRID_THREADS - 1) / GRID_THREADS);
+        if (c->coop_blocks < 0) {           /* once per context: can the grid build run as one cooperative kernel? */
+            int coop = 0, per_sm = 0;
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+            if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_grid_fused, GRID_THREADS, 0) == cudaSuccess)
+                c->coop_blocks = per_sm * c->sm_count;
+            else
+                c->coop_blocks = 0;
+            (void)cudaGetLastError();
+        }
+        if (c->coop_blocks > 0 && c->use_fused_grid) {
+            GridArgs GA;
+            GA.N = N; GA.S = S; GA.cutoff = c->params.interacting_cutoff; GA.struct_off = so; GA.bbox = bbox;
+            GA.geom = c->geom.as<StructGeom>(); GA.meta = meta; GA.cell_cnt = cell_cnt; GA.scan_state = state;
+            GA.sc = SC; GA.cell_of = c->cell_of.as<int>(); GA.rank = c->rank.as<int>(); GA.cell_start = c->cell_start.as<int>();
+            unsigned g = blocks < (unsigned)c->coop_blocks ? blocks : (unsigned)c->coop_blocks;
+            void* args[] = { &GA };
+            ARP_CUDA(c, cudaLaunchCooperativeKernel((void*)k_grid_fused, dim3(g), dim3(GRID_THREADS), args, 0, st));
+            c->launches++;
+        } else {
+            k_bbox<<<(unsigned)((N + BBOX_ATOMS_PER_VB - 1) / BBOX_ATOMS_PER_VB), GRID_THREADS, 0, st>>>(c->xyz.as<float>(), so, S, N, bbox);
+            ARP_LAUNCHED(c);
+            k_geom<<<1, GRID_THREADS, 0, st>>>(bbox, so, S, N, c->params.interacting_cutoff, c->geom.as<StructGeom>(), meta);
+            ARP_LAUNCHED(c);
+            k_cellid<<<blocks, GRID_THREADS, 0, st>>>(c->xyz.as<float>(), so, S, N, c->geom.as<StructGeom>(), cell_cnt,
+                                                      c->cell_of.as<int>(), c->rank.as<int>());
+            ARP_LAUNCHED(c);
+            ARP_TRY(arp_scan_exclusive(c, cell_cnt, c->cell_start.as<int>(), state, &meta->ticket_scan, &meta->n_cells, 1,
+                                       c->cell_bound + 1));
+            k_scatter<<<blocks, GRID_THREADS, 0, st>>>(N, SC);
+            ARP_LAUNCHED(c);
+        }
     }
     if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[1], st));
     if (N > 0) {

@@ -206,7 +206,7 @@ void arp_destroy(arp_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     DBuf* bufs[] = { &c->xyz, &c->feat, &c->res_id, &c->rad_class, &c->vdw, &c->cov, &c->res_prev, &c->res_next,
                      &c->res_flags, &c->bond_off, &c->bond_nbr, &c->h_off, &c->h_xyz, &c->xnbr, &c->struct_off,
-                     &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->out, &c->hits,
+                     &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->out, &c->hits, &c->work,
                      &c->radtab, &c->sort_tmp, &c->sort_out, &c->sort_zero, &c->sort_off, &c->within, &c->flush };
     for (DBuf* b : bufs) dbuf_free(*b);
     arp_planes_release(c);
@@ -316,6 +316,10 @@ static int pairs_out_reserve(arp_ctx* c, uint64_t records)
     ARP_TRY(dbuf_reserve(c, c->out, (size_t)records * sizeof(arp_pair)));
     c->out_cap = c->out.cap / sizeof(arp_pair);
     ARP_TRY(dbuf_reserve(c, c->hits, (size_t)c->out_cap * sizeof(uint2)));
+    if (c->work_cap < c->out_cap / 2 + 1024) {       /* first guess: one deferred predicate per two records */
+        ARP_TRY(dbuf_reserve(c, c->work, (size_t)(c->out_cap / 2 + 1024) * 16));
+        c->work_cap = c->work.cap / 16;
+    }
     return ARP_OK;
 }
 
@@ -346,14 +350,20 @@ int arp_pairs_run(arp_ctx* c, uint64_t* n_pairs)
     /* first guess of the stream length; an overflowing run still counts, then is repeated once */
     uint64_t want = c->out_cap ? c->out_cap : (uint64_t)c->N * 16 + 4096;
     ARP_TRY(pairs_out_reserve(c, want));
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    for (int attempt = 0; attempt < 3; ++attempt) {
         ARP_TRY(arp_pairs_enqueue(c, 1));
         ARP_CUDA(c, cudaStreamSynchronize(c->stream));
-        uint64_t n = c->h_meta->n_raw;          /* candidates >= records: both lists share the capacity */
-        if (n <= c->out_cap) break;
-        ARP_REQUIRE(c, attempt == 0, ARP_E_CAPACITY, "record stream overflowed twice");
-        ARP_TRY(pairs_out_reserve(c, n + n / 16 + 1024));
+        const uint64_t n = c->h_meta->n_raw;    /* candidates >= records: both lists share the capacity */
+        const uint64_t nw = c->h_meta->n_work;
+        if (n <= c->out_cap && nw <= c->work_cap) break;
+        ARP_REQUIRE(c, attempt < 2, ARP_E_CAPACITY, "record stream overflowed repeatedly");
+        if (n > c->out_cap) ARP_TRY(pairs_out_reserve(c, n + n / 16 + 1024));
+        else {                                  /* the work-item count is exact once the records fit */
+            ARP_TRY(dbuf_reserve(c, c->work, (size_t)(nw + nw / 16 + 1024) * 16));
+            c->work_cap = c->work.cap / 16;
+        }
     }
+    ARP_REQUIRE(c, c->h_meta->n_pairs < (1ull << 32), ARP_E_CAPACITY, "more than 2^32 records in one run");
     c->n_pairs = c->h_meta->n_pairs;
     c->pairs_valid = 1;
     fill_stats(c, 1);

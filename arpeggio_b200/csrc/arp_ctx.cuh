@@ -55,7 +55,10 @@ struct alignas(128) RunMeta {
     /* line 4 */
     unsigned int ticket_scan;         /* dynamic tile ids of the cell scan */
     unsigned int pad4[31];
-    /* line 5: end-of-kernel statistics */
+    /* line 5 */
+    unsigned long long n_work;        /* work-item cursor of k_classify (deferred predicates) */
+    unsigned int pad6[30];
+    /* line 6: end-of-kernel statistics */
     unsigned long long n_candidates;  /* distance tests performed */
     unsigned int n_cells_nonempty;
     unsigned int pad5[29];
@@ -108,6 +111,8 @@ struct arp_ctx {
     /* output stream */
     DBuf out;                     /* arp_pair records */
     DBuf hits;                    /* uint2 candidate list of the search kernel, same capacity as out */
+    DBuf work;                    /* uint4 deferred-predicate items of the classify kernel */
+    uint64_t work_cap = 0;
     uint64_t out_cap = 0;         /* records */
     uint64_t n_pairs = 0;
     int pairs_valid = 0;

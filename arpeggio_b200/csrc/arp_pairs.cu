@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
  *            the arithmetic of the next.                                                              */
 #define CLS_WARPS   8
 #define CLS_TILE    128
-#define CLS_TAB_K   16                      /* radius tables up to K x K = 256 entries are staged in shared memory */
+#define CLS_TAB_K   8                       /* radius tables up to K x K = 256 entries are staged in shared memory */
 #define CLS_ITEMS   (3 * CLS_TILE)          /* per pair at most: is_hbond scan + (is_weak_hbond scan | halogen) + xbond */
 #define CLS_SMEM_PER_WARP (2 * CLS_TILE * 16 + CLS_ITEMS * 4 + CLS_TILE * 8)
 #define CLS_SMEM    (CLS_WARPS * CLS_SMEM_PER_WARP)
@@ -661,6 +661,8 @@ struct ClassifyArgs {
     RunMeta*      meta;
     arp_pair*     out;
     unsigned long long cap;
+    uint4*        work;                     /* deferred predicates: (donor, acceptor | halogen, record index, kind) */
+    unsigned long long work_cap;
     double        r2;
     int           include_seq_adjacent;
     ArpSide       side;
@@ -691,7 +693,7 @@ __device__ __forceinline__ void bulk_store_wait_read_1()
 #define CLS_KIND_XBOND 5u
 
 #ifndef CLS_MINB
-#define CLS_MINB 3
+#define CLS_MINB 4
 #endif
 __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyArgs A, ArpRuleParams P)
 {
@@ -786,45 +788,69 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
         }
         if (nsurv == 0) continue;                                /* nothing staged: the buffer stays free */
         __syncwarp();
-        /* ---- stage 2: the deferred predicates, 32 items per round ---- */
-        for (unsigned w0 = 0; w0 < n_items; w0 += 32) {
-            const unsigned w = w0 + lane;
-            if (w < n_items) {
-                const uint32_t it = items[w];
-                const unsigned idx = it >> 4;
-                const uint32_t kind = it & 7u;
-                uint2 e = surv[idx];
-                if (it & 8u) { unsigned t = e.x; e.x = e.y; e.y = t; }   /* e.x = donor, e.y = acceptor / halogen */
-                const float4 pd = A.pos4[e.x], pa = A.pos4[e.y];
-                const uint32_t fa = A.att4[e.y].x;
-                const double vdw_a = A.side.vdw[fa & ARPK_RAD_MASK];
-                uint32_t bits = 0;
-                if (kind <= 3u) {
-                    const int got = rule_hbond_scan(A.side, P, __float_as_int(pd.w), pd.x, pd.y, pd.z, pa.x, pa.y, pa.z,
-                                                    vdw_a, (int)kind);
-                    if (got & ARP_HB_NEED_H) bits |= 1u << ARP_SIFT_HBOND;
-                    if (got & ARP_HB_NEED_W) bits |= 1u << ARP_SIFT_WEAK_HBOND;
-                } else if (kind == CLS_KIND_HAL) {
-                    if (rule_is_halogen_weak_hbond(A.side, P, __float_as_int(pd.w), __float_as_int(pa.w), pa.x, pa.y, pa.z,
-                                                   A.side.feat[__float_as_int(pa.w)], vdw_a)) bits = 1u << ARP_SIFT_WEAK_HBOND;
-                } else {
-                    uint32_t fault = 0;
-                    if (rule_is_xbond(A.side, P, __float_as_int(pd.w), pd.x, pd.y, pd.z, pa.x, pa.y, pa.z,
-                                      A.side.feat[__float_as_int(pd.w)], &fault)) bits = 1u << ARP_SIFT_XBOND;
-                    bits |= fault;
-                }
-                if (bits) atomicOr(reinterpret_cast<unsigned*>(&rec[idx].z), bits);
-            }
+        /* ---- stage 3: the tile leaves through the TMA engine; its work items go to the global work list ---- */
+        unsigned long long o = 0, ow = 0;
+        if (lane == 0) {
+            o = atomicAdd(&A.meta->n_pairs, (unsigned long long)nsurv);
+            bulk_store_tile(A.out + o, rec, nsurv * (uint32_t)sizeof(arp_pair));
+            if (n_items) ow = atomicAdd(&A.meta->n_work, (unsigned long long)n_items);
+        }
+        o = __shfl_sync(FULL, o, 0);
+        ow = __shfl_sync(FULL, ow, 0);
+        for (unsigned w = lane; w < n_items; w += 32) {
+            const uint32_t it = items[w];
+            const unsigned slot = it >> 4;
+            uint2 e = surv[slot];
+            if (it & 8u) { const unsigned t = e.x; e.x = e.y; e.y = t; }   /* e.x = donor, e.y = acceptor / halogen */
+            if (ow + w < A.work_cap) A.work[ow + w] = make_uint4(e.x, e.y, (uint32_t)(o + slot), it & 7u);
         }
         __syncwarp();
-        /* ---- stage 3: the tile leaves through the TMA engine ---- */
-        if (lane == 0) {
-            const unsigned long long o = atomicAdd(&A.meta->n_pairs, (unsigned long long)nsurv);
-            bulk_store_tile(A.out + o, rec, nsurv * (uint32_t)sizeof(arp_pair));
-        }
         buf ^= 1;
     }
     if (lane == 0) bulk_store_wait_read_all();                   /* shared memory must outlive the copies */
+}
+
+/* ---- k_hscan -----------------------------------------------------------------------------------
+ * The deferred predicates of k_classify, one thread per work item, dense: utils.is_hbond /
+ * is_weak_hbond (one pass over the donor's hydrogens serves both), is_halogen_weak_hbond, is_xbond
+ * (utils.py:73-179).  A true predicate ORs its SIFt bit into the finished record.                  */
+struct HscanArgs {
+    const float4* pos4;
+    const uint4*  att4;
+    const uint4*  work;
+    const RunMeta* meta;
+    unsigned long long work_cap;
+    arp_pair*     out;
+    ArpSide       side;
+};
+
+__global__ void __launch_bounds__(256) k_hscan(HscanArgs A, ArpRuleParams P)
+{
+    unsigned long long n = A.meta->n_work;
+    if (n > A.work_cap) n = A.work_cap;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < n;
+         w += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 it = A.work[w];
+        const float4 pd = A.pos4[it.x], pa = A.pos4[it.y];
+        const uint32_t fa = A.att4[it.y].x;
+        const double vdw_a = A.side.vdw[fa & ARPK_RAD_MASK];
+        const uint32_t kind = it.w;
+        uint32_t bits = 0;
+        if (kind <= 3u) {
+            const int got = rule_hbond_scan(A.side, P, __float_as_int(pd.w), pd.x, pd.y, pd.z, pa.x, pa.y, pa.z, vdw_a, (int)kind);
+            if (got & ARP_HB_NEED_H) bits |= 1u << ARP_SIFT_HBOND;
+            if (got & ARP_HB_NEED_W) bits |= 1u << ARP_SIFT_WEAK_HBOND;
+        } else if (kind == CLS_KIND_HAL) {
+            if (rule_is_halogen_weak_hbond(A.side, P, __float_as_int(pd.w), __float_as_int(pa.w), pa.x, pa.y, pa.z,
+                                           A.side.feat[__float_as_int(pa.w)], vdw_a)) bits = 1u << ARP_SIFT_WEAK_HBOND;
+        } else {
+            uint32_t fault = 0;
+            if (rule_is_xbond(A.side, P, __float_as_int(pd.w), pd.x, pd.y, pd.z, pa.x, pa.y, pa.z,
+                              A.side.feat[__float_as_int(pd.w)], &fault)) bits = 1u << ARP_SIFT_XBOND;
+            bits |= fault;
+        }
+        if (bits) atomicOr(&A.out[it.z].mask, bits);
+    }
 }
 
 /* K x K table of the float32 proximity thresholds (interactions.py:717-718, :760-768): NumPy narrows
@@ -954,6 +980,7 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         ClassifyArgs CA;
         CA.pos4 = SA.pos4; CA.att4 = c->att4.as<uint4>(); CA.raw = SA.raw; CA.meta = meta;
         CA.out = c->out.as<arp_pair>(); CA.cap = c->out_cap; CA.side = side;
+        CA.work = c->work.as<uint4>(); CA.work_cap = c->work_cap;
         CA.r2 = c->rp.r2; CA.include_seq_adjacent = c->rp.include_seq_adjacent;
         if (!c->cls_smem_set) {             /* per device: > 48 KB of dynamic shared memory is opt-in */
             ARP_CUDA(c, cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, CLS_SMEM));
@@ -964,6 +991,14 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         unsigned cgrid = (unsigned)(c->sm_count * CLS_MINB);
         if (blocks_needed < cgrid) cgrid = (unsigned)(blocks_needed ? blocks_needed : 1);
         k_classify<<<cgrid, CLS_WARPS * 32, CLS_SMEM, st>>>(CA, c->rp);
+        ARP_LAUNCHED(c);
+        HscanArgs HA;
+        HA.pos4 = SA.pos4; HA.att4 = CA.att4; HA.work = CA.work; HA.meta = meta; HA.work_cap = c->work_cap;
+        HA.out = CA.out; HA.side = side;
+        size_t hb = (size_t)((c->work_cap + 255) / 256);
+        unsigned hgrid = (unsigned)(c->sm_count * 8);
+        if (hb < hgrid) hgrid = (unsigned)(hb ? hb : 1);
+        k_hscan<<<hgrid, 256, 0, st>>>(HA, c->rp);
         ARP_LAUNCHED(c);
     } else if (with_events) {
         ARP_CUDA(c, cudaEventRecord(c->ev[2], st));

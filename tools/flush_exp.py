@@ -9,7 +9,7 @@ soa = synth.cloud_featured(atoms, seed=2)
 with ContactEngine(0, params.make_params()) as eng:
     eng.upload_atoms(soa)
     n = eng.run_pairs()
-    for flush in (True, False, True, False):
+    for flush in (True, False):
         eng.time_pairs(20, flush)
         ms = eng.time_pairs(200, flush)
         st = eng.stats()

@@ -388,14 +388,11 @@ __global__ void __launch_bounds__(GRID_THREADS) k_grid_fused(GridArgs G)
     const int vb_atoms = (N + GRID_THREADS - 1) / GRID_THREADS;
     for (int vb = blockIdx.x; vb * BBOX_ATOMS_PER_VB < N; vb += gridDim.x)
         dev_bbox(G.sc.xyz, G.struct_off, G.S, N, G.bbox, vb);
-    __threadfence();
     grid.sync();
     if (blockIdx.x == 0) dev_geom(G.bbox, G.struct_off, G.S, N, G.cutoff, G.geom, G.meta);
-    __threadfence();
     grid.sync();
     for (int vb = blockIdx.x; vb < vb_atoms; vb += gridDim.x)
         dev_cellid(G.sc.xyz, G.struct_off, G.S, N, G.geom, G.cell_cnt, G.cell_of, G.rank, vb * GRID_THREADS + threadIdx.x);
-    __threadfence();
     grid.sync();
     {
         const long long n = (long long)__ldcg(&G.meta->n_cells) + 1;
@@ -403,7 +400,6 @@ __global__ void __launch_bounds__(GRID_THREADS) k_grid_fused(GridArgs G)
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x)     /* ascending per block, blocks co-resident */
             dev_scan_tile(G.cell_cnt, G.cell_start, G.scan_state, n, tile);
     }
-    __threadfence();
     grid.sync();
     for (int vb = blockIdx.x; vb < vb_atoms; vb += gridDim.x)
         dev_scatter(G.sc, N, vb * GRID_THREADS + threadIdx.x);
@@ -925,7 +921,11 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
             GA.N = N; GA.S = S; GA.cutoff = c->params.interacting_cutoff; GA.struct_off = so; GA.bbox = bbox;
             GA.geom = c->geom.as<StructGeom>(); GA.meta = meta; GA.cell_cnt = cell_cnt; GA.scan_state = state;
             GA.sc = SC; GA.cell_of = c->cell_of.as<int>(); GA.rank = c->rank.as<int>(); GA.cell_start = c->cell_start.as<int>();
-            unsigned g = blocks < (unsigned)c->coop_blocks ? blocks : (unsigned)c->coop_blocks;
+            unsigned cap_blocks = (unsigned)c->coop_blocks;
+#ifdef GRID_FUSED_BLOCKS_PER_SM
+            if (cap_blocks > (unsigned)(c->sm_count * GRID_FUSED_BLOCKS_PER_SM)) cap_blocks = (unsigned)(c->sm_count * GRID_FUSED_BLOCKS_PER_SM);
+#endif
+            unsigned g = blocks < cap_blocks ? blocks : cap_blocks;
             void* args[] = { &GA };
             ARP_CUDA(c, cudaLaunchCooperativeKernel((void*)k_grid_fused, dim3(g), dim3(GRID_THREADS), args, 0, st));
             c->launches++;

@@ -161,6 +161,8 @@ class ArpStats(C.Structure):
         ('ms_grid', C.c_float),
         ('ms_search', C.c_float),
         ('ms_classify', C.c_float),
+        ('ms_hscan', C.c_float),
+        ('pad_', C.c_float),
     ]
 
 

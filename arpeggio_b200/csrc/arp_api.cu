@@ -180,7 +180,7 @@ int arp_create(int device, arp_ctx** out)
     c->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaEventCreate(&c->ev[k]);
+    for (int k = 0; k < 5 && e == cudaSuccess; ++k) e = cudaEventCreate(&c->ev[k]);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_meta, sizeof(RunMeta));
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) {
@@ -190,7 +190,9 @@ int arp_create(int device, arp_ctx** out)
         return ARP_E_CUDA;
     }
     memset(c->h_meta, 0, sizeof(RunMeta));
-    if (getenv("ARPEGGIO_NO_FUSED_GRID")) c->use_fused_grid = 0;     /* debugging / A-B knob: five-kernel grid build */
+    if (getenv("ARPEGGIO_NO_PDL")) c->use_pdl = 0;                   /* A-B knob: plain stream-ordered launches */
+    if (getenv("ARPEGGIO_NO_FUSED_GRID")) c->use_fused_grid = 0;
+    if (getenv("ARPEGGIO_NO_REG_GRID") && c->use_fused_grid > 1) c->use_fused_grid = 1;     /* debugging / A-B knob: five-kernel grid build */
     memset(&c->stats, 0, sizeof c->stats);
     arp_params_default(&c->params);
     derive_rule_params(c->params, &c->rp);
@@ -206,11 +208,11 @@ void arp_destroy(arp_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     DBuf* bufs[] = { &c->xyz, &c->feat, &c->res_id, &c->rad_class, &c->vdw, &c->cov, &c->res_prev, &c->res_next,
                      &c->res_flags, &c->bond_off, &c->bond_nbr, &c->h_off, &c->h_xyz, &c->xnbr, &c->struct_off,
-                     &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->out, &c->hits, &c->work,
+                     &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->hrng, &c->out, &c->hits, &c->work,
                      &c->radtab, &c->sort_tmp, &c->sort_out, &c->sort_zero, &c->sort_off, &c->within, &c->flush };
     for (DBuf* b : bufs) dbuf_free(*b);
     arp_planes_release(c);
-    for (int k = 0; k < 4; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    for (int k = 0; k < 5; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     if (c->h_meta) cudaFreeHost(c->h_meta);
     if (c->stream) cudaStreamDestroy(c->stream);
     (void)cudaGetLastError();
@@ -332,12 +334,18 @@ static void fill_stats(arp_ctx* c, int with_events)
     s.n_cells_nonempty = c->h_meta->n_cells_nonempty;
     s.input_bytes = c->input_bytes;
     s.output_bytes = s.n_pairs * sizeof(arp_pair);
-    if (with_events) {
+    if (with_events >= 2) {
         float a = 0.f, b = 0.f, d = 0.f;
         cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
         cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
         cudaEventElapsedTime(&d, c->ev[2], c->ev[3]);
-        s.ms_grid = a; s.ms_search = b; s.ms_classify = d; s.ms_total = a + b + d;
+        float h = 0.f;
+        cudaEventElapsedTime(&h, c->ev[4], c->ev[3]);
+        s.ms_grid = a; s.ms_search = b; s.ms_classify = d; s.ms_hscan = h; s.ms_total = a + b + d;
+    } else if (with_events == 1) {
+        float w = 0.f;
+        cudaEventElapsedTime(&w, c->ev[0], c->ev[3]);
+        s.ms_total = w; s.ms_grid = s.ms_search = s.ms_classify = s.ms_hscan = 0.f;
     }
 }
 
@@ -447,23 +455,35 @@ int arp_timing_iters(arp_ctx* c, int iters, int flush_l2, float* ms_per_iter)
     if (!c->pairs_valid) ARP_TRY(arp_pairs_run(c, nullptr));      /* sizes the record buffer */
     const size_t flush_bytes = (size_t)384 << 20;
     if (flush_l2) ARP_TRY(dbuf_reserve(c, c->flush, flush_bytes));
-    double tot = 0.0, grid = 0.0, search = 0.0, classify = 0.0;
+    /* the job as the API runs it: events around the whole job only, kernels free to overlap */
+    double tot = 0.0, grid = 0.0, search = 0.0, classify = 0.0, hscan = 0.0;
     for (int it = 0; it < iters; ++it) {
         if (flush_l2) ARP_CUDA(c, cudaMemsetAsync(c->flush.p, it & 0xff, flush_bytes, c->stream));
         ARP_TRY(arp_pairs_enqueue(c, 1));
         ARP_CUDA(c, cudaStreamSynchronize(c->stream));
         ARP_REQUIRE(c, c->h_meta->n_pairs == c->n_pairs, ARP_E_CUDA, "record count changed between iterations");
-        float a = 0.f, b = 0.f, d = 0.f, w = 0.f;
+        float w = 0.f;
+        ARP_CUDA(c, cudaEventElapsedTime(&w, c->ev[0], c->ev[3]));
+        tot += w;
+    }
+    /* the split: a bounded number of extra iterations with events between the kernels (no overlap) */
+    const int split_iters = iters < 32 ? iters : 32;
+    for (int it = 0; it < split_iters; ++it) {
+        if (flush_l2) ARP_CUDA(c, cudaMemsetAsync(c->flush.p, it & 0xff, flush_bytes, c->stream));
+        ARP_TRY(arp_pairs_enqueue(c, 2));
+        ARP_CUDA(c, cudaStreamSynchronize(c->stream));
+        float a = 0.f, b = 0.f, d = 0.f, h = 0.f;
         ARP_CUDA(c, cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
         ARP_CUDA(c, cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
         ARP_CUDA(c, cudaEventElapsedTime(&d, c->ev[2], c->ev[3]));
-        ARP_CUDA(c, cudaEventElapsedTime(&w, c->ev[0], c->ev[3]));
-        grid += a; search += b; classify += d; tot += w;
+        ARP_CUDA(c, cudaEventElapsedTime(&h, c->ev[4], c->ev[3]));
+        grid += a; search += b; classify += d; hscan += h;
     }
     fill_stats(c, 0);
-    c->stats.ms_grid = (float)(grid / iters);
-    c->stats.ms_search = (float)(search / iters);
-    c->stats.ms_classify = (float)(classify / iters);
+    c->stats.ms_grid = (float)(grid / split_iters);
+    c->stats.ms_search = (float)(search / split_iters);
+    c->stats.ms_classify = (float)(classify / split_iters);
+    c->stats.ms_hscan = (float)(hscan / split_iters);
     c->stats.ms_total = (float)(tot / iters);
     c->sorted_valid = 0;
     if (ms_per_iter) *ms_per_iter = (float)(tot / iters);

@@ -58,7 +58,13 @@ struct alignas(128) RunMeta {
     /* line 5 */
     unsigned long long n_work;        /* work-item cursor of k_classify (deferred predicates) */
     unsigned int pad6[30];
-    /* line 6: end-of-kernel statistics */
+    /* line 6 */
+    unsigned int ticket_classify;     /* dynamic tile tickets of k_classify (beyond the first, static tile) */
+    unsigned int pad7[31];
+    /* line 7 */
+    unsigned int ticket_hscan;        /* dynamic chunk tickets of k_hscan */
+    unsigned int pad8[31];
+    /* line 8: end-of-kernel statistics */
     unsigned long long n_candidates;  /* distance tests performed */
     unsigned int n_cells_nonempty;
     unsigned int pad5[29];
@@ -100,12 +106,15 @@ struct arp_ctx {
     DBuf zero;                    /* one memset per run: RunMeta | bbox | cell_cnt | scan_state */
     size_t zero_bytes = 0, off_bbox = 0, off_cnt = 0, off_state = 0;
     size_t cell_bound = 0;        /* upper bound of the number of cells, all structures */
-    DBuf geom, cell_start, cell_of, rank, pos4, att4;
+    DBuf geom, cell_start, cell_of, rank, pos4, att4, hrng;
     DBuf radtab;                  /* K x K float32 proximity thresholds */
     int radtab_valid = 0;
     int cls_smem_set = 0;
+    int hscan_blocks = 0;         /* co-resident blocks of k_hscan (probed once) */
     int coop_blocks = -1;         /* co-resident blocks of k_grid_fused (0: not available, -1: not probed) */
-    int use_fused_grid = 1;
+    int use_fused_grid = 2;       /* 0: five kernels, 1: cooperative kernel through global memory, 2: + register kernel when the atoms fit */
+    int reg_blocks = -1;          /* co-resident blocks of k_grid_reg (0: not available, -1: not probed) */
+    int use_pdl = 1;              /* pair kernels launched with programmatic stream serialization */
     RunMeta* h_meta = nullptr;    /* pinned */
 
     /* output stream */
@@ -128,7 +137,7 @@ struct arp_ctx {
     DBuf within;
 
     /* timing */
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   /* [4]: between k_classify and k_hscan */
     arp_stats stats;
     DBuf flush;                   /* L2 flush buffer for arp_timing_iters */
     unsigned long long launches = 0;   /* kernels launched by this context so far */
@@ -203,7 +212,10 @@ static inline int arp_bind(arp_ctx* c)
 
 /* entry points implemented across translation units */
 int  arp_pairs_prepare(arp_ctx* c);                       /* arp_pairs.cu: size the grid buffers after an upload */
-int  arp_pairs_enqueue(arp_ctx* c, int with_events);      /* arp_pairs.cu: memset + grid build + pair kernel */
+/* arp_pairs.cu: memset + grid build + pair kernels; with_events 0: none, 1: ev[0] / ev[3] around the whole
+   job, 2: also ev[1] / ev[2] between grid build, search and classify (the kernels then run back to back
+   without overlapping) */
+int  arp_pairs_enqueue(arp_ctx* c, int with_events);
 int  arp_pairs_sorted_build(arp_ctx* c);                  /* arp_pairs.cu: (i, j)-ascending copy of the stream */
 int  arp_flag_within_run(arp_ctx* c, double radius);      /* arp_pairs.cu */
 void arp_planes_release(arp_ctx* c);                      /* arp_planes.cu */

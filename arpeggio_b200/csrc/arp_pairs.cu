@@ -30,6 +30,28 @@ namespace cg = cooperative_groups;
 
 #define FULL 0xffffffffu
 
+/* ---- programmatic dependent launch (PDL) ------------------------------------------------------
+ * The pair kernels are launched with the programmatic-stream-serialization attribute: their blocks
+ * become resident while the previous kernel of the stream drains and park in pdl_wait() until that
+ * kernel has completed and its writes are visible.  pdl_trigger() in the primary lets the dependent
+ * grid be scheduled as soon as every primary block has passed it (or exited).                     */
+__device__ __forceinline__ void pdl_wait()    { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                            bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 /* ---- ordered-int encoding of float32 for atomic min/max ------------------------------ */
 __device__ __forceinline__ unsigned f2ord(float f)
 {
@@ -62,15 +84,49 @@ __device__ __forceinline__ int struct_of(const int* __restrict__ struct_off, int
 #define GRID_THREADS       256
 #define BBOX_ATOMS_PER_VB  (GRID_THREADS * 4)
 
+/* the threads' partial boxes (s = structure, -1: none; v = running maxima) go to bbox[s]: warp reduction when
+   every live lane sees the same structure, then one block reduction, at most 6 atomics per block */
+template <int WARPS>
+__device__ __forceinline__ void bbox_commit(int s, unsigned (&v)[6], unsigned* __restrict__ bbox)
+{
+    __shared__ unsigned s_v[WARPS][6];
+    __shared__ int s_s[WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int smax = __reduce_max_sync(FULL, s);
+    bool uniform = __all_sync(FULL, s == smax || s == -1);
+    if (uniform) {
+        for (int k = 0; k < 6; ++k) v[k] = __reduce_max_sync(FULL, v[k]);
+    } else if (s >= 0) {
+        for (int k = 0; k < 6; ++k) atomicMax(&bbox[6 * (size_t)s + k], v[k]);
+    }
+    __syncthreads();                  /* the previous use's readers are done with s_v / s_s */
+    if (lane == 0) {
+        s_s[warp] = uniform ? smax : -1;
+        for (int k = 0; k < 6; ++k) s_v[warp][k] = v[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int ws = lane < WARPS ? s_s[lane] : -1;
+        int bs = __reduce_max_sync(FULL, ws);
+        bool buni = __all_sync(FULL, ws == bs || ws == -1);
+        if (buni) {
+            if (bs >= 0 && lane < 6) {
+                unsigned m = 0;
+                for (int w = 0; w < WARPS; ++w) if (s_s[w] >= 0) m = max(m, s_v[w][lane]);
+                atomicMax(&bbox[6 * (size_t)bs + lane], m);
+            }
+        } else if (lane < WARPS && ws >= 0) {
+            for (int k = 0; k < 6; ++k) atomicMax(&bbox[6 * (size_t)ws + k], s_v[lane][k]);
+        }
+    }
+}
+
 /* ---- phase 1: bounding boxes --------------------------------------------------------------
  * bbox[s][0..2] = max over atoms of ~ord(coord)  (i.e. the minimum), [3..5] = max of ord(coord).
  * Zero-initialised, so a structure without atoms keeps all zeros.                        */
 __device__ __forceinline__ void dev_bbox(const float* __restrict__ xyz, const int* __restrict__ struct_off,
                                          int S, int N, unsigned* __restrict__ bbox, int vb)
 {
-    __shared__ unsigned s_v[8][6];
-    __shared__ int s_s[8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int base = vb * BBOX_ATOMS_PER_VB;
     int s = -1;                       /* structure of this thread's atoms */
     unsigned v[6] = {0, 0, 0, 0, 0, 0};
@@ -92,42 +148,61 @@ __device__ __forceinline__ void dev_bbox(const float* __restrict__ xyz, const in
             v[k] = max(v[k], ~o); v[3 + k] = max(v[3 + k], o);
         }
     }
-    /* warp: reduce when every live lane sees the same structure, else commit per lane */
-    int smax = __reduce_max_sync(FULL, s);
-    bool uniform = __all_sync(FULL, s == smax || s == -1);
-    if (uniform) {
-        for (int k = 0; k < 6; ++k) v[k] = __reduce_max_sync(FULL, v[k]);
-    } else if (s >= 0) {
-        for (int k = 0; k < 6; ++k) atomicMax(&bbox[6 * (size_t)s + k], v[k]);
-    }
-    __syncthreads();                  /* the previous virtual block's readers are done with s_v / s_s */
-    if (lane == 0) {
-        s_s[warp] = uniform ? smax : -1;
-        for (int k = 0; k < 6; ++k) s_v[warp][k] = v[k];
-    }
-    __syncthreads();
-    if (warp == 0) {
-        int ws = lane < 8 ? s_s[lane] : -1;
-        int bs = __reduce_max_sync(FULL, ws);
-        bool buni = __all_sync(FULL, ws == bs || ws == -1);
-        if (buni) {
-            if (bs >= 0 && lane < 6) {
-                unsigned m = 0;
-                for (int w = 0; w < 8; ++w) if (s_s[w] >= 0) m = max(m, s_v[w][lane]);
-                atomicMax(&bbox[6 * (size_t)bs + lane], m);
-            }
-        } else if (lane < 8 && ws >= 0) {
-            for (int k = 0; k < 6; ++k) atomicMax(&bbox[6 * (size_t)ws + k], s_v[lane][k]);
-        }
-    }
+    bbox_commit<GRID_THREADS / 32>(s, v, bbox);
 }
 
-/* ---- phase 2: per-structure grids, one block ---------------------------------------------- */
+/* ---- phase 2: per-structure grids -------------------------------------------------------------- */
+
+/* grid of one structure with n > 0 atoms from its bounding box (cell_base is filled in by the caller);
+   returns false when a coordinate is NaN / Inf (one cell, every test exact) */
+__device__ __forceinline__ bool geom_make(const unsigned* __restrict__ bb, int n, double cutoff, StructGeom& g)
+{
+    double mn[3], mx[3], amax = 0.0;
+    bool finite = true;
+    for (int k = 0; k < 3; ++k) {
+        mn[k] = (double)ord2f(~__ldcg(&bb[k]));
+        mx[k] = (double)ord2f(__ldcg(&bb[3 + k]));
+        if (!(fabs(mn[k]) <= 3.0e38) || !(fabs(mx[k]) <= 3.0e38)) finite = false;
+        amax = fmax(amax, fmax(fabs(mn[k]), fabs(mx[k])));
+    }
+    if (!finite) for (int k = 0; k < 3; ++k) { mn[k] = 0.0; mx[k] = 0.0; }
+    double r = cutoff;
+    double w = r > 1e-3 ? r * 1.0001 + 1e-4 : 1e-3;
+    long long d[3];
+    for (;;) {
+        for (int k = 0; k < 3; ++k) d[k] = (long long)floor((mx[k] - mn[k]) / w) + 1;
+        /* at most 4 n + 64 cells per structure (host sizes the tables on that bound) */
+        if ((double)d[0] * (double)d[1] * (double)d[2] <= 4.0 * (double)n + 64.0) break;
+        w *= 1.5;
+    }
+    g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2];
+    g.inv_w = 1.0 / w;
+    g.dx = (int)d[0]; g.dy = (int)d[1]; g.dz = (int)d[2];
+    g.ncell = g.dx * g.dy * g.dz;
+    /* float32 prefilter band around r^2: u bounds one ulp of any coordinate */
+    double u = amax * 1.1920928955078125e-07;
+    double r2 = r * r;
+    double band = 4.0 * r * u + 4.0 * u * u + r2 * 1.9073486328125e-06;
+    double lo2 = r2 - band, hi2 = r2 + band;
+    g.r2_lo = finite ? __double2float_rd(lo2) : -1.0f;
+    g.r2_hi = finite ? __double2float_ru(hi2) : 3.4e38f;
+    if (!(lo2 > 0.0)) g.r2_lo = -1.0f;
+    return finite;
+}
+
+/* k_classify uses one conservative lower edge of the band for all structures: the minimum */
+__device__ __forceinline__ unsigned r2_lo_key(float r2_lo)
+{
+    return r2_lo > 0.f ? 0x7f800000u - __float_as_uint(r2_lo) : 0x7f800000u;
+}
+
+/* all structures, one block of THREADS threads: grids + global cell numbering (block scan) */
+template <int THREADS>
 __device__ __forceinline__ void dev_geom(const unsigned* __restrict__ bbox, const int* __restrict__ struct_off,
                                          int S, int N, double cutoff, StructGeom* __restrict__ geom,
                                          RunMeta* __restrict__ meta)
 {
-    __shared__ int s_sum[GRID_THREADS];
+    __shared__ int s_sum[THREADS];
     __shared__ int s_carry;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
@@ -140,42 +215,9 @@ __device__ __forceinline__ void dev_geom(const unsigned* __restrict__ bbox, cons
             int lo = struct_off ? struct_off[s] : 0, hi = struct_off ? struct_off[s + 1] : N;
             int n = hi - lo;
             if (n > 0) {
-                double mn[3], mx[3], amax = 0.0;
-                bool finite = true;
-                for (int k = 0; k < 3; ++k) {
-                    mn[k] = (double)ord2f(~__ldcg(&bbox[6 * (size_t)s + k]));
-                    mx[k] = (double)ord2f(__ldcg(&bbox[6 * (size_t)s + 3 + k]));
-                    if (!(fabs(mn[k]) <= 3.0e38) || !(fabs(mx[k]) <= 3.0e38)) finite = false;
-                    amax = fmax(amax, fmax(fabs(mn[k]), fabs(mx[k])));
-                }
-                if (!finite) {           /* NaN / Inf coordinates: one cell, every test exact */
-                    for (int k = 0; k < 3; ++k) { mn[k] = 0.0; mx[k] = 0.0; }
-                    atomicOr(&meta->fault, 1u);
-                }
-                double r = cutoff;
-                double w = r > 1e-3 ? r * 1.0001 + 1e-4 : 1e-3;
-                long long d[3];
-                for (;;) {
-                    for (int k = 0; k < 3; ++k) d[k] = (long long)floor((mx[k] - mn[k]) / w) + 1;
-                    /* at most 4 n + 64 cells per structure (host sizes the tables on that bound) */
-                    if ((double)d[0] * (double)d[1] * (double)d[2] <= 4.0 * (double)n + 64.0) break;
-                    w *= 1.5;
-                }
-                g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2];
-                g.inv_w = 1.0 / w;
-                g.dx = (int)d[0]; g.dy = (int)d[1]; g.dz = (int)d[2];
-                ncell = g.dx * g.dy * g.dz;
-                g.ncell = ncell;
-                /* float32 prefilter band around r^2: u bounds one ulp of any coordinate */
-                double u = amax * 1.1920928955078125e-07;
-                double r2 = r * r;
-                double band = 4.0 * r * u + 4.0 * u * u + r2 * 1.9073486328125e-06;
-                double lo2 = r2 - band, hi2 = r2 + band;
-                g.r2_lo = finite ? __double2float_rd(lo2) : -1.0f;
-                g.r2_hi = finite ? __double2float_ru(hi2) : 3.4e38f;
-                if (!(lo2 > 0.0)) g.r2_lo = -1.0f;
-                /* k_classify uses one conservative lower edge for all structures: the minimum */
-                atomicMax(&meta->r2_lo_inv, g.r2_lo > 0.f ? 0x7f800000u - __float_as_uint(g.r2_lo) : 0x7f800000u);
+                if (!geom_make(bbox + 6 * (size_t)s, n, cutoff, g)) atomicOr(&meta->fault, 1u);
+                ncell = g.ncell;
+                atomicMax(&meta->r2_lo_inv, r2_lo_key(g.r2_lo));
             }
         }
         /* block exclusive scan of ncell */
@@ -226,23 +268,26 @@ __device__ __forceinline__ void dev_cellid(const float* __restrict__ xyz, const 
 
 /* ---- phase 4: single-pass exclusive scan (decoupled look-back) ------------------------------ */
 #define SCAN_THREADS GRID_THREADS
-#define SCAN_ITEMS   (ARP_SCAN_TILE / SCAN_THREADS)
 #define ST_AGG  (1ull << 62)
 #define ST_INCL (2ull << 62)
-#define ST_MASK (3ull << 62)
 
-/* one tile of ARP_SCAN_TILE items; every tile below `tile` has been started by a resident block */
+/* one tile of ARP_SCAN_TILE items by a block of THREADS threads; every tile below `tile` has been started by a
+   resident block.  state[t] = flag (bits 62..63) | value: first the tile's own total (AGG), then the inclusive
+   total of tiles 0..t (INCL); warp 0 looks back over 32 predecessors per step. */
+template <int THREADS>
 __device__ __forceinline__ void dev_scan_tile(const int* __restrict__ in, int* __restrict__ out,
                                               unsigned long long* state, long long n, int tile)
 {
-    __shared__ int s_warp[SCAN_THREADS / 32];
+    constexpr int ITEMS = ARP_SCAN_TILE / THREADS;
+    constexpr int WARPS = THREADS / 32;
+    __shared__ int s_warp[WARPS];
     __shared__ int s_prefix;
     const long long base = (long long)tile * ARP_SCAN_TILE;
-    const long long first = base + (long long)threadIdx.x * SCAN_ITEMS;
-    int v[SCAN_ITEMS];
+    const long long first = base + (long long)threadIdx.x * ITEMS;
+    int v[ITEMS];
     int sum = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
         v[k] = (first + k < n) ? __ldcg(&in[first + k]) : 0;
         sum += v[k];
     }
@@ -258,41 +303,46 @@ __device__ __forceinline__ void dev_scan_tile(const int* __restrict__ in, int* _
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        int w = lane < SCAN_THREADS / 32 ? s_warp[lane] : 0;
+        int w = lane < WARPS ? s_warp[lane] : 0;
 #pragma unroll
-        for (int off = 1; off < SCAN_THREADS / 32; off <<= 1) {
+        for (int off = 1; off < WARPS; off <<= 1) {
             int t = __shfl_up_sync(FULL, w, off);
             if (lane >= off) w += t;
         }
-        if (lane < SCAN_THREADS / 32) s_warp[lane] = w;       /* inclusive warp totals */
-    }
-    __syncthreads();
-    const int warp_excl = warp ? s_warp[warp - 1] : 0;
-    const int tile_total = s_warp[SCAN_THREADS / 32 - 1];
-    if (threadIdx.x == 0) {
+        if (lane < WARPS) s_warp[lane] = w;                   /* inclusive warp totals */
+        const int tile_total = __shfl_sync(FULL, w, WARPS - 1);
         volatile unsigned long long* st = state;
         int prefix = 0;
         if (tile == 0) {
-            st[0] = ST_INCL | (unsigned long long)(unsigned)tile_total;
+            if (lane == 0) st[0] = ST_INCL | (unsigned long long)(unsigned)tile_total;
         } else {
-            st[tile] = ST_AGG | (unsigned long long)(unsigned)tile_total;
-            int p = tile - 1;
+            if (lane == 0) st[tile] = ST_AGG | (unsigned long long)(unsigned)tile_total;
+            int p = tile - 1;                                  /* nearest predecessor of this window */
             for (;;) {
-                unsigned long long w = st[p];
-                unsigned long long f = w & ST_MASK;
-                if (f == 0) continue;                      /* predecessor not published yet */
-                prefix += (int)(unsigned)(w & 0xffffffffull);
-                if (f == ST_INCL) break;
-                --p;
+                const int idx = p - lane;
+                const unsigned long long w64 = idx >= 0 ? st[idx] : ST_INCL;   /* before tile 0: inclusive total 0 */
+                const unsigned f = (unsigned)(w64 >> 62);
+                const unsigned m_incl = __ballot_sync(FULL, f == 2u);
+                const unsigned m_none = __ballot_sync(FULL, f == 0u);
+                const int stop = m_incl ? __ffs(m_incl) - 1 : 31;                /* lanes 0..stop contribute */
+                const unsigned need = stop == 31 ? FULL : ((2u << stop) - 1u);
+                if (m_none & need) continue;                                     /* a predecessor has not published yet */
+                int c = lane <= stop ? (int)(unsigned)(w64 & 0xffffffffull) : 0;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(FULL, c, off);
+                prefix += c;
+                if (m_incl) break;
+                p -= 32;
             }
-            st[tile] = ST_INCL | (unsigned long long)(unsigned)(prefix + tile_total);
+            if (lane == 0) st[tile] = ST_INCL | (unsigned long long)(unsigned)(prefix + tile_total);
         }
-        s_prefix = prefix;
+        if (lane == 0) s_prefix = prefix;
     }
     __syncthreads();
+    const int warp_excl = warp ? s_warp[warp - 1] : 0;
     int run = s_prefix + warp_excl + incl - sum;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
         if (first + k < n) out[first + k] = run;
         run += v[k];
     }
@@ -302,8 +352,9 @@ __device__ __forceinline__ void dev_scan_tile(const int* __restrict__ in, int* _
 struct ScatterArgs {
     const float* xyz; const uint32_t* feat; const int32_t* res_id; const uint16_t* rad_class;
     const int32_t* res_prev; const int32_t* res_next; const uint8_t* res_flags; const int32_t* bond_off;
+    const int32_t* h_off;            /* null: no hydrogens uploaded */
     const int* cell_of; const int* rank; const int* cell_start;
-    float4* pos4; uint4* att4;
+    float4* pos4; uint4* att4; int2* hrng;
 };
 
 __device__ __forceinline__ void dev_scatter(const ScatterArgs& A, int N, int i)
@@ -315,6 +366,7 @@ __device__ __forceinline__ void dev_scatter(const ScatterArgs& A, int N, int i)
                                      A.bond_off && A.bond_off[i + 1] > A.bond_off[i]);
     A.pos4[dst] = make_float4(A.xyz[3 * (size_t)i], A.xyz[3 * (size_t)i + 1], A.xyz[3 * (size_t)i + 2], __int_as_float(i));
     A.att4[dst] = make_uint4(w, (uint32_t)r, (uint32_t)A.res_prev[r], (uint32_t)A.res_next[r]);
+    A.hrng[dst] = A.h_off ? make_int2(A.h_off[i], A.h_off[i + 1]) : make_int2(0, 0);
 }
 
 /* ---- the phases as separate kernels ------------------------------------------------------------- */
@@ -328,7 +380,7 @@ __global__ void __launch_bounds__(GRID_THREADS) k_geom(const unsigned* __restric
                                                        int S, int N, double cutoff, StructGeom* __restrict__ geom,
                                                        RunMeta* __restrict__ meta)
 {
-    dev_geom(bbox, struct_off, S, N, cutoff, geom, meta);
+    dev_geom<GRID_THREADS>(bbox, struct_off, S, N, cutoff, geom, meta);
 }
 
 __global__ void __launch_bounds__(GRID_THREADS) k_cellid(const float* __restrict__ xyz, const int* __restrict__ struct_off,
@@ -349,7 +401,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const int* __restrict__ i
     const int tile = s_tile;
     const long long n = (long long)(n_dev ? *n_dev : 0u) + n_add;
     if ((long long)tile * ARP_SCAN_TILE >= n) return;
-    dev_scan_tile(in, out, state, n, tile);
+    dev_scan_tile<SCAN_THREADS>(in, out, state, n, tile);
 }
 
 int arp_scan_exclusive(arp_ctx* c, const int* in, int* out, unsigned long long* state, unsigned int* ticket,
@@ -389,7 +441,7 @@ __global__ void __launch_bounds__(GRID_THREADS) k_grid_fused(GridArgs G)
     for (int vb = blockIdx.x; vb * BBOX_ATOMS_PER_VB < N; vb += gridDim.x)
         dev_bbox(G.sc.xyz, G.struct_off, G.S, N, G.bbox, vb);
     grid.sync();
-    if (blockIdx.x == 0) dev_geom(G.bbox, G.struct_off, G.S, N, G.cutoff, G.geom, G.meta);
+    if (blockIdx.x == 0) dev_geom<GRID_THREADS>(G.bbox, G.struct_off, G.S, N, G.cutoff, G.geom, G.meta);
     grid.sync();
     for (int vb = blockIdx.x; vb < vb_atoms; vb += gridDim.x)
         dev_cellid(G.sc.xyz, G.struct_off, G.S, N, G.geom, G.cell_cnt, G.cell_of, G.rank, vb * GRID_THREADS + threadIdx.x);
@@ -398,11 +450,116 @@ __global__ void __launch_bounds__(GRID_THREADS) k_grid_fused(GridArgs G)
         const long long n = (long long)__ldcg(&G.meta->n_cells) + 1;
         const int tiles = (int)((n + ARP_SCAN_TILE - 1) / ARP_SCAN_TILE);
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x)     /* ascending per block, blocks co-resident */
-            dev_scan_tile(G.cell_cnt, G.cell_start, G.scan_state, n, tile);
+            dev_scan_tile<GRID_THREADS>(G.cell_cnt, G.cell_start, G.scan_state, n, tile);
     }
     grid.sync();
     for (int vb = blockIdx.x; vb < vb_atoms; vb += gridDim.x)
         dev_scatter(G.sc, N, vb * GRID_THREADS + threadIdx.x);
+}
+
+/* ---- the phases as one cooperative kernel, atoms held in registers ------------------------------
+ * For inputs of up to REG_APT atoms per thread of a one-block-per-SM grid (about 3 * 10^5 atoms on 148 SMs):
+ * every thread loads its atoms once, keeps coordinates, cell, rank and the packed attribute record in
+ * registers across the phases, and the attribute loads of the scatter are in flight while the grid
+ * synchronises.  One structure: every block derives the grid from the bounding box itself (one grid barrier
+ * less).  Three grid barriers in all; the look-back of the cell scan is warp-parallel.              */
+#define REG_THREADS 1024
+#define REG_APT     2
+
+template <int APT>
+__global__ void __launch_bounds__(REG_THREADS, 1) k_grid_reg(GridArgs G)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ StructGeom s_geom;
+    const int N = G.N, S = G.S;
+    const int T = gridDim.x * REG_THREADS;
+    const int gtid = blockIdx.x * REG_THREADS + threadIdx.x;
+    float x[APT], y[APT], z[APT];
+    int st[APT];
+    /* ---- phase 1: load, bounding boxes (block-contiguous atoms per k: one reduction each) ---- */
+#pragma unroll
+    for (int k = 0; k < APT; ++k) {
+        const int i = k * T + gtid;
+        unsigned v[6] = {0, 0, 0, 0, 0, 0};
+        st[k] = -1;
+        x[k] = y[k] = z[k] = 0.f;
+        if (i < N) {
+            x[k] = G.sc.xyz[3 * (size_t)i]; y[k] = G.sc.xyz[3 * (size_t)i + 1]; z[k] = G.sc.xyz[3 * (size_t)i + 2];
+            st[k] = struct_of(G.struct_off, S, i);
+            const unsigned ox = f2ord(x[k]), oy = f2ord(y[k]), oz = f2ord(z[k]);
+            v[0] = ~ox; v[1] = ~oy; v[2] = ~oz; v[3] = ox; v[4] = oy; v[5] = oz;
+        }
+        if (k * T + blockIdx.x * REG_THREADS < N) bbox_commit<REG_THREADS / 32>(st[k], v, G.bbox);   /* block-uniform */
+    }
+    /* attribute loads of the scatter: issued now, consumed after the last barrier */
+    uint32_t aw[APT];
+    int ar[APT], ap[APT], an[APT];
+    int2 ah[APT];
+#pragma unroll
+    for (int k = 0; k < APT; ++k) {
+        const int i = k * T + gtid;
+        aw[k] = 0; ar[k] = ap[k] = an[k] = 0; ah[k] = make_int2(0, 0);
+        if (i < N) {
+            const int r = G.sc.res_id[i];
+            aw[k] = arp_pack_word(G.sc.feat[i], G.sc.res_flags[r], G.sc.rad_class[i],
+                                  G.sc.bond_off && G.sc.bond_off[i + 1] > G.sc.bond_off[i]);
+            ar[k] = r; ap[k] = G.sc.res_prev[r]; an[k] = G.sc.res_next[r];
+            if (G.sc.h_off) ah[k] = make_int2(G.sc.h_off[i], G.sc.h_off[i + 1]);
+        }
+    }
+    grid.sync();
+    /* ---- phase 2: grids ---- */
+    if (S == 1) {
+        if (threadIdx.x == 0) {
+            StructGeom g;
+            memset(&g, 0, sizeof g);
+            const bool finite = geom_make(G.bbox, N, G.cutoff, g);
+            s_geom = g;
+            if (blockIdx.x == 0) {
+                G.geom[0] = g;
+                G.meta->n_cells = (unsigned)g.ncell;
+                G.meta->r2_lo_inv = r2_lo_key(g.r2_lo);
+                if (!finite) atomicOr(&G.meta->fault, 1u);
+            }
+        }
+        __syncthreads();
+    } else {
+        if (blockIdx.x == 0) dev_geom<REG_THREADS>(G.bbox, G.struct_off, S, N, G.cutoff, G.geom, G.meta);
+        grid.sync();
+    }
+    /* ---- phase 3: cell of every atom, rank inside the cell ---- */
+    int cell[APT], rank[APT];
+#pragma unroll
+    for (int k = 0; k < APT; ++k) {
+        cell[k] = 0; rank[k] = 0;
+        if (st[k] >= 0) {
+            const StructGeom* g = S == 1 ? &s_geom : G.geom + st[k];
+            const int cx = cell_coord((double)x[k], g->ox, g->inv_w, g->dx);
+            const int cy = cell_coord((double)y[k], g->oy, g->inv_w, g->dy);
+            const int cz = cell_coord((double)z[k], g->oz, g->inv_w, g->dz);
+            cell[k] = g->cell_base + (cz * g->dy + cy) * g->dx + cx;
+            rank[k] = atomicAdd(&G.cell_cnt[cell[k]], 1);
+        }
+    }
+    grid.sync();
+    /* ---- phase 4: scan of the cell counts ---- */
+    {
+        const long long n = (long long)(S == 1 ? (unsigned)s_geom.ncell : __ldcg(&G.meta->n_cells)) + 1;
+        const int tiles = (int)((n + ARP_SCAN_TILE - 1) / ARP_SCAN_TILE);
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x)     /* ascending per block, blocks co-resident */
+            dev_scan_tile<REG_THREADS>(G.cell_cnt, G.cell_start, G.scan_state, n, tile);
+    }
+    grid.sync();
+    /* ---- phase 5: atoms into cell order ---- */
+#pragma unroll
+    for (int k = 0; k < APT; ++k) {
+        if (st[k] < 0) continue;
+        const int i = k * T + gtid;
+        const int dst = __ldcg(&G.cell_start[cell[k]]) + rank[k];
+        G.sc.pos4[dst] = make_float4(x[k], y[k], z[k], __int_as_float(i));
+        G.sc.att4[dst] = make_uint4(aw[k], (uint32_t)ar[k], (uint32_t)ap[k], (uint32_t)an[k]);
+        G.sc.hrng[dst] = ah[k];
+    }
 }
 
 /* ---- k_search ---------------------------------------------------------------------------------
@@ -509,6 +666,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
     unsigned nonempty = 0;
     const unsigned lt_mask = (1u << lane) - 1u;
 
+    pdl_wait();                                 /* the grid build has completed */
+    pdl_trigger();
     const int n_cells = (int)A.meta->n_cells;
     int s = 0;                                  /* warp-uniform: structure of the ticket's first cell */
     int s_end = A.geom[0].cell_base + A.geom[0].ncell;
@@ -644,7 +803,9 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
  *            TMA engine) behind one cursor atomic, double buffered so that the store of one tile overlaps
  *            the arithmetic of the next.                                                              */
 #define CLS_WARPS   8
-#define CLS_TILE    128
+#ifndef CLS_TILE
+#define CLS_TILE    64
+#endif
 #define CLS_TAB_K   8                       /* radius tables up to K x K = 256 entries are staged in shared memory */
 #define CLS_ITEMS   (3 * CLS_TILE)          /* per pair at most: is_hbond scan + (is_weak_hbond scan | halogen) + xbond */
 #define CLS_SMEM_PER_WARP (2 * CLS_TILE * 16 + CLS_ITEMS * 4 + CLS_TILE * 8)
@@ -682,12 +843,15 @@ __device__ __forceinline__ void bulk_store_wait_read_1()
     asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
 
-/* item = record index in the tile << 4 | direction << 3 | kind (bits 0..2):
+/* item = radius class of the acceptor / halogen << 16 | record index in the tile << 4 | direction << 3 | kind (bits 0..2):
    kind 1..3 = ARP_HB_NEED_* of a hydrogen scan, 4 = halogen weak hbond, 5 = xbond;
    direction 0: donor = bgn, 1: donor = end */
 #define CLS_KIND_HAL   4u
 #define CLS_KIND_XBOND 5u
 
+#ifndef CLS_DYNAMIC
+#define CLS_DYNAMIC 0
+#endif
 #ifndef CLS_MINB
 #define CLS_MINB 4
 #endif
@@ -710,6 +874,8 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
         A.side.radtab = s_radtab;
         A.side.vdw = s_vdw;
     }
+    pdl_wait();                                                  /* k_search has completed */
+    pdl_trigger();
     unsigned long long n = A.meta->n_raw;
     if (n > A.cap) n = A.cap;                                    /* overflowing run: host repeats it with a larger buffer */
     const float r2_lo = A.meta->r2_lo_inv == 0x7f800000u ? -1.0f : __uint_as_float(0x7f800000u - A.meta->r2_lo_inv);
@@ -717,7 +883,8 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
     const unsigned long long warp_id = (unsigned long long)blockIdx.x * CLS_WARPS + warp;
     const unsigned long long n_warps = (unsigned long long)gridDim.x * CLS_WARPS;
     int buf = 0;
-    for (unsigned long long tile = warp_id; tile < n_tiles; tile += n_warps) {
+    /* tiles: the first one is static (tile = global warp id), the rest are handed out by a counter */
+    for (unsigned long long tile = warp_id; tile < n_tiles; ) {
         const unsigned long long base = tile * CLS_TILE;
         const unsigned cnt = (unsigned)min((unsigned long long)CLS_TILE, n - base);
         int4* rec = rec0 + buf * CLS_TILE;
@@ -763,25 +930,36 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
             }
             /* append the work items of this round, one kind of slot at a time (ballot compaction) */
             if (__any_sync(FULL, work != 0)) {
+                const uint32_t it0 = ((ae.x & ARPK_RAD_MASK) << 16) | (slot << 4);         /* donor = bgn, acceptor = end */
+                const uint32_t it1 = ((ab.x & ARPK_RAD_MASK) << 16) | (slot << 4) | 8u;    /* donor = end, acceptor = bgn */
                 unsigned m = __ballot_sync(FULL, (work & ARP_WORK_SCAN0) != 0);
-                if (work & ARP_WORK_SCAN0) items[n_items + __popc(m & lt_mask)] = (slot << 4) | (work & 3u);
+                if (work & ARP_WORK_SCAN0) items[n_items + __popc(m & lt_mask)] = it0 | (work & 3u);
                 n_items += __popc(m);
                 m = __ballot_sync(FULL, (work & ARP_WORK_SCAN1) != 0);
-                if (work & ARP_WORK_SCAN1) items[n_items + __popc(m & lt_mask)] = (slot << 4) | 8u | ((work >> 2) & 3u);
+                if (work & ARP_WORK_SCAN1) items[n_items + __popc(m & lt_mask)] = it1 | ((work >> 2) & 3u);
                 n_items += __popc(m);
                 const uint32_t rare = work & (ARP_WORK_HAL0 | ARP_WORK_HAL1 | ARP_WORK_XB0 | ARP_WORK_XB1);
                 if (__any_sync(FULL, rare != 0)) {
                     m = __ballot_sync(FULL, (rare & (ARP_WORK_HAL0 | ARP_WORK_HAL1)) != 0);
                     if (rare & (ARP_WORK_HAL0 | ARP_WORK_HAL1))
-                        items[n_items + __popc(m & lt_mask)] = (slot << 4) | ((rare & ARP_WORK_HAL1) ? 8u : 0u) | CLS_KIND_HAL;
+                        items[n_items + __popc(m & lt_mask)] = ((rare & ARP_WORK_HAL1) ? it1 : it0) | CLS_KIND_HAL;
                     n_items += __popc(m);
                     m = __ballot_sync(FULL, (rare & (ARP_WORK_XB0 | ARP_WORK_XB1)) != 0);
                     if (rare & (ARP_WORK_XB0 | ARP_WORK_XB1))
-                        items[n_items + __popc(m & lt_mask)] = (slot << 4) | ((rare & ARP_WORK_XB1) ? 8u : 0u) | CLS_KIND_XBOND;
+                        items[n_items + __popc(m & lt_mask)] = ((rare & ARP_WORK_XB1) ? it1 : it0) | CLS_KIND_XBOND;
                     n_items += __popc(m);
                 }
             }
         }
+#if CLS_DYNAMIC
+        {                                                        /* next tile (taken early: the atomic's latency hides behind stage 3) */
+            unsigned t = 0;
+            if (lane == 0) t = atomicAdd(&A.meta->ticket_classify, 1u);
+            tile = n_warps + __shfl_sync(FULL, t, 0);
+        }
+#else
+        tile += n_warps;
+#endif
         if (nsurv == 0) continue;                                /* nothing staged: the buffer stays free */
         __syncwarp();
         /* ---- stage 3: the tile leaves through the TMA engine; its work items go to the global work list ---- */
@@ -795,10 +973,10 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
         ow = __shfl_sync(FULL, ow, 0);
         for (unsigned w = lane; w < n_items; w += 32) {
             const uint32_t it = items[w];
-            const unsigned slot = it >> 4;
+            const unsigned slot = (it >> 4) & 0xfffu;
             uint2 e = surv[slot];
             if (it & 8u) { const unsigned t = e.x; e.x = e.y; e.y = t; }   /* e.x = donor, e.y = acceptor / halogen */
-            if (ow + w < A.work_cap) A.work[ow + w] = make_uint4(e.x, e.y, (uint32_t)(o + slot), it & 7u);
+            if (ow + w < A.work_cap) A.work[ow + w] = make_uint4(e.x, e.y, (uint32_t)(o + slot), (it & 7u) | ((it >> 16) << 8));
         }
         __syncwarp();
         buf ^= 1;
@@ -812,28 +990,56 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
  * (utils.py:73-179).  A true predicate ORs its SIFt bit into the finished record.                  */
 struct HscanArgs {
     const float4* pos4;
-    const uint4*  att4;
+    const int2*   hrng;                     /* hydrogen range of every atom, cell order */
     const uint4*  work;
-    const RunMeta* meta;
+    RunMeta*      meta;
     unsigned long long work_cap;
     arp_pair*     out;
     ArpSide       side;
 };
 
-__global__ void __launch_bounds__(256) k_hscan(HscanArgs A, ArpRuleParams P)
+#ifndef HSCAN_MINB
+#define HSCAN_MINB 4
+#endif
+#define HSCAN_WARPS 8
+#ifndef HSCAN_DYNAMIC
+#define HSCAN_DYNAMIC 0
+#endif
+__global__ void __launch_bounds__(HSCAN_WARPS * 32, HSCAN_MINB) k_hscan(HscanArgs A, ArpRuleParams P)
 {
+    __shared__ double s_vdw[CLS_TAB_K];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (A.side.K <= CLS_TAB_K) {                                 /* uploaded table, not written by the run */
+        if (threadIdx.x < A.side.K) s_vdw[threadIdx.x] = A.side.vdw[threadIdx.x];
+        __syncthreads();
+        A.side.vdw = s_vdw;
+    }
+    pdl_wait();                                                  /* k_classify has completed */
     unsigned long long n = A.meta->n_work;
     if (n > A.work_cap) n = A.work_cap;
-    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < n;
-         w += (unsigned long long)gridDim.x * blockDim.x) {
+    /* chunks of 32 items per warp: the first one static (global warp id), the rest from a counter */
+    const unsigned long long n_chunks = (n + 31) / 32;
+    const unsigned long long n_warps = (unsigned long long)gridDim.x * HSCAN_WARPS;
+    for (unsigned long long chunk = (unsigned long long)blockIdx.x * HSCAN_WARPS + warp; chunk < n_chunks; ) {
+        const unsigned long long w = chunk * 32 + lane;
+#if HSCAN_DYNAMIC
+        {
+            unsigned t = 0;
+            if (lane == 0) t = atomicAdd(&A.meta->ticket_hscan, 1u);
+            chunk = n_warps + __shfl_sync(FULL, t, 0);
+        }
+#else
+        chunk += n_warps;
+#endif
+        if (w >= n) continue;
         const uint4 it = A.work[w];
         const float4 pd = A.pos4[it.x], pa = A.pos4[it.y];
-        const uint32_t fa = A.att4[it.y].x;
-        const double vdw_a = A.side.vdw[fa & ARPK_RAD_MASK];
-        const uint32_t kind = it.w;
+        const uint32_t kind = it.w & 7u;
+        const double vdw_a = A.side.vdw[it.w >> 8];
         uint32_t bits = 0;
         if (kind <= 3u) {
-            const int got = rule_hbond_scan(A.side, P, __float_as_int(pd.w), pd.x, pd.y, pd.z, pa.x, pa.y, pa.z, vdw_a, (int)kind);
+            const int2 hr = A.hrng[it.x];
+            const int got = rule_hbond_scan_range(A.side, P, hr.x, hr.y, pd.x, pd.y, pd.z, pa.x, pa.y, pa.z, vdw_a, (int)kind);
             if (got & ARP_HB_NEED_H) bits |= 1u << ARP_SIFT_HBOND;
             if (got & ARP_HB_NEED_W) bits |= 1u << ARP_SIFT_WEAK_HBOND;
         } else if (kind == CLS_KIND_HAL) {
@@ -882,6 +1088,7 @@ int arp_pairs_prepare(arp_ctx* c)
     ARP_TRY(dbuf_reserve(c, c->rank, sizeof(int) * N));
     ARP_TRY(dbuf_reserve(c, c->pos4, sizeof(float4) * N));
     ARP_TRY(dbuf_reserve(c, c->att4, sizeof(uint4) * N));
+    ARP_TRY(dbuf_reserve(c, c->hrng, sizeof(int2) * N));
     return ARP_OK;
 }
 
@@ -896,6 +1103,16 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
     const int* so = S > 1 ? c->struct_off.as<int>() : nullptr;
     cudaStream_t st = c->stream;
 
+    /* K x K float32 proximity thresholds: once per (atoms, params); ahead of the run so that the pair
+       kernels follow each other directly (programmatic dependent launch) */
+    if (N > 0 && !c->radtab_valid) {
+        ARP_TRY(dbuf_reserve(c, c->radtab, sizeof(float4) * (size_t)c->K * c->K));
+        k_radtab<<<(unsigned)((c->K * c->K + 127) / 128), 128, 0, st>>>(c->K, c->vdw.as<double>(), c->cov.as<double>(),
+                                                                       c->params.vdw_comp, c->radtab.as<float4>());
+        ARP_LAUNCHED(c);
+        c->radtab_valid = 1;
+    }
+    const bool split_events = with_events >= 2;       /* events between the kernels keep them from overlapping */
     if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[0], st));
     ARP_CUDA(c, cudaMemsetAsync(z, 0, c->zero_bytes, st));
     if (N > 0) {
@@ -904,6 +1121,8 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         SC.rad_class = c->rad_class.as<uint16_t>(); SC.res_prev = c->res_prev.as<int32_t>();
         SC.res_next = c->res_next.as<int32_t>(); SC.res_flags = c->res_flags.as<uint8_t>();
         SC.bond_off = c->has_bonds ? c->bond_off.as<int32_t>() : nullptr;
+        SC.h_off = c->has_h ? c->h_off.as<int32_t>() : nullptr;
+        SC.hrng = c->hrng.as<int2>();
         SC.cell_of = c->cell_of.as<int>(); SC.rank = c->rank.as<int>(); SC.cell_start = c->cell_start.as<int>();
         SC.pos4 = c->pos4.as<float4>(); SC.att4 = c->att4.as<uint4>();
         unsigned blocks = (unsigned)((N + GRID_THREADS - 1) / GRID_THREADS);
@@ -917,10 +1136,26 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
             (void)cudaGetLastError();
         }
         if (c->coop_blocks > 0 && c->use_fused_grid) {
+            if (c->reg_blocks < 0) {        /* one 1024-thread block per SM, co-resident? */
+                int per_sm = 0;
+                c->reg_blocks = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_grid_reg<REG_APT>, REG_THREADS, 0) == cudaSuccess && per_sm >= 1)
+                    c->reg_blocks = c->sm_count;
+                (void)cudaGetLastError();
+            }
             GridArgs GA;
             GA.N = N; GA.S = S; GA.cutoff = c->params.interacting_cutoff; GA.struct_off = so; GA.bbox = bbox;
             GA.geom = c->geom.as<StructGeom>(); GA.meta = meta; GA.cell_cnt = cell_cnt; GA.scan_state = state;
             GA.sc = SC; GA.cell_of = c->cell_of.as<int>(); GA.rank = c->rank.as<int>(); GA.cell_start = c->cell_start.as<int>();
+            const long long reg_threads = (long long)c->reg_blocks * REG_THREADS;
+            if (c->use_fused_grid >= 2 && reg_threads > 0 && (long long)N <= reg_threads * REG_APT) {
+                const int apt = (long long)N <= reg_threads ? 1 : 2;
+                unsigned g = (unsigned)(((long long)N + (long long)apt * REG_THREADS - 1) / ((long long)apt * REG_THREADS));
+                void* args[] = { &GA };
+                ARP_CUDA(c, cudaLaunchCooperativeKernel(apt == 1 ? (void*)k_grid_reg<1> : (void*)k_grid_reg<2>, dim3(g),
+                                                        dim3(REG_THREADS), args, 0, st));
+                c->launches++;
+            } else {
             unsigned cap_blocks = (unsigned)c->coop_blocks;
 #ifdef GRID_FUSED_BLOCKS_PER_SM
             if (cap_blocks > (unsigned)(c->sm_count * GRID_FUSED_BLOCKS_PER_SM)) cap_blocks = (unsigned)(c->sm_count * GRID_FUSED_BLOCKS_PER_SM);
@@ -929,6 +1164,7 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
             void* args[] = { &GA };
             ARP_CUDA(c, cudaLaunchCooperativeKernel((void*)k_grid_fused, dim3(g), dim3(GRID_THREADS), args, 0, st));
             c->launches++;
+            }
         } else {
             k_bbox<<<(unsigned)((N + BBOX_ATOMS_PER_VB - 1) / BBOX_ATOMS_PER_VB), GRID_THREADS, 0, st>>>(c->xyz.as<float>(), so, S, N, bbox);
             ARP_LAUNCHED(c);
@@ -943,24 +1179,14 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
             ARP_LAUNCHED(c);
         }
     }
-    if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[1], st));
+    if (split_events) ARP_CUDA(c, cudaEventRecord(c->ev[1], st));
     if (N > 0) {
         ArpSide side;
         memset(&side, 0, sizeof side);
         side.vdw = c->vdw.as<double>(); side.cov = c->cov.as<double>();
         side.K = c->K;
         side.feat = c->feat.as<uint32_t>();
-        side.radtab = nullptr;
-        {
-            if (!c->radtab_valid) {
-                ARP_TRY(dbuf_reserve(c, c->radtab, sizeof(float4) * (size_t)c->K * c->K));
-                k_radtab<<<(unsigned)((c->K * c->K + 127) / 128), 128, 0, st>>>(c->K, c->vdw.as<double>(), c->cov.as<double>(),
-                                                                               c->params.vdw_comp, c->radtab.as<float4>());
-                ARP_LAUNCHED(c);
-                c->radtab_valid = 1;
-            }
-            side.radtab = c->radtab.as<float4>();
-        }
+        side.radtab = c->radtab.as<float4>();
         side.bond_off = c->has_bonds ? c->bond_off.as<int32_t>() : nullptr;
         side.bond_nbr = c->has_bonds ? c->bond_nbr.as<int32_t>() : nullptr;
         side.h_off = c->has_h ? c->h_off.as<int32_t>() : nullptr;
@@ -973,9 +1199,10 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         unsigned grid = (unsigned)(c->sm_count * SEARCH_GRID_MULT);
         size_t want = ((size_t)N / 24) / SEARCH_WARPS + 1;     /* about one warp per few cells on small inputs */
         if (want < grid) grid = (unsigned)want;
-        k_search<<<grid, SEARCH_WARPS * 32, 0, st>>>(SA);
-        ARP_LAUNCHED(c);
-        if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[2], st));
+        const bool pdl = c->use_pdl != 0;
+        ARP_CUDA(c, launch_k(k_search, grid, SEARCH_WARPS * 32, 0, st, pdl, SA));
+        c->launches++;
+        if (split_events) ARP_CUDA(c, cudaEventRecord(c->ev[2], st));
 
         ClassifyArgs CA;
         CA.pos4 = SA.pos4; CA.att4 = c->att4.as<uint4>(); CA.raw = SA.raw; CA.meta = meta;
@@ -990,18 +1217,27 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         size_t blocks_needed = (tiles + CLS_WARPS - 1) / CLS_WARPS;
         unsigned cgrid = (unsigned)(c->sm_count * CLS_MINB);
         if (blocks_needed < cgrid) cgrid = (unsigned)(blocks_needed ? blocks_needed : 1);
-        k_classify<<<cgrid, CLS_WARPS * 32, CLS_SMEM, st>>>(CA, c->rp);
-        ARP_LAUNCHED(c);
+        ARP_CUDA(c, launch_k(k_classify, cgrid, CLS_WARPS * 32, CLS_SMEM, st, pdl, CA, c->rp));
+        c->launches++;
+        if (split_events) ARP_CUDA(c, cudaEventRecord(c->ev[4], st));
         HscanArgs HA;
-        HA.pos4 = SA.pos4; HA.att4 = CA.att4; HA.work = CA.work; HA.meta = meta; HA.work_cap = c->work_cap;
+        HA.pos4 = SA.pos4; HA.hrng = c->hrng.as<int2>(); HA.work = CA.work; HA.meta = meta; HA.work_cap = c->work_cap;
         HA.out = CA.out; HA.side = side;
+        if (!c->hscan_blocks) {             /* a persistent grid: exactly the blocks that are resident together */
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hscan, HSCAN_WARPS * 32, 0) != cudaSuccess || per_sm < 1)
+                per_sm = 1;
+            (void)cudaGetLastError();
+            c->hscan_blocks = per_sm * c->sm_count;
+        }
         size_t hb = (size_t)((c->work_cap + 255) / 256);
-        unsigned hgrid = (unsigned)(c->sm_count * 8);
+        unsigned hgrid = (unsigned)c->hscan_blocks;
         if (hb < hgrid) hgrid = (unsigned)(hb ? hb : 1);
-        k_hscan<<<hgrid, 256, 0, st>>>(HA, c->rp);
-        ARP_LAUNCHED(c);
-    } else if (with_events) {
+        ARP_CUDA(c, launch_k(k_hscan, hgrid, HSCAN_WARPS * 32, 0, st, pdl, HA, c->rp));
+        c->launches++;
+    } else if (split_events) {
         ARP_CUDA(c, cudaEventRecord(c->ev[2], st));
+        ARP_CUDA(c, cudaEventRecord(c->ev[4], st));
     }
     if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[3], st));
     ARP_CUDA(c, cudaMemcpyAsync(c->h_meta, meta, sizeof(RunMeta), cudaMemcpyDeviceToHost, st));

@@ -329,11 +329,9 @@ ARP_HD_NOINLINE float cos_angle_fff(const float* a, float bx, float by, float bz
  * differ only in the angle threshold, so hydrogen distance and cosine are shared.
  * Returns the subset of `need` whose predicate is true.
  */
-ARP_HD int rule_hbond_scan(const ArpSide& S, const ArpRuleParams& P, int donor, float dcx, float dcy, float dcz,
-                           float acx, float acy, float acz, double vdw_acc, int need)
+ARP_HD int rule_hbond_scan_range(const ArpSide& S, const ArpRuleParams& P, int h0, int h1, float dcx, float dcy, float dcz,
+                                 float acx, float acy, float acz, double vdw_acc, int need)
 {
-    if (!S.h_off) return 0;
-    const int h0 = S.h_off[donor], h1 = S.h_off[donor + 1];
     if (h0 == h1) return 0;
     const double lim = d_add(d_add(P.h_vdw, vdw_acc), P.vdw_comp);                  /* utils.py:89 */
     const double lim2 = lim * lim;
@@ -382,6 +380,14 @@ ARP_HD int rule_hbond_scan(const ArpSide& S, const ArpRuleParams& P, int donor, 
         if ((need & ~got) == 0) break;                       /* the reference returns at the first success */
     }
     return got & need;
+}
+
+/* the same with the donor's hydrogens looked up in the CSR (h_off of the ORIGINAL atom index) */
+ARP_HD int rule_hbond_scan(const ArpSide& S, const ArpRuleParams& P, int donor, float dcx, float dcy, float dcz,
+                           float acx, float acy, float acz, double vdw_acc, int need)
+{
+    if (!S.h_off) return 0;
+    return rule_hbond_scan_range(S, P, S.h_off[donor], S.h_off[donor + 1], dcx, dcy, dcz, acx, acy, acz, vdw_acc, need);
 }
 
 /* utils.is_halogen_weak_hbond (utils.py:119-155), screened like rule_hbond_scan */

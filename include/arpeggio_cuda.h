@@ -237,7 +237,9 @@ typedef struct arp_stats {
     float    ms_total;          /* CUDA-event time of the last run, first to last kernel */
     float    ms_grid;           /* cell build part   */
     float    ms_search;         /* search kernel: neighbour search + filters -> hit list */
-    float    ms_classify;       /* classify kernel: distance + angle + bitmask rules -> records */
+    float    ms_classify;       /* classify kernels: distance + angle + bitmask rules -> records (includes ms_hscan) */
+    float    ms_hscan;          /* of which the deferred hydrogen / halogen / xbond predicates */
+    float    pad_;
 } arp_stats;
 
 /* ---- life cycle ---------------------------------------------------------- */

@@ -152,6 +152,25 @@ def test_batch_equals_per_structure(engine):
     util.assert_records_equal(got, util.sort_pairs(np.concatenate(pieces)), 'batch vs per-structure runs')
 
 
+@pytest.mark.parametrize('knob', [None, 'ARPEGGIO_NO_REG_GRID', 'ARPEGGIO_NO_FUSED_GRID', 'ARPEGGIO_NO_PDL'])
+def test_every_grid_build_path(monkeypatch, knob):
+    """The cell grid is built by one of three code paths (register-cached cooperative kernel with 1 or 2 atoms
+    per thread, cooperative kernel through global memory, five kernels); each must give the oracle's stream for
+    a single structure of either size class and for a small batch."""
+    from arpeggio_b200.engine import ContactEngine
+    if knob:
+        monkeypatch.setenv(knob, '1')
+    p = arp_params.make_params()
+    parts = [synth.cloud_featured(n, seed=70 + k) for k, n in enumerate((4000, 9, 2500))]
+    cases = {'30k': synth.cloud_featured(30_000, seed=61), '200k': synth.cloud_featured(200_000, seed=62),
+             'batch': AtomSoA.concat(parts)}
+    if knob == 'ARPEGGIO_NO_PDL':
+        del cases['200k']
+    with ContactEngine(0, p) as eng:
+        for name, soa in cases.items():
+            util.assert_records_equal(eng.pairs(soa), oracle.pairs(soa, p), f'{knob or "default"} {name}')
+
+
 def test_rerun_is_stable_and_overflow_regrows(engine):
     """A sparse structure sizes the record buffer small; a dense one must regrow it (overflow path)."""
     p = arp_params.make_params()

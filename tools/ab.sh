@@ -1,8 +1,20 @@
 #!/bin/bash
-# tools/ab.sh name1 name2 ...: bench the variant libraries under variants/ (run under gpurun)
+# tools/ab.sh name1 name2 ...: time the resident configs[2] job with the variant libraries under variants/
+# (run under gpurun; A/B tooling, never a bench number).  ATOMS / STEPS override the defaults.
 for v in "$@"; do
-  ARPEGGIO_CUDA_LIB=$PWD/variants/lib_$v.so python bench.py --steps 200 --warmup 10 --no-cpu 2>&1 | tail -1 | python -c "
-import sys, json
-d = json.loads(sys.stdin.read()); r = d['roofline']
-print('$v', 'ms/step %.4f' % d['ms_per_step'], 'grid %.4f search %.4f classify %.4f' % (r['grid_build_ms'], r['search_ms'], r['classify_ms']), 'e2e ms %.3f' % d['e2e']['ms_per_step'])"
+  ARPEGGIO_CUDA_LIB=$PWD/variants/lib_$v.so python - "$v" <<'PY'
+import os, sys
+sys.path.insert(0, os.getcwd())
+from arpeggio_b200 import params, synth
+from arpeggio_b200.engine import ContactEngine
+atoms = int(os.environ.get('ATOMS', 100000)); steps = int(os.environ.get('STEPS', 300))
+soa = synth.cloud_featured(atoms, seed=2)
+with ContactEngine(0, params.make_params()) as eng:
+    eng.upload_atoms(soa); n = eng.run_pairs()
+    eng.time_pairs(20, flush_l2=True)
+    ms = eng.time_pairs(steps, flush_l2=True); st = eng.stats()
+    print('%-10s us/step %6.1f | grid %5.1f search %5.1f classify %5.1f hscan %5.1f | %.2f Gpairs/s' % (
+        sys.argv[1], ms * 1e3, st['ms_grid'] * 1e3, st['ms_search'] * 1e3, (st['ms_classify'] - st['ms_hscan']) * 1e3,
+        st['ms_hscan'] * 1e3, n / ms / 1e6))
+PY
 done

@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """Per-source-line instruction counts and stall samples of one kernel in an .ncu-rep:
-    python tools/ncu_lines.py gpurun_out/prof_x.ncu-rep k_search [top]"""
+    python tools/ncu_lines.py gpurun_out/prof_x.ncu-rep k_search [top] [samples]"""
 import csv, io, subprocess, sys
 
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+by_samples = len(sys.argv) > 4 and sys.argv[4] == 'samples'
 out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass', '--kernel-name', kern],
                      capture_output=True, text=True).stdout
 seen_launch = 0
@@ -26,7 +27,7 @@ for r in csv.reader(io.StringIO(out)):
         hdr = r
         continue
     if hdr and r[0]:
-        d = dict(zip(hdr[4:], r[4:]))
+        d = dict(zip(hdr[2:], r[2:]))
         try:
             rows.append((int(d['Instructions Executed']), int(d['# Samples'] or 0), float(d['Avg. Threads Executed'] or 0),
                          path, int(r[0]), r[1].strip()))
@@ -35,5 +36,5 @@ for r in csv.reader(io.StringIO(out)):
 tot = sum(r[0] for r in rows) or 1
 ts = sum(r[1] for r in rows) or 1
 print(f'{kern}: {tot} warp instructions, {ts} samples, {len(rows)} source lines')
-for n, s, act, p, ln, src in sorted(rows, reverse=True)[:top]:
+for n, s, act, p, ln, src in sorted(rows, key=lambda r: (r[1], r[0]) if by_samples else (r[0], r[1]), reverse=True)[:top]:
     print(f'{n:9d} {100 * n / tot:5.1f}% samp={100 * s / ts:5.1f}% act={act:4.1f} {p}:{ln} | {src[:100]}')

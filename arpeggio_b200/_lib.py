@@ -57,6 +57,8 @@ def lib():
         'arp_amide_amide_fetch': (i32, [vp, vp, u64]),
         'arp_amide_ring_run': (i32, [vp, u64p]),
         'arp_amide_ring_fetch': (i32, [vp, vp, u64]),
+        'arp_atom_sifts_run': (i32, [vp]),
+        'arp_atom_sifts_fetch': (i32, [vp, vp, u64]),
         'arp_flag_within': (i32, [vp, C.c_double, vp, u64]),
         'arp_sync': (i32, [vp]),
         'arp_get_stats': (i32, [vp, C.POINTER(abi.ArpStats)]),

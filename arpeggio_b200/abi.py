@@ -170,7 +170,10 @@ class ArpStats(C.Structure):
 PAIR_DTYPE = np.dtype([('i', '<i4'), ('j', '<i4'), ('mask', '<u4'), ('dist', '<f4')])
 PLANE_PAIR_DTYPE = np.dtype([('a', '<i4'), ('b', '<i4'), ('code', '<u4'), ('_pad', '<u4'), ('dist', '<f8')])
 ATOM_PLANE_DTYPE = np.dtype([('atom', '<i4'), ('ring', '<i4'), ('code', '<u4'), ('_pad', '<u4'), ('dist', '<f8')])
+ATOM_SIFT_DTYPE = np.dtype([('sift', '<u2', (4,)), ('integer_sift', '<u4', (4,)), ('hbonds', '<u4', (4,)), ('polars', '<u4', (4,))])
 assert PAIR_DTYPE.itemsize == 16 and PLANE_PAIR_DTYPE.itemsize == 24 and ATOM_PLANE_DTYPE.itemsize == 24
+assert ATOM_SIFT_DTYPE.itemsize == 56
+SIFT_CATEGORIES = ('', '_inter_only', '_intra_only', '_water_only')     # attribute suffixes of the four categories
 
 # every symbol include/arpeggio_cuda.h declares (tests check the built library exports all of them)
 EXPORTED_SYMBOLS = (
@@ -179,7 +182,7 @@ EXPORTED_SYMBOLS = (
     'arp_upload_atoms', 'arp_pairs_run', 'arp_pairs_fetch', 'arp_pairs_device_ptr',
     'arp_upload_planes', 'arp_ring_ring_run', 'arp_ring_ring_fetch', 'arp_atom_ring_run',
     'arp_atom_ring_fetch', 'arp_amide_amide_run', 'arp_amide_amide_fetch', 'arp_amide_ring_run',
-    'arp_amide_ring_fetch', 'arp_flag_within', 'arp_sync', 'arp_get_stats', 'arp_timing_iters', 'arp_launch_count',
+    'arp_amide_ring_fetch', 'arp_atom_sifts_run', 'arp_atom_sifts_fetch', 'arp_flag_within', 'arp_sync', 'arp_get_stats', 'arp_timing_iters', 'arp_launch_count',
 )
 
 

@@ -208,7 +208,7 @@ void arp_destroy(arp_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     DBuf* bufs[] = { &c->xyz, &c->feat, &c->res_id, &c->rad_class, &c->vdw, &c->cov, &c->res_prev, &c->res_next,
                      &c->res_flags, &c->bond_off, &c->bond_nbr, &c->h_off, &c->h_xyz, &c->xnbr, &c->struct_off,
-                     &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->hrng, &c->out, &c->hits, &c->work,
+                     &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->hrng, &c->sift_acc, &c->sift_out, &c->out, &c->hits, &c->work,
                      &c->radtab, &c->sort_tmp, &c->sort_out, &c->sort_zero, &c->sort_off, &c->within, &c->flush };
     for (DBuf* b : bufs) dbuf_free(*b);
     arp_planes_release(c);
@@ -354,7 +354,7 @@ int arp_pairs_run(arp_ctx* c, uint64_t* n_pairs)
     if (!c) return ARP_E_INVALID_ARG;
     ARP_REQUIRE(c, c->have_atoms, ARP_E_NOT_READY, "arp_pairs_run before arp_upload_atoms");
     ARP_TRY(arp_bind(c));
-    c->pairs_valid = 0; c->sorted_valid = 0;
+    c->pairs_valid = 0; c->sorted_valid = 0; c->sifts_valid = 0;
     /* first guess of the stream length; an overflowing run still counts, then is repeated once */
     uint64_t want = c->out_cap ? c->out_cap : (uint64_t)c->N * 16 + 4096;
     ARP_TRY(pairs_out_reserve(c, want));
@@ -403,6 +403,29 @@ int arp_pairs_device_ptr(arp_ctx* c, const arp_pair** dptr)
     ARP_REQUIRE(c, dptr != nullptr, ARP_E_INVALID_ARG, "dptr is NULL");
     ARP_REQUIRE(c, c->pairs_valid, ARP_E_NOT_READY, "no record stream yet");
     *dptr = c->out.as<arp_pair>();
+    return ARP_OK;
+}
+
+int arp_atom_sifts_run(arp_ctx* c)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_REQUIRE(c, c->pairs_valid, ARP_E_NOT_READY, "arp_atom_sifts_run before arp_pairs_run");
+    ARP_TRY(arp_bind(c));
+    ARP_TRY(arp_atom_sifts_enqueue(c));
+    c->sifts_valid = 1;
+    return ARP_OK;
+}
+
+int arp_atom_sifts_fetch(arp_ctx* c, arp_atom_sift* dst, uint64_t cap)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_REQUIRE(c, c->sifts_valid && c->pairs_valid, ARP_E_NOT_READY, "arp_atom_sifts_fetch before arp_atom_sifts_run");
+    ARP_REQUIRE(c, cap >= (uint64_t)c->N, ARP_E_CAPACITY, "destination holds fewer entries than there are atoms");
+    if (c->N == 0) return ARP_OK;
+    ARP_REQUIRE(c, dst != nullptr, ARP_E_INVALID_ARG, "dst is NULL");
+    ARP_TRY(arp_bind(c));
+    ARP_CUDA(c, cudaMemcpyAsync(dst, c->sift_out.p, (size_t)c->N * sizeof(arp_atom_sift), cudaMemcpyDeviceToHost, c->stream));
+    ARP_CUDA(c, cudaStreamSynchronize(c->stream));
     return ARP_OK;
 }
 
@@ -485,7 +508,7 @@ int arp_timing_iters(arp_ctx* c, int iters, int flush_l2, float* ms_per_iter)
     c->stats.ms_classify = (float)(classify / split_iters);
     c->stats.ms_hscan = (float)(hscan / split_iters);
     c->stats.ms_total = (float)(tot / iters);
-    c->sorted_valid = 0;
+    c->sorted_valid = 0; c->sifts_valid = 0;
     if (ms_per_iter) *ms_per_iter = (float)(tot / iters);
     return ARP_OK;
 }

@@ -136,6 +136,10 @@ struct arp_ctx {
     /* binding-site flags */
     DBuf within;
 
+    /* per-atom SIFt reductions */
+    DBuf sift_acc, sift_out;
+    int sifts_valid = 0;
+
     /* timing */
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   /* [4]: between k_classify and k_hscan */
     arp_stats stats;
@@ -218,6 +222,7 @@ int  arp_pairs_prepare(arp_ctx* c);                       /* arp_pairs.cu: size 
 int  arp_pairs_enqueue(arp_ctx* c, int with_events);
 int  arp_pairs_sorted_build(arp_ctx* c);                  /* arp_pairs.cu: (i, j)-ascending copy of the stream */
 int  arp_flag_within_run(arp_ctx* c, double radius);      /* arp_pairs.cu */
+int  arp_atom_sifts_enqueue(arp_ctx* c);                  /* arp_sifts.cu: sorted stream -> arp_atom_sift[N] */
 void arp_planes_release(arp_ctx* c);                      /* arp_planes.cu */
 
 /* exclusive scan of n ints (n read from *n_dev + n_add when n_dev != null), single pass;

@@ -162,6 +162,15 @@ class ContactEngine:
         return self._plane_term(self._L.arp_amide_ring_run, self._L.arp_amide_ring_fetch, abi.PLANE_PAIR_DTYPE)
 
     # ------------------------------------------------------------------
+    def atom_sifts(self):
+        """arp_atom_sift[N] of the last run_pairs: the per-atom SIFt words, integer SIFts and hbond / polar
+        counters the reference's pair loop leaves on the atoms (utils.py:182-242, interactions.py:822-852)."""
+        n = self._soa.n_atoms
+        out = np.zeros(n, dtype=abi.ATOM_SIFT_DTYPE)
+        self._check(self._L.arp_atom_sifts_run(self._ctx))
+        self._check(self._L.arp_atom_sifts_fetch(self._ctx, out.ctypes.data if n else None, n))
+        return out
+
     def flag_within(self, radius):
         """uint8[N]: atom selected or within `radius` of a selected atom (interactions.py:1420-1424)."""
         n = self._soa.n_atoms

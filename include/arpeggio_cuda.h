@@ -227,6 +227,20 @@ typedef struct arp_atom_plane { /* AtomPlaneContact, interactions.py:19-21 */
     double   dist;
 } arp_atom_plane;
 
+/* per-atom SIFt reductions: what the pair loop leaves on every atom as a side effect
+   (interactions.py:822-852, :924-934 through utils.update_atom_integer_sift / update_atom_sift /
+   update_atom_fsift, utils.py:182-242).  Category k: 0 every contact, 1 contact_type == 'INTER',
+   2 'INTRA' in contact_type, 3 'WATER' in contact_type. */
+typedef struct arp_atom_sift {
+    uint16_t sift[4];           /* atom.sift, .sift_inter_only, .sift_intra_only, .sift_water_only: bit b = SIFt[b];
+                                   atom.actual_fsift* is the same word >> 5 (SIFt[5:]) */
+    uint32_t integer_sift[4];   /* atom.integer_sift*: 2 bits per SIFt position, values 0..2.  The reference ASSIGNS
+                                   sift-before-this-contact + SIFt at every contact (utils.py:233), so the value is
+                                   that of the atom's LAST contact of the category in loop order */
+    uint32_t hbonds[4];         /* atom.actual_hbonds, _inter_only, _intra_only, _water_only (interactions.py:822-836) */
+    uint32_t polars[4];         /* atom.actual_polars, ...                                  (interactions.py:838-852) */
+} arp_atom_sift;
+
 typedef struct arp_stats {
     uint64_t n_pairs;           /* records emitted by the last arp_pairs_run */
     uint64_t n_candidates;      /* distance tests performed */
@@ -286,6 +300,14 @@ int  arp_amide_amide_run(arp_ctx* ctx, uint64_t* n);
 int  arp_amide_amide_fetch(arp_ctx* ctx, arp_plane_pair* dst, uint64_t cap);
 int  arp_amide_ring_run(arp_ctx* ctx, uint64_t* n);
 int  arp_amide_ring_fetch(arp_ctx* ctx, arp_plane_pair* dst, uint64_t cap);
+
+/* ---- per-atom SIFt reductions ----------------------------------
+ * Segmented OR / count / last-contact reduction of the record stream of the last arp_pairs_run onto
+ * the atoms, for the loop order = ascending (bgn, end) (the order of the sorted stream; the reference's
+ * own order is the KD-tree traversal of Bio.PDB.NeighborSearch, which only matters for integer_sift).
+ * dst[i] belongs to atom i of the uploaded list; cap >= n_atoms.                                  */
+int  arp_atom_sifts_run(arp_ctx* ctx);
+int  arp_atom_sifts_fetch(arp_ctx* ctx, arp_atom_sift* dst, uint64_t cap);
 
 /* ---- binding-site expansion -----------------------------------
  * replaces the search_all(6.0) loop of _make_selection (interactions.py:1420-1424):

@@ -500,6 +500,62 @@ int orc_pairs_bruteforce(const arp_atoms* A, const arp_params* P, arp_pair** out
     return ARP_OK;
 }
 
+/* ---- per-atom SIFt side effects of the pair loop -------------------------------------
+ * The loop of _calculate_atom_contacts, replayed over finished records IN THE GIVEN ORDER
+ * (interactions.py:822-852 counters, :924-934 SIFt updates):
+ *   utils.update_atom_integer_sift (utils.py:225-242): integer_sift* = sift* + SIFt   (an assignment, from
+ *       the binary sift BEFORE this contact -- it is called first, interactions.py:925-926)
+ *   utils.update_atom_sift (utils.py:182-199):         sift* |= SIFt
+ *   utils.update_atom_fsift (utils.py:202-222):        actual_fsift* |= SIFt[5:]  (= sift* >> 5, not stored)
+ * categories: every contact; contact_type == 'INTER'; 'INTRA' in contact_type; 'WATER' in contact_type. */
+int orc_atom_sifts(const arp_pair* rec, uint64_t n, int n_atoms, arp_atom_sift* out)
+{
+    typedef struct { int sift[4][ARP_SIFT_NBITS]; int integer[4][ARP_SIFT_NBITS]; uint32_t hb[4], pl[4]; } atom_state;
+    atom_state* st = (atom_state*)calloc((size_t)(n_atoms > 0 ? n_atoms : 1), sizeof(atom_state));
+    if (!st) return -1;
+    for (uint64_t r = 0; r < n; ++r) {
+        int sift[ARP_SIFT_NBITS];
+        for (int b = 0; b < ARP_SIFT_NBITS; ++b) sift[b] = (int)(rec[r].mask >> b & 1u);
+        const uint32_t cls = (rec[r].mask >> ARP_CLASS_SHIFT) & 7u;
+        /* the class names (interactions.py:643-691) as the substring tests see them */
+        const int is_inter = cls == ARP_CLASS_INTER;
+        const int has_intra = cls == ARP_CLASS_INTRA_NON_SELECTION || cls == ARP_CLASS_INTRA_SELECTION;
+        const int has_water = cls == ARP_CLASS_SELECTION_WATER || cls == ARP_CLASS_NON_SELECTION_WATER || cls == ARP_CLASS_WATER_WATER;
+        const int atoms[2] = { rec[r].i, rec[r].j };
+        for (int side = 0; side < 2; ++side) {
+            if (atoms[side] < 0 || atoms[side] >= n_atoms) { free(st); return -2; }
+            atom_state* a = st + atoms[side];
+            /* counters, interactions.py:822-852: if 'INTRA' ... elif 'INTER' ... elif 'WATER' */
+            const int cat = has_intra ? 2 : is_inter ? 1 : has_water ? 3 : 0;
+            if (sift[ARP_SIFT_HBOND]) { a->hb[0]++; if (cat) a->hb[cat]++; }
+            if (sift[ARP_SIFT_POLAR]) { a->pl[0]++; if (cat) a->pl[cat]++; }
+            /* update_atom_integer_sift, then update_atom_sift */
+            const int on[4] = { 1, is_inter, has_intra, has_water };
+            for (int c = 0; c < 4; ++c) {
+                if (!on[c]) continue;
+                for (int b = 0; b < ARP_SIFT_NBITS; ++b) a->integer[c][b] = a->sift[c][b] + sift[b];
+            }
+            for (int c = 0; c < 4; ++c) {
+                if (!on[c]) continue;
+                for (int b = 0; b < ARP_SIFT_NBITS; ++b) a->sift[c][b] = a->sift[c][b] || sift[b];
+            }
+        }
+    }
+    for (int i = 0; i < n_atoms; ++i) {
+        memset(&out[i], 0, sizeof out[i]);
+        for (int c = 0; c < 4; ++c) {
+            for (int b = 0; b < ARP_SIFT_NBITS; ++b) {
+                out[i].sift[c] |= (uint16_t)(st[i].sift[c][b] << b);
+                out[i].integer_sift[c] |= (uint32_t)st[i].integer[c][b] << (2 * b);
+            }
+            out[i].hbonds[c] = st[i].hb[c];
+            out[i].polars[c] = st[i].pl[c];
+        }
+    }
+    free(st);
+    return 0;
+}
+
 void orc_free(void* p) { free(p); }
 
 /* binding-site expansion of _make_selection (interactions.py:1420-1424) */

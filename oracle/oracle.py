@@ -42,6 +42,7 @@ def lib():
                                      C.POINTER(vp), u64p]
         L.orc_atom_ring.argtypes = [C.POINTER(abi.ArpAtoms), C.POINTER(abi.ArpPlanes), C.POINTER(abi.ArpParams),
                                     C.POINTER(vp), u64p]
+        L.orc_atom_sifts.argtypes = [vp, C.c_uint64, C.c_int, vp]
         L.orc_free.argtypes = [vp]
         L.orc_free.restype = None
         fp, dp = C.POINTER(C.c_float), C.POINTER(C.c_double)
@@ -100,6 +101,15 @@ def classify(soa, params, b, e):
     _check(lib().orc_classify(C.byref(a), C.byref(params), b.ctypes.data, e.ctypes.data, b.shape[0],
                               out.ctypes.data, emitted.ctypes.data))
     return out, emitted.astype(bool)
+
+
+def atom_sifts(records, n_atoms):
+    """Oracle of atom_sifts(): the pair loop's side effects on the atoms, replayed over `records` in their order."""
+    rec = np.ascontiguousarray(records, dtype=abi.PAIR_DTYPE)
+    out = np.zeros(int(n_atoms), dtype=abi.ATOM_SIFT_DTYPE)
+    _check(lib().orc_atom_sifts(rec.ctypes.data if rec.shape[0] else None, rec.shape[0], int(n_atoms),
+                                out.ctypes.data if n_atoms else None))
+    return out
 
 
 def flag_within(soa, radius):

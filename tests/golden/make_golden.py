@@ -54,6 +54,11 @@ CASES = {
 }
 
 
+RESIDUE_PLANE_SIFTS = ('ring_ring_inter_integer_sift', 'ring_atom_inter_integer_sift', 'atom_ring_inter_integer_sift',
+                       'mc_atom_ring_inter_integer_sift', 'sc_atom_ring_inter_integer_sift', 'amide_ring_inter_integer_sift',
+                       'ring_amide_inter_integer_sift', 'amide_amide_inter_integer_sift')
+
+
 def reference_complex(cx):
     """An InteractionComplex whose __init__ (file parsing) is skipped and whose fields are the mock's."""
     ic = object.__new__(ref_interactions.InteractionComplex)
@@ -141,6 +146,26 @@ def run_case(name, kwargs, selections, cutoff, vdw_comp, incl):
 
     contacts_json = json.dumps(ic.get_contacts(), sort_keys=True) if meta['raises'] is None else '[]'
 
+    # the pair loop's side effects on the atoms (utils.py:182-242, interactions.py:822-852), list order
+    atom_sifts = np.zeros(len(packed.atoms), dtype=abi.ATOM_SIFT_DTYPE)
+    for i, a in enumerate(packed.atoms):
+        for c, suffix in enumerate(abi.SIFT_CATEGORIES):
+            sift, integer = getattr(a, 'sift' + suffix), getattr(a, 'integer_sift' + suffix)
+            fsift = getattr(a, 'actual_fsift' + suffix)
+            assert len(sift) == 15 and len(integer) == 15 and list(fsift) == list(sift[5:])
+            assert set(sift) <= {0, 1, True, False} and set(integer) <= {0, 1, 2}
+            atom_sifts['sift'][i, c] = sum(int(bool(v)) << b for b, v in enumerate(sift))
+            atom_sifts['integer_sift'][i, c] = sum(int(v) << (2 * b) for b, v in enumerate(integer))
+            atom_sifts['hbonds'][i, c] = getattr(a, 'actual_hbonds' + suffix)
+            atom_sifts['polars'][i, c] = getattr(a, 'actual_polars' + suffix)
+    # per-residue counters of the plane loops (interactions.py:1040-1057, :1171-1176, :1290-1291, :1371-1373)
+    res_sifts = {}
+    for r in ic.biopython_str.get_residues():
+        entry = {n: list(getattr(r, n)) for n in RESIDUE_PLANE_SIFTS}
+        if any(any(v) for v in entry.values()):
+            res_sifts[mockbio.residue_key(r)] = entry
+    meta['residue_plane_sifts'] = res_sifts
+
     meta.update(
         selection_serials=[a.serial_number for a in ic.selection],
         selection_plus_serials=[a.serial_number for a in ic.selection_plus],
@@ -158,7 +183,7 @@ def run_case(name, kwargs, selections, cutoff, vdw_comp, incl):
         ring_flags=packed.rings.flags,
         amide_center=packed.amides.center, amide_normal=packed.amides.normal, amide_res=packed.amides.res_id,
         amide_flags=packed.amides.flags,
-        exp_pairs=pairs, exp_ring_ring=rr, exp_atom_ring=ap, exp_amide_amide=aa, exp_amide_ring=ar,
+        exp_atom_sifts=atom_sifts, exp_pairs=pairs, exp_ring_ring=rr, exp_atom_ring=ap, exp_amide_amide=aa, exp_amide_ring=ar,
         meta=np.array(json.dumps(meta)), contacts_json=np.array(contacts_json))
     np.savez_compressed(os.path.join(HERE, name + '.npz'), **arrays)
     print(f'  {name}: N={len(packed.atoms)} pairs={len(pairs)} ring-ring={len(rr)} atom-ring={len(ap)} '

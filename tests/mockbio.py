@@ -289,6 +289,11 @@ class MockComplex:
         self.group_plane_contacts = []
 
 
+def residue_key(r):
+    """A stable name of a residue across rebuilds of the same recipe."""
+    return f'{r.get_parent().id}/{r.id[0].strip()}/{r.id[1]}/{r.id[2].strip()}/{r.resname}'
+
+
 def flag_polypeptides(cx):
     """Polypeptide flags exactly as _handle_chains_residues_and_breaks leaves them
     (interactions.py:1663-1695): only residues of a polypeptide get prev_/next_residue."""

@@ -171,6 +171,44 @@ def test_every_grid_build_path(monkeypatch, knob):
             util.assert_records_equal(eng.pairs(soa), oracle.pairs(soa, p), f'{knob or "default"} {name}')
 
 
+@pytest.mark.parametrize('case', [c for c in CASES if c != 'xbond_fault'])
+def test_atom_sifts_golden(engine, case):
+    """atom.sift*, integer_sift*, actual_hbonds*, actual_polars* as the reference left them."""
+    g = util.Golden(case)
+    engine.set_params(g.params)
+    engine.pairs(g.soa)
+    got = engine.atom_sifts()
+    for f in got.dtype.names:
+        assert np.array_equal(got[f], g.exp_atom_sifts[f]), f
+
+
+def test_atom_sifts_full_size(engine):
+    p = arp_params.make_params()
+    engine.set_params(p)
+    soa = synth.cloud_featured(100_000, seed=2)
+    rec = engine.pairs(soa)
+    got = engine.atom_sifts()
+    exp = oracle.atom_sifts(rec, soa.n_atoms)
+    for f in got.dtype.names:
+        assert np.array_equal(got[f], exp[f]), f
+    # size-independent properties: every record touches two atoms; OR of the atom words = OR of the record masks
+    assert int(got['hbonds'][:, 0].sum()) == 2 * int(np.count_nonzero(rec['mask'] >> 5 & 1))
+    assert int(got['polars'][:, 0].sum()) == 2 * int(np.count_nonzero(rec['mask'] >> 13 & 1))
+    assert np.bitwise_or.reduce(got['sift'][:, 0]) == np.bitwise_or.reduce(rec['mask']) & 0x7FFF
+    assert np.array_equal(got['sift'][:, 0], got['sift'][:, 1] | got['sift'][:, 2] | got['sift'][:, 3])
+    # an empty structure and a structure without contacts
+    empty = AtomSoA(xyz=np.zeros((0, 3), np.float32), feat=np.zeros(0, np.uint32), res_id=np.zeros(0, np.int32),
+                    rad_class=np.zeros(0, np.uint16), vdw=soa.vdw, cov=soa.cov, res_prev=np.zeros(0, np.int32),
+                    res_next=np.zeros(0, np.int32), res_flags=np.zeros(0, np.uint8))
+    engine.pairs(empty)
+    assert engine.atom_sifts().shape == (0,)
+    lone = synth.cloud_featured(3, seed=5)
+    lone.xyz[:] = np.array([[0, 0, 0], [50, 0, 0], [0, 50, 0]], np.float32)
+    assert engine.pairs(lone).shape[0] == 0
+    z = engine.atom_sifts()
+    assert z.shape == (3,) and not z['sift'].any() and not z['integer_sift'].any()
+
+
 def test_rerun_is_stable_and_overflow_regrows(engine):
     """A sparse structure sizes the record buffer small; a dense one must regrow it (overflow path)."""
     p = arp_params.make_params()

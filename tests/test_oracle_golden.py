@@ -42,3 +42,17 @@ def test_planes_match_reference(case):
     util.assert_records_equal(oracle.atom_ring(g.soa, g.rings, g.params), g.exp_atom_ring, f'{case} atom-ring')
     util.assert_records_equal(oracle.amide_amide(g.amides, g.params), g.exp_amide_amide, f'{case} amide-amide')
     util.assert_records_equal(oracle.amide_ring(g.amides, g.rings, g.params), g.exp_amide_ring, f'{case} amide-ring')
+
+
+@pytest.mark.parametrize('case', [c for c in CASES if c != 'xbond_fault'])
+def test_atom_sifts_match_reference(case):
+    """The per-atom side effects of the reference's pair loop (atom.sift*, integer_sift*, actual_hbonds*,
+    actual_polars*; utils.py:182-242, interactions.py:822-852) replayed by the oracle over the records."""
+    g = util.Golden(case)
+    got = oracle.atom_sifts(g.exp_pairs, g.soa.n_atoms)
+    for f in got.dtype.names:
+        assert np.array_equal(got[f], g.exp_atom_sifts[f]), f
+    assert (got['integer_sift'] != 0).any() and (got['hbonds'][:, 0] > 0).any()
+    # the integer SIFt is not the plain count-capped OR: the last contact decides (utils.py:233)
+    two = (got['integer_sift'][:, 0][:, None] >> (2 * np.arange(15)) & 3) == 2
+    assert two.any()

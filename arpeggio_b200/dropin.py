@@ -14,11 +14,15 @@ loops (file parsing, typing, ``_make_selection``) stays the reference's host cod
     ic = InteractionComplex('1tqn_h.cif'); ic.structure_checks(); ic.initialize()
     ic.run_arpeggio(['/A/508/'], 5.0, 0.1, False); contacts = ic.get_contacts()
 
-Not reproduced: the per-atom / per-residue SIFt counters the reference updates as a
-side effect inside the loops (interactions.py:822-852, :924-934, :1040-1057, :1171-1176); they
-feed only the CSV writers the reference CLI has disabled.  List order: the reference emits pairs in
-KD-tree traversal order; here records come out sorted by (bgn index, end index) of
-``selection_plus``.
+Side effects of the loops: the per-atom SIFt words, integer SIFts and hbond / polar counters
+(interactions.py:822-852, :924-934) come from the GPU reduction ``ContactEngine.atom_sifts`` and are
+written back onto the atoms as the same attributes (``atom.sift``, ``integer_sift_inter_only``,
+``actual_fsift``, ``actual_hbonds`` ...); the per-residue counters of the plane loops (:1040-1057,
+:1171-1176, :1290-1291, :1371-1373) are re-derived from the plane records.  Every run starts them
+from zero (what ``initialize()`` leaves), so ``write_atom_sifts`` / ``_calc_residue_sifts`` and the other
+CSV writers work on top.  List order: the reference emits pairs in KD-tree traversal order; here
+records come out sorted by (bgn index, end index) of ``selection_plus`` -- that is also the loop order
+the order-dependent ``integer_sift`` (utils.py:233) is evaluated for.
 """
 import collections
 
@@ -72,11 +76,52 @@ def _contact_types_of(obj):
     return None, arp_params.DEFAULT_DIST_MAX, arp_params.DEFAULT_H_VDW
 
 
+MAINCHAIN_ATOMS = frozenset(('N', 'C', 'CA', 'O', 'OXT'))          # config.py:35
+
+_RESIDUE_PLANE_SIFTS = (('ring_ring_inter_integer_sift', 9), ('ring_atom_inter_integer_sift', 5),
+                        ('atom_ring_inter_integer_sift', 5), ('mc_atom_ring_inter_integer_sift', 5),
+                        ('sc_atom_ring_inter_integer_sift', 5), ('amide_ring_inter_integer_sift', 1),
+                        ('ring_amide_inter_integer_sift', 1), ('amide_amide_inter_integer_sift', 1))
+
+
+def _bump(residue, name, k):
+    """residue.<name>[k] += 1 as the reference spells it (a fresh list each time, interactions.py:1047)."""
+    v = list(getattr(residue, name))
+    v[k] = v[k] + 1
+    setattr(residue, name, v)
+
+
+def apply_atom_sifts(atoms, sifts):
+    """Write an ``arp_atom_sift`` array back onto the atoms as the attributes the reference's pair loop
+    leaves (utils.py:182-242: sift*, integer_sift*, actual_fsift*; interactions.py:822-852: actual_hbonds*,
+    actual_polars*), as plain Python lists / ints."""
+    nb = abi.SIFT_NBITS
+    shifts = np.arange(nb, dtype=np.uint32)
+    for c, suffix in enumerate(abi.SIFT_CATEGORIES):
+        bits = ((sifts['sift'][:, c].astype(np.uint32)[:, None] >> shifts) & 1).astype(np.int64).tolist()
+        integer = ((sifts['integer_sift'][:, c][:, None] >> (2 * shifts)) & 3).astype(np.int64).tolist()
+        hb, pl = sifts['hbonds'][:, c].tolist(), sifts['polars'][:, c].tolist()
+        for k, atom in enumerate(atoms):
+            setattr(atom, 'sift' + suffix, bits[k])
+            setattr(atom, 'integer_sift' + suffix, integer[k])
+            setattr(atom, 'actual_fsift' + suffix, bits[k][5:])
+            setattr(atom, 'actual_hbonds' + suffix, hb[k])
+            setattr(atom, 'actual_polars' + suffix, pl[k])
+
+
 class CudaContactsMixin:
     """Mix in before ``arpeggio.core.InteractionComplex`` (or a duck-typed stand-in)."""
 
     cuda_device = 0
     cuda_engine = None          # set to a private ContactEngine to avoid the shared one
+    cuda_atom_sifts = True      # reproduce the per-atom / per-residue SIFt side effects of the loops
+
+    def _cuda_reset_residue_sifts(self, names):
+        """The counters start from what _initialize_residue_sift leaves (interactions.py:1869-1883)."""
+        sizes = dict(_RESIDUE_PLANE_SIFTS)
+        for residue in self.biopython_str.get_residues():
+            for n in names:
+                setattr(residue, n, [0] * sizes[n])
 
     # ------------------------------------------------------------------
     def _cuda_engine(self):
@@ -123,6 +168,8 @@ class CudaContactsMixin:
         for k, (i, j) in enumerate(zip(rec['i'].tolist(), rec['j'].tolist())):
             out.append(AAC(atoms[i], atoms[j], bits[k], abi.CLASS_NAMES[classes[k]], dist[k]))
         self.atom_contacts = out
+        if self.cuda_atom_sifts:
+            apply_atom_sifts(atoms, eng.atom_sifts())
 
     def _calculate_ring_contacts(self):
         """Replaces interactions.py:938-1194 (plane-plane and atom-plane)."""
@@ -141,6 +188,12 @@ class CudaContactsMixin:
                 v = names[key] = sorted(a.get_id() for a in rings[key]['atoms'])
             return v
 
+        sifts = self.cuda_atom_sifts
+        if sifts:
+            self._cuda_reset_residue_sifts(('ring_ring_inter_integer_sift', 'ring_atom_inter_integer_sift',
+                                            'atom_ring_inter_integer_sift', 'mc_atom_ring_inter_integer_sift',
+                                            'sc_atom_ring_inter_integer_sift'))
+        inter = abi.CLASS_NAMES.index('INTER')
         self.plane_plane_contacts = []
         for r in eng.ring_ring():
             ka, kb = packed.ring_keys[int(r['a'])], packed.ring_keys[int(r['b'])]
@@ -148,6 +201,16 @@ class CudaContactsMixin:
             labels = [abi.GEOM_NAMES[code & 0xF]]
             if (code >> 4) & 0xF != 0xF:
                 labels.append(abi.GEOM_NAMES[(code >> 4) & 0xF])
+            if sifts and (code >> 8) & 7 == inter and not code >> 11 & 1:
+                # interactions.py:1171-1176, once per VISIT: (a, b) credits ring a's residue with its geometry,
+                # (b, a) credits ring b's with its own -- the second label when it differed, else the same
+                g1 = code & 0xF
+                g2 = (code >> 4) & 0xF
+                if g1 < 9:
+                    _bump(rings[ka]['residue'], 'ring_ring_inter_integer_sift', g1)
+                g2 = g1 if g2 == 0xF else g2
+                if g2 < 9:
+                    _bump(rings[kb]['residue'], 'ring_ring_inter_integer_sift', g2)
             self.plane_plane_contacts.append(PPC(ka, rings[ka]['residue'], list(ring_atoms(ka)), kb, rings[kb]['residue'],
                                                  list(ring_atoms(kb)), np.float64(r['dist']), labels,
                                                  abi.CLASS_NAMES[(code >> 8) & 7]))
@@ -156,6 +219,15 @@ class CudaContactsMixin:
             key = packed.ring_keys[int(r['ring'])]
             code = int(r['code'])
             labels = sorted(n for b, n in enumerate(abi.AP_NAMES) if code >> b & 1)
+            if sifts and (code >> 8) & 7 == inter and not code >> 11 & 1:          # interactions.py:1039-1057
+                atom = packed.atoms[int(r['atom'])]
+                parent = atom.get_parent()
+                for k in range(len(abi.AP_NAMES)):
+                    if code >> k & 1:
+                        _bump(rings[key]['residue'], 'ring_atom_inter_integer_sift', k)
+                        _bump(parent, 'atom_ring_inter_integer_sift', k)
+                        if parent in self.polypeptide_residues:
+                            _bump(parent, ('mc' if atom.name in MAINCHAIN_ATOMS else 'sc') + '_atom_ring_inter_integer_sift', k)
             self.atom_plane_contacts.append(APC(packed.atoms[int(r['atom'])], rings[key]['residue'], list(ring_atoms(key)),
                                                 np.float64(r['dist']), labels, abi.CLASS_NAMES[(code >> 8) & 7]))
 
@@ -171,15 +243,29 @@ class CudaContactsMixin:
         def names(group):
             return sorted(a.get_id() for a in group['atoms'])
 
+        sifts = self.cuda_atom_sifts
+        if sifts:
+            self._cuda_reset_residue_sifts(('amide_ring_inter_integer_sift', 'ring_amide_inter_integer_sift',
+                                            'amide_amide_inter_integer_sift'))
+        inter = abi.CLASS_NAMES.index('INTER')
+
+        def counted(code):                  # contact_type == 'INTER' and not intra_residue (interactions.py:1290, :1371)
+            return sifts and (code >> 8) & 7 == inter and not code >> 11 & 1
+
         self.group_group_contacts = []
         for r in eng.amide_amide():
             a, b = amides[packed.amide_keys[int(r['a'])]], amides[packed.amide_keys[int(r['b'])]]
+            if counted(int(r['code'])):
+                _bump(a['residue'], 'amide_amide_inter_integer_sift', 0)
             self.group_group_contacts.append(PPC(a['amide_id'], a['residue'], names(a), b['amide_id'], b['residue'], names(b),
                                                  np.float32(r['dist']), ['AMIDEAMIDE'],
                                                  abi.CLASS_NAMES[(int(r['code']) >> 8) & 7]))
         self.group_plane_contacts = []
         for r in eng.amide_ring():
             a, g = amides[packed.amide_keys[int(r['a'])]], rings[packed.ring_keys[int(r['b'])]]
+            if counted(int(r['code'])):
+                _bump(a['residue'], 'amide_ring_inter_integer_sift', 0)
+                _bump(g['residue'], 'ring_amide_inter_integer_sift', 0)
             self.group_plane_contacts.append(PPC(a['amide_id'], a['residue'], names(a), g['ring_id'], g['residue'], names(g),
                                                  np.float64(r['dist']), ['AMIDERING'],
                                                  abi.CLASS_NAMES[(int(r['code']) >> 8) & 7]))

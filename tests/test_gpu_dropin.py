@@ -34,6 +34,40 @@ def test_get_contacts_json_matches_reference(engine, case):
     assert 'atom-atom' in kinds
 
 
+@pytest.mark.parametrize('case', [c for c in util.golden_cases() if c != 'xbond_fault'])
+def test_sift_side_effects_match_reference(engine, case):
+    """SURVEY 8 f3 through the drop-in: after run_arpeggio the atoms carry the attributes the reference's pair loop
+    leaves (sift*, integer_sift*, actual_fsift*, actual_hbonds*, actual_polars*) and the residues the counters
+    of the plane loops, value for value."""
+    import mockbio
+    from arpeggio_b200 import abi
+    g = util.Golden(case)
+    host = mock_host.host_from_golden(g)
+    host.cuda_engine = engine
+    m = g.meta
+    host.run_arpeggio(m['cutoff'], m['vdw_comp'], m['include_sequence_adjacent'])
+    exp = g.exp_atom_sifts
+    for i, a in enumerate(host.selection_plus):
+        for c, suffix in enumerate(abi.SIFT_CATEGORIES):
+            sift = [int(exp['sift'][i, c]) >> b & 1 for b in range(15)]
+            assert a.__dict__['sift' + suffix] == sift
+            assert a.__dict__['actual_fsift' + suffix] == sift[5:]
+            assert a.__dict__['integer_sift' + suffix] == [int(exp['integer_sift'][i, c]) >> 2 * b & 3 for b in range(15)]
+            assert a.__dict__['actual_hbonds' + suffix] == int(exp['hbonds'][i, c])
+            assert a.__dict__['actual_polars' + suffix] == int(exp['polars'][i, c])
+    want = m['residue_plane_sifts']
+    seen = 0
+    for r in host.biopython_str.get_residues():
+        e = want.get(mockbio.residue_key(r))
+        for name in ('ring_ring_inter_integer_sift', 'ring_atom_inter_integer_sift', 'atom_ring_inter_integer_sift',
+                     'mc_atom_ring_inter_integer_sift', 'sc_atom_ring_inter_integer_sift', 'amide_ring_inter_integer_sift',
+                     'ring_amide_inter_integer_sift', 'amide_amide_inter_integer_sift'):
+            got = getattr(r, name)
+            assert got == (e[name] if e else [0] * len(got)), (mockbio.residue_key(r), name)
+        seen += e is not None
+    assert seen == len(want)
+
+
 def test_record_types_and_dtypes(engine):
     import numpy as np
     g = util.Golden('ligand_site')

@@ -59,6 +59,8 @@ def lib():
         'arp_amide_ring_fetch': (i32, [vp, vp, u64]),
         'arp_atom_sifts_run': (i32, [vp]),
         'arp_atom_sifts_fetch': (i32, [vp, vp, u64]),
+        'arp_pairs_json_size': (i32, [vp, u64, i32, vp, i32, u64p]),
+        'arp_pairs_json_write': (i32, [vp, u64, i32, vp, vp, i32, vp, u64, u64p]),
         'arp_flag_within': (i32, [vp, C.c_double, vp, u64]),
         'arp_sync': (i32, [vp]),
         'arp_get_stats': (i32, [vp, C.POINTER(abi.ArpStats)]),

@@ -25,10 +25,11 @@ records come out sorted by (bgn index, end index) of ``selection_plus`` -- that 
 the order-dependent ``integer_sift`` (utils.py:233) is evaluated for.
 """
 import collections
+import collections.abc
 
 import numpy as np
 
-from . import abi, params as arp_params
+from . import abi, jsonout, params as arp_params
 from .engine import ContactEngine
 from .packing import pack_complex
 
@@ -76,6 +77,52 @@ def _contact_types_of(obj):
     return None, arp_params.DEFAULT_DIST_MAX, arp_params.DEFAULT_H_VDW
 
 
+class LazyAtomContacts(collections.abc.Sequence):
+    """``atom_contacts`` without one namedtuple per record up front: a read-only sequence over the
+    record array that builds the reference's ``AtomAtomContact(bgn_atom, end_atom, sifts, contact_type,
+    distance)`` (interactions.py:28-29, :936) when an element is asked for.  Iteration, indexing, slicing,
+    ``len`` and ``filter(...)`` -- everything the reference does with the list after the loop -- work."""
+
+    def __init__(self, records, atoms, record_type):
+        self.records, self._atoms, self._type = records, atoms, record_type
+
+    def __len__(self):
+        return self.records.shape[0]
+
+    def _make(self, r):
+        m = int(r['mask'])
+        return self._type(self._atoms[int(r['i'])], self._atoms[int(r['j'])], [m >> b & 1 for b in range(abi.SIFT_NBITS)],
+                          abi.CLASS_NAMES[(m >> abi.CLASS_SHIFT) & abi.CLASS_MASK], r['dist'])
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self._make(r) for r in self.records[k]]
+        return self._make(self.records[k])
+
+    def __iter__(self):
+        atoms, make = self._atoms, self._type
+        rec = self.records
+        names = abi.CLASS_NAMES
+        dist = rec['dist']
+        for k, (i, j, m) in enumerate(zip(rec['i'].tolist(), rec['j'].tolist(), rec['mask'].tolist())):
+            yield make(atoms[i], atoms[j], [m >> b & 1 for b in range(abi.SIFT_NBITS)],
+                       names[(m >> abi.CLASS_SHIFT) & abi.CLASS_MASK], dist[k])
+
+
+def _host_helpers(obj):
+    """utils.make_pymol_json / utils.get_residue_name of the module the host class comes from (utils.py:530-564,
+    :748-767)."""
+    import sys
+    for klass in type(obj).__mro__:
+        mod = sys.modules.get(klass.__module__)
+        if mod is None:
+            continue
+        for holder in (getattr(mod, 'utils', None), mod):
+            if holder is not None and hasattr(holder, 'make_pymol_json') and hasattr(holder, 'get_residue_name'):
+                return holder.make_pymol_json, holder.get_residue_name
+    raise AttributeError('the host class offers no make_pymol_json / get_residue_name')
+
+
 MAINCHAIN_ATOMS = frozenset(('N', 'C', 'CA', 'O', 'OXT'))          # config.py:35
 
 _RESIDUE_PLANE_SIFTS = (('ring_ring_inter_integer_sift', 9), ('ring_atom_inter_integer_sift', 5),
@@ -115,6 +162,7 @@ class CudaContactsMixin:
     cuda_device = 0
     cuda_engine = None          # set to a private ContactEngine to avoid the shared one
     cuda_atom_sifts = True      # reproduce the per-atom / per-residue SIFt side effects of the loops
+    cuda_lazy_contacts = False  # atom_contacts as a LazyAtomContacts sequence instead of a list of namedtuples
 
     def _cuda_reset_residue_sifts(self, names):
         """The counters start from what _initialize_residue_sift leaves (interactions.py:1869-1883)."""
@@ -160,14 +208,9 @@ class CudaContactsMixin:
             # utils.is_xbond dereferences None when the donor has no single-bond neighbour (utils.py:173)
             raise AttributeError("'NoneType' object has no attribute 'coord'")
         atoms = packed.atoms
-        masks = rec['mask']
-        bits = ((masks[:, None] >> np.arange(abi.SIFT_NBITS, dtype=np.uint32)) & 1).astype(np.int64).tolist()
-        classes = ((masks >> abi.CLASS_SHIFT) & abi.CLASS_MASK).tolist()
-        dist = rec['dist']
-        out = []
-        for k, (i, j) in enumerate(zip(rec['i'].tolist(), rec['j'].tolist())):
-            out.append(AAC(atoms[i], atoms[j], bits[k], abi.CLASS_NAMES[classes[k]], dist[k]))
-        self.atom_contacts = out
+        self._cuda_pair_records = rec
+        lazy = LazyAtomContacts(rec, atoms, AAC)
+        self.atom_contacts = lazy if self.cuda_lazy_contacts else list(lazy)
         if self.cuda_atom_sifts:
             apply_atom_sifts(atoms, eng.atom_sifts())
 
@@ -269,6 +312,39 @@ class CudaContactsMixin:
             self.group_plane_contacts.append(PPC(a['amide_id'], a['residue'], names(a), g['ring_id'], g['residue'], names(g),
                                                  np.float64(r['dist']), ['AMIDERING'],
                                                  abi.CLASS_NAMES[(int(r['code']) >> 8) & 7]))
+
+
+    # ------------------------------------------------------------------
+    def _cuda_json_parts(self, threads=None):
+        rec = getattr(self, '_cuda_pair_records', None)
+        if rec is None or len(self.atom_contacts) != rec.shape[0]:
+            raise RuntimeError('the contact JSON needs the record stream of the last _calculate_atom_contacts')
+        make_json, residue_name = _host_helpers(self)
+        frags = []
+        for atom in self._cuda_packed().atoms:
+            d = make_json(atom)
+            d['label_comp_type'] = self.component_types[residue_name(atom)]
+            frags.append(jsonout.atom_fragment(d))
+        body = jsonout.pairs_json(rec, frags, threads=threads)
+        keep = self.atom_contacts
+        self.atom_contacts = []
+        try:
+            others = self.get_contacts()
+        finally:
+            self.atom_contacts = keep
+        return body, others
+
+    def contacts_json_text(self, threads=None):
+        """The text ``json.dump(self.get_contacts(), fp, indent=4, sort_keys=True)`` writes
+        (process_protein_cli.py:187-188), byte for byte, without a Python dict per atom-atom contact: the records
+        of the last run go through the C emitter, the plane / group entries through the host's own get_contacts."""
+        body, others = self._cuda_json_parts(threads)
+        return jsonout.splice(body, others)
+
+    def write_contacts_json(self, path, threads=None):
+        body, others = self._cuda_json_parts(threads)
+        with open(path, 'wb') as fp:
+            jsonout.write_spliced(fp, body, others)
 
 
 def cuda_interaction_complex(base_cls=None, device=0):

@@ -139,6 +139,41 @@ class CpuPort:
         return sum(counts), time.perf_counter() - t0
 
 
+def json_emitter_leg(records, n_atoms):
+    """SURVEY 8 f2, host side: records -> the text of json.dump(get_contacts(), indent=4, sort_keys=True).
+    C emitter (libarpeggio_cuda.so, arp_pairs_json_write) on all records against the reference's per-contact
+    Python (get_contacts loop, interactions.py:183-196, + json.dumps) on a bounded sample of the same records."""
+    from arpeggio_b200 import abi, jsonout
+    atoms = [{'label_comp_id': 'ALA', 'auth_seq_id': a // 8, 'auth_asym_id': 'A', 'auth_atom_id': f'C{a % 8}',
+              'pdbx_PDB_ins_code': ' ', 'label_comp_type': 'P'} for a in range(n_atoms)]
+    rec = np.array(records)
+    jsonout.pairs_json(rec[:1000], [jsonout.atom_fragment(d) for d in atoms])
+    t0 = time.perf_counter()
+    frags = [jsonout.atom_fragment(d) for d in atoms]          # one rendering per atom is part of the job
+    text = jsonout.pairs_json(rec, frags)
+    dt_c = time.perf_counter() - t0
+    sample = rec[:20000]
+    names = abi.SIFT_NAMES
+    t0 = time.perf_counter()
+    bag = []
+    for r in sample:
+        m = int(r['mask'])
+        sifts = [m >> b & 1 for b in range(15)]
+        e = {'bgn': dict(atoms[int(r['i'])]), 'end': dict(atoms[int(r['j'])]), 'type': 'atom-atom',
+             'distance': round(np.float64(r['dist']), 2), 'contact': [k for k, v in zip(names, sifts) if v == 1],
+             'interacting_entities': abi.CLASS_NAMES[(m >> 16) & 7]}
+        bag.append(e)
+    ref_text = json.dumps(bag, indent=4, sort_keys=True)
+    dt_py = time.perf_counter() - t0
+    ours = bytes(jsonout.pairs_json(sample, frags)).decode()
+    assert '[\n' + ours + '\n]' == ref_text, 'emitter text differs from the Python dump'
+    return {'emitter_pairs_per_s': rec.shape[0] / dt_c, 'emitter_bytes': len(text), 'emitter_s': dt_c,
+            'emitter_threads': min(16, os.cpu_count() or 1),
+            'python_pairs_per_s': sample.shape[0] / dt_py, 'python_sample': int(sample.shape[0]),
+            'what': 'records -> contact JSON text (indent=4, sort_keys): C emitter on all records vs the per-contact Python '
+                    'of get_contacts + json.dumps on a sample; texts compared byte for byte on the sample'}
+
+
 def dist_env():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -267,6 +302,7 @@ def run_ours(args):
         counts, dt_b = runner.run(shard, check_finite=False)
         batch = (len(shard), float(sum(counts)), dt_b)
     runner.close()
+    json_leg = json_emitter_leg(got, args.atoms) if rank == 0 and not args.no_cpu else None
     t_end = time.time()
     clocks = sampler.stop(t_begin, t_end) if sampler else None
 
@@ -309,6 +345,8 @@ def run_ours(args):
             'clocks': clocks,
             'candidate_tests_per_step': int(st['n_candidates']),
         }
+        if json_leg:
+            line['json'] = json_leg
         if batch:
             line['batch'] = {'metric': 'structures/s (configs[4]: PDB-batch of synthetic 20k-atom structures)',
                              'value': batch[0] / batch[2], 'unit': 'structures/s', 'structures': batch[0],

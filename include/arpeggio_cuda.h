@@ -309,6 +309,19 @@ int  arp_amide_ring_fetch(arp_ctx* ctx, arp_plane_pair* dst, uint64_t cap);
 int  arp_atom_sifts_run(arp_ctx* ctx);
 int  arp_atom_sifts_fetch(arp_ctx* ctx, arp_atom_sift* dst, uint64_t cap);
 
+/* ---- contact JSON ------------------------------------------------
+ * Host-side emitter of the atom-atom entries of InteractionComplex.get_contacts (interactions.py:172-196)
+ * exactly as json.dump(contacts, fp, indent=4, sort_keys=True) writes them (process_protein_cli.py:187-188):
+ * entries joined by ",\n", WITHOUT the enclosing "[\n" ... "\n]" (the plane entries follow in the same list).
+ * frag[a] / frag_len[a]: the rendered 'bgn' / 'end' object of atom a (utils.make_pymol_json, utils.py:530-564,
+ * + label_comp_type) as json.dumps leaves it at nesting depth 2, not NUL-terminated.  distance is
+ * float.__repr__(round(np.float64(dist), 2)).  rec: host memory (what arp_pairs_fetch wrote).
+ * threads: host threads to use (>= 1).  No device, no context.                                      */
+int  arp_pairs_json_size(const arp_pair* rec, uint64_t n, int32_t n_atoms, const uint32_t* frag_len, int threads,
+                         uint64_t* bytes);
+int  arp_pairs_json_write(const arp_pair* rec, uint64_t n, int32_t n_atoms, const char* const* frag,
+                          const uint32_t* frag_len, int threads, char* dst, uint64_t cap, uint64_t* written);
+
 /* ---- binding-site expansion -----------------------------------
  * replaces the search_all(6.0) loop of _make_selection (interactions.py:1420-1424):
  * flag[i] = 1 iff atom i is selected or lies within `radius` of a selected atom

@@ -3,6 +3,7 @@ _calculate_ring_contacts, _calculate_group_contacts -> get_contacts) over the CU
 the real reference produced for the same complex (tests/golden/*.npz, `contacts_json`)."""
 import json
 
+import numpy as np
 import pytest
 
 import mock_host
@@ -66,6 +67,30 @@ def test_sift_side_effects_match_reference(engine, case):
             assert got == (e[name] if e else [0] * len(got)), (mockbio.residue_key(r), name)
         seen += e is not None
     assert seen == len(want)
+
+
+@pytest.mark.parametrize('case', [c for c in util.golden_cases() if c != 'xbond_fault'])
+@pytest.mark.parametrize('lazy', [False, True])
+def test_contacts_json_text_is_the_reference_dump(engine, case, lazy, tmp_path):
+    """the file process_protein_cli.py:187-188 writes, byte for byte, from the C emitter; and the lazy
+    atom_contacts sequence behaves like the reference's list."""
+    g = util.Golden(case)
+    host = mock_host.host_from_golden(g)
+    host.cuda_engine = engine
+    host.cuda_lazy_contacts = lazy
+    m = g.meta
+    host.run_arpeggio(m['cutoff'], m['vdw_comp'], m['include_sequence_adjacent'])
+    want = json.dumps(g.contacts_json, indent=4, sort_keys=True)
+    assert host.contacts_json_text() == want
+    assert json.dumps(host.get_contacts(), indent=4, sort_keys=True) == want
+    host.write_contacts_json(tmp_path / 'out.json')
+    assert (tmp_path / 'out.json').read_text() == want
+    ac = host.atom_contacts
+    assert len(ac) == g.exp_pairs.shape[0]
+    if lazy and len(ac):
+        assert ac[0] == list(ac)[0] == ac[0:1][0] and ac[-1] == list(ac)[-1]
+        inter = list(filter(lambda c: c.contact_type == 'INTER', ac))
+        assert len(inter) == int(np.count_nonzero((g.exp_pairs['mask'] >> 16 & 7) == 2))
 
 
 def test_record_types_and_dtypes(engine):

@@ -208,7 +208,7 @@ void arp_destroy(arp_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     DBuf* bufs[] = { &c->xyz, &c->feat, &c->res_id, &c->rad_class, &c->vdw, &c->cov, &c->res_prev, &c->res_next,
                      &c->res_flags, &c->bond_off, &c->bond_nbr, &c->h_off, &c->h_xyz, &c->xnbr, &c->struct_off,
-                     &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->hrng, &c->sift_acc, &c->sift_out, &c->out, &c->hits, &c->work,
+                     &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->hrng, &c->sift_acc, &c->sift_out, &c->ring_scratch, &c->out, &c->hits, &c->work,
                      &c->radtab, &c->sort_tmp, &c->sort_out, &c->sort_zero, &c->sort_off, &c->within, &c->flush };
     for (DBuf* b : bufs) dbuf_free(*b);
     arp_planes_release(c);
@@ -404,6 +404,18 @@ int arp_pairs_device_ptr(arp_ctx* c, const arp_pair** dptr)
     ARP_REQUIRE(c, c->pairs_valid, ARP_E_NOT_READY, "no record stream yet");
     *dptr = c->out.as<arp_pair>();
     return ARP_OK;
+}
+
+int arp_ring_nearest_atom(arp_ctx* c, const float* xyz, int32_t n_atoms, const double* centers, int32_t n_rings,
+                          double radius, int32_t* atom_out, double* dist_out)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_REQUIRE(c, n_atoms >= 0 && n_rings >= 0 && radius >= 0.0, ARP_E_INVALID_ARG, "negative size or radius");
+    if (n_rings == 0) return ARP_OK;
+    ARP_REQUIRE(c, centers && atom_out && dist_out && (xyz || n_atoms == 0), ARP_E_INVALID_ARG, "NULL array");
+    ARP_REQUIRE(c, c->have_params, ARP_E_NOT_READY, "arp_ring_nearest_atom before arp_set_params");
+    ARP_TRY(arp_bind(c));
+    return arp_ring_nearest_run(c, xyz, n_atoms, centers, n_rings, radius, atom_out, dist_out);
 }
 
 int arp_atom_sifts_run(arp_ctx* c)

@@ -136,6 +136,9 @@ struct arp_ctx {
     /* binding-site flags */
     DBuf within;
 
+    /* ring -> nearest atom scratch (coordinates, centroids, results) */
+    DBuf ring_scratch;
+
     /* per-atom SIFt reductions */
     DBuf sift_acc, sift_out;
     int sifts_valid = 0;
@@ -222,6 +225,8 @@ int  arp_pairs_prepare(arp_ctx* c);                       /* arp_pairs.cu: size 
 int  arp_pairs_enqueue(arp_ctx* c, int with_events);
 int  arp_pairs_sorted_build(arp_ctx* c);                  /* arp_pairs.cu: (i, j)-ascending copy of the stream */
 int  arp_flag_within_run(arp_ctx* c, double radius);      /* arp_pairs.cu */
+int  arp_ring_nearest_run(arp_ctx* c, const float* xyz, int n_atoms, const double* centers, int n_rings, double radius,
+                          int32_t* atom_out, double* dist_out);   /* arp_rings.cu */
 int  arp_atom_sifts_enqueue(arp_ctx* c);                  /* arp_sifts.cu: sorted stream -> arp_atom_sift[N] */
 void arp_planes_release(arp_ctx* c);                      /* arp_planes.cu */
 

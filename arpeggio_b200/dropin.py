@@ -196,6 +196,38 @@ class CudaContactsMixin:
                                       contact_types=ct, dist_max=dist_max, h_vdw=h_vdw)
 
     # ------------------------------------------------------------------
+    def _assign_aromatic_rings_to_residues(self):
+        """Replaces interactions.py:1453-1492: the closest atom within 3 A of every ring centroid
+        comes from the GPU (ties: lowest atom index); the bookkeeping on rings and residues is the reference's."""
+        import logging
+        import sys
+        for klass in type(self).__mro__:                 # the reference also leaves a whole-structure search tree
+            mod = sys.modules.get(klass.__module__)
+            ns = getattr(mod, 'NeighborSearch', None) if mod is not None else None
+            if ns is not None:
+                self.ns = ns(self.s_atoms)
+                break
+        rings = self.biopython_str.rings
+        keys = list(rings)
+        if not keys:
+            return
+        atoms = list(self.s_atoms)
+        xyz = np.array([a.coord for a in atoms], dtype=np.float32).reshape(-1, 3)
+        centers = np.array([rings[k]['center'] for k in keys], dtype=np.float64).reshape(-1, 3)
+        eng = self._cuda_engine()
+        nearest, dist = eng.ring_nearest_atom(xyz, centers, 3.0)
+        for k, a, d in zip(keys, nearest.tolist(), dist):
+            if a < 0:
+                logging.warning(f'Residue assignment was not possible for ring {k}.')
+                rings[k]['residue'] = None
+                continue
+            residue = atoms[a].get_parent()
+            rings[k]['residue'] = residue
+            rings[k]['residue_shortest_distance'] = d
+            if not hasattr(residue, 'rings'):
+                residue.rings = []
+            residue.rings.append(k)
+
     def _calculate_atom_contacts(self, interacting_cutoff, vdw_comp_factor, include_sequence_adjacent):
         """Replaces interactions.py:693-936 (neighbour search + per-pair rules) with the CUDA path."""
         AAC, _, _ = _record_types(self)

@@ -171,6 +171,20 @@ class ContactEngine:
         self._check(self._L.arp_atom_sifts_fetch(self._ctx, out.ctypes.data if n else None, n))
         return out
 
+    def ring_nearest_atom(self, xyz, centers, radius=3.0):
+        """(atom index or -1, float64 distance) of the atom closest to every ring centroid within `radius`
+        (_assign_aromatic_rings_to_residues, interactions.py:1453-1492).  xyz: float32[N][3] of the atoms
+        searched (the reference searches s_atoms), centers: float64[R][3]."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        centers = np.ascontiguousarray(centers, dtype=np.float64).reshape(-1, 3)
+        r = centers.shape[0]
+        atom = np.full(r, -1, dtype=np.int32)
+        dist = np.zeros(r, dtype=np.float64)
+        if r:
+            self._check(self._L.arp_ring_nearest_atom(self._ctx, xyz.ctypes.data if xyz.shape[0] else None, xyz.shape[0],
+                                                      centers.ctypes.data, r, float(radius), atom.ctypes.data, dist.ctypes.data))
+        return atom, dist
+
     def flag_within(self, radius):
         """uint8[N]: atom selected or within `radius` of a selected atom (interactions.py:1420-1424)."""
         n = self._soa.n_atoms

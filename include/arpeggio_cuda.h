@@ -309,6 +309,15 @@ int  arp_amide_ring_fetch(arp_ctx* ctx, arp_plane_pair* dst, uint64_t cap);
 int  arp_atom_sifts_run(arp_ctx* ctx);
 int  arp_atom_sifts_fetch(arp_ctx* ctx, arp_atom_sift* dst, uint64_t cap);
 
+/* ---- ring -> residue assignment -----------------------------------
+ * replaces the search of _assign_aromatic_rings_to_residues (interactions.py:1453-1492): for every ring
+ * centroid (double[n_rings][3], OBRing.findCenterAndNormal) the closest atom of xyz (float[n_atoms][3], the
+ * structure's s_atoms) within `radius` as NeighborSearch.search tests it (double, d2 <= r*r), distance =
+ * np.linalg.norm(atom.coord - centroid) in float64; atom_out[r] = -1 when no atom is that close (the reference
+ * then sets ring['residue'] = None).  Ties go to the lowest atom index.  Host pointers; synchronous.          */
+int  arp_ring_nearest_atom(arp_ctx* ctx, const float* xyz, int32_t n_atoms, const double* centers, int32_t n_rings,
+                           double radius, int32_t* atom_out, double* dist_out);
+
 /* ---- contact JSON ------------------------------------------------
  * Host-side emitter of the atom-atom entries of InteractionComplex.get_contacts (interactions.py:172-196)
  * exactly as json.dump(contacts, fp, indent=4, sort_keys=True) writes them (process_protein_cli.py:187-188):

@@ -556,6 +556,30 @@ int orc_atom_sifts(const arp_pair* rec, uint64_t n, int n_atoms, arp_atom_sift* 
     return 0;
 }
 
+/* _assign_aromatic_rings_to_residues (interactions.py:1453-1492): closest atom within `radius` of every ring
+   centroid; NeighborSearch.search restated as a double-precision scan in ascending atom order, the strict `<`
+   of :1471 keeps the first minimum */
+int orc_ring_nearest(const float* xyz, int n_atoms, const double* centers, int n_rings, double radius, int blas_fma,
+                     int32_t* atom_out, double* dist_out)
+{
+    const double r2 = radius * radius;
+    for (int r = 0; r < n_rings; ++r) {
+        const double* c = centers + 3 * (size_t)r;
+        int best_i = -1; double best = 0.0;
+        for (int i = 0; i < n_atoms; ++i) {
+            const float* x = xyz + 3 * (size_t)i;
+            double dv[3] = { (double)x[0] - c[0], (double)x[1] - c[1], (double)x[2] - c[2] };
+            double s = 0.0; s += dv[0] * dv[0]; s += dv[1] * dv[1]; s += dv[2] * dv[2];
+            if (!(s <= r2)) continue;
+            double distance = norm3_f64(dv, blas_fma);                          /* :1469 */
+            if (best_i < 0 || distance < best) { best_i = i; best = distance; } /* :1471 */
+        }
+        atom_out[r] = best_i;
+        dist_out[r] = best_i >= 0 ? best : 0.0;
+    }
+    return 0;
+}
+
 void orc_free(void* p) { free(p); }
 
 /* binding-site expansion of _make_selection (interactions.py:1420-1424) */

@@ -43,6 +43,7 @@ def lib():
         L.orc_atom_ring.argtypes = [C.POINTER(abi.ArpAtoms), C.POINTER(abi.ArpPlanes), C.POINTER(abi.ArpParams),
                                     C.POINTER(vp), u64p]
         L.orc_atom_sifts.argtypes = [vp, C.c_uint64, C.c_int, vp]
+        L.orc_ring_nearest.argtypes = [vp, C.c_int, vp, C.c_int, C.c_double, C.c_int, vp, vp]
         L.orc_free.argtypes = [vp]
         L.orc_free.restype = None
         fp, dp = C.POINTER(C.c_float), C.POINTER(C.c_double)
@@ -110,6 +111,16 @@ def atom_sifts(records, n_atoms):
     _check(lib().orc_atom_sifts(rec.ctypes.data if rec.shape[0] else None, rec.shape[0], int(n_atoms),
                                 out.ctypes.data if n_atoms else None))
     return out
+
+
+def ring_nearest_atom(xyz, centers, radius, params):
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    centers = np.ascontiguousarray(centers, dtype=np.float64).reshape(-1, 3)
+    atom = np.full(centers.shape[0], -1, dtype=np.int32)
+    dist = np.zeros(centers.shape[0], dtype=np.float64)
+    _check(lib().orc_ring_nearest(xyz.ctypes.data, xyz.shape[0], centers.ctypes.data, centers.shape[0], float(radius),
+                                  int(params.blas_fma), atom.ctypes.data, dist.ctypes.data))
+    return atom, dist
 
 
 def flag_within(soa, radius):

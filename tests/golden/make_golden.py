@@ -85,6 +85,35 @@ def mask_of(sifts, text):
     return m | (abi.CLASS_NAMES.index(text) << abi.CLASS_SHIFT)
 
 
+def ring_assignment(kwargs):
+    """The reference's _assign_aromatic_rings_to_residues (interactions.py:1453-1492) on a fresh copy of the
+    complex, plus one ring far from every atom (-> residue None)."""
+    cx = mockbio.build_complex(**kwargs)
+    ic = reference_complex(cx)
+    rings = ic.biopython_str.rings
+    far = max(rings) + 1 if rings else 0
+    rings[far] = {'ring_id': far, 'center': np.array([900.0, -900.0, 900.0]), 'atoms': []}
+    for r in rings.values():
+        r.pop('residue', None)
+        r.pop('residue_shortest_distance', None)
+    for res in ic.biopython_str.get_residues():
+        if hasattr(res, 'rings'):
+            del res.rings
+    ic._assign_aromatic_rings_to_residues()
+    res_index = {id(r): k for k, r in enumerate(ic.biopython_str.get_residues())}
+    keys = list(rings)
+    out = dict(
+        f4_xyz=np.array([a.coord for a in ic.s_atoms], dtype=np.float32).reshape(-1, 3),
+        f4_atom_res=np.array([res_index[id(a.get_parent())] for a in ic.s_atoms], dtype=np.int32),
+        f4_centers=np.array([rings[k]['center'] for k in keys], dtype=np.float64).reshape(-1, 3),
+        f4_ring_res=np.array([res_index[id(rings[k]['residue'])] if rings[k]['residue'] is not None else -1 for k in keys], dtype=np.int32),
+        f4_ring_dist=np.array([rings[k].get('residue_shortest_distance', 0.0) for k in keys], dtype=np.float64))
+    assert out['f4_ring_res'][-1] == -1
+    for k in keys:                                       # the bookkeeping on the residue side (:1488-1491)
+        assert rings[k]['residue'] is None or k in rings[k]['residue'].rings
+    return out
+
+
 def run_case(name, kwargs, selections, cutoff, vdw_comp, incl):
     cx = mockbio.build_complex(**kwargs)
     ic = reference_complex(cx)
@@ -184,7 +213,7 @@ def run_case(name, kwargs, selections, cutoff, vdw_comp, incl):
         amide_center=packed.amides.center, amide_normal=packed.amides.normal, amide_res=packed.amides.res_id,
         amide_flags=packed.amides.flags,
         exp_atom_sifts=atom_sifts, exp_pairs=pairs, exp_ring_ring=rr, exp_atom_ring=ap, exp_amide_amide=aa, exp_amide_ring=ar,
-        meta=np.array(json.dumps(meta)), contacts_json=np.array(contacts_json))
+        meta=np.array(json.dumps(meta)), contacts_json=np.array(contacts_json), **ring_assignment(kwargs))
     np.savez_compressed(os.path.join(HERE, name + '.npz'), **arrays)
     print(f'  {name}: N={len(packed.atoms)} pairs={len(pairs)} ring-ring={len(rr)} atom-ring={len(ap)} '
           f'amide-amide={len(aa)} amide-ring={len(ar)}')

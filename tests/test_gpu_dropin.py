@@ -93,6 +93,33 @@ def test_contacts_json_text_is_the_reference_dump(engine, case, lazy, tmp_path):
         assert len(inter) == int(np.count_nonzero((g.exp_pairs['mask'] >> 16 & 7) == 2))
 
 
+@pytest.mark.parametrize('case', util.golden_cases())
+def test_ring_assignment_through_the_dropin(engine, case):
+    """_assign_aromatic_rings_to_residues of the mixin leaves the rings and residues as the
+    reference's function did (tests/golden: f4_*), including a ring with no atom within 3 A."""
+    g = util.Golden(case)
+    host = mock_host.host_from_golden(g)
+    host.cuda_engine = engine
+    rings = host.biopython_str.rings
+    far = max(rings) + 1 if rings else 0
+    rings[far] = {'ring_id': far, 'center': np.array([900.0, -900.0, 900.0]), 'atoms': []}
+    for r in rings.values():
+        r.pop('residue', None)
+        r.pop('residue_shortest_distance', None)
+    residues = list(host.biopython_str.get_residues())
+    for res in residues:
+        res.__dict__.pop('rings', None)
+    host._assign_aromatic_rings_to_residues()
+    index = {id(r): k for k, r in enumerate(residues)}
+    got_res = [index[id(rings[k]['residue'])] if rings[k]['residue'] is not None else -1 for k in rings]
+    assert got_res == g.f4['ring_res'].tolist()
+    got_dist = np.array([rings[k].get('residue_shortest_distance', 0.0) for k in rings])
+    assert np.array_equal(got_dist.view(np.uint64), g.f4['ring_dist'].view(np.uint64))
+    for k in rings:
+        assert rings[k]['residue'] is None or k in rings[k]['residue'].rings
+    assert isinstance(host.ns, type(host.ns)) and len(host.ns.atom_list) == len(host.s_atoms)
+
+
 def test_record_types_and_dtypes(engine):
     import numpy as np
     g = util.Golden('ligand_site')

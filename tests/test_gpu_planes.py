@@ -83,3 +83,39 @@ def test_empty_planes(engine):
     assert engine.ring_ring().shape[0] == 0
     assert engine.amide_amide().shape[0] == 0
     assert engine.amide_ring().shape[0] == 0
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_ring_assignment_golden(engine, case):
+    """ring -> residue assignment as the reference's own function left it."""
+    g = util.Golden(case)
+    engine.set_params(g.params)
+    f = g.f4
+    atom, dist = engine.ring_nearest_atom(f['xyz'], f['centers'], 3.0)
+    res = np.where(atom >= 0, f['atom_res'][np.maximum(atom, 0)], -1)
+    assert np.array_equal(res, f['ring_res'])
+    assert np.array_equal(dist.view(np.uint64), f['ring_dist'].view(np.uint64))
+    o_atom, o_dist = oracle.ring_nearest_atom(f['xyz'], f['centers'], 3.0, g.params)
+    assert np.array_equal(atom, o_atom) and np.array_equal(dist.view(np.uint64), o_dist.view(np.uint64))
+
+
+def test_ring_assignment_large_and_edges(engine):
+    p = arp_params.make_params()
+    engine.set_params(p)
+    soa = synth.cloud_featured(100_000, seed=2)
+    rings, _ = synth.plane_set(2048, 8, n_atoms=100_000, seed=3)
+    for radius in (3.0, 0.9, 0.0):
+        atom, dist = engine.ring_nearest_atom(soa.xyz, rings.center, radius)
+        o_atom, o_dist = oracle.ring_nearest_atom(soa.xyz, rings.center, radius, p)
+        assert np.array_equal(atom, o_atom) and np.array_equal(dist.view(np.uint64), o_dist.view(np.uint64))
+    assert (atom == -1).any()
+    # exact ties: two atoms mirror-symmetric about the centroid -> lowest index; duplicates of one atom
+    xyz = np.array([[1, 0, 0], [-1, 0, 0], [0, 2, 0], [0, 2, 0], [50, 50, 50]], np.float32)
+    centers = np.array([[0, 0, 0], [0, 2.5, 0], [50, 50, 53.0000001], [50, 50, 53]], np.float64)
+    atom, dist = engine.ring_nearest_atom(xyz, centers, 3.0)
+    assert atom.tolist() == [0, 2, -1, 4] and dist.tolist() == [1.0, 0.5, 0.0, 3.0]
+    # no atoms / no rings
+    a, d = engine.ring_nearest_atom(np.zeros((0, 3), np.float32), centers, 3.0)
+    assert a.tolist() == [-1] * 4
+    a, d = engine.ring_nearest_atom(xyz, np.zeros((0, 3)), 3.0)
+    assert a.shape == (0,)

@@ -56,3 +56,16 @@ def test_atom_sifts_match_reference(case):
     # the integer SIFt is not the plain count-capped OR: the last contact decides (utils.py:233)
     two = (got['integer_sift'][:, 0][:, None] >> (2 * np.arange(15)) & 3) == 2
     assert two.any()
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_ring_assignment_matches_reference(case):
+    """_assign_aromatic_rings_to_residues (interactions.py:1453-1492): residue of the closest atom within 3 A of
+    every ring centroid and that distance, float64 bits; rings with no atom nearby get None."""
+    g = util.Golden(case)
+    f = g.f4
+    atom, dist = oracle.ring_nearest_atom(f['xyz'], f['centers'], 3.0, g.params)
+    res = np.where(atom >= 0, f['atom_res'][np.maximum(atom, 0)], -1)
+    assert np.array_equal(res, f['ring_res'])
+    assert np.array_equal(dist.view(np.uint64), f['ring_dist'].view(np.uint64))
+    assert (atom[-1] == -1) and (atom >= 0).any()

@@ -29,6 +29,7 @@ class Golden:
         self.rings = PlaneSoA(z['ring_center'], z['ring_normal'], z['ring_res'], z['ring_flags'], False)
         self.amides = PlaneSoA(z['amide_center'], z['amide_normal'], z['amide_res'], z['amide_flags'], True)
         self.exp_atom_sifts = z['exp_atom_sifts']
+        self.f4 = {k: z['f4_' + k] for k in ('xyz', 'atom_res', 'centers', 'ring_res', 'ring_dist')}
         self.exp_pairs = z['exp_pairs']
         self.exp_ring_ring = z['exp_ring_ring']
         self.exp_atom_ring = z['exp_atom_ring']

@@ -196,6 +196,61 @@ class CudaContactsMixin:
                                       contact_types=ct, dist_max=dist_max, h_vdw=h_vdw)
 
     # ------------------------------------------------------------------
+    def _cuda_parse_selection(self, selections, entity):
+        """utils.selection_parser of the host module (interactions.py:1396)."""
+        import sys
+        for klass in type(self).__mro__:
+            mod = sys.modules.get(klass.__module__)
+            utils = getattr(mod, 'utils', None) if mod is not None else None
+            if utils is not None and hasattr(utils, 'selection_parser'):
+                return utils.selection_parser(selections, entity)
+        raise AttributeError('the host class offers no utils.selection_parser')
+
+    def _make_selection(self, selections):
+        """Replaces interactions.py:1384-1451: the binding-site expansion -- every atom within 6 A of
+        a selected atom -- is one GPU pass (``arp_flag_within``) instead of ``search_all(6.0)`` over the whole
+        structure with a Python tuple per pair.  The bookkeeping (residue / ring / amide id sets) follows the
+        reference.  ``selection_plus`` keeps the reference's construction, ``list(set(...))``: like there, its
+        order is whatever the set yields."""
+        import logging
+        import sys
+        from .soa import AtomSoA
+        entity = list(self.s_atoms)
+        selection = entity if not selections else self._cuda_parse_selection(selections, entity)
+        if not selection:
+            logging.error('Selection was empty.')
+            raise AttributeError('Selection must not be empty.')
+        rings, amides = self.biopython_str.rings, self.biopython_str.amides
+        selection_set = set(selection)
+        n = len(entity)
+        feat = np.zeros(n, dtype=np.uint32)
+        feat[[k for k, a in enumerate(entity) if a in selection_set]] = abi.F_IN_SELECTION
+        soa = AtomSoA(xyz=np.array([a.coord for a in entity], dtype=np.float32).reshape(-1, 3), feat=feat,
+                      res_id=np.zeros(n, np.int32), rad_class=np.zeros(n, np.uint16), vdw=np.ones(1), cov=np.ones(1),
+                      res_prev=np.full(1, -1, np.int32), res_next=np.full(1, -1, np.int32), res_flags=np.zeros(1, np.uint8))
+        eng = self._cuda_engine()
+        eng.upload_atoms(soa)
+        near = eng.flag_within(6.0)
+        selection_plus = set(selection)
+        selection_plus.update(a for a, f in zip(entity, near.tolist()) if f)
+        selection_plus = list(selection_plus)
+
+        selection_residues = {a.get_parent() for a in selection}
+        selection_plus_residues = {a.get_parent() for a in selection_plus}
+        self.selection = selection
+        self.selection_ring_ids = {k for k in rings if rings[k]['residue'] in selection_residues}
+        self.selection_amide_ids = {k for k in amides if amides[k]['residue'] in selection_residues}
+        self.selection_plus = selection_plus
+        self.selection_plus_residues = selection_plus_residues
+        self.selection_plus_ring_ids = {k for k in rings if rings[k]['residue'] in selection_plus_residues}
+        self.selection_plus_amide_ids = {k for k in amides if amides[k]['residue'] in selection_plus_residues}
+        for klass in type(self).__mro__:                 # the reference leaves a search tree over selection_plus
+            mod = sys.modules.get(klass.__module__)
+            ns = getattr(mod, 'NeighborSearch', None) if mod is not None else None
+            if ns is not None:
+                self.ns = ns(selection_plus)
+                break
+
     def _assign_aromatic_rings_to_residues(self):
         """Replaces interactions.py:1453-1492: the closest atom within 3 A of every ring centroid
         comes from the GPU (ties: lowest atom index); the bookkeeping on rings and residues is the reference's."""

@@ -120,6 +120,35 @@ def test_ring_assignment_through_the_dropin(engine, case):
     assert isinstance(host.ns, type(host.ns)) and len(host.ns.atom_list) == len(host.s_atoms)
 
 
+@pytest.mark.parametrize('case', util.golden_cases())
+def test_make_selection_through_the_dropin(engine, case):
+    """the binding-site expansion of _make_selection (interactions.py:1420-1424) from the GPU flags gives
+    the reference's selection_plus (as a set: its list order is a set's iteration order there too) and id sets."""
+    g = util.Golden(case)
+    host = mock_host.host_from_golden(g)
+    host.cuda_engine = engine
+    m = g.meta
+    by_serial = {a.serial_number: a for a in host.s_atoms}
+    want_sel = [by_serial[s] for s in m['selection_serials']]
+    host._cuda_parse_selection = lambda selections, entity: list(want_sel)
+    for name in ('selection', 'selection_plus', 'selection_ring_ids', 'selection_plus_ring_ids', 'selection_amide_ids',
+                 'selection_plus_amide_ids'):
+        host.__dict__.pop(name, None)
+    host._make_selection(m['selections'] or ['x'])
+    assert [a.serial_number for a in host.selection] == m['selection_serials']
+    assert len(host.selection_plus) == len(m['selection_plus_serials'])
+    assert {a.serial_number for a in host.selection_plus} == set(m['selection_plus_serials'])
+    assert sorted(host.selection_ring_ids) == m['selection_ring_ids']
+    assert sorted(host.selection_plus_ring_ids) == m['selection_plus_ring_ids']
+    assert sorted(host.selection_amide_ids) == m['selection_amide_ids']
+    assert sorted(host.selection_plus_amide_ids) == m['selection_plus_amide_ids']
+    assert host.selection_plus_residues == {a.get_parent() for a in host.selection_plus}
+    assert len(host.ns.atom_list) == len(host.selection_plus)
+    with pytest.raises(AttributeError):
+        host._cuda_parse_selection = lambda selections, entity: []
+        host._make_selection(['nothing'])
+
+
 def test_record_types_and_dtypes(engine):
     import numpy as np
     g = util.Golden('ligand_site')

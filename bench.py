@@ -241,11 +241,11 @@ def run_ours(args):
     t_begin = time.time()
     ms_step = eng.time_pairs(args.steps, flush_l2=True)          # mean per-step CUDA-event time
     eng.sync()
+    st = eng.stats()                                             # the split of the timed steps (before the next run resets it)
     l0 = eng.launch_count()
     eng.run_pairs()                                              # kernels of one step, counted by the library
     per_step = eng.launch_count() - l0
     launches = per_step * args.steps                             # the timed steps (the 32 split-timing steps not counted)
-    st = eng.stats()
     if dist:
         dist.barrier()
 

@@ -38,7 +38,7 @@ def shard_indices(sizes, world_size, rank):
 class BatchRunner:
     """`slots` ContactEngines on one device, driven by `slots` worker threads."""
 
-    def __init__(self, device=0, slots=3, params=None):
+    def __init__(self, device=0, slots=6, params=None):
         self.device = device
         self.engines = [ContactEngine(device, params) for _ in range(max(1, slots))]
         self._pins = [None] * len(self.engines)

@@ -208,7 +208,7 @@ void arp_destroy(arp_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     DBuf* bufs[] = { &c->xyz, &c->feat, &c->res_id, &c->rad_class, &c->vdw, &c->cov, &c->res_prev, &c->res_next,
                      &c->res_flags, &c->bond_off, &c->bond_nbr, &c->h_off, &c->h_xyz, &c->xnbr, &c->struct_off,
-                     &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->hrng, &c->sift_acc, &c->sift_out, &c->ring_scratch, &c->out, &c->hits, &c->work,
+                     &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->hrng, &c->sift_acc, &c->sift_out, &c->ring_scratch, &c->hreach, &c->arena, &c->out, &c->hits, &c->work,
                      &c->radtab, &c->sort_tmp, &c->sort_out, &c->sort_zero, &c->sort_off, &c->within, &c->flush };
     for (DBuf* b : bufs) dbuf_free(*b);
     arp_planes_release(c);
@@ -288,25 +288,68 @@ int arp_upload_atoms(arp_ctx* c, const arp_atoms* a)
     ARP_REQUIRE(c, c->E == 0 || a->bond_nbr, ARP_E_INVALID_ARG, "bond_nbr is NULL");
     ARP_REQUIRE(c, c->H == 0 || a->h_xyz, ARP_E_INVALID_ARG, "h_xyz is NULL");
     const size_t n = (size_t)N;
-    ARP_TRY(upload(c, c->xyz, a->xyz, n * 12));
-    ARP_TRY(upload(c, c->feat, a->feat, n * 4));
-    ARP_TRY(upload(c, c->res_id, a->res_id, n * 4));
-    ARP_TRY(upload(c, c->rad_class, a->rad_class, n * 2));
-    ARP_TRY(upload(c, c->vdw, a->vdw, (size_t)c->K * 8));
-    ARP_TRY(upload(c, c->cov, a->cov, (size_t)c->K * 8));
-    ARP_TRY(upload(c, c->res_prev, a->res_prev, (size_t)c->Rs * 4));
-    ARP_TRY(upload(c, c->res_next, a->res_next, (size_t)c->Rs * 4));
-    ARP_TRY(upload(c, c->res_flags, a->res_flags, (size_t)c->Rs));
+    struct Piece { DBuf* dst; const void* src; size_t bytes; };
+    Piece pieces[15];
+    int np = 0;
+    auto piece = [&](DBuf& d, const void* src, size_t bytes) { pieces[np++] = Piece{ &d, src, bytes }; };
+    piece(c->xyz, a->xyz, n * 12);
+    piece(c->feat, a->feat, n * 4);
+    piece(c->res_id, a->res_id, n * 4);
+    piece(c->rad_class, a->rad_class, n * 2);
+    piece(c->vdw, a->vdw, (size_t)c->K * 8);
+    piece(c->cov, a->cov, (size_t)c->K * 8);
+    piece(c->res_prev, a->res_prev, (size_t)c->Rs * 4);
+    piece(c->res_next, a->res_next, (size_t)c->Rs * 4);
+    piece(c->res_flags, a->res_flags, (size_t)c->Rs);
     if (c->has_bonds) {
-        ARP_TRY(upload(c, c->bond_off, a->bond_off, (n + 1) * 4));
-        ARP_TRY(upload(c, c->bond_nbr, a->bond_nbr, (size_t)c->E * 4));
+        piece(c->bond_off, a->bond_off, (n + 1) * 4);
+        piece(c->bond_nbr, a->bond_nbr, (size_t)c->E * 4);
     }
     if (c->has_h) {
-        ARP_TRY(upload(c, c->h_off, a->h_off, (n + 1) * 4));
-        ARP_TRY(upload(c, c->h_xyz, a->h_xyz, (size_t)c->H * 24));
+        piece(c->h_off, a->h_off, (n + 1) * 4);
+        piece(c->h_xyz, a->h_xyz, (size_t)c->H * 24);
     }
-    if (c->has_xnbr) ARP_TRY(upload(c, c->xnbr, a->xnbr_xyz, n * 12));
-    if (S > 1) ARP_TRY(upload(c, c->struct_off, a->struct_off, (size_t)(S + 1) * 4));
+    if (c->has_xnbr) piece(c->xnbr, a->xnbr_xyz, n * 12);
+    if (S > 1) piece(c->struct_off, a->struct_off, (size_t)(S + 1) * 4);
+    /* One host block (e.g. engine.pinned_soa: every array at a 256-byte offset of one pinned allocation) goes up in
+       ONE copy and the device arrays become views of the arena: 14 small DMA transfers cost about 110 us for a
+       20k-atom structure, one transfer of the same 1.4 MB about 35 us.  Otherwise one copy per array. */
+    uintptr_t lo = UINTPTR_MAX, hi = 0;
+    size_t sum = 0;
+    bool packed = N > 0;
+    for (int k = 0; k < np; ++k) {
+        if (!pieces[k].bytes) continue;
+        const uintptr_t p0 = (uintptr_t)pieces[k].src;
+        lo = p0 < lo ? p0 : lo;
+        hi = p0 + pieces[k].bytes > hi ? p0 + pieces[k].bytes : hi;
+        sum += pieces[k].bytes;
+    }
+    for (int k = 0; k < np && packed; ++k)
+        if (pieces[k].bytes && ((uintptr_t)pieces[k].src - lo) % 16 != 0) packed = false;
+    if (packed && (hi - lo) > sum + 512 * (size_t)np) packed = false;          /* gaps beyond alignment padding */
+    for (int k = 0; k < np && packed; ++k)                                      /* no overlaps: aliasing arrays stay separate */
+        for (int j = 0; j < k; ++j) {
+            const uintptr_t a0 = (uintptr_t)pieces[k].src, a1 = a0 + pieces[k].bytes;
+            const uintptr_t b0 = (uintptr_t)pieces[j].src, b1 = b0 + pieces[j].bytes;
+            if (pieces[k].bytes && pieces[j].bytes && a0 < b1 && b0 < a1) packed = false;
+        }
+    if (packed) {
+        ARP_TRY(dbuf_reserve(c, c->arena, hi - lo));
+        ARP_CUDA(c, cudaMemcpyAsync(c->arena.p, (const void*)lo, hi - lo, cudaMemcpyHostToDevice, c->stream));
+        for (int k = 0; k < np; ++k) {
+            DBuf& d = *pieces[k].dst;
+            dbuf_free(d);
+            if (pieces[k].bytes) {
+                d.p = c->arena.as<char>() + ((uintptr_t)pieces[k].src - lo);
+                d.view = true;
+            } else {
+                ARP_TRY(dbuf_reserve(c, d, 0));          /* kernels may form (never dereference) the address */
+            }
+        }
+        c->input_bytes = sum;
+    } else {
+        for (int k = 0; k < np; ++k) ARP_TRY(upload(c, *pieces[k].dst, pieces[k].src, pieces[k].bytes));
+    }
     ARP_TRY(arp_pairs_prepare(c));
     c->have_atoms = 1;
     return ARP_OK;

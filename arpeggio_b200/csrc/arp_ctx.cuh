@@ -19,6 +19,7 @@
 struct DBuf {
     void*  p = nullptr;
     size_t cap = 0;
+    bool   view = false;       /* p points into another allocation (the upload arena): never freed, never grown in place */
     template <class T> T* as() const { return (T*)p; }
 };
 
@@ -99,6 +100,7 @@ struct arp_ctx {
     int have_atoms = 0;
     DBuf xyz, feat, res_id, rad_class, vdw, cov, res_prev, res_next, res_flags;
     DBuf bond_off, bond_nbr, h_off, h_xyz, xnbr, struct_off;
+    DBuf arena;                   /* one block for all of the above when the caller's arrays are one host block */
     int has_bonds = 0, has_h = 0, has_xnbr = 0;
     uint64_t input_bytes = 0;
 
@@ -108,6 +110,8 @@ struct arp_ctx {
     size_t cell_bound = 0;        /* upper bound of the number of cells, all structures */
     DBuf geom, cell_start, cell_of, rank, pos4, att4, hrng;
     DBuf radtab;                  /* K x K float32 proximity thresholds */
+    DBuf hreach;                  /* upload generation << 32 | float bits of the longest donor-hydrogen distance */
+    unsigned upload_gen = 0;
     int radtab_valid = 0;
     int cls_smem_set = 0;
     int hscan_blocks = 0;         /* co-resident blocks of k_hscan (probed once) */
@@ -186,6 +190,7 @@ static inline int arp_fail(arp_ctx* c, int code, const char* what, const char* f
 
 static inline int dbuf_reserve(arp_ctx* c, DBuf& b, size_t bytes)
 {
+    if (b.view) { b.p = nullptr; b.cap = 0; b.view = false; }
     if (bytes <= b.cap && b.p) return ARP_OK;
     if (bytes == 0) bytes = 16;
     size_t want = bytes + bytes / 8 + 256;
@@ -207,8 +212,8 @@ static inline int dbuf_reserve(arp_ctx* c, DBuf& b, size_t bytes)
 
 static inline void dbuf_free(DBuf& b)
 {
-    if (b.p) cudaFree(b.p);
-    b.p = nullptr; b.cap = 0;
+    if (b.p && !b.view) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0; b.view = false;
 }
 
 static inline int arp_bind(arp_ctx* c)

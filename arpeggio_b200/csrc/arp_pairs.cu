@@ -812,6 +812,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
 #define CLS_SMEM    (CLS_WARPS * CLS_SMEM_PER_WARP)
 
 struct ClassifyArgs {
+    const unsigned long long* h_reach;      /* upload generation << 32 | float bits of the longest donor-hydrogen distance (k_hreach) */
+    unsigned      h_gen;                    /* generation of the current upload */
     const float4* pos4;
     const uint4*  att4;
     const uint2*  raw;
@@ -867,12 +869,23 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
     /* small radius tables live in shared memory: one dependent global load less per pair */
     __shared__ float4 s_radtab[CLS_TAB_K * CLS_TAB_K];
     __shared__ double s_vdw[CLS_TAB_K];
+    __shared__ float s_hlim[CLS_TAB_K];
+    A.side.hlim = nullptr;
     if (A.side.K <= CLS_TAB_K) {
         for (int k = threadIdx.x; k < A.side.K * A.side.K; k += blockDim.x) s_radtab[k] = A.side.radtab[k];
-        for (int k = threadIdx.x; k < A.side.K; k += blockDim.x) s_vdw[k] = A.side.vdw[k];
+        for (int k = threadIdx.x; k < A.side.K; k += blockDim.x) {
+            s_vdw[k] = A.side.vdw[k];
+            /* donor farther than this from an acceptor of class k: none of its hydrogens can be within
+               h_vdw + vdw_k + comp (utils.py:89, :149) of it; generous rounding margin on top */
+            const unsigned long long hr = *A.h_reach;     /* an older generation: this upload has no hydrogens at all */
+            const float reach = (unsigned)(hr >> 32) == A.h_gen ? __uint_as_float((unsigned)hr) : __int_as_float(0xff800000);
+            const double lim = (double)reach + P.h_vdw + A.side.vdw[k] + P.vdw_comp;
+            s_hlim[k] = lim == lim ? __double2float_ru(lim) * 1.000001f + 2e-3f : __int_as_float(0x7f800000);
+        }
         __syncthreads();
         A.side.radtab = s_radtab;
         A.side.vdw = s_vdw;
+        A.side.hlim = s_hlim;
     }
     pdl_wait();                                                  /* k_search has completed */
     pdl_trigger();
@@ -1055,6 +1068,30 @@ __global__ void __launch_bounds__(HSCAN_WARPS * 32, HSCAN_MINB) k_hscan(HscanArg
     }
 }
 
+/* longest donor-hydrogen distance of the upload (float, rounded up; +inf when a distance is not finite).
+   *reach = upload generation << 32 | float bits: non-negative floats order like their bit patterns and a newer
+   generation beats every older value, so the word never needs resetting */
+__global__ void __launch_bounds__(256) k_hreach(int N, const float* __restrict__ xyz, const int32_t* __restrict__ h_off,
+                                                const double* __restrict__ h_xyz, unsigned long long* __restrict__ reach,
+                                                unsigned gen)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float m = -1.f;
+    if (i < N) {
+        const double x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
+        for (int k = h_off[i]; k < h_off[i + 1]; ++k) {
+            const double dx = h_xyz[3 * (size_t)k] - x, dy = h_xyz[3 * (size_t)k + 1] - y, dz = h_xyz[3 * (size_t)k + 2] - z;
+            const double d = sqrt(dx * dx + dy * dy + dz * dz);
+            float f = __double2float_ru(d);
+            if (!(f < 3.0e38f)) f = __int_as_float(0x7f800000);
+            m = fmaxf(m, f);
+        }
+    }
+    int key = m < 0.f ? -1 : __float_as_int(m);
+    key = __reduce_max_sync(FULL, key);
+    if ((threadIdx.x & 31) == 0 && key >= 0) atomicMax(reach, ((unsigned long long)gen << 32) | (unsigned)key);
+}
+
 /* K x K table of the float32 proximity thresholds (interactions.py:717-718, :760-768): NumPy narrows
    the python-float sums to float32 before comparing with the float32 distance (NEP 50) */
 __global__ void k_radtab(int K, const double* __restrict__ vdw, const double* __restrict__ cov, double comp,
@@ -1089,6 +1126,18 @@ int arp_pairs_prepare(arp_ctx* c)
     ARP_TRY(dbuf_reserve(c, c->pos4, sizeof(float4) * N));
     ARP_TRY(dbuf_reserve(c, c->att4, sizeof(uint4) * N));
     ARP_TRY(dbuf_reserve(c, c->hrng, sizeof(int2) * N));
+    /* longest donor-hydrogen distance: a property of the uploaded atoms, computed once per upload */
+    if (!c->hreach.p) {
+        ARP_TRY(dbuf_reserve(c, c->hreach, 16));
+        ARP_CUDA(c, cudaMemsetAsync(c->hreach.p, 0, 16, c->stream));
+    }
+    c->upload_gen++;
+    if (c->has_h && N > 0 && c->H > 0) {
+        k_hreach<<<(unsigned)((N + 255) / 256), 256, 0, c->stream>>>((int)N, c->xyz.as<float>(), c->h_off.as<int32_t>(),
+                                                                      c->h_xyz.as<double>(), c->hreach.as<unsigned long long>(),
+                                                                      c->upload_gen);
+        ARP_LAUNCHED(c);
+    }
     return ARP_OK;
 }
 
@@ -1192,6 +1241,7 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         side.h_off = c->has_h ? c->h_off.as<int32_t>() : nullptr;
         side.h_xyz = c->has_h ? c->h_xyz.as<double>() : nullptr;
         side.xnbr = c->has_xnbr ? c->xnbr.as<float>() : nullptr;
+        side.hlim = nullptr;                 /* k_classify builds it in shared memory */
 
         SearchArgs SA;
         SA.pos4 = c->pos4.as<float4>(); SA.cell_start = c->cell_start.as<int>();
@@ -1205,6 +1255,7 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         if (split_events) ARP_CUDA(c, cudaEventRecord(c->ev[2], st));
 
         ClassifyArgs CA;
+        CA.h_reach = c->hreach.as<unsigned long long>(); CA.h_gen = c->upload_gen;
         CA.pos4 = SA.pos4; CA.att4 = c->att4.as<uint4>(); CA.raw = SA.raw; CA.meta = meta;
         CA.out = c->out.as<arp_pair>(); CA.cap = c->out_cap; CA.side = side;
         CA.work = c->work.as<uint4>(); CA.work_cap = c->work_cap;

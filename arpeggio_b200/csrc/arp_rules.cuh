@@ -112,6 +112,9 @@ struct ArpSide {               /* side arrays, original atom order (device point
     const int32_t*  h_off;     /* [N+1] or null */
     const double*   h_xyz;     /* [H][3] */
     const float*    xnbr;      /* [N][3] or null */
+    const float*    hlim;      /* [K] or null: no hydrogen of ANY atom lies within utils.py:89's limit of an acceptor of
+                                  radius class k once the donor is farther than hlim[k] (triangle inequality over the
+                                  longest donor-hydrogen distance of the upload, rounded up) */
 };
 
 struct ArpRuleParams {         /* arp_params narrowed the way NumPy (NEP 50) narrows it */
@@ -554,6 +557,11 @@ ARP_HD void rule_classify_core(const ArpSide& S, const ArpRuleParams& P, int b, 
         /* xbond :889-895 */
         if (in_vdwc && (X & (3u << 22))) work |= ARP_XB(23) ? ARP_WORK_XB0 : ARP_WORK_XB1;
         /* ionic :898-904, carbonyl :907-913, aromatic :916-917, hydrophobic :920-921 */
+        /* hydrogen scans that cannot succeed are not scheduled: |H - acceptor| >= d - |donor - H| > limit */
+        if (S.hlim && (work & 0x3Fu)) {
+            if (d > S.hlim[we & ARPK_RAD_MASK]) work &= ~(ARP_WORK_SCAN0 | ARP_WORK_HAL0);   /* acceptor / halogen = end */
+            if (d > S.hlim[wb & ARPK_RAD_MASK]) work &= ~(ARP_WORK_SCAN1 | ARP_WORK_HAL1);   /* acceptor / halogen = bgn */
+        }
         if (d <= P.ionic) m |= (ARP_XB(24) | ARP_XB(25)) << ARP_SIFT_IONIC;
         if (d <= P.carbonyl) m |= (ARP_XB(26) | ARP_XB(27)) << ARP_SIFT_CARBONYL;
         if (d <= P.aromatic) m |= ((Y >> 15) & 1u) << ARP_SIFT_AROMATIC;

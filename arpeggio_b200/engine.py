@@ -54,6 +54,32 @@ class PinnedBuffer:
             pass
 
 
+def pinned_soa(soa):
+    """A copy of an AtomSoA in ONE block of page-locked host memory (arp_host_alloc), every array at a 256-byte
+    offset: arp_upload_atoms then moves the whole structure with a single asynchronous DMA (one transfer instead of
+    fourteen) and the device arrays are views of one arena.  The returned object keeps the block alive (``_keep``)."""
+    from .soa import AtomSoA
+    names = ('xyz', 'feat', 'res_id', 'rad_class', 'vdw', 'cov', 'res_prev', 'res_next', 'res_flags',
+             'bond_off', 'bond_nbr', 'h_off', 'h_xyz', 'xnbr_xyz', 'struct_off')
+    arrays = [(k, getattr(soa, k, None)) for k in names]
+    offsets, total = {}, 0
+    for k, a in arrays:
+        if a is not None:
+            offsets[k] = total
+            total += (a.nbytes + 255) // 256 * 256
+    block = PinnedBuffer(max(total, 256))
+    raw = block.array(np.uint8)
+    fields = {}
+    for k, a in arrays:
+        if a is None:
+            fields[k] = None
+            continue
+        v = raw[offsets[k]:offsets[k] + a.nbytes].view(a.dtype).reshape(a.shape)
+        v[...] = a
+        fields[k] = v
+    return AtomSoA(**fields, _keep=[block])
+
+
 class ContactEngine:
     def __init__(self, device=0, params=None):
         self._L = lib()

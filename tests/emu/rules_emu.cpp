@@ -17,7 +17,25 @@ extern "C" int emu_classify(const arp_atoms* A, const arp_params* P, const int32
     S.feat = A->feat;
     S.bond_off = A->bond_off; S.bond_nbr = A->bond_nbr; S.h_off = A->h_off; S.h_xyz = A->h_xyz; S.xnbr = A->xnbr_xyz;
     float4* tab = 0;
-    (void)use_table;
+    /* use_table != 0: also the hydrogen-reach screen of k_classify (S.hlim), built as k_hreach + the kernel prologue do */
+    float* hlim = 0;
+    if (use_table) {
+        float reach = -INFINITY;
+        for (int a = 0; A->h_off && a < A->n_atoms; ++a)
+            for (int k = A->h_off[a]; k < A->h_off[a + 1]; ++k) {
+                double dx = A->h_xyz[3 * (size_t)k] - A->xyz[3 * (size_t)a], dy = A->h_xyz[3 * (size_t)k + 1] - A->xyz[3 * (size_t)a + 1],
+                       dz = A->h_xyz[3 * (size_t)k + 2] - A->xyz[3 * (size_t)a + 2];
+                float f = nextafterf((float)sqrt(dx * dx + dy * dy + dz * dz), INFINITY);
+                if (!(f < 3.0e38f)) f = INFINITY;
+                if (f > reach) reach = f;
+            }
+        hlim = new float[S.K];
+        for (int k = 0; k < S.K; ++k) {
+            double lim = (double)reach + R.h_vdw + A->vdw[k] + R.vdw_comp;
+            hlim[k] = lim == lim ? nextafterf((float)lim, INFINITY) * 1.000001f + 2e-3f : INFINITY;
+        }
+        S.hlim = hlim;
+    }
     {
         int K = S.K;
         tab = new float4[(size_t)K * K];
@@ -44,5 +62,6 @@ extern "C" int emu_classify(const arp_atoms* A, const arp_params* P, const int32
         rule_classify(S, R, i, j, pb[0], pb[1], pb[2], pe[0], pe[1], pe[2], fb, fe, &out[k].mask, &out[k].dist);
     }
     delete[] tab;
+    delete[] hlim;
     return 0;
 }

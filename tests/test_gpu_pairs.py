@@ -209,6 +209,26 @@ def test_atom_sifts_full_size(engine):
     assert z.shape == (3,) and not z['sift'].any() and not z['integer_sift'].any()
 
 
+def test_single_block_upload_equals_per_array_upload(engine):
+    """engine.pinned_soa lays a structure out as one pinned block that goes up in one DMA (device arrays = views of
+    an arena); results must not depend on the upload path, also when the two alternate or the arena has to grow."""
+    from arpeggio_b200.engine import pinned_soa
+    p = arp_params.make_params()
+    engine.set_params(p)
+    small, big = synth.cloud_featured(3000, seed=81), synth.cloud_featured(40_000, seed=82)
+    parts = [synth.cloud_featured(n, seed=90 + k) for k, n in enumerate((2000, 5, 1200))]
+    batch = AtomSoA.concat(parts)
+    exp = {id(s): oracle.pairs(s, p) for s in (small, big, batch)}
+    for soa in (small, pinned_soa(small), pinned_soa(big), small, pinned_soa(batch), big, pinned_soa(small)):
+        key = [s for s in (small, big, batch) if s.n_atoms == soa.n_atoms][0]
+        util.assert_records_equal(engine.pairs(soa), exp[id(key)], f'upload of {soa.n_atoms} atoms')
+    for f in ('sift', 'integer_sift'):
+        assert np.array_equal(engine.atom_sifts()[f], oracle.atom_sifts(exp[id(small)], small.n_atoms)[f])
+    nohyd = AtomSoA(xyz=small.xyz, feat=small.feat, res_id=small.res_id, rad_class=small.rad_class, vdw=small.vdw,
+                    cov=small.cov, res_prev=small.res_prev, res_next=small.res_next, res_flags=small.res_flags)
+    util.assert_records_equal(engine.pairs(pinned_soa(nohyd)), oracle.pairs(nohyd, p), 'no hydrogens: every scan screened out')
+
+
 def test_rerun_is_stable_and_overflow_regrows(engine):
     """A sparse structure sizes the record buffer small; a dense one must regrow it (overflow path)."""
     p = arp_params.make_params()

@@ -162,7 +162,7 @@ class ArpStats(C.Structure):
         ('ms_search', C.c_float),
         ('ms_classify', C.c_float),
         ('ms_hscan', C.c_float),
-        ('pad_', C.c_float),
+        ('ms_pairs', C.c_float),
     ]
 
 

@@ -225,8 +225,8 @@ static inline int arp_bind(arp_ctx* c)
 /* entry points implemented across translation units */
 int  arp_pairs_prepare(arp_ctx* c);                       /* arp_pairs.cu: size the grid buffers after an upload */
 /* arp_pairs.cu: memset + grid build + pair kernels; with_events 0: none, 1: ev[0] / ev[3] around the whole
-   job, 2: also ev[1] / ev[2] between grid build, search and classify (the kernels then run back to back
-   without overlapping) */
+   job, 2: also ev[1] between the grid build and the pair kernels, 3: also ev[2] / ev[4] between the pair kernels
+   (every event between two kernels keeps them from overlapping and costs a few microseconds) */
 int  arp_pairs_enqueue(arp_ctx* c, int with_events);
 int  arp_pairs_sorted_build(arp_ctx* c);                  /* arp_pairs.cu: (i, j)-ascending copy of the stream */
 int  arp_flag_within_run(arp_ctx* c, double radius);      /* arp_pairs.cu */

@@ -901,6 +901,10 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
         const unsigned long long base = tile * CLS_TILE;
         const unsigned cnt = (unsigned)min((unsigned long long)CLS_TILE, n - base);
         int4* rec = rec0 + buf * CLS_TILE;
+#if CLS_DYNAMIC
+        unsigned next_ticket = 0;                                /* requested now, consumed after the tile: the atomic's latency is hidden */
+        if (lane == 0) next_ticket = atomicAdd(&A.meta->ticket_classify, 1u);
+#endif
         if (lane == 0) bulk_store_wait_read_1();                 /* the store that last used this buffer has read it */
         __syncwarp();
         /* ---- stages 0 + 1, 32 candidates per round ---- */
@@ -965,11 +969,7 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
             }
         }
 #if CLS_DYNAMIC
-        {                                                        /* next tile (taken early: the atomic's latency hides behind stage 3) */
-            unsigned t = 0;
-            if (lane == 0) t = atomicAdd(&A.meta->ticket_classify, 1u);
-            tile = n_warps + __shfl_sync(FULL, t, 0);
-        }
+        tile = n_warps + __shfl_sync(FULL, next_ticket, 0);
 #else
         tile += n_warps;
 #endif
@@ -1036,15 +1036,10 @@ __global__ void __launch_bounds__(HSCAN_WARPS * 32, HSCAN_MINB) k_hscan(HscanArg
     for (unsigned long long chunk = (unsigned long long)blockIdx.x * HSCAN_WARPS + warp; chunk < n_chunks; ) {
         const unsigned long long w = chunk * 32 + lane;
 #if HSCAN_DYNAMIC
-        {
-            unsigned t = 0;
-            if (lane == 0) t = atomicAdd(&A.meta->ticket_hscan, 1u);
-            chunk = n_warps + __shfl_sync(FULL, t, 0);
-        }
-#else
-        chunk += n_warps;
+        unsigned next_ticket = 0;
+        if (lane == 0) next_ticket = atomicAdd(&A.meta->ticket_hscan, 1u);
 #endif
-        if (w >= n) continue;
+        if (w < n) {
         const uint4 it = A.work[w];
         const float4 pd = A.pos4[it.x], pa = A.pos4[it.y];
         const uint32_t kind = it.w & 7u;
@@ -1065,6 +1060,12 @@ __global__ void __launch_bounds__(HSCAN_WARPS * 32, HSCAN_MINB) k_hscan(HscanArg
             bits |= fault;
         }
         if (bits) atomicOr(&A.out[it.z].mask, bits);
+        }
+#if HSCAN_DYNAMIC
+        chunk = n_warps + __shfl_sync(FULL, next_ticket, 0);
+#else
+        chunk += n_warps;
+#endif
     }
 }
 
@@ -1161,7 +1162,8 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         ARP_LAUNCHED(c);
         c->radtab_valid = 1;
     }
-    const bool split_events = with_events >= 2;       /* events between the kernels keep them from overlapping */
+    const bool grid_event = with_events >= 2;         /* events between the kernels keep them from overlapping */
+    const bool split_events = with_events >= 3;
     if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[0], st));
     ARP_CUDA(c, cudaMemsetAsync(z, 0, c->zero_bytes, st));
     if (N > 0) {
@@ -1228,7 +1230,7 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
             ARP_LAUNCHED(c);
         }
     }
-    if (split_events) ARP_CUDA(c, cudaEventRecord(c->ev[1], st));
+    if (grid_event) ARP_CUDA(c, cudaEventRecord(c->ev[1], st));
     if (N > 0) {
         ArpSide side;
         memset(&side, 0, sizeof side);

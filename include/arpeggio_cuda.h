@@ -253,7 +253,7 @@ typedef struct arp_stats {
     float    ms_search;         /* search kernel: neighbour search + filters -> hit list */
     float    ms_classify;       /* classify kernels: distance + angle + bitmask rules -> records (includes ms_hscan) */
     float    ms_hscan;          /* of which the deferred hydrogen / halogen / xbond predicates */
-    float    pad_;
+    float    ms_pairs;          /* the three pair kernels back to back (no events between them) */
 } arp_stats;
 
 /* ---- life cycle ---------------------------------------------------------- */

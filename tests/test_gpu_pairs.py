@@ -62,6 +62,30 @@ def test_parameter_sweep(engine, cutoff, comp, adj):
     _check_vs_oracle(engine, soa, arp_params.make_params(cutoff, comp, adj), f'cutoff={cutoff}')
 
 
+@pytest.mark.parametrize('seed', range(12))
+def test_randomized_structures(engine, seed):
+    """Seeded sweep over size, density, cutoff, compensation factor, hydrogen bond lengths (the hydrogen-reach screen
+    of k_classify depends on the longest one) and residue sizes; every stream bit-identical to the oracle's, and so
+    are the per-atom SIFt reductions."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.choice([37, 300, 2_000, 9_000, 25_000]))
+    soa = synth.cloud_featured(n, seed=2000 + seed, atoms_per_residue=int(rng.integers(1, 12)), chain_len=int(rng.integers(2, 50)))
+    scale = float(rng.choice([0.6, 1.0, 1.0, 1.7]))             # denser / sparser than protein density
+    soa.xyz[:] = np.round(soa.xyz.astype(np.float64) * scale, 3).astype(np.float32)
+    owner = np.repeat(np.arange(n), np.diff(soa.h_off))
+    d = rng.normal(size=(owner.shape[0], 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    length = rng.uniform(0.5, float(rng.choice([1.1, 1.1, 2.5])), size=(owner.shape[0], 1))
+    soa.h_xyz[:] = soa.xyz[owner].astype(np.float64) + d * length
+    if soa.xnbr_xyz is not None:
+        soa.xnbr_xyz[:] = (soa.xnbr_xyz.astype(np.float64) * scale).astype(np.float32)
+    p = arp_params.make_params(float(rng.choice([4.0, 5.0, 5.0, 6.5])), float(rng.choice([0.0, 0.1, 0.1, 0.4])), bool(rng.integers(2)))
+    got = _check_vs_oracle(engine, soa, p, f'seed {seed}: n={n} scale={scale}')
+    sifts, exp = engine.atom_sifts(), oracle.atom_sifts(got, n)
+    for f in sifts.dtype.names:
+        assert np.array_equal(sifts[f], exp[f]), f
+
+
 def test_far_from_origin(engine):
     soa = synth.cloud_featured(5_000, seed=8)
     soa.xyz += np.float32(9000.0)          # large coordinates widen the float32 prefilter band

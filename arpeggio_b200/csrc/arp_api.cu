@@ -190,6 +190,7 @@ int arp_create(int device, arp_ctx** out)
         return ARP_E_CUDA;
     }
     memset(c->h_meta, 0, sizeof(RunMeta));
+    if (getenv("ARPEGGIO_NO_PLANE_SCREEN")) c->use_plane_screen = 0; /* A-B knob: unscreened double loops for the plane terms */
     if (getenv("ARPEGGIO_NO_PDL")) c->use_pdl = 0;                   /* A-B knob: plain stream-ordered launches */
     if (getenv("ARPEGGIO_NO_FUSED_GRID")) c->use_fused_grid = 0;
     if (getenv("ARPEGGIO_NO_REG_GRID") && c->use_fused_grid > 1) c->use_fused_grid = 1;     /* debugging / A-B knob: five-kernel grid build */

@@ -118,6 +118,7 @@ struct arp_ctx {
     int coop_blocks = -1;         /* co-resident blocks of k_grid_fused (0: not available, -1: not probed) */
     int use_fused_grid = 2;       /* 0: five kernels, 1: cooperative kernel through global memory, 2: + register kernel when the atoms fit */
     int reg_blocks = -1;          /* co-resident blocks of k_grid_reg (0: not available, -1: not probed) */
+    int use_plane_screen = 1;     /* plane terms: float32 distance screen + hit bitmask (0: plain double loops) */
     int use_pdl = 1;              /* pair kernels launched with programmatic stream serialization */
     RunMeta* h_meta = nullptr;    /* pinned */
 

@@ -231,6 +231,149 @@ __global__ void __launch_bounds__(PLANE_WARPS * 32) k_plane_rows(PlaneArgs A, in
     if (!EMIT && lane == 0) row_cnt[row] = cnt;
 }
 
+/* ---- screened variant ------------------------------------------------------------------------------
+ * The double loops visit n_rows x n_cols pairs of which a few thousand lie within the 6 A of the centroid /
+ * search tests.  k_plane_scan tiles the column points through shared memory as float32 (one tile serves the
+ * eight rows of a block) and runs the exact predicate only where a float32 distance screen cannot exclude the
+ * pair; the exact hits of a row are kept as a bit per column, so the emitting pass (k_plane_emit) re-evaluates
+ * those pairs only.  The screen is conservative: threshold widened by the float32 rounding of the largest
+ * coordinate of the row point and of the tile, `!(d2 > T2)` keeps NaN for the exact code to judge.       */
+#define PL_TILE 1024
+
+template <int KIND> __device__ __forceinline__ float4 col_point(const PlaneArgs& A, int col)
+{
+    float x, y, z;
+    bool live = true;
+    if (KIND == KIND_ATOM_RING) {
+        x = A.xyz[3 * (size_t)col]; y = A.xyz[3 * (size_t)col + 1]; z = A.xyz[3 * (size_t)col + 2];
+    } else if (KIND == KIND_AMIDE_AMIDE) {
+        x = A.ac[3 * (size_t)col]; y = A.ac[3 * (size_t)col + 1]; z = A.ac[3 * (size_t)col + 2];
+        live = (A.aflags[col] & ARP_P_IN_SELECTION_PLUS) != 0;
+    } else {
+        x = (float)A.rc[3 * (size_t)col]; y = (float)A.rc[3 * (size_t)col + 1]; z = (float)A.rc[3 * (size_t)col + 2];
+        live = (A.rflags[col] & ARP_P_IN_SELECTION_PLUS) != 0;
+    }
+    const float mag = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+    if (!live) return make_float4(__int_as_float(0x7f800000), 0.f, 0.f, 0.f);      /* +inf: beyond every threshold */
+    return make_float4(x, y, z, mag);
+}
+
+template <int KIND> __device__ __forceinline__ float4 row_point(const PlaneArgs& A, int row)
+{
+    float x, y, z;
+    if (KIND == KIND_RING_RING || KIND == KIND_ATOM_RING) {
+        x = (float)A.rc[3 * (size_t)row]; y = (float)A.rc[3 * (size_t)row + 1]; z = (float)A.rc[3 * (size_t)row + 2];
+    } else {
+        x = A.ac[3 * (size_t)row]; y = A.ac[3 * (size_t)row + 1]; z = A.ac[3 * (size_t)row + 2];
+    }
+    return make_float4(x, y, z, fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))));
+}
+
+template <int KIND> __device__ __forceinline__ float screen_radius(const PlaneArgs& A)
+{
+    return (float)(KIND == KIND_RING_RING ? A.ring_centroid : KIND == KIND_ATOM_RING ? A.met_sulphur : A.amide_centroid);
+}
+
+#define PL_ROWS (PLANE_WARPS * 32)          /* rows per block: one per thread */
+
+template <int KIND>
+__global__ void __launch_bounds__(PL_ROWS) k_plane_scan(PlaneArgs A, int n_rows, int n_cols, int words,
+                                                       int* __restrict__ row_cnt, uint32_t* __restrict__ mask)
+{
+    /* thread = row (its point in registers), the column points of a tile are broadcast from shared memory:
+       one conflict-free LDS serves 32 rows, and the 32 screen bits a thread collects for 32 consecutive columns
+       are exactly its row's word of the hit bitmask -- no ballots.  blockIdx.y splits the columns so that every
+       SM has work when the rows are few (atom-ring). */
+    __shared__ float4 s_col[PL_TILE];
+    __shared__ float s_mag[PLANE_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * PL_ROWS + threadIdx.x;
+    const bool live = row < n_rows && row_live<KIND>(A, row);
+    float4 rp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) rp = row_point<KIND>(A, row);
+    const float r = screen_radius<KIND>(A);
+    int cnt = 0;
+    const int tiles = (n_cols + PL_TILE - 1) / PL_TILE;
+    const int t_lo = (int)((long long)tiles * blockIdx.y / gridDim.y), t_hi = (int)((long long)tiles * (blockIdx.y + 1) / gridDim.y);
+    for (int c0 = t_lo * PL_TILE; c0 < t_hi * PL_TILE && c0 < n_cols; c0 += PL_TILE) {
+        const int m = min(PL_TILE, n_cols - c0);
+        __syncthreads();                                   /* the previous tile has been consumed */
+        float mag = 0.f;
+        for (int k = threadIdx.x; k < PL_TILE; k += PL_ROWS) {
+            float4 q = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, 0.f);
+            if (k < m) q = col_point<KIND>(A, c0 + k);
+            s_col[k] = q;
+            mag = q.w == q.w ? fmaxf(mag, q.w) : q.w;      /* a NaN coordinate poisons the tile: nothing is screened out */
+        }
+        {   /* warp maximum; non-negative floats order like their bit patterns */
+            const bool nan = __any_sync(FULL, mag != mag);
+            mag = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(mag == mag ? mag : 0.f)));
+            if (nan) mag = __int_as_float(0x7fc00000);
+        }
+        if (lane == 0) s_mag[warp] = mag;
+        __syncthreads();
+        float tile_mag = 0.f;
+#pragma unroll
+        for (int w = 0; w < PLANE_WARPS; ++w) tile_mag = s_mag[w] == s_mag[w] ? fmaxf(tile_mag, s_mag[w]) : s_mag[w];
+        const float T = r * 1.000004f + 1e-6f + 4e-7f * (rp.w + tile_mag);
+        const float T2 = T * T;
+#pragma unroll 1
+        for (int g = 0; g < PL_TILE / 32 && c0 + 32 * g < n_cols; ++g) {
+            uint32_t w = 0;                                /* bit b: column c0 + 32 g + b survives the screen */
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                const float4 q = s_col[g * 32 + b];
+                const float dx = rp.x - q.x, dy = rp.y - q.y, dz = rp.z - q.z;
+                const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                if (!(d2 > T2)) w |= 1u << b;
+            }
+            if (live && w) {                               /* rare: the exact predicate decides */
+                uint32_t hits = 0;
+                while (w) {
+                    const int b = __ffs(w) - 1;
+                    w &= w - 1;
+                    const int col = c0 + g * 32 + b;
+                    PlaneRec rec;
+                    if (col < n_cols && plane_eval<KIND>(A, row, col, &rec)) hits |= 1u << b;
+                }
+                if (hits) {
+                    mask[(size_t)row * words + (c0 >> 5) + g] = hits;
+                    cnt += __popc(hits);
+                }
+            }
+        }
+    }
+    if (cnt) atomicAdd(&row_cnt[row], cnt);                /* row_cnt is zeroed by the caller */
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(PLANE_WARPS * 32) k_plane_emit(PlaneArgs A, int n_rows, int words,
+                                                                 const int* __restrict__ row_off, const uint32_t* __restrict__ mask,
+                                                                 PlaneRec* __restrict__ rec)
+{
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * PLANE_WARPS + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int base = row_off[row], n = row_off[row + 1] - base;
+    const unsigned lt = (1u << lane) - 1u;
+    int cnt = 0;
+    for (int w0 = 0; w0 < words && cnt < n; w0 += 32) {
+        const uint32_t wv = w0 + lane < words ? mask[(size_t)row * words + w0 + lane] : 0u;
+        unsigned nz = __ballot_sync(FULL, wv != 0u);
+        while (nz) {
+            const int j = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const uint32_t word = __shfl_sync(FULL, wv, j);
+            if (word >> lane & 1u) {
+                PlaneRec r;
+                plane_eval<KIND>(A, row, (w0 + j) * 32 + lane, &r);
+                rec[base + cnt + __popc(word & lt)] = r;
+            }
+            cnt += __popc(word);
+        }
+    }
+}
+
 /* ---- host side ------------------------------------------------------------------------------- */
 
 static int plane_upload(arp_ctx* c, PlaneSet& ps, const arp_planes* p)
@@ -291,7 +434,22 @@ template <int KIND> static int plane_run(arp_ctx* c, PlaneResult& R, int n_rows,
         int* row_off = (int*)(z + o_off);
         ARP_CUDA(c, cudaMemsetAsync(z, 0, o_off, c->stream));
         unsigned blocks = (unsigned)((n_rows + PLANE_WARPS - 1) / PLANE_WARPS);
-        k_plane_rows<KIND, false><<<blocks, PLANE_WARPS * 32, 0, c->stream>>>(A, n_rows, n_cols, row_cnt, nullptr, nullptr);
+        /* one bit per (row, column) for the exact hits, if that fits: the emitting pass then touches only those */
+        const int words = (n_cols + 31) / 32;
+        const size_t mask_bytes = (size_t)n_rows * (size_t)words * 4;
+        const bool screened = c->use_plane_screen && mask_bytes <= ((size_t)1 << 30);
+        if (screened) {
+            ARP_TRY(dbuf_reserve(c, R.tmp, mask_bytes));
+            ARP_CUDA(c, cudaMemsetAsync(R.tmp.p, 0, mask_bytes, c->stream));
+            const unsigned tiles = (unsigned)((n_cols + PL_TILE - 1) / PL_TILE);
+            const unsigned row_blocks = (unsigned)((n_rows + PL_ROWS - 1) / PL_ROWS);
+            unsigned splits = ((unsigned)c->sm_count * 6 + row_blocks - 1) / row_blocks;
+            splits = splits < 1 ? 1 : splits > tiles ? tiles : splits;
+            k_plane_scan<KIND><<<dim3(row_blocks, splits), PL_ROWS, 0, c->stream>>>(A, n_rows, n_cols, words, row_cnt,
+                                                                                   R.tmp.as<uint32_t>());
+        } else {
+            k_plane_rows<KIND, false><<<blocks, PLANE_WARPS * 32, 0, c->stream>>>(A, n_rows, n_cols, row_cnt, nullptr, nullptr);
+        }
         ARP_LAUNCHED(c);
         ARP_TRY(arp_scan_exclusive(c, row_cnt, row_off, state, ticket, nullptr, n_rows + 1, (size_t)n_rows + 1));
         int total = 0;
@@ -299,8 +457,12 @@ template <int KIND> static int plane_run(arp_ctx* c, PlaneResult& R, int n_rows,
         ARP_CUDA(c, cudaStreamSynchronize(c->stream));
         if (total > 0) {
             ARP_TRY(dbuf_reserve(c, R.rec, (size_t)total * sizeof(PlaneRec)));
-            k_plane_rows<KIND, true><<<blocks, PLANE_WARPS * 32, 0, c->stream>>>(A, n_rows, n_cols, nullptr, row_off,
-                                                                                 R.rec.as<PlaneRec>());
+            if (screened)
+                k_plane_emit<KIND><<<blocks, PLANE_WARPS * 32, 0, c->stream>>>(A, n_rows, words, row_off, R.tmp.as<uint32_t>(),
+                                                                               R.rec.as<PlaneRec>());
+            else
+                k_plane_rows<KIND, true><<<blocks, PLANE_WARPS * 32, 0, c->stream>>>(A, n_rows, n_cols, nullptr, row_off,
+                                                                                     R.rec.as<PlaneRec>());
             ARP_LAUNCHED(c);
             ARP_CUDA(c, cudaStreamSynchronize(c->stream));
         }

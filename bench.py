@@ -174,6 +174,34 @@ def json_emitter_leg(records, n_atoms):
                     'of get_contacts + json.dumps on a sample; texts compared byte for byte on the sample'}
 
 
+def planes_leg_run(eng, soa, p, n_atoms, cpu=True):
+    """configs[3]: the ring / amide plane terms on the synthetic plane set (2 048 rings, 12 500 amides, the configs[2]
+    atoms): per term the wall time of one run + fetch through the public API (inputs resident), the record count
+    and, beside it, the single-threaded CPU port of the reference's double loop."""
+    from arpeggio_b200 import synth
+    from oracle import oracle
+    rings, amides = synth.plane_set(2048, 12_500, n_atoms=n_atoms, seed=3)
+    eng.upload_atoms(soa)
+    eng.upload_planes(rings, amides)
+    out = {'rings': 2048, 'amides': 12_500, 'atoms': n_atoms, 'terms': {}}
+    cpu_fn = {'ring_ring': lambda: oracle.ring_ring(rings, p), 'atom_ring': lambda: oracle.atom_ring(soa, rings, p),
+              'amide_amide': lambda: oracle.amide_amide(amides, p), 'amide_ring': lambda: oracle.amide_ring(amides, rings, p)}
+    for name in ('ring_ring', 'atom_ring', 'amide_amide', 'amide_ring'):
+        f = getattr(eng, name)
+        n = int(f().shape[0])
+        t0 = time.perf_counter()
+        for _ in range(10):
+            f()
+        entry = {'records': n, 'us_per_call': (time.perf_counter() - t0) / 10 * 1e6}
+        if cpu:
+            t0 = time.perf_counter()
+            m = int(cpu_fn[name]().shape[0])
+            entry['cpu_port_us'] = (time.perf_counter() - t0) * 1e6
+            assert m == n
+        out['terms'][name] = entry
+    return out
+
+
 def dist_env():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -293,6 +321,7 @@ def run_ours(args):
         batch = (len(shard), float(sum(counts)), dt_b)
     runner.close()
     json_leg = json_emitter_leg(got, args.atoms) if rank == 0 and not args.no_cpu else None
+    planes_leg = planes_leg_run(eng, soa, p, args.atoms, cpu=not args.no_cpu) if rank == 0 and args.atoms >= 1000 else None
     t_end = time.time()
     clocks = sampler.stop(t_begin, t_end) if sampler else None
 
@@ -338,6 +367,8 @@ def run_ours(args):
         }
         if json_leg:
             line['json'] = json_leg
+        if planes_leg:
+            line['planes'] = planes_leg
         if batch:
             line['batch'] = {'metric': 'structures/s (configs[4]: PDB-batch of synthetic 20k-atom structures)',
                              'value': batch[0] / batch[2], 'unit': 'structures/s', 'structures': batch[0],

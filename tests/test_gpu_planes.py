@@ -77,6 +77,60 @@ def test_degenerate_planes(engine):
     util.assert_records_equal(engine.amide_ring(), oracle.amide_ring(amides, rings, p), 'amide-ring degenerate')
 
 
+def _all_terms(eng, soa, rings, amides, p, what):
+    eng.set_params(p)
+    eng.upload_atoms(soa)
+    eng.upload_planes(rings, amides)
+    util.assert_records_equal(eng.ring_ring(), oracle.ring_ring(rings, p), what + ' ring-ring')
+    util.assert_records_equal(eng.atom_ring(), oracle.atom_ring(soa, rings, p), what + ' atom-ring')
+    util.assert_records_equal(eng.amide_amide(), oracle.amide_amide(amides, p), what + ' amide-amide')
+    util.assert_records_equal(eng.amide_ring(), oracle.amide_ring(amides, rings, p), what + ' amide-ring')
+
+
+@pytest.mark.parametrize('knob', [None, 'ARPEGGIO_NO_PLANE_SCREEN'])
+def test_screened_and_plain_plane_loops(monkeypatch, knob):
+    """The float32 distance screen + hit bitmask in front of the plane predicates must not change a record: far from
+    the origin (large float32 rounding), thresholds hit exactly, non-finite centres, column counts that are not a
+    multiple of the tile, with and without the screen."""
+    from arpeggio_b200.engine import ContactEngine
+    if knob:
+        monkeypatch.setenv(knob, '1')
+    p = arp_params.make_params()
+    with ContactEngine(0, p) as eng:
+        soa = synth.cloud_featured(3_000, seed=31, bonds=False)
+        rings, amides = synth.plane_set(300, 1_500, n_atoms=3_000, seed=32, n_residues=375)
+        _all_terms(eng, soa, rings, amides, p, 'plain')
+        # 40 km from the origin: one float32 ulp is 4e-3 A there
+        off = np.array([40000.0, -35000.0, 20000.0])
+        far = synth.cloud_featured(3_000, seed=31, bonds=False)
+        far.xyz[:] = (far.xyz.astype(np.float64) + off).astype(np.float32)
+        far.h_xyz[:] = far.h_xyz + off
+        rings_f, amides_f = synth.plane_set(300, 1_500, n_atoms=3_000, seed=32, n_residues=375)
+        rings_f.center[:] = rings_f.center + off
+        amides_f.center[:] = (amides_f.center.astype(np.float64) + off).astype(np.float32)
+        _all_terms(eng, far, rings_f, amides_f, p, 'far')
+        # centroid distances exactly on / one ulp around the 6 A thresholds, along x
+        rings_k, amides_k = synth.plane_set(64, 64, n_atoms=100, seed=33, n_residues=8)
+        for k in range(0, 60, 2):
+            d = np.nextafter(6.0, [0.0, 6.0, 12.0][k // 2 % 3]) if k // 2 % 3 != 1 else 6.0
+            rings_k.center[k] = [100.0 * k, 0.0, 0.0]
+            rings_k.center[k + 1] = [100.0 * k + d, 0.0, 0.0]
+            rings_k.normal[k] = rings_k.normal[k + 1] = [0.0, 0.0, 1.0]
+            d32 = [np.nextafter(np.float32(6.0), np.float32(0)), np.float32(6.0), np.nextafter(np.float32(6.0), np.float32(12))][k // 2 % 3]
+            amides_k.center[k] = [8.0 * k, 50.0, 0.0]
+            amides_k.center[k + 1] = [np.float32(8.0 * k) + d32, 50.0, 0.0]
+            amides_k.normal[k] = amides_k.normal[k + 1] = [0.0, 0.0, 1.0]
+        small = synth.cloud_featured(1_025, seed=34, bonds=False)
+        small.xyz[:64] = (rings_k.center + np.array([0.0, 0.0, 6.0])).astype(np.float32)      # atoms exactly 6 A above the centroids
+        _all_terms(eng, small, rings_k, amides_k, p, 'knife edge')
+        # a NaN and an infinite centre: the reference's `distance > threshold` does not reject NaN
+        rings_n, amides_n = synth.plane_set(40, 40, n_atoms=100, seed=35, n_residues=8)
+        rings_n.center[3, 1] = np.nan
+        rings_n.center[7, 0] = np.inf
+        amides_n.center[5, 2] = np.nan
+        _all_terms(eng, small, rings_n, amides_n, p, 'non-finite')
+
+
 def test_empty_planes(engine):
     from arpeggio_b200.soa import PlaneSoA
     engine.upload_planes(PlaneSoA.empty(False), PlaneSoA.empty(True))

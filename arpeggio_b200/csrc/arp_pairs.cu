@@ -38,6 +38,14 @@ namespace cg = cooperative_groups;
 __device__ __forceinline__ void pdl_wait()    { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+#ifdef PAIR_PROFILE       /* diagnostic build: first and last instruction of every block on the global timer */
+__device__ unsigned long long g_prof[4][2048][2];
+#define PROF_STAMP(kern, which) do { if (threadIdx.x == 0 && blockIdx.x < 2048) { unsigned long long t_; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_prof[kern][blockIdx.x][which] = t_; } } while (0)
+#else
+#define PROF_STAMP(kern, which) do { } while (0)
+#endif
+
 template <class... KArgs, class... Args>
 static cudaError_t launch_k(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
                             bool pdl, Args... args)
@@ -459,55 +467,92 @@ __global__ void __launch_bounds__(GRID_THREADS) k_grid_fused(GridArgs G)
 
 /* ---- the phases as one cooperative kernel, atoms held in registers ------------------------------
  * For inputs of up to REG_APT atoms per thread of a one-block-per-SM grid (about 3 * 10^5 atoms on 148 SMs):
- * every thread loads its atoms once, keeps coordinates, cell, rank and the packed attribute record in
- * registers across the phases, and the attribute loads of the scatter are in flight while the grid
- * synchronises.  One structure: every block derives the grid from the bounding box itself (one grid barrier
- * less).  Three grid barriers in all; the look-back of the cell scan is warp-parallel.              */
+ * every thread loads its atoms once and keeps coordinates, cell, rank and the attribute values in registers
+ * across the phases; the attribute loads are issued before the first barrier and consumed after it.  One
+ * structure: every block derives the grid from the bounding box itself (no barrier for the grid).  A small
+ * table of cell counts (up to REG_SMEM_CELLS entries, about 45 000 atoms at protein density) is scanned by
+ * every block for itself in shared memory and the atoms go to their places straight from there: two grid
+ * barriers in all.  Larger tables take the single-pass scan with decoupled look-back and a third barrier
+ * (the redundant scan grows with the table, the look-back does not).
+ *
+ * No memset in front of this kernel: block 0 zeroes the run's counters (RunMeta) here, the bounding boxes and
+ * the scan state are zeroed again as soon as their last reader is past a barrier, and the cell counts are
+ * zeroed by k_hscan (the last kernel of the run), so the next run finds everything clean.             */
 #define REG_THREADS 1024
 #define REG_APT     2
+#ifndef REG_SMEM_CELLS
+#define REG_SMEM_CELLS 8192     /* measured: 3 600 cells (20k atoms) 1.8 us faster in shared memory, 17 600 cells (100k) 2 us slower */
+#endif
+#define REG_SIDX(j)    ((j) + ((j) >> 5))
+#define REG_SMEM_BYTES ((REG_SMEM_CELLS + REG_SMEM_CELLS / 32 + 32) * sizeof(int))
+
+#ifdef GRID_PROFILE      /* diagnostic build: phase boundaries of block 0 on the global timer */
+#define GRID_STAMP(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(stamp[k])); } while (0)
+#else
+#define GRID_STAMP(k) do { } while (0)
+#endif
 
 template <int APT>
 __global__ void __launch_bounds__(REG_THREADS, 1) k_grid_reg(GridArgs G)
 {
     cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) int s_off[];        /* exclusive cell offsets (REG_SMEM_CELLS entries + padding) */
     __shared__ StructGeom s_geom;
+    __shared__ int s_wsum[REG_THREADS / 32];
+#ifdef GRID_PROFILE
+    unsigned long long stamp[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    GRID_STAMP(0);
+    PROF_STAMP(0, 0);
     const int N = G.N, S = G.S;
     const int T = gridDim.x * REG_THREADS;
     const int gtid = blockIdx.x * REG_THREADS + threadIdx.x;
+    if (blockIdx.x == 0) {              /* the run's counters; their first writers come after the first grid barrier */
+        unsigned* m = reinterpret_cast<unsigned*>(G.meta);
+        for (int k = threadIdx.x; k < (int)(sizeof(RunMeta) / sizeof(unsigned)); k += REG_THREADS) m[k] = 0u;
+    }
     float x[APT], y[APT], z[APT];
     int st[APT];
-    /* ---- phase 1: load, bounding boxes (block-contiguous atoms per k: one reduction each) ---- */
+    /* ---- phase 1: load; the attribute loads are in flight during the bounding-box reductions ---- */
+    uint32_t af[APT], arc[APT];
+    int ar[APT], ab0[APT], ab1[APT];
+    int2 ah[APT];
 #pragma unroll
     for (int k = 0; k < APT; ++k) {
         const int i = k * T + gtid;
-        unsigned v[6] = {0, 0, 0, 0, 0, 0};
         st[k] = -1;
         x[k] = y[k] = z[k] = 0.f;
+        af[k] = 0; arc[k] = 0; ar[k] = 0; ab0[k] = ab1[k] = 0; ah[k] = make_int2(0, 0);
         if (i < N) {
             x[k] = G.sc.xyz[3 * (size_t)i]; y[k] = G.sc.xyz[3 * (size_t)i + 1]; z[k] = G.sc.xyz[3 * (size_t)i + 2];
+            ar[k] = G.sc.res_id[i];
+            af[k] = G.sc.feat[i];
+            arc[k] = G.sc.rad_class[i];
+            if (G.sc.bond_off) { ab0[k] = G.sc.bond_off[i]; ab1[k] = G.sc.bond_off[i + 1]; }
+            if (G.sc.h_off) ah[k] = make_int2(G.sc.h_off[i], G.sc.h_off[i + 1]);
             st[k] = struct_of(G.struct_off, S, i);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < APT; ++k) {     /* block-contiguous atoms per k: one reduction each */
+        unsigned v[6] = {0, 0, 0, 0, 0, 0};
+        if (st[k] >= 0) {
             const unsigned ox = f2ord(x[k]), oy = f2ord(y[k]), oz = f2ord(z[k]);
             v[0] = ~ox; v[1] = ~oy; v[2] = ~oz; v[3] = ox; v[4] = oy; v[5] = oz;
         }
         if (k * T + blockIdx.x * REG_THREADS < N) bbox_commit<REG_THREADS / 32>(st[k], v, G.bbox);   /* block-uniform */
     }
-    /* attribute loads of the scatter: issued now, consumed after the last barrier */
-    uint32_t aw[APT];
-    int ar[APT], ap[APT], an[APT];
-    int2 ah[APT];
+    GRID_STAMP(1);
+    uint32_t arf[APT];
+    int ap[APT], an[APT];
 #pragma unroll
-    for (int k = 0; k < APT; ++k) {
-        const int i = k * T + gtid;
-        aw[k] = 0; ar[k] = ap[k] = an[k] = 0; ah[k] = make_int2(0, 0);
-        if (i < N) {
-            const int r = G.sc.res_id[i];
-            aw[k] = arp_pack_word(G.sc.feat[i], G.sc.res_flags[r], G.sc.rad_class[i],
-                                  G.sc.bond_off && G.sc.bond_off[i + 1] > G.sc.bond_off[i]);
-            ar[k] = r; ap[k] = G.sc.res_prev[r]; an[k] = G.sc.res_next[r];
-            if (G.sc.h_off) ah[k] = make_int2(G.sc.h_off[i], G.sc.h_off[i + 1]);
-        }
+    for (int k = 0; k < APT; ++k) {     /* residue of the atom: its flags and chain links */
+        arf[k] = 0; ap[k] = an[k] = 0;
+        if (st[k] >= 0) { arf[k] = G.sc.res_flags[ar[k]]; ap[k] = G.sc.res_prev[ar[k]]; an[k] = G.sc.res_next[ar[k]]; }
     }
+    GRID_STAMP(2);
     grid.sync();
+    GRID_STAMP(3);
     /* ---- phase 2: grids ---- */
     if (S == 1) {
         if (threadIdx.x == 0) {
@@ -527,6 +572,7 @@ __global__ void __launch_bounds__(REG_THREADS, 1) k_grid_reg(GridArgs G)
         if (blockIdx.x == 0) dev_geom<REG_THREADS>(G.bbox, G.struct_off, S, N, G.cutoff, G.geom, G.meta);
         grid.sync();
     }
+    GRID_STAMP(4);
     /* ---- phase 3: cell of every atom, rank inside the cell ---- */
     int cell[APT], rank[APT];
 #pragma unroll
@@ -541,25 +587,97 @@ __global__ void __launch_bounds__(REG_THREADS, 1) k_grid_reg(GridArgs G)
             rank[k] = atomicAdd(&G.cell_cnt[cell[k]], 1);
         }
     }
+    uint32_t aw[APT];
+#pragma unroll
+    for (int k = 0; k < APT; ++k) aw[k] = arp_pack_word(af[k], arf[k], arc[k], ab1[k] > ab0[k]);
+    GRID_STAMP(5);
     grid.sync();
+    GRID_STAMP(6);
+    if (blockIdx.x == 0)                /* every reader of the bounding boxes is past a barrier: clean for the next run */
+        for (int k = threadIdx.x; k < 6 * S; k += REG_THREADS) G.bbox[k] = 0u;
     /* ---- phase 4: scan of the cell counts ---- */
-    {
-        const long long n = (long long)(S == 1 ? (unsigned)s_geom.ncell : __ldcg(&G.meta->n_cells)) + 1;
-        const int tiles = (int)((n + ARP_SCAN_TILE - 1) / ARP_SCAN_TILE);
+    const int n = (int)(S == 1 ? (unsigned)s_geom.ncell : __ldcg(&G.meta->n_cells)) + 1;
+    const bool in_smem = n <= REG_SMEM_CELLS;
+    if (in_smem) {
+        /* every block scans the whole table in its own shared memory: no barrier, no look-back.  The counts
+           arrive with independent loads (one L2 latency for all of them); thread t then owns C consecutive
+           entries; one padding word per 32 entries keeps the threads' walks off each other's banks */
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        {
+            const int n4 = n >> 2;
+            const int4* src = reinterpret_cast<const int4*>(G.cell_cnt);
+#pragma unroll 8
+            for (int j4 = threadIdx.x; j4 < n4; j4 += REG_THREADS) {
+                const int4 v = __ldcg(src + j4);
+                const int j = 4 * j4;
+                s_off[REG_SIDX(j)] = v.x; s_off[REG_SIDX(j + 1)] = v.y; s_off[REG_SIDX(j + 2)] = v.z; s_off[REG_SIDX(j + 3)] = v.w;
+            }
+            if (threadIdx.x < (n & 3)) { const int j = 4 * n4 + threadIdx.x; s_off[REG_SIDX(j)] = __ldcg(G.cell_cnt + j); }
+        }
+        __syncthreads();
+        const int C = (n + REG_THREADS - 1) / REG_THREADS;
+        const int j0 = threadIdx.x * C, j1 = min(n, j0 + C);
+        int sum = 0;
+        for (int j = j0; j < j1; ++j) sum += s_off[REG_SIDX(j)];
+        int incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_wsum[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(FULL, w, off);
+                if (lane >= off) w += t;
+            }
+            s_wsum[lane] = w;                                     /* inclusive warp totals */
+        }
+        __syncthreads();
+        int run = (warp ? s_wsum[warp - 1] : 0) + incl - sum;
+        for (int j = j0; j < j1; ++j) {
+            const int v = s_off[REG_SIDX(j)];
+            s_off[REG_SIDX(j)] = run;
+            run += v;
+        }
+        __syncthreads();
+        /* the global table (k_search reads it): every block writes its share */
+        const int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int lo = (int)blockIdx.x * per, hi = min(n, lo + per);
+        for (int j = lo + threadIdx.x; j < hi; j += REG_THREADS) G.cell_start[j] = s_off[REG_SIDX(j)];
+        GRID_STAMP(7);
+        GRID_STAMP(8);
+    } else {
+        const int tiles = (int)(((long long)n + ARP_SCAN_TILE - 1) / ARP_SCAN_TILE);
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x)     /* ascending per block, blocks co-resident */
             dev_scan_tile<REG_THREADS>(G.cell_cnt, G.cell_start, G.scan_state, n, tile);
+        GRID_STAMP(7);
+        grid.sync();
+        GRID_STAMP(8);
+        if (blockIdx.x == 0)            /* the look-backs are over: clean for the next run */
+            for (int k = threadIdx.x; k < tiles; k += REG_THREADS) G.scan_state[k] = 0ull;
     }
-    grid.sync();
     /* ---- phase 5: atoms into cell order ---- */
 #pragma unroll
     for (int k = 0; k < APT; ++k) {
         if (st[k] < 0) continue;
         const int i = k * T + gtid;
-        const int dst = __ldcg(&G.cell_start[cell[k]]) + rank[k];
+        const int dst = (in_smem ? s_off[REG_SIDX(cell[k])] : __ldcg(&G.cell_start[cell[k]])) + rank[k];
         G.sc.pos4[dst] = make_float4(x[k], y[k], z[k], __int_as_float(i));
         G.sc.att4[dst] = make_uint4(aw[k], (uint32_t)ar[k], (uint32_t)ap[k], (uint32_t)an[k]);
         G.sc.hrng[dst] = ah[k];
     }
+    GRID_STAMP(9);
+    PROF_STAMP(0, 1);
+#ifdef GRID_PROFILE
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        printf("grid ns: load+bbox %llu attr %llu sync1 %llu geom %llu cellid %llu sync2 %llu scan %llu sync3 %llu scatter %llu | total %llu\n",
+               stamp[1] - stamp[0], stamp[2] - stamp[1], stamp[3] - stamp[2], stamp[4] - stamp[3], stamp[5] - stamp[4],
+               stamp[6] - stamp[5], stamp[7] - stamp[6], stamp[8] - stamp[7], stamp[9] - stamp[8], stamp[9] - stamp[0]);
+#endif
 }
 
 /* ---- k_search ---------------------------------------------------------------------------------
@@ -577,22 +695,24 @@ __global__ void __launch_bounds__(REG_THREADS, 1) k_grid_reg(GridArgs G)
 #ifndef SEARCH_CELLS
 #define SEARCH_CELLS  4
 #endif
-/* cells per ticket (<= 4); 8 lanes describe one cell's runs */
+/* most cells per ticket (<= 4; SearchArgs.cells of them are used); 8 lanes describe one cell's runs */
 
 struct SearchArgs {
     const float4* pos4;
     const int*    cell_start;
     const StructGeom* geom;
     RunMeta*      meta;
-    uint2*        raw;                      /* candidate pairs (cell-sorted indices), float32 d^2 <= r2_hi */
-    unsigned long long cap;
+    uint2*        raw;                      /* this slice's candidate pairs (cell-sorted indices), float32 d^2 <= r2_hi */
+    unsigned long long cap;                 /* capacity of this slice's list */
+    int           slice, n_slices;          /* this launch handles tickets [T slice / n_slices, T (slice + 1) / n_slices) */
+    int           cells;                    /* cells per ticket, 1..SEARCH_CELLS */
 };
 
 /* the warp's queued candidates go to the global candidate list behind one cursor atomic */
 __device__ __forceinline__ void search_flush(const SearchArgs& A, const uint2* q, unsigned n, int lane)
 {
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&A.meta->n_raw, (unsigned long long)n);
+    if (lane == 0) base = atomicAdd(&A.meta->slice[A.slice].n_raw, (unsigned long long)n);
     base = __shfl_sync(FULL, base, 0);
     for (unsigned r = lane; r < n; r += 32)
         if (base + r < A.cap) A.raw[base + r] = q[r];
@@ -668,15 +788,23 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
 
     pdl_wait();                                 /* the grid build has completed */
     pdl_trigger();
+    PROF_STAMP(1, 0);
     const int n_cells = (int)A.meta->n_cells;
     int s = 0;                                  /* warp-uniform: structure of the ticket's first cell */
     int s_end = A.geom[0].cell_base + A.geom[0].ncell;
 
     /* tickets: the first one is static (ticket = global warp id), the rest come from a shared counter that
        starts at the number of warps; a plain read screens the counter so that late warps leave without
-       an atomic */
+       an atomic.  Measured alternatives, all slower on the 100k-atom job (profiles/README.md): a counter per
+       block in shared memory over a contiguous cell range per block, static tickets strided over the warps,
+       and a grid of up to four times the resident blocks (the block scheduler as the balancer). */
     const unsigned n_warps_total = gridDim.x * SEARCH_WARPS;
-    const unsigned n_tickets = ((unsigned)n_cells + SEARCH_CELLS - 1) / SEARCH_CELLS;
+    const int cpt = A.cells;
+    const unsigned all_tickets = ((unsigned)n_cells + (unsigned)cpt - 1) / (unsigned)cpt;
+    /* this slice's tickets [t_lo, t_lo + n_tickets) */
+    const unsigned t_lo = (unsigned)((unsigned long long)all_tickets * (unsigned)A.slice / (unsigned)A.n_slices);
+    const unsigned n_tickets = (unsigned)((unsigned long long)all_tickets * (unsigned)(A.slice + 1) / (unsigned)A.n_slices) - t_lo;
+    unsigned* const ticket_ctr = &A.meta->slice[A.slice].ticket_search;
     bool first = true;
     for (;;) {
         unsigned t = 0;
@@ -686,13 +814,13 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
         } else {
             if (lane == 0) {
                 t = n_tickets;
-                if (*(volatile unsigned*)&A.meta->ticket_search + n_warps_total < n_tickets)
-                    t = atomicAdd(&A.meta->ticket_search, 1u) + n_warps_total;
+                if (*(volatile unsigned*)ticket_ctr + n_warps_total < n_tickets)
+                    t = atomicAdd(ticket_ctr, 1u) + n_warps_total;
             }
             t = __shfl_sync(FULL, t, 0);
         }
         if (t >= n_tickets) break;
-        const long long c0l = (long long)t * SEARCH_CELLS;
+        const long long c0l = (long long)(t_lo + t) * cpt;
         const int c0 = (int)c0l;
         while (c0 >= s_end) { ++s; s_end = A.geom[s].cell_base + A.geom[s].ncell; }   /* tickets ascend */
         /* ---- run tables of the ticket's cells: lane = (cell q, run r) ---- */
@@ -701,7 +829,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
             const int c = c0 + qc;
             int rbeg = 0, rlen = 0, nh = 0;
             float band_lo = 0.f, band_hi = 0.f;
-            if (qc < SEARCH_CELLS && c < n_cells) {
+            if (qc < cpt && c < n_cells) {
                 const StructGeom* gp = A.geom + s;
                 while (c >= gp->cell_base + gp->ncell) ++gp;                  /* the cell may lie in a later structure */
                 band_lo = gp->r2_lo; band_hi = gp->r2_hi;
@@ -732,14 +860,14 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
             const int total = __shfl_sync(FULL, incl, 7, 8);
             nh = __shfl_sync(FULL, nh, 0, 8);
             __syncwarp();
-            if (qc < SEARCH_CELLS) {
+            if (qc < cpt) {
                 if (r < 5) s_runs[warp][qc][r] = make_int2(rbeg, incl - rlen);
                 else if (r == 5) s_runs[warp][qc][5] = make_int2(total, nh);
                 else if (r == 6) s_runs[warp][qc][6] = make_int2(__float_as_int(band_lo), __float_as_int(band_hi));
             }
             __syncwarp();
         }
-        for (int qc = 0; qc < SEARCH_CELLS; ++qc) {
+        for (int qc = 0; qc < cpt; ++qc) {
             const int2 tn = s_runs[warp][qc][5];
             const int total = tn.x, nh = tn.y;
             if (nh == 0) continue;
@@ -785,6 +913,10 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
         if (ncand) atomicAdd(&A.meta->n_candidates, ncand);
         if (nonempty) atomicAdd(&A.meta->n_cells_nonempty, nonempty);
     }
+#ifdef PAIR_PROFILE
+    __syncthreads();
+    PROF_STAMP(1, 1);
+#endif
 }
 
 /* ---- k_classify ---------------------------------------------------------------------------------
@@ -816,12 +948,13 @@ struct ClassifyArgs {
     unsigned      h_gen;                    /* generation of the current upload */
     const float4* pos4;
     const uint4*  att4;
-    const uint2*  raw;
+    const uint2*  raw;                      /* this slice's candidate list */
     RunMeta*      meta;
     arp_pair*     out;
-    unsigned long long cap;
-    uint4*        work;                     /* deferred predicates: (donor, acceptor | halogen, record index, kind) */
+    unsigned long long cap;                 /* capacity of this slice's candidate list */
+    uint4*        work;                     /* this slice's deferred predicates: (donor, acceptor | halogen, record index, kind) */
     unsigned long long work_cap;
+    int           slice;
     double        r2;
     int           include_seq_adjacent;
     ArpSide       side;
@@ -889,14 +1022,17 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
     }
     pdl_wait();                                                  /* k_search has completed */
     pdl_trigger();
-    unsigned long long n = A.meta->n_raw;
+    PROF_STAMP(2, 0);
+    unsigned long long n = A.meta->slice[A.slice].n_raw;
     if (n > A.cap) n = A.cap;                                    /* overflowing run: host repeats it with a larger buffer */
     const float r2_lo = A.meta->r2_lo_inv == 0x7f800000u ? -1.0f : __uint_as_float(0x7f800000u - A.meta->r2_lo_inv);
-    const unsigned long long n_tiles = (n + CLS_TILE - 1) / CLS_TILE;
     const unsigned long long warp_id = (unsigned long long)blockIdx.x * CLS_WARPS + warp;
     const unsigned long long n_warps = (unsigned long long)gridDim.x * CLS_WARPS;
+    const unsigned long long n_tiles = (n + CLS_TILE - 1) / CLS_TILE;
     int buf = 0;
-    /* tiles: the first one is static (tile = global warp id), the rest are handed out by a counter */
+    /* tiles: strided over the warps (tile = global warp id + k * warps).  Contiguous shares per warp, equal to
+       within one round of 32, were measured 2 us slower: the candidate list is not uniform along its length, and
+       the stride is what spreads the expensive stretches over all warps. */
     for (unsigned long long tile = warp_id; tile < n_tiles; ) {
         const unsigned long long base = tile * CLS_TILE;
         const unsigned cnt = (unsigned)min((unsigned long long)CLS_TILE, n - base);
@@ -980,7 +1116,7 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
         if (lane == 0) {
             o = atomicAdd(&A.meta->n_pairs, (unsigned long long)nsurv);
             bulk_store_tile(A.out + o, rec, nsurv * (uint32_t)sizeof(arp_pair));
-            if (n_items) ow = atomicAdd(&A.meta->n_work, (unsigned long long)n_items);
+            if (n_items) ow = atomicAdd(&A.meta->slice[A.slice].n_work, (unsigned long long)n_items);
         }
         o = __shfl_sync(FULL, o, 0);
         ow = __shfl_sync(FULL, ow, 0);
@@ -995,6 +1131,10 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
         buf ^= 1;
     }
     if (lane == 0) bulk_store_wait_read_all();                   /* shared memory must outlive the copies */
+#ifdef PAIR_PROFILE
+    __syncthreads();
+    PROF_STAMP(2, 1);
+#endif
 }
 
 /* ---- k_hscan -----------------------------------------------------------------------------------
@@ -1004,11 +1144,13 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
 struct HscanArgs {
     const float4* pos4;
     const int2*   hrng;                     /* hydrogen range of every atom, cell order */
-    const uint4*  work;
+    const uint4*  work;                     /* this slice's work list */
     RunMeta*      meta;
     unsigned long long work_cap;
     arp_pair*     out;
     ArpSide       side;
+    int           slice;
+    int*          clean_cnt;                /* slice 0: the cell counts of the grid build, zeroed here for the next run */
 };
 
 #ifndef HSCAN_MINB
@@ -1028,7 +1170,13 @@ __global__ void __launch_bounds__(HSCAN_WARPS * 32, HSCAN_MINB) k_hscan(HscanArg
         A.side.vdw = s_vdw;
     }
     pdl_wait();                                                  /* k_classify has completed */
-    unsigned long long n = A.meta->n_work;
+    PROF_STAMP(3, 0);
+    if (A.clean_cnt) {                                           /* the grid build is long over: leave its counts clean */
+        const unsigned nc = A.meta->n_cells + 1u;
+        for (unsigned k = blockIdx.x * (HSCAN_WARPS * 32) + threadIdx.x; k < nc; k += gridDim.x * (HSCAN_WARPS * 32))
+            A.clean_cnt[k] = 0;
+    }
+    unsigned long long n = A.meta->slice[A.slice].n_work;
     if (n > A.work_cap) n = A.work_cap;
     /* chunks of 32 items per warp: the first one static (global warp id), the rest from a counter */
     const unsigned long long n_chunks = (n + 31) / 32;
@@ -1067,6 +1215,10 @@ __global__ void __launch_bounds__(HSCAN_WARPS * 32, HSCAN_MINB) k_hscan(HscanArg
         chunk += n_warps;
 #endif
     }
+#ifdef PAIR_PROFILE
+    __syncthreads();
+    PROF_STAMP(3, 1);
+#endif
 }
 
 /* longest donor-hydrogen distance of the upload (float, rounded up; +inf when a distance is not finite).
@@ -1165,7 +1317,42 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
     const bool grid_event = with_events >= 2;         /* events between the kernels keep them from overlapping */
     const bool split_events = with_events >= 3;
     if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[0], st));
-    ARP_CUDA(c, cudaMemsetAsync(z, 0, c->zero_bytes, st));
+    /* Which grid build?  The register kernel needs no memset when the previous run on this layout of the zero
+       region was one of its own (it zeroes its counters itself and every run leaves the rest clean). */
+    bool reg_path = false;
+    int reg_apt = 1;
+    if (N > 0) {
+        if (c->coop_blocks < 0) {           /* once per context: can the grid build run as one cooperative kernel? */
+            int coop = 0, per_sm = 0;
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+            if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_grid_fused, GRID_THREADS, 0) == cudaSuccess)
+                c->coop_blocks = per_sm * c->sm_count;
+            else
+                c->coop_blocks = 0;
+            (void)cudaGetLastError();
+        }
+        if (c->coop_blocks > 0 && c->use_fused_grid >= 2) {
+            if (c->reg_blocks < 0) {        /* one 1024-thread block per SM with the shared-memory cell table, co-resident? */
+                int per_sm = 0;
+                c->reg_blocks = 0;
+                const size_t smem = REG_SMEM_BYTES;
+                if (cudaFuncSetAttribute(k_grid_reg<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                    cudaFuncSetAttribute(k_grid_reg<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_grid_reg<REG_APT>, REG_THREADS, smem) == cudaSuccess && per_sm >= 1)
+                    c->reg_blocks = c->sm_count;
+                (void)cudaGetLastError();
+            }
+            const long long reg_threads = (long long)c->reg_blocks * REG_THREADS;
+            if (reg_threads > 0 && (long long)N <= reg_threads * REG_APT) {
+                reg_path = true;
+                reg_apt = (long long)N <= reg_threads ? 1 : 2;
+            }
+        }
+    }
+    const bool clean = c->zero_clean && c->clean_ptr == (void*)z && c->clean_bytes == c->zero_bytes &&
+                       c->clean_off_cnt == c->off_cnt && c->clean_off_state == c->off_state;
+    c->zero_clean = 0;
+    if (!(reg_path && clean)) ARP_CUDA(c, cudaMemsetAsync(z, 0, c->zero_bytes, st));
     if (N > 0) {
         ScatterArgs SC;
         SC.xyz = c->xyz.as<float>(); SC.feat = c->feat.as<uint32_t>(); SC.res_id = c->res_id.as<int32_t>();
@@ -1177,44 +1364,25 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         SC.cell_of = c->cell_of.as<int>(); SC.rank = c->rank.as<int>(); SC.cell_start = c->cell_start.as<int>();
         SC.pos4 = c->pos4.as<float4>(); SC.att4 = c->att4.as<uint4>();
         unsigned blocks = (unsigned)((N + GRID_THREADS - 1) / GRID_THREADS);
-        if (c->coop_blocks < 0) {           /* once per context: can the grid build run as one cooperative kernel? */
-            int coop = 0, per_sm = 0;
-            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
-            if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_grid_fused, GRID_THREADS, 0) == cudaSuccess)
-                c->coop_blocks = per_sm * c->sm_count;
-            else
-                c->coop_blocks = 0;
-            (void)cudaGetLastError();
-        }
         if (c->coop_blocks > 0 && c->use_fused_grid) {
-            if (c->reg_blocks < 0) {        /* one 1024-thread block per SM, co-resident? */
-                int per_sm = 0;
-                c->reg_blocks = 0;
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_grid_reg<REG_APT>, REG_THREADS, 0) == cudaSuccess && per_sm >= 1)
-                    c->reg_blocks = c->sm_count;
-                (void)cudaGetLastError();
-            }
             GridArgs GA;
             GA.N = N; GA.S = S; GA.cutoff = c->params.interacting_cutoff; GA.struct_off = so; GA.bbox = bbox;
             GA.geom = c->geom.as<StructGeom>(); GA.meta = meta; GA.cell_cnt = cell_cnt; GA.scan_state = state;
             GA.sc = SC; GA.cell_of = c->cell_of.as<int>(); GA.rank = c->rank.as<int>(); GA.cell_start = c->cell_start.as<int>();
-            const long long reg_threads = (long long)c->reg_blocks * REG_THREADS;
-            if (c->use_fused_grid >= 2 && reg_threads > 0 && (long long)N <= reg_threads * REG_APT) {
-                const int apt = (long long)N <= reg_threads ? 1 : 2;
-                unsigned g = (unsigned)(((long long)N + (long long)apt * REG_THREADS - 1) / ((long long)apt * REG_THREADS));
-                void* args[] = { &GA };
-                ARP_CUDA(c, cudaLaunchCooperativeKernel(apt == 1 ? (void*)k_grid_reg<1> : (void*)k_grid_reg<2>, dim3(g),
-                                                        dim3(REG_THREADS), args, 0, st));
+            void* args[] = { &GA };
+            if (reg_path) {
+                unsigned g = (unsigned)(((long long)N + (long long)reg_apt * REG_THREADS - 1) / ((long long)reg_apt * REG_THREADS));
+                ARP_CUDA(c, cudaLaunchCooperativeKernel(reg_apt == 1 ? (void*)k_grid_reg<1> : (void*)k_grid_reg<2>, dim3(g),
+                                                        dim3(REG_THREADS), args, REG_SMEM_BYTES, st));
                 c->launches++;
             } else {
-            unsigned cap_blocks = (unsigned)c->coop_blocks;
+                unsigned cap_blocks = (unsigned)c->coop_blocks;
 #ifdef GRID_FUSED_BLOCKS_PER_SM
-            if (cap_blocks > (unsigned)(c->sm_count * GRID_FUSED_BLOCKS_PER_SM)) cap_blocks = (unsigned)(c->sm_count * GRID_FUSED_BLOCKS_PER_SM);
+                if (cap_blocks > (unsigned)(c->sm_count * GRID_FUSED_BLOCKS_PER_SM)) cap_blocks = (unsigned)(c->sm_count * GRID_FUSED_BLOCKS_PER_SM);
 #endif
-            unsigned g = blocks < cap_blocks ? blocks : cap_blocks;
-            void* args[] = { &GA };
-            ARP_CUDA(c, cudaLaunchCooperativeKernel((void*)k_grid_fused, dim3(g), dim3(GRID_THREADS), args, 0, st));
-            c->launches++;
+                unsigned g = blocks < cap_blocks ? blocks : cap_blocks;
+                ARP_CUDA(c, cudaLaunchCooperativeKernel((void*)k_grid_fused, dim3(g), dim3(GRID_THREADS), args, 0, st));
+                c->launches++;
             }
         } else {
             k_bbox<<<(unsigned)((N + BBOX_ATOMS_PER_VB - 1) / BBOX_ATOMS_PER_VB), GRID_THREADS, 0, st>>>(c->xyz.as<float>(), so, S, N, bbox);
@@ -1245,37 +1413,28 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         side.xnbr = c->has_xnbr ? c->xnbr.as<float>() : nullptr;
         side.hlim = nullptr;                 /* k_classify builds it in shared memory */
 
-        SearchArgs SA;
-        SA.pos4 = c->pos4.as<float4>(); SA.cell_start = c->cell_start.as<int>();
-        SA.geom = c->geom.as<StructGeom>(); SA.meta = meta; SA.raw = c->hits.as<uint2>(); SA.cap = c->out_cap;
-        unsigned grid = (unsigned)(c->sm_count * SEARCH_GRID_MULT);
-        size_t want = ((size_t)N / 24) / SEARCH_WARPS + 1;     /* about one warp per few cells on small inputs */
-        if (want < grid) grid = (unsigned)want;
+        /* ---- slices of the pair phase (see ARP_MAX_SLICES).  One by default: measured on a B200, two to four
+           slices of a 40k..300k-atom structure run no faster than one (profiles/README.md) -- the pair kernels
+           fill the register file, so blocks of different slices take turns instead of overlapping.  The
+           diagnostic timing with events between the kernels always runs one slice. ---- */
+        int n_slices = c->want_slices > 0 ? c->want_slices : 1;
+        if (split_events) n_slices = 1;
+        if (n_slices > ARP_MAX_SLICES) n_slices = ARP_MAX_SLICES;
+        for (int k = 0; k + 1 < n_slices; ++k) {           /* streams and events of the extra slices, created on first use */
+            if (!c->slice_stream[k]) ARP_CUDA(c, cudaStreamCreateWithFlags(&c->slice_stream[k], cudaStreamNonBlocking));
+            if (!c->ev_join[k]) ARP_CUDA(c, cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
+        }
+        if (n_slices > 1 && !c->ev_fork) ARP_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        int cells = c->want_cells > 0 ? c->want_cells : SEARCH_CELLS;       /* cells per search ticket */
+        if (cells > SEARCH_CELLS) cells = SEARCH_CELLS;
+        c->run_slices = n_slices;
+        c->slice_cap = c->out_cap / (uint64_t)n_slices;
+        c->slice_work_cap = c->work_cap / (uint64_t)n_slices;
         const bool pdl = c->use_pdl != 0;
-        ARP_CUDA(c, launch_k(k_search, grid, SEARCH_WARPS * 32, 0, st, pdl, SA));
-        c->launches++;
-        if (split_events) ARP_CUDA(c, cudaEventRecord(c->ev[2], st));
-
-        ClassifyArgs CA;
-        CA.h_reach = c->hreach.as<unsigned long long>(); CA.h_gen = c->upload_gen;
-        CA.pos4 = SA.pos4; CA.att4 = c->att4.as<uint4>(); CA.raw = SA.raw; CA.meta = meta;
-        CA.out = c->out.as<arp_pair>(); CA.cap = c->out_cap; CA.side = side;
-        CA.work = c->work.as<uint4>(); CA.work_cap = c->work_cap;
-        CA.r2 = c->rp.r2; CA.include_seq_adjacent = c->rp.include_seq_adjacent;
         if (!c->cls_smem_set) {             /* per device: > 48 KB of dynamic shared memory is opt-in */
             ARP_CUDA(c, cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, CLS_SMEM));
             c->cls_smem_set = 1;
         }
-        size_t tiles = (size_t)((c->out_cap + CLS_TILE - 1) / CLS_TILE);
-        size_t blocks_needed = (tiles + CLS_WARPS - 1) / CLS_WARPS;
-        unsigned cgrid = (unsigned)(c->sm_count * CLS_MINB);
-        if (blocks_needed < cgrid) cgrid = (unsigned)(blocks_needed ? blocks_needed : 1);
-        ARP_CUDA(c, launch_k(k_classify, cgrid, CLS_WARPS * 32, CLS_SMEM, st, pdl, CA, c->rp));
-        c->launches++;
-        if (split_events) ARP_CUDA(c, cudaEventRecord(c->ev[4], st));
-        HscanArgs HA;
-        HA.pos4 = SA.pos4; HA.hrng = c->hrng.as<int2>(); HA.work = CA.work; HA.meta = meta; HA.work_cap = c->work_cap;
-        HA.out = CA.out; HA.side = side;
         if (!c->hscan_blocks) {             /* a persistent grid: exactly the blocks that are resident together */
             int per_sm = 0;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hscan, HSCAN_WARPS * 32, 0) != cudaSuccess || per_sm < 1)
@@ -1283,17 +1442,95 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
             (void)cudaGetLastError();
             c->hscan_blocks = per_sm * c->sm_count;
         }
-        size_t hb = (size_t)((c->work_cap + 255) / 256);
-        unsigned hgrid = (unsigned)c->hscan_blocks;
-        if (hb < hgrid) hgrid = (unsigned)(hb ? hb : 1);
-        ARP_CUDA(c, launch_k(k_hscan, hgrid, HSCAN_WARPS * 32, 0, st, pdl, HA, c->rp));
-        c->launches++;
+        if (n_slices > 1) {
+            ARP_CUDA(c, cudaEventRecord(c->ev_fork, st));
+            for (int k = 0; k + 1 < n_slices; ++k) ARP_CUDA(c, cudaStreamWaitEvent(c->slice_stream[k], c->ev_fork, 0));
+        }
+        /* kernel by kernel over the slices, so that the launches reach the device in the order they can start */
+        for (int sl = 0; sl < n_slices; ++sl) {
+            cudaStream_t ss = sl == 0 ? st : c->slice_stream[sl - 1];
+            SearchArgs SA;
+            SA.pos4 = c->pos4.as<float4>(); SA.cell_start = c->cell_start.as<int>();
+            SA.geom = c->geom.as<StructGeom>(); SA.meta = meta;
+            SA.raw = c->hits.as<uint2>() + (size_t)sl * c->slice_cap; SA.cap = c->slice_cap;
+            SA.slice = sl; SA.n_slices = n_slices; SA.cells = cells;
+            unsigned grid = (unsigned)(c->sm_count * SEARCH_GRID_MULT);
+            size_t want = ((size_t)N / 6 / (size_t)cells / (size_t)n_slices) / SEARCH_WARPS + 1;   /* about one warp per ticket on small inputs */
+            if (want < grid) grid = (unsigned)want;
+            ARP_CUDA(c, launch_k(k_search, grid, SEARCH_WARPS * 32, 0, ss, pdl, SA));
+            c->launches++;
+        }
+        if (split_events) ARP_CUDA(c, cudaEventRecord(c->ev[2], st));
+        for (int sl = 0; sl < n_slices; ++sl) {
+            cudaStream_t ss = sl == 0 ? st : c->slice_stream[sl - 1];
+            ClassifyArgs CA;
+            CA.h_reach = c->hreach.as<unsigned long long>(); CA.h_gen = c->upload_gen;
+            CA.pos4 = c->pos4.as<float4>(); CA.att4 = c->att4.as<uint4>();
+            CA.raw = c->hits.as<uint2>() + (size_t)sl * c->slice_cap; CA.cap = c->slice_cap; CA.meta = meta;
+            CA.out = c->out.as<arp_pair>(); CA.side = side;
+            CA.work = c->work.as<uint4>() + (size_t)sl * c->slice_work_cap; CA.work_cap = c->slice_work_cap;
+            CA.r2 = c->rp.r2; CA.include_seq_adjacent = c->rp.include_seq_adjacent; CA.slice = sl;
+            size_t tiles = (size_t)((c->slice_cap + CLS_TILE - 1) / CLS_TILE);
+            size_t blocks_needed = (tiles + CLS_WARPS - 1) / CLS_WARPS;
+            unsigned cgrid = (unsigned)(c->sm_count * CLS_MINB);
+            if (blocks_needed < cgrid) cgrid = (unsigned)(blocks_needed ? blocks_needed : 1);
+            ARP_CUDA(c, launch_k(k_classify, cgrid, CLS_WARPS * 32, CLS_SMEM, ss, pdl, CA, c->rp));
+            c->launches++;
+        }
+        if (split_events) ARP_CUDA(c, cudaEventRecord(c->ev[4], st));
+        for (int sl = 0; sl < n_slices; ++sl) {
+            cudaStream_t ss = sl == 0 ? st : c->slice_stream[sl - 1];
+            HscanArgs HA;
+            HA.pos4 = c->pos4.as<float4>(); HA.hrng = c->hrng.as<int2>();
+            HA.work = c->work.as<uint4>() + (size_t)sl * c->slice_work_cap; HA.meta = meta; HA.work_cap = c->slice_work_cap;
+            HA.out = c->out.as<arp_pair>(); HA.side = side; HA.slice = sl;
+            HA.clean_cnt = sl == 0 ? cell_cnt : nullptr;
+            size_t hb = (size_t)((c->slice_work_cap + 255) / 256);
+            unsigned hgrid = (unsigned)c->hscan_blocks;
+            if (hb < hgrid) hgrid = (unsigned)(hb ? hb : 1);
+            ARP_CUDA(c, launch_k(k_hscan, hgrid, HSCAN_WARPS * 32, 0, ss, pdl, HA, c->rp));
+            c->launches++;
+            if (sl > 0) {                   /* join: the context's stream continues after every slice */
+                ARP_CUDA(c, cudaEventRecord(c->ev_join[sl - 1], ss));
+                ARP_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[sl - 1], 0));
+            }
+        }
     } else if (split_events) {
         ARP_CUDA(c, cudaEventRecord(c->ev[2], st));
         ARP_CUDA(c, cudaEventRecord(c->ev[4], st));
     }
     if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[3], st));
     ARP_CUDA(c, cudaMemcpyAsync(c->h_meta, meta, sizeof(RunMeta), cudaMemcpyDeviceToHost, st));
+#ifdef PAIR_PROFILE
+    {
+        static unsigned long long h[4][2048][2];
+        static int runs = 0;
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(h, g_prof, sizeof h);
+        if (++runs % 8 == 0) {
+            unsigned long long t0 = ~0ull;
+            for (int b = 0; b < 2048; ++b) if (h[0][b][0] && h[0][b][0] < t0) t0 = h[0][b][0];
+            const char* nm[4] = { "grid", "search", "classify", "hscan" };
+            for (int k = 0; k < 4; ++k) {
+                unsigned long long s0 = ~0ull, s1 = 0, e0 = ~0ull, e1 = 0; double es = 0; int nb = 0;
+                unsigned long long ends[2048];
+                for (int b = 0; b < 2048; ++b) if (h[k][b][0] >= t0 && h[k][b][1] >= h[k][b][0]) {
+                    s0 = h[k][b][0] < s0 ? h[k][b][0] : s0; s1 = h[k][b][0] > s1 ? h[k][b][0] : s1;
+                    e0 = h[k][b][1] < e0 ? h[k][b][1] : e0; e1 = h[k][b][1] > e1 ? h[k][b][1] : e1;
+                    es += (double)(h[k][b][1] - t0); ends[nb++] = h[k][b][1] - t0;
+                }
+                if (!nb) continue;
+                for (int a = 1; a < nb; ++a) { unsigned long long v = ends[a]; int b = a - 1; while (b >= 0 && ends[b] > v) { ends[b + 1] = ends[b]; --b; } ends[b + 1] = v; }
+                fprintf(stderr, "%-8s blocks %4d | first start %6llu last start %6llu | first end %6llu median end %6llu p90 end %6llu last end %6llu (ns after the grid kernel's first block)\n",
+                        nm[k], nb, s0 - t0, s1 - t0, e0 - t0, ends[nb / 2], ends[nb * 9 / 10], e1 - t0);
+            }
+        }
+    }
+#endif
+    if (reg_path) {                         /* everything enqueued: this layout of the zero region is clean after the run */
+        c->zero_clean = 1; c->clean_ptr = (void*)z; c->clean_bytes = c->zero_bytes;
+        c->clean_off_cnt = c->off_cnt; c->clean_off_state = c->off_state;
+    }
     return ARP_OK;
 }
 

@@ -1,6 +1,8 @@
 """GPU parity of the atom-atom path: libarpeggio_cuda.so (through the C ABI) against the CPU oracle
 and against the golden records produced by the reference's own code.  Bit-exact: pair set, (i < j)
 orientation, 15-bit mask + entity class, float32 distance bits."""
+import dataclasses
+
 import numpy as np
 import pytest
 
@@ -193,6 +195,34 @@ def test_every_grid_build_path(monkeypatch, knob):
     with ContactEngine(0, p) as eng:
         for name, soa in cases.items():
             util.assert_records_equal(eng.pairs(soa), oracle.pairs(soa, p), f'{knob or "default"} {name}')
+
+
+@pytest.mark.parametrize('slices,cells', [(1, 4), (2, 4), (2, 1), (3, 2), (4, 3)])
+def test_sliced_pair_phase(monkeypatch, slices, cells):
+    """The pair phase runs as 1..4 slices of the search tickets on their own streams, with 1..4 cells per ticket;
+    every combination must give the oracle's stream: one structure of either size class, a small batch, an input
+    with fewer cells than slices, and the golden ligand site."""
+    from arpeggio_b200.engine import ContactEngine
+    monkeypatch.setenv('ARPEGGIO_SLICES', str(slices))
+    monkeypatch.setenv('ARPEGGIO_SEARCH_CELLS', str(cells))
+    p = arp_params.make_params()
+    parts = [synth.cloud_featured(n, seed=170 + k) for k, n in enumerate((3000, 0, 17, 2500))]
+    cases = {'60k': synth.cloud_featured(60_000, seed=161), '3 atoms': synth.cloud_featured(3, seed=162),
+             'batch': AtomSoA.concat(parts)}
+    with ContactEngine(0, p) as eng:
+        for name, soa in cases.items():
+            util.assert_records_equal(eng.pairs(soa), oracle.pairs(soa, p), f'{slices} slices, {cells} cells: {name}')
+        g = util.Golden('ligand_site')
+        eng.set_params(g.params)
+        util.assert_records_equal(eng.pairs(g.soa), g.exp_pairs, f'{slices} slices, {cells} cells: golden ligand_site')
+        # skewed density: almost all candidates fall into one slice, whose share of the candidate list overflows
+        # and is regrown
+        eng.set_params(p)
+        dense = synth.cloud_featured(20_000, seed=163)
+        far = synth.cloud_featured(20_000, seed=164)
+        xyz = np.concatenate([dense.xyz * np.float32(0.6), far.xyz * np.float32(3.0) + np.float32(400.0)])
+        skew = dataclasses.replace(AtomSoA.concat([dense, far]), xyz=xyz, struct_off=None)
+        util.assert_records_equal(eng.pairs(skew), oracle.pairs(skew, p), f'{slices} slices, {cells} cells: skewed')
 
 
 @pytest.mark.parametrize('case', [c for c in CASES if c != 'xbond_fault'])

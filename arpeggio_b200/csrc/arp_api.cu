@@ -368,7 +368,12 @@ static int pairs_out_reserve(arp_ctx* c, uint64_t records)
     if (records <= c->out_cap && c->out.p) return ARP_OK;
     ARP_TRY(dbuf_reserve(c, c->out, (size_t)records * sizeof(arp_pair)));
     c->out_cap = c->out.cap / sizeof(arp_pair);
-    ARP_TRY(dbuf_reserve(c, c->hits, (size_t)c->out_cap * sizeof(uint2)));
+    {   /* the candidate list is all zero between runs (k_classify zeroes what it reads): a new allocation starts so */
+        const void* before = c->hits.p;
+        const size_t cap_before = c->hits.cap;
+        ARP_TRY(dbuf_reserve(c, c->hits, (size_t)c->out_cap * sizeof(uint2)));
+        if (c->hits.p != before || c->hits.cap != cap_before) ARP_CUDA(c, cudaMemsetAsync(c->hits.p, 0, c->hits.cap, c->stream));
+    }
     if (c->work_cap < c->out_cap / 2 + 1024) {       /* first guess: one deferred predicate per two records */
         ARP_TRY(dbuf_reserve(c, c->work, (size_t)(c->out_cap / 2 + 1024) * 16));
         c->work_cap = c->work.cap / 16;
@@ -427,6 +432,12 @@ int arp_pairs_run(arp_ctx* c, uint64_t* n_pairs)
             ARP_TRY(dbuf_reserve(c, c->work, (size_t)(nw + nw / 16 + 1024) * 16));
             c->work_cap = c->work.cap / 16;
         }
+    }
+    if (c->h_meta->fault & 2u) {            /* never seen; the list may hold unread entries: clean it before reporting */
+        cudaMemsetAsync(c->hits.p, 0, c->hits.cap, c->stream);
+        cudaStreamSynchronize(c->stream);
+        (void)cudaGetLastError();
+        return arp_fail(c, ARP_E_CUDA, "candidate hand-off between k_search and k_classify timed out", __FILE__, __LINE__);
     }
     ARP_REQUIRE(c, c->h_meta->n_pairs < (1ull << 32), ARP_E_CAPACITY, "more than 2^32 records in one run");
     c->n_pairs = c->h_meta->n_pairs;

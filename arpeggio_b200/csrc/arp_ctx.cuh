@@ -40,6 +40,9 @@ struct StructGeom {
    stream, candidate list, work list and cursors, so that the search of one slice overlaps the classification
    of another and the launch ramps and tails of the three pair kernels hide behind useful work. */
 #define ARP_MAX_SLICES 4
+#ifndef ARP_CLS_COUNTERS
+#define ARP_CLS_COUNTERS 16
+#endif
 
 /* one 128-byte line per hot counter */
 struct alignas(128) SliceMeta {
@@ -49,6 +52,10 @@ struct alignas(128) SliceMeta {
     unsigned int pad1[30];
     unsigned int ticket_search;       /* dynamic cell tickets of k_search */
     unsigned int pad2[31];
+    /* dynamic tile tickets of k_classify: ARP_CLS_COUNTERS counters, each handing out the tiles of one residue
+       class modulo ARP_CLS_COUNTERS (same-address atomics serialise in L2: one counter for 20 000 tiles costs
+       more than the balancing gains) */
+    struct alignas(128) { unsigned int v; unsigned int pad[31]; } ticket_cls[ARP_CLS_COUNTERS];
 };
 
 /* counters the kernels leave behind (device, copied to pinned host memory after a run).

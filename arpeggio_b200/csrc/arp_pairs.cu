@@ -948,7 +948,7 @@ struct ClassifyArgs {
     unsigned      h_gen;                    /* generation of the current upload */
     const float4* pos4;
     const uint4*  att4;
-    const uint2*  raw;                      /* this slice's candidate list */
+    uint2*        raw;                      /* this slice's candidate list; every entry is zeroed again once it is read */
     RunMeta*      meta;
     arp_pair*     out;
     unsigned long long cap;                 /* capacity of this slice's candidate list */
@@ -984,9 +984,26 @@ __device__ __forceinline__ void bulk_store_wait_read_1()
 #define CLS_KIND_HAL   4u
 #define CLS_KIND_XBOND 5u
 
-#ifndef CLS_DYNAMIC
-#define CLS_DYNAMIC 0
+#ifndef CLS_GROUP
+#define CLS_GROUP 1                         /* tiles per ticket */
 #endif
+
+/* candidate `pos` of the list: read from L2, waited for while k_search is still running (the cursor is advanced
+   before the entries are stored), and zeroed for the next run */
+#define CLS_FAULT_HANDOFF 2u
+__device__ __forceinline__ uint2 cls_fetch(const ClassifyArgs& A, unsigned long long pos, bool final)
+{
+    uint2 v = __ldcg(A.raw + pos);
+    if (!final) {
+        unsigned spins = 0;
+        while ((v.x | v.y) == 0u) {
+            v = __ldcg(A.raw + pos);
+            if (++spins > (1u << 22)) { atomicOr(&A.meta->fault, CLS_FAULT_HANDOFF); break; }   /* never seen; the host reports it */
+        }
+    }
+    A.raw[pos] = make_uint2(0u, 0u);
+    return v;
+}
 #ifndef CLS_MINB
 #define CLS_MINB 4
 #endif
@@ -1020,38 +1037,63 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
         A.side.vdw = s_vdw;
         A.side.hlim = s_hlim;
     }
-    pdl_wait();                                                  /* k_search has completed */
     pdl_trigger();
     PROF_STAMP(2, 0);
-    unsigned long long n = A.meta->slice[A.slice].n_raw;
-    if (n > A.cap) n = A.cap;                                    /* overflowing run: host repeats it with a larger buffer */
+    /* The blocks of this kernel become resident while k_search drains (programmatic dependent launch) and start
+       on the candidates that are already there instead of waiting for its last warp: the candidate cursor tells
+       how far the list has been handed out, and an entry is in place once it is non-zero (a pair never has two
+       zero indices; the list is all zero before a run because every reader zeroes what it has read).  A warp
+       whose next tile is not handed out yet sleeps in griddepcontrol.wait until k_search has completed; from
+       then on the count is final.  What k_search leaves in r2_lo_inv was written by the grid build, which had
+       completed before k_search could trigger this launch. */
+    const volatile unsigned long long* const n_raw_p = &A.meta->slice[A.slice].n_raw;
     const float r2_lo = A.meta->r2_lo_inv == 0x7f800000u ? -1.0f : __uint_as_float(0x7f800000u - A.meta->r2_lo_inv);
-    const unsigned long long warp_id = (unsigned long long)blockIdx.x * CLS_WARPS + warp;
-    const unsigned long long n_warps = (unsigned long long)gridDim.x * CLS_WARPS;
-    const unsigned long long n_tiles = (n + CLS_TILE - 1) / CLS_TILE;
+    bool final = false;                                          /* k_search has completed: n and n_tiles are valid */
+    unsigned long long n = 0, n_tiles = 0;
     int buf = 0;
-    /* tiles: strided over the warps (tile = global warp id + k * warps).  Contiguous shares per warp, equal to
-       within one round of 32, were measured 2 us slower: the candidate list is not uniform along its length, and
-       the stride is what spreads the expensive stretches over all warps. */
-    for (unsigned long long tile = warp_id; tile < n_tiles; ) {
+    /* Tickets of CLS_GROUP consecutive tiles, handed out dynamically because the blocks start at different times
+       (whenever k_search frees a slot).  ARP_CLS_COUNTERS counters share the work: counter c owns the tickets
+       congruent to c and serves the blocks congruent to c; a warp's first ticket is static (its rank among the
+       warps of its class), the rest come from the counter, requested one ticket ahead so that the atomic's
+       latency is hidden. */
+    const unsigned nc = min((unsigned)ARP_CLS_COUNTERS, gridDim.x);      /* classes in use: every one needs a block */
+    const unsigned cls = blockIdx.x % nc;
+    unsigned* const ticket_ctr = &A.meta->slice[A.slice].ticket_cls[cls].v;
+    const unsigned long long class_warps = (unsigned long long)((gridDim.x - cls + nc - 1) / nc) * CLS_WARPS;
+    unsigned long long ticket = ((unsigned long long)(blockIdx.x / nc) * CLS_WARPS + warp) * nc + cls;
+    unsigned long long snap = 0;                                 /* the cursor when it was last read: a lower bound */
+    for (;;) {
+        if (!final && (ticket + 1) * (CLS_GROUP * CLS_TILE) > min(snap, A.cap)) {
+            if (lane == 0) snap = *n_raw_p;                      /* look again */
+            snap = __shfl_sync(FULL, snap, 0);
+            if ((ticket + 1) * (CLS_GROUP * CLS_TILE) > min(snap, A.cap)) {   /* not handed out yet (or holds the last, partial tile) */
+                pdl_wait();                                      /* k_search has completed */
+                final = true;
+                n = *n_raw_p;
+                if (n > A.cap) n = A.cap;                        /* overflowing run: host repeats it with a larger buffer */
+                n_tiles = (n + CLS_TILE - 1) / CLS_TILE;
+            }
+        }
+        if (final && ticket * CLS_GROUP >= n_tiles) break;
+        unsigned next_ticket = 0;                                /* requested now, used after this ticket's tiles */
+        unsigned long long seen = 0;
+        if (lane == 0) next_ticket = atomicAdd(ticket_ctr, 1u);
+        if (lane == 1 && !final) seen = *n_raw_p;
+      for (unsigned long long tile = ticket * CLS_GROUP; tile < (ticket + 1) * CLS_GROUP && (!final || tile < n_tiles); ++tile) {
         const unsigned long long base = tile * CLS_TILE;
-        const unsigned cnt = (unsigned)min((unsigned long long)CLS_TILE, n - base);
+        const unsigned cnt = final ? (unsigned)min((unsigned long long)CLS_TILE, n - base) : (unsigned)CLS_TILE;
         int4* rec = rec0 + buf * CLS_TILE;
-#if CLS_DYNAMIC
-        unsigned next_ticket = 0;                                /* requested now, consumed after the tile: the atomic's latency is hidden */
-        if (lane == 0) next_ticket = atomicAdd(&A.meta->ticket_classify, 1u);
-#endif
         if (lane == 0) bulk_store_wait_read_1();                 /* the store that last used this buffer has read it */
         __syncwarp();
         /* ---- stages 0 + 1, 32 candidates per round ---- */
         unsigned nsurv = 0, n_items = 0;
-        uint2 e_next = lane < cnt ? A.raw[base + lane] : make_uint2(0, 0);   /* candidates are fetched one round ahead */
+        uint2 e_next = lane < cnt ? cls_fetch(A, base + lane, final) : make_uint2(0, 0);   /* candidates are fetched one round ahead */
 #pragma unroll 1
         for (unsigned i0 = 0; i0 < cnt; i0 += 32) {
             const unsigned idx = i0 + lane;
             bool keep = false;
             uint2 e = e_next;
-            if (idx + 32 < cnt) e_next = A.raw[base + idx + 32];
+            if (idx + 32 < cnt) e_next = cls_fetch(A, base + idx + 32, final);
             float4 pa, pb;
             uint4 ab, ae;
             if (idx < cnt) {
@@ -1104,11 +1146,6 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
                 }
             }
         }
-#if CLS_DYNAMIC
-        tile = n_warps + __shfl_sync(FULL, next_ticket, 0);
-#else
-        tile += n_warps;
-#endif
         if (nsurv == 0) continue;                                /* nothing staged: the buffer stays free */
         __syncwarp();
         /* ---- stage 3: the tile leaves through the TMA engine; its work items go to the global work list ---- */
@@ -1129,6 +1166,9 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
         }
         __syncwarp();
         buf ^= 1;
+      }
+        ticket = (class_warps + __shfl_sync(FULL, next_ticket, 0)) * nc + cls;
+        snap = __shfl_sync(FULL, seen, 1);
     }
     if (lane == 0) bulk_store_wait_read_all();                   /* shared memory must outlive the copies */
 #ifdef PAIR_PROFILE

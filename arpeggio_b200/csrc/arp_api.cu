@@ -193,8 +193,7 @@ int arp_create(int device, arp_ctx** out)
     if (getenv("ARPEGGIO_NO_PLANE_SCREEN")) c->use_plane_screen = 0; /* A-B knob: unscreened double loops for the plane terms */
     if (getenv("ARPEGGIO_NO_PDL")) c->use_pdl = 0;                   /* A-B knob: plain stream-ordered launches */
     if (getenv("ARPEGGIO_NO_FUSED_GRID")) c->use_fused_grid = 0;
-    if (const char* v = getenv("ARPEGGIO_SLICES")) c->want_slices = atoi(v);             /* A-B knob: slices of the pair phase */
-    if (const char* v = getenv("ARPEGGIO_SEARCH_CELLS")) c->want_cells = atoi(v);        /* A-B knob: cells per search ticket */
+    if (getenv("ARPEGGIO_NO_EARLY_CLASSIFY")) c->use_early_cls = 0;                     /* A-B knob: k_classify waits for k_search */
     if (getenv("ARPEGGIO_NO_REG_GRID") && c->use_fused_grid > 1) c->use_fused_grid = 1;     /* debugging / A-B knob: five-kernel grid build */
     memset(&c->stats, 0, sizeof c->stats);
     arp_params_default(&c->params);
@@ -216,11 +215,6 @@ void arp_destroy(arp_ctx* c)
     for (DBuf* b : bufs) dbuf_free(*b);
     arp_planes_release(c);
     for (int k = 0; k < 5; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
-    for (int k = 0; k < ARP_MAX_SLICES - 1; ++k) {
-        if (c->slice_stream[k]) { cudaStreamSynchronize(c->slice_stream[k]); cudaStreamDestroy(c->slice_stream[k]); }
-        if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
-    }
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->h_meta) cudaFreeHost(c->h_meta);
     if (c->stream) cudaStreamDestroy(c->stream);
     (void)cudaGetLastError();
@@ -372,7 +366,10 @@ static int pairs_out_reserve(arp_ctx* c, uint64_t records)
         const void* before = c->hits.p;
         const size_t cap_before = c->hits.cap;
         ARP_TRY(dbuf_reserve(c, c->hits, (size_t)c->out_cap * sizeof(uint2)));
-        if (c->hits.p != before || c->hits.cap != cap_before) ARP_CUDA(c, cudaMemsetAsync(c->hits.p, 0, c->hits.cap, c->stream));
+        if (c->hits.p != before || c->hits.cap != cap_before) {
+            ARP_CUDA(c, cudaMemsetAsync(c->hits.p, 0, c->hits.cap, c->stream));
+            c->hits_dirty = 0;
+        }
     }
     if (c->work_cap < c->out_cap / 2 + 1024) {       /* first guess: one deferred predicate per two records */
         ARP_TRY(dbuf_reserve(c, c->work, (size_t)(c->out_cap / 2 + 1024) * 16));
@@ -417,16 +414,10 @@ int arp_pairs_run(arp_ctx* c, uint64_t* n_pairs)
     for (int attempt = 0; attempt < 3; ++attempt) {
         ARP_TRY(arp_pairs_enqueue(c, 1));
         ARP_CUDA(c, cudaStreamSynchronize(c->stream));
-        /* candidates >= records, and both lists share the capacity; every slice owns an equal part of the
-           candidate list and of the work list, so the fullest slice decides */
-        uint64_t n = 0, nw = 0;
-        for (int s = 0; s < c->run_slices; ++s) {
-            n = c->h_meta->slice[s].n_raw > n ? c->h_meta->slice[s].n_raw : n;
-            nw = c->h_meta->slice[s].n_work > nw ? c->h_meta->slice[s].n_work : nw;
-        }
-        if (n <= c->slice_cap && nw <= c->slice_work_cap) break;
+        const uint64_t n = c->h_meta->n_raw;    /* candidates >= records: both lists share the capacity */
+        const uint64_t nw = c->h_meta->n_work;
+        if (n <= c->out_cap && nw <= c->work_cap) break;
         ARP_REQUIRE(c, attempt < 2, ARP_E_CAPACITY, "record stream overflowed repeatedly");
-        n *= (uint64_t)c->run_slices; nw *= (uint64_t)c->run_slices;
         if (n > c->out_cap) ARP_TRY(pairs_out_reserve(c, n + n / 16 + 1024));
         else {                                  /* the work-item count is exact once the records fit */
             ARP_TRY(dbuf_reserve(c, c->work, (size_t)(nw + nw / 16 + 1024) * 16));

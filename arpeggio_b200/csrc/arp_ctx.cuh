@@ -36,54 +36,42 @@ struct StructGeom {
     int    pad;
 };
 
-/* The pair phase of one run may be cut into slices: contiguous ranges of the search tickets, each with its own
-   stream, candidate list, work list and cursors, so that the search of one slice overlaps the classification
-   of another and the launch ramps and tails of the three pair kernels hide behind useful work. */
-#define ARP_MAX_SLICES 4
+/* k_classify hands out its tiles from ARP_CLS_COUNTERS counters, each serving the tickets and the blocks of one
+   residue class modulo ARP_CLS_COUNTERS (same-address atomics serialise in L2: one counter for 20 000 tiles
+   costs more than the balancing gains) */
 #ifndef ARP_CLS_COUNTERS
 #define ARP_CLS_COUNTERS 16
 #endif
 
-/* one 128-byte line per hot counter */
-struct alignas(128) SliceMeta {
-    unsigned long long n_raw;         /* candidate cursor of k_search */
-    unsigned int pad0[30];
-    unsigned long long n_work;        /* work-item cursor of k_classify (deferred predicates) */
-    unsigned int pad1[30];
-    unsigned int ticket_search;       /* dynamic cell tickets of k_search */
-    unsigned int pad2[31];
-    /* dynamic tile tickets of k_classify: ARP_CLS_COUNTERS counters, each handing out the tiles of one residue
-       class modulo ARP_CLS_COUNTERS (same-address atomics serialise in L2: one counter for 20 000 tiles costs
-       more than the balancing gains) */
-    struct alignas(128) { unsigned int v; unsigned int pad[31]; } ticket_cls[ARP_CLS_COUNTERS];
-};
-
 /* counters the kernels leave behind (device, copied to pinned host memory after a run).
    Every counter that many warps hammer with atomics sits on its own 128-byte line. */
 struct alignas(128) RunMeta {
-    /* line 0: written once by k_geom, read by everybody */
+    /* line 0: written once by the grid build, read by everybody */
     unsigned int n_cells;
     unsigned int r2_lo_inv;           /* 0x7f800000 - bits(min over structures of r2_lo); 0x7f800000 = no quick accept */
     unsigned int fault;               /* sticky device-side diagnostics */
     unsigned int pad0[29];
     /* line 1 */
-    unsigned long long n_pairs;       /* record cursor: total records the run produced (all slices) */
-    unsigned int pad2[30];
+    unsigned long long n_raw;         /* candidate cursor of k_search */
+    unsigned int pad1[30];
     /* line 2 */
+    unsigned long long n_pairs;       /* record cursor: total records the run produced */
+    unsigned int pad2[30];
+    /* line 3 */
+    unsigned int ticket_search;       /* dynamic cell tickets of k_search */
+    unsigned int pad3[31];
+    /* line 4 */
     unsigned int ticket_scan;         /* dynamic tile ids of the cell scan */
     unsigned int pad4[31];
-    /* line 3 */
-    unsigned int ticket_classify;     /* dynamic tile tickets of k_classify (beyond the first, static tile) */
-    unsigned int pad7[31];
-    /* line 4 */
-    unsigned int ticket_hscan;        /* dynamic chunk tickets of k_hscan */
-    unsigned int pad8[31];
-    /* line 5: end-of-kernel statistics */
+    /* line 5 */
+    unsigned long long n_work;        /* work-item cursor of k_classify (deferred predicates) */
+    unsigned int pad6[30];
+    /* line 6: end-of-kernel statistics */
     unsigned long long n_candidates;  /* distance tests performed */
     unsigned int n_cells_nonempty;
     unsigned int pad5[29];
-    /* per-slice cursors */
-    SliceMeta slice[ARP_MAX_SLICES];
+    /* dynamic tile tickets of k_classify */
+    struct alignas(128) { unsigned int v; unsigned int pad[31]; } ticket_cls[ARP_CLS_COUNTERS];
 };
 
 struct PlaneSet {
@@ -135,12 +123,8 @@ struct arp_ctx {
     int reg_blocks = -1;          /* co-resident blocks of k_grid_reg (0: not available, -1: not probed) */
     int use_plane_screen = 1;     /* plane terms: float32 distance screen + hit bitmask (0: plain double loops) */
     int use_pdl = 1;              /* pair kernels launched with programmatic stream serialization */
-    int want_slices = 0;          /* slices of the pair phase: 0 = by input size, otherwise forced (ARPEGGIO_SLICES) */
-    int want_cells = 0;           /* cells per search ticket: 0 = by input size, otherwise forced (ARPEGGIO_SEARCH_CELLS) */
-    int run_slices = 1;           /* what the last enqueue used */
-    uint64_t slice_cap = 0, slice_work_cap = 0;   /* per-slice capacities of the last enqueue */
-    cudaStream_t slice_stream[ARP_MAX_SLICES - 1] = {nullptr, nullptr, nullptr};   /* slice 0 runs on `stream` */
-    cudaEvent_t ev_fork = nullptr, ev_join[ARP_MAX_SLICES - 1] = {nullptr, nullptr, nullptr};
+    int use_early_cls = 1;        /* k_classify consumes candidates while k_search drains (ARPEGGIO_NO_EARLY_CLASSIFY turns it off) */
+    int hits_dirty = 0;           /* the candidate list may hold non-zero entries (a run without the early start) */
     RunMeta* h_meta = nullptr;    /* pinned */
     /* the zero region as the last register-grid run left it: counters, bounding boxes, cell counts and scan state
        all zero again, for exactly this allocation and layout (a run of another path, a failed enqueue or a new

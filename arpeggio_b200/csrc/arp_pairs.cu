@@ -695,24 +695,22 @@ __global__ void __launch_bounds__(REG_THREADS, 1) k_grid_reg(GridArgs G)
 #ifndef SEARCH_CELLS
 #define SEARCH_CELLS  4
 #endif
-/* most cells per ticket (<= 4; SearchArgs.cells of them are used); 8 lanes describe one cell's runs */
+/* cells per ticket (<= 4); 8 lanes describe one cell's runs */
 
 struct SearchArgs {
     const float4* pos4;
     const int*    cell_start;
     const StructGeom* geom;
     RunMeta*      meta;
-    uint2*        raw;                      /* this slice's candidate pairs (cell-sorted indices), float32 d^2 <= r2_hi */
-    unsigned long long cap;                 /* capacity of this slice's list */
-    int           slice, n_slices;          /* this launch handles tickets [T slice / n_slices, T (slice + 1) / n_slices) */
-    int           cells;                    /* cells per ticket, 1..SEARCH_CELLS */
+    uint2*        raw;                      /* candidate pairs (cell-sorted indices), float32 d^2 <= r2_hi */
+    unsigned long long cap;
 };
 
 /* the warp's queued candidates go to the global candidate list behind one cursor atomic */
 __device__ __forceinline__ void search_flush(const SearchArgs& A, const uint2* q, unsigned n, int lane)
 {
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&A.meta->slice[A.slice].n_raw, (unsigned long long)n);
+    if (lane == 0) base = atomicAdd(&A.meta->n_raw, (unsigned long long)n);
     base = __shfl_sync(FULL, base, 0);
     for (unsigned r = lane; r < n; r += 32)
         if (base + r < A.cap) A.raw[base + r] = q[r];
@@ -799,12 +797,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
        block in shared memory over a contiguous cell range per block, static tickets strided over the warps,
        and a grid of up to four times the resident blocks (the block scheduler as the balancer). */
     const unsigned n_warps_total = gridDim.x * SEARCH_WARPS;
-    const int cpt = A.cells;
-    const unsigned all_tickets = ((unsigned)n_cells + (unsigned)cpt - 1) / (unsigned)cpt;
-    /* this slice's tickets [t_lo, t_lo + n_tickets) */
-    const unsigned t_lo = (unsigned)((unsigned long long)all_tickets * (unsigned)A.slice / (unsigned)A.n_slices);
-    const unsigned n_tickets = (unsigned)((unsigned long long)all_tickets * (unsigned)(A.slice + 1) / (unsigned)A.n_slices) - t_lo;
-    unsigned* const ticket_ctr = &A.meta->slice[A.slice].ticket_search;
+    const unsigned n_tickets = ((unsigned)n_cells + SEARCH_CELLS - 1) / SEARCH_CELLS;
+    unsigned* const ticket_ctr = &A.meta->ticket_search;
     bool first = true;
     for (;;) {
         unsigned t = 0;
@@ -820,7 +814,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
             t = __shfl_sync(FULL, t, 0);
         }
         if (t >= n_tickets) break;
-        const long long c0l = (long long)(t_lo + t) * cpt;
+        const long long c0l = (long long)t * SEARCH_CELLS;
         const int c0 = (int)c0l;
         while (c0 >= s_end) { ++s; s_end = A.geom[s].cell_base + A.geom[s].ncell; }   /* tickets ascend */
         /* ---- run tables of the ticket's cells: lane = (cell q, run r) ---- */
@@ -829,7 +823,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
             const int c = c0 + qc;
             int rbeg = 0, rlen = 0, nh = 0;
             float band_lo = 0.f, band_hi = 0.f;
-            if (qc < cpt && c < n_cells) {
+            if (qc < SEARCH_CELLS && c < n_cells) {
                 const StructGeom* gp = A.geom + s;
                 while (c >= gp->cell_base + gp->ncell) ++gp;                  /* the cell may lie in a later structure */
                 band_lo = gp->r2_lo; band_hi = gp->r2_hi;
@@ -860,14 +854,14 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
             const int total = __shfl_sync(FULL, incl, 7, 8);
             nh = __shfl_sync(FULL, nh, 0, 8);
             __syncwarp();
-            if (qc < cpt) {
+            if (qc < SEARCH_CELLS) {
                 if (r < 5) s_runs[warp][qc][r] = make_int2(rbeg, incl - rlen);
                 else if (r == 5) s_runs[warp][qc][5] = make_int2(total, nh);
                 else if (r == 6) s_runs[warp][qc][6] = make_int2(__float_as_int(band_lo), __float_as_int(band_hi));
             }
             __syncwarp();
         }
-        for (int qc = 0; qc < cpt; ++qc) {
+        for (int qc = 0; qc < SEARCH_CELLS; ++qc) {
             const int2 tn = s_runs[warp][qc][5];
             const int total = tn.x, nh = tn.y;
             if (nh == 0) continue;
@@ -948,13 +942,12 @@ struct ClassifyArgs {
     unsigned      h_gen;                    /* generation of the current upload */
     const float4* pos4;
     const uint4*  att4;
-    uint2*        raw;                      /* this slice's candidate list; every entry is zeroed again once it is read */
+    uint2*        raw;                      /* candidate list; with the early start every entry is zeroed again once it is read */
     RunMeta*      meta;
     arp_pair*     out;
-    unsigned long long cap;                 /* capacity of this slice's candidate list */
-    uint4*        work;                     /* this slice's deferred predicates: (donor, acceptor | halogen, record index, kind) */
+    unsigned long long cap;                 /* capacity of the candidate list */
+    uint4*        work;                     /* deferred predicates: (donor, acceptor | halogen, record index, kind) */
     unsigned long long work_cap;
-    int           slice;
     double        r2;
     int           include_seq_adjacent;
     ArpSide       side;
@@ -984,15 +977,14 @@ __device__ __forceinline__ void bulk_store_wait_read_1()
 #define CLS_KIND_HAL   4u
 #define CLS_KIND_XBOND 5u
 
-#ifndef CLS_GROUP
-#define CLS_GROUP 1                         /* tiles per ticket */
-#endif
 
 /* candidate `pos` of the list: read from L2, waited for while k_search is still running (the cursor is advanced
    before the entries are stored), and zeroed for the next run */
 #define CLS_FAULT_HANDOFF 2u
+template <bool EARLY>
 __device__ __forceinline__ uint2 cls_fetch(const ClassifyArgs& A, unsigned long long pos, bool final)
 {
+    if (!EARLY) return A.raw[pos];
     uint2 v = __ldcg(A.raw + pos);
     if (!final) {
         unsigned spins = 0;
@@ -1007,6 +999,7 @@ __device__ __forceinline__ uint2 cls_fetch(const ClassifyArgs& A, unsigned long 
 #ifndef CLS_MINB
 #define CLS_MINB 4
 #endif
+template <bool EARLY>
 __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyArgs A, ArpRuleParams P)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
@@ -1046,40 +1039,51 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
        whose next tile is not handed out yet sleeps in griddepcontrol.wait until k_search has completed; from
        then on the count is final.  What k_search leaves in r2_lo_inv was written by the grid build, which had
        completed before k_search could trigger this launch. */
-    const volatile unsigned long long* const n_raw_p = &A.meta->slice[A.slice].n_raw;
+    const volatile unsigned long long* const n_raw_p = &A.meta->n_raw;
     const float r2_lo = A.meta->r2_lo_inv == 0x7f800000u ? -1.0f : __uint_as_float(0x7f800000u - A.meta->r2_lo_inv);
-    bool final = false;                                          /* k_search has completed: n and n_tiles are valid */
+    bool final = !EARLY;                                         /* k_search has completed: n and n_tiles are valid */
     unsigned long long n = 0, n_tiles = 0;
     int buf = 0;
-    /* Tickets of CLS_GROUP consecutive tiles, handed out dynamically because the blocks start at different times
-       (whenever k_search frees a slot).  ARP_CLS_COUNTERS counters share the work: counter c owns the tickets
-       congruent to c and serves the blocks congruent to c; a warp's first ticket is static (its rank among the
-       warps of its class), the rest come from the counter, requested one ticket ahead so that the atomic's
-       latency is hidden. */
+    if (!EARLY) {                                                /* large inputs: the drain of k_search is short against the job */
+        pdl_wait();
+        n = *n_raw_p;
+        if (n > A.cap) n = A.cap;                                /* overflowing run: host repeats it with a larger buffer */
+        n_tiles = (n + CLS_TILE - 1) / CLS_TILE;
+    }
+    /* Tiles.  Without the early start all blocks begin together: plain stride over the warps (tile = global warp
+       id + k * warps; contiguous shares per warp were measured 2 us slower -- the candidate list is not uniform
+       along its length and the stride spreads the expensive stretches).  With the early start the blocks begin
+       whenever k_search frees a slot, so the tiles are handed out dynamically: ARP_CLS_COUNTERS counters share
+       the work, counter c owns the tiles congruent to c and serves the blocks congruent to c; a warp's first tile
+       is static (its rank among the warps of its class), the rest come from the counter, requested one tile
+       ahead so that the atomic's latency is hidden. */
     const unsigned nc = min((unsigned)ARP_CLS_COUNTERS, gridDim.x);      /* classes in use: every one needs a block */
     const unsigned cls = blockIdx.x % nc;
-    unsigned* const ticket_ctr = &A.meta->slice[A.slice].ticket_cls[cls].v;
+    unsigned* const ticket_ctr = &A.meta->ticket_cls[cls].v;
     const unsigned long long class_warps = (unsigned long long)((gridDim.x - cls + nc - 1) / nc) * CLS_WARPS;
-    unsigned long long ticket = ((unsigned long long)(blockIdx.x / nc) * CLS_WARPS + warp) * nc + cls;
+    const unsigned long long n_warps = (unsigned long long)gridDim.x * CLS_WARPS;
+    unsigned long long tile = EARLY ? ((unsigned long long)(blockIdx.x / nc) * CLS_WARPS + warp) * nc + cls
+                                    : (unsigned long long)blockIdx.x * CLS_WARPS + warp;
     unsigned long long snap = 0;                                 /* the cursor when it was last read: a lower bound */
     for (;;) {
-        if (!final && (ticket + 1) * (CLS_GROUP * CLS_TILE) > min(snap, A.cap)) {
+        if (EARLY && !final && (tile + 1) * CLS_TILE > min(snap, A.cap)) {
             if (lane == 0) snap = *n_raw_p;                      /* look again */
             snap = __shfl_sync(FULL, snap, 0);
-            if ((ticket + 1) * (CLS_GROUP * CLS_TILE) > min(snap, A.cap)) {   /* not handed out yet (or holds the last, partial tile) */
+            if ((tile + 1) * CLS_TILE > min(snap, A.cap)) {      /* not handed out yet (or the last, partial tile) */
                 pdl_wait();                                      /* k_search has completed */
                 final = true;
                 n = *n_raw_p;
-                if (n > A.cap) n = A.cap;                        /* overflowing run: host repeats it with a larger buffer */
+                if (n > A.cap) n = A.cap;
                 n_tiles = (n + CLS_TILE - 1) / CLS_TILE;
             }
         }
-        if (final && ticket * CLS_GROUP >= n_tiles) break;
-        unsigned next_ticket = 0;                                /* requested now, used after this ticket's tiles */
+        if (final && tile >= n_tiles) break;
+        unsigned next_ticket = 0;                                /* requested now, used after this tile */
         unsigned long long seen = 0;
-        if (lane == 0) next_ticket = atomicAdd(ticket_ctr, 1u);
-        if (lane == 1 && !final) seen = *n_raw_p;
-      for (unsigned long long tile = ticket * CLS_GROUP; tile < (ticket + 1) * CLS_GROUP && (!final || tile < n_tiles); ++tile) {
+        if (EARLY) {
+            if (lane == 0) next_ticket = atomicAdd(ticket_ctr, 1u);
+            if (lane == 1 && !final) seen = *n_raw_p;
+        }
         const unsigned long long base = tile * CLS_TILE;
         const unsigned cnt = final ? (unsigned)min((unsigned long long)CLS_TILE, n - base) : (unsigned)CLS_TILE;
         int4* rec = rec0 + buf * CLS_TILE;
@@ -1087,13 +1091,13 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
         __syncwarp();
         /* ---- stages 0 + 1, 32 candidates per round ---- */
         unsigned nsurv = 0, n_items = 0;
-        uint2 e_next = lane < cnt ? cls_fetch(A, base + lane, final) : make_uint2(0, 0);   /* candidates are fetched one round ahead */
+        uint2 e_next = lane < cnt ? cls_fetch<EARLY>(A, base + lane, final) : make_uint2(0, 0);   /* candidates are fetched one round ahead */
 #pragma unroll 1
         for (unsigned i0 = 0; i0 < cnt; i0 += 32) {
             const unsigned idx = i0 + lane;
             bool keep = false;
             uint2 e = e_next;
-            if (idx + 32 < cnt) e_next = cls_fetch(A, base + idx + 32, final);
+            if (idx + 32 < cnt) e_next = cls_fetch<EARLY>(A, base + idx + 32, final);
             float4 pa, pb;
             uint4 ab, ae;
             if (idx < cnt) {
@@ -1146,6 +1150,8 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
                 }
             }
         }
+        tile = EARLY ? (class_warps + __shfl_sync(FULL, next_ticket, 0)) * nc + cls : tile + n_warps;
+        if (EARLY) snap = __shfl_sync(FULL, seen, 1);
         if (nsurv == 0) continue;                                /* nothing staged: the buffer stays free */
         __syncwarp();
         /* ---- stage 3: the tile leaves through the TMA engine; its work items go to the global work list ---- */
@@ -1153,7 +1159,7 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
         if (lane == 0) {
             o = atomicAdd(&A.meta->n_pairs, (unsigned long long)nsurv);
             bulk_store_tile(A.out + o, rec, nsurv * (uint32_t)sizeof(arp_pair));
-            if (n_items) ow = atomicAdd(&A.meta->slice[A.slice].n_work, (unsigned long long)n_items);
+            if (n_items) ow = atomicAdd(&A.meta->n_work, (unsigned long long)n_items);
         }
         o = __shfl_sync(FULL, o, 0);
         ow = __shfl_sync(FULL, ow, 0);
@@ -1166,9 +1172,6 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
         }
         __syncwarp();
         buf ^= 1;
-      }
-        ticket = (class_warps + __shfl_sync(FULL, next_ticket, 0)) * nc + cls;
-        snap = __shfl_sync(FULL, seen, 1);
     }
     if (lane == 0) bulk_store_wait_read_all();                   /* shared memory must outlive the copies */
 #ifdef PAIR_PROFILE
@@ -1184,22 +1187,18 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
 struct HscanArgs {
     const float4* pos4;
     const int2*   hrng;                     /* hydrogen range of every atom, cell order */
-    const uint4*  work;                     /* this slice's work list */
+    const uint4*  work;
     RunMeta*      meta;
     unsigned long long work_cap;
     arp_pair*     out;
     ArpSide       side;
-    int           slice;
-    int*          clean_cnt;                /* slice 0: the cell counts of the grid build, zeroed here for the next run */
+    int*          clean_cnt;                /* the cell counts of the grid build, zeroed here for the next run */
 };
 
 #ifndef HSCAN_MINB
 #define HSCAN_MINB 4
 #endif
 #define HSCAN_WARPS 8
-#ifndef HSCAN_DYNAMIC
-#define HSCAN_DYNAMIC 0
-#endif
 __global__ void __launch_bounds__(HSCAN_WARPS * 32, HSCAN_MINB) k_hscan(HscanArgs A, ArpRuleParams P)
 {
     __shared__ double s_vdw[CLS_TAB_K];
@@ -1216,17 +1215,14 @@ __global__ void __launch_bounds__(HSCAN_WARPS * 32, HSCAN_MINB) k_hscan(HscanArg
         for (unsigned k = blockIdx.x * (HSCAN_WARPS * 32) + threadIdx.x; k < nc; k += gridDim.x * (HSCAN_WARPS * 32))
             A.clean_cnt[k] = 0;
     }
-    unsigned long long n = A.meta->slice[A.slice].n_work;
+    unsigned long long n = A.meta->n_work;
     if (n > A.work_cap) n = A.work_cap;
-    /* chunks of 32 items per warp: the first one static (global warp id), the rest from a counter */
+    /* chunks of 32 items per warp, strided over the warps (chunks from a counter, one or sixteen, were measured
+       1-2 us slower: a chunk is 4-7 us of latency and a warp sees two of them) */
     const unsigned long long n_chunks = (n + 31) / 32;
     const unsigned long long n_warps = (unsigned long long)gridDim.x * HSCAN_WARPS;
-    for (unsigned long long chunk = (unsigned long long)blockIdx.x * HSCAN_WARPS + warp; chunk < n_chunks; ) {
+    for (unsigned long long chunk = (unsigned long long)blockIdx.x * HSCAN_WARPS + warp; chunk < n_chunks; chunk += n_warps) {
         const unsigned long long w = chunk * 32 + lane;
-#if HSCAN_DYNAMIC
-        unsigned next_ticket = 0;
-        if (lane == 0) next_ticket = atomicAdd(&A.meta->ticket_hscan, 1u);
-#endif
         if (w < n) {
         const uint4 it = A.work[w];
         const float4 pd = A.pos4[it.x], pa = A.pos4[it.y];
@@ -1249,11 +1245,6 @@ __global__ void __launch_bounds__(HSCAN_WARPS * 32, HSCAN_MINB) k_hscan(HscanArg
         }
         if (bits) atomicOr(&A.out[it.z].mask, bits);
         }
-#if HSCAN_DYNAMIC
-        chunk = n_warps + __shfl_sync(FULL, next_ticket, 0);
-#else
-        chunk += n_warps;
-#endif
     }
 #ifdef PAIR_PROFILE
     __syncthreads();
@@ -1453,26 +1444,10 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         side.xnbr = c->has_xnbr ? c->xnbr.as<float>() : nullptr;
         side.hlim = nullptr;                 /* k_classify builds it in shared memory */
 
-        /* ---- slices of the pair phase (see ARP_MAX_SLICES).  One by default: measured on a B200, two to four
-           slices of a 40k..300k-atom structure run no faster than one (profiles/README.md) -- the pair kernels
-           fill the register file, so blocks of different slices take turns instead of overlapping.  The
-           diagnostic timing with events between the kernels always runs one slice. ---- */
-        int n_slices = c->want_slices > 0 ? c->want_slices : 1;
-        if (split_events) n_slices = 1;
-        if (n_slices > ARP_MAX_SLICES) n_slices = ARP_MAX_SLICES;
-        for (int k = 0; k + 1 < n_slices; ++k) {           /* streams and events of the extra slices, created on first use */
-            if (!c->slice_stream[k]) ARP_CUDA(c, cudaStreamCreateWithFlags(&c->slice_stream[k], cudaStreamNonBlocking));
-            if (!c->ev_join[k]) ARP_CUDA(c, cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
-        }
-        if (n_slices > 1 && !c->ev_fork) ARP_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-        int cells = c->want_cells > 0 ? c->want_cells : SEARCH_CELLS;       /* cells per search ticket */
-        if (cells > SEARCH_CELLS) cells = SEARCH_CELLS;
-        c->run_slices = n_slices;
-        c->slice_cap = c->out_cap / (uint64_t)n_slices;
-        c->slice_work_cap = c->work_cap / (uint64_t)n_slices;
         const bool pdl = c->use_pdl != 0;
         if (!c->cls_smem_set) {             /* per device: > 48 KB of dynamic shared memory is opt-in */
-            ARP_CUDA(c, cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, CLS_SMEM));
+            ARP_CUDA(c, cudaFuncSetAttribute(k_classify<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CLS_SMEM));
+            ARP_CUDA(c, cudaFuncSetAttribute(k_classify<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CLS_SMEM));
             c->cls_smem_set = 1;
         }
         if (!c->hscan_blocks) {             /* a persistent grid: exactly the blocks that are resident together */
@@ -1482,59 +1457,49 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
             (void)cudaGetLastError();
             c->hscan_blocks = per_sm * c->sm_count;
         }
-        if (n_slices > 1) {
-            ARP_CUDA(c, cudaEventRecord(c->ev_fork, st));
-            for (int k = 0; k + 1 < n_slices; ++k) ARP_CUDA(c, cudaStreamWaitEvent(c->slice_stream[k], c->ev_fork, 0));
+        /* k_classify starts while k_search drains when that drain is a visible part of the job; the price is one
+           8-byte store per candidate (the list is left all zero), which costs more than it gains beyond ~5 * 10^5
+           atoms.  A list that a run without the early start left dirty is zeroed first.  The diagnostic timing with
+           events between the kernels measures the kernels one after the other. */
+        const int early = c->use_early_cls && N <= 500000 && !split_events;
+        if (early && c->hits_dirty) {
+            ARP_CUDA(c, cudaMemsetAsync(c->hits.p, 0, c->hits.cap, st));
+            c->hits_dirty = 0;
         }
-        /* kernel by kernel over the slices, so that the launches reach the device in the order they can start */
-        for (int sl = 0; sl < n_slices; ++sl) {
-            cudaStream_t ss = sl == 0 ? st : c->slice_stream[sl - 1];
-            SearchArgs SA;
-            SA.pos4 = c->pos4.as<float4>(); SA.cell_start = c->cell_start.as<int>();
-            SA.geom = c->geom.as<StructGeom>(); SA.meta = meta;
-            SA.raw = c->hits.as<uint2>() + (size_t)sl * c->slice_cap; SA.cap = c->slice_cap;
-            SA.slice = sl; SA.n_slices = n_slices; SA.cells = cells;
-            unsigned grid = (unsigned)(c->sm_count * SEARCH_GRID_MULT);
-            size_t want = ((size_t)N / 6 / (size_t)cells / (size_t)n_slices) / SEARCH_WARPS + 1;   /* about one warp per ticket on small inputs */
-            if (want < grid) grid = (unsigned)want;
-            ARP_CUDA(c, launch_k(k_search, grid, SEARCH_WARPS * 32, 0, ss, pdl, SA));
-            c->launches++;
-        }
+        if (!early) c->hits_dirty = 1;
+
+        SearchArgs SA;
+        SA.pos4 = c->pos4.as<float4>(); SA.cell_start = c->cell_start.as<int>();
+        SA.geom = c->geom.as<StructGeom>(); SA.meta = meta; SA.raw = c->hits.as<uint2>(); SA.cap = c->out_cap;
+        unsigned grid = (unsigned)(c->sm_count * SEARCH_GRID_MULT);
+        size_t want = ((size_t)N / (6 * SEARCH_CELLS)) / SEARCH_WARPS + 1;     /* about one warp per ticket on small inputs */
+        if (want < grid) grid = (unsigned)want;
+        ARP_CUDA(c, launch_k(k_search, grid, SEARCH_WARPS * 32, 0, st, pdl, SA));
+        c->launches++;
         if (split_events) ARP_CUDA(c, cudaEventRecord(c->ev[2], st));
-        for (int sl = 0; sl < n_slices; ++sl) {
-            cudaStream_t ss = sl == 0 ? st : c->slice_stream[sl - 1];
-            ClassifyArgs CA;
-            CA.h_reach = c->hreach.as<unsigned long long>(); CA.h_gen = c->upload_gen;
-            CA.pos4 = c->pos4.as<float4>(); CA.att4 = c->att4.as<uint4>();
-            CA.raw = c->hits.as<uint2>() + (size_t)sl * c->slice_cap; CA.cap = c->slice_cap; CA.meta = meta;
-            CA.out = c->out.as<arp_pair>(); CA.side = side;
-            CA.work = c->work.as<uint4>() + (size_t)sl * c->slice_work_cap; CA.work_cap = c->slice_work_cap;
-            CA.r2 = c->rp.r2; CA.include_seq_adjacent = c->rp.include_seq_adjacent; CA.slice = sl;
-            size_t tiles = (size_t)((c->slice_cap + CLS_TILE - 1) / CLS_TILE);
-            size_t blocks_needed = (tiles + CLS_WARPS - 1) / CLS_WARPS;
-            unsigned cgrid = (unsigned)(c->sm_count * CLS_MINB);
-            if (blocks_needed < cgrid) cgrid = (unsigned)(blocks_needed ? blocks_needed : 1);
-            ARP_CUDA(c, launch_k(k_classify, cgrid, CLS_WARPS * 32, CLS_SMEM, ss, pdl, CA, c->rp));
-            c->launches++;
-        }
+
+        ClassifyArgs CA;
+        CA.h_reach = c->hreach.as<unsigned long long>(); CA.h_gen = c->upload_gen;
+        CA.pos4 = SA.pos4; CA.att4 = c->att4.as<uint4>(); CA.raw = SA.raw; CA.cap = c->out_cap; CA.meta = meta;
+        CA.out = c->out.as<arp_pair>(); CA.side = side;
+        CA.work = c->work.as<uint4>(); CA.work_cap = c->work_cap;
+        CA.r2 = c->rp.r2; CA.include_seq_adjacent = c->rp.include_seq_adjacent;
+        size_t tiles = (size_t)((c->out_cap + CLS_TILE - 1) / CLS_TILE);
+        size_t blocks_needed = (tiles + CLS_WARPS - 1) / CLS_WARPS;
+        unsigned cgrid = (unsigned)(c->sm_count * CLS_MINB);
+        if (blocks_needed < cgrid) cgrid = (unsigned)(blocks_needed ? blocks_needed : 1);
+        ARP_CUDA(c, launch_k(early ? k_classify<true> : k_classify<false>, cgrid, CLS_WARPS * 32, CLS_SMEM, st, pdl, CA, c->rp));
+        c->launches++;
         if (split_events) ARP_CUDA(c, cudaEventRecord(c->ev[4], st));
-        for (int sl = 0; sl < n_slices; ++sl) {
-            cudaStream_t ss = sl == 0 ? st : c->slice_stream[sl - 1];
-            HscanArgs HA;
-            HA.pos4 = c->pos4.as<float4>(); HA.hrng = c->hrng.as<int2>();
-            HA.work = c->work.as<uint4>() + (size_t)sl * c->slice_work_cap; HA.meta = meta; HA.work_cap = c->slice_work_cap;
-            HA.out = c->out.as<arp_pair>(); HA.side = side; HA.slice = sl;
-            HA.clean_cnt = sl == 0 ? cell_cnt : nullptr;
-            size_t hb = (size_t)((c->slice_work_cap + 255) / 256);
-            unsigned hgrid = (unsigned)c->hscan_blocks;
-            if (hb < hgrid) hgrid = (unsigned)(hb ? hb : 1);
-            ARP_CUDA(c, launch_k(k_hscan, hgrid, HSCAN_WARPS * 32, 0, ss, pdl, HA, c->rp));
-            c->launches++;
-            if (sl > 0) {                   /* join: the context's stream continues after every slice */
-                ARP_CUDA(c, cudaEventRecord(c->ev_join[sl - 1], ss));
-                ARP_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[sl - 1], 0));
-            }
-        }
+
+        HscanArgs HA;
+        HA.pos4 = SA.pos4; HA.hrng = c->hrng.as<int2>(); HA.work = CA.work; HA.meta = meta; HA.work_cap = c->work_cap;
+        HA.out = CA.out; HA.side = side; HA.clean_cnt = cell_cnt;
+        size_t hb = (size_t)((c->work_cap + 255) / 256);
+        unsigned hgrid = (unsigned)c->hscan_blocks;
+        if (hb < hgrid) hgrid = (unsigned)(hb ? hb : 1);
+        ARP_CUDA(c, launch_k(k_hscan, hgrid, HSCAN_WARPS * 32, 0, st, pdl, HA, c->rp));
+        c->launches++;
     } else if (split_events) {
         ARP_CUDA(c, cudaEventRecord(c->ev[2], st));
         ARP_CUDA(c, cudaEventRecord(c->ev[4], st));

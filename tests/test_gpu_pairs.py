@@ -178,7 +178,8 @@ def test_batch_equals_per_structure(engine):
     util.assert_records_equal(got, util.sort_pairs(np.concatenate(pieces)), 'batch vs per-structure runs')
 
 
-@pytest.mark.parametrize('knob', [None, 'ARPEGGIO_NO_REG_GRID', 'ARPEGGIO_NO_FUSED_GRID', 'ARPEGGIO_NO_PDL'])
+@pytest.mark.parametrize('knob', [None, 'ARPEGGIO_NO_REG_GRID', 'ARPEGGIO_NO_FUSED_GRID', 'ARPEGGIO_NO_PDL',
+                                  'ARPEGGIO_NO_EARLY_CLASSIFY'])
 def test_every_grid_build_path(monkeypatch, knob):
     """The cell grid is built by one of three code paths (register-cached cooperative kernel with 1 or 2 atoms
     per thread, cooperative kernel through global memory, five kernels); each must give the oracle's stream for
@@ -197,32 +198,23 @@ def test_every_grid_build_path(monkeypatch, knob):
             util.assert_records_equal(eng.pairs(soa), oracle.pairs(soa, p), f'{knob or "default"} {name}')
 
 
-@pytest.mark.parametrize('slices,cells', [(1, 4), (2, 4), (2, 1), (3, 2), (4, 3)])
-def test_sliced_pair_phase(monkeypatch, slices, cells):
-    """The pair phase runs as 1..4 slices of the search tickets on their own streams, with 1..4 cells per ticket;
-    every combination must give the oracle's stream: one structure of either size class, a small batch, an input
-    with fewer cells than slices, and the golden ligand site."""
+def test_skewed_density_and_odd_sizes():
+    """Inputs that stress the hand-over between k_search and k_classify and the capacity logic: three atoms, a batch
+    with an empty structure, and one structure whose dense corner holds almost all candidates while a sparse remainder
+    stretches the grid (widened cells; the first guess of the list capacity overflows and is regrown)."""
     from arpeggio_b200.engine import ContactEngine
-    monkeypatch.setenv('ARPEGGIO_SLICES', str(slices))
-    monkeypatch.setenv('ARPEGGIO_SEARCH_CELLS', str(cells))
     p = arp_params.make_params()
     parts = [synth.cloud_featured(n, seed=170 + k) for k, n in enumerate((3000, 0, 17, 2500))]
+    dense = synth.cloud_featured(20_000, seed=163)
+    far = synth.cloud_featured(20_000, seed=164)
+    xyz = np.concatenate([dense.xyz * np.float32(0.6), far.xyz * np.float32(3.0) + np.float32(400.0)])
+    skew = dataclasses.replace(AtomSoA.concat([dense, far]), xyz=xyz, struct_off=None)
     cases = {'60k': synth.cloud_featured(60_000, seed=161), '3 atoms': synth.cloud_featured(3, seed=162),
-             'batch': AtomSoA.concat(parts)}
+             'batch': AtomSoA.concat(parts), 'skewed': skew}
     with ContactEngine(0, p) as eng:
         for name, soa in cases.items():
-            util.assert_records_equal(eng.pairs(soa), oracle.pairs(soa, p), f'{slices} slices, {cells} cells: {name}')
-        g = util.Golden('ligand_site')
-        eng.set_params(g.params)
-        util.assert_records_equal(eng.pairs(g.soa), g.exp_pairs, f'{slices} slices, {cells} cells: golden ligand_site')
-        # skewed density: almost all candidates fall into one slice, whose share of the candidate list overflows
-        # and is regrown
-        eng.set_params(p)
-        dense = synth.cloud_featured(20_000, seed=163)
-        far = synth.cloud_featured(20_000, seed=164)
-        xyz = np.concatenate([dense.xyz * np.float32(0.6), far.xyz * np.float32(3.0) + np.float32(400.0)])
-        skew = dataclasses.replace(AtomSoA.concat([dense, far]), xyz=xyz, struct_off=None)
-        util.assert_records_equal(eng.pairs(skew), oracle.pairs(skew, p), f'{slices} slices, {cells} cells: skewed')
+            util.assert_records_equal(eng.pairs(soa), oracle.pairs(soa, p), name)
+        util.assert_records_equal(eng.pairs(cases['60k']), oracle.pairs(cases['60k'], p), '60k after the regrown run')
 
 
 @pytest.mark.parametrize('case', [c for c in CASES if c != 'xbond_fault'])
@@ -299,6 +291,22 @@ def test_rerun_is_stable_and_overflow_regrows(engine):
         assert got.shape[0] > 2000 * 16 + 4096
         util.assert_records_equal(got, oracle.pairs(dense, p), 'dense after sparse')
         util.assert_records_equal(e2.pairs(), got, 'second run on resident inputs')
+
+
+def test_early_and_late_classify_alternate():
+    """Up to 5 * 10^5 atoms k_classify starts on the candidates while k_search drains and leaves the candidate list
+    zeroed; larger inputs wait for k_search and leave the list as it is.  Alternating the two on one context must
+    keep every stream identical to the oracle's (the list is zeroed again before an early run)."""
+    from arpeggio_b200.engine import ContactEngine
+    p = arp_params.make_params()
+    small = synth.cloud_featured(50_000, seed=301)
+    large = synth.cloud_featured(520_000, seed=302)
+    exp_small = oracle.pairs(small, p)
+    with ContactEngine(0, p) as eng:
+        util.assert_records_equal(eng.pairs(small), exp_small, 'early start, first run')
+        util.assert_records_equal(eng.pairs(large), oracle.pairs(large, p), 'late start, 520k atoms')
+        for k in range(3):
+            util.assert_records_equal(eng.pairs(small), exp_small, f'early start after a late one, run {k}')
 
 
 def test_flag_within(engine):

@@ -72,6 +72,8 @@ struct alignas(128) RunMeta {
     unsigned int pad5[29];
     /* dynamic tile tickets of k_classify */
     struct alignas(128) { unsigned int v; unsigned int pad[31]; } ticket_cls[ARP_CLS_COUNTERS];
+    /* dynamic cell tickets of k_search when it uses class counters (SEARCH_NC > 1) */
+    struct alignas(128) { unsigned int v; unsigned int pad[31]; } ticket_srch[ARP_CLS_COUNTERS];
 };
 
 struct PlaneSet {

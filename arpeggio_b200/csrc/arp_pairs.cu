@@ -361,6 +361,7 @@ struct ScatterArgs {
     const float* xyz; const uint32_t* feat; const int32_t* res_id; const uint16_t* rad_class;
     const int32_t* res_prev; const int32_t* res_next; const uint8_t* res_flags; const int32_t* bond_off;
     const int32_t* h_off;            /* null: no hydrogens uploaded */
+    const double* h_xyz;             /* hydrogens of the donors (k_grid_reg pulls them into L2 for k_hscan) */
     const int* cell_of; const int* rank; const int* cell_start;
     float4* pos4; uint4* att4; int2* hrng;
 };
@@ -669,6 +670,10 @@ __global__ void __launch_bounds__(REG_THREADS, 1) k_grid_reg(GridArgs G)
         G.sc.pos4[dst] = make_float4(x[k], y[k], z[k], __int_as_float(i));
         G.sc.att4[dst] = make_uint4(aw[k], (uint32_t)ar[k], (uint32_t)ap[k], (uint32_t)an[k]);
         G.sc.hrng[dst] = ah[k];
+        /* the donor's hydrogens are read once, by k_hscan at the end of the run, on its critical path: bring
+           their line into L2 now (up to five hydrogens per 128-byte line) */
+        if (ah[k].y > ah[k].x && G.sc.h_xyz)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(G.sc.h_xyz + 3 * (size_t)ah[k].x));
     }
     GRID_STAMP(9);
     PROF_STAMP(0, 1);
@@ -694,6 +699,9 @@ __global__ void __launch_bounds__(REG_THREADS, 1) k_grid_reg(GridArgs G)
 #define SEARCH_DRAIN  128
 #ifndef SEARCH_CELLS
 #define SEARCH_CELLS  4
+#endif
+#ifndef SEARCH_NC
+#define SEARCH_NC 1                         /* > 1: dynamic tickets from that many class counters (as in k_classify) */
 #endif
 /* cells per ticket (<= 4); 8 lanes describe one cell's runs */
 
@@ -798,19 +806,34 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, SEARCH_MINB) k_search(Searc
        and a grid of up to four times the resident blocks (the block scheduler as the balancer). */
     const unsigned n_warps_total = gridDim.x * SEARCH_WARPS;
     const unsigned n_tickets = ((unsigned)n_cells + SEARCH_CELLS - 1) / SEARCH_CELLS;
+#if SEARCH_NC > 1
+    const unsigned nc = min((unsigned)SEARCH_NC, gridDim.x);
+    const unsigned cls = blockIdx.x % nc;
+    unsigned* const ticket_ctr = &A.meta->ticket_srch[cls].v;
+    const unsigned class_warps = ((gridDim.x - cls + nc - 1) / nc) * SEARCH_WARPS;
+#else
     unsigned* const ticket_ctr = &A.meta->ticket_search;
+#endif
     bool first = true;
     for (;;) {
         unsigned t = 0;
         if (first) {
+#if SEARCH_NC > 1
+            t = ((blockIdx.x / nc) * SEARCH_WARPS + warp) * nc + cls;
+#else
             t = blockIdx.x * SEARCH_WARPS + warp;
+#endif
             first = false;
         } else {
+#if SEARCH_NC > 1
+            if (lane == 0) t = (class_warps + atomicAdd(ticket_ctr, 1u)) * nc + cls;
+#else
             if (lane == 0) {
                 t = n_tickets;
                 if (*(volatile unsigned*)ticket_ctr + n_warps_total < n_tickets)
                     t = atomicAdd(ticket_ctr, 1u) + n_warps_total;
             }
+#endif
             t = __shfl_sync(FULL, t, 0);
         }
         if (t >= n_tickets) break;
@@ -1210,11 +1233,6 @@ __global__ void __launch_bounds__(HSCAN_WARPS * 32, HSCAN_MINB) k_hscan(HscanArg
     }
     pdl_wait();                                                  /* k_classify has completed */
     PROF_STAMP(3, 0);
-    if (A.clean_cnt) {                                           /* the grid build is long over: leave its counts clean */
-        const unsigned nc = A.meta->n_cells + 1u;
-        for (unsigned k = blockIdx.x * (HSCAN_WARPS * 32) + threadIdx.x; k < nc; k += gridDim.x * (HSCAN_WARPS * 32))
-            A.clean_cnt[k] = 0;
-    }
     unsigned long long n = A.meta->n_work;
     if (n > A.work_cap) n = A.work_cap;
     /* chunks of 32 items per warp, strided over the warps (chunks from a counter, one or sixteen, were measured
@@ -1245,6 +1263,11 @@ __global__ void __launch_bounds__(HSCAN_WARPS * 32, HSCAN_MINB) k_hscan(HscanArg
         }
         if (bits) atomicOr(&A.out[it.z].mask, bits);
         }
+    }
+    if (A.clean_cnt) {                                           /* the grid build is long over: leave its counts clean */
+        const unsigned nc = A.meta->n_cells + 1u;
+        for (unsigned k = blockIdx.x * (HSCAN_WARPS * 32) + threadIdx.x; k < nc; k += gridDim.x * (HSCAN_WARPS * 32))
+            A.clean_cnt[k] = 0;
     }
 #ifdef PAIR_PROFILE
     __syncthreads();
@@ -1391,6 +1414,7 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         SC.res_next = c->res_next.as<int32_t>(); SC.res_flags = c->res_flags.as<uint8_t>();
         SC.bond_off = c->has_bonds ? c->bond_off.as<int32_t>() : nullptr;
         SC.h_off = c->has_h ? c->h_off.as<int32_t>() : nullptr;
+        SC.h_xyz = c->has_h && c->H > 0 ? c->h_xyz.as<double>() : nullptr;
         SC.hrng = c->hrng.as<int2>();
         SC.cell_of = c->cell_of.as<int>(); SC.rank = c->rank.as<int>(); SC.cell_start = c->cell_start.as<int>();
         SC.pos4 = c->pos4.as<float4>(); SC.att4 = c->att4.as<uint4>();

@@ -26,7 +26,7 @@ for r in rows[2:]:
     rd = float(d['dram__bytes_read.sum']) * scale[rows[1][hdr.index('dram__bytes_read.sum')]]
     wr = float(d['dram__bytes_write.sum']) * scale[rows[1][hdr.index('dram__bytes_write.sum')]]
     detail[name] = {'read': int(rd), 'write': int(wr), 'us': float(d['gpu__time_duration.sum'])}
-pair = [k for k in detail if k in ('k_search', 'k_classify', 'k_hscan')]
+pair = [k for k in detail if k.split('<')[0] in ('k_search', 'k_classify', 'k_hscan')]
 json.dump({'atoms': 100000, 'dram_bytes_per_launch': sum(detail[k]['read'] + detail[k]['write'] for k in pair),
            'kernels': pair, 'detail': detail,
            'source': f'ncu --set full --clock-control none (caches flushed before every replayed kernel, so lists that stay in L2 '

@@ -1370,6 +1370,16 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
     }
     const bool grid_event = with_events >= 2;         /* events between the kernels keep them from overlapping */
     const bool split_events = with_events >= 3;
+    /* k_classify starts while k_search drains when that drain is a visible part of the job; the price is one
+       8-byte store per candidate (the list is left all zero), which costs more than it gains beyond ~5 * 10^5
+       atoms.  The diagnostic timing with events between the kernels measures the kernels one after the other.
+       A list that an earlier run without the early start left dirty is zeroed first (state repair, not part of
+       this run: ahead of the first event). */
+    const int early = c->use_early_cls && N <= 500000 && !split_events;
+    if (early && c->hits_dirty && c->hits.p) {
+        ARP_CUDA(c, cudaMemsetAsync(c->hits.p, 0, c->hits.cap, st));
+        c->hits_dirty = 0;
+    }
     if (with_events) ARP_CUDA(c, cudaEventRecord(c->ev[0], st));
     /* Which grid build?  The register kernel needs no memset when the previous run on this layout of the zero
        region was one of its own (it zeroes its counters itself and every run leaves the rest clean). */
@@ -1480,15 +1490,6 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
                 per_sm = 1;
             (void)cudaGetLastError();
             c->hscan_blocks = per_sm * c->sm_count;
-        }
-        /* k_classify starts while k_search drains when that drain is a visible part of the job; the price is one
-           8-byte store per candidate (the list is left all zero), which costs more than it gains beyond ~5 * 10^5
-           atoms.  A list that a run without the early start left dirty is zeroed first.  The diagnostic timing with
-           events between the kernels measures the kernels one after the other. */
-        const int early = c->use_early_cls && N <= 500000 && !split_events;
-        if (early && c->hits_dirty) {
-            ARP_CUDA(c, cudaMemsetAsync(c->hits.p, 0, c->hits.cap, st));
-            c->hits_dirty = 0;
         }
         if (!early) c->hits_dirty = 1;
 

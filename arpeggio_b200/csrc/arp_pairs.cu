@@ -1497,7 +1497,10 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         SA.pos4 = c->pos4.as<float4>(); SA.cell_start = c->cell_start.as<int>();
         SA.geom = c->geom.as<StructGeom>(); SA.meta = meta; SA.raw = c->hits.as<uint2>(); SA.cap = c->out_cap;
         unsigned grid = (unsigned)(c->sm_count * SEARCH_GRID_MULT);
-        size_t want = ((size_t)N / (6 * SEARCH_CELLS)) / SEARCH_WARPS + 1;     /* about one warp per ticket on small inputs */
+#ifndef SEARCH_ATOMS_PER_CELL
+#define SEARCH_ATOMS_PER_CELL 5      /* 5.7 at protein density; a block too many exits at once, one too few leaves tickets to the counter */
+#endif
+        size_t want = ((size_t)N / (SEARCH_ATOMS_PER_CELL * SEARCH_CELLS)) / SEARCH_WARPS + 1;     /* about one warp per ticket on small inputs */
         if (want < grid) grid = (unsigned)want;
         ARP_CUDA(c, launch_k(k_search, grid, SEARCH_WARPS * 32, 0, st, pdl, SA));
         c->launches++;

@@ -51,6 +51,10 @@ CASES = {
     'wide_cutoff': (dict(seed=14, n_chains=2, n_res=12, n_waters=6), ['/A/3/', '/A/4/', 'RESNAME:LIG'], 6.5, 0.25, False),
     'degenerate': (dict(seed=15, n_chains=1, n_res=12, n_waters=6, degenerate=True), ['RESNAME:DEG', 'RESNAME:LIG'], 5.0, 0.1, False),
     'xbond_fault': (dict(seed=16, n_chains=1, n_res=10, n_waters=4, lone_xdonor=True), ['RESNAME:LIG'], 5.0, 0.1, False),
+    'tight_cutoff': (dict(seed=21, n_chains=2, n_res=18, n_waters=10), ['RESNAME:LIG'], 3.5, 0.0, False),
+    'big_site': (dict(seed=22, n_chains=3, n_res=40, n_waters=40), ['/A/5/', '/B/7/', 'RESNAME:LIG'], 5.0, 0.1, False),
+    'no_explicit_h': (dict(seed=23, n_chains=2, n_res=16, n_waters=8, explicit_h=False), ['RESNAME:LIG'], 5.0, 0.1, False),
+    'apo_adjacent': (dict(seed=24, n_chains=2, n_res=20, n_waters=12, ligand=False), [], 4.0, 0.2, True),
 }
 
 

@@ -118,7 +118,8 @@ def ring_assignment(kwargs):
     return out
 
 
-def run_case(name, kwargs, selections, cutoff, vdw_comp, incl):
+def compute_case(name, kwargs, selections, cutoff, vdw_comp, incl, verbose=True):
+    """Run the reference on one seeded mock complex; returns the arrays of a fixture (nothing is written)."""
     cx = mockbio.build_complex(**kwargs)
     ic = reference_complex(cx)
     meta = dict(case=name, recipe=kwargs, selections=selections, cutoff=cutoff, vdw_comp=vdw_comp,
@@ -127,7 +128,8 @@ def run_case(name, kwargs, selections, cutoff, vdw_comp, incl):
         ic.run_arpeggio(selections, cutoff, vdw_comp, incl)
     except AttributeError as err:           # utils.py:173 on a donor without single-bond neighbour
         meta['raises'] = 'AttributeError'
-        print(f'  {name}: reference raised AttributeError ({err})')
+        if verbose:
+            print(f'  {name}: reference raised AttributeError ({err})')
         # selection bookkeeping is complete at that point; contacts are not
         ic.atom_contacts = []
     packed = pack_complex(ic)
@@ -218,8 +220,15 @@ def run_case(name, kwargs, selections, cutoff, vdw_comp, incl):
         amide_flags=packed.amides.flags,
         exp_atom_sifts=atom_sifts, exp_pairs=pairs, exp_ring_ring=rr, exp_atom_ring=ap, exp_amide_amide=aa, exp_amide_ring=ar,
         meta=np.array(json.dumps(meta)), contacts_json=np.array(contacts_json), **ring_assignment(kwargs))
+    return arrays
+
+
+def run_case(name, kwargs, selections, cutoff, vdw_comp, incl):
+    arrays = compute_case(name, kwargs, selections, cutoff, vdw_comp, incl)
     np.savez_compressed(os.path.join(HERE, name + '.npz'), **arrays)
-    print(f'  {name}: N={len(packed.atoms)} pairs={len(pairs)} ring-ring={len(rr)} atom-ring={len(ap)} '
+    pairs, rr, ap, aa, ar = (arrays[k] for k in ('exp_pairs', 'exp_ring_ring', 'exp_atom_ring', 'exp_amide_amide', 'exp_amide_ring'))
+    n_atoms = arrays['xyz'].shape[0]
+    print(f'  {name}: N={n_atoms} pairs={len(pairs)} ring-ring={len(rr)} atom-ring={len(ap)} '
           f'amide-amide={len(aa)} amide-ring={len(ar)}')
     from collections import Counter
     bits = Counter()

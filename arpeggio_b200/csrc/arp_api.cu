@@ -415,7 +415,7 @@ int arp_pairs_run(arp_ctx* c, uint64_t* n_pairs)
         ARP_TRY(arp_pairs_enqueue(c, 1));
         ARP_CUDA(c, cudaStreamSynchronize(c->stream));
         const uint64_t n = c->h_meta->n_raw;    /* candidates >= records: both lists share the capacity */
-        const uint64_t nw = c->h_meta->n_work;
+        const uint64_t nw = c->h_meta->n_work + c->h_meta->n_work_rare;     /* the list is filled from both ends */
         if (n <= c->out_cap && nw <= c->work_cap) break;
         ARP_REQUIRE(c, attempt < 2, ARP_E_CAPACITY, "record stream overflowed repeatedly");
         if (n > c->out_cap) ARP_TRY(pairs_out_reserve(c, n + n / 16 + 1024));

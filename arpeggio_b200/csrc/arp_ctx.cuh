@@ -64,8 +64,10 @@ struct alignas(128) RunMeta {
     unsigned int ticket_scan;         /* dynamic tile ids of the cell scan */
     unsigned int pad4[31];
     /* line 5 */
-    unsigned long long n_work;        /* work-item cursor of k_classify (deferred predicates) */
+    unsigned long long n_work;        /* work-item cursor of k_classify: hydrogen scans, from the front of the list */
     unsigned int pad6[30];
+    unsigned long long n_work_rare;   /* the rare predicates (halogen weak hbond, xbond), from the back of the list */
+    unsigned int pad9[30];
     /* line 6: end-of-kernel statistics */
     unsigned long long n_candidates;  /* distance tests performed */
     unsigned int n_cells_nonempty;

@@ -1113,7 +1113,7 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
         if (lane == 0) bulk_store_wait_read_1();                 /* the store that last used this buffer has read it */
         __syncwarp();
         /* ---- stages 0 + 1, 32 candidates per round ---- */
-        unsigned nsurv = 0, n_items = 0;
+        unsigned nsurv = 0, n_items = 0, n_rare = 0;             /* rare items are staged from the back of `items` */
         uint2 e_next = lane < cnt ? cls_fetch<EARLY>(A, base + lane, final) : make_uint2(0, 0);   /* candidates are fetched one round ahead */
 #pragma unroll 1
         for (unsigned i0 = 0; i0 < cnt; i0 += 32) {
@@ -1164,12 +1164,12 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
                 if (__any_sync(FULL, rare != 0)) {
                     m = __ballot_sync(FULL, (rare & (ARP_WORK_HAL0 | ARP_WORK_HAL1)) != 0);
                     if (rare & (ARP_WORK_HAL0 | ARP_WORK_HAL1))
-                        items[n_items + __popc(m & lt_mask)] = ((rare & ARP_WORK_HAL1) ? it1 : it0) | CLS_KIND_HAL;
-                    n_items += __popc(m);
+                        items[CLS_ITEMS - 1 - (n_rare + __popc(m & lt_mask))] = ((rare & ARP_WORK_HAL1) ? it1 : it0) | CLS_KIND_HAL;
+                    n_rare += __popc(m);
                     m = __ballot_sync(FULL, (rare & (ARP_WORK_XB0 | ARP_WORK_XB1)) != 0);
                     if (rare & (ARP_WORK_XB0 | ARP_WORK_XB1))
-                        items[n_items + __popc(m & lt_mask)] = ((rare & ARP_WORK_XB1) ? it1 : it0) | CLS_KIND_XBOND;
-                    n_items += __popc(m);
+                        items[CLS_ITEMS - 1 - (n_rare + __popc(m & lt_mask))] = ((rare & ARP_WORK_XB1) ? it1 : it0) | CLS_KIND_XBOND;
+                    n_rare += __popc(m);
                 }
             }
         }
@@ -1178,20 +1178,28 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
         if (nsurv == 0) continue;                                /* nothing staged: the buffer stays free */
         __syncwarp();
         /* ---- stage 3: the tile leaves through the TMA engine; its work items go to the global work list ---- */
-        unsigned long long o = 0, ow = 0;
+        /* The hydrogen scans fill the work list from its front, the rare predicates (halogen weak hbond, xbond:
+           a few per cent of the items) from its back: one of them in a chunk of 32 would make the whole warp of
+           k_hscan walk a second, different chain of loads. */
+        unsigned long long o = 0, ow = 0, owr = 0;
         if (lane == 0) {
             o = atomicAdd(&A.meta->n_pairs, (unsigned long long)nsurv);
             bulk_store_tile(A.out + o, rec, nsurv * (uint32_t)sizeof(arp_pair));
             if (n_items) ow = atomicAdd(&A.meta->n_work, (unsigned long long)n_items);
+            if (n_rare) owr = atomicAdd(&A.meta->n_work_rare, (unsigned long long)n_rare);
         }
         o = __shfl_sync(FULL, o, 0);
         ow = __shfl_sync(FULL, ow, 0);
-        for (unsigned w = lane; w < n_items; w += 32) {
-            const uint32_t it = items[w];
+        owr = __shfl_sync(FULL, owr, 0);
+        for (unsigned w = lane; w < n_items + n_rare; w += 32) {
+            const bool is_rare = w >= n_items;
+            const uint32_t it = is_rare ? items[CLS_ITEMS - 1 - (w - n_items)] : items[w];
             const unsigned slot = (it >> 4) & 0xfffu;
             uint2 e = surv[slot];
             if (it & 8u) { const unsigned t = e.x; e.x = e.y; e.y = t; }   /* e.x = donor, e.y = acceptor / halogen */
-            if (ow + w < A.work_cap) A.work[ow + w] = make_uint4(e.x, e.y, (uint32_t)(o + slot), (it & 7u) | ((it >> 16) << 8));
+            const unsigned long long pos = is_rare ? owr + (w - n_items) : ow + w;
+            if (pos < A.work_cap)
+                A.work[is_rare ? A.work_cap - 1 - pos : pos] = make_uint4(e.x, e.y, (uint32_t)(o + slot), (it & 7u) | ((it >> 16) << 8));
         }
         __syncwarp();
         buf ^= 1;
@@ -1233,16 +1241,17 @@ __global__ void __launch_bounds__(HSCAN_WARPS * 32, HSCAN_MINB) k_hscan(HscanArg
     }
     pdl_wait();                                                  /* k_classify has completed */
     PROF_STAMP(3, 0);
-    unsigned long long n = A.meta->n_work;
-    if (n > A.work_cap) n = A.work_cap;
+    unsigned long long n = A.meta->n_work, n_rare = A.meta->n_work_rare;
+    if (n + n_rare > A.work_cap) n = n_rare = 0;                 /* the two ends of the list met: host repeats the run with a larger list */
     /* chunks of 32 items per warp, strided over the warps (chunks from a counter, one or sixteen, were measured
        1-2 us slower: a chunk is 4-7 us of latency and a warp sees two of them) */
-    const unsigned long long n_chunks = (n + 31) / 32;
+    const unsigned long long c_front = (n + 31) / 32, n_chunks = c_front + (n_rare + 31) / 32;
     const unsigned long long n_warps = (unsigned long long)gridDim.x * HSCAN_WARPS;
     for (unsigned long long chunk = (unsigned long long)blockIdx.x * HSCAN_WARPS + warp; chunk < n_chunks; chunk += n_warps) {
-        const unsigned long long w = chunk * 32 + lane;
-        if (w < n) {
-        const uint4 it = A.work[w];
+        const bool back = chunk >= c_front;                      /* a chunk of rare predicates, from the back of the list */
+        const unsigned long long w = (back ? chunk - c_front : chunk) * 32 + lane;
+        if (w < (back ? n_rare : n)) {
+        const uint4 it = A.work[back ? A.work_cap - 1 - w : w];
         const float4 pd = A.pos4[it.x], pa = A.pos4[it.y];
         const uint32_t kind = it.w & 7u;
         const double vdw_a = A.side.vdw[it.w >> 8];

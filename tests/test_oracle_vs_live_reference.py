@@ -59,3 +59,19 @@ def test_oracle_equals_the_running_reference(make_golden, k):
     sifts = oracle.atom_sifts(z['exp_pairs'], soa.n_atoms)
     for f in sifts.dtype.names:
         assert np.array_equal(sifts[f], z['exp_atom_sifts'][f]), what + ' per-atom ' + f
+
+
+def test_default_thresholds_are_the_references_config():
+    """params.DEFAULT_CONTACT_TYPES / DEFAULT_DIST_MAX / DEFAULT_H_VDW restate config.py:592-660 and :23-25; here they
+    are compared with the reference's own module, key by key (the drop-in reads the live config anyway)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('ref_config', '/root/reference/arpeggio/core/config.py')
+    cfg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cfg)
+    ours = arp_params.DEFAULT_CONTACT_TYPES
+    for kind, entries in ours.items():
+        assert kind in cfg.CONTACT_TYPES, kind
+        for key, value in entries.items():
+            assert cfg.CONTACT_TYPES[kind][key] == value, (kind, key, cfg.CONTACT_TYPES[kind][key], value)
+    assert cfg.CONTACT_TYPES_DIST_MAX == arp_params.DEFAULT_DIST_MAX
+    assert cfg.VDW_RADII['H'] == arp_params.DEFAULT_H_VDW

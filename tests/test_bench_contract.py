@@ -50,3 +50,24 @@ def test_product_arm_fails_loudly_without_a_device():
     assert r.returncode != 0
     assert 'no CUDA device' in (r.stderr + r.stdout) or 'no CPU fallback' in (r.stderr + r.stdout)
     assert not any(ln.startswith('{') for ln in r.stdout.splitlines())
+
+
+@pytest.mark.gpu
+def test_product_arm_prints_the_contract_line():
+    r = _run('--steps', '5', '--warmup', '3', '--batch-structures', '12', timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert 'impl' not in d and d['metric'] == 'classified atom-pairs/s' and d['n_gpus'] == 1 and d['steps'] == 5
+    assert d['value'] > 1e9 and d['scaling'] == 'weak' and d['data'] == 'synthetic' and d['vs_baseline'] is None
+    assert d['gpu_launches'] == d['kernels_per_step'] * d['steps'] and d['kernels_per_step'] >= 3
+    e = d['e2e']
+    assert 0 < e['value'] < d['value'] and e['h2d_bytes_per_step'] > 0 and e['d2h_bytes_per_step'] >= 16 * d['config']['pairs_per_structure']
+    rf = d['roofline']
+    assert rf['bound'] == 'hbm' and rf['unit'] == 'GB/s' and abs(rf['frac'] - rf['achieved'] / rf['peak']) < 1e-9
+    assert rf['algorithmic_bytes'] > 16 * d['config']['pairs_per_structure']
+    cb = d['cpu_baseline']
+    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] > 0
+    assert 'sm_mhz' in d['clocks'] and 'reasons' in d['clocks']
+    assert d['batch']['structures'] == 12 and d['batch']['value'] > 0

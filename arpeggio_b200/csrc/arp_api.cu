@@ -193,6 +193,8 @@ int arp_create(int device, arp_ctx** out)
     if (getenv("ARPEGGIO_NO_PLANE_SCREEN")) c->use_plane_screen = 0; /* A-B knob: unscreened double loops for the plane terms */
     if (getenv("ARPEGGIO_NO_PDL")) c->use_pdl = 0;                   /* A-B knob: plain stream-ordered launches */
     if (getenv("ARPEGGIO_NO_FUSED_GRID")) c->use_fused_grid = 0;
+    if (getenv("ARPEGGIO_TILES")) c->use_tiles = 1;                                     /* A-B knob: the fused tile kernel instead of k_search + k_classify */
+    if (const char* tx = getenv("ARPEGGIO_TILE_X")) { int v = atoi(tx); if (v >= 1 && v <= ARP_TILE_XMAX) c->tile_x = v; }
     if (getenv("ARPEGGIO_NO_EARLY_CLASSIFY")) c->use_early_cls = 0;                     /* A-B knob: k_classify waits for k_search */
     if (getenv("ARPEGGIO_NO_REG_GRID") && c->use_fused_grid > 1) c->use_fused_grid = 1;     /* debugging / A-B knob: five-kernel grid build */
     memset(&c->stats, 0, sizeof c->stats);
@@ -210,7 +212,7 @@ void arp_destroy(arp_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     DBuf* bufs[] = { &c->xyz, &c->feat, &c->res_id, &c->rad_class, &c->vdw, &c->cov, &c->res_prev, &c->res_next,
                      &c->res_flags, &c->bond_off, &c->bond_nbr, &c->h_off, &c->h_xyz, &c->xnbr, &c->struct_off,
-                     &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->hrng, &c->sift_acc, &c->sift_out, &c->ring_scratch, &c->hreach, &c->arena, &c->out, &c->hits, &c->work,
+                     &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->runtab, &c->sift_acc, &c->sift_out, &c->ring_scratch, &c->hreach, &c->arena, &c->out, &c->hits, &c->work,
                      &c->radtab, &c->sort_tmp, &c->sort_out, &c->sort_zero, &c->sort_off, &c->within, &c->flush };
     for (DBuf* b : bufs) dbuf_free(*b);
     arp_planes_release(c);
@@ -362,7 +364,7 @@ static int pairs_out_reserve(arp_ctx* c, uint64_t records)
     if (records <= c->out_cap && c->out.p) return ARP_OK;
     ARP_TRY(dbuf_reserve(c, c->out, (size_t)records * sizeof(arp_pair)));
     c->out_cap = c->out.cap / sizeof(arp_pair);
-    {   /* the candidate list is all zero between runs (k_classify zeroes what it reads): a new allocation starts so */
+    if (!c->use_tiles) {   /* the candidate list is all zero between runs (k_classify zeroes what it reads): a new allocation starts so */
         const void* before = c->hits.p;
         const size_t cap_before = c->hits.cap;
         ARP_TRY(dbuf_reserve(c, c->hits, (size_t)c->out_cap * sizeof(uint2)));
@@ -414,7 +416,8 @@ int arp_pairs_run(arp_ctx* c, uint64_t* n_pairs)
     for (int attempt = 0; attempt < 3; ++attempt) {
         ARP_TRY(arp_pairs_enqueue(c, 1));
         ARP_CUDA(c, cudaStreamSynchronize(c->stream));
-        const uint64_t n = c->h_meta->n_raw;    /* candidates >= records: both lists share the capacity */
+        /* candidates >= records: both lists share the capacity (k_tiles has no candidate list: n_raw stays 0) */
+        const uint64_t n = c->h_meta->n_raw > c->h_meta->n_pairs ? c->h_meta->n_raw : c->h_meta->n_pairs;
         const uint64_t nw = c->h_meta->n_work + c->h_meta->n_work_rare;     /* the list is filled from both ends */
         if (n <= c->out_cap && nw <= c->work_cap) break;
         ARP_REQUIRE(c, attempt < 2, ARP_E_CAPACITY, "record stream overflowed repeatedly");

@@ -33,8 +33,17 @@ struct StructGeom {
     float  r2_lo, r2_hi;    /* float32 d^2 at or below r2_lo is certainly within the cutoff,
                                above r2_hi certainly outside; in between the exact double
                                test of Bio.PDB.kdtrees decides */
+    /* work units of the tile kernel (k_tiles): a unit is a segment of seg_x consecutive home cells of one x-row */
+    int    seg_x;           /* home cells per unit (1 .. ARP_TILE_XMAX), chosen from the structure's mean cell population */
+    int    nseg;            /* segments per row = ceil(dx / seg_x) */
+    int    n_units;         /* nseg * dy * dz */
+    int    unit_base;       /* global id of the structure's first unit */
     int    pad;
 };
+
+/* tile kernel: most home cells per unit, atoms staged per unit (shared-memory capacity) */
+#define ARP_TILE_XMAX 8
+#define ARP_TILE_CAP  512
 
 /* k_classify hands out its tiles from ARP_CLS_COUNTERS counters, each serving the tickets and the blocks of one
    residue class modulo ARP_CLS_COUNTERS (same-address atomics serialise in L2: one counter for 20 000 tiles
@@ -50,7 +59,8 @@ struct alignas(128) RunMeta {
     unsigned int n_cells;
     unsigned int r2_lo_inv;           /* 0x7f800000 - bits(min over structures of r2_lo); 0x7f800000 = no quick accept */
     unsigned int fault;               /* sticky device-side diagnostics */
-    unsigned int pad0[29];
+    unsigned int n_units;             /* work units of k_tiles (all structures) */
+    unsigned int pad0[28];
     /* line 1 */
     unsigned long long n_raw;         /* candidate cursor of k_search */
     unsigned int pad1[30];
@@ -115,7 +125,8 @@ struct arp_ctx {
     DBuf zero;                    /* one memset per run: RunMeta | bbox | cell_cnt | scan_state */
     size_t zero_bytes = 0, off_bbox = 0, off_cnt = 0, off_state = 0;
     size_t cell_bound = 0;        /* upper bound of the number of cells, all structures */
-    DBuf geom, cell_start, cell_of, rank, pos4, att4, hrng;
+    DBuf geom, cell_start, cell_of, rank, pos4, att4;
+    DBuf runtab;                  /* per-cell run tables of k_tiles: int2[6] per cell (arp_pairs.cu dev_runtab) */
     DBuf radtab;                  /* K x K float32 proximity thresholds */
     DBuf hreach;                  /* upload generation << 32 | float bits of the longest donor-hydrogen distance */
     unsigned upload_gen = 0;
@@ -127,6 +138,11 @@ struct arp_ctx {
     int reg_blocks = -1;          /* co-resident blocks of k_grid_reg (0: not available, -1: not probed) */
     int use_plane_screen = 1;     /* plane terms: float32 distance screen + hit bitmask (0: plain double loops) */
     int use_pdl = 1;              /* pair kernels launched with programmatic stream serialization */
+    int use_tiles = 0;            /* 1: search + classify as ONE kernel on TMA-staged shared-memory tiles (k_tiles, arp_tiles.cuh;
+                                     ARPEGGIO_TILES=1).  Bit-exact, but measured slower than k_search + k_classify (72 vs 58 us at
+                                     100k atoms, 463 vs 374 us at 1M): 16 warps per SM against 32 (profiles/README.md, round 2) */
+    int tile_x = ARP_TILE_XMAX;   /* most home cells per unit of k_tiles (ARPEGGIO_TILE_X) */
+    int tiles_blocks = 0;         /* co-resident blocks of k_tiles (probed once) */
     int use_early_cls = 1;        /* k_classify consumes candidates while k_search drains (ARPEGGIO_NO_EARLY_CLASSIFY turns it off) */
     int hits_dirty = 0;           /* the candidate list may hold non-zero entries (a run without the early start) */
     RunMeta* h_meta = nullptr;    /* pinned */

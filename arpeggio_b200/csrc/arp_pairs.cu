@@ -163,7 +163,7 @@ __device__ __forceinline__ void dev_bbox(const float* __restrict__ xyz, const in
 
 /* grid of one structure with n > 0 atoms from its bounding box (cell_base is filled in by the caller);
    returns false when a coordinate is NaN / Inf (one cell, every test exact) */
-__device__ __forceinline__ bool geom_make(const unsigned* __restrict__ bb, int n, double cutoff, StructGeom& g)
+__device__ __forceinline__ bool geom_make(const unsigned* __restrict__ bb, int n, double cutoff, int tile_x, StructGeom& g)
 {
     double mn[3], mx[3], amax = 0.0;
     bool finite = true;
@@ -187,6 +187,19 @@ __device__ __forceinline__ bool geom_make(const unsigned* __restrict__ bb, int n
     g.inv_w = 1.0 / w;
     g.dx = (int)d[0]; g.dy = (int)d[1]; g.dz = (int)d[2];
     g.ncell = g.dx * g.dy * g.dz;
+    {   /* work units of k_tiles: segments of seg_x home cells of one x-row; a unit stages the segment's five
+           neighbour-row windows, (5 seg_x + 9) cells, which should fit ARP_TILE_CAP atoms with room for the
+           fluctuations of the cell population (a unit that does not fit is still correct: it reads global memory) */
+        const double per_cell = (double)n / (double)g.ncell;
+        int sx = (int)floor(((double)ARP_TILE_CAP / (1.5 * per_cell) - 9.0) / 5.0);
+        sx = sx < 1 ? 1 : sx;
+        sx = sx > tile_x ? tile_x : sx;
+        sx = sx > g.dx ? g.dx : sx;
+        g.seg_x = sx;
+        g.nseg = (g.dx + sx - 1) / sx;
+        g.n_units = g.nseg * g.dy * g.dz;
+        g.unit_base = 0;
+    }
     /* float32 prefilter band around r^2: u bounds one ulp of any coordinate */
     double u = amax * 1.1920928955078125e-07;
     double r2 = r * r;
@@ -207,47 +220,52 @@ __device__ __forceinline__ unsigned r2_lo_key(float r2_lo)
 /* all structures, one block of THREADS threads: grids + global cell numbering (block scan) */
 template <int THREADS>
 __device__ __forceinline__ void dev_geom(const unsigned* __restrict__ bbox, const int* __restrict__ struct_off,
-                                         int S, int N, double cutoff, StructGeom* __restrict__ geom,
+                                         int S, int N, double cutoff, int tile_x, StructGeom* __restrict__ geom,
                                          RunMeta* __restrict__ meta)
 {
-    __shared__ int s_sum[THREADS];
-    __shared__ int s_carry;
+    __shared__ long long s_sum[THREADS];      /* units << 32 | cells: both totals stay below 2^31 */
+    __shared__ long long s_carry;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     for (int s0 = 0; s0 < S; s0 += blockDim.x) {
         int s = s0 + threadIdx.x;
         StructGeom g;
         memset(&g, 0, sizeof g);
-        int ncell = 0;
+        long long mine = 0;
         if (s < S) {
             int lo = struct_off ? struct_off[s] : 0, hi = struct_off ? struct_off[s + 1] : N;
             int n = hi - lo;
             if (n > 0) {
-                if (!geom_make(bbox + 6 * (size_t)s, n, cutoff, g)) atomicOr(&meta->fault, 1u);
-                ncell = g.ncell;
+                if (!geom_make(bbox + 6 * (size_t)s, n, cutoff, tile_x, g)) atomicOr(&meta->fault, 1u);
+                mine = ((long long)g.n_units << 32) | (long long)g.ncell;
                 atomicMax(&meta->r2_lo_inv, r2_lo_key(g.r2_lo));
             }
         }
-        /* block exclusive scan of ncell */
-        s_sum[threadIdx.x] = ncell;
+        /* block exclusive scan of (units, cells) */
+        s_sum[threadIdx.x] = mine;
         __syncthreads();
         for (int off = 1; off < blockDim.x; off <<= 1) {
-            int t = threadIdx.x >= off ? s_sum[threadIdx.x - off] : 0;
+            long long t = threadIdx.x >= off ? s_sum[threadIdx.x - off] : 0;
             __syncthreads();
             s_sum[threadIdx.x] += t;
             __syncthreads();
         }
-        int incl = s_sum[threadIdx.x];
-        int carry = s_carry;
+        long long incl = s_sum[threadIdx.x];
+        long long carry = s_carry;
         if (s < S) {
-            g.cell_base = carry + incl - ncell;
+            const long long excl = carry + incl - mine;
+            g.cell_base = (int)(excl & 0xffffffffll);
+            g.unit_base = (int)(excl >> 32);
             geom[s] = g;
         }
         __syncthreads();
         if (threadIdx.x == blockDim.x - 1) s_carry = carry + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) meta->n_cells = (unsigned)s_carry;
+    if (threadIdx.x == 0) {
+        meta->n_cells = (unsigned)(s_carry & 0xffffffffll);
+        meta->n_units = (unsigned)(s_carry >> 32);
+    }
 }
 
 __device__ __forceinline__ int cell_coord(double v, double o, double inv_w, int dim)
@@ -363,7 +381,8 @@ struct ScatterArgs {
     const int32_t* h_off;            /* null: no hydrogens uploaded */
     const double* h_xyz;             /* hydrogens of the donors (k_grid_reg pulls them into L2 for k_hscan) */
     const int* cell_of; const int* rank; const int* cell_start;
-    float4* pos4; uint4* att4; int2* hrng;
+    float4* pos4; uint4* att4;
+    uint4* arec;                     /* non-null: 32-byte records (pos4 | att4) for k_tiles instead of the three arrays above */
 };
 
 __device__ __forceinline__ void dev_scatter(const ScatterArgs& A, int N, int i)
@@ -373,9 +392,67 @@ __device__ __forceinline__ void dev_scatter(const ScatterArgs& A, int N, int i)
     int r = A.res_id[i];
     const uint32_t w = arp_pack_word(A.feat[i], A.res_flags[r], A.rad_class[i],
                                      A.bond_off && A.bond_off[i + 1] > A.bond_off[i]);
-    A.pos4[dst] = make_float4(A.xyz[3 * (size_t)i], A.xyz[3 * (size_t)i + 1], A.xyz[3 * (size_t)i + 2], __int_as_float(i));
-    A.att4[dst] = make_uint4(w, (uint32_t)r, (uint32_t)A.res_prev[r], (uint32_t)A.res_next[r]);
-    A.hrng[dst] = A.h_off ? make_int2(A.h_off[i], A.h_off[i + 1]) : make_int2(0, 0);
+    const float4 p4 = make_float4(A.xyz[3 * (size_t)i], A.xyz[3 * (size_t)i + 1], A.xyz[3 * (size_t)i + 2], __int_as_float(i));
+    const uint4 a4 = make_uint4(w, (uint32_t)r, (uint32_t)A.res_prev[r], (uint32_t)A.res_next[r]);
+    if (A.arec) {
+        A.arec[2 * (size_t)dst] = make_uint4(__float_as_uint(p4.x), __float_as_uint(p4.y), __float_as_uint(p4.z), (uint32_t)i);
+        A.arec[2 * (size_t)dst + 1] = a4;
+        return;
+    }
+    A.pos4[dst] = p4;
+    A.att4[dst] = a4;
+}
+
+/* ---- phase 6 (k_tiles only): run table of every cell ---------------------------------------------
+ * The home cell and its 13 forward neighbours are five contiguous runs of the cell-sorted records.  One THREAD
+ * per cell writes them once -- runtab[6 j + r] = (first position, length) of run r, runtab[6 j + 5] = (home
+ * atoms, float bits of the structure's upper band edge) -- instead of one warp per cell deriving them in the pair
+ * kernel.  cs(i) returns cell_start[i] (from shared or global memory). */
+template <class CS>
+__device__ __forceinline__ void dev_runtab(const StructGeom* __restrict__ geom, int S, int j, CS cs, int2* __restrict__ runtab)
+{
+    int s = 0;
+    if (S > 1) {                      /* last structure whose first cell is <= j (empty structures share their successor's) */
+        int lo = 0, hi = S;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (geom[mid].cell_base <= j) lo = mid; else hi = mid;
+        }
+        s = lo;
+    }
+    const StructGeom* g = geom + s;
+    const int gdx = g->dx, gdy = g->dy, gdz = g->dz, base = g->cell_base;
+    const int lc = j - base;
+    const int t2 = lc / gdx, cx = lc - t2 * gdx;
+    const int cz = t2 / gdy, cy = t2 - cz * gdy;
+    int4* dst = reinterpret_cast<int4*>(runtab + 6 * (size_t)j);
+    const int xh = min(cx + 1, gdx - 1), xm = max(cx - 1, 0);
+    auto run = [&](int r, int& beg, int& len) {
+        const int y = cy + (r == 1 || r == 4 ? 1 : (r == 2 ? -1 : 0));
+        const int z = cz + (r >= 2 ? 1 : 0);
+        beg = 0; len = 0;
+        if (y >= 0 && y < gdy && z < gdz) {
+            const int row = base + (z * gdy + y) * gdx;
+            beg = cs(row + (r == 0 ? cx : xm));
+            len = cs(row + xh + 1) - beg;
+        }
+    };
+    int b0, l0, b1, l1;
+    run(0, b0, l0); run(1, b1, l1);
+    const int nh = cs(j + 1) - b0;    /* run 0 starts with the home cell */
+    dst[0] = make_int4(b0, l0, b1, l1);
+    run(2, b0, l0); run(3, b1, l1);
+    dst[1] = make_int4(b0, l0, b1, l1);
+    run(4, b0, l0);
+    dst[2] = make_int4(b0, l0, nh, __float_as_int(g->r2_hi));
+}
+
+__global__ void __launch_bounds__(256) k_runtab(const StructGeom* __restrict__ geom, int S, const RunMeta* __restrict__ meta,
+                                                const int* __restrict__ cell_start, int2* __restrict__ runtab)
+{
+    const int n_cells = (int)meta->n_cells;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_cells; j += gridDim.x * blockDim.x)
+        dev_runtab(geom, S, j, [&](int i) { return __ldcg(&cell_start[i]); }, runtab);
 }
 
 /* ---- the phases as separate kernels ------------------------------------------------------------- */
@@ -386,10 +463,10 @@ __global__ void __launch_bounds__(GRID_THREADS) k_bbox(const float* __restrict__
 }
 
 __global__ void __launch_bounds__(GRID_THREADS) k_geom(const unsigned* __restrict__ bbox, const int* __restrict__ struct_off,
-                                                       int S, int N, double cutoff, StructGeom* __restrict__ geom,
+                                                       int S, int N, double cutoff, int tile_x, StructGeom* __restrict__ geom,
                                                        RunMeta* __restrict__ meta)
 {
-    dev_geom<GRID_THREADS>(bbox, struct_off, S, N, cutoff, geom, meta);
+    dev_geom<GRID_THREADS>(bbox, struct_off, S, N, cutoff, tile_x, geom, meta);
 }
 
 __global__ void __launch_bounds__(GRID_THREADS) k_cellid(const float* __restrict__ xyz, const int* __restrict__ struct_off,
@@ -431,6 +508,7 @@ __global__ void __launch_bounds__(GRID_THREADS) k_scatter(int N, ScatterArgs A)
 /* ---- the phases as one cooperative kernel ----------------------------------------------------- */
 struct GridArgs {
     int N, S;
+    int tile_x;                     /* most home cells per unit of k_tiles */
     double cutoff;
     const int* struct_off;
     unsigned* bbox;
@@ -438,6 +516,7 @@ struct GridArgs {
     RunMeta* meta;
     int* cell_cnt;
     unsigned long long* scan_state;
+    int2* runtab;                   /* non-null: per-cell run tables for k_tiles (dev_runtab) */
     ScatterArgs sc;                 /* sc.cell_of / rank / cell_start are written by earlier phases */
     int* cell_of; int* rank; int* cell_start;
 };
@@ -450,7 +529,7 @@ __global__ void __launch_bounds__(GRID_THREADS) k_grid_fused(GridArgs G)
     for (int vb = blockIdx.x; vb * BBOX_ATOMS_PER_VB < N; vb += gridDim.x)
         dev_bbox(G.sc.xyz, G.struct_off, G.S, N, G.bbox, vb);
     grid.sync();
-    if (blockIdx.x == 0) dev_geom<GRID_THREADS>(G.bbox, G.struct_off, G.S, N, G.cutoff, G.geom, G.meta);
+    if (blockIdx.x == 0) dev_geom<GRID_THREADS>(G.bbox, G.struct_off, G.S, N, G.cutoff, G.tile_x, G.geom, G.meta);
     grid.sync();
     for (int vb = blockIdx.x; vb < vb_atoms; vb += gridDim.x)
         dev_cellid(G.sc.xyz, G.struct_off, G.S, N, G.geom, G.cell_cnt, G.cell_of, G.rank, vb * GRID_THREADS + threadIdx.x);
@@ -464,6 +543,11 @@ __global__ void __launch_bounds__(GRID_THREADS) k_grid_fused(GridArgs G)
     grid.sync();
     for (int vb = blockIdx.x; vb < vb_atoms; vb += gridDim.x)
         dev_scatter(G.sc, N, vb * GRID_THREADS + threadIdx.x);
+    if (G.runtab) {
+        const int n_cells = (int)__ldcg(&G.meta->n_cells);
+        for (int j = blockIdx.x * GRID_THREADS + threadIdx.x; j < n_cells; j += gridDim.x * GRID_THREADS)
+            dev_runtab(G.geom, G.S, j, [&](int i) { return __ldcg(&G.cell_start[i]); }, G.runtab);
+    }
 }
 
 /* ---- the phases as one cooperative kernel, atoms held in registers ------------------------------
@@ -559,18 +643,19 @@ __global__ void __launch_bounds__(REG_THREADS, 1) k_grid_reg(GridArgs G)
         if (threadIdx.x == 0) {
             StructGeom g;
             memset(&g, 0, sizeof g);
-            const bool finite = geom_make(G.bbox, N, G.cutoff, g);
+            const bool finite = geom_make(G.bbox, N, G.cutoff, G.tile_x, g);
             s_geom = g;
             if (blockIdx.x == 0) {
                 G.geom[0] = g;
                 G.meta->n_cells = (unsigned)g.ncell;
+                G.meta->n_units = (unsigned)g.n_units;
                 G.meta->r2_lo_inv = r2_lo_key(g.r2_lo);
                 if (!finite) atomicOr(&G.meta->fault, 1u);
             }
         }
         __syncthreads();
     } else {
-        if (blockIdx.x == 0) dev_geom<REG_THREADS>(G.bbox, G.struct_off, S, N, G.cutoff, G.geom, G.meta);
+        if (blockIdx.x == 0) dev_geom<REG_THREADS>(G.bbox, G.struct_off, S, N, G.cutoff, G.tile_x, G.geom, G.meta);
         grid.sync();
     }
     GRID_STAMP(4);
@@ -667,13 +752,27 @@ __global__ void __launch_bounds__(REG_THREADS, 1) k_grid_reg(GridArgs G)
         if (st[k] < 0) continue;
         const int i = k * T + gtid;
         const int dst = (in_smem ? s_off[REG_SIDX(cell[k])] : __ldcg(&G.cell_start[cell[k]])) + rank[k];
-        G.sc.pos4[dst] = make_float4(x[k], y[k], z[k], __int_as_float(i));
-        G.sc.att4[dst] = make_uint4(aw[k], (uint32_t)ar[k], (uint32_t)ap[k], (uint32_t)an[k]);
-        G.sc.hrng[dst] = ah[k];
+        if (G.sc.arec) {
+            G.sc.arec[2 * (size_t)dst] = make_uint4(__float_as_uint(x[k]), __float_as_uint(y[k]), __float_as_uint(z[k]), (uint32_t)i);
+            G.sc.arec[2 * (size_t)dst + 1] = make_uint4(aw[k], (uint32_t)ar[k], (uint32_t)ap[k], (uint32_t)an[k]);
+        } else {
+            G.sc.pos4[dst] = make_float4(x[k], y[k], z[k], __int_as_float(i));
+            G.sc.att4[dst] = make_uint4(aw[k], (uint32_t)ar[k], (uint32_t)ap[k], (uint32_t)an[k]);
+        }
         /* the donor's hydrogens are read once, by k_hscan at the end of the run, on its critical path: bring
            their line into L2 now (up to five hydrogens per 128-byte line) */
         if (ah[k].y > ah[k].x && G.sc.h_xyz)
             asm volatile("prefetch.global.L2 [%0];" :: "l"(G.sc.h_xyz + 3 * (size_t)ah[k].x));
+    }
+    if (G.runtab) {                     /* run tables of the cells for k_tiles: one thread per cell */
+        const int n_cells = n - 1;
+        if (in_smem) {
+            for (int j = gtid; j < n_cells; j += T)
+                dev_runtab(S == 1 ? &s_geom : G.geom, S, j, [&](int i) { return s_off[REG_SIDX(i)]; }, G.runtab);
+        } else {
+            for (int j = gtid; j < n_cells; j += T)
+                dev_runtab(S == 1 ? &s_geom : G.geom, S, j, [&](int i) { return __ldcg(&G.cell_start[i]); }, G.runtab);
+        }
     }
     GRID_STAMP(9);
     PROF_STAMP(0, 1);
@@ -1148,7 +1247,7 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
                 uint32_t mask; float dist;
                 rule_classify_core(A.side, P, ib, ie, pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, ab.x, ae.x, &mask, &dist, &work);
                 rec[slot] = make_int4(ib, ie, (int)mask, __float_as_int(dist));
-                if (work) surv[slot] = e;                        /* stage 2 finds donor / acceptor through this */
+                if (work) surv[slot] = make_uint2((unsigned)ib, (unsigned)ie);   /* k_hscan finds donor / acceptor through this: ORIGINAL indices */
             }
             /* append the work items of this round, one kind of slot at a time (ballot compaction) */
             if (__any_sync(FULL, work != 0)) {
@@ -1216,8 +1315,7 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
  * is_weak_hbond (one pass over the donor's hydrogens serves both), is_halogen_weak_hbond, is_xbond
  * (utils.py:73-179).  A true predicate ORs its SIFt bit into the finished record.                  */
 struct HscanArgs {
-    const float4* pos4;
-    const int2*   hrng;                     /* hydrogen range of every atom, cell order */
+    const float*  xyz;                      /* coordinates in upload order (the work items carry original atom indices) */
     const uint4*  work;
     RunMeta*      meta;
     unsigned long long work_cap;
@@ -1252,12 +1350,15 @@ __global__ void __launch_bounds__(HSCAN_WARPS * 32, HSCAN_MINB) k_hscan(HscanArg
         const unsigned long long w = (back ? chunk - c_front : chunk) * 32 + lane;
         if (w < (back ? n_rare : n)) {
         const uint4 it = A.work[back ? A.work_cap - 1 - w : w];
-        const float4 pd = A.pos4[it.x], pa = A.pos4[it.y];
+        const float* dp = A.xyz + 3 * (size_t)it.x;
+        const float* ap = A.xyz + 3 * (size_t)it.y;
+        const float4 pd = make_float4(dp[0], dp[1], dp[2], __int_as_float((int)it.x));
+        const float4 pa = make_float4(ap[0], ap[1], ap[2], __int_as_float((int)it.y));
         const uint32_t kind = it.w & 7u;
         const double vdw_a = A.side.vdw[it.w >> 8];
         uint32_t bits = 0;
         if (kind <= 3u) {
-            const int2 hr = A.hrng[it.x];
+            const int2 hr = A.side.h_off ? make_int2(A.side.h_off[it.x], A.side.h_off[it.x + 1]) : make_int2(0, 0);
             const int got = rule_hbond_scan_range(A.side, P, hr.x, hr.y, pd.x, pd.y, pd.z, pa.x, pa.y, pa.z, vdw_a, (int)kind);
             if (got & ARP_HB_NEED_H) bits |= 1u << ARP_SIFT_HBOND;
             if (got & ARP_HB_NEED_W) bits |= 1u << ARP_SIFT_WEAK_HBOND;
@@ -1283,6 +1384,8 @@ __global__ void __launch_bounds__(HSCAN_WARPS * 32, HSCAN_MINB) k_hscan(HscanArg
     PROF_STAMP(3, 1);
 #endif
 }
+
+#include "arp_tiles.cuh"
 
 /* longest donor-hydrogen distance of the upload (float, rounded up; +inf when a distance is not finite).
    *reach = upload generation << 32 | float bits: non-negative floats order like their bit patterns and a newer
@@ -1337,11 +1440,11 @@ int arp_pairs_prepare(arp_ctx* c)
     ARP_TRY(dbuf_reserve(c, c->zero, c->zero_bytes));
     ARP_TRY(dbuf_reserve(c, c->geom, sizeof(StructGeom) * S));
     ARP_TRY(dbuf_reserve(c, c->cell_start, sizeof(int) * (c->cell_bound + 2)));
+    if (c->use_tiles) ARP_TRY(dbuf_reserve(c, c->runtab, sizeof(int2) * 6 * (c->cell_bound + 2)));
     ARP_TRY(dbuf_reserve(c, c->cell_of, sizeof(int) * N));
     ARP_TRY(dbuf_reserve(c, c->rank, sizeof(int) * N));
-    ARP_TRY(dbuf_reserve(c, c->pos4, sizeof(float4) * N));
+    ARP_TRY(dbuf_reserve(c, c->pos4, sizeof(float4) * N * (c->use_tiles ? 2 : 1)));
     ARP_TRY(dbuf_reserve(c, c->att4, sizeof(uint4) * N));
-    ARP_TRY(dbuf_reserve(c, c->hrng, sizeof(int2) * N));
     /* longest donor-hydrogen distance: a property of the uploaded atoms, computed once per upload */
     if (!c->hreach.p) {
         ARP_TRY(dbuf_reserve(c, c->hreach, 16));
@@ -1384,7 +1487,7 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
        atoms.  The diagnostic timing with events between the kernels measures the kernels one after the other.
        A list that an earlier run without the early start left dirty is zeroed first (state repair, not part of
        this run: ahead of the first event). */
-    const int early = c->use_early_cls && N <= 500000 && !split_events;
+    const int early = !c->use_tiles && c->use_early_cls && N <= 500000 && !split_events;
     if (early && c->hits_dirty && c->hits.p) {
         ARP_CUDA(c, cudaMemsetAsync(c->hits.p, 0, c->hits.cap, st));
         c->hits_dirty = 0;
@@ -1434,13 +1537,13 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         SC.bond_off = c->has_bonds ? c->bond_off.as<int32_t>() : nullptr;
         SC.h_off = c->has_h ? c->h_off.as<int32_t>() : nullptr;
         SC.h_xyz = c->has_h && c->H > 0 ? c->h_xyz.as<double>() : nullptr;
-        SC.hrng = c->hrng.as<int2>();
         SC.cell_of = c->cell_of.as<int>(); SC.rank = c->rank.as<int>(); SC.cell_start = c->cell_start.as<int>();
         SC.pos4 = c->pos4.as<float4>(); SC.att4 = c->att4.as<uint4>();
+        SC.arec = c->use_tiles ? c->pos4.as<uint4>() : nullptr;      /* the records take the place of pos4 (sized for both layouts) */
         unsigned blocks = (unsigned)((N + GRID_THREADS - 1) / GRID_THREADS);
         if (c->coop_blocks > 0 && c->use_fused_grid) {
             GridArgs GA;
-            GA.N = N; GA.S = S; GA.cutoff = c->params.interacting_cutoff; GA.struct_off = so; GA.bbox = bbox;
+            GA.runtab = c->use_tiles ? c->runtab.as<int2>() : nullptr; GA.N = N; GA.S = S; GA.tile_x = c->tile_x; GA.cutoff = c->params.interacting_cutoff; GA.struct_off = so; GA.bbox = bbox;
             GA.geom = c->geom.as<StructGeom>(); GA.meta = meta; GA.cell_cnt = cell_cnt; GA.scan_state = state;
             GA.sc = SC; GA.cell_of = c->cell_of.as<int>(); GA.rank = c->rank.as<int>(); GA.cell_start = c->cell_start.as<int>();
             void* args[] = { &GA };
@@ -1461,7 +1564,7 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         } else {
             k_bbox<<<(unsigned)((N + BBOX_ATOMS_PER_VB - 1) / BBOX_ATOMS_PER_VB), GRID_THREADS, 0, st>>>(c->xyz.as<float>(), so, S, N, bbox);
             ARP_LAUNCHED(c);
-            k_geom<<<1, GRID_THREADS, 0, st>>>(bbox, so, S, N, c->params.interacting_cutoff, c->geom.as<StructGeom>(), meta);
+            k_geom<<<1, GRID_THREADS, 0, st>>>(bbox, so, S, N, c->params.interacting_cutoff, c->tile_x, c->geom.as<StructGeom>(), meta);
             ARP_LAUNCHED(c);
             k_cellid<<<blocks, GRID_THREADS, 0, st>>>(c->xyz.as<float>(), so, S, N, c->geom.as<StructGeom>(), cell_cnt,
                                                       c->cell_of.as<int>(), c->rank.as<int>());
@@ -1470,6 +1573,10 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
                                        c->cell_bound + 1));
             k_scatter<<<blocks, GRID_THREADS, 0, st>>>(N, SC);
             ARP_LAUNCHED(c);
+            if (c->use_tiles) {
+                k_runtab<<<(unsigned)(c->sm_count * 4), 256, 0, st>>>(c->geom.as<StructGeom>(), S, meta, c->cell_start.as<int>(), c->runtab.as<int2>());
+                ARP_LAUNCHED(c);
+            }
         }
     }
     if (grid_event) ARP_CUDA(c, cudaEventRecord(c->ev[1], st));
@@ -1500,38 +1607,65 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
             (void)cudaGetLastError();
             c->hscan_blocks = per_sm * c->sm_count;
         }
-        if (!early) c->hits_dirty = 1;
+        if (!early && !c->use_tiles) c->hits_dirty = 1;
 
-        SearchArgs SA;
-        SA.pos4 = c->pos4.as<float4>(); SA.cell_start = c->cell_start.as<int>();
-        SA.geom = c->geom.as<StructGeom>(); SA.meta = meta; SA.raw = c->hits.as<uint2>(); SA.cap = c->out_cap;
-        unsigned grid = (unsigned)(c->sm_count * SEARCH_GRID_MULT);
-#ifndef SEARCH_ATOMS_PER_CELL
-#define SEARCH_ATOMS_PER_CELL 5      /* 5.7 at protein density; a block too many exits at once, one too few leaves tickets to the counter */
-#endif
-        size_t want = ((size_t)N / (SEARCH_ATOMS_PER_CELL * SEARCH_CELLS)) / SEARCH_WARPS + 1;     /* about one warp per ticket on small inputs */
-        if (want < grid) grid = (unsigned)want;
-        ARP_CUDA(c, launch_k(k_search, grid, SEARCH_WARPS * 32, 0, st, pdl, SA));
-        c->launches++;
-        if (split_events) ARP_CUDA(c, cudaEventRecord(c->ev[2], st));
+        const bool tiles = c->use_tiles != 0;
+        if (tiles) {
+            /* search + classify in one kernel from shared-memory tiles (arp_tiles.cuh) */
+            if (!c->tiles_blocks) {             /* a persistent grid: exactly the blocks that are resident together */
+                ARP_CUDA(c, cudaFuncSetAttribute(k_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
+                int per_sm = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiles, TW_THREADS, TW_SMEM) != cudaSuccess || per_sm < 1)
+                    per_sm = 1;
+                (void)cudaGetLastError();
+                c->tiles_blocks = per_sm * c->sm_count;
+            }
+            if (split_events) ARP_CUDA(c, cudaEventRecord(c->ev[2], st));      /* no separate search kernel */
+            TileArgs TA;
+            TA.arec = c->pos4.as<uint4>(); TA.runtab = c->runtab.as<int2>();
+            TA.meta = meta; TA.out = c->out.as<arp_pair>(); TA.cap = c->out_cap;
+            TA.work = c->work.as<uint4>(); TA.work_cap = c->work_cap;
+            TA.h_reach = c->hreach.as<unsigned long long>(); TA.h_gen = c->upload_gen;
+            TA.r2 = c->rp.r2; TA.include_seq_adjacent = c->rp.include_seq_adjacent; TA.side = side;
+            /* about one warp per two cells of ~6 atoms on small inputs */
+            unsigned tgrid = (unsigned)c->tiles_blocks;
+            size_t want = (size_t)N / (12 * TW_WARPS) + 1;
+            if (want < tgrid) tgrid = (unsigned)want;
+            ARP_CUDA(c, launch_k(k_tiles, tgrid, TW_THREADS, TW_SMEM, st, pdl, TA, c->rp));
+            c->launches++;
+            if (split_events) ARP_CUDA(c, cudaEventRecord(c->ev[4], st));
+        } else {
+            SearchArgs SA;
+            SA.pos4 = c->pos4.as<float4>(); SA.cell_start = c->cell_start.as<int>();
+            SA.geom = c->geom.as<StructGeom>(); SA.meta = meta; SA.raw = c->hits.as<uint2>(); SA.cap = c->out_cap;
+            unsigned grid = (unsigned)(c->sm_count * SEARCH_GRID_MULT);
+    #ifndef SEARCH_ATOMS_PER_CELL
+    #define SEARCH_ATOMS_PER_CELL 5      /* 5.7 at protein density; a block too many exits at once, one too few leaves tickets to the counter */
+    #endif
+            size_t want = ((size_t)N / (SEARCH_ATOMS_PER_CELL * SEARCH_CELLS)) / SEARCH_WARPS + 1;     /* about one warp per ticket on small inputs */
+            if (want < grid) grid = (unsigned)want;
+            ARP_CUDA(c, launch_k(k_search, grid, SEARCH_WARPS * 32, 0, st, pdl, SA));
+            c->launches++;
+            if (split_events) ARP_CUDA(c, cudaEventRecord(c->ev[2], st));
 
-        ClassifyArgs CA;
-        CA.h_reach = c->hreach.as<unsigned long long>(); CA.h_gen = c->upload_gen;
-        CA.pos4 = SA.pos4; CA.att4 = c->att4.as<uint4>(); CA.raw = SA.raw; CA.cap = c->out_cap; CA.meta = meta;
-        CA.out = c->out.as<arp_pair>(); CA.side = side;
-        CA.work = c->work.as<uint4>(); CA.work_cap = c->work_cap;
-        CA.r2 = c->rp.r2; CA.include_seq_adjacent = c->rp.include_seq_adjacent;
-        size_t tiles = (size_t)((c->out_cap + CLS_TILE - 1) / CLS_TILE);
-        size_t blocks_needed = (tiles + CLS_WARPS - 1) / CLS_WARPS;
-        unsigned cgrid = (unsigned)(c->sm_count * CLS_MINB);
-        if (blocks_needed < cgrid) cgrid = (unsigned)(blocks_needed ? blocks_needed : 1);
-        ARP_CUDA(c, launch_k(early ? k_classify<true> : k_classify<false>, cgrid, CLS_WARPS * 32, CLS_SMEM, st, pdl, CA, c->rp));
-        c->launches++;
-        if (split_events) ARP_CUDA(c, cudaEventRecord(c->ev[4], st));
+            ClassifyArgs CA;
+            CA.h_reach = c->hreach.as<unsigned long long>(); CA.h_gen = c->upload_gen;
+            CA.pos4 = SA.pos4; CA.att4 = c->att4.as<uint4>(); CA.raw = SA.raw; CA.cap = c->out_cap; CA.meta = meta;
+            CA.out = c->out.as<arp_pair>(); CA.side = side;
+            CA.work = c->work.as<uint4>(); CA.work_cap = c->work_cap;
+            CA.r2 = c->rp.r2; CA.include_seq_adjacent = c->rp.include_seq_adjacent;
+            size_t tiles = (size_t)((c->out_cap + CLS_TILE - 1) / CLS_TILE);
+            size_t blocks_needed = (tiles + CLS_WARPS - 1) / CLS_WARPS;
+            unsigned cgrid = (unsigned)(c->sm_count * CLS_MINB);
+            if (blocks_needed < cgrid) cgrid = (unsigned)(blocks_needed ? blocks_needed : 1);
+            ARP_CUDA(c, launch_k(early ? k_classify<true> : k_classify<false>, cgrid, CLS_WARPS * 32, CLS_SMEM, st, pdl, CA, c->rp));
+            c->launches++;
+            if (split_events) ARP_CUDA(c, cudaEventRecord(c->ev[4], st));
+        }
 
         HscanArgs HA;
-        HA.pos4 = SA.pos4; HA.hrng = c->hrng.as<int2>(); HA.work = CA.work; HA.meta = meta; HA.work_cap = c->work_cap;
-        HA.out = CA.out; HA.side = side; HA.clean_cnt = cell_cnt;
+        HA.work = c->work.as<uint4>(); HA.meta = meta; HA.work_cap = c->work_cap;
+        HA.out = c->out.as<arp_pair>(); HA.side = side; HA.clean_cnt = cell_cnt; HA.xyz = c->xyz.as<float>();
         size_t hb = (size_t)((c->work_cap + 255) / 256);
         unsigned hgrid = (unsigned)c->hscan_blocks;
         if (hb < hgrid) hgrid = (unsigned)(hb ? hb : 1);

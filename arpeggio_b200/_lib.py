@@ -48,6 +48,11 @@ def lib():
         'arp_pairs_run': (i32, [vp, u64p]),
         'arp_pairs_fetch': (i32, [vp, vp, u64, i32]),
         'arp_pairs_device_ptr': (i32, [vp, C.POINTER(vp)]),
+        'arp_pairs_run_async': (i32, [vp]),
+        'arp_pairs_count': (i32, [vp, u64p]),
+        'arp_pairs_fetch_compact': (i32, [vp, vp, vp, u64, vp, u64p]),
+        'arp_pairs_fetch_dist': (i32, [vp, vp, u64]),
+        'arp_pairs_unpack': (i32, [vp, vp, vp, i32, vp, u64]),
         'arp_upload_planes': (i32, [vp, C.POINTER(abi.ArpPlanes), C.POINTER(abi.ArpPlanes)]),
         'arp_ring_ring_run': (i32, [vp, u64p]),
         'arp_ring_ring_fetch': (i32, [vp, vp, u64]),
@@ -67,6 +72,7 @@ def lib():
         'arp_get_stats': (i32, [vp, C.POINTER(abi.ArpStats)]),
         'arp_timing_iters': (i32, [vp, i32, i32, C.POINTER(C.c_float)]),
         'arp_launch_count': (u64, [vp]),
+        'arp_memcpy_probe': (i32, [vp, u64, u64, i32, C.POINTER(C.c_float)]),
     }
     assert set(proto) == set(abi.EXPORTED_SYMBOLS)
     for name, (res, args) in proto.items():

@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # ---- error codes ---------------------------------------------------------
 OK = 0
@@ -163,11 +163,18 @@ class ArpStats(C.Structure):
         ('ms_classify', C.c_float),
         ('ms_hscan', C.c_float),
         ('ms_pairs', C.c_float),
+        ('faults', C.c_uint32),
+        ('_pad', C.c_uint32),
     ]
+
+
+FAULT_NONFINITE = 1
+FAULT_HANDOFF = 2
 
 
 # record layouts as NumPy structured dtypes (arp_pair / arp_plane_pair / arp_atom_plane)
 PAIR_DTYPE = np.dtype([('i', '<i4'), ('j', '<i4'), ('mask', '<u4'), ('dist', '<f4')])
+PAIR_C_DTYPE = np.dtype([('j', '<i4'), ('mask', '<u4')])      # arp_pair_c: compact view of the sorted stream
 PLANE_PAIR_DTYPE = np.dtype([('a', '<i4'), ('b', '<i4'), ('code', '<u4'), ('_pad', '<u4'), ('dist', '<f8')])
 ATOM_PLANE_DTYPE = np.dtype([('atom', '<i4'), ('ring', '<i4'), ('code', '<u4'), ('_pad', '<u4'), ('dist', '<f8')])
 ATOM_SIFT_DTYPE = np.dtype([('sift', '<u2', (4,)), ('integer_sift', '<u4', (4,)), ('hbonds', '<u4', (4,)), ('polars', '<u4', (4,))])
@@ -180,9 +187,10 @@ EXPORTED_SYMBOLS = (
     'arp_abi_version', 'arp_device_count', 'arp_create', 'arp_destroy', 'arp_last_error',
     'arp_params_default', 'arp_set_params', 'arp_host_alloc', 'arp_host_free',
     'arp_upload_atoms', 'arp_pairs_run', 'arp_pairs_fetch', 'arp_pairs_device_ptr',
+    'arp_pairs_run_async', 'arp_pairs_count', 'arp_pairs_fetch_compact', 'arp_pairs_fetch_dist', 'arp_pairs_unpack',
     'arp_upload_planes', 'arp_ring_ring_run', 'arp_ring_ring_fetch', 'arp_atom_ring_run',
     'arp_atom_ring_fetch', 'arp_amide_amide_run', 'arp_amide_amide_fetch', 'arp_amide_ring_run',
-    'arp_amide_ring_fetch', 'arp_atom_sifts_run', 'arp_atom_sifts_fetch', 'arp_ring_nearest_atom', 'arp_pairs_json_size', 'arp_pairs_json_write', 'arp_flag_within', 'arp_sync', 'arp_get_stats', 'arp_timing_iters', 'arp_launch_count',
+    'arp_amide_ring_fetch', 'arp_atom_sifts_run', 'arp_atom_sifts_fetch', 'arp_ring_nearest_atom', 'arp_pairs_json_size', 'arp_pairs_json_write', 'arp_flag_within', 'arp_sync', 'arp_get_stats', 'arp_timing_iters', 'arp_launch_count', 'arp_memcpy_probe',
 )
 
 

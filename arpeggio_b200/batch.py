@@ -15,7 +15,7 @@ import time
 import numpy as np
 
 from . import abi
-from .engine import ContactEngine, PinnedBuffer
+from .engine import CompactPairs, ContactEngine, PinnedBuffer
 
 
 def shard_indices(sizes, world_size, rank):
@@ -42,6 +42,7 @@ class BatchRunner:
         self.device = device
         self.engines = [ContactEngine(device, params) for _ in range(max(1, slots))]
         self._pins = [None] * len(self.engines)
+        self._last_n = [0] * len(self.engines)
 
     def close(self):
         for e in self.engines:
@@ -69,11 +70,31 @@ class BatchRunner:
             pb = self._pins[slot] = PinnedBuffer(16 * (n + n // 8 + 1024))
         return pb.array(abi.PAIR_DTYPE)
 
-    def run(self, soas, consume=None, sorted=False, check_finite=True):
+    def _compact_buffer(self, slot, n_atoms, n, with_dist):
+        """One pinned block per slot carved into row offsets | compact records | distances."""
+        o_rec = (4 * (n_atoms + 1) + 255) // 256 * 256
+        o_dist = o_rec + (8 * n + 255) // 256 * 256
+        need = o_dist + (4 * n if with_dist else 0)
+        pb = self._pins[slot]
+        if pb is None or pb.nbytes < need:
+            if pb is not None:
+                pb.free()
+            pb = self._pins[slot] = PinnedBuffer(need + need // 8 + 4096)
+        raw = pb.array(np.uint8)
+        cap = (pb.nbytes - o_rec) // (12 if with_dist else 8)
+        o_dist = o_rec + (8 * cap + 255) // 256 * 256
+        if with_dist:
+            cap = min(cap, (pb.nbytes - o_dist) // 4)
+        return CompactPairs(raw[:4 * (n_atoms + 1)].view(np.uint32), raw[o_rec:o_rec + 8 * cap].view(abi.PAIR_C_DTYPE),
+                            raw[o_dist:o_dist + 4 * cap].view(np.float32) if with_dist else None)
+
+    def run(self, soas, consume=None, sorted=False, check_finite=True, compact=False, with_dist=False):
         """Upload -> grid build + pair kernels -> fetch for every AtomSoA of `soas`.
 
         consume(index, records): called in the worker thread with a view of the slot's pinned record
-        buffer (valid only during the call).  Returns (pairs_per_structure, seconds)."""
+        buffer (valid only during the call).  compact: the (i, j)-sorted stream in its compact form
+        (engine.CompactPairs; distances only with_dist) instead of 16-byte records.
+        Returns (pairs_per_structure, seconds)."""
         soas = list(soas)
         counts = [0] * len(soas)
         todo = queue.SimpleQueue()
@@ -90,8 +111,18 @@ class BatchRunner:
                     except queue.Empty:
                         return
                     eng.upload_atoms(soas[i], check_finite=check_finite)
-                    n = eng.run_pairs()
-                    rec = eng.fetch_pairs(n, sorted=sorted, out=self._out_buffer(slot, n))
+                    if compact:
+                        # one wait per structure: the fetch waits for the run; the slot's buffer is sized from the
+                        # structures it has seen (a stream that does not fit reports its length and is fetched again)
+                        eng.run_pairs_async()
+                        guess = max(self._last_n[slot], 14 * soas[i].n_atoms)
+                        buf = self._compact_buffer(slot, soas[i].n_atoms, guess, with_dist)
+                        rec = eng.fetch_pairs_compact(with_dist, out=buf, grow=lambda m, s=slot, a=soas[i].n_atoms:
+                                                      self._compact_buffer(s, a, m, with_dist))
+                        n = self._last_n[slot] = rec.n
+                    else:
+                        n = eng.run_pairs()
+                        rec = eng.fetch_pairs(n, sorted=sorted, out=self._out_buffer(slot, n))
                     counts[i] = n
                     if consume is not None:
                         consume(i, rec)

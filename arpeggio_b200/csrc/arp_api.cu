@@ -116,6 +116,13 @@ int upload(arp_ctx* c, DBuf& b, const void* src, size_t bytes)
     return ARP_OK;
 }
 
+/* the record stream of the last run is no longer current; a run that is still in flight is waited for first */
+void pairs_invalidate(arp_ctx* c)
+{
+    if (c->run_pending) { cudaStreamSynchronize(c->stream); (void)cudaGetLastError(); c->run_pending = 0; }
+    c->pairs_valid = 0; c->sorted_valid = 0; c->compact_valid = 0; c->sort_tmp_valid = 0; c->sifts_valid = 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -213,7 +220,7 @@ void arp_destroy(arp_ctx* c)
     DBuf* bufs[] = { &c->xyz, &c->feat, &c->res_id, &c->rad_class, &c->vdw, &c->cov, &c->res_prev, &c->res_next,
                      &c->res_flags, &c->bond_off, &c->bond_nbr, &c->h_off, &c->h_xyz, &c->xnbr, &c->struct_off,
                      &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->runtab, &c->sift_acc, &c->sift_out, &c->ring_scratch, &c->hreach, &c->arena, &c->out, &c->hits, &c->work,
-                     &c->radtab, &c->sort_tmp, &c->sort_out, &c->sort_zero, &c->sort_off, &c->within, &c->flush };
+                     &c->radtab, &c->sort_tmp, &c->sort_out, &c->sort_c, &c->sort_d, &c->sort_zero, &c->sort_off, &c->within, &c->flush };
     for (DBuf* b : bufs) dbuf_free(*b);
     arp_planes_release(c);
     for (int k = 0; k < 5; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
@@ -235,7 +242,7 @@ int arp_set_params(arp_ctx* c, const arp_params* p)
     derive_rule_params(c->params, &c->rp);
     c->have_params = 1;
     c->radtab_valid = 0;
-    c->pairs_valid = 0; c->sorted_valid = 0;
+    pairs_invalidate(c);
     c->ring_ring.valid = c->atom_ring.valid = c->amide_amide.valid = c->amide_ring.valid = 0;
     return ARP_OK;
 }
@@ -279,7 +286,7 @@ int arp_upload_atoms(arp_ctx* c, const arp_atoms* a)
             ARP_REQUIRE(c, a->struct_off[s] <= a->struct_off[s + 1], ARP_E_INVALID_ARG, "struct_off must ascend");
     }
     ARP_TRY(arp_bind(c));
-    c->have_atoms = 0; c->pairs_valid = 0; c->sorted_valid = 0; c->radtab_valid = 0;
+    c->have_atoms = 0; pairs_invalidate(c); c->radtab_valid = 0;
     c->atom_ring.valid = 0;
     c->input_bytes = 0;
     c->N = N; c->Rs = a->n_residues; c->K = a->n_rad_classes; c->S = S;
@@ -389,6 +396,7 @@ static void fill_stats(arp_ctx* c, int with_events)
     s.n_cells_nonempty = c->h_meta->n_cells_nonempty;
     s.input_bytes = c->input_bytes;
     s.output_bytes = s.n_pairs * sizeof(arp_pair);
+    s.faults = c->h_meta->fault;
     if (with_events >= 3) {
         float a = 0.f, b = 0.f, d = 0.f;
         cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
@@ -404,21 +412,25 @@ static void fill_stats(arp_ctx* c, int with_events)
     }
 }
 
-int arp_pairs_run(arp_ctx* c, uint64_t* n_pairs)
+/* waits for the enqueued run and repeats it with larger buffers when the record stream or the work list overflowed
+   (an overflowing run still counts, so one repetition is enough) */
+static int pairs_finish(arp_ctx* c)
 {
-    if (!c) return ARP_E_INVALID_ARG;
-    ARP_REQUIRE(c, c->have_atoms, ARP_E_NOT_READY, "arp_pairs_run before arp_upload_atoms");
-    ARP_TRY(arp_bind(c));
-    c->pairs_valid = 0; c->sorted_valid = 0; c->sifts_valid = 0;
-    /* first guess of the stream length; an overflowing run still counts, then is repeated once */
-    uint64_t want = c->out_cap ? c->out_cap : (uint64_t)c->N * 16 + 4096;
-    ARP_TRY(pairs_out_reserve(c, want));
     for (int attempt = 0; attempt < 3; ++attempt) {
-        ARP_TRY(arp_pairs_enqueue(c, 1));
+        if (attempt > 0) ARP_TRY(arp_pairs_enqueue(c, 1));
         ARP_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->run_pending = 0;
         /* candidates >= records: both lists share the capacity (k_tiles has no candidate list: n_raw stays 0) */
         const uint64_t n = c->h_meta->n_raw > c->h_meta->n_pairs ? c->h_meta->n_raw : c->h_meta->n_pairs;
         const uint64_t nw = c->h_meta->n_work + c->h_meta->n_work_rare;     /* the list is filled from both ends */
+        if (c->h_meta->fault & 2u) {
+            /* k_classify gave up waiting for a candidate that k_search had announced (slow producer: time slicing,
+               a debugger).  Not an error: clean the list and repeat the run with k_classify waiting for k_search. */
+            if (c->hits.p) ARP_CUDA(c, cudaMemsetAsync(c->hits.p, 0, c->hits.cap, c->stream));
+            ARP_REQUIRE(c, attempt < 2, ARP_E_CUDA, "candidate hand-off between k_search and k_classify timed out repeatedly");
+            c->use_early_cls = 0;
+            continue;
+        }
         if (n <= c->out_cap && nw <= c->work_cap) break;
         ARP_REQUIRE(c, attempt < 2, ARP_E_CAPACITY, "record stream overflowed repeatedly");
         if (n > c->out_cap) ARP_TRY(pairs_out_reserve(c, n + n / 16 + 1024));
@@ -427,31 +439,54 @@ int arp_pairs_run(arp_ctx* c, uint64_t* n_pairs)
             c->work_cap = c->work.cap / 16;
         }
     }
-    if (c->h_meta->fault & 2u) {            /* never seen; the list may hold unread entries: clean it before reporting */
-        cudaMemsetAsync(c->hits.p, 0, c->hits.cap, c->stream);
-        cudaStreamSynchronize(c->stream);
-        (void)cudaGetLastError();
-        return arp_fail(c, ARP_E_CUDA, "candidate hand-off between k_search and k_classify timed out", __FILE__, __LINE__);
-    }
     ARP_REQUIRE(c, c->h_meta->n_pairs < (1ull << 32), ARP_E_CAPACITY, "more than 2^32 records in one run");
     c->n_pairs = c->h_meta->n_pairs;
     c->pairs_valid = 1;
     fill_stats(c, 1);
+    return ARP_OK;
+}
+
+int arp_pairs_run_async(arp_ctx* c)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_REQUIRE(c, c->have_atoms, ARP_E_NOT_READY, "arp_pairs_run before arp_upload_atoms");
+    ARP_TRY(arp_bind(c));
+    pairs_invalidate(c);
+    /* first guess of the stream length; an overflowing run still counts, then is repeated once */
+    uint64_t want = c->out_cap ? c->out_cap : (uint64_t)c->N * 16 + 4096;
+    ARP_TRY(pairs_out_reserve(c, want));
+    ARP_TRY(arp_pairs_enqueue(c, 1));
+    c->run_pending = 1;
+    return ARP_OK;
+}
+
+int arp_pairs_run(arp_ctx* c, uint64_t* n_pairs)
+{
+    ARP_TRY(arp_pairs_run_async(c));
+    ARP_TRY(pairs_finish(c));
     if (n_pairs) *n_pairs = c->n_pairs;
+    return ARP_OK;
+}
+
+/* a run enqueued by arp_pairs_run_async is waited for by the first call that needs its result */
+static int pairs_ready(arp_ctx* c, const char* what)
+{
+    if (c->run_pending) { ARP_TRY(arp_bind(c)); ARP_TRY(pairs_finish(c)); }
+    ARP_REQUIRE(c, c->pairs_valid, ARP_E_NOT_READY, what);
     return ARP_OK;
 }
 
 int arp_pairs_fetch(arp_ctx* c, arp_pair* dst, uint64_t cap, int sorted)
 {
     if (!c) return ARP_E_INVALID_ARG;
-    ARP_REQUIRE(c, c->pairs_valid, ARP_E_NOT_READY, "arp_pairs_fetch before arp_pairs_run");
+    ARP_TRY(pairs_ready(c, "arp_pairs_fetch before arp_pairs_run"));
     ARP_REQUIRE(c, cap >= c->n_pairs, ARP_E_CAPACITY, "destination holds fewer records than the run produced");
     if (c->n_pairs == 0) return ARP_OK;
     ARP_REQUIRE(c, dst != nullptr, ARP_E_INVALID_ARG, "dst is NULL");
     ARP_TRY(arp_bind(c));
     const arp_pair* src = c->out.as<arp_pair>();
     if (sorted) {
-        ARP_TRY(arp_pairs_sorted_build(c));
+        ARP_TRY(arp_pairs_sorted_build(c, 0));
         src = c->sort_out.as<arp_pair>();
     }
     ARP_CUDA(c, cudaMemcpyAsync(dst, src, (size_t)c->n_pairs * sizeof(arp_pair), cudaMemcpyDeviceToHost, c->stream));
@@ -459,11 +494,70 @@ int arp_pairs_fetch(arp_ctx* c, arp_pair* dst, uint64_t cap, int sorted)
     return ARP_OK;
 }
 
+int arp_pairs_count(arp_ctx* c, uint64_t* n_pairs)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_REQUIRE(c, n_pairs != nullptr, ARP_E_INVALID_ARG, "n_pairs is NULL");
+    ARP_TRY(pairs_ready(c, "arp_pairs_count before arp_pairs_run"));
+    *n_pairs = c->n_pairs;
+    return ARP_OK;
+}
+
+int arp_pairs_fetch_compact(arp_ctx* c, uint32_t* row_off, arp_pair_c* rec, uint64_t cap, float* dist, uint64_t* n_pairs)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_TRY(pairs_ready(c, "arp_pairs_fetch_compact before arp_pairs_run"));
+    if (n_pairs) *n_pairs = c->n_pairs;
+    ARP_REQUIRE(c, cap >= c->n_pairs, ARP_E_CAPACITY, "destination holds fewer records than the run produced");
+    ARP_REQUIRE(c, row_off != nullptr, ARP_E_INVALID_ARG, "row_off is NULL");
+    ARP_REQUIRE(c, c->n_pairs == 0 || rec != nullptr, ARP_E_INVALID_ARG, "rec is NULL");
+    ARP_TRY(arp_bind(c));
+    ARP_TRY(arp_pairs_sorted_build(c, 1));
+    ARP_CUDA(c, cudaMemcpyAsync(row_off, c->sort_off.p, ((size_t)c->N + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (c->n_pairs) {
+        ARP_CUDA(c, cudaMemcpyAsync(rec, c->sort_c.p, (size_t)c->n_pairs * sizeof(arp_pair_c), cudaMemcpyDeviceToHost, c->stream));
+        if (dist) ARP_CUDA(c, cudaMemcpyAsync(dist, c->sort_d.p, (size_t)c->n_pairs * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    ARP_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ARP_OK;
+}
+
+int arp_pairs_fetch_dist(arp_ctx* c, float* dist, uint64_t cap)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_TRY(pairs_ready(c, "arp_pairs_fetch_dist before arp_pairs_run"));
+    ARP_REQUIRE(c, cap >= c->n_pairs, ARP_E_CAPACITY, "destination holds fewer distances than the run produced");
+    if (c->n_pairs == 0) return ARP_OK;
+    ARP_REQUIRE(c, dist != nullptr, ARP_E_INVALID_ARG, "dist is NULL");
+    ARP_TRY(arp_bind(c));
+    ARP_TRY(arp_pairs_sorted_build(c, 1));
+    ARP_CUDA(c, cudaMemcpyAsync(dist, c->sort_d.p, (size_t)c->n_pairs * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    ARP_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ARP_OK;
+}
+
+/* host only: the compact view back into 16-byte records (dist == NULL: distance 0) */
+int arp_pairs_unpack(const uint32_t* row_off, const arp_pair_c* rec, const float* dist, int32_t n_atoms, arp_pair* dst, uint64_t cap)
+{
+    if (n_atoms < 0 || (n_atoms > 0 && !row_off)) return ARP_E_INVALID_ARG;
+    if (n_atoms == 0) return ARP_OK;
+    const uint64_t n = row_off[n_atoms];
+    if (n > cap) return ARP_E_CAPACITY;
+    if (n && (!rec || !dst)) return ARP_E_INVALID_ARG;
+    for (int32_t i = 0; i < n_atoms; ++i) {
+        if (row_off[i + 1] < row_off[i] || row_off[i + 1] > n) return ARP_E_INVALID_ARG;
+        for (uint64_t k = row_off[i]; k < row_off[i + 1]; ++k) {
+            dst[k].i = i; dst[k].j = rec[k].j; dst[k].mask = rec[k].mask; dst[k].dist = dist ? dist[k] : 0.f;
+        }
+    }
+    return ARP_OK;
+}
+
 int arp_pairs_device_ptr(arp_ctx* c, const arp_pair** dptr)
 {
     if (!c) return ARP_E_INVALID_ARG;
     ARP_REQUIRE(c, dptr != nullptr, ARP_E_INVALID_ARG, "dptr is NULL");
-    ARP_REQUIRE(c, c->pairs_valid, ARP_E_NOT_READY, "no record stream yet");
+    ARP_TRY(pairs_ready(c, "no record stream yet"));
     *dptr = c->out.as<arp_pair>();
     return ARP_OK;
 }
@@ -483,7 +577,7 @@ int arp_ring_nearest_atom(arp_ctx* c, const float* xyz, int32_t n_atoms, const d
 int arp_atom_sifts_run(arp_ctx* c)
 {
     if (!c) return ARP_E_INVALID_ARG;
-    ARP_REQUIRE(c, c->pairs_valid, ARP_E_NOT_READY, "arp_atom_sifts_run before arp_pairs_run");
+    ARP_TRY(pairs_ready(c, "arp_atom_sifts_run before arp_pairs_run"));
     ARP_TRY(arp_bind(c));
     ARP_TRY(arp_atom_sifts_enqueue(c));
     c->sifts_valid = 1;
@@ -549,6 +643,7 @@ int arp_timing_iters(arp_ctx* c, int iters, int flush_l2, float* ms_per_iter)
     ARP_REQUIRE(c, c->have_atoms, ARP_E_NOT_READY, "arp_timing_iters before arp_upload_atoms");
     ARP_REQUIRE(c, iters > 0, ARP_E_INVALID_ARG, "iters must be positive");
     ARP_TRY(arp_bind(c));
+    if (c->run_pending) ARP_TRY(pairs_finish(c));
     if (!c->pairs_valid) ARP_TRY(arp_pairs_run(c, nullptr));      /* sizes the record buffer */
     const size_t flush_bytes = (size_t)384 << 20;
     if (flush_l2) ARP_TRY(dbuf_reserve(c, c->flush, flush_bytes));
@@ -595,8 +690,48 @@ int arp_timing_iters(arp_ctx* c, int iters, int flush_l2, float* ms_per_iter)
     c->stats.ms_classify = (float)(classify / split_iters);
     c->stats.ms_hscan = (float)(hscan / split_iters);
     c->stats.ms_total = (float)(tot / iters);
-    c->sorted_valid = 0; c->sifts_valid = 0;
+    c->sorted_valid = 0; c->compact_valid = 0; c->sort_tmp_valid = 0; c->sifts_valid = 0;
     if (ms_per_iter) *ms_per_iter = (float)(tot / iters);
+    return ARP_OK;
+}
+
+int arp_memcpy_probe(arp_ctx* c, uint64_t h2d_bytes, uint64_t d2h_bytes, int iters, float* ms)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_REQUIRE(c, ms != nullptr && iters > 0 && h2d_bytes > 0 && d2h_bytes > 0, ARP_E_INVALID_ARG, "bad probe arguments");
+    ARP_TRY(arp_bind(c));
+    void *hu = nullptr, *hd = nullptr, *du = nullptr, *dd = nullptr;
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaError_t e = cudaMallocHost(&hu, h2d_bytes);
+    if (e == cudaSuccess) e = cudaMallocHost(&hd, d2h_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&du, h2d_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&dd, d2h_bytes);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+    for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaEventCreate(&ev[k]);
+    if (e == cudaSuccess) {
+        memset(hu, 1, h2d_bytes);
+        cudaMemsetAsync(dd, 2, d2h_bytes, c->stream);
+        for (int w = 0; w < 2; ++w) {       /* one warm-up pass, one timed */
+            cudaStreamSynchronize(c->stream); cudaStreamSynchronize(s2);
+            cudaEventRecord(ev[0], c->stream); cudaEventRecord(ev[2], s2);
+            for (int it = 0; it < iters; ++it) {
+                cudaMemcpyAsync(du, hu, h2d_bytes, cudaMemcpyHostToDevice, c->stream);
+                cudaMemcpyAsync(hd, dd, d2h_bytes, cudaMemcpyDeviceToHost, s2);
+            }
+            cudaEventRecord(ev[1], c->stream); cudaEventRecord(ev[3], s2);
+        }
+        cudaStreamSynchronize(c->stream);
+        e = cudaStreamSynchronize(s2);
+        if (e == cudaSuccess) { cudaEventElapsedTime(&ms[0], ev[0], ev[1]); cudaEventElapsedTime(&ms[1], ev[2], ev[3]); }
+    }
+    for (int k = 0; k < 4; ++k) if (ev[k]) cudaEventDestroy(ev[k]);
+    if (s2) cudaStreamDestroy(s2);
+    if (hu) cudaFreeHost(hu);
+    if (hd) cudaFreeHost(hd);
+    if (du) cudaFree(du);
+    if (dd) cudaFree(dd);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return arp_fail(c, ARP_E_CUDA, cudaGetErrorString(e), __FILE__, __LINE__); }
     return ARP_OK;
 }
 

@@ -162,7 +162,9 @@ struct arp_ctx {
     uint64_t n_pairs = 0;
     int pairs_valid = 0;
     DBuf sort_tmp, sort_out, sort_zero, sort_off;
-    int sorted_valid = 0;
+    DBuf sort_c, sort_d;          /* compact view of the sorted stream: arp_pair_c[n] and float[n] (row offsets: sort_off) */
+    int sorted_valid = 0, compact_valid = 0, sort_tmp_valid = 0;
+    int run_pending = 0;          /* arp_pairs_run_async has enqueued a run that nobody has waited for yet */
 
     /* planes */
     PlaneSet rings, amides;
@@ -260,7 +262,7 @@ int  arp_pairs_prepare(arp_ctx* c);                       /* arp_pairs.cu: size 
    job, 2: also ev[1] between the grid build and the pair kernels, 3: also ev[2] / ev[4] between the pair kernels
    (every event between two kernels keeps them from overlapping and costs a few microseconds) */
 int  arp_pairs_enqueue(arp_ctx* c, int with_events);
-int  arp_pairs_sorted_build(arp_ctx* c);                  /* arp_pairs.cu: (i, j)-ascending copy of the stream */
+int  arp_pairs_sorted_build(arp_ctx* c, int compact);     /* arp_pairs.cu: (i, j)-ascending copy of the stream (16-byte records or the compact view) */
 int  arp_flag_within_run(arp_ctx* c, double radius);      /* arp_pairs.cu */
 int  arp_ring_nearest_run(arp_ctx* c, const float* xyz, int n_atoms, const double* centers, int n_rings, double radius,
                           int32_t* atom_out, double* dist_out);   /* arp_rings.cu */

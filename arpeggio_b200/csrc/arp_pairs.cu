@@ -1730,9 +1730,12 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const arp_pair* __restrict
 }
 
 /* records of one i are contiguous in tmp; (i, j) is unique, so the rank of j inside the segment
-   is the final position */
+   is the final position.  COMPACT: the sorted stream leaves as 8-byte records (j, mask) -- i is implied by the
+   row offsets `off` -- and the distances as a stream of their own (arp_pairs_fetch_compact). */
+template <bool COMPACT>
 __global__ void __launch_bounds__(256) k_sort_place(const arp_pair* __restrict__ tmp, unsigned long long n,
-                                                    const int* __restrict__ off, arp_pair* __restrict__ out)
+                                                    const int* __restrict__ off, arp_pair* __restrict__ out,
+                                                    arp_pair_c* __restrict__ outc, float* __restrict__ outd)
 {
     unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
@@ -1740,42 +1743,67 @@ __global__ void __launch_bounds__(256) k_sort_place(const arp_pair* __restrict__
     int b = off[v.x], e = off[v.x + 1];
     int rank = 0;
     for (int k = b; k < e; ++k) rank += tmp[k].j < v.y ? 1 : 0;
-    reinterpret_cast<int4*>(out)[b + rank] = v;
+    if (COMPACT) {
+        reinterpret_cast<int2*>(outc)[b + rank] = make_int2(v.y, v.z);
+        outd[b + rank] = __int_as_float(v.w);
+    } else {
+        reinterpret_cast<int4*>(out)[b + rank] = v;
+    }
 }
 
-int arp_pairs_sorted_build(arp_ctx* c)
+/* compact != 0: sort_c (arp_pair_c[n]) + sort_d (float[n]) + sort_off (row offsets) instead of sort_out */
+int arp_pairs_sorted_build(arp_ctx* c, int compact)
 {
-    if (c->sorted_valid) return ARP_OK;
+    if (compact ? c->compact_valid : c->sorted_valid) return ARP_OK;
     const unsigned long long n = c->n_pairs;
     const size_t N = (size_t)c->N;
     if (n >= (1ull << 31)) return arp_fail(c, ARP_E_CAPACITY, "too many records for the sorted view", __FILE__, __LINE__);
-    ARP_TRY(dbuf_reserve(c, c->sort_out, sizeof(arp_pair) * (size_t)n));
-    if (n == 0) { c->sorted_valid = 1; return ARP_OK; }
-    ARP_TRY(dbuf_reserve(c, c->sort_tmp, sizeof(arp_pair) * (size_t)n));
-    /* zero region: cnt[N+1] | cur[N+1] | ticket | scan state */
-    size_t tiles = (N + 1 + ARP_SCAN_TILE - 1) / ARP_SCAN_TILE + 1;
-    size_t o_cur = align_up(sizeof(int) * (N + 2), 256);
-    size_t o_tick = align_up(o_cur + sizeof(int) * (N + 2), 256);
-    size_t o_state = o_tick + 256;
-    size_t zb = o_state + tiles * sizeof(unsigned long long);
-    ARP_TRY(dbuf_reserve(c, c->sort_zero, zb));
+    if (compact) {
+        ARP_TRY(dbuf_reserve(c, c->sort_c, sizeof(arp_pair_c) * (size_t)n));
+        ARP_TRY(dbuf_reserve(c, c->sort_d, sizeof(float) * (size_t)n));
+    } else {
+        ARP_TRY(dbuf_reserve(c, c->sort_out, sizeof(arp_pair) * (size_t)n));
+    }
     ARP_TRY(dbuf_reserve(c, c->sort_off, sizeof(int) * (N + 2)));
-    char* z = c->sort_zero.as<char>();
-    int* cnt = (int*)z; int* cur = (int*)(z + o_cur);
-    unsigned* ticket = (unsigned*)(z + o_tick);
-    unsigned long long* state = (unsigned long long*)(z + o_state);
-    ARP_CUDA(c, cudaMemsetAsync(z, 0, zb, c->stream));
+    if (n == 0) {
+        ARP_CUDA(c, cudaMemsetAsync(c->sort_off.p, 0, sizeof(int) * (N + 2), c->stream));
+        if (compact) c->compact_valid = 1; else c->sorted_valid = 1;
+        return ARP_OK;
+    }
     unsigned blocks = (unsigned)((n + 255) / 256);
-    k_sort_count<<<blocks, 256, 0, c->stream>>>(c->out.as<arp_pair>(), n, cnt);
-    ARP_LAUNCHED(c);
-    ARP_TRY(arp_scan_exclusive(c, cnt, c->sort_off.as<int>(), state, ticket, nullptr, (int)(N + 1), N + 1));
-    k_sort_scatter<<<blocks, 256, 0, c->stream>>>(c->out.as<arp_pair>(), n, c->sort_off.as<int>(), cur,
-                                                  c->sort_tmp.as<arp_pair>());
-    ARP_LAUNCHED(c);
-    k_sort_place<<<blocks, 256, 0, c->stream>>>(c->sort_tmp.as<arp_pair>(), n, c->sort_off.as<int>(),
-                                                c->sort_out.as<arp_pair>());
-    ARP_LAUNCHED(c);
-    c->sorted_valid = 1;
+    if (!c->sort_tmp_valid) {           /* records grouped by i (tmp) + row offsets: shared by both views */
+        ARP_TRY(dbuf_reserve(c, c->sort_tmp, sizeof(arp_pair) * (size_t)n));
+        /* zero region: cnt[N+1] | cur[N+1] | ticket | scan state */
+        size_t tiles = (N + 1 + ARP_SCAN_TILE - 1) / ARP_SCAN_TILE + 1;
+        size_t o_cur = align_up(sizeof(int) * (N + 2), 256);
+        size_t o_tick = align_up(o_cur + sizeof(int) * (N + 2), 256);
+        size_t o_state = o_tick + 256;
+        size_t zb = o_state + tiles * sizeof(unsigned long long);
+        ARP_TRY(dbuf_reserve(c, c->sort_zero, zb));
+        char* z = c->sort_zero.as<char>();
+        int* cnt = (int*)z; int* cur = (int*)(z + o_cur);
+        unsigned* ticket = (unsigned*)(z + o_tick);
+        unsigned long long* state = (unsigned long long*)(z + o_state);
+        ARP_CUDA(c, cudaMemsetAsync(z, 0, zb, c->stream));
+        k_sort_count<<<blocks, 256, 0, c->stream>>>(c->out.as<arp_pair>(), n, cnt);
+        ARP_LAUNCHED(c);
+        ARP_TRY(arp_scan_exclusive(c, cnt, c->sort_off.as<int>(), state, ticket, nullptr, (int)(N + 1), N + 1));
+        k_sort_scatter<<<blocks, 256, 0, c->stream>>>(c->out.as<arp_pair>(), n, c->sort_off.as<int>(), cur,
+                                                      c->sort_tmp.as<arp_pair>());
+        ARP_LAUNCHED(c);
+        c->sort_tmp_valid = 1;
+    }
+    if (compact) {
+        k_sort_place<true><<<blocks, 256, 0, c->stream>>>(c->sort_tmp.as<arp_pair>(), n, c->sort_off.as<int>(), nullptr,
+                                                          c->sort_c.as<arp_pair_c>(), c->sort_d.as<float>());
+        ARP_LAUNCHED(c);
+        c->compact_valid = 1;
+    } else {
+        k_sort_place<false><<<blocks, 256, 0, c->stream>>>(c->sort_tmp.as<arp_pair>(), n, c->sort_off.as<int>(),
+                                                           c->sort_out.as<arp_pair>(), nullptr, nullptr);
+        ARP_LAUNCHED(c);
+        c->sorted_valid = 1;
+    }
     return ARP_OK;
 }
 

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) k_sift_finalize(int N, const SiftAcc* __r
 int arp_atom_sifts_enqueue(arp_ctx* c)
 {
     const size_t N = (size_t)c->N;
-    ARP_TRY(arp_pairs_sorted_build(c));
+    ARP_TRY(arp_pairs_sorted_build(c, 0));
     ARP_TRY(dbuf_reserve(c, c->sift_acc, sizeof(SiftAcc) * N));
     ARP_TRY(dbuf_reserve(c, c->sift_out, sizeof(arp_atom_sift) * N));
     if (N == 0) return ARP_OK;

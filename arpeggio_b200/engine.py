@@ -80,6 +80,38 @@ def pinned_soa(soa):
     return AtomSoA(**fields, _keep=[block])
 
 
+class CompactPairs:
+    """Compact view of an (i, j)-sorted record stream: the records of bgn atom i are rec[row_off[i]:row_off[i + 1]]
+    (fields j, mask); dist (float32, same order) is optional.  to_records() gives the 16-byte PAIR_DTYPE array."""
+
+    def __init__(self, row_off, rec_buf, dist_buf):
+        self.row_off, self.rec_buf, self.dist_buf = row_off, rec_buf, dist_buf
+        self.rec, self.dist, self.n, self.n_atoms = rec_buf[:0], None, 0, 0
+
+    def view(self, n_atoms, n, with_dist):
+        v = CompactPairs(self.row_off, self.rec_buf, self.dist_buf)
+        v.n_atoms, v.n = n_atoms, n
+        v.row_off = self.row_off[:n_atoms + 1]
+        v.rec = self.rec_buf[:n]
+        v.dist = self.dist_buf[:n] if with_dist and self.dist_buf is not None else None
+        return v
+
+    @property
+    def nbytes(self):
+        return self.row_off.nbytes + self.rec.nbytes + (self.dist.nbytes if self.dist is not None else 0)
+
+    def to_records(self, dist=None):
+        """PAIR_DTYPE[n] through the library's host unpacker (arp_pairs_unpack)."""
+        out = np.empty(self.n, dtype=abi.PAIR_DTYPE)
+        d = self.dist if dist is None else np.ascontiguousarray(dist, np.float32)
+        rc = lib().arp_pairs_unpack(self.row_off.ctypes.data, self.rec.ctypes.data if self.n else None,
+                                    d.ctypes.data if d is not None and self.n else None, self.n_atoms,
+                                    out.ctypes.data if self.n else None, self.n)
+        if rc != abi.OK:
+            raise ArpeggioCudaError(rc, 'arp_pairs_unpack failed')
+        return out
+
+
 class ContactEngine:
     def __init__(self, device=0, params=None):
         self._L = lib()
@@ -145,6 +177,46 @@ class ContactEngine:
             raise ValueError('out must be a C-contiguous PAIR_DTYPE array of at least n records')
         self._check(self._L.arp_pairs_fetch(self._ctx, out.ctypes.data if out.shape[0] else None, out.shape[0],
                                             1 if sorted else 0))
+        return out[:n]
+
+    def run_pairs_async(self):
+        """Enqueues the job of run_pairs without waiting for it: the next pair_count / fetch_* call does."""
+        self._check(self._L.arp_pairs_run_async(self._ctx))
+
+    def pair_count(self):
+        n = C.c_uint64()
+        self._check(self._L.arp_pairs_count(self._ctx, C.byref(n)))
+        return int(n.value)
+
+    def fetch_pairs_compact(self, with_dist=False, out=None, grow=None):
+        """The (i, j)-sorted stream of the last run in its compact form (arp_pairs_fetch_compact): returns
+        CompactPairs(row_off uint32[N + 1], rec PAIR_C_DTYPE[n], dist float32[n] or None).  8 bytes per record + 4 per
+        atom cross PCIe instead of 16 per record; distances on demand (fetch_pairs_dist).  out: a CompactPairs whose
+        arrays are reused when they are large enough (pinned buffers of a batch slot); grow(n): called for a larger
+        CompactPairs when the stream does not fit `out`."""
+        n_atoms = self._soa.n_atoms
+        n = C.c_uint64()
+        if out is None or out.row_off.shape[0] < n_atoms + 1:
+            out = CompactPairs(np.empty(n_atoms + 1, np.uint32), np.empty(0, abi.PAIR_C_DTYPE), None)
+        for attempt in range(2):
+            dist = out.dist_buf if with_dist else None
+            cap = out.rec_buf.shape[0] if dist is None else min(out.rec_buf.shape[0], dist.shape[0])
+            rc = self._L.arp_pairs_fetch_compact(self._ctx, out.row_off.ctypes.data, out.rec_buf.ctypes.data if cap else None, cap,
+                                                 dist.ctypes.data if dist is not None and cap else None, C.byref(n))
+            if rc == abi.E_CAPACITY and attempt == 0:      # the count is known now: size the buffers and fetch again
+                m = int(n.value)
+                out = grow(m) if grow is not None else CompactPairs(out.row_off, np.empty(m, abi.PAIR_C_DTYPE),
+                                                                    np.empty(m, np.float32) if with_dist else None)
+                continue
+            self._check(rc)
+            break
+        return out.view(n_atoms, int(n.value), with_dist)
+
+    def fetch_pairs_dist(self, n, out=None):
+        """float32 distances of the sorted stream, same order as the compact records."""
+        if out is None:
+            out = np.empty(n, np.float32)
+        self._check(self._L.arp_pairs_fetch_dist(self._ctx, out.ctypes.data if n else None, out.shape[0]))
         return out[:n]
 
     def pairs(self, soa=None, sorted=True):
@@ -228,6 +300,13 @@ class ContactEngine:
 
     def launch_count(self):
         return int(self._L.arp_launch_count(self._ctx))
+
+    def memcpy_probe(self, h2d_bytes, d2h_bytes, iters=20):
+        """GB/s of pinned cudaMemcpyAsync host -> device and device -> host, both directions at once (bench hook)."""
+        ms = (C.c_float * 2)()
+        self._check(self._L.arp_memcpy_probe(self._ctx, int(h2d_bytes), int(d2h_bytes), int(iters), ms))
+        return {'h2d_gbs': h2d_bytes * iters / (ms[0] * 1e6) if ms[0] > 0 else 0.0,
+                'd2h_gbs': d2h_bytes * iters / (ms[1] * 1e6) if ms[1] > 0 else 0.0}
 
     def time_pairs(self, iters, flush_l2=True):
         """Mean CUDA-event time (ms) of the whole atom-atom job over `iters` runs on the resident inputs."""

@@ -8,10 +8,17 @@ One step = one pass of the whole atom-atom job (cell-grid build + pair kernel: n
 filters, fused 15-bit CREDO classifier, record emission) over the configs[2] structure.
   value     pairs/s with the inputs resident in HBM; every step is bracketed by CUDA events on the
             library's stream and L2 is flushed (384 MiB memset) between steps, outside the brackets
-  e2e       the same metric through the public API (ContactEngine.pairs) with HOST buffers: pinned
-            H2D of the step's arrays + kernels + D2H of the record stream inside the timed region
-  roofline  the pair kernel's algorithmic bytes (sum of input array bytes + 16 B per record) over its
-            mean CUDA-event duration in the same timed steps, against MEASURED_PEAKS.json (HBM copy)
+  e2e       the same metric through the public API with HOST buffers: pinned H2D of the step's arrays +
+            kernels + canonical (i, j) sort + D2H of the record stream inside the timed region.  The
+            stream crosses PCIe in its compact form (arp_pairs_fetch_compact: row offsets + 8-byte
+            (j, mask) records; the float32 distances stay on the device until asked for);
+            `records16` repeats the measurement with the 16-byte records (sorted too)
+  roofline  the step's algorithmic bytes (sum of input array bytes + 16 B per record) over the mean
+            CUDA-event duration of the WHOLE step (grid build + pair kernels), against
+            MEASURED_PEAKS.json (HBM copy); `pair_kernels` repeats it for the pair kernels alone and
+            `large` for a 1M-atom cloud of the same recipe
+  pcie      what the box's PCIe gives this rank while every rank copies at the same time: pinned
+            cudaMemcpyAsync of the e2e step's sizes, H2D and D2H concurrently (arp_memcpy_probe)
   cpu_baseline / --impl reference
             the CPU oracle (oracle/arp_oracle.c, a C port of the reference's Python loop -- the
             reference itself needs BioPython/OpenBabel/gemmi, which are not installable here) on the
@@ -52,7 +59,8 @@ def measured_peak():
 
 
 def ncu_traffic(atoms):
-    """dram bytes per k_pairs launch from the committed ncu --set full capture, if one was summarised."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the step's kernels, per step, from the committed ncu --set full
+    capture of this build (profiles/k_pairs_traffic.json, written by tools/make_profiles.py); None without one."""
     try:
         with open(os.path.join(ROOT, 'profiles', 'k_pairs_traffic.json')) as fh:
             t = json.load(fh)
@@ -232,7 +240,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 10_000 if args.steps <= 400 else 4_000
+    sample = args.atoms                      # the same configs[2] cloud as the product arm, one per host thread
     port = CpuPort(sample, cores)
     for _ in range(max(args.warmup, 1)):
         port.step()
@@ -242,12 +250,12 @@ def run_reference(args):
         pairs += n
         t_tot += dt
     value = pairs / t_tot
-    desc = f'{cores} threads x one {sample}-atom cloud of the configs[2] recipe per step (C port of the reference loop)'
+    desc = f'{cores} threads x one {sample}-atom cloud of the configs[2] recipe per step (C port of the reference loop; the reference itself is single-threaded Python)'
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * t_tot / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32 distance / f64 angles / u32 masks', 'data': 'synthetic',
-        'config': {'workload': workload_name(args.atoms), 'sample': desc},
+        'config': {'workload': workload_name(args.atoms), 'atoms_per_gpu': args.atoms, 'cutoff': 5.0, 'sample': desc},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -300,15 +308,25 @@ def run_ours(args):
     out_pin = PinnedBuffer(16 * (n_pairs + 1024))
     out = out_pin.array(abi.PAIR_DTYPE)
     e2e_steps = max(3, min(args.steps, 200))
+    runner = BatchRunner(device=local, slots=6, params=p)
+    cbuf = runner._compact_buffer(0, soa.n_atoms, n_pairs, False)      # pinned block of slot 0, reused by the serial leg
 
-    def e2e_step():
+    def e2e_step():                          # single stream: upload, run (not waited for), sorted compact fetch
+        eng.upload_atoms(host)
+        eng.run_pairs_async()
+        return eng.fetch_pairs_compact(False, out=cbuf)
+
+    def e2e_step16():                        # the same with the 16-byte records
         eng.upload_atoms(host)
         n = eng.run_pairs()
-        return eng.fetch_pairs(n, sorted=False, out=out)
+        return eng.fetch_pairs(n, sorted=True, out=out)
 
     for _ in range(3):
-        got = e2e_step()
-    assert got.shape[0] == n_pairs
+        got_c = e2e_step()
+        got = e2e_step16()
+    assert got_c.n == n_pairs and got.shape[0] == n_pairs
+    d2h_bytes = int(got_c.nbytes)
+    assert np.array_equal(got_c.to_records()[['i', 'j', 'mask']], got[['i', 'j', 'mask']])
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
@@ -316,27 +334,46 @@ def run_ours(args):
         e2e_step()
     eng.sync()
     e2e_serial_s = (time.perf_counter() - t0) / e2e_steps
-    # the batch API: the same steps through 3 stream slots, so that the H2D copy of one step, the kernels of
+    # the batch API: the same steps through 6 stream slots, so that the H2D copy of one step, the kernels of
     # another and the D2H copy of a third overlap; every step still moves its own inputs and results
-    runner = BatchRunner(device=local, slots=6, params=p)
     checked = []
-    runner.run([host] * 6, consume=lambda i, rec: checked.append(int(rec.shape[0])))
+    runner.run([host] * 6, consume=lambda i, cp: checked.append(int(cp.n)), compact=True)
     assert checked and all(c == n_pairs for c in checked)
     if dist:
         dist.barrier()
-    _, dt = runner.run([host] * e2e_steps, check_finite=False)
+    _, dt = runner.run([host] * e2e_steps, check_finite=False, compact=True)
     e2e_s = dt / e2e_steps
+    if dist:
+        dist.barrier()
+    runner.run([host] * 6, check_finite=False, sorted=True)          # warm-up: the sorted 16-byte view has buffers of its own
+    _, dt16 = runner.run([host] * e2e_steps, check_finite=False, sorted=True)
+    e2e16_s = dt16 / e2e_steps
+    # what PCIe gives this rank while all ranks copy at once: the same sizes, H2D and D2H concurrently
+    if dist:
+        dist.barrier()
+    pcie = eng.memcpy_probe(int(in_bytes), d2h_bytes, 40)
     # ---- configs[4]: PDB-batch throughput, this rank's shard of 20k-atom structures, host buffers, end to end ----
     batch = None
     if args.batch_structures > 0:
         distinct = [pinned_soa(synth.cloud_featured(args.batch_atoms, seed=1000 + 97 * rank + k)) for k in range(8)]
         shard = [distinct[k % len(distinct)] for k in range(args.batch_structures)]
-        runner.run(shard[:6], check_finite=False)
+        runner.run(shard[:6], check_finite=False, compact=True)
         if dist:
             dist.barrier()
-        counts, dt_b = runner.run(shard, check_finite=False)
+        counts, dt_b = runner.run(shard, check_finite=False, compact=True)
         batch = (len(shard), float(sum(counts)), dt_b)
     runner.close()
+    large = None
+    if rank == 0 and args.large_atoms > 0:
+        big = synth.cloud_featured(args.large_atoms, seed=5)
+        eng.upload_atoms(big)
+        n_big = eng.run_pairs()
+        eng.time_pairs(3, flush_l2=True)
+        ms_big = eng.time_pairs(20, flush_l2=True)
+        large = (args.large_atoms, n_big, ms_big, big.input_bytes() + 16 * n_big)
+        del big
+        eng.upload_atoms(soa)
+        eng.run_pairs()
     json_leg = json_emitter_leg(got, args.atoms) if rank == 0 and not args.no_cpu else None
     planes_leg = planes_leg_run(eng, soa, p, args.atoms, cpu=not args.no_cpu) if rank == 0 and args.atoms >= 1000 else None
     t_end = time.time()
@@ -344,11 +381,14 @@ def run_ours(args):
 
     # ---- aggregate over ranks: slowest rank's time, total pairs ------------------------------
     ms_pair = st['ms_pairs']                # the three pair kernels back to back, one event before and one after
-    tot_pairs, ms_max, e2e_max, e2e_serial_max = float(n_pairs), ms_step, e2e_s, e2e_serial_s
+    tot_pairs, ms_max, e2e_max, e2e_serial_max, e2e16_max = float(n_pairs), ms_step, e2e_s, e2e_serial_s, e2e16_s
+    pcie_min = dict(pcie)
     if dist:
         import torch
-        t = torch.tensor([ms_step, e2e_s, e2e_serial_s, batch[2] if batch else 0.0], dtype=torch.float64)
+        t = torch.tensor([ms_step, e2e_s, e2e_serial_s, batch[2] if batch else 0.0, e2e16_s, -pcie['h2d_gbs'], -pcie['d2h_gbs']], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e16_max = float(t[4])
+        pcie_min = {'h2d_gbs': -float(t[5]), 'd2h_gbs': -float(t[6])}
         s = torch.tensor([float(n_pairs), batch[0] if batch else 0.0, batch[1] if batch else 0.0], dtype=torch.float64)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
         ms_max, e2e_max, e2e_serial_max, tot_pairs = float(t[0]), float(t[1]), float(t[2]), float(s[0])
@@ -357,7 +397,8 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        achieved = alg_bytes / (ms_pair * 1e-3) / 1e9
+        achieved = alg_bytes / (ms_max * 1e-3) / 1e9            # t = first kernel start to last kernel end
+        achieved_pairs = alg_bytes / (ms_pair * 1e-3) / 1e9
         line = {
             'metric': METRIC, 'value': tot_pairs / (ms_max * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_max, 'higher_is_better': True, 'scaling': 'weak',
@@ -367,16 +408,26 @@ def run_ours(args):
                        'timing': 'sum of per-step CUDA-event brackets on the library stream, max over ranks',
                        'sharding': 'one independent structure per GPU, no collective'},
             'e2e': {'value': tot_pairs / e2e_max, 'unit': UNIT, 'h2d_bytes_per_step': int(in_bytes),
-                    'd2h_bytes_per_step': int(16 * n_pairs + 64), 'steps': e2e_steps, 'ms_per_step': e2e_max * 1e3,
-                    'api': 'BatchRunner.run, 6 stream slots, one pinned host block per structure',
+                    'd2h_bytes_per_step': d2h_bytes, 'steps': e2e_steps, 'ms_per_step': e2e_max * 1e3, 'sorted': True,
+                    'stream': 'compact: uint32 row offsets [atoms + 1] + 8-byte (j, mask) records, (i, j) ascending; float32 '
+                              'distances stay on the device (arp_pairs_fetch_dist)',
+                    'api': 'BatchRunner.run(compact=True), 6 stream slots, one pinned host block per structure, one wait per structure',
                     'serial_value': tot_pairs / e2e_serial_max, 'serial_ms_per_step': e2e_serial_max * 1e3,
-                    'serial_api': 'ContactEngine.upload_atoms + run_pairs + fetch_pairs, one stream'},
+                    'serial_api': 'ContactEngine.upload_atoms + run_pairs_async + fetch_pairs_compact, one stream',
+                    'records16': {'value': tot_pairs / e2e16_max, 'ms_per_step': e2e16_max * 1e3, 'd2h_bytes_per_step': int(16 * n_pairs),
+                                  'api': 'BatchRunner.run(sorted=True): 16-byte arp_pair records'},
+                    'pcie': dict(pcie_min, what='pinned cudaMemcpyAsync of the step\'s H2D and D2H sizes, both directions at once, '
+                                                'every rank at the same time (min over ranks, GB/s per GPU)',
+                                 d2h_floor_ms=d2h_bytes / (pcie_min['d2h_gbs'] * 1e6) if pcie_min['d2h_gbs'] else None,
+                                 h2d_floor_ms=in_bytes / (pcie_min['h2d_gbs'] * 1e6) if pcie_min['h2d_gbs'] else None)},
             'gpu_launches': int(launches),
             'kernels_per_step': int(per_step),
-            'roofline': {'bound': 'hbm', 'kernel': 'k_search + k_classify + k_hscan (the pair kernels, timed together)',
+            'roofline': {'bound': 'hbm', 'kernel': 'the whole step: k_grid_reg + k_search + k_classify + k_hscan',
                          'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'frac_of_nominal_8tbs': achieved / 8000.0,
-                         'traffic': ncu_traffic(args.atoms), 'algorithmic_bytes': int(alg_bytes), 'kernel_ms': ms_pair,
+                         'traffic': ncu_traffic(args.atoms), 'algorithmic_bytes': int(alg_bytes), 'kernel_ms': ms_max,
+                         'pair_kernels': {'kernel': 'k_search + k_classify + k_hscan, one event before and one after',
+                                          'kernel_ms': ms_pair, 'achieved': achieved_pairs, 'frac': achieved_pairs / peak},
                          'grid_build_ms': st['ms_grid'],
                          'split_with_events_between_all_kernels': {'search_ms': st['ms_search'], 'classify_ms': st['ms_classify'] - st['ms_hscan'], 'hscan_ms': st['ms_hscan']},
                          'peak_source': peak_src},
@@ -384,6 +435,11 @@ def run_ours(args):
             'candidate_tests_per_step': int(st['n_candidates']),
             'candidate_tests_per_s': float(st['n_candidates']) * world / (ms_max * 1e-3),
         }
+        if large:
+            a_l = large[3] / (large[2] * 1e-3) / 1e9
+            line['roofline']['large'] = {'atoms': large[0], 'pairs': large[1], 'ms_per_step': large[2], 'pairs_per_s': large[1] / (large[2] * 1e-3),
+                                         'algorithmic_bytes': int(large[3]), 'achieved': a_l, 'frac': a_l / peak,
+                                         'what': 'the same step on a 1M-atom cloud of the same recipe (20 steps, L2 flushed), where launch ramps and tails no longer dominate'}
         if json_leg:
             line['json'] = json_leg
         if planes_leg:
@@ -424,6 +480,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--batch-structures', type=int, default=128, help='structures per GPU of the PDB-batch leg (0: skip)')
     ap.add_argument('--batch-atoms', type=int, default=20_000)
+    ap.add_argument('--large-atoms', type=int, default=1_000_000, help='size of the roofline.large leg (0: skip)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ARP_ABI_VERSION 4
+#define ARP_ABI_VERSION 5
 
 /* ---- error codes -------------------------------------------------------- */
 #define ARP_OK              0
@@ -210,6 +210,14 @@ typedef struct arp_pair {       /* AtomAtomContact, interactions.py:28-29, :936 
     float    dist;              /* np.linalg.norm(bgn.coord - end.coord), float32 */
 } arp_pair;
 
+/* compact view of the (i, j)-sorted stream (arp_pairs_fetch_compact): the records of bgn atom i are rows
+   row_off[i] .. row_off[i + 1] - 1; `i` is not stored and the float32 distances travel as a separate stream that is
+   fetched only on demand: 8 bytes per record + 4 per atom over PCIe instead of 16 per record. */
+typedef struct arp_pair_c {
+    int32_t  j;                 /* end atom index (ascending inside a row) */
+    uint32_t mask;              /* as arp_pair.mask */
+} arp_pair_c;
+
 typedef struct arp_plane_pair { /* PlanePlaneContact, interactions.py:23-26 */
     int32_t  a;                 /* bgn plane index */
     int32_t  b;                 /* end plane index */
@@ -254,7 +262,13 @@ typedef struct arp_stats {
     float    ms_classify;       /* classify kernels: distance + angle + bitmask rules -> records (includes ms_hscan) */
     float    ms_hscan;          /* of which the deferred hydrogen / halogen / xbond predicates */
     float    ms_pairs;          /* the three pair kernels back to back (no events between them) */
+    uint32_t faults;            /* device-side diagnostics of the last run: ARP_FAULT_* */
+    uint32_t _pad;
 } arp_stats;
+
+#define ARP_FAULT_NONFINITE  1u  /* a NaN / Inf coordinate: that structure was searched as ONE cell (every pair tested);
+                                    pairs with such an atom never compare true, as in the reference */
+#define ARP_FAULT_HANDOFF    2u  /* the early start of k_classify timed out once; the run was repeated without it */
 
 /* ---- life cycle ---------------------------------------------------------- */
 int  arp_abi_version(void);
@@ -281,6 +295,19 @@ int  arp_upload_atoms(arp_ctx* ctx, const arp_atoms* atoms);     /* async H2D */
 int  arp_pairs_run(arp_ctx* ctx, uint64_t* n_pairs);             /* kernels; returns the record count */
 int  arp_pairs_fetch(arp_ctx* ctx, arp_pair* dst, uint64_t cap, int sorted); /* D2H; sorted!=0: (i,j) ascending */
 int  arp_pairs_device_ptr(arp_ctx* ctx, const arp_pair** dptr);  /* device pointer of the record stream */
+/* The same job without the host waiting for it ("arp_pairs_run is asynchronous; fetch / sync block"):
+   arp_pairs_run_async only enqueues; the first of arp_pairs_count / arp_pairs_fetch* / arp_atom_sifts_run /
+   arp_pairs_device_ptr waits for the run (and repeats it if the record buffer was too small). */
+int  arp_pairs_run_async(arp_ctx* ctx);
+int  arp_pairs_count(arp_ctx* ctx, uint64_t* n_pairs);
+/* Compact D2H of the (i, j)-sorted stream: row_off[n_atoms + 1], rec[cap >= n_pairs], dist[cap] or NULL (the distances
+   stay on the device and can be fetched later with arp_pairs_fetch_dist, same order).  *n_pairs is set even when the
+   call fails with ARP_E_CAPACITY, so the caller can size its buffers and call again (the run is not repeated). */
+int  arp_pairs_fetch_compact(arp_ctx* ctx, uint32_t* row_off, arp_pair_c* rec, uint64_t cap, float* dist, uint64_t* n_pairs);
+int  arp_pairs_fetch_dist(arp_ctx* ctx, float* dist, uint64_t cap);
+/* host only, no context: compact view -> 16-byte records (dist NULL: distance 0) */
+int  arp_pairs_unpack(const uint32_t* row_off, const arp_pair_c* rec, const float* dist, int32_t n_atoms,
+                      arp_pair* dst, uint64_t cap);
 
 /* ---- plane terms -----------------------------------------------------------
  * arp_ring_ring_run   replaces __calculate_plane_plane_contacts (interactions.py:1064-1194)
@@ -346,6 +373,10 @@ int  arp_get_stats(arp_ctx* ctx, arp_stats* out);
    mean whole-job time; arp_get_stats then holds the mean grid-build / pair-kernel split. */
 int  arp_timing_iters(arp_ctx* ctx, int iters, int flush_l2, float* ms_per_iter);
 uint64_t arp_launch_count(arp_ctx* ctx);           /* kernels this context has launched so far */
+/* bench hook: `iters` pinned cudaMemcpyAsync of h2d_bytes host -> device and of d2h_bytes device -> host, the two
+   directions concurrently on two streams; ms[0] = CUDA-event time of the H2D copies, ms[1] of the D2H copies.
+   What PCIe gives this GPU for the transfer sizes of one end-to-end step (no kernels involved). */
+int  arp_memcpy_probe(arp_ctx* ctx, uint64_t h2d_bytes, uint64_t d2h_bytes, int iters, float* ms);
 
 #ifdef __cplusplus
 }

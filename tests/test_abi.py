@@ -49,9 +49,13 @@ def test_record_layouts_match_header(tmp_path):
     class AtomPlane(C.Structure):
         _fields_ = [('atom', C.c_int32), ('ring', C.c_int32), ('code', C.c_uint32), ('_pad', C.c_uint32), ('dist', C.c_double)]
 
-    got = _probe(tmp_path, [('arp_pair', Pair), ('arp_plane_pair', PlanePair), ('arp_atom_plane', AtomPlane)])
+    class PairC(C.Structure):
+        _fields_ = [('j', C.c_int32), ('mask', C.c_uint32)]
+
+    got = _probe(tmp_path, [('arp_pair', Pair), ('arp_plane_pair', PlanePair), ('arp_atom_plane', AtomPlane),
+                            ('arp_pair_c', PairC)])
     for cname, cls, dt in (('arp_pair', Pair, abi.PAIR_DTYPE), ('arp_plane_pair', PlanePair, abi.PLANE_PAIR_DTYPE),
-                           ('arp_atom_plane', AtomPlane, abi.ATOM_PLANE_DTYPE)):
+                           ('arp_atom_plane', AtomPlane, abi.ATOM_PLANE_DTYPE), ('arp_pair_c', PairC, abi.PAIR_C_DTYPE)):
         assert got[(cname, 'size')] == dt.itemsize
         for f, _ in cls._fields_:
             assert got[(cname, f)] == dt.fields[f][1], (cname, f)
@@ -116,3 +120,34 @@ def test_default_params_from_c_match_python_thresholds():
             assert list(a) == list(b), f
         else:
             assert a == b, f
+
+
+def test_unpack_compact_records_on_the_host():
+    """arp_pairs_unpack needs no device: rows -> (i, j, mask, dist) records; malformed offsets are refused."""
+    from arpeggio_b200.engine import CompactPairs
+    from arpeggio_b200 import _lib
+    rng = np.random.default_rng(3)
+    n_atoms = 57
+    per_row = rng.integers(0, 6, size=n_atoms)
+    per_row[[0, 13, n_atoms - 1]] = 0                       # empty rows at the ends and in the middle
+    row_off = np.concatenate([[0], np.cumsum(per_row)]).astype(np.uint32)
+    n = int(row_off[-1])
+    rec = np.zeros(n, abi.PAIR_C_DTYPE)
+    rec['j'] = rng.integers(0, n_atoms, size=n)
+    rec['mask'] = rng.integers(0, 1 << 19, size=n)
+    dist = rng.random(n).astype(np.float32)
+    cp = CompactPairs(row_off, rec, dist).view(n_atoms, n, True)
+    out = cp.to_records()
+    assert np.array_equal(out['i'], np.repeat(np.arange(n_atoms), per_row))
+    assert np.array_equal(out['j'], rec['j']) and np.array_equal(out['mask'], rec['mask'])
+    assert np.array_equal(out['dist'].view(np.uint32), dist.view(np.uint32))
+    assert np.all(CompactPairs(row_off, rec, None).view(n_atoms, n, False).to_records()['dist'] == 0)
+    assert cp.nbytes == 4 * (n_atoms + 1) + 12 * n
+    L = _lib.lib()
+    small = np.empty(max(n - 1, 0), abi.PAIR_DTYPE)
+    assert L.arp_pairs_unpack(row_off.ctypes.data, rec.ctypes.data, None, n_atoms, small.ctypes.data, small.shape[0]) == abi.E_CAPACITY
+    bad = row_off.copy()
+    bad[5], bad[6] = bad[6] + 1, bad[5]                     # descending offsets
+    big = np.empty(n + 8, abi.PAIR_DTYPE)
+    assert L.arp_pairs_unpack(bad.ctypes.data, rec.ctypes.data, None, n_atoms, big.ctypes.data, big.shape[0]) == abi.E_INVALID_ARG
+    assert L.arp_pairs_unpack(None, None, None, 0, None, 0) == abi.OK

@@ -54,7 +54,7 @@ def test_product_arm_fails_loudly_without_a_device():
 
 @pytest.mark.gpu
 def test_product_arm_prints_the_contract_line():
-    r = _run('--steps', '5', '--warmup', '3', '--batch-structures', '12', timeout=900)
+    r = _run('--steps', '5', '--warmup', '3', '--batch-structures', '12', '--large-atoms', '150000', timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
     assert len(lines) == 1
@@ -63,10 +63,16 @@ def test_product_arm_prints_the_contract_line():
     assert d['value'] > 1e9 and d['scaling'] == 'weak' and d['data'] == 'synthetic' and d['vs_baseline'] is None
     assert d['gpu_launches'] == d['kernels_per_step'] * d['steps'] and d['kernels_per_step'] >= 3
     e = d['e2e']
-    assert 0 < e['value'] < d['value'] and e['h2d_bytes_per_step'] > 0 and e['d2h_bytes_per_step'] >= 16 * d['config']['pairs_per_structure']
+    # the end-to-end stream is the compact sorted one: 8 bytes per record + 4 per atom (+ 4)
+    assert 0 < e['value'] < d['value'] and e['h2d_bytes_per_step'] > 0 and e['sorted'] is True
+    assert e['d2h_bytes_per_step'] == 8 * d['config']['pairs_per_structure'] + 4 * (d['config']['atoms_per_gpu'] + 1)
+    assert e['records16']['d2h_bytes_per_step'] == 16 * d['config']['pairs_per_structure'] and e['records16']['value'] > 0
+    assert e['pcie']['h2d_gbs'] > 1 and e['pcie']['d2h_gbs'] > 1
     rf = d['roofline']
     assert rf['bound'] == 'hbm' and rf['unit'] == 'GB/s' and abs(rf['frac'] - rf['achieved'] / rf['peak']) < 1e-9
     assert rf['algorithmic_bytes'] > 16 * d['config']['pairs_per_structure']
+    assert abs(rf['kernel_ms'] - d['ms_per_step']) < 1e-12 and rf['pair_kernels']['kernel_ms'] <= rf['kernel_ms'] * 1.2
+    assert rf['large']['atoms'] == 150000 and rf['large']['frac'] > 0
     cb = d['cpu_baseline']
     assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] > 0
     assert 'sm_mhz' in d['clocks'] and 'reasons' in d['clocks']

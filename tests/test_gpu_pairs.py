@@ -340,3 +340,46 @@ def test_errors_are_reported(engine):
             assert ei.value.code == abi.E_CAPACITY
     with pytest.raises(ArpeggioCudaError):
         ContactEngine(device=4096)
+
+
+@pytest.mark.parametrize('n', [0, 1, 40, 3000, 60_000])
+def test_compact_stream_and_async_run(engine, n):
+    """arp_pairs_run_async + arp_pairs_fetch_compact: the compact view (row offsets, (j, mask) records, distances as a
+    stream of their own) unpacks to exactly the sorted 16-byte stream; the fetch is what waits for the run."""
+    p = arp_params.make_params()
+    engine.set_params(p)
+    soa = synth.cloud_featured(max(n, 1), seed=31)
+    if n == 0:
+        soa = AtomSoA(xyz=soa.xyz[:0], feat=soa.feat[:0], res_id=soa.res_id[:0], rad_class=soa.rad_class[:0], vdw=soa.vdw,
+                      cov=soa.cov, res_prev=soa.res_prev, res_next=soa.res_next, res_flags=soa.res_flags)
+    engine.upload_atoms(soa)
+    engine.run_pairs_async()
+    cp = engine.fetch_pairs_compact(with_dist=True)            # waits for the run, sizes its own buffers
+    exp = engine.fetch_pairs(cp.n, sorted=True)
+    assert cp.n == exp.shape[0] == engine.pair_count()
+    assert cp.row_off.shape[0] == soa.n_atoms + 1 and int(cp.row_off[-1]) == cp.n
+    util.assert_records_equal(cp.to_records(), exp, f'compact n={n}')
+    assert np.all(np.diff(cp.row_off.astype(np.int64)) >= 0)
+    # the split stream: records now, distances later
+    engine.run_pairs_async()
+    cp2 = engine.fetch_pairs_compact(with_dist=False)
+    assert cp2.dist is None and cp2.nbytes == 4 * (soa.n_atoms + 1) + 8 * cp2.n
+    d = engine.fetch_pairs_dist(cp2.n)
+    util.assert_records_equal(cp2.to_records(dist=d), exp, f'compact + distances on demand n={n}')
+    if n >= 3000:
+        util.assert_records_equal(exp, oracle.pairs(soa, p), 'against the oracle')
+
+
+def test_capacity_error_reports_the_count(engine):
+    """A destination that is too small fails with ARP_E_CAPACITY, nothing is written, the count comes back."""
+    import ctypes as C
+    engine.set_params(arp_params.make_params())
+    soa = synth.cloud_featured(2000, seed=32)
+    engine.upload_atoms(soa)
+    n = engine.run_pairs()
+    row = np.zeros(soa.n_atoms + 1, np.uint32)
+    rec = np.full(8, 7, dtype=np.int64).view(abi.PAIR_C_DTYPE)
+    got = C.c_uint64()
+    rc = engine._L.arp_pairs_fetch_compact(engine._ctx, row.ctypes.data, rec.ctypes.data, rec.shape[0], None, C.byref(got))
+    assert rc == abi.E_CAPACITY and got.value == n and np.all(rec.view(np.int64) == 7)
+    assert engine.stats()['faults'] == 0

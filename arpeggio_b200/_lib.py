@@ -62,6 +62,7 @@ def lib():
         'arp_amide_amide_fetch': (i32, [vp, vp, u64]),
         'arp_amide_ring_run': (i32, [vp, u64p]),
         'arp_amide_ring_fetch': (i32, [vp, vp, u64]),
+        'arp_planes_run_all': (i32, [vp, u64p]),
         'arp_ring_nearest_atom': (i32, [vp, vp, i32, vp, i32, C.c_double, vp, vp]),
         'arp_atom_sifts_run': (i32, [vp]),
         'arp_atom_sifts_fetch': (i32, [vp, vp, u64]),

@@ -190,7 +190,7 @@ EXPORTED_SYMBOLS = (
     'arp_pairs_run_async', 'arp_pairs_count', 'arp_pairs_fetch_compact', 'arp_pairs_fetch_dist', 'arp_pairs_unpack',
     'arp_upload_planes', 'arp_ring_ring_run', 'arp_ring_ring_fetch', 'arp_atom_ring_run',
     'arp_atom_ring_fetch', 'arp_amide_amide_run', 'arp_amide_amide_fetch', 'arp_amide_ring_run',
-    'arp_amide_ring_fetch', 'arp_atom_sifts_run', 'arp_atom_sifts_fetch', 'arp_ring_nearest_atom', 'arp_pairs_json_size', 'arp_pairs_json_write', 'arp_flag_within', 'arp_sync', 'arp_get_stats', 'arp_timing_iters', 'arp_launch_count', 'arp_memcpy_probe',
+    'arp_amide_ring_fetch', 'arp_planes_run_all', 'arp_atom_sifts_run', 'arp_atom_sifts_fetch', 'arp_ring_nearest_atom', 'arp_pairs_json_size', 'arp_pairs_json_write', 'arp_flag_within', 'arp_sync', 'arp_get_stats', 'arp_timing_iters', 'arp_launch_count', 'arp_memcpy_probe',
 )
 
 

@@ -197,7 +197,7 @@ int arp_create(int device, arp_ctx** out)
         return ARP_E_CUDA;
     }
     memset(c->h_meta, 0, sizeof(RunMeta));
-    if (getenv("ARPEGGIO_NO_PLANE_SCREEN")) c->use_plane_screen = 0; /* A-B knob: unscreened double loops for the plane terms */
+    if (getenv("ARPEGGIO_NO_PLANE_GRID")) c->use_plane_grid = 0;     /* A-B knob: plain double loops for the plane terms */
     if (getenv("ARPEGGIO_NO_PDL")) c->use_pdl = 0;                   /* A-B knob: plain stream-ordered launches */
     if (getenv("ARPEGGIO_NO_FUSED_GRID")) c->use_fused_grid = 0;
     if (getenv("ARPEGGIO_TILES")) c->use_tiles = 1;                                     /* A-B knob: the fused tile kernel instead of k_search + k_classify */

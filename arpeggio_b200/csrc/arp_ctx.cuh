@@ -94,6 +94,8 @@ struct PlaneSet {
 };
 
 struct PlaneResult {
+    const void* ptr = nullptr;   /* the records of the last run (device) */
+    const char* host = nullptr;  /* ... and their pinned host mirror when the run has already copied them */
     DBuf rec;              /* arp_plane_pair / arp_atom_plane records, sorted */
     DBuf tmp;              /* unsorted stream */
     DBuf cnt;              /* record cursor (device) */
@@ -136,7 +138,6 @@ struct arp_ctx {
     int coop_blocks = -1;         /* co-resident blocks of k_grid_fused (0: not available, -1: not probed) */
     int use_fused_grid = 2;       /* 0: five kernels, 1: cooperative kernel through global memory, 2: + register kernel when the atoms fit */
     int reg_blocks = -1;          /* co-resident blocks of k_grid_reg (0: not available, -1: not probed) */
-    int use_plane_screen = 1;     /* plane terms: float32 distance screen + hit bitmask (0: plain double loops) */
     int use_pdl = 1;              /* pair kernels launched with programmatic stream serialization */
     int use_tiles = 0;            /* 1: search + classify as ONE kernel on TMA-staged shared-memory tiles (k_tiles, arp_tiles.cuh;
                                      ARPEGGIO_TILES=1).  Bit-exact, but measured slower than k_search + k_classify (72 vs 58 us at
@@ -169,7 +170,13 @@ struct arp_ctx {
     /* planes */
     PlaneSet rings, amides;
     int have_planes = 0;
+    int planes_finite = 1;        /* every plane centre is finite (checked at upload): the grid path applies */
+    int use_plane_grid = 1;       /* plane terms through cell grids (0: plain double loops, ARPEGGIO_NO_PLANE_GRID) */
     PlaneResult ring_ring, atom_ring, amide_amide, amide_ring;
+    DBuf plane_scratch, plane_tmp, plane_rec;
+    void* h_plane_rec = nullptr;  /* pinned mirror of plane_rec */
+    size_t h_plane_cap = 0;       /* ... in records */
+    int* h_plane_tot = nullptr;   /* pinned: record offsets at the term boundaries */
 
     /* binding-site flags */
     DBuf within;

@@ -16,6 +16,8 @@
  * (BLAS dot/norm model), amide-amide in float32.  arccos is never evaluated: the folded angle
  * |deg| <= 30/60/90 tests compare the cosine with the host-computed images in arp_params.
  */
+#include <math.h>
+
 #include "arp_ctx.cuh"
 
 #define FULL 0xffffffffu
@@ -231,33 +233,6 @@ __global__ void __launch_bounds__(PLANE_WARPS * 32) k_plane_rows(PlaneArgs A, in
     if (!EMIT && lane == 0) row_cnt[row] = cnt;
 }
 
-/* ---- screened variant ------------------------------------------------------------------------------
- * The double loops visit n_rows x n_cols pairs of which a few thousand lie within the 6 A of the centroid /
- * search tests.  k_plane_scan tiles the column points through shared memory as float32 (one tile serves the
- * eight rows of a block) and runs the exact predicate only where a float32 distance screen cannot exclude the
- * pair; the exact hits of a row are kept as a bit per column, so the emitting pass (k_plane_emit) re-evaluates
- * those pairs only.  The screen is conservative: threshold widened by the float32 rounding of the largest
- * coordinate of the row point and of the tile, `!(d2 > T2)` keeps NaN for the exact code to judge.       */
-#define PL_TILE 1024
-
-template <int KIND> __device__ __forceinline__ float4 col_point(const PlaneArgs& A, int col)
-{
-    float x, y, z;
-    bool live = true;
-    if (KIND == KIND_ATOM_RING) {
-        x = A.xyz[3 * (size_t)col]; y = A.xyz[3 * (size_t)col + 1]; z = A.xyz[3 * (size_t)col + 2];
-    } else if (KIND == KIND_AMIDE_AMIDE) {
-        x = A.ac[3 * (size_t)col]; y = A.ac[3 * (size_t)col + 1]; z = A.ac[3 * (size_t)col + 2];
-        live = (A.aflags[col] & ARP_P_IN_SELECTION_PLUS) != 0;
-    } else {
-        x = (float)A.rc[3 * (size_t)col]; y = (float)A.rc[3 * (size_t)col + 1]; z = (float)A.rc[3 * (size_t)col + 2];
-        live = (A.rflags[col] & ARP_P_IN_SELECTION_PLUS) != 0;
-    }
-    const float mag = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
-    if (!live) return make_float4(__int_as_float(0x7f800000), 0.f, 0.f, 0.f);      /* +inf: beyond every threshold */
-    return make_float4(x, y, z, mag);
-}
-
 template <int KIND> __device__ __forceinline__ float4 row_point(const PlaneArgs& A, int row)
 {
     float x, y, z;
@@ -274,104 +249,264 @@ template <int KIND> __device__ __forceinline__ float screen_radius(const PlaneAr
     return (float)(KIND == KIND_RING_RING ? A.ring_centroid : KIND == KIND_ATOM_RING ? A.met_sulphur : A.amide_centroid);
 }
 
-#define PL_ROWS (PLANE_WARPS * 32)          /* rows per block: one per thread */
+/* ---- grid variant ----------------------------------------------------------------------------------
+ * The double loops visit n_rows x n_cols pairs of which a few thousand lie within the 6 A of the centroid /
+ * search tests (interactions.py:960 searches the KD-tree around the centroid; :1113, :1270, :1351 skip on the
+ * centroid distance).  Here the column points of all terms -- atoms (atom-ring), ring centroids (ring-ring,
+ * amide-ring), amide centres (amide-amide) -- are binned into three cell grids of edge >= the largest radius in
+ * ONE launch sequence (bounding box, count, scan, scatter), one warp per row then visits the 27 cells around the
+ * row point (9 contiguous runs of the cell-sorted float32 copies), a conservative float32 screen leaves the exact
+ * predicate of the reference (plane_eval) to the few pairs that can be within the radius, and count -> scan ->
+ * emit keeps the reference's creation order (row, column ascending) for all four terms at once.  O(rows) work.
+ *
+ * Cell coordinates are clamped to the grid, which is monotone: two points within one cell edge of each other land
+ * in cells that differ by at most one per axis whatever the grid's origin and size, so one bounding box (of all
+ * points) serves all three grids and a point outside it is still found.  The screen keeps NaN distances
+ * (`!(d2 > T2)`); non-finite plane centres, whose pairs the reference does NOT skip, are detected at upload and
+ * take the plain double loops (k_plane_rows).                                                                  */
+#define PLG_SETS 3                       /* 0 atoms, 1 ring centroids, 2 amide centres */
+#define PLG_TERMS 4
 
-template <int KIND>
-__global__ void __launch_bounds__(PL_ROWS) k_plane_scan(PlaneArgs A, int n_rows, int n_cols, int words,
-                                                       int* __restrict__ row_cnt, uint32_t* __restrict__ mask)
+struct PlaneGrid {
+    double ox, oy, oz, inv_w;
+    int dx, dy, dz, ncell;
+    int cell_base;                       /* first global cell id of the set */
+    int n;                               /* points of the set */
+    int pt_base;                         /* first global point id of the set */
+    int pad;
+};
+
+struct PlaneGridArgs {
+    PlaneArgs A;
+    int term_mask;                       /* bit t: term t runs (KIND_* order) */
+    double edge;                         /* cell edge before widening: >= every radius */
+    unsigned* bbox;                      /* [6] ordered-int min (as max of ~ord) and max */
+    PlaneGrid* grids;                    /* [PLG_SETS] */
+    unsigned* n_cells;                   /* cells of the three grids together */
+    int* cell_cnt;                       /* [total cells + 1] */
+    int* cell_start;
+    int* cell_of; int* rank;             /* per point */
+    float4* spos;                        /* cell-sorted points: x, y, z (float32), index in its set */
+    int* row_cnt; int* row_off;          /* rows of the four terms, concatenated */
+    int row_base[PLG_TERMS + 1];
+    PlaneRec* tmp;                       /* records in discovery order (all terms, positions = row_off) */
+    unsigned long long tmp_cap;
+    PlaneRec* rec[PLG_TERMS];            /* per term: records in (row, column) order */
+    unsigned long long cap[PLG_TERMS];
+};
+
+__device__ __forceinline__ unsigned pl_f2ord(float f)
 {
-    /* thread = row (its point in registers), the column points of a tile are broadcast from shared memory:
-       one conflict-free LDS serves 32 rows, and the 32 screen bits a thread collects for 32 consecutive columns
-       are exactly its row's word of the hit bitmask -- no ballots.  blockIdx.y splits the columns so that every
-       SM has work when the rows are few (atom-ring). */
-    __shared__ float4 s_col[PL_TILE];
-    __shared__ float s_mag[PLANE_WARPS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int row = blockIdx.x * PL_ROWS + threadIdx.x;
-    const bool live = row < n_rows && row_live<KIND>(A, row);
-    float4 rp = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) rp = row_point<KIND>(A, row);
-    const float r = screen_radius<KIND>(A);
-    int cnt = 0;
-    const int tiles = (n_cols + PL_TILE - 1) / PL_TILE;
-    const int t_lo = (int)((long long)tiles * blockIdx.y / gridDim.y), t_hi = (int)((long long)tiles * (blockIdx.y + 1) / gridDim.y);
-    for (int c0 = t_lo * PL_TILE; c0 < t_hi * PL_TILE && c0 < n_cols; c0 += PL_TILE) {
-        const int m = min(PL_TILE, n_cols - c0);
-        __syncthreads();                                   /* the previous tile has been consumed */
-        float mag = 0.f;
-        for (int k = threadIdx.x; k < PL_TILE; k += PL_ROWS) {
-            float4 q = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, 0.f);
-            if (k < m) q = col_point<KIND>(A, c0 + k);
-            s_col[k] = q;
-            mag = q.w == q.w ? fmaxf(mag, q.w) : q.w;      /* a NaN coordinate poisons the tile: nothing is screened out */
-        }
-        {   /* warp maximum; non-negative floats order like their bit patterns */
-            const bool nan = __any_sync(FULL, mag != mag);
-            mag = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(mag == mag ? mag : 0.f)));
-            if (nan) mag = __int_as_float(0x7fc00000);
-        }
-        if (lane == 0) s_mag[warp] = mag;
-        __syncthreads();
-        float tile_mag = 0.f;
-#pragma unroll
-        for (int w = 0; w < PLANE_WARPS; ++w) tile_mag = s_mag[w] == s_mag[w] ? fmaxf(tile_mag, s_mag[w]) : s_mag[w];
-        const float T = r * 1.000004f + 1e-6f + 4e-7f * (rp.w + tile_mag);
-        const float T2 = T * T;
-#pragma unroll 1
-        for (int g = 0; g < PL_TILE / 32 && c0 + 32 * g < n_cols; ++g) {
-            uint32_t w = 0;                                /* bit b: column c0 + 32 g + b survives the screen */
-#pragma unroll
-            for (int b = 0; b < 32; ++b) {
-                const float4 q = s_col[g * 32 + b];
-                const float dx = rp.x - q.x, dy = rp.y - q.y, dz = rp.z - q.z;
-                const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-                if (!(d2 > T2)) w |= 1u << b;
-            }
-            if (live && w) {                               /* rare: the exact predicate decides */
-                uint32_t hits = 0;
-                while (w) {
-                    const int b = __ffs(w) - 1;
-                    w &= w - 1;
-                    const int col = c0 + g * 32 + b;
-                    PlaneRec rec;
-                    if (col < n_cols && plane_eval<KIND>(A, row, col, &rec)) hits |= 1u << b;
-                }
-                if (hits) {
-                    mask[(size_t)row * words + (c0 >> 5) + g] = hits;
-                    cnt += __popc(hits);
-                }
-            }
-        }
-    }
-    if (cnt) atomicAdd(&row_cnt[row], cnt);                /* row_cnt is zeroed by the caller */
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float pl_ord2f(unsigned u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(PLANE_WARPS * 32) k_plane_emit(PlaneArgs A, int n_rows, int words,
-                                                                 const int* __restrict__ row_off, const uint32_t* __restrict__ mask,
-                                                                 PlaneRec* __restrict__ rec)
+/* point p of the concatenated sets -> (set, index, float32 coordinates, binned?) */
+__device__ __forceinline__ bool pl_point(const PlaneArgs& A, int n_atoms, int p, int* set, int* idx, float* x, float* y, float* z)
 {
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * PLANE_WARPS + (threadIdx.x >> 5);
-    if (row >= n_rows) return;
-    const int base = row_off[row], n = row_off[row + 1] - base;
-    const unsigned lt = (1u << lane) - 1u;
-    int cnt = 0;
-    for (int w0 = 0; w0 < words && cnt < n; w0 += 32) {
-        const uint32_t wv = w0 + lane < words ? mask[(size_t)row * words + w0 + lane] : 0u;
-        unsigned nz = __ballot_sync(FULL, wv != 0u);
-        while (nz) {
-            const int j = __ffs(nz) - 1;
-            nz &= nz - 1;
-            const uint32_t word = __shfl_sync(FULL, wv, j);
-            if (word >> lane & 1u) {
-                PlaneRec r;
-                plane_eval<KIND>(A, row, (w0 + j) * 32 + lane, &r);
-                rec[base + cnt + __popc(word & lt)] = r;
-            }
-            cnt += __popc(word);
+    if (p < n_atoms) {
+        *set = 0; *idx = p;
+        *x = A.xyz[3 * (size_t)p]; *y = A.xyz[3 * (size_t)p + 1]; *z = A.xyz[3 * (size_t)p + 2];
+        return !(A.feat[p] & ARP_F_ELEM_H);                                           /* interactions.py:964 */
+    }
+    p -= n_atoms;
+    if (p < A.nr) {
+        *set = 1; *idx = p;
+        *x = (float)A.rc[3 * (size_t)p]; *y = (float)A.rc[3 * (size_t)p + 1]; *z = (float)A.rc[3 * (size_t)p + 2];
+        return (A.rflags[p] & ARP_P_IN_SELECTION_PLUS) != 0;                          /* :1085, :1318 */
+    }
+    p -= A.nr;
+    *set = 2; *idx = p;
+    *x = A.ac[3 * (size_t)p]; *y = A.ac[3 * (size_t)p + 1]; *z = A.ac[3 * (size_t)p + 2];
+    return (A.aflags[p] & ARP_P_IN_SELECTION_PLUS) != 0;                              /* :1237 */
+}
+
+__global__ void __launch_bounds__(256) k_pl_bbox(PlaneGridArgs G, int n_atoms, int n_points)
+{
+    unsigned v[6] = {0, 0, 0, 0, 0, 0};
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_points; p += gridDim.x * blockDim.x) {
+        int set, idx; float x, y, z;
+        pl_point(G.A, n_atoms, p, &set, &idx, &x, &y, &z);
+        if (x == x && y == y && z == z && fabsf(x) < 3e38f && fabsf(y) < 3e38f && fabsf(z) < 3e38f) {   /* finite points only */
+            const unsigned ox = pl_f2ord(x), oy = pl_f2ord(y), oz = pl_f2ord(z);
+            v[0] = max(v[0], ~ox); v[1] = max(v[1], ~oy); v[2] = max(v[2], ~oz);
+            v[3] = max(v[3], ox); v[4] = max(v[4], oy); v[5] = max(v[5], oz);
         }
     }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        v[k] = __reduce_max_sync(FULL, v[k]);
+        if ((threadIdx.x & 31) == 0 && v[k]) atomicMax(&G.bbox[k], v[k]);
+    }
+}
+
+__device__ __forceinline__ int pl_cell_coord(double v, double o, double inv_w, int dim)
+{
+    double t = floor((v - o) * inv_w);
+    t = fmin(fmax(t, 0.0), (double)(dim - 1));         /* clamped (monotone); NaN -> 0 */
+    return (int)t;
+}
+__device__ __forceinline__ int pl_cell(const PlaneGrid& g, float x, float y, float z, int* cx, int* cy, int* cz)
+{
+    *cx = pl_cell_coord((double)x, g.ox, g.inv_w, g.dx);
+    *cy = pl_cell_coord((double)y, g.oy, g.inv_w, g.dy);
+    *cz = pl_cell_coord((double)z, g.oz, g.inv_w, g.dz);
+    return (*cz * g.dy + *cy) * g.dx + *cx;
+}
+
+/* every block derives the three grids from the bounding box itself; block 0 publishes them */
+__device__ __forceinline__ void pl_make_grids(const PlaneGridArgs& G, int n_atoms, PlaneGrid* out)
+{
+    double mn[3], mx[3];
+    bool any = false;
+    for (int k = 0; k < 3; ++k) {
+        const unsigned lo = G.bbox[k], hi = G.bbox[3 + k];
+        any = any || hi != 0u;
+        mn[k] = hi ? (double)pl_ord2f(~lo) : 0.0;
+        mx[k] = hi ? (double)pl_ord2f(hi) : 0.0;
+    }
+    (void)any;
+    double amax = 0.0;
+    for (int k = 0; k < 3; ++k) amax = fmax(amax, fmax(fabs(mn[k]), fabs(mx[k])));
+    const double edge = G.edge + 5e-7 * amax;          /* the points are binned by their float32 images */
+    const int n_set[PLG_SETS] = { n_atoms, G.A.nr, G.A.na };
+    int cell_base = 0, pt_base = 0;
+    for (int s = 0; s < PLG_SETS; ++s) {
+        PlaneGrid g;
+        double w = edge;
+        long long d[3];
+        for (;;) {
+            for (int k = 0; k < 3; ++k) d[k] = (long long)floor((mx[k] - mn[k]) / w) + 1;
+            if ((double)d[0] * (double)d[1] * (double)d[2] <= 4.0 * (double)n_set[s] + 64.0) break;   /* the host sizes the tables on this bound */
+            w *= 1.5;
+        }
+        g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2]; g.inv_w = 1.0 / w;
+        g.dx = (int)d[0]; g.dy = (int)d[1]; g.dz = (int)d[2]; g.ncell = g.dx * g.dy * g.dz;
+        g.cell_base = cell_base; g.n = n_set[s]; g.pt_base = pt_base; g.pad = 0;
+        cell_base += g.ncell; pt_base += n_set[s];
+        out[s] = g;
+    }
+}
+/* total number of cells of the three grids (block 0 of k_pl_count leaves it for the scan) */
+
+__global__ void __launch_bounds__(256) k_pl_count(PlaneGridArgs G, int n_atoms, int n_points)
+{
+    __shared__ PlaneGrid s_g[PLG_SETS];
+    if (threadIdx.x == 0) {
+        pl_make_grids(G, n_atoms, s_g);
+        if (blockIdx.x == 0) {
+            for (int s = 0; s < PLG_SETS; ++s) G.grids[s] = s_g[s];
+            *G.n_cells = (unsigned)(s_g[PLG_SETS - 1].cell_base + s_g[PLG_SETS - 1].ncell);
+        }
+    }
+    __syncthreads();
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_points; p += gridDim.x * blockDim.x) {
+        int set, idx, cx, cy, cz; float x, y, z;
+        int c = -1, r = 0;
+        if (pl_point(G.A, n_atoms, p, &set, &idx, &x, &y, &z)) {
+            c = s_g[set].cell_base + pl_cell(s_g[set], x, y, z, &cx, &cy, &cz);
+            r = atomicAdd(&G.cell_cnt[c], 1);
+        }
+        G.cell_of[p] = c; G.rank[p] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pl_scatter(PlaneGridArgs G, int n_atoms, int n_points)
+{
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_points; p += gridDim.x * blockDim.x) {
+        const int c = G.cell_of[p];
+        if (c < 0) continue;
+        int set, idx; float x, y, z;
+        pl_point(G.A, n_atoms, p, &set, &idx, &x, &y, &z);
+        G.spos[G.cell_start[c] + G.rank[p]] = make_float4(x, y, z, __int_as_float(idx));
+    }
+}
+
+template <int KIND> __device__ __forceinline__ int pl_col_set() { return KIND == KIND_ATOM_RING ? 0 : KIND == KIND_AMIDE_AMIDE ? 2 : 1; }
+
+/* one warp, one row of term KIND: the 27 cells around the row point as 9 runs; EMIT: records in discovery order to
+   tmp, then by ascending column into rec */
+template <int KIND, bool EMIT>
+__device__ __forceinline__ void pl_row(const PlaneGridArgs& G, const PlaneGrid& g, int row, int grow, int lane)
+{
+    const PlaneArgs& A = G.A;
+    int cnt = 0;
+    const int base = EMIT ? G.row_off[grow] : 0;
+    const int tbase = EMIT ? G.row_off[G.row_base[KIND]] : 0;      /* first record of the term */
+    if (row_live<KIND>(A, row)) {
+        const float4 rp = row_point<KIND>(A, row);
+        const float r = screen_radius<KIND>(A);
+        const float t0 = r * 1.000004f + 1e-6f;
+        int cx, cy, cz;
+        pl_cell(g, rp.x, rp.y, rp.z, &cx, &cy, &cz);
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
+        const unsigned lt = (1u << lane) - 1u;
+        for (int k = 0; k < 9; ++k) {
+            const int y = cy + k % 3 - 1, z = cz + k / 3 - 1;
+            if (y < 0 || y >= g.dy || z < 0 || z >= g.dz) continue;      /* warp-uniform */
+            const int rowc = g.cell_base + (z * g.dy + y) * g.dx;
+            const int b = G.cell_start[rowc + x0], e = G.cell_start[rowc + x1 + 1];
+            for (int q0 = b; q0 < e; q0 += 32) {
+                const int q = q0 + lane;
+                bool hit = false;
+                PlaneRec rec;
+                if (q < e) {
+                    const float4 cp = G.spos[q];
+                    const float dx = rp.x - cp.x, dy = rp.y - cp.y, dz = rp.z - cp.z;
+                    const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                    const float T = t0 + 4e-7f * (rp.w + fmaxf(fabsf(cp.x), fmaxf(fabsf(cp.y), fabsf(cp.z))));
+                    if (!(d2 > T * T)) hit = plane_eval<KIND>(A, row, __float_as_int(cp.w), &rec);    /* rare: the exact predicate decides */
+                }
+                const unsigned m = __ballot_sync(FULL, hit);
+                if (EMIT && hit) {
+                    const unsigned long long pos = (unsigned long long)base + cnt + __popc(m & lt);
+                    if (pos < G.tmp_cap) G.tmp[pos] = rec;
+                }
+                cnt += __popc(m);
+            }
+        }
+    }
+    if (!EMIT) {
+        if (lane == 0) G.row_cnt[grow] = cnt;
+        return;
+    }
+    if (cnt == 0 || (unsigned long long)base + cnt > G.tmp_cap || (unsigned long long)(base - tbase) + cnt > G.cap[KIND]) return;
+    __syncwarp();
+    /* column order inside the row: the rank of a record is the number of the row's records with a smaller column.
+       The column is field b, except for atom-ring records (atom, ring), where it is field a. */
+    for (int h = lane; h < cnt; h += 32) {
+        const PlaneRec mine = G.tmp[base + h];
+        const int key = KIND == KIND_ATOM_RING ? mine.a : mine.b;
+        int rk = 0;
+        for (int k = 0; k < cnt; ++k) {
+            const PlaneRec& o = G.tmp[base + k];
+            rk += (KIND == KIND_ATOM_RING ? o.a : o.b) < key ? 1 : 0;
+        }
+        G.rec[KIND][base - tbase + rk] = mine;
+    }
+}
+
+/* the record offsets at the term boundaries, contiguous for one small copy */
+__global__ void k_pl_totals(PlaneGridArgs G, int* __restrict__ tot)
+{
+    if (threadIdx.x <= PLG_TERMS) tot[threadIdx.x] = G.row_off[G.row_base[threadIdx.x]];
+}
+
+#define PLG_WARPS 8
+template <bool EMIT>
+__global__ void __launch_bounds__(PLG_WARPS * 32) k_pl_pass(PlaneGridArgs G)
+{
+    const int lane = threadIdx.x & 31;
+    const int grow = blockIdx.x * PLG_WARPS + (threadIdx.x >> 5);
+    if (grow >= G.row_base[PLG_TERMS]) return;
+    if (grow < G.row_base[1])      pl_row<KIND_RING_RING, EMIT>(G, G.grids[pl_col_set<KIND_RING_RING>()], grow - G.row_base[0], grow, lane);
+    else if (grow < G.row_base[2]) pl_row<KIND_ATOM_RING, EMIT>(G, G.grids[pl_col_set<KIND_ATOM_RING>()], grow - G.row_base[1], grow, lane);
+    else if (grow < G.row_base[3]) pl_row<KIND_AMIDE_AMIDE, EMIT>(G, G.grids[pl_col_set<KIND_AMIDE_AMIDE>()], grow - G.row_base[2], grow, lane);
+    else                           pl_row<KIND_AMIDE_RING, EMIT>(G, G.grids[pl_col_set<KIND_AMIDE_RING>()], grow - G.row_base[3], grow, lane);
 }
 
 /* ---- host side ------------------------------------------------------------------------------- */
@@ -416,9 +551,10 @@ static void plane_args(arp_ctx* c, PlaneArgs* A)
     }
 }
 
-template <int KIND> static int plane_run(arp_ctx* c, PlaneResult& R, int n_rows, int n_cols, uint64_t* n_out)
+/* the plain double loop of one term: fallback for non-finite plane centres, and the A/B knob ARPEGGIO_NO_PLANE_GRID */
+template <int KIND> static int plane_run_rows(arp_ctx* c, PlaneResult& R, int n_rows, int n_cols)
 {
-    R.valid = 0; R.n = 0;
+    R.valid = 0; R.n = 0; R.ptr = nullptr; R.host = nullptr;
     if (n_rows > 0 && n_cols > 0) {
         PlaneArgs A; plane_args(c, &A);
         /* zero region: row_cnt[n_rows + 1] | ticket | scan state ; then row_off */
@@ -434,22 +570,7 @@ template <int KIND> static int plane_run(arp_ctx* c, PlaneResult& R, int n_rows,
         int* row_off = (int*)(z + o_off);
         ARP_CUDA(c, cudaMemsetAsync(z, 0, o_off, c->stream));
         unsigned blocks = (unsigned)((n_rows + PLANE_WARPS - 1) / PLANE_WARPS);
-        /* one bit per (row, column) for the exact hits, if that fits: the emitting pass then touches only those */
-        const int words = (n_cols + 31) / 32;
-        const size_t mask_bytes = (size_t)n_rows * (size_t)words * 4;
-        const bool screened = c->use_plane_screen && mask_bytes <= ((size_t)1 << 30);
-        if (screened) {
-            ARP_TRY(dbuf_reserve(c, R.tmp, mask_bytes));
-            ARP_CUDA(c, cudaMemsetAsync(R.tmp.p, 0, mask_bytes, c->stream));
-            const unsigned tiles = (unsigned)((n_cols + PL_TILE - 1) / PL_TILE);
-            const unsigned row_blocks = (unsigned)((n_rows + PL_ROWS - 1) / PL_ROWS);
-            unsigned splits = ((unsigned)c->sm_count * 6 + row_blocks - 1) / row_blocks;
-            splits = splits < 1 ? 1 : splits > tiles ? tiles : splits;
-            k_plane_scan<KIND><<<dim3(row_blocks, splits), PL_ROWS, 0, c->stream>>>(A, n_rows, n_cols, words, row_cnt,
-                                                                                   R.tmp.as<uint32_t>());
-        } else {
-            k_plane_rows<KIND, false><<<blocks, PLANE_WARPS * 32, 0, c->stream>>>(A, n_rows, n_cols, row_cnt, nullptr, nullptr);
-        }
+        k_plane_rows<KIND, false><<<blocks, PLANE_WARPS * 32, 0, c->stream>>>(A, n_rows, n_cols, row_cnt, nullptr, nullptr);
         ARP_LAUNCHED(c);
         ARP_TRY(arp_scan_exclusive(c, row_cnt, row_off, state, ticket, nullptr, n_rows + 1, (size_t)n_rows + 1));
         int total = 0;
@@ -457,19 +578,132 @@ template <int KIND> static int plane_run(arp_ctx* c, PlaneResult& R, int n_rows,
         ARP_CUDA(c, cudaStreamSynchronize(c->stream));
         if (total > 0) {
             ARP_TRY(dbuf_reserve(c, R.rec, (size_t)total * sizeof(PlaneRec)));
-            if (screened)
-                k_plane_emit<KIND><<<blocks, PLANE_WARPS * 32, 0, c->stream>>>(A, n_rows, words, row_off, R.tmp.as<uint32_t>(),
-                                                                               R.rec.as<PlaneRec>());
-            else
-                k_plane_rows<KIND, true><<<blocks, PLANE_WARPS * 32, 0, c->stream>>>(A, n_rows, n_cols, nullptr, row_off,
-                                                                                     R.rec.as<PlaneRec>());
+            k_plane_rows<KIND, true><<<blocks, PLANE_WARPS * 32, 0, c->stream>>>(A, n_rows, n_cols, nullptr, row_off, R.rec.as<PlaneRec>());
             ARP_LAUNCHED(c);
-            ARP_CUDA(c, cudaStreamSynchronize(c->stream));
         }
         R.n = (uint64_t)total;
+        R.ptr = R.rec.p;
     }
     R.valid = 1;
-    if (n_out) *n_out = R.n;
+    return ARP_OK;
+}
+
+static PlaneResult& plane_result(arp_ctx* c, int term)
+{
+    return term == KIND_RING_RING ? c->ring_ring : term == KIND_ATOM_RING ? c->atom_ring : term == KIND_AMIDE_AMIDE ? c->amide_amide : c->amide_ring;
+}
+
+/* The terms of `mask` through the cell grids: ONE launch sequence for all of them (bounding box, count, scan,
+   scatter, counting pass, scan, emitting pass) and one wait, for the record totals. */
+static int planes_run_grid(arp_ctx* c, int mask)
+{
+    PlaneGridArgs G;
+    memset(&G, 0, sizeof G);
+    plane_args(c, &G.A);
+    const int nr = c->rings.n, na = c->amides.n;
+    const int n_atoms = (mask & (1 << KIND_ATOM_RING)) ? c->N : 0;      /* the atoms are binned only for atom-ring */
+    const int rows_t[PLG_TERMS] = { (mask & 1) ? nr : 0, (mask & 2) ? nr : 0, (mask & 4) ? na : 0, (mask & 8) ? na : 0 };
+    G.row_base[0] = 0;
+    for (int t = 0; t < PLG_TERMS; ++t) G.row_base[t + 1] = G.row_base[t] + rows_t[t];
+    const int rows = G.row_base[PLG_TERMS];
+    for (int t = 0; t < PLG_TERMS; ++t) if (mask & (1 << t)) { PlaneResult& R = plane_result(c, t); R.valid = 0; R.n = 0; R.ptr = nullptr; R.host = nullptr; }
+    if (rows == 0) {
+        for (int t = 0; t < PLG_TERMS; ++t) if (mask & (1 << t)) plane_result(c, t).valid = 1;
+        return ARP_OK;
+    }
+    G.term_mask = mask;
+    const arp_params& p = c->params;
+    double r = p.ring_centroid_dist > p.amide_centroid_dist ? p.ring_centroid_dist : p.amide_centroid_dist;
+    r = p.met_sulphur_dist > r ? p.met_sulphur_dist : r;
+    G.edge = r > 1e-3 ? r * (1.0 + 1e-5) + 1e-5 : 1e-3;
+    const size_t P = (size_t)n_atoms + nr + na;
+    const size_t cells = 4 * P + 64 * PLG_SETS + 2;
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    /* zero region: bbox | n_cells | cell_cnt | scan tickets and states | row_cnt */
+    const size_t tiles_c = (cells + ARP_SCAN_TILE - 1) / ARP_SCAN_TILE + 1, tiles_r = ((size_t)rows + 1 + ARP_SCAN_TILE - 1) / ARP_SCAN_TILE + 1;
+    const size_t o_cnt = 256, o_tick = up(o_cnt + cells * 4), o_state_c = o_tick + 256, o_state_r = up(o_state_c + tiles_c * 8);
+    const size_t o_rcnt = up(o_state_r + tiles_r * 8), zero_bytes = up(o_rcnt + ((size_t)rows + 2) * 4);
+    /* scratch: grids | cell_start | cell_of | rank | spos | row_off */
+    const size_t o_start = up(zero_bytes + sizeof(PlaneGrid) * PLG_SETS), o_cellof = up(o_start + cells * 4), o_rank = up(o_cellof + P * 4);
+    const size_t o_spos = up(o_rank + P * 4), o_roff = up(o_spos + P * 16), bytes = up(o_roff + ((size_t)rows + 2) * 4);
+    ARP_TRY(dbuf_reserve(c, c->plane_scratch, bytes));
+    char* z = c->plane_scratch.as<char>();
+    G.bbox = (unsigned*)z; G.n_cells = (unsigned*)(z + 64); G.cell_cnt = (int*)(z + o_cnt);
+    unsigned* tick_c = (unsigned*)(z + o_tick); unsigned* tick_r = (unsigned*)(z + o_tick + 128);
+    unsigned long long* state_c = (unsigned long long*)(z + o_state_c); unsigned long long* state_r = (unsigned long long*)(z + o_state_r);
+    G.row_cnt = (int*)(z + o_rcnt);
+    G.grids = (PlaneGrid*)(z + zero_bytes); G.cell_start = (int*)(z + o_start); G.cell_of = (int*)(z + o_cellof);
+    G.rank = (int*)(z + o_rank); G.spos = (float4*)(z + o_spos); G.row_off = (int*)(z + o_roff);
+    cudaStream_t st = c->stream;
+    ARP_CUDA(c, cudaMemsetAsync(z, 0, zero_bytes, st));
+    const unsigned pb = (unsigned)((P + 255) / 256 < (size_t)c->sm_count * 8 ? (P + 255) / 256 : (size_t)c->sm_count * 8);
+    k_pl_bbox<<<pb ? pb : 1, 256, 0, st>>>(G, n_atoms, (int)P);
+    ARP_LAUNCHED(c);
+    k_pl_count<<<pb ? pb : 1, 256, 0, st>>>(G, n_atoms, (int)P);
+    ARP_LAUNCHED(c);
+    ARP_TRY(arp_scan_exclusive(c, G.cell_cnt, G.cell_start, state_c, tick_c, G.n_cells, 1, cells));
+    k_pl_scatter<<<pb ? pb : 1, 256, 0, st>>>(G, n_atoms, (int)P);
+    ARP_LAUNCHED(c);
+    const unsigned rb = (unsigned)((rows + PLG_WARPS - 1) / PLG_WARPS);
+    k_pl_pass<false><<<rb, PLG_WARPS * 32, 0, st>>>(G);
+    ARP_LAUNCHED(c);
+    ARP_TRY(arp_scan_exclusive(c, G.row_cnt, G.row_off, state_r, tick_r, nullptr, rows + 1, (size_t)rows + 1));
+    int* h_tot = c->h_plane_tot;                    /* pinned: the record offsets at the term boundaries */
+    int* d_tot = (int*)(z + 128);                   /* inside the zero region, behind the bounding box and the cell total */
+    k_pl_totals<<<1, 32, 0, st>>>(G, d_tot);
+    ARP_LAUNCHED(c);
+    ARP_CUDA(c, cudaMemcpyAsync(h_tot, d_tot, (PLG_TERMS + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ARP_CUDA(c, cudaStreamSynchronize(st));
+    const int total = h_tot[PLG_TERMS];
+    /* every run of this path leaves its records in ONE buffer (term t at offset h_tot[t]) and, with one copy, in a pinned
+       host mirror: the fetch calls then cost no CUDA call.  Results of earlier plane runs are no longer valid. */
+    for (PlaneResult* R : { &c->ring_ring, &c->atom_ring, &c->amide_amide, &c->amide_ring }) { R->valid = 0; R->host = nullptr; }
+    if (total > 0) {
+        ARP_TRY(dbuf_reserve(c, c->plane_tmp, (size_t)total * sizeof(PlaneRec)));
+        ARP_TRY(dbuf_reserve(c, c->plane_rec, (size_t)total * sizeof(PlaneRec)));
+        if (c->h_plane_cap < (size_t)total) {
+            if (c->h_plane_rec) cudaFreeHost(c->h_plane_rec);
+            c->h_plane_rec = nullptr; c->h_plane_cap = 0;
+            const size_t want = (size_t)total + (size_t)total / 4 + 1024;
+            ARP_CUDA(c, cudaMallocHost(&c->h_plane_rec, want * sizeof(PlaneRec)));
+            c->h_plane_cap = want;
+        }
+        G.tmp = c->plane_tmp.as<PlaneRec>(); G.tmp_cap = (unsigned long long)total;
+        for (int t = 0; t < PLG_TERMS; ++t) {
+            G.rec[t] = c->plane_rec.as<PlaneRec>() + h_tot[t]; G.cap[t] = (unsigned long long)(h_tot[t + 1] - h_tot[t]);
+        }
+        k_pl_pass<true><<<rb, PLG_WARPS * 32, 0, st>>>(G);
+        ARP_LAUNCHED(c);
+        ARP_CUDA(c, cudaMemcpyAsync(c->h_plane_rec, c->plane_rec.p, (size_t)total * sizeof(PlaneRec), cudaMemcpyDeviceToHost, st));
+        ARP_CUDA(c, cudaStreamSynchronize(st));
+    }
+    for (int t = 0; t < PLG_TERMS; ++t) if (mask & (1 << t)) {
+        PlaneResult& R = plane_result(c, t);
+        R.n = (uint64_t)(h_tot[t + 1] - h_tot[t]);
+        R.ptr = c->plane_rec.as<PlaneRec>() + h_tot[t];
+        R.host = R.n ? (const char*)c->h_plane_rec + (size_t)h_tot[t] * sizeof(PlaneRec) : nullptr;
+        R.valid = 1;
+    }
+    return ARP_OK;
+}
+
+/* runs the terms of `mask`; n_out[t] (may be null) receives the record counts */
+static int planes_run(arp_ctx* c, int mask, uint64_t* n_out)
+{
+    const bool need_atoms = (mask & (1 << KIND_ATOM_RING)) != 0;
+    if (need_atoms) {
+        ARP_REQUIRE(c, c->have_atoms, ARP_E_NOT_READY, "arp_atom_ring_run before arp_upload_atoms");
+        ARP_REQUIRE(c, c->S == 1, ARP_E_INVALID_ARG, "plane terms need a single structure");
+    }
+    if (c->use_plane_grid && c->planes_finite) {
+        ARP_TRY(planes_run_grid(c, mask));
+    } else {
+        if (mask & 1) ARP_TRY(plane_run_rows<KIND_RING_RING>(c, c->ring_ring, c->rings.n, c->rings.n));
+        if (mask & 2) ARP_TRY(plane_run_rows<KIND_ATOM_RING>(c, c->atom_ring, c->rings.n, c->N));
+        if (mask & 4) ARP_TRY(plane_run_rows<KIND_AMIDE_AMIDE>(c, c->amide_amide, c->amides.n, c->amides.n));
+        if (mask & 8) ARP_TRY(plane_run_rows<KIND_AMIDE_RING>(c, c->amide_ring, c->amides.n, c->rings.n));
+    }
+    if (n_out) for (int t = 0; t < PLG_TERMS; ++t) if (mask & (1 << t)) n_out[t] = plane_result(c, t).n;
     return ARP_OK;
 }
 
@@ -479,8 +713,12 @@ static int plane_fetch(arp_ctx* c, PlaneResult& R, void* dst, uint64_t cap)
     ARP_REQUIRE(c, cap >= R.n, ARP_E_CAPACITY, "destination holds fewer records than the run produced");
     if (R.n == 0) return ARP_OK;
     ARP_REQUIRE(c, dst != nullptr, ARP_E_INVALID_ARG, "dst is NULL");
+    if (R.host) {                       /* the run has already brought the records to the host */
+        memcpy(dst, R.host, (size_t)R.n * sizeof(PlaneRec));
+        return ARP_OK;
+    }
     ARP_TRY(arp_bind(c));
-    ARP_CUDA(c, cudaMemcpyAsync(dst, R.rec.p, (size_t)R.n * sizeof(PlaneRec), cudaMemcpyDeviceToHost, c->stream));
+    ARP_CUDA(c, cudaMemcpyAsync(dst, R.ptr, (size_t)R.n * sizeof(PlaneRec), cudaMemcpyDeviceToHost, c->stream));
     ARP_CUDA(c, cudaStreamSynchronize(c->stream));
     return ARP_OK;
 }
@@ -493,6 +731,9 @@ void arp_planes_release(arp_ctx* c)
     for (PlaneResult* r : { &c->ring_ring, &c->atom_ring, &c->amide_amide, &c->amide_ring }) {
         dbuf_free(r->rec); dbuf_free(r->tmp); dbuf_free(r->cnt);
     }
+    dbuf_free(c->plane_scratch); dbuf_free(c->plane_tmp); dbuf_free(c->plane_rec);
+    if (c->h_plane_tot) { cudaFreeHost(c->h_plane_tot); c->h_plane_tot = nullptr; }
+    if (c->h_plane_rec) { cudaFreeHost(c->h_plane_rec); c->h_plane_rec = nullptr; c->h_plane_cap = 0; }
 }
 
 extern "C" {
@@ -507,16 +748,36 @@ int arp_upload_planes(arp_ctx* c, const arp_planes* rings, const arp_planes* ami
     c->ring_ring.valid = c->atom_ring.valid = c->amide_amide.valid = c->amide_ring.valid = 0;
     ARP_TRY(plane_upload(c, c->rings, rings));
     ARP_TRY(plane_upload(c, c->amides, amides));
+    /* a non-finite centre makes the reference's `distance > threshold: continue` tests false, i.e. it pairs that plane
+       with every other one: such inputs take the plain double loops */
+    c->planes_finite = 1;
+    if (rings && rings->n > 0) {
+        const double* p = (const double*)rings->center;
+        for (size_t k = 0; k < (size_t)rings->n * 3; ++k) if (!(fabs(p[k]) <= 1.7e308)) { c->planes_finite = 0; break; }
+    }
+    if (amides && amides->n > 0) {
+        const float* p = (const float*)amides->center;
+        for (size_t k = 0; k < (size_t)amides->n * 3; ++k) if (!(fabsf(p[k]) <= 3.4e38f)) { c->planes_finite = 0; break; }
+    }
     c->have_planes = 1;
     return ARP_OK;
 }
 
-int arp_ring_ring_run(arp_ctx* c, uint64_t* n)
+static int planes_entry(arp_ctx* c, int mask, uint64_t* n_out, const char* what)
 {
     if (!c) return ARP_E_INVALID_ARG;
-    ARP_REQUIRE(c, c->have_planes, ARP_E_NOT_READY, "arp_ring_ring_run before arp_upload_planes");
+    ARP_REQUIRE(c, c->have_planes, ARP_E_NOT_READY, what);
     ARP_TRY(arp_bind(c));
-    return plane_run<KIND_RING_RING>(c, c->ring_ring, c->rings.n, c->rings.n, n);
+    if (!c->h_plane_tot) ARP_CUDA(c, cudaMallocHost((void**)&c->h_plane_tot, 64));
+    return planes_run(c, mask, n_out);
+}
+
+int arp_ring_ring_run(arp_ctx* c, uint64_t* n)
+{
+    uint64_t v[PLG_TERMS] = {0, 0, 0, 0};
+    int rc = planes_entry(c, 1 << KIND_RING_RING, v, "arp_ring_ring_run before arp_upload_planes");
+    if (rc == ARP_OK && n) *n = v[KIND_RING_RING];
+    return rc;
 }
 int arp_ring_ring_fetch(arp_ctx* c, arp_plane_pair* dst, uint64_t cap)
 {
@@ -526,12 +787,10 @@ int arp_ring_ring_fetch(arp_ctx* c, arp_plane_pair* dst, uint64_t cap)
 
 int arp_atom_ring_run(arp_ctx* c, uint64_t* n)
 {
-    if (!c) return ARP_E_INVALID_ARG;
-    ARP_REQUIRE(c, c->have_planes, ARP_E_NOT_READY, "arp_atom_ring_run before arp_upload_planes");
-    ARP_REQUIRE(c, c->have_atoms, ARP_E_NOT_READY, "arp_atom_ring_run before arp_upload_atoms");
-    ARP_REQUIRE(c, c->S == 1, ARP_E_INVALID_ARG, "plane terms need a single structure");
-    ARP_TRY(arp_bind(c));
-    return plane_run<KIND_ATOM_RING>(c, c->atom_ring, c->rings.n, c->N, n);
+    uint64_t v[PLG_TERMS] = {0, 0, 0, 0};
+    int rc = planes_entry(c, 1 << KIND_ATOM_RING, v, "arp_atom_ring_run before arp_upload_planes");
+    if (rc == ARP_OK && n) *n = v[KIND_ATOM_RING];
+    return rc;
 }
 int arp_atom_ring_fetch(arp_ctx* c, arp_atom_plane* dst, uint64_t cap)
 {
@@ -541,10 +800,10 @@ int arp_atom_ring_fetch(arp_ctx* c, arp_atom_plane* dst, uint64_t cap)
 
 int arp_amide_amide_run(arp_ctx* c, uint64_t* n)
 {
-    if (!c) return ARP_E_INVALID_ARG;
-    ARP_REQUIRE(c, c->have_planes, ARP_E_NOT_READY, "arp_amide_amide_run before arp_upload_planes");
-    ARP_TRY(arp_bind(c));
-    return plane_run<KIND_AMIDE_AMIDE>(c, c->amide_amide, c->amides.n, c->amides.n, n);
+    uint64_t v[PLG_TERMS] = {0, 0, 0, 0};
+    int rc = planes_entry(c, 1 << KIND_AMIDE_AMIDE, v, "arp_amide_amide_run before arp_upload_planes");
+    if (rc == ARP_OK && n) *n = v[KIND_AMIDE_AMIDE];
+    return rc;
 }
 int arp_amide_amide_fetch(arp_ctx* c, arp_plane_pair* dst, uint64_t cap)
 {
@@ -554,15 +813,28 @@ int arp_amide_amide_fetch(arp_ctx* c, arp_plane_pair* dst, uint64_t cap)
 
 int arp_amide_ring_run(arp_ctx* c, uint64_t* n)
 {
-    if (!c) return ARP_E_INVALID_ARG;
-    ARP_REQUIRE(c, c->have_planes, ARP_E_NOT_READY, "arp_amide_ring_run before arp_upload_planes");
-    ARP_TRY(arp_bind(c));
-    return plane_run<KIND_AMIDE_RING>(c, c->amide_ring, c->amides.n, c->rings.n, n);
+    uint64_t v[PLG_TERMS] = {0, 0, 0, 0};
+    int rc = planes_entry(c, 1 << KIND_AMIDE_RING, v, "arp_amide_ring_run before arp_upload_planes");
+    if (rc == ARP_OK && n) *n = v[KIND_AMIDE_RING];
+    return rc;
 }
 int arp_amide_ring_fetch(arp_ctx* c, arp_plane_pair* dst, uint64_t cap)
 {
     if (!c) return ARP_E_INVALID_ARG;
     return plane_fetch(c, c->amide_ring, dst, cap);
+}
+
+/* all four terms in one launch sequence: n[0..3] = records of ring-ring, atom-ring, amide-amide, amide-ring
+   (atom-ring is left out -- n[1] = 0, its fetch fails with ARP_E_NOT_READY -- when no single structure is uploaded) */
+int arp_planes_run_all(arp_ctx* c, uint64_t* n)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    int mask = 0xF;
+    if (!c->have_atoms || c->S != 1) { mask &= ~(1 << KIND_ATOM_RING); c->atom_ring.valid = 0; }
+    uint64_t v[PLG_TERMS] = {0, 0, 0, 0};
+    int rc = planes_entry(c, mask, v, "arp_planes_run_all before arp_upload_planes");
+    if (rc == ARP_OK && n) for (int t = 0; t < PLG_TERMS; ++t) n[t] = v[t];
+    return rc;
 }
 
 }  /* extern "C" */

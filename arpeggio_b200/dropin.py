@@ -138,10 +138,17 @@ def _bump(residue, name, k):
     setattr(residue, name, v)
 
 
-def apply_atom_sifts(atoms, sifts):
+def apply_atom_sifts(atoms, sifts, integer_sifts=False):
     """Write an ``arp_atom_sift`` array back onto the atoms as the attributes the reference's pair loop
     leaves (utils.py:182-242: sift*, integer_sift*, actual_fsift*; interactions.py:822-852: actual_hbonds*,
-    actual_polars*), as plain Python lists / ints."""
+    actual_polars*), as plain Python lists / ints.
+
+    ``integer_sift*`` is ORDER-DEPENDENT in the reference: utils.py:233 ASSIGNS sift-before-this-contact + SIFt at
+    every contact, so the value is that of the atom's last contact in loop order, and the reference's loop order is
+    the KD-tree traversal of Bio.PDB.NeighborSearch.search_all, which this library does not reproduce (records are
+    (bgn, end)-sorted).  integer_sifts=False (the default of the mixin) therefore REMOVES the attributes, so that a
+    consumer (_calc_residue_sifts, the SIFt CSV writers) fails loudly instead of reading values that can differ from
+    a BioPython run; integer_sifts=True writes the values of the sorted loop order."""
     nb = abi.SIFT_NBITS
     shifts = np.arange(nb, dtype=np.uint32)
     for c, suffix in enumerate(abi.SIFT_CATEGORIES):
@@ -150,7 +157,10 @@ def apply_atom_sifts(atoms, sifts):
         hb, pl = sifts['hbonds'][:, c].tolist(), sifts['polars'][:, c].tolist()
         for k, atom in enumerate(atoms):
             setattr(atom, 'sift' + suffix, bits[k])
-            setattr(atom, 'integer_sift' + suffix, integer[k])
+            if integer_sifts:
+                setattr(atom, 'integer_sift' + suffix, integer[k])
+            elif hasattr(atom, 'integer_sift' + suffix):
+                delattr(atom, 'integer_sift' + suffix)
             setattr(atom, 'actual_fsift' + suffix, bits[k][5:])
             setattr(atom, 'actual_hbonds' + suffix, hb[k])
             setattr(atom, 'actual_polars' + suffix, pl[k])
@@ -162,6 +172,8 @@ class CudaContactsMixin:
     cuda_device = 0
     cuda_engine = None          # set to a private ContactEngine to avoid the shared one
     cuda_atom_sifts = True      # reproduce the per-atom / per-residue SIFt side effects of the loops
+    cuda_integer_sifts = False  # opt in to atom.integer_sift* evaluated in (bgn, end)-sorted loop order: the reference's
+                                # value depends on Bio.PDB's KD-tree traversal order (utils.py:233), see apply_atom_sifts
     cuda_lazy_contacts = False  # atom_contacts as a LazyAtomContacts sequence instead of a list of namedtuples
 
     def _cuda_reset_residue_sifts(self, names):
@@ -176,13 +188,21 @@ class CudaContactsMixin:
         return self.cuda_engine if self.cuda_engine is not None else shared_engine(self.cuda_device)
 
     def _cuda_packed(self):
-        """SoA image of the current selection (rebuilt whenever _make_selection produced new lists)."""
-        key = (id(self.selection_plus), len(self.selection_plus), id(self.selection), len(self.selection))
+        """SoA image of the current selection (rebuilt whenever _make_selection produced new lists; call
+        cuda_invalidate() after changing coordinates, hydrogens, atom types, rings or amides in place)."""
+        key = (id(self.selection_plus), len(self.selection_plus), id(self.selection), len(self.selection),
+               getattr(self, '_cuda_pack_version', 0))
         cached = getattr(self, '_cuda_pack_cache', None)
         if cached is None or cached[0] != key:
             cached = (key, pack_complex(self, ob=getattr(self, '_cuda_ob_module', None)))
             self._cuda_pack_cache = cached
         return cached[1]
+
+    def cuda_invalidate(self):
+        """Forget the packed image: the next contact call packs the complex again (coordinates after
+        minimize_hydrogens, atom types, rings, amides ... are read at packing time)."""
+        self._cuda_pack_version = getattr(self, '_cuda_pack_version', 0) + 1
+        self._cuda_pack_cache = None
 
     def _cuda_params(self, interacting_cutoff=None, vdw_comp_factor=None, include_sequence_adjacent=None):
         last = getattr(self, '_cuda_last_run', None)
@@ -237,6 +257,7 @@ class CudaContactsMixin:
 
         selection_residues = {a.get_parent() for a in selection}
         selection_plus_residues = {a.get_parent() for a in selection_plus}
+        self.cuda_invalidate()          # new lists; the engine also holds the whole structure now, not the packed selection
         self.selection = selection
         self.selection_ring_ids = {k for k in rings if rings[k]['residue'] in selection_residues}
         self.selection_amide_ids = {k for k in amides if amides[k]['residue'] in selection_residues}
@@ -299,7 +320,7 @@ class CudaContactsMixin:
         lazy = LazyAtomContacts(rec, atoms, AAC)
         self.atom_contacts = lazy if self.cuda_lazy_contacts else list(lazy)
         if self.cuda_atom_sifts:
-            apply_atom_sifts(atoms, eng.atom_sifts())
+            apply_atom_sifts(atoms, eng.atom_sifts(), integer_sifts=self.cuda_integer_sifts)
 
     def _calculate_ring_contacts(self):
         """Replaces interactions.py:938-1194 (plane-plane and atom-plane)."""
@@ -309,6 +330,9 @@ class CudaContactsMixin:
         eng.set_params(self._cuda_params())
         eng.upload_atoms(packed.soa)
         eng.upload_planes(packed.rings, packed.amides)
+        # all four plane terms in one launch sequence; the amide terms are kept for _calculate_group_contacts
+        terms = eng.planes_all()
+        self._cuda_plane_terms = (id(packed), terms)
         rings = self.biopython_str.rings
         names = {}
 
@@ -325,7 +349,7 @@ class CudaContactsMixin:
                                             'sc_atom_ring_inter_integer_sift'))
         inter = abi.CLASS_NAMES.index('INTER')
         self.plane_plane_contacts = []
-        for r in eng.ring_ring():
+        for r in terms['ring_ring']:
             ka, kb = packed.ring_keys[int(r['a'])], packed.ring_keys[int(r['b'])]
             code = int(r['code'])
             labels = [abi.GEOM_NAMES[code & 0xF]]
@@ -345,7 +369,7 @@ class CudaContactsMixin:
                                                  list(ring_atoms(kb)), np.float64(r['dist']), labels,
                                                  abi.CLASS_NAMES[(code >> 8) & 7]))
         self.atom_plane_contacts = []
-        for r in eng.atom_ring():
+        for r in terms['atom_ring']:
             key = packed.ring_keys[int(r['ring'])]
             code = int(r['code'])
             labels = sorted(n for b, n in enumerate(abi.AP_NAMES) if code >> b & 1)
@@ -366,8 +390,14 @@ class CudaContactsMixin:
         _, PPC, _ = _record_types(self)
         packed = self._cuda_packed()
         eng = self._cuda_engine()
-        eng.set_params(self._cuda_params())
-        eng.upload_planes(packed.rings, packed.amides)
+        stash = getattr(self, '_cuda_plane_terms', None)
+        self._cuda_plane_terms = None
+        if stash is not None and stash[0] == id(packed):
+            terms = stash[1]                                  # computed together with the ring terms just before
+        else:
+            eng.set_params(self._cuda_params())
+            eng.upload_planes(packed.rings, packed.amides)
+            terms = {'amide_amide': eng.amide_amide(), 'amide_ring': eng.amide_ring()}
         rings, amides = self.biopython_str.rings, self.biopython_str.amides
 
         def names(group):
@@ -383,7 +413,7 @@ class CudaContactsMixin:
             return sifts and (code >> 8) & 7 == inter and not code >> 11 & 1
 
         self.group_group_contacts = []
-        for r in eng.amide_amide():
+        for r in terms['amide_amide']:
             a, b = amides[packed.amide_keys[int(r['a'])]], amides[packed.amide_keys[int(r['b'])]]
             if counted(int(r['code'])):
                 _bump(a['residue'], 'amide_amide_inter_integer_sift', 0)
@@ -391,7 +421,7 @@ class CudaContactsMixin:
                                                  np.float32(r['dist']), ['AMIDEAMIDE'],
                                                  abi.CLASS_NAMES[(int(r['code']) >> 8) & 7]))
         self.group_plane_contacts = []
-        for r in eng.amide_ring():
+        for r in terms['amide_ring']:
             a, g = amides[packed.amide_keys[int(r['a'])]], rings[packed.ring_keys[int(r['b'])]]
             if counted(int(r['code'])):
                 _bump(a['residue'], 'amide_ring_inter_integer_sift', 0)

@@ -247,6 +247,25 @@ class ContactEngine:
         self._check(fetch(self._ctx, out.ctypes.data if out.shape[0] else None, out.shape[0]))
         return out
 
+    def planes_all(self):
+        """All four plane terms in one launch sequence (arp_planes_run_all): dict of record arrays
+        ring_ring / atom_ring / amide_amide / amide_ring (atom_ring is None when no single structure is uploaded)."""
+        n = (C.c_uint64 * 4)()
+        self._check(self._L.arp_planes_run_all(self._ctx, n))
+        have_atoms = self._soa is not None and getattr(self._soa, 'struct_off', None) is None
+        out = {}
+        for k, (name, fetch, dtype) in enumerate((('ring_ring', self._L.arp_ring_ring_fetch, abi.PLANE_PAIR_DTYPE),
+                                                  ('atom_ring', self._L.arp_atom_ring_fetch, abi.ATOM_PLANE_DTYPE),
+                                                  ('amide_amide', self._L.arp_amide_amide_fetch, abi.PLANE_PAIR_DTYPE),
+                                                  ('amide_ring', self._L.arp_amide_ring_fetch, abi.PLANE_PAIR_DTYPE))):
+            if name == 'atom_ring' and not have_atoms:
+                out[name] = None
+                continue
+            a = np.empty(int(n[k]), dtype=dtype)
+            self._check(fetch(self._ctx, a.ctypes.data if a.shape[0] else None, a.shape[0]))
+            out[name] = a
+        return out
+
     def ring_ring(self):
         return self._plane_term(self._L.arp_ring_ring_run, self._L.arp_ring_ring_fetch, abi.PLANE_PAIR_DTYPE)
 

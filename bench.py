@@ -194,9 +194,17 @@ def planes_leg_run(eng, soa, p, n_atoms, cpu=True):
     out = {'rings': 2048, 'amides': 12_500, 'atoms': n_atoms, 'terms': {}}
     cpu_fn = {'ring_ring': lambda: oracle.ring_ring(rings, p), 'atom_ring': lambda: oracle.atom_ring(soa, rings, p),
               'amide_amide': lambda: oracle.amide_amide(amides, p), 'amide_ring': lambda: oracle.amide_ring(amides, rings, p)}
+    got = eng.planes_all()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        eng.planes_all()
+    out['all_terms_us_per_call'] = (time.perf_counter() - t0) / 20 * 1e6
+    out['what'] = ('all_terms: arp_planes_run_all (one launch sequence: three cell grids, count, scan, emit; one wait) + the four '
+                   'fetches, wall time per call; terms: each term run + fetched on its own')
     for name in ('ring_ring', 'atom_ring', 'amide_amide', 'amide_ring'):
         f = getattr(eng, name)
         n = int(f().shape[0])
+        assert n == got[name].shape[0]
         t0 = time.perf_counter()
         for _ in range(10):
             f()

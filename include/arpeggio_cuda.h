@@ -317,7 +317,9 @@ int  arp_pairs_unpack(const uint32_t* row_off, const arp_pair_c* rec, const floa
  * with utils.group_angle / group_group_angle (utils.py:638-693).
  * Planes belong to the single structure last uploaded (n_structures == 1).
  * Results are returned sorted (ring-ring: by first visit in the reference's
- * double loop; the others by (a, b)).                                        */
+ * double loop; the others by (a, b)).  A plane run makes the results of earlier
+ * plane runs invalid (their fetch fails with ARP_E_NOT_READY): fetch before the
+ * next run, or run all four at once with arp_planes_run_all.                  */
 int  arp_upload_planes(arp_ctx* ctx, const arp_planes* rings, const arp_planes* amides);
 int  arp_ring_ring_run(arp_ctx* ctx, uint64_t* n);
 int  arp_ring_ring_fetch(arp_ctx* ctx, arp_plane_pair* dst, uint64_t cap);
@@ -327,6 +329,9 @@ int  arp_amide_amide_run(arp_ctx* ctx, uint64_t* n);
 int  arp_amide_amide_fetch(arp_ctx* ctx, arp_plane_pair* dst, uint64_t cap);
 int  arp_amide_ring_run(arp_ctx* ctx, uint64_t* n);
 int  arp_amide_ring_fetch(arp_ctx* ctx, arp_plane_pair* dst, uint64_t cap);
+/* all four terms in ONE launch sequence and one wait: n[0..3] = record counts of ring-ring, atom-ring, amide-amide,
+   amide-ring; the four fetch calls then return them (atom-ring is left out when no single structure is uploaded) */
+int  arp_planes_run_all(arp_ctx* ctx, uint64_t* n);
 
 /* ---- per-atom SIFt reductions ----------------------------------
  * Segmented OR / count / last-contact reduction of the record stream of the last arp_pairs_run onto

@@ -55,7 +55,18 @@ CASES = {
     'big_site': (dict(seed=22, n_chains=3, n_res=40, n_waters=40), ['/A/5/', '/B/7/', 'RESNAME:LIG'], 5.0, 0.1, False),
     'no_explicit_h': (dict(seed=23, n_chains=2, n_res=16, n_waters=8, explicit_h=False), ['RESNAME:LIG'], 5.0, 0.1, False),
     'apo_adjacent': (dict(seed=24, n_chains=2, n_res=20, n_waters=12, ligand=False), [], 4.0, 0.2, True),
+    # protein-like density (backbone in a 1.5x larger sphere) + 100 / 90 copies of the geometries the rare rules need
+    # (C-Cl...O, C-H...Br-C, N+...O-, Zn with three O ligands, water clusters): xbond, halogen weak hbond, ionic,
+    # metal complex and WATER_WATER get >= 50 positive records each from the reference's own code
+    'rich_whole': (dict(seed=31, n_chains=2, n_res=30, n_waters=10, motifs=100, spread=1.5), [], 5.0, 0.1, False),
+    'rich_site': (dict(seed=32, n_chains=2, n_res=24, n_waters=8, motifs=90, spread=1.4),
+                  ['RESNAME:CLX', 'RESNAME:BRX', 'RESNAME:LYX', 'RESNAME:ZN', 'RESNAME:HOH', 'RESNAME:LIG'], 4.5, 0.15, False),
+    # the pairs of search_all in a seeded shuffle instead of ascending (i, j) (stand-in for Bio.PDB's KD-tree order):
+    # the reference's selection_plus = list(set(...)) then comes out in another order than an insertion in entity
+    # order gives, and integer_sift (utils.py:233) is that of another last contact
+    'kd_order': (dict(seed=33, n_chains=2, n_res=18, n_waters=10), ['RESNAME:LIG'], 5.0, 0.1, False),
 }
+PAIR_ORDER_SEED = {'kd_order': 5}
 
 
 RESIDUE_PLANE_SIFTS = ('ring_ring_inter_integer_sift', 'ring_atom_inter_integer_sift', 'atom_ring_inter_integer_sift',
@@ -123,7 +134,9 @@ def compute_case(name, kwargs, selections, cutoff, vdw_comp, incl, verbose=True)
     cx = mockbio.build_complex(**kwargs)
     ic = reference_complex(cx)
     meta = dict(case=name, recipe=kwargs, selections=selections, cutoff=cutoff, vdw_comp=vdw_comp,
-                include_sequence_adjacent=incl, numpy=np.__version__, raises=None)
+                include_sequence_adjacent=incl, numpy=np.__version__, raises=None,
+                pair_order_seed=PAIR_ORDER_SEED.get(name))
+    mockbio.NeighborSearch.pair_order_seed = PAIR_ORDER_SEED.get(name)
     try:
         ic.run_arpeggio(selections, cutoff, vdw_comp, incl)
     except AttributeError as err:           # utils.py:173 on a donor without single-bond neighbour
@@ -132,6 +145,7 @@ def compute_case(name, kwargs, selections, cutoff, vdw_comp, incl, verbose=True)
             print(f'  {name}: reference raised AttributeError ({err})')
         # selection bookkeeping is complete at that point; contacts are not
         ic.atom_contacts = []
+    mockbio.NeighborSearch.pair_order_seed = None
     packed = pack_complex(ic)
     idx = {id(a): i for i, a in enumerate(packed.atoms)}
     ring_idx = {k: i for i, k in enumerate(packed.ring_keys)}
@@ -237,6 +251,11 @@ def run_case(name, kwargs, selections, cutoff, vdw_comp, incl):
             if m >> b & 1:
                 bits[abi.SIFT_NAMES[b]] += 1
     print('     bits:', dict(bits))
+    hal = (arrays['feat'] & abi.F_IS_HALOGEN) != 0
+    n_hal_weak = int(np.count_nonzero((pairs['mask'] >> 6 & 1).astype(bool) & (hal[pairs['i']] | hal[pairs['j']])))
+    print('     weak_hbond records with a halogen (is_halogen_weak_hbond):', n_hal_weak)
+    cls = Counter(abi.CLASS_NAMES[(int(m) >> abi.CLASS_SHIFT) & abi.CLASS_MASK] for m in pairs['mask'])
+    print('     classes:', dict(cls))
 
 
 if __name__ == '__main__':

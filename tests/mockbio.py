@@ -116,7 +116,14 @@ class DisorderedAtom:   # only needed for isinstance() in InteractionComplex.__i
 
 
 class NeighborSearch:
-    """Bio.PDB.NeighborSearch restated (see module docstring)."""
+    """Bio.PDB.NeighborSearch restated (see module docstring).
+
+    pair_order_seed: Bio.PDB reports the pairs of search_all in KD-tree traversal order, which nothing here can
+    reproduce; a seed makes search_all return its pairs in a seeded shuffle instead of ascending (i, j), to exercise
+    everything that depends on that order (the insertion order of the reference's selection_plus set, the
+    order-dependent integer_sift, the order of atom_contacts)."""
+
+    pair_order_seed = None
 
     def __init__(self, atom_list, bucket_size=10):
         self.atom_list = list(atom_list)
@@ -131,6 +138,9 @@ class NeighborSearch:
             s = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]
             for j in np.nonzero(s <= r2)[0]:
                 out.append((self.atom_list[i], self.atom_list[i + 1 + int(j)]))
+        if self.pair_order_seed is not None:
+            order = np.random.default_rng(self.pair_order_seed).permutation(len(out))
+            out = [out[int(k)] for k in order]
         return out
 
     def search(self, center, radius, level='A'):
@@ -325,17 +335,23 @@ def _plane_normal(pts):
 
 
 def build_complex(seed=0, n_chains=2, n_res=24, n_waters=16, ligand=True, explicit_h=True,
-                  degenerate=False, lone_xdonor=False):
+                  degenerate=False, lone_xdonor=False, motifs=0, spread=1.0):
     """A small protein-like complex with every feature the contact rules look at.
 
     degenerate=True adds exact-geometry corner cases: coincident atoms, parallel and
     axis-aligned plane normals, a hydrogen sitting on its donor, atoms at exactly the cutoff.
+    spread > 1 lets the backbone walk in a larger sphere (fewer steric clashes: protein-like density).
+    motifs=m adds m copies each of the geometries the RARE rules need, every copy in residues of its own,
+    anchored at least 3.4 A away from everything placed before: a C-Cl...O halogen bond (is_xbond, around its
+    distance and angle thresholds), a C-H...Br-C contact (is_halogen_weak_hbond), a Lys-N+ ... Asp-O- pair (ionic,
+    2.6-4.4 A), a zinc ion with three oxygen ligands (metal complex, 1.9-3.1 A) and a cluster of five waters
+    (WATER_WATER entity class).
     """
     rng = np.random.default_rng(seed)
     cx = MockComplex()
     st = cx.biopython_str
     serial = [0]
-    sphere = 4.2 * (n_chains * n_res) ** (1.0 / 3.0) + 3.0
+    sphere = (4.2 * (n_chains * n_res) ** (1.0 / 3.0) + 3.0) * spread
 
     def add_atom(res, name, element, xyz, types=(), n_h=0):
         serial[0] += 1
@@ -518,6 +534,74 @@ def build_complex(seed=0, n_chains=2, n_res=24, n_waters=16, ligand=True, explic
     sulf = [a for a in cx.s_atoms if a.element == 'S']
     if len(sulf) >= 2:
         bond(sulf[0], sulf[-1])
+
+    if motifs:
+        placed = np.zeros((len(cx.s_atoms) + 18 * motifs + 16, 3))
+        n_placed = [len(cx.s_atoms)]
+        placed[:n_placed[0]] = [np.array(a.coord, dtype='d') for a in cx.s_atoms]
+        reach = sphere + 6.0
+
+        def anchor(clear=3.4, room=4.5):
+            """a point at least `clear` from every atom so far (the motif then occupies a ball of radius `room`)"""
+            for _ in range(400):
+                p = _unit(rng) * reach * rng.uniform(0.2, 1.0) ** (1.0 / 3.0)
+                d = placed[:n_placed[0]] - p
+                if np.sqrt((d * d).sum(axis=1).min()) >= clear + room * 0.5:
+                    return p
+            return _unit(rng) * (reach + rng.uniform(4.0, 30.0))
+
+        def het_res(code):
+            nonlocal seq
+            seq += 1
+            return Residue(het, 'H_' + code, seq, ' ', code)
+
+        def put(res, name, element, xyz, types=(), n_h=0):
+            a = add_atom(res, name, element, xyz, types, n_h)
+            placed[n_placed[0]] = np.array(a.coord, dtype='d')
+            n_placed[0] += 1
+            return a
+
+        def perp(u):
+            v = np.cross(u, _unit(rng))
+            return v / np.linalg.norm(v)
+
+        for _ in range(motifs):
+            # (1) C-Cl ... O: angle C-Cl-O between ~95 and 180 degrees, Cl...O between 2.9 and 3.6 A
+            p = anchor(); u = _unit(rng)
+            r1 = het_res('CLX')
+            c1 = put(r1, 'C1', 'C', p, {'hydrophobe'})
+            cl = put(r1, 'CL1', 'CL', p + u * 1.74, {'xbond donor', 'weak hbond acceptor', 'hydrophobe'})
+            bond(c1, cl)
+            d = u + perp(u) * rng.uniform(0.0, 1.1)
+            d /= np.linalg.norm(d)
+            put(het_res('ACX'), 'O1', 'O', np.array(cl.coord, dtype='d') + d * rng.uniform(2.9, 3.6),
+                {'hbond acceptor', 'xbond acceptor'})
+            # (2) C-H ... Br-C: the hydrogen 2.4-3.4 A from the bromine, C-Br...H between ~40 and 180 degrees
+            p = anchor(); w = _unit(rng)
+            r2 = het_res('BRX')
+            c2 = put(r2, 'C1', 'C', p, {'hydrophobe'})
+            br = put(r2, 'BR1', 'BR', p + w * 1.9, {'weak hbond acceptor'})
+            bond(c2, br)
+            d = w * rng.uniform(-0.2, 1.0) + perp(w) * rng.uniform(0.3, 1.0)
+            d /= np.linalg.norm(d)
+            hpos = np.array(br.coord, dtype='d') + d * rng.uniform(2.4, 3.4)
+            don = put(het_res('WDN'), 'C1', 'C', hpos + d * 1.09 + _unit(rng) * 0.15, {'weak hbond donor', 'hydrophobe'})
+            don.h_coords.append(hpos)
+            # (3) N+ ... O-: 2.6-4.4 A (ionic needs <= 4.0)
+            p = anchor()
+            put(het_res('LYX'), 'NZ', 'N', p, {'hbond donor', 'pos ionisable'}, 3)
+            put(het_res('ASX'), 'OD1', 'O', p + _unit(rng) * rng.uniform(2.6, 4.4), {'hbond acceptor', 'neg ionisable', 'xbond acceptor'})
+            # (4) Zn with three oxygen ligands at 1.9-3.1 A (metal complex needs <= 2.8)
+            p = anchor()
+            put(het_res('ZN'), 'ZN', 'ZN', p)
+            for k in range(3):
+                put(het_res('ACM'), 'O1', 'O', p + _unit(rng) * rng.uniform(1.9, 3.1), {'hbond acceptor'})
+            # (5) five waters within a 2.2 A ball
+            p = anchor()
+            for k in range(5):
+                seq += 1
+                put(Residue(het, 'W', seq, ' ', 'HOH'), 'O', 'O', p + _unit(rng) * rng.uniform(0.8, 2.2) * (k > 0),
+                    {'hbond acceptor', 'hbond donor'}, 2)
 
     if degenerate:
         seq += 1

@@ -224,8 +224,7 @@ def test_atom_sifts_golden(engine, case):
     engine.set_params(g.params)
     engine.pairs(g.soa)
     got = engine.atom_sifts()
-    for f in got.dtype.names:
-        assert np.array_equal(got[f], g.exp_atom_sifts[f]), f
+    util.assert_atom_sifts_equal(got, g, case)
 
 
 def test_atom_sifts_full_size(engine):

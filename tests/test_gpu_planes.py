@@ -173,3 +173,79 @@ def test_ring_assignment_large_and_edges(engine):
     assert a.tolist() == [-1] * 4
     a, d = engine.ring_nearest_atom(xyz, np.zeros((0, 3)), 3.0)
     assert a.shape == (0,)
+
+
+def test_all_terms_in_one_sequence(engine):
+    """arp_planes_run_all == the four single-term runs == the oracle (configs[3] sizes)."""
+    p = arp_params.make_params()
+    engine.set_params(p)
+    soa = synth.cloud_featured(30_000, seed=12, bonds=False)
+    rings, amides = synth.plane_set(700, 4_000, 30_000, seed=13)
+    engine.upload_atoms(soa)
+    engine.upload_planes(rings, amides)
+    got = engine.planes_all()
+    util.assert_records_equal(got['ring_ring'], oracle.ring_ring(rings, p), 'all: ring-ring')
+    util.assert_records_equal(got['atom_ring'], oracle.atom_ring(soa, rings, p), 'all: atom-ring')
+    util.assert_records_equal(got['amide_amide'], oracle.amide_amide(amides, p), 'all: amide-amide')
+    util.assert_records_equal(got['amide_ring'], oracle.amide_ring(amides, rings, p), 'all: amide-ring')
+    util.assert_records_equal(engine.atom_ring(), got['atom_ring'], 'single run after run_all')
+    util.assert_records_equal(engine.ring_ring(), got['ring_ring'], 'single run after run_all')
+
+
+def test_plane_grid_edge_cases(engine):
+    """Points far outside the atoms' bounding box, planes on cell borders, far-from-origin coordinates (float32 images
+    of the float64 ring centroids), a tiny and a huge radius: the grid search must find what the double loop finds."""
+    soa = synth.cloud_featured(3_000, seed=14, bonds=False)
+    rings, amides = synth.plane_set(300, 900, 3_000, seed=15)
+    rings.center[:20] += 500.0                       # outside every other point
+    amides.center[:20] -= np.float32(300.0)
+    rings.center[20:60] = np.round(rings.center[20:60] / 6.0) * 6.0     # on multiples of the default radius
+    for shift in (0.0, 20000.0):
+        soa2 = synth.cloud_featured(3_000, seed=14, bonds=False)
+        soa2.xyz += np.float32(shift)
+        r2 = type(rings)(rings.center + shift, rings.normal, rings.res_id, rings.flags, False)
+        a2 = type(amides)((amides.center + np.float32(shift)).astype(np.float32), amides.normal, amides.res_id, amides.flags, True)
+        for radius in (6.0, 0.7, 25.0):
+            p = arp_params.make_params()
+            p.ring_centroid_dist = p.amide_centroid_dist = p.met_sulphur_dist = radius
+            engine.set_params(p)
+            engine.upload_atoms(soa2)
+            engine.upload_planes(r2, a2)
+            got = engine.planes_all()
+            what = f'shift {shift} radius {radius}'
+            util.assert_records_equal(got['ring_ring'], oracle.ring_ring(r2, p), what + ' ring-ring')
+            util.assert_records_equal(got['atom_ring'], oracle.atom_ring(soa2, r2, p), what + ' atom-ring')
+            util.assert_records_equal(got['amide_amide'], oracle.amide_amide(a2, p), what + ' amide-amide')
+            util.assert_records_equal(got['amide_ring'], oracle.amide_ring(a2, r2, p), what + ' amide-ring')
+    engine.set_params(arp_params.make_params())
+
+
+def test_non_finite_centres_take_the_double_loop(engine):
+    """A NaN centre never compares `distance > threshold` true in the reference, so that plane pairs with every other
+    one: the upload detects it and the plain double loops run (same records as the oracle)."""
+    p = arp_params.make_params()
+    engine.set_params(p)
+    rings, amides = synth.plane_set(120, 200, n_atoms=2_000, seed=16, n_residues=40)
+    rings.center[3, 1] = np.nan
+    amides.center[5, 0] = np.inf
+    engine.upload_planes(rings, amides)
+    util.assert_records_equal(engine.ring_ring(), oracle.ring_ring(rings, p), 'ring-ring NaN centre')
+    util.assert_records_equal(engine.amide_amide(), oracle.amide_amide(amides, p), 'amide-amide inf centre')
+    util.assert_records_equal(engine.amide_ring(), oracle.amide_ring(amides, rings, p), 'amide-ring non-finite')
+
+
+def test_plane_double_loop_knob(monkeypatch):
+    """ARPEGGIO_NO_PLANE_GRID: the plain double loops give the same records (A/B knob and fallback path)."""
+    from arpeggio_b200.engine import ContactEngine
+    monkeypatch.setenv('ARPEGGIO_NO_PLANE_GRID', '1')
+    p = arp_params.make_params()
+    soa = synth.cloud_featured(5_000, seed=17, bonds=False)
+    rings, amides = synth.plane_set(200, 800, 5_000, seed=18)
+    with ContactEngine(0, p) as eng:
+        eng.upload_atoms(soa)
+        eng.upload_planes(rings, amides)
+        got = eng.planes_all()
+    util.assert_records_equal(got['ring_ring'], oracle.ring_ring(rings, p), 'knob ring-ring')
+    util.assert_records_equal(got['atom_ring'], oracle.atom_ring(soa, rings, p), 'knob atom-ring')
+    util.assert_records_equal(got['amide_amide'], oracle.amide_amide(amides, p), 'knob amide-amide')
+    util.assert_records_equal(got['amide_ring'], oracle.amide_ring(amides, rings, p), 'knob amide-ring')

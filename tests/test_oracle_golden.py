@@ -50,8 +50,7 @@ def test_atom_sifts_match_reference(case):
     actual_polars*; utils.py:182-242, interactions.py:822-852) replayed by the oracle over the records."""
     g = util.Golden(case)
     got = oracle.atom_sifts(g.exp_pairs, g.soa.n_atoms)
-    for f in got.dtype.names:
-        assert np.array_equal(got[f], g.exp_atom_sifts[f]), f
+    util.assert_atom_sifts_equal(got, g, case)
     assert (got['integer_sift'] != 0).any() and (got['hbonds'][:, 0] > 0).any()
     # the integer SIFt is not the plain count-capped OR: the last contact decides (utils.py:233)
     two = (got['integer_sift'][:, 0][:, None] >> (2 * np.arange(15)) & 3) == 2

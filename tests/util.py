@@ -20,6 +20,9 @@ class Golden:
         z = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
         self.name = name
         self.meta = json.loads(str(z['meta']))
+        # the reference saw the pairs of search_all in a seeded shuffle (stand-in for Bio.PDB's KD-tree order): everything
+        # order-dependent (integer_sift, utils.py:233) is then NOT reproducible from the (i, j)-sorted stream
+        self.shuffled_pairs = self.meta.get('pair_order_seed') is not None
         self.contacts_json = json.loads(str(z['contacts_json']))
         xn = z['xnbr_xyz']
         self.soa = AtomSoA(xyz=z['xyz'], feat=z['feat'], res_id=z['res_id'], rad_class=z['rad_class'], vdw=z['vdw'],
@@ -64,3 +67,13 @@ def assert_records_equal(got, exp, what, dist_bits=True):
 
 def describe_mask(m):
     return [abi.SIFT_NAMES[b] for b in range(15) if m >> b & 1] + [abi.CLASS_NAMES[(m >> 16) & 7]]
+
+
+def assert_atom_sifts_equal(got, g, what=''):
+    """arp_atom_sift arrays against a fixture: every field; for a fixture whose reference run saw shuffled pairs the
+    order-dependent integer_sift is exempt -- and must indeed differ, or the fixture pins nothing."""
+    for f in got.dtype.names:
+        if f == 'integer_sift' and g.shuffled_pairs:
+            assert not np.array_equal(got[f], g.exp_atom_sifts[f]), 'integer_sift did not depend on the pair order'
+            continue
+        assert np.array_equal(got[f], g.exp_atom_sifts[f]), f'{what} {f}'

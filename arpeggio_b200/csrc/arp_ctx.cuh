@@ -176,6 +176,7 @@ struct arp_ctx {
     DBuf plane_scratch, plane_tmp, plane_rec;
     void* h_plane_rec = nullptr;  /* pinned mirror of plane_rec */
     size_t h_plane_cap = 0;       /* ... in records */
+    size_t plane_cap_guess = 0;   /* records the last grid run produced (+ 50 %): capacity of the next blind emitting pass */
     int* h_plane_tot = nullptr;   /* pinned: record offsets at the term boundaries */
 
     /* binding-site flags */

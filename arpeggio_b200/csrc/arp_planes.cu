@@ -266,6 +266,7 @@ template <int KIND> __device__ __forceinline__ float screen_radius(const PlaneAr
  * take the plain double loops (k_plane_rows).                                                                  */
 #define PLG_SETS 3                       /* 0 atoms, 1 ring centroids, 2 amide centres */
 #define PLG_TERMS 4
+#define PLG_SLOTS 8                      /* records a row can leave in the counting pass; rows with more are searched again */
 
 struct PlaneGrid {
     double ox, oy, oz, inv_w;
@@ -289,7 +290,9 @@ struct PlaneGridArgs {
     float4* spos;                        /* cell-sorted points: x, y, z (float32), index in its set */
     int* row_cnt; int* row_off;          /* rows of the four terms, concatenated */
     int row_base[PLG_TERMS + 1];
-    PlaneRec* tmp;                       /* records in discovery order (all terms, positions = row_off) */
+    PlaneRec* slots;                     /* counting pass: the first PLG_SLOTS records of every row, discovery order */
+    int* d_tot;                          /* the record offsets at the term boundaries, for the host */
+    PlaneRec* tmp;                       /* rows with more records: all of them in discovery order (positions = row_off) */
     unsigned long long tmp_cap;
     PlaneRec* rec[PLG_TERMS];            /* per term: records in (row, column) order */
     unsigned long long cap[PLG_TERMS];
@@ -327,6 +330,7 @@ __device__ __forceinline__ bool pl_point(const PlaneArgs& A, int n_atoms, int p,
 
 __global__ void __launch_bounds__(256) k_pl_bbox(PlaneGridArgs G, int n_atoms, int n_points)
 {
+    __shared__ unsigned s_v[8][6];
     unsigned v[6] = {0, 0, 0, 0, 0, 0};
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_points; p += gridDim.x * blockDim.x) {
         int set, idx; float x, y, z;
@@ -340,7 +344,13 @@ __global__ void __launch_bounds__(256) k_pl_bbox(PlaneGridArgs G, int n_atoms, i
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         v[k] = __reduce_max_sync(FULL, v[k]);
-        if ((threadIdx.x & 31) == 0 && v[k]) atomicMax(&G.bbox[k], v[k]);
+        if ((threadIdx.x & 31) == 0) s_v[threadIdx.x >> 5][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {                      /* six atomics per block */
+        unsigned m = 0;
+        for (int w = 0; w < 8; ++w) m = max(m, s_v[w][threadIdx.x]);
+        if (m) atomicMax(&G.bbox[threadIdx.x], m);
     }
 }
 
@@ -428,15 +438,36 @@ __global__ void __launch_bounds__(256) k_pl_scatter(PlaneGridArgs G, int n_atoms
 
 template <int KIND> __device__ __forceinline__ int pl_col_set() { return KIND == KIND_ATOM_RING ? 0 : KIND == KIND_AMIDE_AMIDE ? 2 : 1; }
 
-/* one warp, one row of term KIND: the 27 cells around the row point as 9 runs; EMIT: records in discovery order to
-   tmp, then by ascending column into rec */
+/* one warp, one row of term KIND: the 27 cells around the row point are 9 contiguous runs of the cell-sorted points;
+   lanes 0..8 fetch the runs' bounds together (one round trip), then the lanes stride over the concatenated
+   candidates.  EMIT: records in discovery order to tmp, then by ascending column into rec */
+template <int KIND> __device__ __forceinline__ int pl_key(const PlaneRec& r) { return KIND == KIND_ATOM_RING ? r.a : r.b; }
+
+/* EMIT == false (counting pass): the row's records are counted and the first PLG_SLOTS of them kept in the row's slots;
+   EMIT == true (emitting pass): a row with at most PLG_SLOTS records only moves them from its slots to their places,
+   by ascending column; a row with more is searched again, its records go through tmp */
 template <int KIND, bool EMIT>
 __device__ __forceinline__ void pl_row(const PlaneGridArgs& G, const PlaneGrid& g, int row, int grow, int lane)
 {
     const PlaneArgs& A = G.A;
     int cnt = 0;
-    const int base = EMIT ? G.row_off[grow] : 0;
-    const int tbase = EMIT ? G.row_off[G.row_base[KIND]] : 0;      /* first record of the term */
+    int base = 0;
+    if (EMIT) {
+        base = G.row_off[grow];
+        const int n = G.row_off[grow + 1] - base;
+        if (n == 0 || (unsigned long long)base + n > G.cap[KIND]) return;
+        if (n <= PLG_SLOTS) {
+            if (lane < n) {
+                const PlaneRec mine = G.slots[(size_t)grow * PLG_SLOTS + lane];
+                const int key = pl_key<KIND>(mine);
+                int rk = 0;
+                for (int k = 0; k < n; ++k) rk += pl_key<KIND>(G.slots[(size_t)grow * PLG_SLOTS + k]) < key ? 1 : 0;
+                G.rec[KIND][base + rk] = mine;                  /* one buffer for all terms: the row offsets are global */
+            }
+            return;
+        }
+        if ((unsigned long long)base + n > G.tmp_cap) return;
+    }
     if (row_live<KIND>(A, row)) {
         const float4 rp = row_point<KIND>(A, row);
         const float r = screen_radius<KIND>(A);
@@ -445,63 +476,73 @@ __device__ __forceinline__ void pl_row(const PlaneGridArgs& G, const PlaneGrid& 
         pl_cell(g, rp.x, rp.y, rp.z, &cx, &cy, &cz);
         const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
         const unsigned lt = (1u << lane) - 1u;
-        for (int k = 0; k < 9; ++k) {
-            const int y = cy + k % 3 - 1, z = cz + k / 3 - 1;
-            if (y < 0 || y >= g.dy || z < 0 || z >= g.dz) continue;      /* warp-uniform */
-            const int rowc = g.cell_base + (z * g.dy + y) * g.dx;
-            const int b = G.cell_start[rowc + x0], e = G.cell_start[rowc + x1 + 1];
-            for (int q0 = b; q0 < e; q0 += 32) {
-                const int q = q0 + lane;
-                bool hit = false;
-                PlaneRec rec;
-                if (q < e) {
-                    const float4 cp = G.spos[q];
-                    const float dx = rp.x - cp.x, dy = rp.y - cp.y, dz = rp.z - cp.z;
-                    const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-                    const float T = t0 + 4e-7f * (rp.w + fmaxf(fabsf(cp.x), fmaxf(fabsf(cp.y), fabsf(cp.z))));
-                    if (!(d2 > T * T)) hit = plane_eval<KIND>(A, row, __float_as_int(cp.w), &rec);    /* rare: the exact predicate decides */
-                }
-                const unsigned m = __ballot_sync(FULL, hit);
-                if (EMIT && hit) {
-                    const unsigned long long pos = (unsigned long long)base + cnt + __popc(m & lt);
-                    if (pos < G.tmp_cap) G.tmp[pos] = rec;
-                }
-                cnt += __popc(m);
+        int rb = 0, rl = 0;                                        /* lane k < 9: run k = (first position, length) */
+        if (lane < 9) {
+            const int y = cy + lane % 3 - 1, z = cz + lane / 3 - 1;
+            if (y >= 0 && y < g.dy && z >= 0 && z < g.dz) {
+                const int rowc = g.cell_base + (z * g.dy + y) * g.dx;
+                rb = G.cell_start[rowc + x0];
+                rl = G.cell_start[rowc + x1 + 1] - rb;
             }
+        }
+        int incl = rl;
+#pragma unroll
+        for (int off = 1; off < 16; off <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, off);
+            if (lane >= off) incl += v;
+        }
+        const int total = __shfl_sync(FULL, incl, 8);
+        const int cofs = rb - (incl - rl);                         /* position = cofs + k for the k of this run */
+        int co[9], pe[9];                                          /* per run: offset, end of its k range */
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { co[k] = __shfl_sync(FULL, cofs, k); pe[k] = __shfl_sync(FULL, incl, k); }
+        for (int k0 = 0; k0 < total; k0 += 32) {
+            const int k = k0 + lane;
+            bool hit = false;
+            PlaneRec rec;
+            if (k < total) {
+                int q = k + co[8];
+#pragma unroll
+                for (int t = 7; t >= 0; --t) if (k < pe[t]) q = k + co[t];
+                const float4 cp = G.spos[q];
+                const float dx = rp.x - cp.x, dy = rp.y - cp.y, dz = rp.z - cp.z;
+                const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                const float T = t0 + 4e-7f * (rp.w + fmaxf(fabsf(cp.x), fmaxf(fabsf(cp.y), fabsf(cp.z))));
+                if (!(d2 > T * T)) hit = plane_eval<KIND>(A, row, __float_as_int(cp.w), &rec);    /* rare: the exact predicate decides */
+            }
+            const unsigned m = __ballot_sync(FULL, hit);
+            if (hit) {
+                const int pos = cnt + __popc(m & lt);
+                if (EMIT) G.tmp[base + pos] = rec;
+                else if (pos < PLG_SLOTS) G.slots[(size_t)grow * PLG_SLOTS + pos] = rec;
+            }
+            cnt += __popc(m);
         }
     }
     if (!EMIT) {
         if (lane == 0) G.row_cnt[grow] = cnt;
         return;
     }
-    if (cnt == 0 || (unsigned long long)base + cnt > G.tmp_cap || (unsigned long long)(base - tbase) + cnt > G.cap[KIND]) return;
     __syncwarp();
     /* column order inside the row: the rank of a record is the number of the row's records with a smaller column.
        The column is field b, except for atom-ring records (atom, ring), where it is field a. */
     for (int h = lane; h < cnt; h += 32) {
         const PlaneRec mine = G.tmp[base + h];
-        const int key = KIND == KIND_ATOM_RING ? mine.a : mine.b;
+        const int key = pl_key<KIND>(mine);
         int rk = 0;
-        for (int k = 0; k < cnt; ++k) {
-            const PlaneRec& o = G.tmp[base + k];
-            rk += (KIND == KIND_ATOM_RING ? o.a : o.b) < key ? 1 : 0;
-        }
-        G.rec[KIND][base - tbase + rk] = mine;
+        for (int k = 0; k < cnt; ++k) rk += pl_key<KIND>(G.tmp[base + k]) < key ? 1 : 0;
+        G.rec[KIND][base + rk] = mine;
     }
-}
-
-/* the record offsets at the term boundaries, contiguous for one small copy */
-__global__ void k_pl_totals(PlaneGridArgs G, int* __restrict__ tot)
-{
-    if (threadIdx.x <= PLG_TERMS) tot[threadIdx.x] = G.row_off[G.row_base[threadIdx.x]];
 }
 
 #define PLG_WARPS 8
 template <bool EMIT>
-__global__ void __launch_bounds__(PLG_WARPS * 32) k_pl_pass(PlaneGridArgs G)
+__global__ void __launch_bounds__(PLG_WARPS * 32, 4) k_pl_pass(PlaneGridArgs G)
 {
     const int lane = threadIdx.x & 31;
     const int grow = blockIdx.x * PLG_WARPS + (threadIdx.x >> 5);
+    if (EMIT && blockIdx.x == 0 && threadIdx.x <= PLG_TERMS)      /* the record offsets at the term boundaries, for the host */
+        G.d_tot[threadIdx.x] = G.row_off[G.row_base[threadIdx.x]];
     if (grow >= G.row_base[PLG_TERMS]) return;
     if (grow < G.row_base[1])      pl_row<KIND_RING_RING, EMIT>(G, G.grids[pl_col_set<KIND_RING_RING>()], grow - G.row_base[0], grow, lane);
     else if (grow < G.row_base[2]) pl_row<KIND_ATOM_RING, EMIT>(G, G.grids[pl_col_set<KIND_ATOM_RING>()], grow - G.row_base[1], grow, lane);
@@ -625,7 +666,8 @@ static int planes_run_grid(arp_ctx* c, int mask)
     const size_t o_rcnt = up(o_state_r + tiles_r * 8), zero_bytes = up(o_rcnt + ((size_t)rows + 2) * 4);
     /* scratch: grids | cell_start | cell_of | rank | spos | row_off */
     const size_t o_start = up(zero_bytes + sizeof(PlaneGrid) * PLG_SETS), o_cellof = up(o_start + cells * 4), o_rank = up(o_cellof + P * 4);
-    const size_t o_spos = up(o_rank + P * 4), o_roff = up(o_spos + P * 16), bytes = up(o_roff + ((size_t)rows + 2) * 4);
+    const size_t o_spos = up(o_rank + P * 4), o_roff = up(o_spos + P * 16), o_slots = up(o_roff + ((size_t)rows + 2) * 4);
+    const size_t bytes = up(o_slots + (size_t)rows * PLG_SLOTS * sizeof(PlaneRec));
     ARP_TRY(dbuf_reserve(c, c->plane_scratch, bytes));
     char* z = c->plane_scratch.as<char>();
     G.bbox = (unsigned*)z; G.n_cells = (unsigned*)(z + 64); G.cell_cnt = (int*)(z + o_cnt);
@@ -634,6 +676,7 @@ static int planes_run_grid(arp_ctx* c, int mask)
     G.row_cnt = (int*)(z + o_rcnt);
     G.grids = (PlaneGrid*)(z + zero_bytes); G.cell_start = (int*)(z + o_start); G.cell_of = (int*)(z + o_cellof);
     G.rank = (int*)(z + o_rank); G.spos = (float4*)(z + o_spos); G.row_off = (int*)(z + o_roff);
+    G.slots = (PlaneRec*)(z + o_slots); G.d_tot = (int*)(z + 128);       /* d_tot: inside the zero region, behind the bounding box and the cell total */
     cudaStream_t st = c->stream;
     ARP_CUDA(c, cudaMemsetAsync(z, 0, zero_bytes, st));
     const unsigned pb = (unsigned)((P + 255) / 256 < (size_t)c->sm_count * 8 ? (P + 255) / 256 : (size_t)c->sm_count * 8);
@@ -649,34 +692,35 @@ static int planes_run_grid(arp_ctx* c, int mask)
     ARP_LAUNCHED(c);
     ARP_TRY(arp_scan_exclusive(c, G.row_cnt, G.row_off, state_r, tick_r, nullptr, rows + 1, (size_t)rows + 1));
     int* h_tot = c->h_plane_tot;                    /* pinned: the record offsets at the term boundaries */
-    int* d_tot = (int*)(z + 128);                   /* inside the zero region, behind the bounding box and the cell total */
-    k_pl_totals<<<1, 32, 0, st>>>(G, d_tot);
-    ARP_LAUNCHED(c);
-    ARP_CUDA(c, cudaMemcpyAsync(h_tot, d_tot, (PLG_TERMS + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
-    ARP_CUDA(c, cudaStreamSynchronize(st));
-    const int total = h_tot[PLG_TERMS];
     /* every run of this path leaves its records in ONE buffer (term t at offset h_tot[t]) and, with one copy, in a pinned
-       host mirror: the fetch calls then cost no CUDA call.  Results of earlier plane runs are no longer valid. */
+       host mirror: the fetch calls then cost no CUDA call.  Results of earlier plane runs are no longer valid.
+       The emitting pass is enqueued BLIND behind the counting pass, with the capacity the last runs needed, so that
+       the whole sequence costs one wait; a run that needs more is emitted again with larger buffers. */
     for (PlaneResult* R : { &c->ring_ring, &c->atom_ring, &c->amide_amide, &c->amide_ring }) { R->valid = 0; R->host = nullptr; }
-    if (total > 0) {
-        ARP_TRY(dbuf_reserve(c, c->plane_tmp, (size_t)total * sizeof(PlaneRec)));
-        ARP_TRY(dbuf_reserve(c, c->plane_rec, (size_t)total * sizeof(PlaneRec)));
-        if (c->h_plane_cap < (size_t)total) {
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        size_t cap = c->plane_cap_guess > 1024 ? c->plane_cap_guess : 1024;
+        if (attempt == 1) cap = (size_t)h_tot[PLG_TERMS] + (size_t)h_tot[PLG_TERMS] / 4 + 1024;
+        ARP_TRY(dbuf_reserve(c, c->plane_tmp, cap * sizeof(PlaneRec)));
+        ARP_TRY(dbuf_reserve(c, c->plane_rec, cap * sizeof(PlaneRec)));
+        if (c->h_plane_cap < cap) {
             if (c->h_plane_rec) cudaFreeHost(c->h_plane_rec);
             c->h_plane_rec = nullptr; c->h_plane_cap = 0;
-            const size_t want = (size_t)total + (size_t)total / 4 + 1024;
-            ARP_CUDA(c, cudaMallocHost(&c->h_plane_rec, want * sizeof(PlaneRec)));
-            c->h_plane_cap = want;
+            ARP_CUDA(c, cudaMallocHost(&c->h_plane_rec, cap * sizeof(PlaneRec)));
+            c->h_plane_cap = cap;
         }
-        G.tmp = c->plane_tmp.as<PlaneRec>(); G.tmp_cap = (unsigned long long)total;
-        for (int t = 0; t < PLG_TERMS; ++t) {
-            G.rec[t] = c->plane_rec.as<PlaneRec>() + h_tot[t]; G.cap[t] = (unsigned long long)(h_tot[t + 1] - h_tot[t]);
-        }
+        G.tmp = c->plane_tmp.as<PlaneRec>(); G.tmp_cap = (unsigned long long)cap;
+        /* the term's first record sits at row_off[row_base[t]], which only the device knows yet: one buffer, term offsets
+           applied in the kernel (rec[t] = buffer start + that offset) */
+        for (int t = 0; t < PLG_TERMS; ++t) { G.rec[t] = c->plane_rec.as<PlaneRec>(); G.cap[t] = (unsigned long long)cap; }
         k_pl_pass<true><<<rb, PLG_WARPS * 32, 0, st>>>(G);
         ARP_LAUNCHED(c);
-        ARP_CUDA(c, cudaMemcpyAsync(c->h_plane_rec, c->plane_rec.p, (size_t)total * sizeof(PlaneRec), cudaMemcpyDeviceToHost, st));
+        ARP_CUDA(c, cudaMemcpyAsync(h_tot, G.d_tot, (PLG_TERMS + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+        ARP_CUDA(c, cudaMemcpyAsync(c->h_plane_rec, c->plane_rec.p, cap * sizeof(PlaneRec), cudaMemcpyDeviceToHost, st));
         ARP_CUDA(c, cudaStreamSynchronize(st));
+        if ((size_t)h_tot[PLG_TERMS] <= cap) break;
+        ARP_REQUIRE(c, attempt == 0, ARP_E_CAPACITY, "plane records overflowed repeatedly");
     }
+    c->plane_cap_guess = (size_t)h_tot[PLG_TERMS] + (size_t)h_tot[PLG_TERMS] / 2 + 1024;
     for (int t = 0; t < PLG_TERMS; ++t) if (mask & (1 << t)) {
         PlaneResult& R = plane_result(c, t);
         R.n = (uint64_t)(h_tot[t + 1] - h_tot[t]);

@@ -45,6 +45,7 @@ def lib():
         'arp_host_alloc': (i32, [C.POINTER(vp), u64]),
         'arp_host_free': (i32, [vp]),
         'arp_upload_atoms': (i32, [vp, C.POINTER(abi.ArpAtoms)]),
+        'arp_upload_atoms_batch': (i32, [vp, C.POINTER(C.POINTER(abi.ArpAtoms)), i32]),
         'arp_pairs_run': (i32, [vp, u64p]),
         'arp_pairs_fetch': (i32, [vp, vp, u64, i32]),
         'arp_pairs_device_ptr': (i32, [vp, C.POINTER(vp)]),

@@ -186,7 +186,7 @@ SIFT_CATEGORIES = ('', '_inter_only', '_intra_only', '_water_only')     # attrib
 EXPORTED_SYMBOLS = (
     'arp_abi_version', 'arp_device_count', 'arp_create', 'arp_destroy', 'arp_last_error',
     'arp_params_default', 'arp_set_params', 'arp_host_alloc', 'arp_host_free',
-    'arp_upload_atoms', 'arp_pairs_run', 'arp_pairs_fetch', 'arp_pairs_device_ptr',
+    'arp_upload_atoms', 'arp_upload_atoms_batch', 'arp_pairs_run', 'arp_pairs_fetch', 'arp_pairs_device_ptr',
     'arp_pairs_run_async', 'arp_pairs_count', 'arp_pairs_fetch_compact', 'arp_pairs_fetch_dist', 'arp_pairs_unpack',
     'arp_upload_planes', 'arp_ring_ring_run', 'arp_ring_ring_fetch', 'arp_atom_ring_run',
     'arp_atom_ring_fetch', 'arp_amide_amide_run', 'arp_amide_amide_fetch', 'arp_amide_ring_run',

@@ -88,17 +88,21 @@ class BatchRunner:
         return CompactPairs(raw[:4 * (n_atoms + 1)].view(np.uint32), raw[o_rec:o_rec + 8 * cap].view(abi.PAIR_C_DTYPE),
                             raw[o_dist:o_dist + 4 * cap].view(np.float32) if with_dist else None)
 
-    def run(self, soas, consume=None, sorted=False, check_finite=True, compact=False, with_dist=False):
+    def run(self, soas, consume=None, sorted=False, check_finite=True, compact=False, with_dist=False, pack=1):
         """Upload -> grid build + pair kernels -> fetch for every AtomSoA of `soas`.
 
         consume(index, records): called in the worker thread with a view of the slot's pinned record
         buffer (valid only during the call).  compact: the (i, j)-sorted stream in its compact form
-        (engine.CompactPairs; distances only with_dist) instead of 16-byte records.
+        (engine.CompactPairs; distances only with_dist) instead of 16-byte records.  pack > 1 (compact only): that
+        many consecutive structures go up as ONE batch (arp_upload_atoms_batch: one DMA per structure, concatenated on
+        the device) and run as one launch sequence; consume still sees one CompactPairs per structure (the j of its
+        records are batch-global: subtract its atom_base).
         Returns (pairs_per_structure, seconds)."""
         soas = list(soas)
         counts = [0] * len(soas)
         todo = queue.SimpleQueue()
-        for i in range(len(soas)):
+        pack = max(1, int(pack)) if compact else 1
+        for i in range(0, len(soas), pack):
             todo.put(i)
         errors = []
 
@@ -110,6 +114,22 @@ class BatchRunner:
                         i = todo.get_nowait()
                     except queue.Empty:
                         return
+                    if pack > 1:
+                        group = soas[i:i + pack]
+                        off = eng.upload_atoms_batch(group, check_finite=check_finite)
+                        eng.run_pairs_async()
+                        n_atoms = int(off[-1])
+                        guess = max(self._last_n[slot], 14 * n_atoms)
+                        buf = self._compact_buffer(slot, n_atoms, guess, with_dist)
+                        rec = eng.fetch_pairs_compact(with_dist, out=buf, grow=lambda m, s=slot, a=n_atoms:
+                                                      self._compact_buffer(s, a, m, with_dist))
+                        self._last_n[slot] = rec.n
+                        for k in range(len(group)):
+                            part = rec.structure(int(off[k]), int(off[k + 1]))
+                            counts[i + k] = part.n
+                            if consume is not None:
+                                consume(i + k, part)
+                        continue
                     eng.upload_atoms(soas[i], check_finite=check_finite)
                     if compact:
                         # one wait per structure: the fetch waits for the run; the slot's buffer is sized from the

@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <new>
+#include <vector>
 
 #include "arp_ctx.cuh"
 
@@ -125,6 +126,104 @@ void pairs_invalidate(arp_ctx* c)
 
 }  // namespace
 
+/* ---- a batch of structures in ONE upload: packed on the device ---------------------------------------------
+ * arp_upload_atoms takes a batch as ONE arp_atoms whose arrays the caller has already concatenated (struct_off,
+ * residue / bond / hydrogen indices rebased).  arp_upload_atoms_batch takes the structures as they are -- one
+ * arp_atoms each, indices local to the structure, radius tables of their own -- moves every structure with its own
+ * DMA(s) into a staging arena and lets the device do the concatenation: indices rebased, radius classes mapped
+ * onto one merged table.  The batch then runs as one launch sequence (struct_off inside): 16 structures of 20k atoms
+ * cost the kernels of one 320k-atom structure instead of 16 separate launch sequences. */
+namespace {
+
+struct PartDesc {                      /* device: where the arrays of one structure sit in the staging arena (byte offsets, -1: absent) */
+    int atom_base, n_atoms, res_base, n_res, bond_base, h_base, class_base, pad;
+    long long o_xyz, o_feat, o_res_id, o_rad, o_prev, o_next, o_flags, o_boff, o_bnbr, o_hoff, o_hxyz, o_xnbr;
+};
+
+struct MergeArgs {
+    const PartDesc* parts; int n_parts;
+    const char* stage; const unsigned short* class_map;
+    int N, Rs, E, H;
+    float* xyz; uint32_t* feat; int32_t* res_id; uint16_t* rad_class; int32_t* res_prev; int32_t* res_next; uint8_t* res_flags;
+    int32_t* bond_off; int32_t* bond_nbr; int32_t* h_off; double* h_xyz; float* xnbr;
+};
+
+/* part of global index i for bases ascending with duplicates (empty structures): last part whose base is <= i */
+template <class F> __device__ __forceinline__ int part_of(const PartDesc* p, int n, int i, F base)
+{
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (base(p[mid]) <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) k_merge_atoms(MergeArgs M)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        if (M.bond_off) M.bond_off[M.N] = M.E;
+        if (M.h_off) M.h_off[M.N] = M.H;
+    }
+    if (i >= M.N) return;
+    const PartDesc& d = M.parts[part_of(M.parts, M.n_parts, i, [](const PartDesc& q) { return q.atom_base; })];
+    const int li = i - d.atom_base;
+    const float* x = (const float*)(M.stage + d.o_xyz) + 3 * (size_t)li;
+    M.xyz[3 * (size_t)i] = x[0]; M.xyz[3 * (size_t)i + 1] = x[1]; M.xyz[3 * (size_t)i + 2] = x[2];
+    M.feat[i] = ((const uint32_t*)(M.stage + d.o_feat))[li];
+    M.res_id[i] = ((const int32_t*)(M.stage + d.o_res_id))[li] + d.res_base;
+    M.rad_class[i] = M.class_map[d.class_base + ((const uint16_t*)(M.stage + d.o_rad))[li]];
+    if (M.bond_off) M.bond_off[i] = d.bond_base + (d.o_boff >= 0 ? ((const int32_t*)(M.stage + d.o_boff))[li] : 0);
+    if (M.h_off) M.h_off[i] = d.h_base + (d.o_hoff >= 0 ? ((const int32_t*)(M.stage + d.o_hoff))[li] : 0);
+    if (M.xnbr) {
+        float a = 0.f, b = 0.f, c = 0.f;
+        if (d.o_xnbr >= 0) { const float* q = (const float*)(M.stage + d.o_xnbr) + 3 * (size_t)li; a = q[0]; b = q[1]; c = q[2]; }
+        M.xnbr[3 * (size_t)i] = a; M.xnbr[3 * (size_t)i + 1] = b; M.xnbr[3 * (size_t)i + 2] = c;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_merge_rest(MergeArgs M)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < M.Rs) {
+        const PartDesc& d = M.parts[part_of(M.parts, M.n_parts, t, [](const PartDesc& q) { return q.res_base; })];
+        const int lr = t - d.res_base;
+        const int pv = ((const int32_t*)(M.stage + d.o_prev))[lr], nx = ((const int32_t*)(M.stage + d.o_next))[lr];
+        M.res_prev[t] = pv >= 0 ? pv + d.res_base : pv;
+        M.res_next[t] = nx >= 0 ? nx + d.res_base : nx;
+        M.res_flags[t] = ((const uint8_t*)(M.stage + d.o_flags))[lr];
+    }
+    if (t < M.E) {
+        const PartDesc& d = M.parts[part_of(M.parts, M.n_parts, t, [](const PartDesc& q) { return q.bond_base; })];
+        M.bond_nbr[t] = ((const int32_t*)(M.stage + d.o_bnbr))[t - d.bond_base] + d.atom_base;
+    }
+    if (t < M.H) {
+        const PartDesc& d = M.parts[part_of(M.parts, M.n_parts, t, [](const PartDesc& q) { return q.h_base; })];
+        const double* h = (const double*)(M.stage + d.o_hxyz) + 3 * (size_t)(t - d.h_base);
+        M.h_xyz[3 * (size_t)t] = h[0]; M.h_xyz[3 * (size_t)t + 1] = h[1]; M.h_xyz[3 * (size_t)t + 2] = h[2];
+    }
+}
+
+int check_part(arp_ctx* c, const arp_atoms* a)
+{
+    ARP_REQUIRE(c, a != nullptr, ARP_E_INVALID_ARG, "a structure of the batch is NULL");
+    ARP_REQUIRE(c, a->n_atoms >= 0 && a->n_residues >= 0 && a->n_rad_classes >= 0, ARP_E_INVALID_ARG, "negative size");
+    ARP_REQUIRE(c, a->n_structures <= 1, ARP_E_INVALID_ARG, "arp_upload_atoms_batch takes single structures");
+    if (a->n_atoms > 0) {
+        ARP_REQUIRE(c, a->xyz && a->feat && a->res_id && a->rad_class && a->vdw && a->cov && a->res_prev &&
+                       a->res_next && a->res_flags, ARP_E_INVALID_ARG, "a required atom array is NULL");
+        ARP_REQUIRE(c, a->n_residues > 0 && a->n_rad_classes > 0, ARP_E_INVALID_ARG, "atoms without residues or radius classes");
+        ARP_REQUIRE(c, !a->bond_off || a->bond_off[0] == 0, ARP_E_INVALID_ARG, "bond_off[0] != 0");
+        ARP_REQUIRE(c, !a->h_off || a->h_off[0] == 0, ARP_E_INVALID_ARG, "h_off[0] != 0");
+        ARP_REQUIRE(c, !a->bond_off || a->bond_off[a->n_atoms] == 0 || a->bond_nbr, ARP_E_INVALID_ARG, "bond_nbr is NULL");
+        ARP_REQUIRE(c, !a->h_off || a->h_off[a->n_atoms] == 0 || a->h_xyz, ARP_E_INVALID_ARG, "h_xyz is NULL");
+    }
+    return ARP_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int arp_abi_version(void) { return ARP_ABI_VERSION; }
@@ -220,11 +319,12 @@ void arp_destroy(arp_ctx* c)
     DBuf* bufs[] = { &c->xyz, &c->feat, &c->res_id, &c->rad_class, &c->vdw, &c->cov, &c->res_prev, &c->res_next,
                      &c->res_flags, &c->bond_off, &c->bond_nbr, &c->h_off, &c->h_xyz, &c->xnbr, &c->struct_off,
                      &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->runtab, &c->sift_acc, &c->sift_out, &c->ring_scratch, &c->hreach, &c->arena, &c->out, &c->hits, &c->work,
-                     &c->radtab, &c->sort_tmp, &c->sort_out, &c->sort_c, &c->sort_d, &c->sort_zero, &c->sort_off, &c->within, &c->flush };
+                     &c->batch_small, &c->batch_stage, &c->radtab, &c->sort_tmp, &c->sort_out, &c->sort_c, &c->sort_d, &c->sort_zero, &c->sort_off, &c->within, &c->flush };
     for (DBuf* b : bufs) dbuf_free(*b);
     arp_planes_release(c);
     for (int k = 0; k < 5; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     if (c->h_meta) cudaFreeHost(c->h_meta);
+    if (c->h_batch) cudaFreeHost(c->h_batch);
     if (c->stream) cudaStreamDestroy(c->stream);
     (void)cudaGetLastError();
     delete c;
@@ -443,6 +543,143 @@ static int pairs_finish(arp_ctx* c)
     c->n_pairs = c->h_meta->n_pairs;
     c->pairs_valid = 1;
     fill_stats(c, 1);
+    return ARP_OK;
+}
+
+int arp_upload_atoms_batch(arp_ctx* c, const arp_atoms* const* parts, int32_t n_parts)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_REQUIRE(c, parts != nullptr && n_parts >= 1, ARP_E_INVALID_ARG, "no structures");
+    long long N = 0, Rs = 0, E = 0, H = 0;
+    bool any_bonds = false, any_h = false, any_x = false;
+    for (int s = 0; s < n_parts; ++s) {
+        ARP_TRY(check_part(c, parts[s]));
+        const arp_atoms* a = parts[s];
+        N += a->n_atoms; Rs += a->n_atoms > 0 ? a->n_residues : 0;
+        if (a->n_atoms > 0 && a->bond_off) { any_bonds = true; E += a->bond_off[a->n_atoms]; }
+        if (a->n_atoms > 0 && a->h_off) { any_h = true; H += a->h_off[a->n_atoms]; }
+        if (a->n_atoms > 0 && a->xnbr_xyz) any_x = true;
+    }
+    ARP_REQUIRE(c, N <= 500000000 && E < (1ll << 31) && H < (1ll << 31), ARP_E_INVALID_ARG, "batch too large");
+    ARP_TRY(arp_bind(c));
+    c->have_atoms = 0; pairs_invalidate(c); c->radtab_valid = 0;
+    c->atom_ring.valid = 0;
+    /* ---- host tables: part descriptors, struct_off, merged radius table + class maps (one pinned block) ---- */
+    std::vector<double> vdw, cov;
+    std::vector<unsigned short> cmap;
+    std::vector<PartDesc> desc((size_t)n_parts);
+    std::vector<int32_t> soff((size_t)n_parts + 1);
+    size_t stage_bytes = 0;
+    auto up256 = [](size_t v) { return (v + 255) / 256 * 256; };
+    struct Copy { size_t dst; const void* src; size_t bytes; };
+    std::vector<Copy> copies;
+    long long ab = 0, rb = 0, bb = 0, hb = 0;
+    c->input_bytes = 0;
+    for (int s = 0; s < n_parts; ++s) {
+        const arp_atoms* a = parts[s];
+        PartDesc& d = desc[(size_t)s];
+        memset(&d, 0, sizeof d);
+        soff[(size_t)s] = (int32_t)ab;
+        const size_t n = (size_t)a->n_atoms, nr = n ? (size_t)a->n_residues : 0;
+        const size_t ne = (n && a->bond_off) ? (size_t)a->bond_off[n] : 0, nh = (n && a->h_off) ? (size_t)a->h_off[n] : 0;
+        d.atom_base = (int)ab; d.n_atoms = (int)n; d.res_base = (int)rb; d.n_res = (int)nr; d.bond_base = (int)bb; d.h_base = (int)hb;
+        d.class_base = (int)cmap.size();
+        for (int k = 0; n && k < a->n_rad_classes; ++k) {          /* merged radius table: identical (vdw, cov) pairs share a class */
+            size_t m = 0;
+            while (m < vdw.size() && !(memcmp(&vdw[m], &a->vdw[k], 8) == 0 && memcmp(&cov[m], &a->cov[k], 8) == 0)) ++m;
+            if (m == vdw.size()) { vdw.push_back(a->vdw[k]); cov.push_back(a->cov[k]); }
+            cmap.push_back((unsigned short)m);
+        }
+        struct Piece { long long* off; const void* src; size_t bytes; };
+        Piece pc[12] = {
+            { &d.o_xyz, a->xyz, n * 12 }, { &d.o_feat, a->feat, n * 4 }, { &d.o_res_id, a->res_id, n * 4 }, { &d.o_rad, a->rad_class, n * 2 },
+            { &d.o_prev, a->res_prev, nr * 4 }, { &d.o_next, a->res_next, nr * 4 }, { &d.o_flags, a->res_flags, nr },
+            { &d.o_boff, n ? a->bond_off : nullptr, (n && a->bond_off) ? (n + 1) * 4 : 0 }, { &d.o_bnbr, a->bond_nbr, ne * 4 },
+            { &d.o_hoff, n ? a->h_off : nullptr, (n && a->h_off) ? (n + 1) * 4 : 0 }, { &d.o_hxyz, a->h_xyz, nh * 24 },
+            { &d.o_xnbr, n ? a->xnbr_xyz : nullptr, (n && a->xnbr_xyz) ? n * 12 : 0 } };
+        /* one host block (engine.pinned_soa) -> one DMA for the structure; otherwise one per array */
+        uintptr_t lo = UINTPTR_MAX, hi = 0;
+        size_t sum = 0;
+        for (const Piece& q : pc) if (q.bytes) {
+            const uintptr_t p0 = (uintptr_t)q.src;
+            lo = p0 < lo ? p0 : lo; hi = p0 + q.bytes > hi ? p0 + q.bytes : hi; sum += q.bytes;
+        }
+        bool packed = sum > 0 && (hi - lo) <= sum + 512 * 12;
+        for (const Piece& q : pc) if (q.bytes && ((uintptr_t)q.src - lo) % 8 != 0) packed = false;
+        if (packed) {
+            copies.push_back(Copy{ stage_bytes, (const void*)lo, hi - lo });
+            for (const Piece& q : pc) *q.off = q.bytes ? (long long)(stage_bytes + ((uintptr_t)q.src - lo)) : -1;
+            stage_bytes = up256(stage_bytes + (hi - lo));
+        } else {
+            for (const Piece& q : pc) {
+                *q.off = q.bytes ? (long long)stage_bytes : -1;
+                if (q.bytes) { copies.push_back(Copy{ stage_bytes, q.src, q.bytes }); stage_bytes = up256(stage_bytes + q.bytes); }
+            }
+        }
+        c->input_bytes += sum + (n ? (size_t)a->n_rad_classes * 16 : 0);
+        ab += (long long)n; rb += (long long)nr; bb += (long long)ne; hb += (long long)nh;
+    }
+    soff[(size_t)n_parts] = (int32_t)ab;
+    ARP_REQUIRE(c, vdw.size() <= ARPK_MAX_RAD, ARP_E_INVALID_ARG, "more than 512 distinct radius classes in the batch");
+    const int K = (int)vdw.size();
+    /* small tables in one pinned block, kept until the next upload */
+    const size_t o_desc = 0, o_soff = up256(o_desc + desc.size() * sizeof(PartDesc)), o_vdw = up256(o_soff + soff.size() * 4);
+    const size_t o_cov = up256(o_vdw + (size_t)(K ? K : 1) * 8), o_cmap = up256(o_cov + (size_t)(K ? K : 1) * 8);
+    const size_t small = up256(o_cmap + (cmap.size() ? cmap.size() : 1) * 2);
+    if (c->h_batch_cap < small) {
+        if (c->h_batch) cudaFreeHost(c->h_batch);
+        c->h_batch = nullptr; c->h_batch_cap = 0;
+        ARP_CUDA(c, cudaMallocHost(&c->h_batch, small + small / 2));
+        c->h_batch_cap = small + small / 2;
+    }
+    char* hb8 = (char*)c->h_batch;
+    memcpy(hb8 + o_desc, desc.data(), desc.size() * sizeof(PartDesc));
+    memcpy(hb8 + o_soff, soff.data(), soff.size() * 4);
+    if (K) { memcpy(hb8 + o_vdw, vdw.data(), (size_t)K * 8); memcpy(hb8 + o_cov, cov.data(), (size_t)K * 8); }
+    if (!cmap.empty()) memcpy(hb8 + o_cmap, cmap.data(), cmap.size() * 2);
+    ARP_TRY(dbuf_reserve(c, c->batch_small, small));
+    ARP_CUDA(c, cudaMemcpyAsync(c->batch_small.p, hb8, small, cudaMemcpyHostToDevice, c->stream));
+    ARP_TRY(dbuf_reserve(c, c->batch_stage, stage_bytes));
+    for (const Copy& q : copies)
+        ARP_CUDA(c, cudaMemcpyAsync(c->batch_stage.as<char>() + q.dst, q.src, q.bytes, cudaMemcpyHostToDevice, c->stream));
+    /* ---- the merged arrays ---- */
+    c->N = (int)N; c->Rs = (int)Rs; c->K = K; c->S = n_parts; c->E = (int)E; c->H = (int)H;
+    c->has_bonds = any_bonds; c->has_h = any_h; c->has_xnbr = any_x;
+    const size_t n = (size_t)N;
+    ARP_TRY(dbuf_reserve(c, c->xyz, n * 12)); ARP_TRY(dbuf_reserve(c, c->feat, n * 4)); ARP_TRY(dbuf_reserve(c, c->res_id, n * 4));
+    ARP_TRY(dbuf_reserve(c, c->rad_class, n * 2)); ARP_TRY(dbuf_reserve(c, c->res_prev, (size_t)Rs * 4));
+    ARP_TRY(dbuf_reserve(c, c->res_next, (size_t)Rs * 4)); ARP_TRY(dbuf_reserve(c, c->res_flags, (size_t)Rs));
+    if (any_bonds) { ARP_TRY(dbuf_reserve(c, c->bond_off, (n + 1) * 4)); ARP_TRY(dbuf_reserve(c, c->bond_nbr, (size_t)E * 4)); }
+    if (any_h) { ARP_TRY(dbuf_reserve(c, c->h_off, (n + 1) * 4)); ARP_TRY(dbuf_reserve(c, c->h_xyz, (size_t)H * 24)); }
+    if (any_x) ARP_TRY(dbuf_reserve(c, c->xnbr, n * 12));
+    /* vdw / cov / struct_off: views of the small device block */
+    for (DBuf* b : { &c->vdw, &c->cov, &c->struct_off }) dbuf_free(*b);
+    c->vdw.p = c->batch_small.as<char>() + o_vdw; c->vdw.view = true;
+    c->cov.p = c->batch_small.as<char>() + o_cov; c->cov.view = true;
+    c->struct_off.p = c->batch_small.as<char>() + o_soff; c->struct_off.view = true;
+    if (N > 0) {
+        MergeArgs M;
+        memset(&M, 0, sizeof M);
+        M.parts = (const PartDesc*)(c->batch_small.as<char>() + o_desc); M.n_parts = n_parts;
+        M.stage = c->batch_stage.as<char>(); M.class_map = (const unsigned short*)(c->batch_small.as<char>() + o_cmap);
+        M.N = (int)N; M.Rs = (int)Rs; M.E = (int)E; M.H = (int)H;
+        M.xyz = c->xyz.as<float>(); M.feat = c->feat.as<uint32_t>(); M.res_id = c->res_id.as<int32_t>();
+        M.rad_class = c->rad_class.as<uint16_t>(); M.res_prev = c->res_prev.as<int32_t>(); M.res_next = c->res_next.as<int32_t>();
+        M.res_flags = c->res_flags.as<uint8_t>();
+        M.bond_off = any_bonds ? c->bond_off.as<int32_t>() : nullptr; M.bond_nbr = any_bonds ? c->bond_nbr.as<int32_t>() : nullptr;
+        M.h_off = any_h ? c->h_off.as<int32_t>() : nullptr; M.h_xyz = any_h ? c->h_xyz.as<double>() : nullptr;
+        M.xnbr = any_x ? c->xnbr.as<float>() : nullptr;
+        k_merge_atoms<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(M);
+        ARP_LAUNCHED(c);
+        long long rest = Rs > E ? Rs : E;
+        rest = H > rest ? H : rest;
+        if (rest > 0) {
+            k_merge_rest<<<(unsigned)((rest + 255) / 256), 256, 0, c->stream>>>(M);
+            ARP_LAUNCHED(c);
+        }
+    }
+    ARP_TRY(arp_pairs_prepare(c));
+    c->have_atoms = 1;
     return ARP_OK;
 }
 

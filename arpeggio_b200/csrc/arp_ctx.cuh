@@ -120,6 +120,9 @@ struct arp_ctx {
     DBuf xyz, feat, res_id, rad_class, vdw, cov, res_prev, res_next, res_flags;
     DBuf bond_off, bond_nbr, h_off, h_xyz, xnbr, struct_off;
     DBuf arena;                   /* one block for all of the above when the caller's arrays are one host block */
+    DBuf batch_stage, batch_small;/* arp_upload_atoms_batch: the structures as uploaded; descriptors, struct_off, merged radius table */
+    void* h_batch = nullptr;      /* pinned image of batch_small */
+    size_t h_batch_cap = 0;
     int has_bonds = 0, has_h = 0, has_xnbr = 0;
     uint64_t input_bytes = 0;
 

@@ -86,7 +86,7 @@ class CompactPairs:
 
     def __init__(self, row_off, rec_buf, dist_buf):
         self.row_off, self.rec_buf, self.dist_buf = row_off, rec_buf, dist_buf
-        self.rec, self.dist, self.n, self.n_atoms = rec_buf[:0], None, 0, 0
+        self.rec, self.dist, self.n, self.n_atoms, self.atom_base = rec_buf[:0], None, 0, 0, 0
 
     def view(self, n_atoms, n, with_dist):
         v = CompactPairs(self.row_off, self.rec_buf, self.dist_buf)
@@ -100,6 +100,17 @@ class CompactPairs:
     def nbytes(self):
         return self.row_off.nbytes + self.rec.nbytes + (self.dist.nbytes if self.dist is not None else 0)
 
+    def structure(self, a0, a1):
+        """The rows of atoms [a0, a1) -- one structure of a batch -- as a CompactPairs of its own (views; the j of its
+        records stay GLOBAL atom indices: subtract a0 for indices local to the structure)."""
+        v = CompactPairs(self.row_off, self.rec_buf, self.dist_buf)
+        r0, r1 = int(self.row_off[a0]), int(self.row_off[a1])
+        v.n_atoms, v.n, v.atom_base = a1 - a0, r1 - r0, a0
+        v.row_off = self.row_off[a0:a1 + 1] - np.uint32(r0)
+        v.rec = self.rec[r0:r1]
+        v.dist = self.dist[r0:r1] if self.dist is not None else None
+        return v
+
     def to_records(self, dist=None):
         """PAIR_DTYPE[n] through the library's host unpacker (arp_pairs_unpack)."""
         out = np.empty(self.n, dtype=abi.PAIR_DTYPE)
@@ -110,6 +121,14 @@ class CompactPairs:
         if rc != abi.OK:
             raise ArpeggioCudaError(rc, 'arp_pairs_unpack failed')
         return out
+
+
+class _BatchInfo:
+    """What the engine remembers of a batch upload: the host arrays (kept alive) and the total atom count."""
+
+    def __init__(self, soas, n_atoms):
+        self.soas, self.n_atoms = soas, n_atoms
+        self.struct_off = True          # a batch: the plane terms do not apply
 
 
 class ContactEngine:
@@ -162,6 +181,23 @@ class ContactEngine:
         a = soa.as_ctypes()
         self._check(self._L.arp_upload_atoms(self._ctx, C.byref(a)))
         self._soa = soa            # keeps the host arrays alive while the copies are in flight
+
+    def upload_atoms_batch(self, soas, check_finite=True):
+        """Several independent structures (AtomSoA each, indices local to the structure) as one batch: every structure
+        travels with its own DMA and the device concatenates them (arp_upload_atoms_batch), so that run_pairs works on
+        all of them in one launch sequence.  Returns the atom offsets [len(soas) + 1] of the structures in the batch:
+        the atom indices of the results are global."""
+        soas = list(soas)
+        if check_finite:
+            for soa in soas:
+                if soa.n_atoms and not np.isfinite(soa.xyz).all():
+                    raise ValueError('non-finite atom coordinates')
+        structs = [soa.as_ctypes() for soa in soas]
+        arr = (C.POINTER(abi.ArpAtoms) * len(structs))(*[C.pointer(a) for a in structs])
+        self._check(self._L.arp_upload_atoms_batch(self._ctx, arr, len(structs)))
+        off = np.concatenate([[0], np.cumsum([soa.n_atoms for soa in soas])]).astype(np.int64)
+        self._soa = _BatchInfo(soas, int(off[-1]))            # keeps the host arrays alive while the copies are in flight
+        return off
 
     def run_pairs(self):
         """Grid build + pair kernel on the uploaded atoms; returns the number of contact records."""

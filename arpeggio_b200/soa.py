@@ -119,6 +119,15 @@ class AtomSoA:
         return tot
 
     def as_ctypes(self):
+        """The arp_atoms image of the arrays; cached for as long as the same array objects are in place (a batch
+        driver asks for it once per upload, and building it costs about as much as a small structure's kernels)."""
+        names = ('xyz', 'feat', 'res_id', 'rad_class', 'vdw', 'cov', 'res_prev', 'res_next',
+                 'res_flags', 'bond_off', 'bond_nbr', 'h_off', 'h_xyz', 'xnbr_xyz', 'struct_off')
+        arrays = tuple(getattr(self, n) for n in names)       # kept with the cache: their ids cannot be reused meanwhile
+        key = tuple(id(a) for a in arrays)
+        cached = self.__dict__.get('_ct_cache')
+        if cached is not None and cached[0] == key:
+            return cached[1]
         s = abi.ArpAtoms()
         s.n_atoms = self.n_atoms
         s.n_residues = self.n_residues
@@ -127,6 +136,7 @@ class AtomSoA:
         for name in ('xyz', 'feat', 'res_id', 'rad_class', 'vdw', 'cov', 'res_prev', 'res_next',
                      'res_flags', 'bond_off', 'bond_nbr', 'h_off', 'h_xyz', 'xnbr_xyz', 'struct_off'):
             setattr(s, name, abi.ptr(getattr(self, name)))
+        self.__dict__['_ct_cache'] = (key, s, arrays)
         return s
 
     def structure(self, s):

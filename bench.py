@@ -365,10 +365,10 @@ def run_ours(args):
     if args.batch_structures > 0:
         distinct = [pinned_soa(synth.cloud_featured(args.batch_atoms, seed=1000 + 97 * rank + k)) for k in range(8)]
         shard = [distinct[k % len(distinct)] for k in range(args.batch_structures)]
-        runner.run(shard[:6], check_finite=False, compact=True)
+        runner.run(shard[:6 * args.batch_pack], check_finite=False, compact=True, pack=args.batch_pack)
         if dist:
             dist.barrier()
-        counts, dt_b = runner.run(shard, check_finite=False, compact=True)
+        counts, dt_b = runner.run(shard, check_finite=False, compact=True, pack=args.batch_pack)
         batch = (len(shard), float(sum(counts)), dt_b)
     runner.close()
     large = None
@@ -456,8 +456,10 @@ def run_ours(args):
             line['batch'] = {'metric': 'structures/s (configs[4]: PDB-batch of synthetic 20k-atom structures)',
                              'value': batch[0] / batch[2], 'unit': 'structures/s', 'structures': batch[0],
                              'atoms_per_structure': args.batch_atoms, 'pairs_per_s': batch[1] / batch[2],
-                             'seconds': batch[2], 'sharding': f'{args.batch_structures} structures per GPU, one per stream slot, '
-                                                              'no collective; H2D + kernels + D2H of every structure inside the timed region'}
+                             'seconds': batch[2], 'structures_per_launch': args.batch_pack,
+                             'sharding': f'{args.batch_structures} structures per GPU, {args.batch_pack} per launch sequence (one DMA per '
+                                         'structure, concatenated on the device: arp_upload_atoms_batch), 6 stream slots, no collective; H2D + '
+                                         'kernels + sort + compact D2H of every structure inside the timed region'}
         if not args.no_cpu:
             kd = kdtree_leg(soa, 5.0)
             if kd:
@@ -486,8 +488,9 @@ def main():
     ap.add_argument('--impl', choices=('ours', 'reference'), default='ours')
     ap.add_argument('--atoms', type=int, default=100_000)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
-    ap.add_argument('--batch-structures', type=int, default=128, help='structures per GPU of the PDB-batch leg (0: skip)')
+    ap.add_argument('--batch-structures', type=int, default=768, help='structures per GPU of the PDB-batch leg (0: skip)')
     ap.add_argument('--batch-atoms', type=int, default=20_000)
+    ap.add_argument('--batch-pack', type=int, default=16, help='structures per launch sequence of the PDB-batch leg')
     ap.add_argument('--large-atoms', type=int, default=1_000_000, help='size of the roofline.large leg (0: skip)')
     args = ap.parse_args()
     if args.impl == 'reference':

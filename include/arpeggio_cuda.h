@@ -292,6 +292,11 @@ int  arp_host_free(void* ptr);
  * the predicates utils.is_hbond/is_weak_hbond/is_halogen_weak_hbond/is_xbond
  * (utils.py:73-179) and utils.get_angle (utils.py:696-745).                  */
 int  arp_upload_atoms(arp_ctx* ctx, const arp_atoms* atoms);     /* async H2D */
+/* A batch of independent structures as they are -- one arp_atoms each (n_structures <= 1), indices local to the
+   structure, radius tables of their own: every structure travels with its own DMA(s) and the DEVICE concatenates
+   them (residue / bond / hydrogen indices rebased, radius classes merged), so that the batch runs as one launch
+   sequence.  Atom indices of the results are global: structure s owns [sum of n_atoms before s, + n_atoms). */
+int  arp_upload_atoms_batch(arp_ctx* ctx, const arp_atoms* const* parts, int32_t n_parts);
 int  arp_pairs_run(arp_ctx* ctx, uint64_t* n_pairs);             /* kernels; returns the record count */
 int  arp_pairs_fetch(arp_ctx* ctx, arp_pair* dst, uint64_t cap, int sorted); /* D2H; sorted!=0: (i,j) ascending */
 int  arp_pairs_device_ptr(arp_ctx* ctx, const arp_pair** dptr);  /* device pointer of the record stream */

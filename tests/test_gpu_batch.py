@@ -42,3 +42,42 @@ def test_batch_runner_compact_stream(engine):
                 exp = exp.copy()
                 exp['dist'] = 0
             util.assert_records_equal(got[i], exp, f'structure {i} with_dist={with_dist}')
+
+
+def _local(cp):
+    rec = cp.to_records()
+    rec['i'] += 0                      # rows are local already (row_off is rebased); j is batch-global
+    rec['j'] -= cp.atom_base
+    return rec
+
+
+def test_device_packed_batches(engine):
+    """arp_upload_atoms_batch: structures with their own residue numbering, bond / hydrogen tables and radius tables
+    (some sharing classes, some not, one without bonds, one without hydrogens, an empty one) are concatenated on the
+    device; every structure's stream equals its stand-alone oracle stream."""
+    p = arp_params.make_params()
+    engine.set_params(p)
+    soas = [synth.cloud_featured(n, seed=90 + k, bonds=(k != 2)) for k, n in enumerate((900, 4000, 1500, 1, 2500, 7000))]
+    soas[3] = synth.cloud_featured(5, seed=99)
+    # another radius table for one structure (reordered classes + a new one) and no hydrogens for another
+    import dataclasses
+    perm = np.array([5, 3, 0, 1, 2, 4])
+    soas[1] = dataclasses.replace(soas[1], vdw=np.append(soas[1].vdw[perm], 2.3), cov=np.append(soas[1].cov[perm], 1.4),
+                                  rad_class=np.argsort(perm)[soas[1].rad_class].astype(np.uint16))
+    soas[4] = dataclasses.replace(soas[4], h_off=None, h_xyz=None)
+    exp = [oracle.pairs(s, p) for s in soas]
+    off = engine.upload_atoms_batch(soas)
+    engine.run_pairs_async()
+    cp = engine.fetch_pairs_compact(with_dist=True)
+    assert cp.n == sum(e.shape[0] for e in exp)
+    for k, e in enumerate(exp):
+        util.assert_records_equal(_local(cp.structure(int(off[k]), int(off[k + 1]))), e, f'packed structure {k}')
+    # the same through the batch runner, groups of 4 and of 3 (last group short), 2 slots
+    got = {}
+    with BatchRunner(device=engine.device, slots=2, params=p) as runner:
+        for pack in (4, 3):
+            got.clear()
+            counts, _ = runner.run(soas, consume=lambda i, part: got.__setitem__(i, _local(part)), compact=True, with_dist=True, pack=pack)
+            for k, e in enumerate(exp):
+                assert counts[k] == e.shape[0]
+                util.assert_records_equal(got[k], e, f'pack={pack} structure {k}')

@@ -3,7 +3,11 @@
  * parameters, uploads, the atom-atom run/fetch calls and the benchmark hooks.
  * The plane entry points live in arp_planes.cu.
  */
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
 #include <math.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <new>
 #include <vector>
@@ -347,10 +351,49 @@ int arp_set_params(arp_ctx* c, const arp_params* p)
     return ARP_OK;
 }
 
+/* CPUs local to the calling thread's current CUDA device (its PCI function's local_cpulist in sysfs), or an empty set */
+static bool device_local_cpus(cpu_set_t* set)
+{
+    CPU_ZERO(set);
+    int dev = 0;
+    char bdf[32] = {0}, path[128], line[4096];
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bdf, sizeof bdf, dev) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    for (char* p = bdf; *p; ++p) if (*p >= 'A' && *p <= 'F') *p += 'a' - 'A';
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bdf);
+    FILE* f = fopen(path, "r");
+    if (!f) return false;
+    const bool ok = fgets(line, sizeof line, f) != nullptr;
+    fclose(f);
+    if (!ok) return false;
+    int n = 0;
+    for (char* p = line; *p && *p != '\n'; ) {                  /* "0-15,32-47" */
+        char* end = nullptr;
+        long lo = strtol(p, &end, 10), hi = lo;
+        if (end == p) break;
+        p = end;
+        if (*p == '-') { hi = strtol(p + 1, &end, 10); if (end == p + 1) break; p = end; }
+        for (long c = lo; c <= hi && c < CPU_SETSIZE; ++c) if (c >= 0) { CPU_SET((int)c, set); ++n; }
+        if (*p == ',') ++p;
+    }
+    return n > 0;
+}
+
 int arp_host_alloc(void** ptr, uint64_t bytes)
 {
     if (!ptr) return ARP_E_INVALID_ARG;
+    /* ARPEGGIO_NUMA_PIN=1: the buffer is the target of the device's DMA, so place it on the NUMA node of the device:
+       pages land where the allocating thread runs (first touch), so the thread is confined to the device-local CPUs
+       for the duration of the allocation and released again.  Off by default: on the boxes measured (8 GPUs behind
+       ONE NUMA node, profiles/README.md round 2) it changes nothing -- the end-to-end figures stop scaling on the
+       shared host PCIe / memory fabric, which the `pcie` probe of bench.py records. */
+    cpu_set_t before, local, both;
+    bool confined = false;
+    if (getenv("ARPEGGIO_NUMA_PIN") && sched_getaffinity(0, sizeof before, &before) == 0 && device_local_cpus(&local)) {
+        CPU_AND(&both, &before, &local);
+        if (CPU_COUNT(&both) > 0 && !CPU_EQUAL(&both, &before)) confined = sched_setaffinity(0, sizeof both, &both) == 0;
+    }
     cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 16);
+    if (confined) sched_setaffinity(0, sizeof before, &before);
     if (e != cudaSuccess) { (void)cudaGetLastError(); *ptr = nullptr; return e == cudaErrorMemoryAllocation ? ARP_E_OOM : ARP_E_CUDA; }
     return ARP_OK;
 }

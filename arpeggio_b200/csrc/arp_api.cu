@@ -301,6 +301,7 @@ int arp_create(int device, arp_ctx** out)
     }
     memset(c->h_meta, 0, sizeof(RunMeta));
     if (getenv("ARPEGGIO_NO_PLANE_GRID")) c->use_plane_grid = 0;     /* A-B knob: plain double loops for the plane terms */
+    if (getenv("ARPEGGIO_NO_WITHIN_GRID")) c->use_within_grid = 0;    /* A-B knob: binding-site flags by the double loop */
     if (getenv("ARPEGGIO_NO_PDL")) c->use_pdl = 0;                   /* A-B knob: plain stream-ordered launches */
     if (getenv("ARPEGGIO_NO_FUSED_GRID")) c->use_fused_grid = 0;
     if (getenv("ARPEGGIO_TILES")) c->use_tiles = 1;                                     /* A-B knob: the fused tile kernel instead of k_search + k_classify */
@@ -887,7 +888,7 @@ int arp_flag_within(arp_ctx* c, double radius, uint8_t* flags_out, uint64_t cap)
     ARP_REQUIRE(c, flags_out != nullptr, ARP_E_INVALID_ARG, "flags_out is NULL");
     ARP_TRY(arp_bind(c));
     ARP_TRY(arp_flag_within_run(c, radius));
-    const uint8_t* d = c->within.as<uint8_t>() + 16 + (size_t)c->N * 4;
+    const uint8_t* d = c->within.as<uint8_t>() + c->within_flags_off;
     ARP_CUDA(c, cudaMemcpyAsync(flags_out, d, (size_t)c->N, cudaMemcpyDeviceToHost, c->stream));
     ARP_CUDA(c, cudaStreamSynchronize(c->stream));
     return ARP_OK;

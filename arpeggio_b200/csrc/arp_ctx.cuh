@@ -184,6 +184,8 @@ struct arp_ctx {
 
     /* binding-site flags */
     DBuf within;
+    size_t within_flags_off = 0;  /* where arp_flag_within_run left the flags inside `within` */
+    int use_within_grid = 1;      /* binding-site flags through a cell grid for large inputs (ARPEGGIO_NO_WITHIN_GRID: double loop) */
 
     /* ring -> nearest atom scratch (coordinates, centroids, results) */
     DBuf ring_scratch;

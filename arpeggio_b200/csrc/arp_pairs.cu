@@ -1856,14 +1856,166 @@ __global__ void __launch_bounds__(256) k_within(int N, int S, const float* __res
     if (live) flags[i] = flag ? 1 : 0;
 }
 
+/* ---- the same through a cell grid (large inputs) -------------------------------------------------
+ * The double loop above costs N x n_sel tests; for a large selection (a chain, several ligands) the selected
+ * atoms are binned into cells of edge >= radius instead and every other atom visits the 27 cells around it.
+ * Cell coordinates are clamped to the grid (monotone, so two atoms within one edge of each other always land in
+ * neighbouring cells, whatever the box); a batch shares one grid, the structure index travels with the point. */
+struct WithinGrid {
+    double ox, oy, oz, inv_w;
+    int dx, dy, dz, ncell;
+};
+
+__device__ __forceinline__ void wg_make(const unsigned* __restrict__ bb, int n, double radius, WithinGrid& g)
+{
+    double mn[3], mx[3], amax = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        const unsigned lo = bb[k], hi = bb[3 + k];
+        mn[k] = hi ? (double)ord2f(~lo) : 0.0;
+        mx[k] = hi ? (double)ord2f(hi) : 0.0;
+        amax = fmax(amax, fmax(fabs(mn[k]), fabs(mx[k])));
+    }
+    double w = (radius > 1e-3 ? radius * (1.0 + 1e-6) + 1e-6 : 1e-3) + 2e-16 * amax;
+    long long d[3];
+    for (;;) {
+        for (int k = 0; k < 3; ++k) d[k] = (long long)floor((mx[k] - mn[k]) / w) + 1;
+        if ((double)d[0] * (double)d[1] * (double)d[2] <= 4.0 * (double)n + 64.0) break;
+        w *= 1.5;
+    }
+    g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2]; g.inv_w = 1.0 / w;
+    g.dx = (int)d[0]; g.dy = (int)d[1]; g.dz = (int)d[2]; g.ncell = g.dx * g.dy * g.dz;
+}
+
+__global__ void __launch_bounds__(256) k_wg_bbox(int N, const float* __restrict__ xyz, unsigned* __restrict__ bbox)
+{
+    __shared__ unsigned s_v[8][6];
+    unsigned v[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
+        if (fabsf(x) < 3e38f && fabsf(y) < 3e38f && fabsf(z) < 3e38f) {                 /* finite atoms only */
+            const unsigned ox = f2ord(x), oy = f2ord(y), oz = f2ord(z);
+            v[0] = max(v[0], ~ox); v[1] = max(v[1], ~oy); v[2] = max(v[2], ~oz);
+            v[3] = max(v[3], ox); v[4] = max(v[4], oy); v[5] = max(v[5], oz);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        v[k] = __reduce_max_sync(FULL, v[k]);
+        if ((threadIdx.x & 31) == 0) s_v[threadIdx.x >> 5][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        unsigned m = 0;
+        for (int w = 0; w < 8; ++w) m = max(m, s_v[w][threadIdx.x]);
+        if (m) atomicMax(&bbox[threadIdx.x], m);
+    }
+}
+
+/* binning of the selected atoms: cell + rank (count pass), then (x, y, z, structure) into cell order */
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_wg_bin(int N, int S, const float* __restrict__ xyz, const uint32_t* __restrict__ feat,
+                                                const int* __restrict__ struct_off, const unsigned* __restrict__ bbox, double radius,
+                                                int* __restrict__ cell_cnt, const int* __restrict__ cell_start,
+                                                int* __restrict__ cell_of, int* __restrict__ rank, float4* __restrict__ spos,
+                                                unsigned* __restrict__ n_cells)
+{
+    __shared__ WithinGrid s_g;
+    if (threadIdx.x == 0) {
+        wg_make(bbox, N, radius, s_g);
+        if (!SCATTER && blockIdx.x == 0) *n_cells = (unsigned)s_g.ncell;
+    }
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        if (!(feat[i] & ARP_F_IN_SELECTION)) continue;
+        const float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
+        if (!SCATTER) {
+            const int c = (cell_coord((double)z, s_g.oz, s_g.inv_w, s_g.dz) * s_g.dy + cell_coord((double)y, s_g.oy, s_g.inv_w, s_g.dy)) * s_g.dx +
+                          cell_coord((double)x, s_g.ox, s_g.inv_w, s_g.dx);
+            cell_of[i] = c;
+            rank[i] = atomicAdd(&cell_cnt[c], 1);
+        } else {
+            spos[cell_start[cell_of[i]] + rank[i]] = make_float4(x, y, z, __int_as_float(struct_of(struct_off, S, i)));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_wg_query(int N, int S, const float* __restrict__ xyz, const uint32_t* __restrict__ feat,
+                                                  const int* __restrict__ struct_off, const unsigned* __restrict__ bbox, double radius,
+                                                  const int* __restrict__ cell_start, const float4* __restrict__ spos,
+                                                  uint8_t* __restrict__ flags)
+{
+    __shared__ WithinGrid s_g;
+    if (threadIdx.x == 0) wg_make(bbox, N, radius, s_g);
+    __syncthreads();
+    const double r2 = radius * radius;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        bool flag = (feat[i] & ARP_F_IN_SELECTION) != 0;
+        if (!flag) {
+            const float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
+            const int s = struct_of(struct_off, S, i);
+            const int cx = cell_coord((double)x, s_g.ox, s_g.inv_w, s_g.dx), cy = cell_coord((double)y, s_g.oy, s_g.inv_w, s_g.dy),
+                      cz = cell_coord((double)z, s_g.oz, s_g.inv_w, s_g.dz);
+            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, s_g.dx - 1);
+            for (int k = 0; k < 9 && !flag; ++k) {
+                const int yy = cy + k % 3 - 1, zz = cz + k / 3 - 1;
+                if (yy < 0 || yy >= s_g.dy || zz < 0 || zz >= s_g.dz) continue;
+                const int row = (zz * s_g.dy + yy) * s_g.dx;
+                for (int q = cell_start[row + x0], e = cell_start[row + x1 + 1]; q < e; ++q) {
+                    const float4 p = spos[q];
+                    if (__float_as_int(p.w) == s && kd_within(p.x, p.y, p.z, x, y, z, r2)) { flag = true; break; }
+                }
+            }
+        }
+        flags[i] = flag ? 1 : 0;
+    }
+}
+
+#ifndef WITHIN_GRID_MIN_ATOMS
+#define WITHIN_GRID_MIN_ATOMS 20000
+#endif
+
 int arp_flag_within_run(arp_ctx* c, double radius)
 {
     const int N = c->N;
+    if (N >= WITHIN_GRID_MIN_ATOMS && c->use_within_grid) {
+        /* zero region: bbox | n_cells | ticket | cell_cnt | scan state ; then cell_start, cell_of, rank, spos, flags */
+        const size_t cells = 4 * (size_t)N + 66;
+        const size_t tiles = (cells + ARP_SCAN_TILE - 1) / ARP_SCAN_TILE + 1;
+        const size_t o_cnt = 256, o_state = align_up(o_cnt + cells * 4, 256), zero_bytes = align_up(o_state + tiles * 8, 256);
+        const size_t o_start = zero_bytes, o_cellof = align_up(o_start + cells * 4, 256), o_rank = align_up(o_cellof + (size_t)N * 4, 256);
+        const size_t o_spos = align_up(o_rank + (size_t)N * 4, 256), o_flags = align_up(o_spos + (size_t)N * 16, 256);
+        ARP_TRY(dbuf_reserve(c, c->within, o_flags + (size_t)N));
+        char* z = c->within.as<char>();
+        unsigned* bbox = (unsigned*)z; unsigned* n_cells = (unsigned*)(z + 64); unsigned* ticket = (unsigned*)(z + 128);
+        int* cell_cnt = (int*)(z + o_cnt); unsigned long long* state = (unsigned long long*)(z + o_state);
+        int* cell_start = (int*)(z + o_start); int* cell_of = (int*)(z + o_cellof); int* rank = (int*)(z + o_rank);
+        float4* spos = (float4*)(z + o_spos);
+        c->within_flags_off = o_flags;
+        const int* so = c->S > 1 ? c->struct_off.as<int>() : nullptr;
+        ARP_CUDA(c, cudaMemsetAsync(z, 0, zero_bytes, c->stream));
+        unsigned blocks = (unsigned)((N + 255) / 256);
+        const unsigned cap = (unsigned)c->sm_count * 8;
+        blocks = blocks < cap ? blocks : cap;
+        k_wg_bbox<<<blocks, 256, 0, c->stream>>>(N, c->xyz.as<float>(), bbox);
+        ARP_LAUNCHED(c);
+        k_wg_bin<false><<<blocks, 256, 0, c->stream>>>(N, c->S, c->xyz.as<float>(), c->feat.as<uint32_t>(), so, bbox, radius, cell_cnt,
+                                                       nullptr, cell_of, rank, nullptr, n_cells);
+        ARP_LAUNCHED(c);
+        ARP_TRY(arp_scan_exclusive(c, cell_cnt, cell_start, state, ticket, n_cells, 1, cells));
+        k_wg_bin<true><<<blocks, 256, 0, c->stream>>>(N, c->S, c->xyz.as<float>(), c->feat.as<uint32_t>(), so, bbox, radius, nullptr,
+                                                      cell_start, cell_of, rank, spos, nullptr);
+        ARP_LAUNCHED(c);
+        k_wg_query<<<blocks, 256, 0, c->stream>>>(N, c->S, c->xyz.as<float>(), c->feat.as<uint32_t>(), so, bbox, radius, cell_start, spos,
+                                                  (uint8_t*)(z + o_flags));
+        ARP_LAUNCHED(c);
+        return ARP_OK;
+    }
     ARP_TRY(dbuf_reserve(c, c->within, (size_t)N * 5 + 64));
     char* base = c->within.as<char>();
     int* n_sel = (int*)base;
     int* sel = (int*)(base + 16);
     uint8_t* flags = (uint8_t*)(base + 16 + (size_t)N * 4);
+    c->within_flags_off = 16 + (size_t)N * 4;
     ARP_CUDA(c, cudaMemsetAsync(n_sel, 0, 16, c->stream));
     if (N == 0) return ARP_OK;
     unsigned blocks = (unsigned)((N + 255) / 256);

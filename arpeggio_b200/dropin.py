@@ -172,6 +172,8 @@ class CudaContactsMixin:
     cuda_device = 0
     cuda_engine = None          # set to a private ContactEngine to avoid the shared one
     cuda_atom_sifts = True      # reproduce the per-atom / per-residue SIFt side effects of the loops
+    cuda_make_selection = True  # False: keep the host class's own _make_selection (the reference's list(set) order of
+                                # selection_plus depends on its KD-tree pair order, INTEGRATION.md "differences" 3)
     cuda_integer_sifts = False  # opt in to atom.integer_sift* evaluated in (bgn, end)-sorted loop order: the reference's
                                 # value depends on Bio.PDB's KD-tree traversal order (utils.py:233), see apply_atom_sifts
     cuda_lazy_contacts = False  # atom_contacts as a LazyAtomContacts sequence instead of a list of namedtuples
@@ -235,6 +237,9 @@ class CudaContactsMixin:
         import logging
         import sys
         from .soa import AtomSoA
+        if not self.cuda_make_selection:
+            self.cuda_invalidate()
+            return super()._make_selection(selections)
         entity = list(self.s_atoms)
         selection = entity if not selections else self._cuda_parse_selection(selections, entity)
         if not selection:

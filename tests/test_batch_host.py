@@ -62,3 +62,21 @@ def test_world_size_2_gloo_reduction(tmp_path):
     assert float(line[1]) == 2.0
     assert float(line[2]) == 13 * 100 * sum(range(1, 41))
     assert int(line[3]) == 40
+
+
+def test_make_selection_can_stay_with_the_host_class():
+    """cuda_make_selection = False: the mixin hands _make_selection to the class it is mixed into (the reference's own
+    list(set(...)) construction, whose order depends on its KD-tree pair order) and forgets its packed image."""
+    from arpeggio_b200.dropin import CudaContactsMixin
+
+    class Base:
+        def _make_selection(self, selections):
+            self.seen = list(selections)
+
+    class Host(CudaContactsMixin, Base):
+        cuda_make_selection = False
+
+    h = Host()
+    h._cuda_pack_cache = ('stale', None)
+    h._make_selection(['/A/508/'])
+    assert h.seen == ['/A/508/'] and h._cuda_pack_cache is None and h._cuda_pack_version == 1

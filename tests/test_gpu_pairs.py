@@ -317,6 +317,34 @@ def test_flag_within(engine):
         assert np.array_equal(engine.flag_within(radius), oracle.flag_within(soa, radius)), radius
 
 
+def test_flag_within_grid_path(engine, monkeypatch):
+    """Large inputs take the cell-grid variant (>= 20 000 atoms): a big selection (a 'chain' of 12 000 atoms), a batch of
+    structures that overlap in space (flags never cross structures), atoms far outside the bulk, a radius larger than
+    the box; the double loop (knob) gives the same flags."""
+    from arpeggio_b200.engine import ContactEngine
+    soa = synth.cloud_featured(60_000, seed=12)
+    soa.feat &= ~np.uint32(abi.F_IN_SELECTION)
+    soa.feat[5_000:17_000] |= abi.F_IN_SELECTION
+    soa.xyz[:50] += np.float32(400.0)                   # outliers: clamped into border cells
+    soa.xyz[59_000:59_020] -= np.float32(250.0)
+    soa.feat[59_010] |= abi.F_IN_SELECTION
+    engine.upload_atoms(soa)
+    exp = {r: oracle.flag_within(soa, r) for r in (6.0, 0.0, 2.5, 300.0)}
+    for r, e in exp.items():
+        assert np.array_equal(engine.flag_within(r), e), r
+    parts = [synth.cloud_featured(n, seed=40 + k) for k, n in enumerate((9_000, 14_000, 30, 8_000))]
+    for k, part in enumerate(parts):
+        part.feat &= ~np.uint32(abi.F_IN_SELECTION)
+        part.feat[k * 7:k * 7 + 40] |= abi.F_IN_SELECTION
+    batch = AtomSoA.concat(parts)
+    engine.upload_atoms(batch)
+    assert np.array_equal(engine.flag_within(6.0), oracle.flag_within(batch, 6.0))
+    monkeypatch.setenv('ARPEGGIO_NO_WITHIN_GRID', '1')
+    with ContactEngine(engine.device) as e2:
+        e2.upload_atoms(soa)
+        assert np.array_equal(e2.flag_within(6.0), exp[6.0])
+
+
 def test_errors_are_reported(engine):
     from arpeggio_b200._lib import ArpeggioCudaError
     from arpeggio_b200.engine import ContactEngine

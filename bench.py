@@ -64,9 +64,11 @@ def ncu_traffic(atoms):
     try:
         with open(os.path.join(ROOT, 'profiles', 'k_pairs_traffic.json')) as fh:
             t = json.load(fh)
-        return float(t['dram_bytes_per_launch']) if int(t.get('atoms', 0)) == atoms else None
+        if int(t.get('atoms', 0)) != atoms:
+            return None, None
+        return float(t['dram_bytes_per_launch']), (t.get('unflushed') or {}).get('l2_bytes_per_step')
     except Exception:
-        return None
+        return None, None
 
 
 # ---------------------------------------------------------------------------------------------
@@ -433,7 +435,9 @@ def run_ours(args):
             'roofline': {'bound': 'hbm', 'kernel': 'the whole step: k_grid_reg + k_search + k_classify + k_hscan',
                          'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'frac_of_nominal_8tbs': achieved / 8000.0,
-                         'traffic': ncu_traffic(args.atoms), 'algorithmic_bytes': int(alg_bytes), 'kernel_ms': ms_max,
+                         'traffic': ncu_traffic(args.atoms)[0], 'traffic_l2_bytes': ncu_traffic(args.atoms)[1],
+                         'traffic_source': 'profiles/k_pairs_traffic.json: ncu captures of this build (tools/prof.sh); DRAM bytes with caches flushed per kernel, L2 bytes with caches left alone',
+                         'algorithmic_bytes': int(alg_bytes), 'kernel_ms': ms_max,
                          'pair_kernels': {'kernel': 'k_search + k_classify + k_hscan, one event before and one after',
                                           'kernel_ms': ms_pair, 'achieved': achieved_pairs, 'frac': achieved_pairs / peak},
                          'grid_build_ms': st['ms_grid'],

@@ -26,12 +26,38 @@ for r in rows[2:]:
     rd = float(d['dram__bytes_read.sum']) * scale[rows[1][hdr.index('dram__bytes_read.sum')]]
     wr = float(d['dram__bytes_write.sum']) * scale[rows[1][hdr.index('dram__bytes_write.sum')]]
     detail[name] = {'read': int(rd), 'write': int(wr), 'us': float(d['gpu__time_duration.sum'])}
-pair = [k for k in detail if k.split('<')[0] in ('k_search', 'k_classify', 'k_hscan')]
-json.dump({'atoms': 100000, 'dram_bytes_per_launch': sum(detail[k]['read'] + detail[k]['write'] for k in pair),
-           'kernels': pair, 'detail': detail,
-           'source': f'ncu --set full --clock-control none (caches flushed before every replayed kernel, so lists that stay in L2 '
-                     f'between the kernels of a real step are read from DRAM here), capture {tag}, profiles/ncu_pair_kernels_{label}.txt'},
-          open(os.path.join(P, 'k_pairs_traffic.json'), 'w'), indent=1)
+# the step's traffic with the caches left alone between the kernels (tools/prof.sh, third capture): per kernel the mean over
+# the captured steps of DRAM read + write bytes and of the bytes through L2
+traffic, tcsv = {}, os.path.join(G, f'traffic_{tag}.csv')
+if os.path.exists(tcsv):
+    trows = [r for r in csv.reader(open(tcsv)) if len(r) > 6]
+    th = trows[0]
+    acc = {}
+    for r in trows[1:]:
+        d = dict(zip(th, r))
+        if not d.get('ID', '').isdigit():
+            continue
+        name = d['Kernel Name'].split('(')[0].replace('void ', '')
+        unit = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-3, 'us': 1, 'usecond': 1, 'nsecond': 1e-3, 'ms': 1e3}.get(d['Metric Unit'], 1)
+        acc.setdefault(name, {}).setdefault(d['Metric Name'], []).append(float(d['Metric Value'].replace(',', '')) * unit)
+    for name, m in acc.items():
+        mean = lambda k: sum(m.get(k, [0])) / max(len(m.get(k, [0])), 1)
+        traffic[name] = {'dram_read': int(mean('dram__bytes_read.sum')), 'dram_write': int(mean('dram__bytes_write.sum')),
+                         'l2_bytes': int(mean('lts__t_bytes.sum')), 'us': mean('gpu__time_duration.sum'), 'launches': len(m.get('gpu__time_duration.sum', []))}
+step = [k for k in (traffic or detail) if k.split('<')[0] in ('k_grid_reg', 'k_search', 'k_classify', 'k_hscan')]
+flushed = sum(detail[k]['read'] + detail[k]['write'] for k in detail if k.split('<')[0] in ('k_grid_reg', 'k_search', 'k_classify', 'k_hscan'))
+out = {'atoms': 100000, 'dram_bytes_per_launch': flushed, 'kernels': step,
+       'what': 'dram_bytes_per_launch: dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of ONE step from the ncu --set full capture '
+               f'(prof_{tag}, caches flushed before every replayed kernel: the inputs come from DRAM as in the benchmark, which flushes L2 between '
+               'steps, but so do the candidate list and the work list, which a real step finds in L2; the 20 MB of records are still in L2 when '
+               'the kernel ends and do not show as DRAM writes).  unflushed: the same kernels with --cache-control none over repeated steps on '
+               'the same input -- inputs and lists L2-resident (126 MB L2), so DRAM traffic all but disappears and l2_bytes shows what the '
+               'kernels really move through L2 per step',
+       'flushed_capture': detail}
+if traffic:
+    out['unflushed'] = {'dram_bytes_per_step': sum(traffic[k]['dram_read'] + traffic[k]['dram_write'] for k in step),
+                        'l2_bytes_per_step': sum(traffic[k]['l2_bytes'] for k in step), 'per_kernel': traffic}
+json.dump(out, open(os.path.join(P, 'k_pairs_traffic.json'), 'w'), indent=1)
 for k in detail:
     base = k.split('<')[0]
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'ncu_lines.py'), rep, base, '45'], capture_output=True, text=True).stdout

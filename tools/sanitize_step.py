@@ -20,6 +20,19 @@ with ContactEngine(0, p) as eng:
         rings, amides = synth.plane_set(64, 256, n_atoms=n, seed=9)
         eng.upload_planes(rings, amides)
         eng.ring_ring(); eng.atom_ring(); eng.amide_amide(); eng.amide_ring()
-        print(n, 'atoms', rec.shape[0], 'records')
+        got = eng.planes_all()                                  # the grid path, all four terms in one sequence
+        print(n, 'atoms', rec.shape[0], 'records;', {k: v.shape[0] for k, v in got.items()}, 'plane records')
+        eng.run_pairs_async()                                   # compact sorted stream + distances on demand
+        cp = eng.fetch_pairs_compact(with_dist=False)
+        eng.fetch_pairs_dist(cp.n)
     batch = AtomSoA.concat([synth.cloud_featured(k, seed=40 + k) for k in (700, 0, 5, 1500)])
     print('batch', eng.pairs(batch).shape[0], 'records')
+    parts = [synth.cloud_featured(k, seed=60 + k) for k in (900, 5, 2500, 1200)]
+    off = eng.upload_atoms_batch(parts)                         # device-side concatenation
+    eng.run_pairs_async()
+    print('device-packed batch', eng.fetch_pairs_compact(with_dist=True).n, 'records', off.tolist())
+    big = synth.cloud_featured(24000, seed=77)                  # binding-site flags through the cell grid (>= 20 000 atoms)
+    eng.upload_atoms(big)
+    print('flag_within (grid)', int(eng.flag_within(6.0).sum()), 'atoms flagged')
+if os.environ.get('ARPEGGIO_TILES'):
+    print('the fused tile kernel (k_tiles) ran in place of k_search + k_classify')

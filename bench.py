@@ -358,6 +358,42 @@ def run_ours(args):
     runner.run([host] * 6, check_finite=False, sorted=True)          # warm-up: the sorted 16-byte view has buffers of its own
     _, dt16 = runner.run([host] * e2e_steps, check_finite=False, sorted=True)
     e2e16_s = dt16 / e2e_steps
+    # the same with the float32 distance stream in the transfer (12 bytes per record + 4 per atom)
+    runner.run([host] * 6, check_finite=False, compact=True, with_dist=True)
+    if dist:
+        dist.barrier()
+    _, dtd = runner.run([host] * e2e_steps, check_finite=False, compact=True, with_dist=True)
+    e2e_dist_s = dtd / e2e_steps
+    # resident inputs, steps of THREE contexts (streams) in flight at once: what the device sustains when the launch ramps and
+    # tails of consecutive steps overlap (the per-step figure `value` serialises them); every context holds its own copy of
+    # the structure and of all buffers (3 x 27 MB in flight), rank 0 only
+    pipelined = None
+    if rank == 0:
+        engs = [ContactEngine(device=local, params=p) for _ in range(3)]
+        for e in engs:
+            e.upload_atoms(soa)
+            assert e.run_pairs() == n_pairs
+        reps = max(args.steps, 30)
+
+        def spin(e):
+            for _ in range(reps):
+                e.run_pairs_async()
+            e.sync()
+
+        for e in engs:
+            spin(e)
+        ths = [threading.Thread(target=spin, args=(e,)) for e in engs]
+        t0 = time.perf_counter()
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        dtp = time.perf_counter() - t0
+        pipelined = {'value': 3 * reps * n_pairs / dtp, 'unit': UNIT, 'us_per_step': dtp / (3 * reps) * 1e6, 'contexts': 3,
+                     'what': 'inputs resident, three contexts on three streams run the step concurrently, wall clock over all steps, no L2 '
+                             'flush (the three working sets are 81 MB): throughput with the ramps and tails of consecutive steps overlapped'}
+        for e in engs:
+            e.close()
     # what PCIe gives this rank while all ranks copy at once: the same sizes, H2D and D2H concurrently
     if dist:
         dist.barrier()
@@ -391,13 +427,13 @@ def run_ours(args):
 
     # ---- aggregate over ranks: slowest rank's time, total pairs ------------------------------
     ms_pair = st['ms_pairs']                # the three pair kernels back to back, one event before and one after
-    tot_pairs, ms_max, e2e_max, e2e_serial_max, e2e16_max = float(n_pairs), ms_step, e2e_s, e2e_serial_s, e2e16_s
+    tot_pairs, ms_max, e2e_max, e2e_serial_max, e2e16_max, e2e_dist_max = float(n_pairs), ms_step, e2e_s, e2e_serial_s, e2e16_s, e2e_dist_s
     pcie_min = dict(pcie)
     if dist:
         import torch
-        t = torch.tensor([ms_step, e2e_s, e2e_serial_s, batch[2] if batch else 0.0, e2e16_s, -pcie['h2d_gbs'], -pcie['d2h_gbs']], dtype=torch.float64)
+        t = torch.tensor([ms_step, e2e_s, e2e_serial_s, batch[2] if batch else 0.0, e2e16_s, -pcie['h2d_gbs'], -pcie['d2h_gbs'], e2e_dist_s], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e16_max = float(t[4])
+        e2e16_max, e2e_dist_max = float(t[4]), float(t[7])
         pcie_min = {'h2d_gbs': -float(t[5]), 'd2h_gbs': -float(t[6])}
         s = torch.tensor([float(n_pairs), batch[0] if batch else 0.0, batch[1] if batch else 0.0], dtype=torch.float64)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
@@ -424,12 +460,15 @@ def run_ours(args):
                     'api': 'BatchRunner.run(compact=True), 6 stream slots, one pinned host block per structure, one wait per structure',
                     'serial_value': tot_pairs / e2e_serial_max, 'serial_ms_per_step': e2e_serial_max * 1e3,
                     'serial_api': 'ContactEngine.upload_atoms + run_pairs_async + fetch_pairs_compact, one stream',
+                    'with_distances': {'value': tot_pairs / e2e_dist_max, 'ms_per_step': e2e_dist_max * 1e3, 'd2h_bytes_per_step': d2h_bytes + 4 * int(n_pairs),
+                                       'api': 'BatchRunner.run(compact=True, with_dist=True): the float32 distance stream fetched with the records'},
                     'records16': {'value': tot_pairs / e2e16_max, 'ms_per_step': e2e16_max * 1e3, 'd2h_bytes_per_step': int(16 * n_pairs),
                                   'api': 'BatchRunner.run(sorted=True): 16-byte arp_pair records'},
                     'pcie': dict(pcie_min, what='pinned cudaMemcpyAsync of the step\'s H2D and D2H sizes, both directions at once, '
                                                 'every rank at the same time (min over ranks, GB/s per GPU)',
                                  d2h_floor_ms=d2h_bytes / (pcie_min['d2h_gbs'] * 1e6) if pcie_min['d2h_gbs'] else None,
                                  h2d_floor_ms=in_bytes / (pcie_min['h2d_gbs'] * 1e6) if pcie_min['h2d_gbs'] else None)},
+            'resident_pipelined': pipelined,
             'gpu_launches': int(launches),
             'kernels_per_step': int(per_step),
             'roofline': {'bound': 'hbm', 'kernel': 'the whole step: k_grid_reg + k_search + k_classify + k_hscan',

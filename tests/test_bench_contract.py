@@ -68,6 +68,7 @@ def test_product_arm_prints_the_contract_line():
     assert e['d2h_bytes_per_step'] == 8 * d['config']['pairs_per_structure'] + 4 * (d['config']['atoms_per_gpu'] + 1)
     assert e['records16']['d2h_bytes_per_step'] == 16 * d['config']['pairs_per_structure'] and e['records16']['value'] > 0
     assert e['pcie']['h2d_gbs'] > 1 and e['pcie']['d2h_gbs'] > 1
+    assert 0 < e['with_distances']['value'] <= e['value'] * 1.2 and d['resident_pipelined']['value'] > 0
     rf = d['roofline']
     assert rf['bound'] == 'hbm' and rf['unit'] == 'GB/s' and abs(rf['frac'] - rf['achieved'] / rf['peak']) < 1e-9
     assert rf['algorithmic_bytes'] > 16 * d['config']['pairs_per_structure']

@@ -179,11 +179,13 @@ def test_batch_equals_per_structure(engine):
 
 
 @pytest.mark.parametrize('knob', [None, 'ARPEGGIO_NO_REG_GRID', 'ARPEGGIO_NO_FUSED_GRID', 'ARPEGGIO_NO_PDL',
-                                  'ARPEGGIO_NO_EARLY_CLASSIFY'])
+                                  'ARPEGGIO_NO_EARLY_CLASSIFY', 'ARPEGGIO_TILES'])
 def test_every_grid_build_path(monkeypatch, knob):
     """The cell grid is built by one of three code paths (register-cached cooperative kernel with 1 or 2 atoms
     per thread, cooperative kernel through global memory, five kernels); each must give the oracle's stream for
-    a single structure of either size class and for a small batch."""
+    a single structure of either size class and for a small batch.  ARPEGGIO_TILES: the fused search + classify tile
+    kernel (k_tiles) in place of k_search + k_classify, plus a dense structure (cells with several jobs) and a golden
+    fixture of the reference."""
     from arpeggio_b200.engine import ContactEngine
     if knob:
         monkeypatch.setenv(knob, '1')
@@ -193,9 +195,18 @@ def test_every_grid_build_path(monkeypatch, knob):
              'batch': AtomSoA.concat(parts)}
     if knob == 'ARPEGGIO_NO_PDL':
         del cases['200k']
+    if knob == 'ARPEGGIO_TILES':
+        dense = synth.cloud_featured(4_000, seed=63)
+        dense.xyz[:] = np.round(dense.xyz.astype(np.float64) * 0.45, 3).astype(np.float32)     # ~11x protein density
+        dense.h_xyz[:] = dense.h_xyz * 0.45
+        cases['dense'] = dense
     with ContactEngine(0, p) as eng:
         for name, soa in cases.items():
             util.assert_records_equal(eng.pairs(soa), oracle.pairs(soa, p), f'{knob or "default"} {name}')
+        if knob == 'ARPEGGIO_TILES':
+            g = util.Golden('rich_whole')
+            eng.set_params(g.params)
+            util.assert_records_equal(eng.pairs(g.soa), g.exp_pairs, 'tiles: golden rich_whole')
 
 
 def test_skewed_density_and_odd_sizes():

@@ -330,6 +330,7 @@ void arp_destroy(arp_ctx* c)
     for (int k = 0; k < 5; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     if (c->h_meta) cudaFreeHost(c->h_meta);
     if (c->h_batch) cudaFreeHost(c->h_batch);
+    if (c->ev_batch) cudaEventDestroy(c->ev_batch);
     if (c->stream) cudaStreamDestroy(c->stream);
     (void)cudaGetLastError();
     delete c;
@@ -671,11 +672,15 @@ int arp_upload_atoms_batch(arp_ctx* c, const arp_atoms* const* parts, int32_t n_
     const size_t o_cov = up256(o_vdw + (size_t)(K ? K : 1) * 8), o_cmap = up256(o_cov + (size_t)(K ? K : 1) * 8);
     const size_t small = up256(o_cmap + (cmap.size() ? cmap.size() : 1) * 2);
     if (c->h_batch_cap < small) {
+        if (c->ev_batch) ARP_CUDA(c, cudaEventSynchronize(c->ev_batch));      /* the old image may still be a copy's source */
         if (c->h_batch) cudaFreeHost(c->h_batch);
         c->h_batch = nullptr; c->h_batch_cap = 0;
         ARP_CUDA(c, cudaMallocHost(&c->h_batch, small + small / 2));
         c->h_batch_cap = small + small / 2;
     }
+    /* the pinned image may still be the source of the previous batch's copy: wait for that copy (not for the stream) */
+    if (!c->ev_batch) ARP_CUDA(c, cudaEventCreateWithFlags(&c->ev_batch, cudaEventDisableTiming));
+    else ARP_CUDA(c, cudaEventSynchronize(c->ev_batch));
     char* hb8 = (char*)c->h_batch;
     memcpy(hb8 + o_desc, desc.data(), desc.size() * sizeof(PartDesc));
     memcpy(hb8 + o_soff, soff.data(), soff.size() * 4);
@@ -683,6 +688,7 @@ int arp_upload_atoms_batch(arp_ctx* c, const arp_atoms* const* parts, int32_t n_
     if (!cmap.empty()) memcpy(hb8 + o_cmap, cmap.data(), cmap.size() * 2);
     ARP_TRY(dbuf_reserve(c, c->batch_small, small));
     ARP_CUDA(c, cudaMemcpyAsync(c->batch_small.p, hb8, small, cudaMemcpyHostToDevice, c->stream));
+    ARP_CUDA(c, cudaEventRecord(c->ev_batch, c->stream));
     ARP_TRY(dbuf_reserve(c, c->batch_stage, stage_bytes));
     for (const Copy& q : copies)
         ARP_CUDA(c, cudaMemcpyAsync(c->batch_stage.as<char>() + q.dst, q.src, q.bytes, cudaMemcpyHostToDevice, c->stream));

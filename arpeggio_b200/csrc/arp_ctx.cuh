@@ -123,6 +123,7 @@ struct arp_ctx {
     DBuf batch_stage, batch_small;/* arp_upload_atoms_batch: the structures as uploaded; descriptors, struct_off, merged radius table */
     void* h_batch = nullptr;      /* pinned image of batch_small */
     size_t h_batch_cap = 0;
+    cudaEvent_t ev_batch = nullptr;   /* after the H2D copy of h_batch: the image is free again */
     int has_bonds = 0, has_h = 0, has_xnbr = 0;
     uint64_t input_bytes = 0;
 

@@ -1213,6 +1213,7 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
         __syncwarp();
         /* ---- stages 0 + 1, 32 candidates per round ---- */
         unsigned nsurv = 0, n_items = 0, n_rare = 0;             /* rare items are staged from the back of `items` */
+        unsigned long long o_early = 0;
         uint2 e_next = lane < cnt ? cls_fetch<EARLY>(A, base + lane, final) : make_uint2(0, 0);   /* candidates are fetched one round ahead */
 #pragma unroll 1
         for (unsigned i0 = 0; i0 < cnt; i0 += 32) {
@@ -1242,10 +1243,16 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
             const unsigned slot = nsurv + __popc(mk & lt_mask);
             nsurv += __popc(mk);
             uint32_t work = 0;
+            /* the record cursor is reserved as soon as the tile's last round knows how many pairs survive: the atomic's
+               round trip then runs under the rules of that round instead of in front of the store */
+            if (i0 + 32 >= cnt && lane == 0 && nsurv) o_early = atomicAdd(&A.meta->n_pairs, (unsigned long long)nsurv);
             if (keep) {
                 const int ib = __float_as_int(pa.w), ie = __float_as_int(pb.w);
+                /* atom_bgn's range in the bond table: fetched now, needed at the very end of the rules */
+                int bb0 = 0, bb1 = 0;
+                if (ab.x & ARPK_HAS_BOND) { bb0 = A.side.bond_off[ib]; bb1 = A.side.bond_off[ib + 1]; }
                 uint32_t mask; float dist;
-                rule_classify_core(A.side, P, ib, ie, pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, ab.x, ae.x, &mask, &dist, &work);
+                rule_classify_core(A.side, P, ib, ie, pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, ab.x, ae.x, &mask, &dist, &work, bb0, bb1);
                 rec[slot] = make_int4(ib, ie, (int)mask, __float_as_int(dist));
                 if (work) surv[slot] = make_uint2((unsigned)ib, (unsigned)ie);   /* k_hscan finds donor / acceptor through this: ORIGINAL indices */
             }
@@ -1282,7 +1289,7 @@ __global__ void __launch_bounds__(CLS_WARPS * 32, CLS_MINB) k_classify(ClassifyA
            k_hscan walk a second, different chain of loads. */
         unsigned long long o = 0, ow = 0, owr = 0;
         if (lane == 0) {
-            o = atomicAdd(&A.meta->n_pairs, (unsigned long long)nsurv);
+            o = o_early;
             bulk_store_tile(A.out + o, rec, nsurv * (uint32_t)sizeof(arp_pair));
             if (n_items) ow = atomicAdd(&A.meta->n_work, (unsigned long long)n_items);
             if (n_rare) owr = atomicAdd(&A.meta->n_work_rare, (unsigned long long)n_rare);

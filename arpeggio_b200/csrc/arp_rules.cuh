@@ -506,44 +506,39 @@ ARP_HD bool rule_pair_survives(uint32_t fb, int rb, int pb, int nb, uint32_t fe,
  * b = atom_bgn (lower list index), e = atom_end; coordinates and packed words are passed in registers.
  * X = wb & pairswap(we): bit 2k = "p on bgn, q on end", bit 2k + 1 = "q on bgn, p on end".
  */
+/* bb0 / bb1: atom_bgn's range in the bond CSR when the caller has already fetched it (bb0 < 0: fetch it here).  The bond
+   walk (two dependent loads, only for atoms that have bonds) comes LAST: everything that does not depend on `bonded` is
+   computed first, so that the caller's early loads of the range fly under that arithmetic.  The reference gates the
+   feature rules on `not clash` (interactions.py:786); here they are evaluated on the distance alone and dropped again
+   for a clash, which is the same thing (they have no other effect). */
 ARP_HD void rule_classify_core(const ArpSide& S, const ArpRuleParams& P, int b, int e,
                                float bx, float by, float bz, float ex, float ey, float ez,
-                               uint32_t wb, uint32_t we, uint32_t* mask_out, float* dist_out, uint32_t* work_out)
+                               uint32_t wb, uint32_t we, uint32_t* mask_out, float* dist_out, uint32_t* work_out,
+                               int bb0 = -1, int bb1 = -1)
 {
     const float4 t = S.radtab[(wb & ARPK_RAD_MASK) * (uint32_t)S.K + (we & ARPK_RAD_MASK)];   /* :717-718 narrowed */
     const float t_cov = t.x, t_vdw = t.y, vdwc = t.z;
     const float d = np_dist_f32(bx, by, bz, ex, ey, ez);                           /* :745 */
 
-    bool bonded = false;                                                           /* :750-754 */
-    if (wb & ARPK_HAS_BOND) {           /* only atom_bgn's neighbour list is consulted */
-        for (int k = S.bond_off[b]; k < S.bond_off[b + 1]; ++k)
-            if (S.bond_nbr[k] == e) { bonded = true; break; }
-    }
-    const bool clash = !bonded && d < t_cov;
-    uint32_t m = bonded ? 1u << ARP_SIFT_COVALENT                                  /* :756-757 */
-               : clash ? 1u << ARP_SIFT_CLASH                                      /* :760 */
-               : d < t_vdw ? 1u << ARP_SIFT_VDW_CLASH                              /* :764 */
-               : d <= vdwc ? 1u << ARP_SIFT_VDW                                    /* :768 */
-               : 1u << ARP_SIFT_PROXIMAL;                                          /* :772 */
-
     const uint32_t sw = ((we & ARPK_PAIR_EVEN) << 1) | ((we & ARPK_PAIR_ODD) >> 1);
     const uint32_t X = wb & sw, Y = wb & we;
 #define ARP_XB(n) ((X >> (n)) & 1u)
+    uint32_t m = 0;
     if (d <= P.metal) m |= (ARP_XB(28) | ARP_XB(29)) << ARP_SIFT_METAL;            /* :777-783 */
 
-    uint32_t work = 0;
-    if (!clash && d <= P.dist_max) {                                               /* :786 */
+    uint32_t mf = 0, work = 0;          /* the feature bits and deferred predicates of a pair that is not a clash */
+    if (d <= P.dist_max) {                                                         /* :786 */
         const bool in_vdwc = d <= vdwc;
         /* hbond / polar :791-819 */
         const bool ws_b = (wb & ARPK_WATER) && in_vdwc;
         const bool ws_e = !ws_b && (we & ARPK_WATER) && in_vdwc;
         if (ws_b) {
-            if (we & (ARPK_ACC | ARPK_DON)) m |= (1u << ARP_SIFT_HBOND) | (1u << ARP_SIFT_POLAR);
+            if (we & (ARPK_ACC | ARPK_DON)) mf |= (1u << ARP_SIFT_HBOND) | (1u << ARP_SIFT_POLAR);
         } else if (ws_e) {
-            if (wb & (ARPK_ACC | ARPK_DON)) m |= (1u << ARP_SIFT_HBOND) | (1u << ARP_SIFT_POLAR);
+            if (wb & (ARPK_ACC | ARPK_DON)) mf |= (1u << ARP_SIFT_HBOND) | (1u << ARP_SIFT_POLAR);
         } else if (X & (3u << 18)) {
             work |= ARP_XB(19) ? ARP_HB_NEED_H : (ARP_HB_NEED_H << 2);             /* is_hbond(bgn, end) before (end, bgn) */
-            if (d <= P.hbond_polar) m |= 1u << ARP_SIFT_POLAR;
+            if (d <= P.hbond_polar) mf |= 1u << ARP_SIFT_POLAR;
         }
         /* weak hbond / weak polar: four independent ifs, each ASSIGNS SIFt[6] (:857-886), so only the
            last applicable one decides the bit; any applicable one enables weak polar */
@@ -552,7 +547,7 @@ ARP_HD void rule_classify_core(const ArpSide& S, const ArpRuleParams& P, int b, 
             else if (ARP_XB(30)) work |= ARP_WORK_HAL1;                            /* halogen bgn, donor end */
             else if (ARP_XB(21)) work |= ARP_HB_NEED_W;                            /* is_weak_hbond(bgn, end) */
             else                 work |= ARP_HB_NEED_W << 2;                       /* is_weak_hbond(end, bgn) */
-            if (d <= P.weak_polar) m |= 1u << ARP_SIFT_WEAK_POLAR;
+            if (d <= P.weak_polar) mf |= 1u << ARP_SIFT_WEAK_POLAR;
         }
         /* xbond :889-895 */
         if (in_vdwc && (X & (3u << 22))) work |= ARP_XB(23) ? ARP_WORK_XB0 : ARP_WORK_XB1;
@@ -562,13 +557,28 @@ ARP_HD void rule_classify_core(const ArpSide& S, const ArpRuleParams& P, int b, 
             if (d > S.hlim[we & ARPK_RAD_MASK]) work &= ~(ARP_WORK_SCAN0 | ARP_WORK_HAL0);   /* acceptor / halogen = end */
             if (d > S.hlim[wb & ARPK_RAD_MASK]) work &= ~(ARP_WORK_SCAN1 | ARP_WORK_HAL1);   /* acceptor / halogen = bgn */
         }
-        if (d <= P.ionic) m |= (ARP_XB(24) | ARP_XB(25)) << ARP_SIFT_IONIC;
-        if (d <= P.carbonyl) m |= (ARP_XB(26) | ARP_XB(27)) << ARP_SIFT_CARBONYL;
-        if (d <= P.aromatic) m |= ((Y >> 15) & 1u) << ARP_SIFT_AROMATIC;
-        if (d <= P.hydrophobic) m |= ((Y >> 16) & 1u) << ARP_SIFT_HYDROPHOBIC;
+        if (d <= P.ionic) mf |= (ARP_XB(24) | ARP_XB(25)) << ARP_SIFT_IONIC;
+        if (d <= P.carbonyl) mf |= (ARP_XB(26) | ARP_XB(27)) << ARP_SIFT_CARBONYL;
+        if (d <= P.aromatic) mf |= ((Y >> 15) & 1u) << ARP_SIFT_AROMATIC;
+        if (d <= P.hydrophobic) mf |= ((Y >> 16) & 1u) << ARP_SIFT_HYDROPHOBIC;
     }
 #undef ARP_XB
-    *mask_out = m | (rule_entity_class(wb, we) << ARP_CLASS_SHIFT);
+    m |= rule_entity_class(wb, we) << ARP_CLASS_SHIFT;
+
+    bool bonded = false;                                                           /* :750-754 */
+    if (wb & ARPK_HAS_BOND) {           /* only atom_bgn's neighbour list is consulted */
+        if (bb0 < 0) { bb0 = S.bond_off[b]; bb1 = S.bond_off[b + 1]; }
+        for (int k = bb0; k < bb1; ++k)
+            if (S.bond_nbr[k] == e) { bonded = true; break; }
+    }
+    const bool clash = !bonded && d < t_cov;
+    m |= bonded ? 1u << ARP_SIFT_COVALENT                                          /* :756-757 */
+       : clash ? 1u << ARP_SIFT_CLASH                                              /* :760 */
+       : d < t_vdw ? 1u << ARP_SIFT_VDW_CLASH                                      /* :764 */
+       : d <= vdwc ? 1u << ARP_SIFT_VDW                                            /* :768 */
+       : 1u << ARP_SIFT_PROXIMAL;                                                  /* :772 */
+    if (clash) { mf = 0; work = 0; }                                               /* :786: the feature rules are skipped for a clash */
+    *mask_out = m | mf;
     *dist_out = d;
     *work_out = work;
 }

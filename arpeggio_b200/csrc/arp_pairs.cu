@@ -819,8 +819,10 @@ __device__ __forceinline__ void search_flush(const SearchArgs& A, const uint2* q
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(&A.meta->n_raw, (unsigned long long)n);
     base = __shfl_sync(FULL, base, 0);
+    /* one 64-bit store per entry: k_classify, which may already be reading the list, sees an entry whole or not at all */
     for (unsigned r = lane; r < n; r += 32)
-        if (base + r < A.cap) A.raw[base + r] = q[r];
+        if (base + r < A.cap)
+            reinterpret_cast<unsigned long long*>(A.raw)[base + r] = reinterpret_cast<const unsigned long long*>(q)[r];
     __syncwarp();
 }
 
@@ -1107,16 +1109,20 @@ template <bool EARLY>
 __device__ __forceinline__ uint2 cls_fetch(const ClassifyArgs& A, unsigned long long pos, bool final)
 {
     if (!EARLY) return A.raw[pos];
-    uint2 v = __ldcg(A.raw + pos);
+    /* the entry travels as ONE 64-bit word in both directions (search_flush), so "non-zero" means "in place" */
+    const unsigned long long* p64 = reinterpret_cast<const unsigned long long*>(A.raw) + pos;
+    unsigned long long w = __ldcg(p64);
     if (!final) {
         unsigned spins = 0;
-        while ((v.x | v.y) == 0u) {
-            v = __ldcg(A.raw + pos);
-            if (++spins > (1u << 22)) { atomicOr(&A.meta->fault, CLS_FAULT_HANDOFF); break; }   /* never seen; the host reports it */
+        while (w == 0ull) {
+            w = __ldcg(p64);
+            /* a producer that slow (time slicing, a debugger): flagged, and the host repeats the run with k_classify
+               waiting for k_search (arp_api.cu, pairs_finish) */
+            if (++spins > (1u << 22)) { atomicOr(&A.meta->fault, CLS_FAULT_HANDOFF); break; }
         }
     }
-    A.raw[pos] = make_uint2(0u, 0u);
-    return v;
+    reinterpret_cast<unsigned long long*>(A.raw)[pos] = 0ull;
+    return make_uint2((unsigned)(w & 0xffffffffull), (unsigned)(w >> 32));
 }
 #ifndef CLS_MINB
 #define CLS_MINB 4

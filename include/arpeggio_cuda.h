@@ -291,6 +291,11 @@ int  arp_host_free(void* ptr);
  * InteractionComplex._calculate_atom_contacts (interactions.py:693-936) +
  * the predicates utils.is_hbond/is_weak_hbond/is_halogen_weak_hbond/is_xbond
  * (utils.py:73-179) and utils.get_angle (utils.py:696-745).                  */
+/* Preconditions of arp_upload_atoms / arp_upload_atoms_batch the library does NOT check (a host pass over the arrays would
+   cost as much as the kernels of a small structure; arpeggio_b200.soa.AtomSoA.validate checks them on the Python side):
+   0 <= res_id[i] < n_residues, rad_class[i] < n_rad_classes, 0 <= bond_nbr[k] < n_atoms, res_prev / res_next in
+   [-1, n_residues), bond_off / h_off non-decreasing.  Out-of-range values are out-of-bounds reads on the device.
+   Checked: sizes, NULL arrays, CSR first entries, struct_off.  Non-finite coordinates are legal (ARP_FAULT_NONFINITE). */
 int  arp_upload_atoms(arp_ctx* ctx, const arp_atoms* atoms);     /* async H2D */
 /* A batch of independent structures as they are -- one arp_atoms each (n_structures <= 1), indices local to the
    structure, radius tables of their own: every structure travels with its own DMA(s) and the DEVICE concatenates

@@ -276,12 +276,17 @@ __device__ __forceinline__ int cell_coord(double v, double o, double inv_w, int 
 }
 
 /* ---- phase 3: cell of every atom, rank inside the cell ---------------------------------------- */
-__device__ __forceinline__ void dev_cellid(const float* __restrict__ xyz, const int* __restrict__ struct_off,
+/* Hydrogens take no part in atom-atom contacts (interactions.py:712-713 skips every pair with one before anything else):
+   they get no cell and never enter the cell-sorted arrays, so the pair kernels neither test nor classify them (a
+   hydrogenated structure has half of its atoms and three quarters of its within-cutoff pairs out of the way). */
+__device__ __forceinline__ void dev_cellid(const float* __restrict__ xyz, const uint32_t* __restrict__ feat,
+                                           const int* __restrict__ struct_off,
                                            int S, int N, const StructGeom* __restrict__ geom,
                                            int* __restrict__ cell_cnt, int* __restrict__ cell_of,
                                            int* __restrict__ rank, int i)
 {
     if (i >= N) return;
+    if (feat[i] & ARP_F_ELEM_H) { cell_of[i] = -1; return; }
     int s = struct_of(struct_off, S, i);
     const StructGeom* g = geom + s;
     int cx = cell_coord((double)xyz[3 * (size_t)i + 0], g->ox, g->inv_w, g->dx);
@@ -388,6 +393,7 @@ struct ScatterArgs {
 __device__ __forceinline__ void dev_scatter(const ScatterArgs& A, int N, int i)
 {
     if (i >= N) return;
+    if (A.cell_of[i] < 0) return;                         /* a hydrogen: not in the cell-sorted arrays (dev_cellid) */
     int dst = __ldcg(&A.cell_start[A.cell_of[i]]) + A.rank[i];
     int r = A.res_id[i];
     const uint32_t w = arp_pack_word(A.feat[i], A.res_flags[r], A.rad_class[i],
@@ -469,12 +475,12 @@ __global__ void __launch_bounds__(GRID_THREADS) k_geom(const unsigned* __restric
     dev_geom<GRID_THREADS>(bbox, struct_off, S, N, cutoff, tile_x, geom, meta);
 }
 
-__global__ void __launch_bounds__(GRID_THREADS) k_cellid(const float* __restrict__ xyz, const int* __restrict__ struct_off,
+__global__ void __launch_bounds__(GRID_THREADS) k_cellid(const float* __restrict__ xyz, const uint32_t* __restrict__ feat, const int* __restrict__ struct_off,
                                                          int S, int N, const StructGeom* __restrict__ geom,
                                                          int* __restrict__ cell_cnt, int* __restrict__ cell_of,
                                                          int* __restrict__ rank)
 {
-    dev_cellid(xyz, struct_off, S, N, geom, cell_cnt, cell_of, rank, blockIdx.x * blockDim.x + threadIdx.x);
+    dev_cellid(xyz, feat, struct_off, S, N, geom, cell_cnt, cell_of, rank, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const int* __restrict__ in, int* __restrict__ out,
@@ -532,7 +538,7 @@ __global__ void __launch_bounds__(GRID_THREADS) k_grid_fused(GridArgs G)
     if (blockIdx.x == 0) dev_geom<GRID_THREADS>(G.bbox, G.struct_off, G.S, N, G.cutoff, G.tile_x, G.geom, G.meta);
     grid.sync();
     for (int vb = blockIdx.x; vb < vb_atoms; vb += gridDim.x)
-        dev_cellid(G.sc.xyz, G.struct_off, G.S, N, G.geom, G.cell_cnt, G.cell_of, G.rank, vb * GRID_THREADS + threadIdx.x);
+        dev_cellid(G.sc.xyz, G.sc.feat, G.struct_off, G.S, N, G.geom, G.cell_cnt, G.cell_of, G.rank, vb * GRID_THREADS + threadIdx.x);
     grid.sync();
     {
         const long long n = (long long)__ldcg(&G.meta->n_cells) + 1;
@@ -664,6 +670,7 @@ __global__ void __launch_bounds__(REG_THREADS, 1) k_grid_reg(GridArgs G)
 #pragma unroll
     for (int k = 0; k < APT; ++k) {
         cell[k] = 0; rank[k] = 0;
+        if (st[k] >= 0 && (af[k] & ARP_F_ELEM_H)) st[k] = -1;     /* hydrogens stay out of the cell grid (dev_cellid) */
         if (st[k] >= 0) {
             const StructGeom* g = S == 1 ? &s_geom : G.geom + st[k];
             const int cx = cell_coord((double)x[k], g->ox, g->inv_w, g->dx);
@@ -1579,7 +1586,7 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
             ARP_LAUNCHED(c);
             k_geom<<<1, GRID_THREADS, 0, st>>>(bbox, so, S, N, c->params.interacting_cutoff, c->tile_x, c->geom.as<StructGeom>(), meta);
             ARP_LAUNCHED(c);
-            k_cellid<<<blocks, GRID_THREADS, 0, st>>>(c->xyz.as<float>(), so, S, N, c->geom.as<StructGeom>(), cell_cnt,
+            k_cellid<<<blocks, GRID_THREADS, 0, st>>>(c->xyz.as<float>(), c->feat.as<uint32_t>(), so, S, N, c->geom.as<StructGeom>(), cell_cnt,
                                                       c->cell_of.as<int>(), c->rank.as<int>());
             ARP_LAUNCHED(c);
             ARP_TRY(arp_scan_exclusive(c, cell_cnt, c->cell_start.as<int>(), state, &meta->ticket_scan, &meta->n_cells, 1,

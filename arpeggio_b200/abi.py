@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # ---- error codes ---------------------------------------------------------
 OK = 0
@@ -135,6 +135,15 @@ class ArpAtoms(C.Structure):
         ('h_xyz', C.c_void_p),
         ('xnbr_xyz', C.c_void_p),
         ('struct_off', C.c_void_p),
+        ('bond_cnt', C.c_void_p),      # wire forms (optional)
+        ('h_cnt', C.c_void_p),
+        ('h_fix', C.c_void_p),
+        ('xnbr_idx', C.c_void_p),
+        ('h_fix_scale', C.c_double),
+        ('n_bond_nbr', C.c_int32),
+        ('n_h', C.c_int32),
+        ('n_xnbr', C.c_int32),
+        ('_pad', C.c_int32),
     ]
 
 
@@ -187,7 +196,7 @@ EXPORTED_SYMBOLS = (
     'arp_abi_version', 'arp_device_count', 'arp_create', 'arp_destroy', 'arp_last_error',
     'arp_params_default', 'arp_set_params', 'arp_host_alloc', 'arp_host_free',
     'arp_upload_atoms', 'arp_upload_atoms_batch', 'arp_pairs_run', 'arp_pairs_fetch', 'arp_pairs_device_ptr',
-    'arp_pairs_run_async', 'arp_pairs_count', 'arp_pairs_fetch_compact', 'arp_pairs_fetch_dist', 'arp_pairs_unpack',
+    'arp_pairs_run_async', 'arp_pairs_count', 'arp_pairs_fetch_compact', 'arp_pairs_fetch_dist', 'arp_pairs_fetch_packed', 'arp_pairs_unpack_packed', 'arp_pairs_fetch_packed_async', 'arp_pairs_fetch_packed_wait', 'arp_pairs_unpack',
     'arp_upload_planes', 'arp_ring_ring_run', 'arp_ring_ring_fetch', 'arp_atom_ring_run',
     'arp_atom_ring_fetch', 'arp_amide_amide_run', 'arp_amide_amide_fetch', 'arp_amide_ring_run',
     'arp_amide_ring_fetch', 'arp_planes_run_all', 'arp_atom_sifts_run', 'arp_atom_sifts_fetch', 'arp_ring_nearest_atom', 'arp_pairs_json_size', 'arp_pairs_json_write', 'arp_flag_within', 'arp_sync', 'arp_get_stats', 'arp_timing_iters', 'arp_launch_count', 'arp_memcpy_probe',

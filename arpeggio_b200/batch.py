@@ -15,7 +15,7 @@ import time
 import numpy as np
 
 from . import abi
-from .engine import CompactPairs, ContactEngine, PinnedBuffer
+from .engine import CompactPairs, ContactEngine, PackedPairs, PinnedBuffer
 
 
 def shard_indices(sizes, world_size, rank):
@@ -38,11 +38,13 @@ def shard_indices(sizes, world_size, rank):
 class BatchRunner:
     """`slots` ContactEngines on one device, driven by `slots` worker threads."""
 
-    def __init__(self, device=0, slots=6, params=None):
+    def __init__(self, device=0, slots=6, params=None, submit_threads=1):
         self.device = device
+        self.submit_threads = submit_threads          # host threads that enqueue the pipelined packed stream (run(packed=True))
         self.engines = [ContactEngine(device, params) for _ in range(max(1, slots))]
         self._pins = [None] * len(self.engines)
         self._last_n = [0] * len(self.engines)
+        self._ratio = [0.0] * len(self.engines)       # records per atom of the slot's last structure (sizes the blind copy)
 
     def close(self):
         for e in self.engines:
@@ -88,7 +90,73 @@ class BatchRunner:
         return CompactPairs(raw[:4 * (n_atoms + 1)].view(np.uint32), raw[o_rec:o_rec + 8 * cap].view(abi.PAIR_C_DTYPE),
                             raw[o_dist:o_dist + 4 * cap].view(np.float32) if with_dist else None)
 
-    def run(self, soas, consume=None, sorted=False, check_finite=True, compact=False, with_dist=False, pack=1):
+    def _packed_buffer(self, slot, n_atoms, n, with_dist):
+        """One pinned block per slot carved into row offsets | low words | high bytes | distances."""
+        wide = n_atoms > (1 << 17)
+        per = 4 + (1 if wide else 0) + (4 if with_dist else 0)
+        o_lo = (4 * (n_atoms + 2) + 255) // 256 * 256          # + 1: scratch entry of arp_pairs_fetch_packed_async
+        need = o_lo + per * n + 1024
+        pb = self._pins[slot]
+        if pb is None or pb.nbytes < need:
+            if pb is not None:
+                pb.free()
+            pb = self._pins[slot] = PinnedBuffer(need + need // 8 + 4096)
+        raw = pb.array(np.uint8)
+        cap = (pb.nbytes - o_lo - 1024) // per
+        o_hi = (o_lo + 4 * cap + 255) // 256 * 256
+        o_dist = (o_hi + (cap if wide else 0) + 255) // 256 * 256
+        return PackedPairs(raw[:4 * (n_atoms + 2)].view(np.uint32), raw[o_lo:o_lo + 4 * cap].view(np.uint32),
+                           raw[o_hi:o_hi + cap] if wide else None,
+                           raw[o_dist:o_dist + 4 * cap].view(np.float32) if with_dist else None)
+
+    def _run_packed(self, soas, consume, with_dist, check_finite, counts, pack=1, slots=None, units=None):
+        """The packed stream, pipelined from ONE host thread: every structure (or group of `pack` structures, uploaded with
+        arp_upload_atoms_batch) is enqueued whole -- upload, kernels, sorted packed view, copies -- on the next slot's
+        stream without a host wait in between (arp_pairs_fetch_packed_async), and waited for only when its slot comes
+        round again.  Six threads doing the same contend for the driver's launch path (each enqueue call then takes 5-10x
+        longer, profiles/README.md round 2); one thread enqueues a whole step in well under 100 us.  slots / units: the
+        share of one submission thread when there are several (submit_threads)."""
+        slots = list(range(len(self.engines))) if slots is None else slots
+        units = range(0, len(soas), pack) if units is None else units
+        S = len(slots)
+        pending = {s: None for s in slots}
+
+        def finish(slot):
+            i, off = pending[slot]
+            pending[slot] = None
+            n_atoms = int(off[-1])
+            rec = self.engines[slot].fetch_pairs_packed_wait(grow=lambda m, s=slot, a=n_atoms: self._packed_buffer(s, a, m, with_dist))
+            if n_atoms:
+                self._ratio[slot] = rec.n / n_atoms
+            for k in range(len(off) - 1):
+                part = rec if len(off) == 2 else rec.structure(int(off[k]), int(off[k + 1]))
+                counts[i + k] = part.n
+                if consume is not None:
+                    consume(i + k, part)
+
+        k = -1
+        for k, i in enumerate(units):
+            slot = slots[k % S]
+            if pending[slot] is not None:
+                finish(slot)
+            eng = self.engines[slot]
+            if pack > 1:
+                off = eng.upload_atoms_batch(soas[i:i + pack], check_finite=check_finite)
+            else:
+                eng.upload_atoms(soas[i], check_finite=check_finite)
+                off = (0, soas[i].n_atoms)
+            n_atoms = int(off[-1])
+            eng.run_pairs_async()
+            expect = int(self._ratio[slot] * n_atoms * 1.02) + 64 if self._ratio[slot] else 14 * n_atoms
+            buf = self._packed_buffer(slot, n_atoms, max(expect, 14 * n_atoms), with_dist)
+            eng.fetch_pairs_packed_async(buf, expect, with_dist)
+            pending[slot] = (i, off)
+        for j in range(S):                                  # oldest first
+            slot = slots[(k + 1 + j) % S]
+            if pending[slot] is not None:
+                finish(slot)
+
+    def run(self, soas, consume=None, sorted=False, check_finite=True, compact=False, with_dist=False, pack=1, packed=False):
         """Upload -> grid build + pair kernels -> fetch for every AtomSoA of `soas`.
 
         consume(index, records): called in the worker thread with a view of the slot's pinned record
@@ -96,12 +164,14 @@ class BatchRunner:
         (engine.CompactPairs; distances only with_dist) instead of 16-byte records.  pack > 1 (compact only): that
         many consecutive structures go up as ONE batch (arp_upload_atoms_batch: one DMA per structure, concatenated on
         the device) and run as one launch sequence; consume still sees one CompactPairs per structure (the j of its
-        records are batch-global: subtract its atom_base).
+        records are batch-global: subtract its atom_base).  packed: the stream as engine.PackedPairs, 4 or 5 bytes per
+        record, pipelined from the calling thread (consume runs there too; with pack > 1 it sees one PackedPairs per
+        structure whose to_records gives structure-local indices).
         Returns (pairs_per_structure, seconds)."""
         soas = list(soas)
         counts = [0] * len(soas)
         todo = queue.SimpleQueue()
-        pack = max(1, int(pack)) if compact else 1
+        pack = max(1, int(pack)) if (compact or packed) else 1
         for i in range(0, len(soas), pack):
             todo.put(i)
         errors = []
@@ -149,6 +219,28 @@ class BatchRunner:
             except Exception as err:           # surface the first failure in the caller's thread
                 errors.append(err)
 
+        if packed:
+            t0 = time.perf_counter()
+            T = max(1, min(self.submit_threads, len(self.engines)))
+            if T == 1:
+                self._run_packed(soas, consume, with_dist, check_finite, counts, pack)
+            else:
+                def share(t):
+                    try:
+                        self._run_packed(soas, consume, with_dist, check_finite, counts, pack, list(range(t, len(self.engines), T)),
+                                         range(t * pack, len(soas), T * pack))
+                    except Exception as err:
+                        errors.append(err)
+                ths = [threading.Thread(target=share, args=(t,)) for t in range(T)]
+                for t in ths:
+                    t.start()
+                for t in ths:
+                    t.join()
+                if errors:
+                    raise errors[0]
+            for e in self.engines:
+                e.sync()
+            return counts, time.perf_counter() - t0
         t0 = time.perf_counter()
         threads = [threading.Thread(target=work, args=(s,)) for s in range(len(self.engines))]
         for t in threads:

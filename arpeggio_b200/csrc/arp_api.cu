@@ -125,7 +125,8 @@ int upload(arp_ctx* c, DBuf& b, const void* src, size_t bytes)
 void pairs_invalidate(arp_ctx* c)
 {
     if (c->run_pending) { cudaStreamSynchronize(c->stream); (void)cudaGetLastError(); c->run_pending = 0; }
-    c->pairs_valid = 0; c->sorted_valid = 0; c->compact_valid = 0; c->sort_tmp_valid = 0; c->sifts_valid = 0;
+    c->pk.pending = 0;
+    c->pairs_valid = 0; c->sorted_valid = 0; c->compact_valid = 0; c->packed_valid = 0; c->sort_tmp_valid = 0; c->sifts_valid = 0;
 }
 
 }  // namespace
@@ -139,17 +140,169 @@ void pairs_invalidate(arp_ctx* c)
  * cost the kernels of one 320k-atom structure instead of 16 separate launch sequences. */
 namespace {
 
+struct HostTimer {                     /* accumulates the host time of a scope into ctx->ht_ns[slot] (ARPEGGIO_HOST_TIMING prints them) */
+    arp_ctx* c; int slot; timespec t0; bool live;
+    HostTimer(arp_ctx* c_, int s) : c(c_), slot(s), live(true) { clock_gettime(CLOCK_MONOTONIC, &t0); }
+    void stop() {
+        if (!live) return;
+        timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1);
+        c->ht_ns[slot] += (unsigned long long)((t1.tv_sec - t0.tv_sec) * 1000000000ll + (t1.tv_nsec - t0.tv_nsec));
+        ++c->ht_calls[slot];
+        live = false;
+    }
+    ~HostTimer() { stop(); }
+};
+
+/* ---- wire forms of arp_atoms, decoded on the device after the copy ------------------------------------------
+ * per-atom counts (1 byte) in place of CSR offsets (4 bytes), the halogen neighbours as (atom index, coordinate)
+ * rows in place of a dense [N][3] array, hydrogen coordinates as int32 fixed point in place of float64.  The
+ * kernels below turn them into the arrays every other kernel reads, so nothing downstream knows the difference. */
+constexpr int CNT_THREADS = 256, CNT_ITEMS = 16, CNT_TILE = CNT_THREADS * CNT_ITEMS;
+
+template <class T> __device__ __forceinline__ int cnt_load(const T* __restrict__ cnt, int n, int base, int (&v)[CNT_ITEMS])
+{
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < CNT_ITEMS; ++k) { const int i = base + k; v[k] = i < n ? (int)cnt[i] : 0; s += v[k]; }
+    return s;
+}
+
+/* exclusive prefix of `s` over the block's threads, and the block total */
+__device__ __forceinline__ int cnt_block_scan(int s, int* total)
+{
+    __shared__ int w_sum[CNT_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) w_sum[w] = inc;
+    __syncthreads();
+    int before = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < CNT_THREADS / 32; ++k) { const int t = w_sum[k]; if (k < w) before += t; tot += t; }
+    *total = tot;
+    return before + inc - s;
+}
+
+/* counts of up to two arrays over the same n atoms (blockIdx.y): tile sums, their prefix, the offsets */
+template <class T> __global__ void __launch_bounds__(CNT_THREADS) k_cnt_sums(const T* __restrict__ cnt_a, const T* __restrict__ cnt_b, int n,
+                                                                             int* __restrict__ sums, int tiles)
+{
+    int v[CNT_ITEMS], tot;
+    const int s = cnt_load(blockIdx.y ? cnt_b : cnt_a, n, blockIdx.x * CNT_TILE + threadIdx.x * CNT_ITEMS, v);
+    cnt_block_scan(s, &tot);
+    if (threadIdx.x == 0) sums[blockIdx.y * tiles + blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(64) k_cnt_top(int* __restrict__ sums, int tiles, int arrays)
+{
+    const int lane = threadIdx.x & 31, y = threadIdx.x >> 5;
+    if (y >= arrays) return;
+    int carry = 0;
+    for (int b = 0; b < tiles; b += 32) {
+        const int v = b + lane < tiles ? sums[y * tiles + b + lane] : 0;
+        int inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+        if (b + lane < tiles) sums[y * tiles + b + lane] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
+/* sum of `v` over the block's threads, in every thread */
+__device__ __forceinline__ int cnt_block_total(int v)
+{
+    __shared__ int w_tot[CNT_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) w_tot[w] = v;
+    __syncthreads();
+    int tot = 0;
+#pragma unroll
+    for (int k = 0; k < CNT_THREADS / 32; ++k) tot += w_tot[k];
+    __syncthreads();
+    return tot;
+}
+
+template <class T, bool SUM_TILES> __global__ void __launch_bounds__(CNT_THREADS) k_cnt_fill(const T* __restrict__ cnt_a, const T* __restrict__ cnt_b, int n,
+                                                                             const int* __restrict__ sums, int tiles,
+                                                                             int* __restrict__ off_a, int* __restrict__ off_b)
+{
+    int v[CNT_ITEMS], tot;
+    const int base = blockIdx.x * CNT_TILE + threadIdx.x * CNT_ITEMS;
+    const int s = cnt_load(blockIdx.y ? cnt_b : cnt_a, n, base, v);
+    int before = 0;
+    if (SUM_TILES) {                    /* few tiles: every block adds up the sums of the tiles before it (no k_cnt_top pass) */
+        for (int t = threadIdx.x; t < (int)blockIdx.x; t += CNT_THREADS) before += sums[blockIdx.y * tiles + t];
+        before = cnt_block_total(before);
+    } else {
+        before = sums[blockIdx.y * tiles + blockIdx.x];
+    }
+    int run = before + cnt_block_scan(s, &tot);
+    int* __restrict__ off = blockIdx.y ? off_b : off_a;
+#pragma unroll
+    for (int k = 0; k < CNT_ITEMS; ++k) {
+        const int i = base + k;
+        if (i < n) { off[i] = run; run += v[k]; if (i == n - 1) off[n] = run; }
+    }
+}
+
+/* offsets [n + 1] of one or two count arrays on c->stream; scratch: 2 * tiles ints */
+template <class T> int counts_to_offsets(arp_ctx* c, const T* cnt_a, int* off_a, const T* cnt_b, int* off_b, int n)
+{
+    if (n <= 0) return ARP_OK;
+    if (!cnt_a) { cnt_a = cnt_b; off_a = off_b; cnt_b = nullptr; off_b = nullptr; }
+    if (!cnt_a) return ARP_OK;
+    const int tiles = (n + CNT_TILE - 1) / CNT_TILE, arrays = cnt_b ? 2 : 1;
+    ARP_TRY(dbuf_reserve(c, c->wire_sums, (size_t)tiles * 2 * sizeof(int)));
+    int* sums = c->wire_sums.as<int>();
+    k_cnt_sums<T><<<dim3((unsigned)tiles, (unsigned)arrays), CNT_THREADS, 0, c->stream>>>(cnt_a, cnt_b, n, sums, tiles);
+    ARP_LAUNCHED(c);
+    if (tiles <= 1024) {
+        k_cnt_fill<T, true><<<dim3((unsigned)tiles, (unsigned)arrays), CNT_THREADS, 0, c->stream>>>(cnt_a, cnt_b, n, sums, tiles, off_a, off_b);
+        ARP_LAUNCHED(c);
+    } else {
+        k_cnt_top<<<1, 64, 0, c->stream>>>(sums, tiles, arrays);
+        ARP_LAUNCHED(c);
+        k_cnt_fill<T, false><<<dim3((unsigned)tiles, (unsigned)arrays), CNT_THREADS, 0, c->stream>>>(cnt_a, cnt_b, n, sums, tiles, off_a, off_b);
+        ARP_LAUNCHED(c);
+    }
+    return ARP_OK;
+}
+
+/* fixed-point hydrogens -> float64 (IEEE division, the caller verified the round trip); sparse halogen neighbours -> dense
+   rows: every atom that carries ARP_F_HAS_XNBR looks its row up in the ascending index list (zeros when it is missing);
+   the rows of the other atoms are never read (arp_rules.cuh tests the flag first) and stay as they are */
+__global__ void __launch_bounds__(256) k_wire_rest(const int32_t* __restrict__ h_fix, double scale, double* __restrict__ h_xyz, long long n_h3,
+                                                   const uint32_t* __restrict__ feat, const int32_t* __restrict__ x_idx,
+                                                   const float* __restrict__ x_src, float* __restrict__ xnbr, int n_x, int n_atoms)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_h3) h_xyz[t] = __ddiv_rn((double)h_fix[t], scale);
+    if (xnbr && t < n_atoms && (feat[t] & ARP_F_HAS_XNBR)) {
+        int lo = 0, hi = n_x;                   /* first entry >= t */
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (x_idx[mid] < (int)t) lo = mid + 1; else hi = mid; }
+        float a = 0.f, b = 0.f, c = 0.f;
+        if (lo < n_x && x_idx[lo] == (int)t) { a = x_src[3 * (size_t)lo]; b = x_src[3 * (size_t)lo + 1]; c = x_src[3 * (size_t)lo + 2]; }
+        xnbr[3 * (size_t)t] = a; xnbr[3 * (size_t)t + 1] = b; xnbr[3 * (size_t)t + 2] = c;
+    }
+}
+
 struct PartDesc {                      /* device: where the arrays of one structure sit in the staging arena (byte offsets, -1: absent) */
-    int atom_base, n_atoms, res_base, n_res, bond_base, h_base, class_base, pad;
+    int atom_base, n_atoms, res_base, n_res, bond_base, h_base, class_base, x_base;
     long long o_xyz, o_feat, o_res_id, o_rad, o_prev, o_next, o_flags, o_boff, o_bnbr, o_hoff, o_hxyz, o_xnbr;
+    long long o_bcnt, o_hcnt, o_hfix, o_xidx;      /* wire forms (arp_atoms.bond_cnt, h_cnt, h_fix, xnbr_idx) */
+    double h_scale;
 };
 
 struct MergeArgs {
     const PartDesc* parts; int n_parts;
     const char* stage; const unsigned short* class_map;
-    int N, Rs, E, H;
+    int N, Rs, E, H, X;                 /* X: rows of all sparse neighbour lists */
     float* xyz; uint32_t* feat; int32_t* res_id; uint16_t* rad_class; int32_t* res_prev; int32_t* res_next; uint8_t* res_flags;
     int32_t* bond_off; int32_t* bond_nbr; int32_t* h_off; double* h_xyz; float* xnbr;
+    int32_t* bond_cnt; int32_t* h_cnt;  /* merged per-atom counts (scanned into bond_off / h_off afterwards) when any structure came with counts */
 };
 
 /* part of global index i for bases ascending with duplicates (empty structures): last part whose base is <= i */
@@ -178,11 +331,21 @@ __global__ void __launch_bounds__(256) k_merge_atoms(MergeArgs M)
     M.feat[i] = ((const uint32_t*)(M.stage + d.o_feat))[li];
     M.res_id[i] = ((const int32_t*)(M.stage + d.o_res_id))[li] + d.res_base;
     M.rad_class[i] = M.class_map[d.class_base + ((const uint16_t*)(M.stage + d.o_rad))[li]];
-    if (M.bond_off) M.bond_off[i] = d.bond_base + (d.o_boff >= 0 ? ((const int32_t*)(M.stage + d.o_boff))[li] : 0);
-    if (M.h_off) M.h_off[i] = d.h_base + (d.o_hoff >= 0 ? ((const int32_t*)(M.stage + d.o_hoff))[li] : 0);
-    if (M.xnbr) {
+    if (M.bond_cnt) {                   /* counts now, offsets by the scan that follows */
+        int n = 0;
+        if (d.o_bcnt >= 0) n = ((const uint8_t*)(M.stage + d.o_bcnt))[li];
+        else if (d.o_boff >= 0) { const int32_t* o = (const int32_t*)(M.stage + d.o_boff); n = o[li + 1] - o[li]; }
+        M.bond_cnt[i] = n;
+    } else if (M.bond_off) M.bond_off[i] = d.bond_base + (d.o_boff >= 0 ? ((const int32_t*)(M.stage + d.o_boff))[li] : 0);
+    if (M.h_cnt) {
+        int n = 0;
+        if (d.o_hcnt >= 0) n = ((const uint8_t*)(M.stage + d.o_hcnt))[li];
+        else if (d.o_hoff >= 0) { const int32_t* o = (const int32_t*)(M.stage + d.o_hoff); n = o[li + 1] - o[li]; }
+        M.h_cnt[i] = n;
+    } else if (M.h_off) M.h_off[i] = d.h_base + (d.o_hoff >= 0 ? ((const int32_t*)(M.stage + d.o_hoff))[li] : 0);
+    if (M.xnbr) {                       /* dense rows here; sparse rows are scattered over the zeros by k_merge_rest */
         float a = 0.f, b = 0.f, c = 0.f;
-        if (d.o_xnbr >= 0) { const float* q = (const float*)(M.stage + d.o_xnbr) + 3 * (size_t)li; a = q[0]; b = q[1]; c = q[2]; }
+        if (d.o_xnbr >= 0 && d.o_xidx < 0) { const float* q = (const float*)(M.stage + d.o_xnbr) + 3 * (size_t)li; a = q[0]; b = q[1]; c = q[2]; }
         M.xnbr[3 * (size_t)i] = a; M.xnbr[3 * (size_t)i + 1] = b; M.xnbr[3 * (size_t)i + 2] = c;
     }
 }
@@ -204,9 +367,78 @@ __global__ void __launch_bounds__(256) k_merge_rest(MergeArgs M)
     }
     if (t < M.H) {
         const PartDesc& d = M.parts[part_of(M.parts, M.n_parts, t, [](const PartDesc& q) { return q.h_base; })];
-        const double* h = (const double*)(M.stage + d.o_hxyz) + 3 * (size_t)(t - d.h_base);
-        M.h_xyz[3 * (size_t)t] = h[0]; M.h_xyz[3 * (size_t)t + 1] = h[1]; M.h_xyz[3 * (size_t)t + 2] = h[2];
+        double x, y, z;
+        if (d.o_hfix >= 0) {
+            const int32_t* h = (const int32_t*)(M.stage + d.o_hfix) + 3 * (size_t)(t - d.h_base);
+            x = __ddiv_rn((double)h[0], d.h_scale); y = __ddiv_rn((double)h[1], d.h_scale); z = __ddiv_rn((double)h[2], d.h_scale);
+        } else {
+            const double* h = (const double*)(M.stage + d.o_hxyz) + 3 * (size_t)(t - d.h_base);
+            x = h[0]; y = h[1]; z = h[2];
+        }
+        M.h_xyz[3 * (size_t)t] = x; M.h_xyz[3 * (size_t)t + 1] = y; M.h_xyz[3 * (size_t)t + 2] = z;
     }
+}
+
+/* sparse halogen-neighbour rows of all structures -> the dense merged array (after k_merge_atoms zeroed / filled it) */
+__global__ void __launch_bounds__(256) k_merge_xnbr(MergeArgs M)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= M.X) return;
+    const PartDesc& d = M.parts[part_of(M.parts, M.n_parts, t, [](const PartDesc& q) { return q.x_base; })];
+    const int r = t - d.x_base;
+    const int i = d.atom_base + ((const int32_t*)(M.stage + d.o_xidx))[r];
+    const float* q = (const float*)(M.stage + d.o_xnbr) + 3 * (size_t)r;
+    M.xnbr[3 * (size_t)i] = q[0]; M.xnbr[3 * (size_t)i + 1] = q[1]; M.xnbr[3 * (size_t)i + 2] = q[2];
+}
+
+/* totals and consistency of the wire forms of one arp_atoms (host): E, H, rows of the neighbour list */
+struct WireSizes { long long E, H, X; bool cnt_b, cnt_h, fix_h, sparse_x; };
+
+int wire_sizes(arp_ctx* c, const arp_atoms* a, WireSizes* w)
+{
+    const int N = a->n_atoms;
+    memset(w, 0, sizeof *w);
+    w->cnt_b = a->bond_cnt != nullptr; w->cnt_h = a->h_cnt != nullptr; w->fix_h = a->h_fix != nullptr; w->sparse_x = a->xnbr_idx != nullptr;
+    if (N <= 0) return ARP_OK;
+    ARP_REQUIRE(c, !(a->bond_cnt && a->bond_off), ARP_E_INVALID_ARG, "bond_cnt and bond_off are alternatives");
+    ARP_REQUIRE(c, !(a->h_cnt && a->h_off), ARP_E_INVALID_ARG, "h_cnt and h_off are alternatives");
+    ARP_REQUIRE(c, !(a->h_fix && a->h_xyz), ARP_E_INVALID_ARG, "h_fix and h_xyz are alternatives");
+    ARP_REQUIRE(c, !a->h_fix || (a->h_fix_scale > 0.0 && a->h_fix_scale < 1e12), ARP_E_INVALID_ARG, "h_fix_scale out of range");
+    auto total = [&](const uint8_t* cnt) {         /* byte sum, eight at a time in four 16-bit lanes (flushed before a lane can overflow) */
+        long long s = 0;
+        int i = 0;
+        const uint64_t M = 0x00ff00ff00ff00ffull;
+        while (i + 8 <= N) {
+            uint64_t acc = 0;
+            for (int k = 0; k < 128 && i + 8 <= N; ++k, i += 8) {
+                uint64_t x;
+                memcpy(&x, cnt + i, 8);
+                acc += (x & M) + ((x >> 8) & M);
+            }
+            s += (long long)((acc & 0xffff) + ((acc >> 16) & 0xffff) + ((acc >> 32) & 0xffff) + (acc >> 48));
+        }
+        for (; i < N; ++i) s += cnt[i];
+        return s;
+    };
+    if (a->bond_cnt) {
+        ARP_REQUIRE(c, a->n_bond_nbr >= 0 && total(a->bond_cnt) == a->n_bond_nbr, ARP_E_INVALID_ARG, "bond_cnt does not sum to n_bond_nbr");
+        w->E = a->n_bond_nbr;
+    } else if (a->bond_off) w->E = a->bond_off[N];
+    if (a->h_cnt) {
+        ARP_REQUIRE(c, a->n_h >= 0 && total(a->h_cnt) == a->n_h, ARP_E_INVALID_ARG, "h_cnt does not sum to n_h");
+        w->H = a->n_h;
+    } else if (a->h_off) w->H = a->h_off[N];
+    ARP_REQUIRE(c, w->E >= 0 && w->H >= 0, ARP_E_INVALID_ARG, "negative CSR size");
+    ARP_REQUIRE(c, w->E == 0 || a->bond_nbr, ARP_E_INVALID_ARG, "bond_nbr is NULL");
+    ARP_REQUIRE(c, w->H == 0 || a->h_xyz || a->h_fix, ARP_E_INVALID_ARG, "h_xyz is NULL");
+    if (a->xnbr_idx) {
+        ARP_REQUIRE(c, a->n_xnbr >= 0 && a->n_xnbr <= N && (a->n_xnbr == 0 || a->xnbr_xyz), ARP_E_INVALID_ARG, "xnbr_idx without rows");
+        for (int k = 0; k < a->n_xnbr; ++k)
+            ARP_REQUIRE(c, a->xnbr_idx[k] >= 0 && a->xnbr_idx[k] < N && (k == 0 || a->xnbr_idx[k] > a->xnbr_idx[k - 1]), ARP_E_INVALID_ARG,
+                        "xnbr_idx must ascend strictly inside the atoms");
+        w->X = a->n_xnbr;
+    }
+    return ARP_OK;
 }
 
 int check_part(arp_ctx* c, const arp_atoms* a)
@@ -220,8 +452,6 @@ int check_part(arp_ctx* c, const arp_atoms* a)
         ARP_REQUIRE(c, a->n_residues > 0 && a->n_rad_classes > 0, ARP_E_INVALID_ARG, "atoms without residues or radius classes");
         ARP_REQUIRE(c, !a->bond_off || a->bond_off[0] == 0, ARP_E_INVALID_ARG, "bond_off[0] != 0");
         ARP_REQUIRE(c, !a->h_off || a->h_off[0] == 0, ARP_E_INVALID_ARG, "h_off[0] != 0");
-        ARP_REQUIRE(c, !a->bond_off || a->bond_off[a->n_atoms] == 0 || a->bond_nbr, ARP_E_INVALID_ARG, "bond_nbr is NULL");
-        ARP_REQUIRE(c, !a->h_off || a->h_off[a->n_atoms] == 0 || a->h_xyz, ARP_E_INVALID_ARG, "h_xyz is NULL");
     }
     return ARP_OK;
 }
@@ -319,12 +549,18 @@ int arp_create(int device, arp_ctx** out)
 void arp_destroy(arp_ctx* c)
 {
     if (!c) return;
+    if (getenv("ARPEGGIO_HOST_TIMING")) {         /* diagnostic: host time inside the entry points of the end-to-end step */
+        static const char* nm[5] = { "upload_atoms (enqueue)", "pairs_run_async (enqueue)", "fetch_packed: wait for the run",
+                                     "fetch_packed: enqueue sort + copies", "fetch_packed: wait for the copies" };
+        for (int k = 0; k < 5; ++k)
+            if (c->ht_calls[k]) fprintf(stderr, "[host timing] %-38s %8llu calls  %8.1f us/call\n", nm[k], c->ht_calls[k], c->ht_ns[k] / 1e3 / c->ht_calls[k]);
+    }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DBuf* bufs[] = { &c->xyz, &c->feat, &c->res_id, &c->rad_class, &c->vdw, &c->cov, &c->res_prev, &c->res_next,
                      &c->res_flags, &c->bond_off, &c->bond_nbr, &c->h_off, &c->h_xyz, &c->xnbr, &c->struct_off,
                      &c->zero, &c->geom, &c->cell_start, &c->cell_of, &c->rank, &c->pos4, &c->att4, &c->runtab, &c->sift_acc, &c->sift_out, &c->ring_scratch, &c->hreach, &c->arena, &c->out, &c->hits, &c->work,
-                     &c->batch_small, &c->batch_stage, &c->radtab, &c->sort_tmp, &c->sort_out, &c->sort_c, &c->sort_d, &c->sort_zero, &c->sort_off, &c->within, &c->flush };
+                     &c->batch_small, &c->batch_stage, &c->w_bcnt, &c->w_hcnt, &c->w_hfix, &c->w_xidx, &c->w_xnbr, &c->wire_sums, &c->w_cnt_merge, &c->radtab, &c->sort_tmp, &c->sort_out, &c->sort_c, &c->sort_d, &c->sort_lo, &c->sort_hi, &c->sort_zero, &c->sort_off, &c->within, &c->flush };
     for (DBuf* b : bufs) dbuf_free(*b);
     arp_planes_release(c);
     for (int k = 0; k < 5; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
@@ -411,6 +647,7 @@ int arp_host_free(void* ptr)
 int arp_upload_atoms(arp_ctx* c, const arp_atoms* a)
 {
     if (!c) return ARP_E_INVALID_ARG;
+    HostTimer ht(c, 0);
     ARP_REQUIRE(c, a != nullptr, ARP_E_INVALID_ARG, "atoms is NULL");
     ARP_REQUIRE(c, a->n_atoms >= 0 && a->n_residues >= 0 && a->n_rad_classes >= 0, ARP_E_INVALID_ARG, "negative size");
     ARP_REQUIRE(c, a->n_atoms <= 500000000, ARP_E_INVALID_ARG, "more than 5e8 atoms");
@@ -423,6 +660,8 @@ int arp_upload_atoms(arp_ctx* c, const arp_atoms* a)
                        a->res_next && a->res_flags, ARP_E_INVALID_ARG, "a required atom array is NULL");
         ARP_REQUIRE(c, a->n_residues > 0 && a->n_rad_classes > 0, ARP_E_INVALID_ARG, "atoms without residues or radius classes");
     }
+    WireSizes w;
+    ARP_TRY(wire_sizes(c, a, &w));
     ARP_REQUIRE(c, !a->bond_off || N == 0 || a->bond_off[0] == 0, ARP_E_INVALID_ARG, "bond_off[0] != 0");
     ARP_REQUIRE(c, !a->h_off || N == 0 || a->h_off[0] == 0, ARP_E_INVALID_ARG, "h_off[0] != 0");
     if (a->struct_off) {
@@ -435,17 +674,15 @@ int arp_upload_atoms(arp_ctx* c, const arp_atoms* a)
     c->atom_ring.valid = 0;
     c->input_bytes = 0;
     c->N = N; c->Rs = a->n_residues; c->K = a->n_rad_classes; c->S = S;
-    c->has_bonds = a->bond_off != nullptr;
-    c->has_h = a->h_off != nullptr;
-    c->has_xnbr = a->xnbr_xyz != nullptr;
-    c->E = (a->bond_off && N > 0) ? a->bond_off[N] : 0;
-    c->H = (a->h_off && N > 0) ? a->h_off[N] : 0;
-    ARP_REQUIRE(c, c->E >= 0 && c->H >= 0, ARP_E_INVALID_ARG, "negative CSR size");
-    ARP_REQUIRE(c, c->E == 0 || a->bond_nbr, ARP_E_INVALID_ARG, "bond_nbr is NULL");
-    ARP_REQUIRE(c, c->H == 0 || a->h_xyz, ARP_E_INVALID_ARG, "h_xyz is NULL");
+    c->has_bonds = a->bond_off != nullptr || w.cnt_b;
+    c->has_h = a->h_off != nullptr || w.cnt_h;
+    c->has_xnbr = a->xnbr_xyz != nullptr || w.sparse_x;
+    ARP_REQUIRE(c, w.E < (1ll << 31) && w.H < (1ll << 31), ARP_E_INVALID_ARG, "CSR size beyond int32");
+    c->E = (int)w.E;
+    c->H = (int)w.H;
     const size_t n = (size_t)N;
     struct Piece { DBuf* dst; const void* src; size_t bytes; };
-    Piece pieces[15];
+    Piece pieces[18];
     int np = 0;
     auto piece = [&](DBuf& d, const void* src, size_t bytes) { pieces[np++] = Piece{ &d, src, bytes }; };
     piece(c->xyz, a->xyz, n * 12);
@@ -457,15 +694,19 @@ int arp_upload_atoms(arp_ctx* c, const arp_atoms* a)
     piece(c->res_prev, a->res_prev, (size_t)c->Rs * 4);
     piece(c->res_next, a->res_next, (size_t)c->Rs * 4);
     piece(c->res_flags, a->res_flags, (size_t)c->Rs);
+    /* the wire forms land in staging buffers and are decoded below into the arrays the kernels read */
     if (c->has_bonds) {
-        piece(c->bond_off, a->bond_off, (n + 1) * 4);
+        if (w.cnt_b) piece(c->w_bcnt, a->bond_cnt, n); else piece(c->bond_off, a->bond_off, (n + 1) * 4);
         piece(c->bond_nbr, a->bond_nbr, (size_t)c->E * 4);
     }
     if (c->has_h) {
-        piece(c->h_off, a->h_off, (n + 1) * 4);
-        piece(c->h_xyz, a->h_xyz, (size_t)c->H * 24);
+        if (w.cnt_h) piece(c->w_hcnt, a->h_cnt, n); else piece(c->h_off, a->h_off, (n + 1) * 4);
+        if (w.fix_h) piece(c->w_hfix, a->h_fix, (size_t)c->H * 12); else piece(c->h_xyz, a->h_xyz, (size_t)c->H * 24);
     }
-    if (c->has_xnbr) piece(c->xnbr, a->xnbr_xyz, n * 12);
+    if (c->has_xnbr) {
+        if (w.sparse_x) { piece(c->w_xidx, a->xnbr_idx, (size_t)w.X * 4); piece(c->w_xnbr, a->xnbr_xyz, (size_t)w.X * 12); }
+        else piece(c->xnbr, a->xnbr_xyz, n * 12);
+    }
     if (S > 1) piece(c->struct_off, a->struct_off, (size_t)(S + 1) * 4);
     /* One host block (e.g. engine.pinned_soa: every array at a 256-byte offset of one pinned allocation) goes up in
        ONE copy and the device arrays become views of the arena: 14 small DMA transfers cost about 110 us for a
@@ -506,6 +747,21 @@ int arp_upload_atoms(arp_ctx* c, const arp_atoms* a)
     } else {
         for (int k = 0; k < np; ++k) ARP_TRY(upload(c, *pieces[k].dst, pieces[k].src, pieces[k].bytes));
     }
+    if (w.cnt_b) ARP_TRY(dbuf_reserve(c, c->bond_off, (n + 1) * 4));
+    if (w.cnt_h) ARP_TRY(dbuf_reserve(c, c->h_off, (n + 1) * 4));
+    if (w.cnt_b || w.cnt_h)
+        ARP_TRY(counts_to_offsets<uint8_t>(c, w.cnt_b ? c->w_bcnt.as<uint8_t>() : nullptr, c->bond_off.as<int>(),
+                                           w.cnt_h ? c->w_hcnt.as<uint8_t>() : nullptr, c->h_off.as<int>(), N));
+    if (w.fix_h) ARP_TRY(dbuf_reserve(c, c->h_xyz, (size_t)c->H * 24));
+    if (w.sparse_x) ARP_TRY(dbuf_reserve(c, c->xnbr, n * 12));
+    const long long h3 = w.fix_h ? 3ll * c->H : 0, xn = w.sparse_x ? (long long)N : 0;
+    if (h3 > 0 || xn > 0) {
+        const long long m = h3 > xn ? h3 : xn;
+        k_wire_rest<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(c->w_hfix.as<int32_t>(), a->h_fix_scale, c->h_xyz.as<double>(), h3,
+                                                                        c->feat.as<uint32_t>(), c->w_xidx.as<int32_t>(), c->w_xnbr.as<float>(),
+                                                                        w.sparse_x ? c->xnbr.as<float>() : nullptr, (int)w.X, N);
+        ARP_LAUNCHED(c);
+    }
     ARP_TRY(arp_pairs_prepare(c));
     c->have_atoms = 1;
     return ARP_OK;
@@ -542,6 +798,7 @@ static void fill_stats(arp_ctx* c, int with_events)
     s.input_bytes = c->input_bytes;
     s.output_bytes = s.n_pairs * sizeof(arp_pair);
     s.faults = c->h_meta->fault;
+    if (with_events > c->events_level) with_events = c->events_level;      /* only what the run recorded */
     if (with_events >= 3) {
         float a = 0.f, b = 0.f, d = 0.f;
         cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
@@ -550,10 +807,12 @@ static void fill_stats(arp_ctx* c, int with_events)
         float h = 0.f;
         cudaEventElapsedTime(&h, c->ev[4], c->ev[3]);
         s.ms_grid = a; s.ms_search = b; s.ms_classify = d; s.ms_hscan = h; s.ms_pairs = b + d; s.ms_total = a + b + d;
-    } else if (with_events == 1) {
+    } else if (with_events >= 1) {
         float w = 0.f;
         cudaEventElapsedTime(&w, c->ev[0], c->ev[3]);
         s.ms_total = w; s.ms_grid = s.ms_search = s.ms_classify = s.ms_hscan = s.ms_pairs = 0.f;
+    } else {
+        s.ms_total = s.ms_grid = s.ms_search = s.ms_classify = s.ms_hscan = s.ms_pairs = 0.f;      /* a run enqueued without events */
     }
 }
 
@@ -562,7 +821,7 @@ static void fill_stats(arp_ctx* c, int with_events)
 static int pairs_finish(arp_ctx* c)
 {
     for (int attempt = 0; attempt < 3; ++attempt) {
-        if (attempt > 0) ARP_TRY(arp_pairs_enqueue(c, 1));
+        if (attempt > 0) { ++c->finish_reruns; ARP_TRY(arp_pairs_enqueue(c, 1)); }
         ARP_CUDA(c, cudaStreamSynchronize(c->stream));
         c->run_pending = 0;
         /* candidates >= records: both lists share the capacity (k_tiles has no candidate list: n_raw stays 0) */
@@ -595,15 +854,19 @@ int arp_upload_atoms_batch(arp_ctx* c, const arp_atoms* const* parts, int32_t n_
 {
     if (!c) return ARP_E_INVALID_ARG;
     ARP_REQUIRE(c, parts != nullptr && n_parts >= 1, ARP_E_INVALID_ARG, "no structures");
-    long long N = 0, Rs = 0, E = 0, H = 0;
-    bool any_bonds = false, any_h = false, any_x = false;
+    long long N = 0, Rs = 0, E = 0, H = 0, X = 0;
+    bool any_bonds = false, any_h = false, any_x = false, cnt_bonds = false, cnt_h = false;
+    std::vector<WireSizes> ws((size_t)n_parts);
     for (int s = 0; s < n_parts; ++s) {
         ARP_TRY(check_part(c, parts[s]));
         const arp_atoms* a = parts[s];
+        WireSizes& w = ws[(size_t)s];
+        ARP_TRY(wire_sizes(c, a, &w));
         N += a->n_atoms; Rs += a->n_atoms > 0 ? a->n_residues : 0;
-        if (a->n_atoms > 0 && a->bond_off) { any_bonds = true; E += a->bond_off[a->n_atoms]; }
-        if (a->n_atoms > 0 && a->h_off) { any_h = true; H += a->h_off[a->n_atoms]; }
-        if (a->n_atoms > 0 && a->xnbr_xyz) any_x = true;
+        E += w.E; H += w.H; X += w.X;
+        if (a->n_atoms > 0 && (a->bond_off || w.cnt_b)) { any_bonds = true; cnt_bonds |= w.cnt_b; }
+        if (a->n_atoms > 0 && (a->h_off || w.cnt_h)) { any_h = true; cnt_h |= w.cnt_h; }
+        if (a->n_atoms > 0 && (a->xnbr_xyz || w.sparse_x)) any_x = true;
     }
     ARP_REQUIRE(c, N <= 500000000 && E < (1ll << 31) && H < (1ll << 31), ARP_E_INVALID_ARG, "batch too large");
     ARP_TRY(arp_bind(c));
@@ -618,7 +881,7 @@ int arp_upload_atoms_batch(arp_ctx* c, const arp_atoms* const* parts, int32_t n_
     auto up256 = [](size_t v) { return (v + 255) / 256 * 256; };
     struct Copy { size_t dst; const void* src; size_t bytes; };
     std::vector<Copy> copies;
-    long long ab = 0, rb = 0, bb = 0, hb = 0;
+    long long ab = 0, rb = 0, bb = 0, hb = 0, xb = 0;
     c->input_bytes = 0;
     for (int s = 0; s < n_parts; ++s) {
         const arp_atoms* a = parts[s];
@@ -626,8 +889,10 @@ int arp_upload_atoms_batch(arp_ctx* c, const arp_atoms* const* parts, int32_t n_
         memset(&d, 0, sizeof d);
         soff[(size_t)s] = (int32_t)ab;
         const size_t n = (size_t)a->n_atoms, nr = n ? (size_t)a->n_residues : 0;
-        const size_t ne = (n && a->bond_off) ? (size_t)a->bond_off[n] : 0, nh = (n && a->h_off) ? (size_t)a->h_off[n] : 0;
+        const WireSizes& w = ws[(size_t)s];
+        const size_t ne = (size_t)w.E, nh = (size_t)w.H, nx = (size_t)w.X;
         d.atom_base = (int)ab; d.n_atoms = (int)n; d.res_base = (int)rb; d.n_res = (int)nr; d.bond_base = (int)bb; d.h_base = (int)hb;
+        d.x_base = (int)xb; d.h_scale = a->h_fix_scale;
         d.class_base = (int)cmap.size();
         for (int k = 0; n && k < a->n_rad_classes; ++k) {          /* merged radius table: identical (vdw, cov) pairs share a class */
             size_t m = 0;
@@ -636,12 +901,14 @@ int arp_upload_atoms_batch(arp_ctx* c, const arp_atoms* const* parts, int32_t n_
             cmap.push_back((unsigned short)m);
         }
         struct Piece { long long* off; const void* src; size_t bytes; };
-        Piece pc[12] = {
+        Piece pc[16] = {
             { &d.o_xyz, a->xyz, n * 12 }, { &d.o_feat, a->feat, n * 4 }, { &d.o_res_id, a->res_id, n * 4 }, { &d.o_rad, a->rad_class, n * 2 },
             { &d.o_prev, a->res_prev, nr * 4 }, { &d.o_next, a->res_next, nr * 4 }, { &d.o_flags, a->res_flags, nr },
             { &d.o_boff, n ? a->bond_off : nullptr, (n && a->bond_off) ? (n + 1) * 4 : 0 }, { &d.o_bnbr, a->bond_nbr, ne * 4 },
-            { &d.o_hoff, n ? a->h_off : nullptr, (n && a->h_off) ? (n + 1) * 4 : 0 }, { &d.o_hxyz, a->h_xyz, nh * 24 },
-            { &d.o_xnbr, n ? a->xnbr_xyz : nullptr, (n && a->xnbr_xyz) ? n * 12 : 0 } };
+            { &d.o_hoff, n ? a->h_off : nullptr, (n && a->h_off) ? (n + 1) * 4 : 0 }, { &d.o_hxyz, w.fix_h ? nullptr : a->h_xyz, w.fix_h ? 0 : nh * 24 },
+            { &d.o_xnbr, n ? a->xnbr_xyz : nullptr, w.sparse_x ? nx * 12 : ((n && a->xnbr_xyz) ? n * 12 : 0) },
+            { &d.o_bcnt, a->bond_cnt, w.cnt_b ? n : 0 }, { &d.o_hcnt, a->h_cnt, w.cnt_h ? n : 0 },
+            { &d.o_hfix, a->h_fix, w.fix_h ? nh * 12 : 0 }, { &d.o_xidx, a->xnbr_idx, w.sparse_x ? nx * 4 : 0 } };
         /* one host block (engine.pinned_soa) -> one DMA for the structure; otherwise one per array */
         uintptr_t lo = UINTPTR_MAX, hi = 0;
         size_t sum = 0;
@@ -649,8 +916,9 @@ int arp_upload_atoms_batch(arp_ctx* c, const arp_atoms* const* parts, int32_t n_
             const uintptr_t p0 = (uintptr_t)q.src;
             lo = p0 < lo ? p0 : lo; hi = p0 + q.bytes > hi ? p0 + q.bytes : hi; sum += q.bytes;
         }
-        bool packed = sum > 0 && (hi - lo) <= sum + 512 * 12;
+        bool packed = sum > 0 && (hi - lo) <= sum + 512 * 16;
         for (const Piece& q : pc) if (q.bytes && ((uintptr_t)q.src - lo) % 8 != 0) packed = false;
+
         if (packed) {
             copies.push_back(Copy{ stage_bytes, (const void*)lo, hi - lo });
             for (const Piece& q : pc) *q.off = q.bytes ? (long long)(stage_bytes + ((uintptr_t)q.src - lo)) : -1;
@@ -662,7 +930,7 @@ int arp_upload_atoms_batch(arp_ctx* c, const arp_atoms* const* parts, int32_t n_
             }
         }
         c->input_bytes += sum + (n ? (size_t)a->n_rad_classes * 16 : 0);
-        ab += (long long)n; rb += (long long)nr; bb += (long long)ne; hb += (long long)nh;
+        ab += (long long)n; rb += (long long)nr; bb += (long long)ne; hb += (long long)nh; xb += (long long)nx;
     }
     soff[(size_t)n_parts] = (int32_t)ab;
     ARP_REQUIRE(c, vdw.size() <= ARPK_MAX_RAD, ARP_E_INVALID_ARG, "more than 512 distinct radius classes in the batch");
@@ -712,7 +980,12 @@ int arp_upload_atoms_batch(arp_ctx* c, const arp_atoms* const* parts, int32_t n_
         memset(&M, 0, sizeof M);
         M.parts = (const PartDesc*)(c->batch_small.as<char>() + o_desc); M.n_parts = n_parts;
         M.stage = c->batch_stage.as<char>(); M.class_map = (const unsigned short*)(c->batch_small.as<char>() + o_cmap);
-        M.N = (int)N; M.Rs = (int)Rs; M.E = (int)E; M.H = (int)H;
+        M.N = (int)N; M.Rs = (int)Rs; M.E = (int)E; M.H = (int)H; M.X = (int)X;
+        if (cnt_bonds || cnt_h) {
+            ARP_TRY(dbuf_reserve(c, c->w_cnt_merge, n * 8));
+            M.bond_cnt = cnt_bonds ? c->w_cnt_merge.as<int32_t>() : nullptr;
+            M.h_cnt = cnt_h ? c->w_cnt_merge.as<int32_t>() + n : nullptr;
+        }
         M.xyz = c->xyz.as<float>(); M.feat = c->feat.as<uint32_t>(); M.res_id = c->res_id.as<int32_t>();
         M.rad_class = c->rad_class.as<uint16_t>(); M.res_prev = c->res_prev.as<int32_t>(); M.res_next = c->res_next.as<int32_t>();
         M.res_flags = c->res_flags.as<uint8_t>();
@@ -727,29 +1000,39 @@ int arp_upload_atoms_batch(arp_ctx* c, const arp_atoms* const* parts, int32_t n_
             k_merge_rest<<<(unsigned)((rest + 255) / 256), 256, 0, c->stream>>>(M);
             ARP_LAUNCHED(c);
         }
+        if (X > 0) {
+            k_merge_xnbr<<<(unsigned)((X + 255) / 256), 256, 0, c->stream>>>(M);
+            ARP_LAUNCHED(c);
+        }
+        if (M.bond_cnt || M.h_cnt)
+            ARP_TRY(counts_to_offsets<int32_t>(c, M.bond_cnt, M.bond_off, M.h_cnt, M.h_off, (int)N));
     }
     ARP_TRY(arp_pairs_prepare(c));
     c->have_atoms = 1;
     return ARP_OK;
 }
 
-int arp_pairs_run_async(arp_ctx* c)
+static int pairs_run_enqueue(arp_ctx* c, int with_events)
 {
     if (!c) return ARP_E_INVALID_ARG;
     ARP_REQUIRE(c, c->have_atoms, ARP_E_NOT_READY, "arp_pairs_run before arp_upload_atoms");
     ARP_TRY(arp_bind(c));
+    HostTimer ht(c, 1);
     pairs_invalidate(c);
     /* first guess of the stream length; an overflowing run still counts, then is repeated once */
     uint64_t want = c->out_cap ? c->out_cap : (uint64_t)c->N * 16 + 4096;
     ARP_TRY(pairs_out_reserve(c, want));
-    ARP_TRY(arp_pairs_enqueue(c, 1));
+    ARP_TRY(arp_pairs_enqueue(c, with_events));
     c->run_pending = 1;
     return ARP_OK;
 }
 
+/* no timing events around an asynchronous run: two API calls less per step (arp_stats.ms_* are 0 for such a run) */
+int arp_pairs_run_async(arp_ctx* c) { return pairs_run_enqueue(c, 0); }
+
 int arp_pairs_run(arp_ctx* c, uint64_t* n_pairs)
 {
-    ARP_TRY(arp_pairs_run_async(c));
+    ARP_TRY(pairs_run_enqueue(c, 1));
     ARP_TRY(pairs_finish(c));
     if (n_pairs) *n_pairs = c->n_pairs;
     return ARP_OK;
@@ -809,6 +1092,130 @@ int arp_pairs_fetch_compact(arp_ctx* c, uint32_t* row_off, arp_pair_c* rec, uint
     return ARP_OK;
 }
 
+int arp_pairs_fetch_packed(arp_ctx* c, uint32_t* row_off, uint32_t* lo32, uint8_t* hi8, uint64_t cap, float* dist,
+                           uint64_t* n_pairs, int32_t* bits_j, uint32_t* n_faults)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    { HostTimer ht(c, 2); ARP_TRY(pairs_ready(c, "arp_pairs_fetch_packed before arp_pairs_run")); }
+    HostTimer ht3(c, 3);
+    const int bj = arp_pairs_bits_j(c);
+    const bool need_hi = bj + 15 > 32;
+    if (n_pairs) *n_pairs = c->n_pairs;
+    if (bits_j) *bits_j = bj;
+    ARP_REQUIRE(c, cap >= c->n_pairs, ARP_E_CAPACITY, "destination holds fewer records than the run produced");
+    ARP_REQUIRE(c, row_off != nullptr && n_faults != nullptr, ARP_E_INVALID_ARG, "row_off or n_faults is NULL");
+    ARP_REQUIRE(c, c->n_pairs == 0 || (lo32 != nullptr && (!need_hi || hi8 != nullptr)), ARP_E_INVALID_ARG,
+                "lo32 is NULL (or hi8, which more than 131072 atoms need)");
+    ARP_TRY(arp_bind(c));
+    ARP_TRY(arp_pairs_sorted_build(c, 2));
+    ARP_CUDA(c, cudaMemcpyAsync(row_off, c->sort_off.p, ((size_t)c->N + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    *n_faults = 0;
+    if (c->n_pairs) {
+        ARP_CUDA(c, cudaMemcpyAsync(lo32, c->sort_lo.p, (size_t)c->n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        if (need_hi) ARP_CUDA(c, cudaMemcpyAsync(hi8, c->sort_hi.p, (size_t)c->n_pairs, cudaMemcpyDeviceToHost, c->stream));
+        if (dist) ARP_CUDA(c, cudaMemcpyAsync(dist, c->sort_d.p, (size_t)c->n_pairs * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        ARP_CUDA(c, cudaMemcpyAsync(&c->h_meta->pad0[0], c->sort_fault, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    }
+    ht3.stop();
+    { HostTimer ht(c, 4); ARP_CUDA(c, cudaStreamSynchronize(c->stream)); }
+    if (c->n_pairs) *n_faults = c->h_meta->pad0[0];
+    return ARP_OK;
+}
+
+/* The whole fetch enqueued behind a run that has not been waited for: the sorted packed view is built with the record
+   count read on the device and the first min(cap, expect) words are copied; arp_pairs_fetch_packed_wait is the one wait of
+   the step.  One host thread can so keep several contexts (streams) busy without ever blocking in the middle of a step. */
+int arp_pairs_fetch_packed_async(arp_ctx* c, uint32_t* row_off, uint32_t* lo32, uint8_t* hi8, uint64_t cap, float* dist, uint64_t expect)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_REQUIRE(c, c->have_atoms && (c->run_pending || c->pairs_valid), ARP_E_NOT_READY, "arp_pairs_fetch_packed_async before arp_pairs_run_async");
+    ARP_REQUIRE(c, row_off != nullptr, ARP_E_INVALID_ARG, "row_off is NULL");          /* n_atoms + 2 entries: the last one is scratch */
+    const bool need_hi = arp_pairs_bits_j(c) + 15 > 32;
+    ARP_REQUIRE(c, cap == 0 || (lo32 != nullptr && (!need_hi || hi8 != nullptr)), ARP_E_INVALID_ARG,
+                "lo32 is NULL (or hi8, which more than 131072 atoms need)");
+    ARP_TRY(arp_bind(c));
+    HostTimer ht(c, 3);
+    const int blind = c->run_pending ? 1 : 0;
+    uint64_t ncopy;
+    if (blind) {
+        ncopy = expect && expect < cap ? expect : cap;
+        if (ncopy > c->out_cap) ncopy = c->out_cap;
+    } else {
+        ncopy = c->n_pairs <= cap ? c->n_pairs : 0;          /* a stream that does not fit is reported by the wait */
+    }
+    ARP_TRY(arp_pairs_sorted_build(c, 2, blind));
+    /* row offsets [N + 1] and the fault counter behind them in one copy */
+    ARP_CUDA(c, cudaMemcpyAsync(row_off, c->sort_off.p, ((size_t)c->N + 2) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (ncopy) {
+        ARP_CUDA(c, cudaMemcpyAsync(lo32, c->sort_lo.p, (size_t)ncopy * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        if (need_hi) ARP_CUDA(c, cudaMemcpyAsync(hi8, c->sort_hi.p, (size_t)ncopy, cudaMemcpyDeviceToHost, c->stream));
+        if (dist) ARP_CUDA(c, cudaMemcpyAsync(dist, c->sort_d.p, (size_t)ncopy * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    c->pk.row_off = row_off; c->pk.lo32 = lo32; c->pk.hi8 = hi8; c->pk.cap = cap; c->pk.dist = dist;
+    c->pk.copied = ncopy; c->pk.blind = blind; c->pk.pending = 1;
+    return ARP_OK;
+}
+
+int arp_pairs_fetch_packed_wait(arp_ctx* c, uint64_t* n_pairs, int32_t* bits_j, uint32_t* n_faults)
+{
+    if (!c) return ARP_E_INVALID_ARG;
+    ARP_REQUIRE(c, c->pk.pending, ARP_E_NOT_READY, "arp_pairs_fetch_packed_wait without arp_pairs_fetch_packed_async");
+    ARP_REQUIRE(c, n_faults != nullptr, ARP_E_INVALID_ARG, "n_faults is NULL");
+    ARP_TRY(arp_bind(c));
+    HostTimer ht(c, 4);
+    c->pk.pending = 0;
+    if (c->pk.blind && c->run_pending) {
+        c->finish_reruns = 0;
+        ARP_TRY(pairs_finish(c));                 /* the wait; repeats a run that overflowed */
+        if (c->finish_reruns == 0) { c->packed_valid = 1; c->sort_tmp_valid = 1; }      /* the view was built from the complete stream */
+    } else {
+        ARP_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    ARP_REQUIRE(c, c->pairs_valid, ARP_E_NOT_READY, "the run was invalidated between arp_pairs_fetch_packed_async and the wait");
+    if (!c->packed_valid)                         /* the run was repeated after the view had been built: the plain way */
+        return arp_pairs_fetch_packed(c, c->pk.row_off, c->pk.lo32, c->pk.hi8, c->pk.cap, c->pk.dist, n_pairs, bits_j, n_faults);
+    const int bj = arp_pairs_bits_j(c);
+    if (n_pairs) *n_pairs = c->n_pairs;
+    if (bits_j) *bits_j = bj;
+    ARP_REQUIRE(c, c->pk.cap >= c->n_pairs, ARP_E_CAPACITY, "destination holds fewer records than the run produced");
+    if (c->n_pairs > c->pk.copied) {              /* more records than expected: the rest of the streams */
+        const size_t o = (size_t)c->pk.copied, m = (size_t)(c->n_pairs - c->pk.copied);
+        ARP_CUDA(c, cudaMemcpyAsync(c->pk.lo32 + o, c->sort_lo.as<uint32_t>() + o, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        if (bj + 15 > 32) ARP_CUDA(c, cudaMemcpyAsync(c->pk.hi8 + o, c->sort_hi.as<uint8_t>() + o, m, cudaMemcpyDeviceToHost, c->stream));
+        if (c->pk.dist) ARP_CUDA(c, cudaMemcpyAsync(c->pk.dist + o, c->sort_d.as<float>() + o, m * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        ARP_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    *n_faults = c->pk.row_off[(size_t)c->N + 1];
+    return ARP_OK;
+}
+
+/* host only: the packed view back into 16-byte records.  feat: the ARP_F_* words of the uploaded atoms (the entity class
+   is a function of their selection / water bits, rule_entity_class_bools = interactions.py:643-691) */
+int arp_pairs_unpack_packed(const uint32_t* row_off, const uint32_t* lo32, const uint8_t* hi8, const float* dist, int32_t n_atoms,
+                            int32_t bits_j, const uint32_t* feat, int32_t atom_base, arp_pair* dst, uint64_t cap)
+{
+    if (n_atoms < 0 || (n_atoms > 0 && (!row_off || !feat)) || bits_j < 1 || bits_j > 31 || atom_base < 0) return ARP_E_INVALID_ARG;
+    if (n_atoms == 0) return ARP_OK;
+    const uint64_t n = row_off[n_atoms];
+    if (n > cap) return ARP_E_CAPACITY;
+    if (n && (!lo32 || !dst || (bits_j + 15 > 32 && !hi8))) return ARP_E_INVALID_ARG;
+    const uint64_t jmask = (1ull << bits_j) - 1ull;
+    for (int32_t i = 0; i < n_atoms; ++i) {
+        if (row_off[i + 1] < row_off[i] || row_off[i + 1] > n) return ARP_E_INVALID_ARG;
+        const bool si = (feat[i] & ARP_F_IN_SELECTION) != 0, wi = (feat[i] & ARP_F_IS_WATER) != 0;
+        for (uint64_t k = row_off[i]; k < row_off[i + 1]; ++k) {
+            const uint64_t w = (uint64_t)lo32[k] | (hi8 ? (uint64_t)hi8[k] << 32 : 0ull);
+            const int64_t j = (int64_t)(w & jmask) - atom_base;        /* local to the view (one structure of a batch) */
+            if (j < 0 || j >= n_atoms) return ARP_E_INVALID_ARG;
+            const uint32_t cls = rule_entity_class_bools(si, (feat[j] & ARP_F_IN_SELECTION) != 0, wi, (feat[j] & ARP_F_IS_WATER) != 0);
+            dst[k].i = i; dst[k].j = (int32_t)j;
+            dst[k].mask = (uint32_t)((w >> bits_j) & 0x7fffu) | (cls << ARP_CLASS_SHIFT);
+            dst[k].dist = dist ? dist[k] : 0.f;
+        }
+    }
+    return ARP_OK;
+}
+
 int arp_pairs_fetch_dist(arp_ctx* c, float* dist, uint64_t cap)
 {
     if (!c) return ARP_E_INVALID_ARG;
@@ -817,7 +1224,7 @@ int arp_pairs_fetch_dist(arp_ctx* c, float* dist, uint64_t cap)
     if (c->n_pairs == 0) return ARP_OK;
     ARP_REQUIRE(c, dist != nullptr, ARP_E_INVALID_ARG, "dist is NULL");
     ARP_TRY(arp_bind(c));
-    ARP_TRY(arp_pairs_sorted_build(c, 1));
+    if (!c->packed_valid) ARP_TRY(arp_pairs_sorted_build(c, 1));          /* the compact and the packed view share the distance stream */
     ARP_CUDA(c, cudaMemcpyAsync(dist, c->sort_d.p, (size_t)c->n_pairs * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     ARP_CUDA(c, cudaStreamSynchronize(c->stream));
     return ARP_OK;
@@ -977,7 +1384,7 @@ int arp_timing_iters(arp_ctx* c, int iters, int flush_l2, float* ms_per_iter)
     c->stats.ms_classify = (float)(classify / split_iters);
     c->stats.ms_hscan = (float)(hscan / split_iters);
     c->stats.ms_total = (float)(tot / iters);
-    c->sorted_valid = 0; c->compact_valid = 0; c->sort_tmp_valid = 0; c->sifts_valid = 0;
+    c->sorted_valid = 0; c->compact_valid = 0; c->packed_valid = 0; c->sort_tmp_valid = 0; c->sifts_valid = 0;
     if (ms_per_iter) *ms_per_iter = (float)(tot / iters);
     return ARP_OK;
 }

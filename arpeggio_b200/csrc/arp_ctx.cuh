@@ -120,6 +120,14 @@ struct arp_ctx {
     DBuf xyz, feat, res_id, rad_class, vdw, cov, res_prev, res_next, res_flags;
     DBuf bond_off, bond_nbr, h_off, h_xyz, xnbr, struct_off;
     DBuf arena;                   /* one block for all of the above when the caller's arrays are one host block */
+    DBuf w_bcnt, w_hcnt, w_hfix, w_xidx, w_xnbr;   /* wire forms of arp_atoms as uploaded (bond_cnt, h_cnt, h_fix, xnbr_idx + rows) */
+    unsigned* sort_fault = nullptr;   /* device: records of the packed view that carried the fault bit (= sort_off[N + 1]) */
+    int events_level = 0;             /* with_events of the last arp_pairs_enqueue */
+    /* arp_pairs_fetch_packed_async -> arp_pairs_fetch_packed_wait */
+    struct { uint32_t* row_off; uint32_t* lo32; uint8_t* hi8; uint64_t cap; float* dist; uint64_t copied; int pending, blind; } pk = {};
+    int finish_reruns = 0;            /* runs pairs_finish had to repeat (overflow, hand-off fault) */
+    unsigned long long ht_ns[8] = {0}, ht_calls[8] = {0};   /* host time inside entry points (diagnostic, ARPEGGIO_HOST_TIMING) */
+    DBuf wire_sums, w_cnt_merge;  /* tile sums of the count scan; merged per-atom counts of a batch */
     DBuf batch_stage, batch_small;/* arp_upload_atoms_batch: the structures as uploaded; descriptors, struct_off, merged radius table */
     void* h_batch = nullptr;      /* pinned image of batch_small */
     size_t h_batch_cap = 0;
@@ -168,7 +176,8 @@ struct arp_ctx {
     int pairs_valid = 0;
     DBuf sort_tmp, sort_out, sort_zero, sort_off;
     DBuf sort_c, sort_d;          /* compact view of the sorted stream: arp_pair_c[n] and float[n] (row offsets: sort_off) */
-    int sorted_valid = 0, compact_valid = 0, sort_tmp_valid = 0;
+    DBuf sort_lo, sort_hi;        /* packed view: low 32 bits (+ the fault counter behind them) and, for N > 2^17, bits 32..39 of the record words */
+    int sorted_valid = 0, compact_valid = 0, packed_valid = 0, sort_tmp_valid = 0;
     int run_pending = 0;          /* arp_pairs_run_async has enqueued a run that nobody has waited for yet */
 
     /* planes */
@@ -276,7 +285,8 @@ int  arp_pairs_prepare(arp_ctx* c);                       /* arp_pairs.cu: size 
    job, 2: also ev[1] between the grid build and the pair kernels, 3: also ev[2] / ev[4] between the pair kernels
    (every event between two kernels keeps them from overlapping and costs a few microseconds) */
 int  arp_pairs_enqueue(arp_ctx* c, int with_events);
-int  arp_pairs_sorted_build(arp_ctx* c, int compact);     /* arp_pairs.cu: (i, j)-ascending copy of the stream (16-byte records or the compact view) */
+int  arp_pairs_sorted_build(arp_ctx* c, int view, int blind = 0);        /* arp_pairs.cu: (i, j)-ascending copy of the stream: 0 16-byte records, 1 compact, 2 packed */
+int  arp_pairs_bits_j(const arp_ctx* c);                  /* bits of an atom index in the packed view */
 int  arp_flag_within_run(arp_ctx* c, double radius);      /* arp_pairs.cu */
 int  arp_ring_nearest_run(arp_ctx* c, const float* xyz, int n_atoms, const double* centers, int n_rings, double radius,
                           int32_t* atom_out, double* dist_out);   /* arp_rings.cu */

@@ -1500,6 +1500,7 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
         ARP_LAUNCHED(c);
         c->radtab_valid = 1;
     }
+    c->events_level = with_events;
     const bool grid_event = with_events >= 2;         /* events between the kernels keep them from overlapping */
     const bool split_events = with_events >= 3;
     /* k_classify starts while k_search drains when that drain is a visible part of the job; the price is one
@@ -1730,100 +1731,150 @@ int arp_pairs_enqueue(arp_ctx* c, int with_events)
     return ARP_OK;
 }
 
-/* ---- canonical (i, j) order of the record stream ----------------------------------------- */
-__global__ void __launch_bounds__(256) k_sort_count(const arp_pair* __restrict__ rec, unsigned long long n,
-                                                    int* __restrict__ cnt)
+/* ---- canonical (i, j) order of the record stream -----------------------------------------
+ * The kernels take the record count either from the host (n_dev == NULL: n_max records) or from the run's own counter on
+ * the device (n_dev = &meta->n_pairs, clamped to the capacity n_max), so that the view can be enqueued behind a run that
+ * has not been waited for (arp_pairs_fetch_packed_async). */
+__device__ __forceinline__ unsigned long long sort_n(const unsigned long long* n_dev, unsigned long long n_max)
 {
-    unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n) atomicAdd(&cnt[rec[r].i], 1);
+    if (!n_dev) return n_max;
+    const unsigned long long n = *n_dev;
+    return n < n_max ? n : n_max;
 }
 
-__global__ void __launch_bounds__(256) k_sort_scatter(const arp_pair* __restrict__ rec, unsigned long long n,
-                                                      const int* __restrict__ off, int* __restrict__ cur,
+__global__ void __launch_bounds__(256) k_sort_count(const arp_pair* __restrict__ rec, const unsigned long long* __restrict__ n_dev,
+                                                    unsigned long long n_max, int* __restrict__ cnt, unsigned* __restrict__ fault_cnt)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) *fault_cnt = 0u;          /* counted by k_sort_place<2>, two kernels later */
+    const unsigned long long n = sort_n(n_dev, n_max), step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += step) atomicAdd(&cnt[rec[r].i], 1);
+}
+
+__global__ void __launch_bounds__(256) k_sort_scatter(const arp_pair* __restrict__ rec, const unsigned long long* __restrict__ n_dev,
+                                                      unsigned long long n_max, const int* __restrict__ off, int* __restrict__ cur,
                                                       arp_pair* __restrict__ tmp)
 {
-    unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    int4 v = reinterpret_cast<const int4*>(rec)[r];
-    int pos = off[v.x] + atomicAdd(&cur[v.x], 1);
-    reinterpret_cast<int4*>(tmp)[pos] = v;
-}
-
-/* records of one i are contiguous in tmp; (i, j) is unique, so the rank of j inside the segment
-   is the final position.  COMPACT: the sorted stream leaves as 8-byte records (j, mask) -- i is implied by the
-   row offsets `off` -- and the distances as a stream of their own (arp_pairs_fetch_compact). */
-template <bool COMPACT>
-__global__ void __launch_bounds__(256) k_sort_place(const arp_pair* __restrict__ tmp, unsigned long long n,
-                                                    const int* __restrict__ off, arp_pair* __restrict__ out,
-                                                    arp_pair_c* __restrict__ outc, float* __restrict__ outd)
-{
-    unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    int4 v = reinterpret_cast<const int4*>(tmp)[r];
-    int b = off[v.x], e = off[v.x + 1];
-    int rank = 0;
-    for (int k = b; k < e; ++k) rank += tmp[k].j < v.y ? 1 : 0;
-    if (COMPACT) {
-        reinterpret_cast<int2*>(outc)[b + rank] = make_int2(v.y, v.z);
-        outd[b + rank] = __int_as_float(v.w);
-    } else {
-        reinterpret_cast<int4*>(out)[b + rank] = v;
+    const unsigned long long n = sort_n(n_dev, n_max), step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += step) {
+        int4 v = reinterpret_cast<const int4*>(rec)[r];
+        int pos = off[v.x] + atomicAdd(&cur[v.x], 1);
+        reinterpret_cast<int4*>(tmp)[pos] = v;
     }
 }
 
-/* compact != 0: sort_c (arp_pair_c[n]) + sort_d (float[n]) + sort_off (row offsets) instead of sort_out */
-int arp_pairs_sorted_build(arp_ctx* c, int compact)
+/* records of one i are contiguous in tmp; (i, j) is unique, so the rank of j inside the segment
+   is the final position.  In the compact and packed views i is implied by the row offsets `off` and the distances
+   leave as a stream of their own (arp_pairs_fetch_compact / arp_pairs_fetch_packed). */
+/* MODE 0: 16-byte records; 1: the compact view, 8-byte records (j, mask) + distance stream; 2: the PACKED view, the 15 SIFt
+   bits above the bits_j bits of j in one word of 32 (+ 8) bits per record + distance stream.  The packed word carries
+   neither the entity class (a function of the two atoms' selection / water flags, which the host has) nor the
+   xbond-without-neighbour fault bit: records that have it are counted in *n_fault instead. */
+template <int MODE>
+__global__ void __launch_bounds__(256) k_sort_place(const arp_pair* __restrict__ tmp, const unsigned long long* __restrict__ n_dev,
+                                                    unsigned long long n_max,
+                                                    const int* __restrict__ off, arp_pair* __restrict__ out,
+                                                    arp_pair_c* __restrict__ outc, float* __restrict__ outd,
+                                                    uint32_t* __restrict__ lo32, uint8_t* __restrict__ hi8, int bits_j,
+                                                    unsigned* __restrict__ n_fault)
 {
-    if (compact ? c->compact_valid : c->sorted_valid) return ARP_OK;
-    const unsigned long long n = c->n_pairs;
+    const unsigned long long n = sort_n(n_dev, n_max), step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += step) {
+        int4 v = reinterpret_cast<const int4*>(tmp)[r];
+        int b = off[v.x], e = off[v.x + 1];
+        int rank = 0;
+        for (int k = b; k < e; ++k) rank += tmp[k].j < v.y ? 1 : 0;
+        if (MODE == 1) {
+            reinterpret_cast<int2*>(outc)[b + rank] = make_int2(v.y, v.z);
+            outd[b + rank] = __int_as_float(v.w);
+        } else if (MODE == 2) {
+            const unsigned long long w = (unsigned long long)(unsigned)v.y | ((unsigned long long)((unsigned)v.z & 0x7fffu) << bits_j);
+            lo32[b + rank] = (uint32_t)w;
+            if (hi8) hi8[b + rank] = (uint8_t)(w >> 32);
+            outd[b + rank] = __int_as_float(v.w);
+            if ((unsigned)v.z & ARPK_FAULT_XBOND_NO_NBR) atomicAdd(n_fault, 1u);
+        } else {
+            reinterpret_cast<int4*>(out)[b + rank] = v;
+        }
+    }
+}
+
+/* bits needed for an atom index of the current upload */
+int arp_pairs_bits_j(const arp_ctx* c)
+{
+    int bits = 1;
+    while (bits < 31 && (1ll << bits) < (long long)c->N) ++bits;
+    return bits;
+}
+
+/* view 0: sort_out (arp_pair[n]); 1: sort_c (arp_pair_c[n]) + sort_d (float[n]); 2: sort_lo (u32[n]) [+ sort_hi (u8[n])] + sort_d;
+   all with sort_off (row offsets).  blind: the run has not been waited for -- the kernels read the record count on the
+   device and the buffers are sized for the capacity of the record stream; the caller marks the view valid once the run
+   turned out complete. */
+int arp_pairs_sorted_build(arp_ctx* c, int view, int blind)
+{
+    int& valid = view == 0 ? c->sorted_valid : view == 1 ? c->compact_valid : c->packed_valid;
+    if (valid && !blind) return ARP_OK;
+    const unsigned long long n = blind ? c->out_cap : c->n_pairs;          /* bound of the record count */
     const size_t N = (size_t)c->N;
     if (n >= (1ull << 31)) return arp_fail(c, ARP_E_CAPACITY, "too many records for the sorted view", __FILE__, __LINE__);
-    if (compact) {
+    const int bits_j = arp_pairs_bits_j(c);
+    const bool need_hi = bits_j + 15 > 32;
+    if (view == 1) {
         ARP_TRY(dbuf_reserve(c, c->sort_c, sizeof(arp_pair_c) * (size_t)n));
+        ARP_TRY(dbuf_reserve(c, c->sort_d, sizeof(float) * (size_t)n));
+    } else if (view == 2) {
+        ARP_TRY(dbuf_reserve(c, c->sort_lo, sizeof(uint32_t) * (size_t)n));
+        if (need_hi) ARP_TRY(dbuf_reserve(c, c->sort_hi, (size_t)n));
         ARP_TRY(dbuf_reserve(c, c->sort_d, sizeof(float) * (size_t)n));
     } else {
         ARP_TRY(dbuf_reserve(c, c->sort_out, sizeof(arp_pair) * (size_t)n));
     }
     ARP_TRY(dbuf_reserve(c, c->sort_off, sizeof(int) * (N + 2)));
+    /* zero region: cnt[N+1] | cur[N+1] | ticket | scan state.  The fault counter of the packed view is the spare entry
+       behind the row offsets, sort_off[N + 1], so that one copy fetches both. */
+    const size_t tiles = (N + 1 + ARP_SCAN_TILE - 1) / ARP_SCAN_TILE + 1;
+    const size_t o_cur = align_up(sizeof(int) * (N + 2), 256);
+    const size_t o_tick = align_up(o_cur + sizeof(int) * (N + 2), 256);
+    const size_t o_state = o_tick + 256;
+    const size_t zb = o_state + tiles * sizeof(unsigned long long);
+    ARP_TRY(dbuf_reserve(c, c->sort_zero, zb));
+    char* z = c->sort_zero.as<char>();
+    c->sort_fault = c->sort_off.as<unsigned>() + (N + 1);
     if (n == 0) {
         ARP_CUDA(c, cudaMemsetAsync(c->sort_off.p, 0, sizeof(int) * (N + 2), c->stream));
-        if (compact) c->compact_valid = 1; else c->sorted_valid = 1;
+        valid = 1;
         return ARP_OK;
     }
-    unsigned blocks = (unsigned)((n + 255) / 256);
-    if (!c->sort_tmp_valid) {           /* records grouped by i (tmp) + row offsets: shared by both views */
+    const unsigned long long* n_dev = blind ? &((const RunMeta*)c->zero.p)->n_pairs : nullptr;
+    size_t want = (size_t)((n + 255) / 256), most = (size_t)c->sm_count * 16;
+    const unsigned blocks = (unsigned)(want < most ? want : most);
+    if (!c->sort_tmp_valid || blind) {           /* records grouped by i (tmp) + row offsets: shared by the views */
         ARP_TRY(dbuf_reserve(c, c->sort_tmp, sizeof(arp_pair) * (size_t)n));
-        /* zero region: cnt[N+1] | cur[N+1] | ticket | scan state */
-        size_t tiles = (N + 1 + ARP_SCAN_TILE - 1) / ARP_SCAN_TILE + 1;
-        size_t o_cur = align_up(sizeof(int) * (N + 2), 256);
-        size_t o_tick = align_up(o_cur + sizeof(int) * (N + 2), 256);
-        size_t o_state = o_tick + 256;
-        size_t zb = o_state + tiles * sizeof(unsigned long long);
-        ARP_TRY(dbuf_reserve(c, c->sort_zero, zb));
-        char* z = c->sort_zero.as<char>();
         int* cnt = (int*)z; int* cur = (int*)(z + o_cur);
         unsigned* ticket = (unsigned*)(z + o_tick);
         unsigned long long* state = (unsigned long long*)(z + o_state);
         ARP_CUDA(c, cudaMemsetAsync(z, 0, zb, c->stream));
-        k_sort_count<<<blocks, 256, 0, c->stream>>>(c->out.as<arp_pair>(), n, cnt);
+        k_sort_count<<<blocks, 256, 0, c->stream>>>(c->out.as<arp_pair>(), n_dev, n, cnt, c->sort_fault);
         ARP_LAUNCHED(c);
         ARP_TRY(arp_scan_exclusive(c, cnt, c->sort_off.as<int>(), state, ticket, nullptr, (int)(N + 1), N + 1));
-        k_sort_scatter<<<blocks, 256, 0, c->stream>>>(c->out.as<arp_pair>(), n, c->sort_off.as<int>(), cur,
+        k_sort_scatter<<<blocks, 256, 0, c->stream>>>(c->out.as<arp_pair>(), n_dev, n, c->sort_off.as<int>(), cur,
                                                       c->sort_tmp.as<arp_pair>());
         ARP_LAUNCHED(c);
-        c->sort_tmp_valid = 1;
+        if (!blind) c->sort_tmp_valid = 1;
+    } else if (view == 2) {
+        ARP_CUDA(c, cudaMemsetAsync(c->sort_fault, 0, sizeof(unsigned), c->stream));
     }
-    if (compact) {
-        k_sort_place<true><<<blocks, 256, 0, c->stream>>>(c->sort_tmp.as<arp_pair>(), n, c->sort_off.as<int>(), nullptr,
-                                                          c->sort_c.as<arp_pair_c>(), c->sort_d.as<float>());
-        ARP_LAUNCHED(c);
-        c->compact_valid = 1;
-    } else {
-        k_sort_place<false><<<blocks, 256, 0, c->stream>>>(c->sort_tmp.as<arp_pair>(), n, c->sort_off.as<int>(),
-                                                           c->sort_out.as<arp_pair>(), nullptr, nullptr);
-        ARP_LAUNCHED(c);
-        c->sorted_valid = 1;
-    }
+    const arp_pair* tmp = c->sort_tmp.as<arp_pair>();
+    const int* off = c->sort_off.as<int>();
+    if (view == 1)
+        k_sort_place<1><<<blocks, 256, 0, c->stream>>>(tmp, n_dev, n, off, nullptr, c->sort_c.as<arp_pair_c>(), c->sort_d.as<float>(), nullptr, nullptr, 0, nullptr);
+    else if (view == 2)
+        k_sort_place<2><<<blocks, 256, 0, c->stream>>>(tmp, n_dev, n, off, nullptr, nullptr, c->sort_d.as<float>(), c->sort_lo.as<uint32_t>(),
+                                                       need_hi ? c->sort_hi.as<uint8_t>() : nullptr, bits_j, c->sort_fault);
+    else
+        k_sort_place<0><<<blocks, 256, 0, c->stream>>>(tmp, n_dev, n, off, c->sort_out.as<arp_pair>(), nullptr, nullptr, nullptr, nullptr, 0, nullptr);
+    ARP_LAUNCHED(c);
+    if (!blind) valid = 1;
     return ARP_OK;
 }
 

@@ -58,9 +58,10 @@ def pinned_soa(soa):
     """A copy of an AtomSoA in ONE block of page-locked host memory (arp_host_alloc), every array at a 256-byte
     offset: arp_upload_atoms then moves the whole structure with a single asynchronous DMA (one transfer instead of
     fourteen) and the device arrays are views of one arena.  The returned object keeps the block alive (``_keep``)."""
-    from .soa import AtomSoA
-    names = ('xyz', 'feat', 'res_id', 'rad_class', 'vdw', 'cov', 'res_prev', 'res_next', 'res_flags',
-             'bond_off', 'bond_nbr', 'h_off', 'h_xyz', 'xnbr_xyz', 'struct_off')
+    from .soa import AtomSoA, WireAtoms
+    wire = isinstance(soa, WireAtoms)
+    names = WireAtoms.NAMES if wire else ('xyz', 'feat', 'res_id', 'rad_class', 'vdw', 'cov', 'res_prev', 'res_next', 'res_flags',
+                                          'bond_off', 'bond_nbr', 'h_off', 'h_xyz', 'xnbr_xyz', 'struct_off')
     arrays = [(k, getattr(soa, k, None)) for k in names]
     offsets, total = {}, 0
     for k, a in arrays:
@@ -77,6 +78,8 @@ def pinned_soa(soa):
         v = raw[offsets[k]:offsets[k] + a.nbytes].view(a.dtype).reshape(a.shape)
         v[...] = a
         fields[k] = v
+    if wire:
+        return WireAtoms(h_fix_scale=soa.h_fix_scale, _keep=[block], **fields)
     return AtomSoA(**fields, _keep=[block])
 
 
@@ -120,6 +123,57 @@ class CompactPairs:
                                     out.ctypes.data if self.n else None, self.n)
         if rc != abi.OK:
             raise ArpeggioCudaError(rc, 'arp_pairs_unpack failed')
+        return out
+
+
+class PackedPairs:
+    """Packed view of an (i, j)-sorted record stream (arp_pairs_fetch_packed): the records of bgn atom i are words
+    row_off[i] .. row_off[i + 1]; a word holds j in its low bits_j bits and the 15 SIFt bits above them (lo32: bits
+    0..31, hi8: bits 32..39, only for more than 131072 atoms).  4 (or 5) bytes per record + 4 per atom.  The entity
+    class is recomputed from the atoms' feat words by to_records(); n_faults counts records whose xbond-without-neighbour
+    fault bit is not in the words."""
+
+    def __init__(self, row_off, lo_buf, hi_buf, dist_buf):
+        self.row_off, self.lo_buf, self.hi_buf, self.dist_buf = row_off, lo_buf, hi_buf, dist_buf
+        self.lo, self.hi, self.dist, self.n, self.n_atoms, self.bits_j, self.n_faults, self.atom_base = lo_buf[:0], None, None, 0, 0, 1, 0, 0
+
+    def view(self, n_atoms, n, bits_j, n_faults, with_dist):
+        v = PackedPairs(self.row_off, self.lo_buf, self.hi_buf, self.dist_buf)
+        v.n_atoms, v.n, v.bits_j, v.n_faults = n_atoms, n, bits_j, n_faults
+        v.row_off = self.row_off[:n_atoms + 1]
+        v.lo = self.lo_buf[:n]
+        v.hi = self.hi_buf[:n] if bits_j + 15 > 32 and self.hi_buf is not None else None
+        v.dist = self.dist_buf[:n] if with_dist and self.dist_buf is not None else None
+        return v
+
+    def structure(self, lo, hi):
+        """The rows of atoms lo..hi-1 (one structure of a batch) as a PackedPairs of their own: row offsets rebased (a small
+        copy), words and distances as views; to_records(feat of that structure) gives indices local to the structure.
+        n_faults stays the count of the whole batch."""
+        r0, r1 = int(self.row_off[lo]), int(self.row_off[hi])
+        v = PackedPairs(self.row_off, self.lo_buf, self.hi_buf, self.dist_buf)
+        v.row_off = self.row_off[lo:hi + 1] - np.uint32(r0)
+        v.lo = self.lo[r0:r1]
+        v.hi = self.hi[r0:r1] if self.hi is not None else None
+        v.dist = self.dist[r0:r1] if self.dist is not None else None
+        v.n, v.n_atoms, v.bits_j, v.n_faults, v.atom_base = r1 - r0, hi - lo, self.bits_j, self.n_faults, self.atom_base + lo
+        return v
+
+    @property
+    def nbytes(self):
+        return self.row_off.nbytes + self.lo.nbytes + (self.hi.nbytes if self.hi is not None else 0) + (self.dist.nbytes if self.dist is not None else 0)
+
+    def to_records(self, feat, dist=None):
+        """PAIR_DTYPE[n] through the library's host unpacker; feat: the uploaded atoms' feature words (uint32[n_atoms])."""
+        out = np.empty(self.n, dtype=abi.PAIR_DTYPE)
+        feat = np.ascontiguousarray(feat, np.uint32)
+        d = self.dist if dist is None else np.ascontiguousarray(dist, np.float32)
+        rc = lib().arp_pairs_unpack_packed(self.row_off.ctypes.data, self.lo.ctypes.data if self.n else None,
+                                           self.hi.ctypes.data if self.hi is not None and self.n else None,
+                                           d.ctypes.data if d is not None and self.n else None, self.n_atoms, self.bits_j,
+                                           feat.ctypes.data if self.n_atoms else None, self.atom_base, out.ctypes.data if self.n else None, self.n)
+        if rc != abi.OK:
+            raise ArpeggioCudaError(rc, 'arp_pairs_unpack_packed failed')
         return out
 
 
@@ -247,6 +301,64 @@ class ContactEngine:
             self._check(rc)
             break
         return out.view(n_atoms, int(n.value), with_dist)
+
+    def fetch_pairs_packed(self, with_dist=False, out=None, grow=None):
+        """The (i, j)-sorted stream of the last run in its packed form (arp_pairs_fetch_packed): PackedPairs, 4 bytes per
+        record (5 beyond 131072 atoms) + 4 per atom.  out / grow as for fetch_pairs_compact."""
+        n_atoms = self._soa.n_atoms
+        n, bits, faults = C.c_uint64(), C.c_int32(), C.c_uint32()
+        wide = n_atoms > (1 << 17)
+        if out is None or out.row_off.shape[0] < n_atoms + 1:
+            out = PackedPairs(np.empty(n_atoms + 1, np.uint32), np.empty(0, np.uint32), np.empty(0, np.uint8) if wide else None, None)
+        for attempt in range(2):
+            dist = out.dist_buf if with_dist else None
+            cap = out.lo_buf.shape[0]
+            if wide:
+                cap = min(cap, out.hi_buf.shape[0]) if out.hi_buf is not None else 0
+            if dist is not None:
+                cap = min(cap, dist.shape[0])
+            rc = self._L.arp_pairs_fetch_packed(self._ctx, out.row_off.ctypes.data, out.lo_buf.ctypes.data if cap else None,
+                                                out.hi_buf.ctypes.data if wide and cap else None, cap,
+                                                dist.ctypes.data if dist is not None and cap else None, C.byref(n), C.byref(bits), C.byref(faults))
+            if rc == abi.E_CAPACITY and attempt == 0:
+                m = int(n.value)
+                out = grow(m) if grow is not None else PackedPairs(out.row_off, np.empty(m, np.uint32), np.empty(m, np.uint8) if wide else None,
+                                                                   np.empty(m, np.float32) if with_dist else None)
+                continue
+            self._check(rc)
+            break
+        return out.view(n_atoms, int(n.value), int(bits.value), int(faults.value), with_dist)
+
+    def fetch_pairs_packed_async(self, out, expect=0, with_dist=False):
+        """Enqueues the sorted packed view and its copies into `out` (PackedPairs over pinned memory) behind a run that has
+        not been waited for (run_pairs_async) and returns at once; fetch_pairs_packed_wait is the step's one wait.  expect:
+        the caller's guess of the record count (that many words are copied blindly; the wait fetches what is missing)."""
+        n_atoms = self._soa.n_atoms
+        wide = n_atoms > (1 << 17)
+        if out.row_off.shape[0] < n_atoms + 2:
+            raise ValueError('out.row_off must hold n_atoms + 2 entries (the last one is scratch)')
+        dist = out.dist_buf if with_dist else None
+        cap = out.lo_buf.shape[0]
+        if wide:
+            cap = min(cap, out.hi_buf.shape[0]) if out.hi_buf is not None else 0
+        if dist is not None:
+            cap = min(cap, dist.shape[0])
+        self._check(self._L.arp_pairs_fetch_packed_async(self._ctx, out.row_off.ctypes.data, out.lo_buf.ctypes.data if cap else None,
+                                                         out.hi_buf.ctypes.data if wide and cap else None, cap,
+                                                         dist.ctypes.data if dist is not None and cap else None, int(expect)))
+        self._pk = (out, with_dist)
+
+    def fetch_pairs_packed_wait(self, grow=None):
+        """The wait of fetch_pairs_packed_async: PackedPairs view of its `out`.  A stream that did not fit is fetched again
+        into grow(n) (or a fresh pageable buffer) -- the views are still on the device, nothing is recomputed."""
+        out, with_dist = self._pk
+        self._pk = None
+        n, bits, faults = C.c_uint64(), C.c_int32(), C.c_uint32()
+        rc = self._L.arp_pairs_fetch_packed_wait(self._ctx, C.byref(n), C.byref(bits), C.byref(faults))
+        if rc == abi.E_CAPACITY:
+            return self.fetch_pairs_packed(with_dist, out=grow(int(n.value)) if grow is not None else None)
+        self._check(rc)
+        return out.view(self._soa.n_atoms, int(n.value), int(bits.value), int(faults.value), with_dist)
 
     def fetch_pairs_dist(self, n, out=None):
         """float32 distances of the sorted stream, same order as the compact records."""

@@ -139,6 +139,10 @@ class AtomSoA:
         self.__dict__['_ct_cache'] = (key, s, arrays)
         return s
 
+    def to_wire(self, h_decimals=3):
+        """The same structure in its wire form (WireAtoms): fewer bytes over PCIe, decoded on the device."""
+        return WireAtoms.from_soa(self, h_decimals)
+
     def structure(self, s):
         """The s-th structure of a batch as a stand-alone AtomSoA (residue ids re-based)."""
         if self.struct_off is None:
@@ -243,3 +247,84 @@ class PlaneSoA:
     @staticmethod
     def empty(is_f32=False):
         return PlaneSoA(np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0, np.int32), np.zeros(0, np.uint32), is_f32)
+
+
+class WireAtoms:
+    """An AtomSoA in the wire forms of arp_atoms (include/arpeggio_cuda.h): per-atom uint8 counts in place of the two
+    int32 CSR offset arrays, the single-bond neighbours of the halogens (get_single_bond_neighbour, utils.py:163-176) as
+    (atom index, coordinate) rows in place of a dense [N, 3] array, and -- when every hydrogen coordinate is a decimal
+    fraction of `h_decimals` digits, as coordinates read from PDB / mmCIF text are -- the float64 hydrogen coordinates as
+    int32 fixed point.  Every form is lossless (the fixed-point one is checked value by value and skipped otherwise); the
+    library decodes them on the device after the copy, so results are those of the AtomSoA.  Accepted wherever an AtomSoA
+    is uploaded (ContactEngine.upload_atoms / upload_atoms_batch, BatchRunner.run, engine.pinned_soa)."""
+
+    NAMES = ('xyz', 'feat', 'res_id', 'rad_class', 'vdw', 'cov', 'res_prev', 'res_next', 'res_flags', 'bond_off', 'bond_cnt',
+             'bond_nbr', 'h_off', 'h_cnt', 'h_xyz', 'h_fix', 'xnbr_idx', 'xnbr_xyz', 'struct_off')
+
+    def __init__(self, h_fix_scale=0.0, _keep=None, **arrays):
+        for k in self.NAMES:
+            setattr(self, k, arrays.pop(k, None))
+        if arrays:
+            raise TypeError(f'unknown arrays {sorted(arrays)}')
+        self.h_fix_scale = float(h_fix_scale)
+        self._keep = _keep or []
+        self._ct = None
+
+    @classmethod
+    def from_soa(cls, soa, h_decimals=3):
+        n = soa.n_atoms
+        kw = dict(xyz=soa.xyz, feat=soa.feat, res_id=soa.res_id, rad_class=soa.rad_class, vdw=soa.vdw, cov=soa.cov,
+                  res_prev=soa.res_prev, res_next=soa.res_next, res_flags=soa.res_flags, struct_off=soa.struct_off)
+        scale = 0.0
+        if soa.bond_off is not None:
+            cnt = np.diff(soa.bond_off)
+            if n and cnt.max() > 255:
+                kw.update(bond_off=soa.bond_off)
+            else:
+                kw.update(bond_cnt=cnt.astype(np.uint8))
+            kw.update(bond_nbr=soa.bond_nbr)
+        if soa.h_off is not None:
+            kw.update(h_cnt=np.diff(soa.h_off).astype(np.uint8))          # AtomSoA.validate: at most 255 hydrogens per atom
+            fix = None
+            if h_decimals is not None and soa.h_xyz.size:
+                s = float(10 ** int(h_decimals))
+                q = np.rint(soa.h_xyz * s)
+                if np.all(np.abs(q) < 2.0 ** 31) and np.array_equal(q / s, soa.h_xyz):      # value by value, NaN fails
+                    fix, scale = q.astype(np.int32), s
+            if fix is not None:
+                kw.update(h_fix=fix)
+            else:
+                kw.update(h_xyz=soa.h_xyz)
+        if soa.xnbr_xyz is not None:
+            idx = np.flatnonzero(soa.feat & np.uint32(abi.F_HAS_XNBR)).astype(np.int32)
+            kw.update(xnbr_idx=idx, xnbr_xyz=np.ascontiguousarray(soa.xnbr_xyz[idx]))
+        return cls(h_fix_scale=scale, **kw)
+
+    @property
+    def n_atoms(self):
+        return self.xyz.shape[0]
+
+    @property
+    def n_residues(self):
+        return self.res_flags.shape[0]
+
+    @property
+    def n_structures(self):
+        return 1 if self.struct_off is None else self.struct_off.shape[0] - 1
+
+    def input_bytes(self):
+        return sum(a.nbytes for a in (getattr(self, k) for k in self.NAMES) if a is not None)
+
+    def as_ctypes(self):
+        if self._ct is None:
+            s = abi.ArpAtoms()
+            s.n_atoms, s.n_residues, s.n_rad_classes, s.n_structures = self.n_atoms, self.n_residues, self.vdw.shape[0], self.n_structures
+            for k in self.NAMES:
+                setattr(s, k, abi.ptr(getattr(self, k)))
+            s.h_fix_scale = self.h_fix_scale
+            s.n_bond_nbr = 0 if self.bond_nbr is None else self.bond_nbr.shape[0]
+            n_h = self.h_fix if self.h_fix is not None else self.h_xyz
+            s.n_h = 0 if n_h is None else n_h.shape[0]
+            s.n_xnbr = 0 if self.xnbr_idx is None else self.xnbr_idx.shape[0]
+            self._ct = s
+        return self._ct

@@ -35,7 +35,7 @@ def cloud_uniform(n=10_000, seed=1):
                    res_flags=np.zeros(n, np.uint8))
 
 
-def cloud_featured(n=100_000, seed=2, atoms_per_residue=8, chain_len=300, bonds=True):
+def cloud_featured(n=100_000, seed=2, atoms_per_residue=8, chain_len=300, bonds=True, h_decimals=None):
     """configs[2]: 100k-atom cloud with SIFt feature masks, residues, hydrogens, bonds, halogen neighbours."""
     rng = np.random.default_rng(seed)
     xyz = cloud_coords(rng, n)
@@ -82,6 +82,8 @@ def cloud_featured(n=100_000, seed=2, atoms_per_residue=8, chain_len=300, bonds=
     d = rng.normal(size=(owner.shape[0], 3))
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     h_xyz = xyz[owner].astype(np.float64) + d
+    if h_decimals is not None:          # as read from PDB / mmCIF text (3 decimals): the wire form can carry these as int32 fixed point
+        h_xyz = np.round(h_xyz, h_decimals)
 
     # halogen / xbond-donor single-bond neighbour at 1.8 A
     d = rng.normal(size=(n, 3))

@@ -313,57 +313,73 @@ def run_ours(args):
         dist.barrier()
 
     # ---- end to end through the public API, host buffers -----------------------------------
+    # Every step moves its own inputs H2D from pinned host memory and its own results D2H.  Headline: the structure in
+    # its wire form (soa.WireAtoms: uint8 counts for the CSR offsets, sparse halogen neighbours), the (i, j)-sorted
+    # stream in its packed form (one 32-bit word per record + row offsets), pipelined over 8 streams from one host thread
+    # (BatchRunner.run(packed=True): upload, kernels, sort, copies of a step enqueued without a host wait in between).
     pins = []
     host = pinned_soa(soa)                   # one pinned block: arp_upload_atoms moves it with a single DMA
+    host_w = pinned_soa(soa.to_wire())
     out_pin = PinnedBuffer(16 * (n_pairs + 1024))
     out = out_pin.array(abi.PAIR_DTYPE)
-    e2e_steps = max(3, min(args.steps, 200))
-    runner = BatchRunner(device=local, slots=6, params=p)
-    cbuf = runner._compact_buffer(0, soa.n_atoms, n_pairs, False)      # pinned block of slot 0, reused by the serial leg
+    e2e_steps = min(max(10 * args.steps, 100), 600)
+    runner = BatchRunner(device=local, slots=8, params=p)
+    ref_rec = eng.fetch_pairs(n_pairs, sorted=True)                  # the 16-byte records of the resident run: the check of every leg
 
-    def e2e_step():                          # single stream: upload, run (not waited for), sorted compact fetch
-        eng.upload_atoms(host)
+    def leg(src, steps, check=None, **kw):
+        """warm-up (6 structures, results checked against the 16-byte records) + `steps` timed structures; seconds per step"""
+        seen = []
+        runner.run([src] * 8, consume=(lambda i, r: seen.append(check(r))) if check else None, check_finite=False, **kw)
+        assert not check or (len(seen) == 8 and all(seen)), kw
+        if dist:
+            dist.barrier()
+        _, dt = runner.run([src] * steps, check_finite=False, **kw)
+        return dt / steps
+
+    same = lambda rec: np.array_equal(rec[['i', 'j', 'mask']], ref_rec[['i', 'j', 'mask']])
+    same_d = lambda rec: np.array_equal(rec, ref_rec)
+    e2e_s = leg(host_w, e2e_steps, check=lambda r: same(r.to_records(soa.feat)), packed=True)
+    in_bytes_wire = int(host_w.input_bytes())
+    d2h_bytes = 4 * (soa.n_atoms + 2) + 4 * n_pairs + (n_pairs if soa.n_atoms > (1 << 17) else 0)      # row offsets + scratch entry, words
+    legs = {}
+    legs['plain_inputs'] = (leg(host, e2e_steps, check=lambda r: same(r.to_records(soa.feat)), packed=True), int(in_bytes), d2h_bytes,
+                            'the AtomSoA as it is (int32 CSR offsets, dense neighbour array), packed stream')
+    legs['with_distances'] = (leg(host_w, e2e_steps, check=lambda r: same_d(r.to_records(soa.feat)), packed=True, with_dist=True),
+                              in_bytes_wire, d2h_bytes + 4 * n_pairs, 'wire inputs, packed stream + the float32 distance stream')
+    steps_t = max(3, min(args.steps, 200))                           # the threaded legs ramp up in a few steps
+    legs['compact'] = (leg(host, steps_t, check=lambda r: same(r.to_records()), compact=True), int(in_bytes), 4 * (soa.n_atoms + 1) + 8 * n_pairs,
+                       'round-1/2 compact stream: 8-byte (j, mask) records + row offsets, one host thread per stream slot')
+    legs['records16'] = (leg(host, steps_t, check=same_d, sorted=True), int(in_bytes), 16 * n_pairs,
+                         '16-byte arp_pair records (BatchRunner.run(sorted=True))')
+    src3 = synth.cloud_featured(args.atoms, seed=2 + rank, h_decimals=3)
+    eng.upload_atoms(src3)
+    ref3 = eng.fetch_pairs(eng.run_pairs(), sorted=True)
+    host3 = pinned_soa(src3.to_wire())
+    assert host3.h_fix is not None
+    legs['wire_h_fix'] = (leg(host3, e2e_steps, check=lambda r: np.array_equal(r.to_records(src3.feat)[['i', 'j', 'mask']], ref3[['i', 'j', 'mask']]),
+                              packed=True), int(host3.input_bytes()), 4 * (soa.n_atoms + 2) + 4 * ref3.shape[0],
+                          'the same cloud with hydrogen coordinates of 3 decimals (PDB / mmCIF text precision): they travel as int32 '
+                          'fixed point, checked lossless on the host')
+    eng.upload_atoms(soa)
+    assert eng.run_pairs() == n_pairs
+    # one stream, one structure at a time (latency, not throughput)
+    sbuf = runner._packed_buffer(0, soa.n_atoms, n_pairs + 1024, False)
+
+    def e2e_serial():
+        eng.upload_atoms(host_w, check_finite=False)
         eng.run_pairs_async()
-        return eng.fetch_pairs_compact(False, out=cbuf)
-
-    def e2e_step16():                        # the same with the 16-byte records
-        eng.upload_atoms(host)
-        n = eng.run_pairs()
-        return eng.fetch_pairs(n, sorted=True, out=out)
+        eng.fetch_pairs_packed_async(sbuf, n_pairs, False)
+        return eng.fetch_pairs_packed_wait()
 
     for _ in range(3):
-        got_c = e2e_step()
-        got = e2e_step16()
-    assert got_c.n == n_pairs and got.shape[0] == n_pairs
-    d2h_bytes = int(got_c.nbytes)
-    assert np.array_equal(got_c.to_records()[['i', 'j', 'mask']], got[['i', 'j', 'mask']])
+        assert e2e_serial().n == n_pairs
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    eng.sync()
-    e2e_serial_s = (time.perf_counter() - t0) / e2e_steps
-    # the batch API: the same steps through 6 stream slots, so that the H2D copy of one step, the kernels of
-    # another and the D2H copy of a third overlap; every step still moves its own inputs and results
-    checked = []
-    runner.run([host] * 6, consume=lambda i, cp: checked.append(int(cp.n)), compact=True)
-    assert checked and all(c == n_pairs for c in checked)
-    if dist:
-        dist.barrier()
-    _, dt = runner.run([host] * e2e_steps, check_finite=False, compact=True)
-    e2e_s = dt / e2e_steps
-    if dist:
-        dist.barrier()
-    runner.run([host] * 6, check_finite=False, sorted=True)          # warm-up: the sorted 16-byte view has buffers of its own
-    _, dt16 = runner.run([host] * e2e_steps, check_finite=False, sorted=True)
-    e2e16_s = dt16 / e2e_steps
-    # the same with the float32 distance stream in the transfer (12 bytes per record + 4 per atom)
-    runner.run([host] * 6, check_finite=False, compact=True, with_dist=True)
-    if dist:
-        dist.barrier()
-    _, dtd = runner.run([host] * e2e_steps, check_finite=False, compact=True, with_dist=True)
-    e2e_dist_s = dtd / e2e_steps
+    for _ in range(steps_t):
+        e2e_serial()
+    e2e_serial_s = (time.perf_counter() - t0) / steps_t
+    got = ref_rec
     # resident inputs, steps of THREE contexts (streams) in flight at once: what the device sustains when the launch ramps and
     # tails of consecutive steps overlap (the per-step figure `value` serialises them); every context holds its own copy of
     # the structure and of all buffers (3 x 27 MB in flight), rank 0 only
@@ -397,16 +413,17 @@ def run_ours(args):
     # what PCIe gives this rank while all ranks copy at once: the same sizes, H2D and D2H concurrently
     if dist:
         dist.barrier()
-    pcie = eng.memcpy_probe(int(in_bytes), d2h_bytes, 40)
+    pcie = eng.memcpy_probe(in_bytes_wire, d2h_bytes, 40)
     # ---- configs[4]: PDB-batch throughput, this rank's shard of 20k-atom structures, host buffers, end to end ----
     batch = None
     if args.batch_structures > 0:
-        distinct = [pinned_soa(synth.cloud_featured(args.batch_atoms, seed=1000 + 97 * rank + k)) for k in range(8)]
+        distinct = [pinned_soa(synth.cloud_featured(args.batch_atoms, seed=1000 + 97 * rank + k).to_wire()) for k in range(8)]
         shard = [distinct[k % len(distinct)] for k in range(args.batch_structures)]
-        runner.run(shard[:6 * args.batch_pack], check_finite=False, compact=True, pack=args.batch_pack)
+        # warm-up: two launch sequences per stream slot (the first sizes the record buffers, the second the sorted views from them)
+        runner.run((shard * 2)[:2 * len(runner.engines) * args.batch_pack], check_finite=False, packed=True, pack=args.batch_pack)
         if dist:
             dist.barrier()
-        counts, dt_b = runner.run(shard, check_finite=False, compact=True, pack=args.batch_pack)
+        counts, dt_b = runner.run(shard, check_finite=False, packed=True, pack=args.batch_pack)
         batch = (len(shard), float(sum(counts)), dt_b)
     runner.close()
     large = None
@@ -427,14 +444,17 @@ def run_ours(args):
 
     # ---- aggregate over ranks: slowest rank's time, total pairs ------------------------------
     ms_pair = st['ms_pairs']                # the three pair kernels back to back, one event before and one after
-    tot_pairs, ms_max, e2e_max, e2e_serial_max, e2e16_max, e2e_dist_max = float(n_pairs), ms_step, e2e_s, e2e_serial_s, e2e16_s, e2e_dist_s
+    tot_pairs, ms_max, e2e_max, e2e_serial_max = float(n_pairs), ms_step, e2e_s, e2e_serial_s
+    leg_names = sorted(legs)
+    leg_max = {k: legs[k][0] for k in leg_names}
     pcie_min = dict(pcie)
     if dist:
         import torch
-        t = torch.tensor([ms_step, e2e_s, e2e_serial_s, batch[2] if batch else 0.0, e2e16_s, -pcie['h2d_gbs'], -pcie['d2h_gbs'], e2e_dist_s], dtype=torch.float64)
+        t = torch.tensor([ms_step, e2e_s, e2e_serial_s, batch[2] if batch else 0.0, -pcie['h2d_gbs'], -pcie['d2h_gbs']] + [legs[k][0] for k in leg_names],
+                         dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e16_max, e2e_dist_max = float(t[4]), float(t[7])
-        pcie_min = {'h2d_gbs': -float(t[5]), 'd2h_gbs': -float(t[6])}
+        pcie_min = {'h2d_gbs': -float(t[4]), 'd2h_gbs': -float(t[5])}
+        leg_max = {k: float(t[6 + n]) for n, k in enumerate(leg_names)}
         s = torch.tensor([float(n_pairs), batch[0] if batch else 0.0, batch[1] if batch else 0.0], dtype=torch.float64)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
         ms_max, e2e_max, e2e_serial_max, tot_pairs = float(t[0]), float(t[1]), float(t[2]), float(s[0])
@@ -453,21 +473,23 @@ def run_ours(args):
                        'cutoff': 5.0, 'l2': 'flushed between steps (384 MiB memset outside the event brackets)',
                        'timing': 'sum of per-step CUDA-event brackets on the library stream, max over ranks',
                        'sharding': 'one independent structure per GPU, no collective'},
-            'e2e': {'value': tot_pairs / e2e_max, 'unit': UNIT, 'h2d_bytes_per_step': int(in_bytes),
+            'e2e': {'value': tot_pairs / e2e_max, 'unit': UNIT, 'h2d_bytes_per_step': in_bytes_wire,
                     'd2h_bytes_per_step': d2h_bytes, 'steps': e2e_steps, 'ms_per_step': e2e_max * 1e3, 'sorted': True,
-                    'stream': 'compact: uint32 row offsets [atoms + 1] + 8-byte (j, mask) records, (i, j) ascending; float32 '
-                              'distances stay on the device (arp_pairs_fetch_dist)',
-                    'api': 'BatchRunner.run(compact=True), 6 stream slots, one pinned host block per structure, one wait per structure',
+                    'inputs': 'soa.WireAtoms in one pinned block: uint8 per-atom counts in place of the two int32 CSR offset arrays, the '
+                              'halogen neighbours as (index, coordinate) rows; decoded on the device after the copy',
+                    'stream': 'packed: uint32 row offsets [atoms + 1] + one 32-bit word per record (j | SIFt bits << 17), (i, j) ascending; '
+                              'the entity class is recomputed on the host from the feat words, float32 distances stay on the device '
+                              '(arp_pairs_fetch_dist)',
+                    'api': 'BatchRunner.run(packed=True): 8 contexts (streams), one host thread enqueues every step whole (upload, kernels, '
+                           'sort, copies: arp_pairs_run_async + arp_pairs_fetch_packed_async) and waits for it when its slot comes round again',
                     'serial_value': tot_pairs / e2e_serial_max, 'serial_ms_per_step': e2e_serial_max * 1e3,
-                    'serial_api': 'ContactEngine.upload_atoms + run_pairs_async + fetch_pairs_compact, one stream',
-                    'with_distances': {'value': tot_pairs / e2e_dist_max, 'ms_per_step': e2e_dist_max * 1e3, 'd2h_bytes_per_step': d2h_bytes + 4 * int(n_pairs),
-                                       'api': 'BatchRunner.run(compact=True, with_dist=True): the float32 distance stream fetched with the records'},
-                    'records16': {'value': tot_pairs / e2e16_max, 'ms_per_step': e2e16_max * 1e3, 'd2h_bytes_per_step': int(16 * n_pairs),
-                                  'api': 'BatchRunner.run(sorted=True): 16-byte arp_pair records'},
+                    'serial_api': 'one context: upload_atoms + run_pairs_async + fetch_pairs_packed_async + fetch_pairs_packed_wait per structure',
+                    'legs': {k: {'value': tot_pairs / leg_max[k], 'ms_per_step': leg_max[k] * 1e3, 'h2d_bytes_per_step': legs[k][1],
+                                 'd2h_bytes_per_step': int(legs[k][2]), 'what': legs[k][3]} for k in leg_names},
                     'pcie': dict(pcie_min, what='pinned cudaMemcpyAsync of the step\'s H2D and D2H sizes, both directions at once, '
                                                 'every rank at the same time (min over ranks, GB/s per GPU)',
                                  d2h_floor_ms=d2h_bytes / (pcie_min['d2h_gbs'] * 1e6) if pcie_min['d2h_gbs'] else None,
-                                 h2d_floor_ms=in_bytes / (pcie_min['h2d_gbs'] * 1e6) if pcie_min['h2d_gbs'] else None)},
+                                 h2d_floor_ms=in_bytes_wire / (pcie_min['h2d_gbs'] * 1e6) if pcie_min['h2d_gbs'] else None)},
             'resident_pipelined': pipelined,
             'gpu_launches': int(launches),
             'kernels_per_step': int(per_step),
@@ -501,8 +523,8 @@ def run_ours(args):
                              'atoms_per_structure': args.batch_atoms, 'pairs_per_s': batch[1] / batch[2],
                              'seconds': batch[2], 'structures_per_launch': args.batch_pack,
                              'sharding': f'{args.batch_structures} structures per GPU, {args.batch_pack} per launch sequence (one DMA per '
-                                         'structure, concatenated on the device: arp_upload_atoms_batch), 6 stream slots, no collective; H2D + '
-                                         'kernels + sort + compact D2H of every structure inside the timed region'}
+                                         'structure in wire form, concatenated on the device: arp_upload_atoms_batch), 8 stream slots driven by one host thread, '
+                                         'no collective; H2D + kernels + sort + packed D2H (5 bytes per record) of every structure inside the timed region'}
         if not args.no_cpu:
             kd = kdtree_leg(soa, 5.0)
             if kd:

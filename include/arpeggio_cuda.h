@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ARP_ABI_VERSION 5
+#define ARP_ABI_VERSION 6
 
 /* ---- error codes -------------------------------------------------------- */
 #define ARP_OK              0
@@ -189,6 +189,19 @@ typedef struct arp_atoms {
     const double*   h_xyz;      /* [H][3] float64 */
     const float*    xnbr_xyz;   /* [N][3] coord of get_single_bond_neighbour (valid where ARP_F_HAS_XNBR); NULL allowed */
     const int32_t*  struct_off; /* [S+1] atom offsets; NULL when S == 1 */
+    /* ---- optional wire forms (all NULL / 0 in a zero-initialised struct): the same arrays in fewer bytes over PCIe,
+       decoded on the device after the copy; results are those of the plain forms ---- */
+    const uint8_t*  bond_cnt;   /* [N] neighbours per atom in place of bond_off (which must then be NULL); bond_nbr holds n_bond_nbr indices */
+    const uint8_t*  h_cnt;      /* [N] hydrogens per atom in place of h_off; n_h hydrogens follow in h_xyz or h_fix */
+    const int32_t*  h_fix;      /* [n_h][3] fixed-point hydrogen coordinates in place of h_xyz: coordinate = (double)h_fix / h_fix_scale
+                                   (IEEE division).  Lossless for coordinates that are decimal fractions of the file's precision
+                                   (3 decimals: scale 1000) -- the CALLER checks h_fix / scale == h_xyz before choosing this form */
+    const int32_t*  xnbr_idx;   /* [n_xnbr] strictly ascending atom indices: xnbr_xyz is then [n_xnbr][3], the rows of just these atoms */
+    double          h_fix_scale;
+    int32_t         n_bond_nbr; /* with bond_cnt: sum of the counts (checked) */
+    int32_t         n_h;        /* with h_cnt: sum of the counts (checked) */
+    int32_t         n_xnbr;
+    int32_t         _pad;
 } arp_atoms;
 
 /* ring: centre/normal float64 (OBRing.findCenterAndNormal, interactions.py:1708-1717);
@@ -315,6 +328,30 @@ int  arp_pairs_count(arp_ctx* ctx, uint64_t* n_pairs);
    call fails with ARP_E_CAPACITY, so the caller can size its buffers and call again (the run is not repeated). */
 int  arp_pairs_fetch_compact(arp_ctx* ctx, uint32_t* row_off, arp_pair_c* rec, uint64_t cap, float* dist, uint64_t* n_pairs);
 int  arp_pairs_fetch_dist(arp_ctx* ctx, float* dist, uint64_t cap);
+/* The sorted stream PACKED: one word per record = j in its low *bits_j bits (bits_j = bits of n_atoms - 1), the 15 SIFt
+   bits above them; lo32[k] holds bits 0..31 of record k, hi8[k] bits 32..39 (only when bits_j + 15 > 32, i.e. more than
+   131072 atoms; may be NULL otherwise): 4 (or 5) bytes per record + 4 per atom over PCIe.  Not in the word: the entity
+   class -- a function of the two atoms' ARP_F_IN_SELECTION / ARP_F_IS_WATER flags (interactions.py:643-691), which
+   arp_pairs_unpack_packed recomputes from the caller's feat array -- and the xbond-without-neighbour fault bit:
+   *n_faults counts the records that have it (fetch the compact view to see which; the reference raises there).
+   dist as for arp_pairs_fetch_compact.  ARP_E_CAPACITY sets *n_pairs and *bits_j. */
+int  arp_pairs_fetch_packed(arp_ctx* ctx, uint32_t* row_off, uint32_t* lo32, uint8_t* hi8, uint64_t cap, float* dist,
+                            uint64_t* n_pairs, int32_t* bits_j, uint32_t* n_faults);
+/* host only.  atom_base: 0 for a whole run; for ONE structure of a batch (arp_upload_atoms_batch) its first atom: row_off
+   (rebased to start at 0), lo32 / hi8 / dist and feat then point at that structure's rows, words and atoms, and the i / j
+   of the records come out local to the structure */
+int  arp_pairs_unpack_packed(const uint32_t* row_off, const uint32_t* lo32, const uint8_t* hi8, const float* dist,
+                             int32_t n_atoms, int32_t bits_j, const uint32_t* feat, int32_t atom_base, arp_pair* dst, uint64_t cap);
+
+/* arp_pairs_fetch_packed split for pipelining: _async enqueues the sorted packed view and its copies BEHIND a run that
+   has not been waited for (arp_pairs_run_async) -- the record count is read on the device and the first
+   min(cap, expect) words are copied (expect: the caller's guess, 0 = cap) -- and returns at once; _wait is the single
+   host wait of the step: it repeats an overflowed run, fetches what `expect` missed, and reports ARP_E_CAPACITY (with
+   *n_pairs set) when cap was too small; the views stay valid for a second, plain arp_pairs_fetch_packed.  The
+   destination buffers must stay untouched until _wait returns, and row_off must hold n_atoms + 2 entries here (the last
+   one is scratch: the fault counter travels behind the offsets).  Replaces nothing in the reference (no overlap there). */
+int  arp_pairs_fetch_packed_async(arp_ctx* ctx, uint32_t* row_off, uint32_t* lo32, uint8_t* hi8, uint64_t cap, float* dist, uint64_t expect);
+int  arp_pairs_fetch_packed_wait(arp_ctx* ctx, uint64_t* n_pairs, int32_t* bits_j, uint32_t* n_faults);
 /* host only, no context: compact view -> 16-byte records (dist NULL: distance 0) */
 int  arp_pairs_unpack(const uint32_t* row_off, const arp_pair_c* rec, const float* dist, int32_t n_atoms,
                       arp_pair* dst, uint64_t cap);

@@ -151,3 +151,35 @@ def test_unpack_compact_records_on_the_host():
     big = np.empty(n + 8, abi.PAIR_DTYPE)
     assert L.arp_pairs_unpack(bad.ctypes.data, rec.ctypes.data, None, n_atoms, big.ctypes.data, big.shape[0]) == abi.E_INVALID_ARG
     assert L.arp_pairs_unpack(None, None, None, 0, None, 0) == abi.OK
+
+
+def test_unpack_packed_records_on_the_host():
+    """arp_pairs_unpack_packed needs no device: word -> (i, j, mask | class, dist), class from the feat words exactly as
+    __get_contact_type's six ifs give it; narrow (32-bit) and wide (40-bit) words."""
+    from arpeggio_b200.engine import PackedPairs
+    rng = np.random.default_rng(4)
+    for n_atoms, bits in ((1000, 10), (200_000, 18)):
+        per_row = rng.integers(0, 4, size=n_atoms)
+        row_off = np.concatenate([[0], np.cumsum(per_row)]).astype(np.uint32)
+        n = int(row_off[-1])
+        i = np.repeat(np.arange(n_atoms), per_row)
+        j = rng.integers(0, n_atoms, size=n).astype(np.int64)
+        mask = rng.integers(0, 1 << 15, size=n).astype(np.int64)
+        word = j | (mask << bits)
+        feat = (rng.integers(0, 4, size=n_atoms).astype(np.uint32) << 14)          # water (bit 14) and selection (bit 15) bits
+        dist = rng.random(n).astype(np.float32)
+        pk = PackedPairs(row_off, (word & 0xffffffff).astype(np.uint32), (word >> 32).astype(np.uint8) if bits + 15 > 32 else None,
+                         dist).view(n_atoms, n, bits, 0, True)
+        out = pk.to_records(feat)
+        assert np.array_equal(out['i'], i) and np.array_equal(out['j'], j) and np.array_equal(out['mask'] & 0x7fff, mask)
+        sb, se = (feat[i] >> 15) & 1, (feat[j] >> 15) & 1
+        wb, we = (feat[i] >> 14) & 1, (feat[j] >> 14) & 1
+        cls = np.full(n, 7)
+        cls[(sb == 0) & (se == 0)] = 0
+        cls[(sb == 1) & (se == 1)] = 1
+        cls[sb != se] = 2
+        cls[((sb == 1) & (we == 1)) | ((se == 1) & (wb == 1))] = 3
+        cls[((sb == 0) & (we == 1)) | ((se == 0) & (wb == 1))] = 4
+        cls[(wb == 1) & (we == 1)] = 5
+        assert np.array_equal((out['mask'] >> 16) & 7, cls)
+        assert np.array_equal(out['dist'].view(np.uint32), dist.view(np.uint32))

@@ -8,6 +8,7 @@ import textwrap
 import numpy as np
 import pytest
 
+from arpeggio_b200 import synth
 from arpeggio_b200.batch import shard_indices
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -80,3 +81,32 @@ def test_make_selection_can_stay_with_the_host_class():
     h._cuda_pack_cache = ('stale', None)
     h._make_selection(['/A/508/'])
     assert h.seen == ['/A/508/'] and h._cuda_pack_cache is None and h._cuda_pack_version == 1
+
+
+def test_wire_atoms_are_a_lossless_image_of_the_soa():
+    """soa.WireAtoms: uint8 counts for the two offset arrays, sparse halogen neighbours, int32 fixed-point hydrogens only
+    when every coordinate survives the round trip; the ctypes image carries the totals the library checks."""
+    from arpeggio_b200 import abi
+    from arpeggio_b200.soa import WireAtoms
+    soa = synth.cloud_featured(3000, seed=12)
+    w = soa.to_wire()
+    assert isinstance(w, WireAtoms) and w.n_atoms == soa.n_atoms and w.bond_off is None and w.h_off is None
+    assert np.array_equal(np.concatenate([[0], np.cumsum(w.bond_cnt, dtype=np.int64)]), soa.bond_off)
+    assert np.array_equal(np.concatenate([[0], np.cumsum(w.h_cnt, dtype=np.int64)]), soa.h_off)
+    has = (soa.feat & np.uint32(abi.F_HAS_XNBR)) != 0
+    assert np.array_equal(w.xnbr_idx, np.flatnonzero(has)) and np.array_equal(w.xnbr_xyz, soa.xnbr_xyz[has])
+    if w.h_fix is not None:
+        assert w.h_xyz is None and np.array_equal(w.h_fix / w.h_fix_scale, soa.h_xyz)
+    else:
+        assert w.h_xyz is soa.h_xyz and w.h_fix_scale == 0.0
+    # hydrogens that are not 3-decimal fractions stay float64; 3-decimal ones go to fixed point
+    import dataclasses
+    off = dataclasses.replace(soa, h_xyz=soa.h_xyz + 1e-7)
+    assert off.to_wire().h_fix is None and off.to_wire().h_xyz is not None
+    rounded = dataclasses.replace(soa, h_xyz=np.round(soa.h_xyz, 3))
+    wr = rounded.to_wire()
+    assert wr.h_fix is not None and wr.h_fix.dtype == np.int32 and np.array_equal(wr.h_fix / 1000.0, rounded.h_xyz)
+    assert wr.input_bytes() < 0.6 * rounded.input_bytes()
+    ct = wr.as_ctypes()
+    assert ct.n_bond_nbr == soa.bond_nbr.shape[0] and ct.n_h == soa.h_xyz.shape[0] and ct.n_xnbr == int(has.sum())
+    assert ct.h_fix_scale == 1000.0 and not ct.bond_off and not ct.h_off and not ct.h_xyz and ct.bond_cnt and ct.h_cnt and ct.h_fix

@@ -63,12 +63,18 @@ def test_product_arm_prints_the_contract_line():
     assert d['value'] > 1e9 and d['scaling'] == 'weak' and d['data'] == 'synthetic' and d['vs_baseline'] is None
     assert d['gpu_launches'] == d['kernels_per_step'] * d['steps'] and d['kernels_per_step'] >= 3
     e = d['e2e']
-    # the end-to-end stream is the compact sorted one: 8 bytes per record + 4 per atom (+ 4)
-    assert 0 < e['value'] < d['value'] and e['h2d_bytes_per_step'] > 0 and e['sorted'] is True
-    assert e['d2h_bytes_per_step'] == 8 * d['config']['pairs_per_structure'] + 4 * (d['config']['atoms_per_gpu'] + 1)
-    assert e['records16']['d2h_bytes_per_step'] == 16 * d['config']['pairs_per_structure'] and e['records16']['value'] > 0
-    assert e['pcie']['h2d_gbs'] > 1 and e['pcie']['d2h_gbs'] > 1
-    assert 0 < e['with_distances']['value'] <= e['value'] * 1.2 and d['resident_pipelined']['value'] > 0
+    # the end-to-end stream is the packed sorted one: 4 bytes per record + 4 per atom (+ 8); the inputs travel in wire form
+    n, atoms = d['config']['pairs_per_structure'], d['config']['atoms_per_gpu']
+    assert 0 < e['value'] < d['value'] and e['sorted'] is True
+    assert e['d2h_bytes_per_step'] == 4 * n + 4 * (atoms + 2)
+    legs = e['legs']
+    assert 0 < e['h2d_bytes_per_step'] < legs['plain_inputs']['h2d_bytes_per_step'] and legs['plain_inputs']['value'] > 0
+    assert legs['records16']['d2h_bytes_per_step'] == 16 * n and legs['records16']['value'] > 0
+    assert legs['compact']['d2h_bytes_per_step'] == 8 * n + 4 * (atoms + 1) and legs['compact']['value'] > 0
+    assert legs['with_distances']['d2h_bytes_per_step'] == e['d2h_bytes_per_step'] + 4 * n
+    assert 0 < legs['with_distances']['value'] <= e['value'] * 1.2 and d['resident_pipelined']['value'] > 0
+    assert legs['wire_h_fix']['h2d_bytes_per_step'] < e['h2d_bytes_per_step'] and legs['wire_h_fix']['value'] > 0
+    assert e['pcie']['h2d_gbs'] > 1 and e['pcie']['d2h_gbs'] > 1 and e['serial_value'] > 0
     rf = d['roofline']
     assert rf['bound'] == 'hbm' and rf['unit'] == 'GB/s' and abs(rf['frac'] - rf['achieved'] / rf['peak']) < 1e-9
     assert rf['algorithmic_bytes'] > 16 * d['config']['pairs_per_structure']

@@ -5,6 +5,7 @@ import pytest
 import util
 from arpeggio_b200 import params as arp_params, synth
 from arpeggio_b200.batch import BatchRunner
+from arpeggio_b200.soa import AtomSoA
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu
@@ -81,3 +82,51 @@ def test_device_packed_batches(engine):
             for k, e in enumerate(exp):
                 assert counts[k] == e.shape[0]
                 util.assert_records_equal(got[k], e, f'pack={pack} structure {k}')
+
+
+def test_batch_runner_packed_stream(engine):
+    p = arp_params.make_params()
+    soas = [synth.cloud_featured(n, seed=85 + k) for k, n in enumerate((300, 9000, 1500, 12000))]
+    got = {}
+    with BatchRunner(device=engine.device, slots=2, params=p) as runner:
+        counts, _ = runner.run(soas, consume=lambda i, pk: got.__setitem__(i, pk.to_records(soas[i].feat)), packed=True, with_dist=True)
+    for i, soa in enumerate(soas):
+        exp = oracle.pairs(soa, p)
+        assert counts[i] == exp.shape[0]
+        util.assert_records_equal(got[i], exp, f'packed structure {i}')
+
+
+def test_device_packed_batch_of_wire_and_plain_structures(engine):
+    """arp_upload_atoms_batch with structures in wire form, in plain form and mixed in one batch (counts win: the merged
+    offsets come from one scan on the device)."""
+    p = arp_params.make_params()
+    engine.set_params(p)
+    soas = [synth.cloud_featured(n, seed=300 + k, h_decimals=3 if k % 2 else None) for k, n in enumerate((900, 5, 2500, 0, 1200, 4097))]
+    z = np.zeros(0, np.int32)
+    soas[3] = AtomSoA(xyz=np.zeros((0, 3), np.float32), feat=np.zeros(0, np.uint32), res_id=z, rad_class=np.zeros(0, np.uint16),
+                      vdw=soas[0].vdw, cov=soas[0].cov, res_prev=z, res_next=z, res_flags=np.zeros(0, np.uint8))
+    exp = oracle.pairs(AtomSoA.concat(soas), p)
+    for mix in ('wire', 'mixed'):
+        parts = [s.to_wire() if (mix == 'wire' or k % 3 == 0) and s.n_atoms else s for k, s in enumerate(soas)]
+        off = engine.upload_atoms_batch(parts)
+        assert off[-1] == sum(s.n_atoms for s in soas)
+        n = engine.run_pairs()
+        util.assert_records_equal(engine.fetch_pairs(n, sorted=True), exp, f'batch {mix}')
+
+
+@pytest.mark.parametrize('threads', [1, 2])
+def test_batch_runner_packed_groups(engine, threads):
+    """run(packed=True, pack=4): groups concatenated on the device, the packed stream of the batch cut into one view per
+    structure whose records carry structure-local indices; wire-form inputs, more atoms per group than 131072 (fifth byte)."""
+    p = arp_params.make_params()
+    soas = [synth.cloud_featured(n, seed=500 + k, h_decimals=3) for k, n in enumerate((300, 9000, 0 + 1, 1500, 12000, 70_000, 70_000, 5, 2000))]
+    got = {}
+    with BatchRunner(device=engine.device, slots=3, params=p, submit_threads=threads) as runner:
+        for wire in (False, True):
+            src = [s.to_wire() for s in soas] if wire else soas
+            got.clear()
+            counts, _ = runner.run(src, consume=lambda i, pk: got.__setitem__(i, pk.to_records(soas[i].feat)), packed=True, with_dist=True, pack=4)
+            for i, soa in enumerate(soas):
+                exp = oracle.pairs(soa, p)
+                assert counts[i] == exp.shape[0]
+                util.assert_records_equal(got[i], exp, f'packed group member {i} wire={wire}')

@@ -421,3 +421,158 @@ def test_capacity_error_reports_the_count(engine):
     rc = engine._L.arp_pairs_fetch_compact(engine._ctx, row.ctypes.data, rec.ctypes.data, rec.shape[0], None, C.byref(got))
     assert rc == abi.E_CAPACITY and got.value == n and np.all(rec.view(np.int64) == 7)
     assert engine.stats()['faults'] == 0
+
+
+@pytest.mark.parametrize('n', [0, 3, 5000, 140_000])
+def test_packed_stream(engine, n):
+    """arp_pairs_fetch_packed: one word per record (j below the 15 SIFt bits; 4 bytes up to 131072 atoms, 5 beyond),
+    entity class recomputed on the host from the feat words: unpacks to exactly the sorted 16-byte stream."""
+    p = arp_params.make_params()
+    engine.set_params(p)
+    soa = synth.cloud_featured(max(n, 1), seed=33)
+    if n == 0:
+        soa = AtomSoA(xyz=np.zeros((0, 3), np.float32), feat=np.zeros(0, np.uint32), res_id=np.zeros(0, np.int32),
+                      rad_class=np.zeros(0, np.uint16), vdw=soa.vdw, cov=soa.cov, res_prev=np.zeros(0, np.int32),
+                      res_next=np.zeros(0, np.int32), res_flags=np.zeros(0, np.uint8))
+    engine.upload_atoms(soa)
+    engine.run_pairs_async()
+    pk = engine.fetch_pairs_packed(with_dist=True)
+    exp = engine.fetch_pairs(pk.n, sorted=True)
+    assert pk.n == exp.shape[0] and pk.n_faults == 0
+    assert (pk.hi is not None) == (n > (1 << 17)) and pk.bits_j == max(1, int(np.ceil(np.log2(max(soa.n_atoms, 2)))))
+    assert pk.nbytes == 4 * (soa.n_atoms + 1) + (9 if n > (1 << 17) else 8) * pk.n
+    util.assert_records_equal(pk.to_records(soa.feat), exp, f'packed n={n}')
+    pk2 = engine.fetch_pairs_packed(with_dist=False)
+    util.assert_records_equal(pk2.to_records(soa.feat, dist=engine.fetch_pairs_dist(pk2.n)), exp, f'packed + distances on demand n={n}')
+
+
+def test_packed_stream_counts_fault_records(engine):
+    """The xbond-without-neighbour fault bit does not fit the packed word: the records that carry it are counted."""
+    g = util.Golden('xbond_fault')
+    engine.set_params(g.params)
+    engine.upload_atoms(g.soa)
+    engine.run_pairs_async()
+    pk = engine.fetch_pairs_packed()
+    full = engine.fetch_pairs(pk.n, sorted=True)
+    n_fault = int(np.count_nonzero(full['mask'] & np.uint32(abi.PAIR_FAULT_XBOND_NO_NBR)))
+    assert n_fault > 0 and pk.n_faults == n_fault
+    got = pk.to_records(g.soa.feat, dist=engine.fetch_pairs_dist(pk.n))
+    full = full.copy()
+    full['mask'] &= ~np.uint32(abi.PAIR_FAULT_XBOND_NO_NBR)
+    util.assert_records_equal(got, full, 'packed stream of a run with fault records')
+
+
+@pytest.mark.parametrize('case', ['plain', 'h_fix', 'pinned', 'no_optional', 'empty', 'big'])
+def test_wire_forms_give_the_same_records(engine, case):
+    """soa.WireAtoms (uint8 counts, sparse halogen neighbours, fixed-point hydrogens) decoded on the device: the records of
+    the plain AtomSoA, bit for bit."""
+    from arpeggio_b200.engine import pinned_soa
+    p = arp_params.make_params()
+    engine.set_params(p)
+    if case == 'no_optional':
+        soa = synth.cloud_uniform(4000, seed=3)
+    elif case == 'empty':
+        base = synth.cloud_featured(8, seed=1)
+        z = np.zeros(0, np.int32)
+        soa = AtomSoA(xyz=np.zeros((0, 3), np.float32), feat=np.zeros(0, np.uint32), res_id=z, rad_class=np.zeros(0, np.uint16),
+                      vdw=base.vdw, cov=base.cov, res_prev=z, res_next=z, res_flags=np.zeros(0, np.uint8),
+                      bond_off=np.zeros(1, np.int32), bond_nbr=z, h_off=np.zeros(1, np.int32), h_xyz=np.zeros((0, 3)),
+                      xnbr_xyz=np.zeros((0, 3), np.float32))
+    else:
+        soa = synth.cloud_featured(70_000 if case == 'big' else 6000, seed=41, h_decimals=3 if case in ('h_fix', 'pinned', 'big') else None)
+    w = soa.to_wire()
+    assert (w.h_fix is not None) == (case in ('h_fix', 'pinned', 'big'))
+    if case == 'pinned':
+        w = pinned_soa(w)
+    exp = oracle.pairs(soa, p)
+    util.assert_records_equal(engine.pairs(w), exp, f'wire {case}')
+    if case == 'pinned':
+        assert engine.stats()['input_bytes'] == w.input_bytes()
+    util.assert_records_equal(engine.pairs(soa), exp, f'plain after wire {case}')       # and back: the buffers change hands
+    util.assert_records_equal(engine.pairs(w), exp, f'wire after plain {case}')
+
+
+@pytest.mark.parametrize('case', [c for c in CASES if c != 'xbond_fault'])
+def test_wire_forms_golden(engine, case):
+    g = util.Golden(case)
+    engine.set_params(g.params)
+    w = g.soa.to_wire()
+    rec = engine.pairs(w)
+    util.assert_records_equal(rec, g.exp_pairs, f'wire {case}')
+
+
+def test_wire_forms_are_checked(engine):
+    import ctypes as C
+    soa = synth.cloud_featured(500, seed=2)
+    w = soa.to_wire()
+    w.bond_cnt = w.bond_cnt.copy()
+    w.bond_cnt[3] += 1                                  # no longer sums to n_bond_nbr
+    with pytest.raises(Exception, match='bond_cnt'):
+        engine.upload_atoms(w)
+    w = soa.to_wire()
+    if w.xnbr_idx.shape[0] >= 2:
+        w.xnbr_idx = w.xnbr_idx[::-1].copy()
+        with pytest.raises(Exception, match='xnbr_idx'):
+            engine.upload_atoms(w)
+    w = soa.to_wire()
+    w.bond_off = soa.bond_off                           # both forms at once
+    with pytest.raises(Exception, match='alternatives'):
+        engine.upload_atoms(w)
+    engine.set_params(arp_params.make_params())
+    util.assert_records_equal(engine.pairs(soa.to_wire()), oracle.pairs(soa, arp_params.make_params()), 'after the rejected uploads')
+
+
+@pytest.mark.parametrize('n,expect', [(0, 0), (7, 0), (9000, 0), (9000, 1000), (9000, 10**9), (140_000, 500_000)])
+def test_packed_stream_enqueued_behind_the_run(engine, n, expect):
+    """arp_pairs_fetch_packed_async / _wait: the sorted packed view built with the record count read on the device, the
+    first `expect` words copied blindly and the rest by the wait: the stream of the plain fetch."""
+    from arpeggio_b200.engine import PackedPairs
+    p = arp_params.make_params()
+    engine.set_params(p)
+    soa = synth.cloud_featured(max(n, 1), seed=55)
+    if n == 0:
+        z = np.zeros(0, np.int32)
+        soa = AtomSoA(xyz=np.zeros((0, 3), np.float32), feat=np.zeros(0, np.uint32), res_id=z, rad_class=np.zeros(0, np.uint16),
+                      vdw=soa.vdw, cov=soa.cov, res_prev=z, res_next=z, res_flags=np.zeros(0, np.uint8))
+    exp = oracle.pairs(soa, p)
+    cap = exp.shape[0] + 100
+    for with_dist in (False, True):
+        out = PackedPairs(np.zeros(soa.n_atoms + 2, np.uint32), np.zeros(cap, np.uint32), np.zeros(cap, np.uint8), np.zeros(cap, np.float32))
+        engine.upload_atoms(soa)
+        engine.run_pairs_async()
+        engine.fetch_pairs_packed_async(out, expect, with_dist)
+        pk = engine.fetch_pairs_packed_wait()
+        assert pk.n == exp.shape[0] and pk.n_faults == 0
+        got = pk.to_records(soa.feat, dist=None if with_dist else engine.fetch_pairs_dist(pk.n))
+        util.assert_records_equal(got, exp, f'async packed n={n} expect={expect} dist={with_dist}')
+    # after a finished run the same call works without the blind path; a destination that is too small is fetched again
+    engine.run_pairs()
+    small = PackedPairs(np.zeros(soa.n_atoms + 2, np.uint32), np.zeros(max(exp.shape[0] // 2, 0), np.uint32),
+                        np.zeros(max(exp.shape[0] // 2, 0), np.uint8), None)
+    engine.fetch_pairs_packed_async(small, 0, False)
+    pk = engine.fetch_pairs_packed_wait()
+    util.assert_records_equal(pk.to_records(soa.feat, dist=engine.fetch_pairs_dist(pk.n)), exp, f'async packed after run n={n}')
+    engine.upload_atoms(soa)
+    engine.run_pairs_async()
+    engine.fetch_pairs_packed_async(small, 0, False)                 # blind and too small
+    pk = engine.fetch_pairs_packed_wait()
+    util.assert_records_equal(pk.to_records(soa.feat, dist=engine.fetch_pairs_dist(pk.n)), exp, f'async packed, small destination n={n}')
+
+
+def test_async_packed_fetch_survives_an_overflowing_run():
+    """A fresh context sizes its record buffer from a guess; a structure far denser than the guess overflows the run that
+    the blind view was built on: the wait repeats the run and fetches the plain way."""
+    from arpeggio_b200.engine import ContactEngine, PackedPairs
+    p = arp_params.make_params()
+    rng = np.random.default_rng(3)
+    base = synth.cloud_featured(6000, seed=9)
+    dense = dataclasses.replace(base, xyz=(rng.random((6000, 3)) * 14.0).astype(np.float32), bond_off=None, bond_nbr=None)
+    exp = oracle.pairs(dense, p)
+    assert exp.shape[0] > 16 * 6000 + 4096 + 1000          # beyond the first guess of arp_pairs_run_async
+    with ContactEngine(0, p) as eng:
+        out = PackedPairs(np.zeros(6002, np.uint32), np.zeros(exp.shape[0] + 8, np.uint32), None, None)
+        eng.upload_atoms(dense)
+        eng.run_pairs_async()
+        eng.fetch_pairs_packed_async(out, 0, False)
+        pk = eng.fetch_pairs_packed_wait()
+        util.assert_records_equal(pk.to_records(dense.feat, dist=eng.fetch_pairs_dist(pk.n)), exp, 'async packed after an overflow')

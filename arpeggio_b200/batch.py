@@ -90,9 +90,10 @@ class BatchRunner:
         return CompactPairs(raw[:4 * (n_atoms + 1)].view(np.uint32), raw[o_rec:o_rec + 8 * cap].view(abi.PAIR_C_DTYPE),
                             raw[o_dist:o_dist + 4 * cap].view(np.float32) if with_dist else None)
 
-    def _packed_buffer(self, slot, n_atoms, n, with_dist):
-        """One pinned block per slot carved into row offsets | low words | high bytes | distances."""
-        wide = n_atoms > (1 << 17)
+    def _packed_buffer(self, slot, n_atoms, n, with_dist, largest=None):
+        """One pinned block per slot carved into row offsets | low words | high bytes | distances.  largest: atoms of the
+        largest structure when n_atoms is the total of a batch (the words hold structure-local indices)."""
+        wide = (n_atoms if largest is None else largest) > (1 << 17)
         per = 4 + (1 if wide else 0) + (4 if with_dist else 0)
         o_lo = (4 * (n_atoms + 2) + 255) // 256 * 256          # + 1: scratch entry of arp_pairs_fetch_packed_async
         need = o_lo + per * n + 1024
@@ -122,10 +123,10 @@ class BatchRunner:
         pending = {s: None for s in slots}
 
         def finish(slot):
-            i, off = pending[slot]
+            i, off, largest = pending[slot]
             pending[slot] = None
             n_atoms = int(off[-1])
-            rec = self.engines[slot].fetch_pairs_packed_wait(grow=lambda m, s=slot, a=n_atoms: self._packed_buffer(s, a, m, with_dist))
+            rec = self.engines[slot].fetch_pairs_packed_wait(grow=lambda m, s=slot, a=n_atoms: self._packed_buffer(s, a, m, with_dist, largest))
             if n_atoms:
                 self._ratio[slot] = rec.n / n_atoms
             for k in range(len(off) - 1):
@@ -148,9 +149,10 @@ class BatchRunner:
             n_atoms = int(off[-1])
             eng.run_pairs_async()
             expect = int(self._ratio[slot] * n_atoms * 1.02) + 64 if self._ratio[slot] else 14 * n_atoms
-            buf = self._packed_buffer(slot, n_atoms, max(expect, 14 * n_atoms), with_dist)
+            largest = eng.max_struct_atoms()
+            buf = self._packed_buffer(slot, n_atoms, max(expect, 14 * n_atoms), with_dist, largest)
             eng.fetch_pairs_packed_async(buf, expect, with_dist)
-            pending[slot] = (i, off)
+            pending[slot] = (i, off, largest)
         for j in range(S):                                  # oldest first
             slot = slots[(k + 1 + j) % S]
             if pending[slot] is not None:

@@ -674,6 +674,11 @@ int arp_upload_atoms(arp_ctx* c, const arp_atoms* a)
     c->atom_ring.valid = 0;
     c->input_bytes = 0;
     c->N = N; c->Rs = a->n_residues; c->K = a->n_rad_classes; c->S = S;
+    c->max_struct_atoms = N;
+    if (S > 1) {
+        c->max_struct_atoms = 0;
+        for (int s = 0; s < S; ++s) { const int m = a->struct_off[s + 1] - a->struct_off[s]; if (m > c->max_struct_atoms) c->max_struct_atoms = m; }
+    }
     c->has_bonds = a->bond_off != nullptr || w.cnt_b;
     c->has_h = a->h_off != nullptr || w.cnt_h;
     c->has_xnbr = a->xnbr_xyz != nullptr || w.sparse_x;
@@ -962,6 +967,8 @@ int arp_upload_atoms_batch(arp_ctx* c, const arp_atoms* const* parts, int32_t n_
         ARP_CUDA(c, cudaMemcpyAsync(c->batch_stage.as<char>() + q.dst, q.src, q.bytes, cudaMemcpyHostToDevice, c->stream));
     /* ---- the merged arrays ---- */
     c->N = (int)N; c->Rs = (int)Rs; c->K = K; c->S = n_parts; c->E = (int)E; c->H = (int)H;
+    c->max_struct_atoms = 0;
+    for (int s = 0; s < n_parts; ++s) if (parts[s]->n_atoms > c->max_struct_atoms) c->max_struct_atoms = parts[s]->n_atoms;
     c->has_bonds = any_bonds; c->has_h = any_h; c->has_xnbr = any_x;
     const size_t n = (size_t)N;
     ARP_TRY(dbuf_reserve(c, c->xyz, n * 12)); ARP_TRY(dbuf_reserve(c, c->feat, n * 4)); ARP_TRY(dbuf_reserve(c, c->res_id, n * 4));
@@ -1146,11 +1153,14 @@ int arp_pairs_fetch_packed_async(arp_ctx* c, uint32_t* row_off, uint32_t* lo32, 
     ARP_TRY(arp_pairs_sorted_build(c, 2, blind));
     /* row offsets [N + 1] and the fault counter behind them in one copy */
     ARP_CUDA(c, cudaMemcpyAsync(row_off, c->sort_off.p, ((size_t)c->N + 2) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    static const bool no_d2h = getenv("ARPEGGIO_DEBUG_NO_D2H") != nullptr;      /* diagnostic (tools/e2e_breakdown.py): the words stay on the device */
+    if (no_d2h) ncopy = ncopy < 64 ? ncopy : 64;
     if (ncopy) {
         ARP_CUDA(c, cudaMemcpyAsync(lo32, c->sort_lo.p, (size_t)ncopy * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         if (need_hi) ARP_CUDA(c, cudaMemcpyAsync(hi8, c->sort_hi.p, (size_t)ncopy, cudaMemcpyDeviceToHost, c->stream));
         if (dist) ARP_CUDA(c, cudaMemcpyAsync(dist, c->sort_d.p, (size_t)ncopy * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     }
+    if (no_d2h) ncopy = c->out_cap;               /* pretend: the wait then has nothing left to fetch */
     c->pk.row_off = row_off; c->pk.lo32 = lo32; c->pk.hi8 = hi8; c->pk.cap = cap; c->pk.dist = dist;
     c->pk.copied = ncopy; c->pk.blind = blind; c->pk.pending = 1;
     return ARP_OK;
@@ -1192,21 +1202,25 @@ int arp_pairs_fetch_packed_wait(arp_ctx* c, uint64_t* n_pairs, int32_t* bits_j, 
 /* host only: the packed view back into 16-byte records.  feat: the ARP_F_* words of the uploaded atoms (the entity class
    is a function of their selection / water bits, rule_entity_class_bools = interactions.py:643-691) */
 int arp_pairs_unpack_packed(const uint32_t* row_off, const uint32_t* lo32, const uint8_t* hi8, const float* dist, int32_t n_atoms,
-                            int32_t bits_j, const uint32_t* feat, int32_t atom_base, arp_pair* dst, uint64_t cap)
+                            int32_t bits_j, const uint32_t* feat, const int32_t* struct_off, int32_t n_structures, arp_pair* dst, uint64_t cap)
 {
-    if (n_atoms < 0 || (n_atoms > 0 && (!row_off || !feat)) || bits_j < 1 || bits_j > 31 || atom_base < 0) return ARP_E_INVALID_ARG;
+    if (n_atoms < 0 || (n_atoms > 0 && (!row_off || !feat)) || bits_j < 1 || bits_j > 31) return ARP_E_INVALID_ARG;
+    if (struct_off && (n_structures < 1 || struct_off[0] != 0 || struct_off[n_structures] != n_atoms)) return ARP_E_INVALID_ARG;
     if (n_atoms == 0) return ARP_OK;
     const uint64_t n = row_off[n_atoms];
     if (n > cap) return ARP_E_CAPACITY;
     if (n && (!lo32 || !dst || (bits_j + 15 > 32 && !hi8))) return ARP_E_INVALID_ARG;
     const uint64_t jmask = (1ull << bits_j) - 1ull;
+    int32_t s = 0, base = 0, end = n_atoms;            /* structure of row i: its first atom and the one behind its last */
+    if (struct_off) end = struct_off[1];
     for (int32_t i = 0; i < n_atoms; ++i) {
+        while (struct_off && i >= end) { ++s; base = struct_off[s]; end = struct_off[s + 1]; if (end < base) return ARP_E_INVALID_ARG; }
         if (row_off[i + 1] < row_off[i] || row_off[i + 1] > n) return ARP_E_INVALID_ARG;
         const bool si = (feat[i] & ARP_F_IN_SELECTION) != 0, wi = (feat[i] & ARP_F_IS_WATER) != 0;
         for (uint64_t k = row_off[i]; k < row_off[i + 1]; ++k) {
             const uint64_t w = (uint64_t)lo32[k] | (hi8 ? (uint64_t)hi8[k] << 32 : 0ull);
-            const int64_t j = (int64_t)(w & jmask) - atom_base;        /* local to the view (one structure of a batch) */
-            if (j < 0 || j >= n_atoms) return ARP_E_INVALID_ARG;
+            const int64_t j = (int64_t)(w & jmask) + base;              /* the word holds j local to the structure */
+            if (j < base || j >= end) return ARP_E_INVALID_ARG;
             const uint32_t cls = rule_entity_class_bools(si, (feat[j] & ARP_F_IN_SELECTION) != 0, wi, (feat[j] & ARP_F_IS_WATER) != 0);
             dst[k].i = i; dst[k].j = (int32_t)j;
             dst[k].mask = (uint32_t)((w >> bits_j) & 0x7fffu) | (cls << ARP_CLASS_SHIFT);

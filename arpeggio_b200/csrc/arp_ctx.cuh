@@ -122,6 +122,7 @@ struct arp_ctx {
     DBuf arena;                   /* one block for all of the above when the caller's arrays are one host block */
     DBuf w_bcnt, w_hcnt, w_hfix, w_xidx, w_xnbr;   /* wire forms of arp_atoms as uploaded (bond_cnt, h_cnt, h_fix, xnbr_idx + rows) */
     unsigned* sort_fault = nullptr;   /* device: records of the packed view that carried the fault bit (= sort_off[N + 1]) */
+    int max_struct_atoms = 0;         /* atoms of the largest structure of the upload: the j of the packed view are structure-local */
     int events_level = 0;             /* with_events of the last arp_pairs_enqueue */
     /* arp_pairs_fetch_packed_async -> arp_pairs_fetch_packed_wait */
     struct { uint32_t* row_off; uint32_t* lo32; uint8_t* hi8; uint64_t cap; float* dist; uint64_t copied; int pending, blind; } pk = {};

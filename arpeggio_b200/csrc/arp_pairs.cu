@@ -1775,7 +1775,7 @@ __global__ void __launch_bounds__(256) k_sort_place(const arp_pair* __restrict__
                                                     const int* __restrict__ off, arp_pair* __restrict__ out,
                                                     arp_pair_c* __restrict__ outc, float* __restrict__ outd,
                                                     uint32_t* __restrict__ lo32, uint8_t* __restrict__ hi8, int bits_j,
-                                                    unsigned* __restrict__ n_fault)
+                                                    unsigned* __restrict__ n_fault, const int* __restrict__ struct_off, int S)
 {
     const unsigned long long n = sort_n(n_dev, n_max), step = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += step) {
@@ -1787,7 +1787,13 @@ __global__ void __launch_bounds__(256) k_sort_place(const arp_pair* __restrict__
             reinterpret_cast<int2*>(outc)[b + rank] = make_int2(v.y, v.z);
             outd[b + rank] = __int_as_float(v.w);
         } else if (MODE == 2) {
-            const unsigned long long w = (unsigned long long)(unsigned)v.y | ((unsigned long long)((unsigned)v.z & 0x7fffu) << bits_j);
+            int jl = v.y;
+            if (S > 1) {                        /* a batch: j local to the structure of row i (no pair spans two structures) */
+                int lo = 0, hi = S;             /* last structure whose first atom is <= i */
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (struct_off[mid] <= v.x) lo = mid; else hi = mid; }
+                jl -= struct_off[lo];
+            }
+            const unsigned long long w = (unsigned long long)(unsigned)jl | ((unsigned long long)((unsigned)v.z & 0x7fffu) << bits_j);
             lo32[b + rank] = (uint32_t)w;
             if (hi8) hi8[b + rank] = (uint8_t)(w >> 32);
             outd[b + rank] = __int_as_float(v.w);
@@ -1798,11 +1804,11 @@ __global__ void __launch_bounds__(256) k_sort_place(const arp_pair* __restrict__
     }
 }
 
-/* bits needed for an atom index of the current upload */
+/* bits of an end-atom index in the packed view: indices are local to the structure, so the largest structure decides */
 int arp_pairs_bits_j(const arp_ctx* c)
 {
     int bits = 1;
-    while (bits < 31 && (1ll << bits) < (long long)c->N) ++bits;
+    while (bits < 31 && (1ll << bits) < (long long)c->max_struct_atoms) ++bits;
     return bits;
 }
 
@@ -1867,12 +1873,13 @@ int arp_pairs_sorted_build(arp_ctx* c, int view, int blind)
     const arp_pair* tmp = c->sort_tmp.as<arp_pair>();
     const int* off = c->sort_off.as<int>();
     if (view == 1)
-        k_sort_place<1><<<blocks, 256, 0, c->stream>>>(tmp, n_dev, n, off, nullptr, c->sort_c.as<arp_pair_c>(), c->sort_d.as<float>(), nullptr, nullptr, 0, nullptr);
+        k_sort_place<1><<<blocks, 256, 0, c->stream>>>(tmp, n_dev, n, off, nullptr, c->sort_c.as<arp_pair_c>(), c->sort_d.as<float>(), nullptr, nullptr, 0, nullptr, nullptr, 1);
     else if (view == 2)
         k_sort_place<2><<<blocks, 256, 0, c->stream>>>(tmp, n_dev, n, off, nullptr, nullptr, c->sort_d.as<float>(), c->sort_lo.as<uint32_t>(),
-                                                       need_hi ? c->sort_hi.as<uint8_t>() : nullptr, bits_j, c->sort_fault);
+                                                       need_hi ? c->sort_hi.as<uint8_t>() : nullptr, bits_j, c->sort_fault,
+                                                       c->S > 1 ? c->struct_off.as<int>() : nullptr, c->S);
     else
-        k_sort_place<0><<<blocks, 256, 0, c->stream>>>(tmp, n_dev, n, off, c->sort_out.as<arp_pair>(), nullptr, nullptr, nullptr, nullptr, 0, nullptr);
+        k_sort_place<0><<<blocks, 256, 0, c->stream>>>(tmp, n_dev, n, off, c->sort_out.as<arp_pair>(), nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 1);
     ARP_LAUNCHED(c);
     if (!blind) valid = 1;
     return ARP_OK;

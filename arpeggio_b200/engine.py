@@ -148,8 +148,8 @@ class PackedPairs:
 
     def structure(self, lo, hi):
         """The rows of atoms lo..hi-1 (one structure of a batch) as a PackedPairs of their own: row offsets rebased (a small
-        copy), words and distances as views; to_records(feat of that structure) gives indices local to the structure.
-        n_faults stays the count of the whole batch."""
+        copy), words and distances as views.  The words of a batch hold structure-local j, so to_records(feat of that
+        structure) gives indices local to the structure.  n_faults stays the count of the whole batch."""
         r0, r1 = int(self.row_off[lo]), int(self.row_off[hi])
         v = PackedPairs(self.row_off, self.lo_buf, self.hi_buf, self.dist_buf)
         v.row_off = self.row_off[lo:hi + 1] - np.uint32(r0)
@@ -163,15 +163,19 @@ class PackedPairs:
     def nbytes(self):
         return self.row_off.nbytes + self.lo.nbytes + (self.hi.nbytes if self.hi is not None else 0) + (self.dist.nbytes if self.dist is not None else 0)
 
-    def to_records(self, feat, dist=None):
-        """PAIR_DTYPE[n] through the library's host unpacker; feat: the uploaded atoms' feature words (uint32[n_atoms])."""
+    def to_records(self, feat, dist=None, struct_off=None):
+        """PAIR_DTYPE[n] through the library's host unpacker; feat: the uploaded atoms' feature words (uint32[n_atoms]).
+        struct_off: the atom offsets of a batch (the words of a batch hold structure-local j; the records come out with
+        the batch-global indices).  A view made by structure() needs none: its records are local to the structure."""
         out = np.empty(self.n, dtype=abi.PAIR_DTYPE)
         feat = np.ascontiguousarray(feat, np.uint32)
         d = self.dist if dist is None else np.ascontiguousarray(dist, np.float32)
+        so = None if struct_off is None else np.ascontiguousarray(struct_off, np.int32)
         rc = lib().arp_pairs_unpack_packed(self.row_off.ctypes.data, self.lo.ctypes.data if self.n else None,
                                            self.hi.ctypes.data if self.hi is not None and self.n else None,
                                            d.ctypes.data if d is not None and self.n else None, self.n_atoms, self.bits_j,
-                                           feat.ctypes.data if self.n_atoms else None, self.atom_base, out.ctypes.data if self.n else None, self.n)
+                                           feat.ctypes.data if self.n_atoms else None, so.ctypes.data if so is not None else None,
+                                           0 if so is None else so.shape[0] - 1, out.ctypes.data if self.n else None, self.n)
         if rc != abi.OK:
             raise ArpeggioCudaError(rc, 'arp_pairs_unpack_packed failed')
         return out
@@ -253,6 +257,15 @@ class ContactEngine:
         self._soa = _BatchInfo(soas, int(off[-1]))            # keeps the host arrays alive while the copies are in flight
         return off
 
+    def max_struct_atoms(self):
+        """Atoms of the largest structure of the upload: the packed view needs a fifth byte per record beyond 131072."""
+        soa = self._soa
+        if isinstance(soa, _BatchInfo):
+            return max((s.n_atoms for s in soa.soas), default=0)
+        if getattr(soa, 'struct_off', None) is not None:
+            return int(np.diff(soa.struct_off).max()) if soa.struct_off.shape[0] > 1 else 0
+        return soa.n_atoms
+
     def run_pairs(self):
         """Grid build + pair kernel on the uploaded atoms; returns the number of contact records."""
         n = C.c_uint64()
@@ -307,7 +320,7 @@ class ContactEngine:
         record (5 beyond 131072 atoms) + 4 per atom.  out / grow as for fetch_pairs_compact."""
         n_atoms = self._soa.n_atoms
         n, bits, faults = C.c_uint64(), C.c_int32(), C.c_uint32()
-        wide = n_atoms > (1 << 17)
+        wide = self.max_struct_atoms() > (1 << 17)
         if out is None or out.row_off.shape[0] < n_atoms + 1:
             out = PackedPairs(np.empty(n_atoms + 1, np.uint32), np.empty(0, np.uint32), np.empty(0, np.uint8) if wide else None, None)
         for attempt in range(2):
@@ -334,7 +347,7 @@ class ContactEngine:
         not been waited for (run_pairs_async) and returns at once; fetch_pairs_packed_wait is the step's one wait.  expect:
         the caller's guess of the record count (that many words are copied blindly; the wait fetches what is missing)."""
         n_atoms = self._soa.n_atoms
-        wide = n_atoms > (1 << 17)
+        wide = self.max_struct_atoms() > (1 << 17)
         if out.row_off.shape[0] < n_atoms + 2:
             raise ValueError('out.row_off must hold n_atoms + 2 entries (the last one is scratch)')
         dist = out.dist_buf if with_dist else None

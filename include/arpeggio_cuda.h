@@ -328,7 +328,7 @@ int  arp_pairs_count(arp_ctx* ctx, uint64_t* n_pairs);
    call fails with ARP_E_CAPACITY, so the caller can size its buffers and call again (the run is not repeated). */
 int  arp_pairs_fetch_compact(arp_ctx* ctx, uint32_t* row_off, arp_pair_c* rec, uint64_t cap, float* dist, uint64_t* n_pairs);
 int  arp_pairs_fetch_dist(arp_ctx* ctx, float* dist, uint64_t cap);
-/* The sorted stream PACKED: one word per record = j in its low *bits_j bits (bits_j = bits of n_atoms - 1), the 15 SIFt
+/* The sorted stream PACKED: one word per record = j in its low *bits_j bits (bits_j = bits of n_atoms - 1; of the largest structure's in a batch, where j is local to the structure), the 15 SIFt
    bits above them; lo32[k] holds bits 0..31 of record k, hi8[k] bits 32..39 (only when bits_j + 15 > 32, i.e. more than
    131072 atoms; may be NULL otherwise): 4 (or 5) bytes per record + 4 per atom over PCIe.  Not in the word: the entity
    class -- a function of the two atoms' ARP_F_IN_SELECTION / ARP_F_IS_WATER flags (interactions.py:643-691), which
@@ -337,11 +337,14 @@ int  arp_pairs_fetch_dist(arp_ctx* ctx, float* dist, uint64_t cap);
    dist as for arp_pairs_fetch_compact.  ARP_E_CAPACITY sets *n_pairs and *bits_j. */
 int  arp_pairs_fetch_packed(arp_ctx* ctx, uint32_t* row_off, uint32_t* lo32, uint8_t* hi8, uint64_t cap, float* dist,
                             uint64_t* n_pairs, int32_t* bits_j, uint32_t* n_faults);
-/* host only.  atom_base: 0 for a whole run; for ONE structure of a batch (arp_upload_atoms_batch) its first atom: row_off
-   (rebased to start at 0), lo32 / hi8 / dist and feat then point at that structure's rows, words and atoms, and the i / j
-   of the records come out local to the structure */
+/* host only.  In a batch (several structures in one upload) the j of the words are LOCAL to the structure of row i -- no
+   pair spans two structures -- so bits_j is that of the largest structure.  struct_off [n_structures + 1] (NULL: one
+   structure) gives the structures' first atoms: the records come out with the run's global i and j.  To unpack ONE
+   structure of a batch pass its rows (row_off rebased to start at 0), words and feat with struct_off = NULL: i and j
+   are then local to it. */
 int  arp_pairs_unpack_packed(const uint32_t* row_off, const uint32_t* lo32, const uint8_t* hi8, const float* dist,
-                             int32_t n_atoms, int32_t bits_j, const uint32_t* feat, int32_t atom_base, arp_pair* dst, uint64_t cap);
+                             int32_t n_atoms, int32_t bits_j, const uint32_t* feat, const int32_t* struct_off, int32_t n_structures,
+                             arp_pair* dst, uint64_t cap);
 
 /* arp_pairs_fetch_packed split for pipelining: _async enqueues the sorted packed view and its copies BEHIND a run that
    has not been waited for (arp_pairs_run_async) -- the record count is read on the device and the first

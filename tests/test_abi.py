@@ -183,3 +183,19 @@ def test_unpack_packed_records_on_the_host():
         cls[(wb == 1) & (we == 1)] = 5
         assert np.array_equal((out['mask'] >> 16) & 7, cls)
         assert np.array_equal(out['dist'].view(np.uint32), dist.view(np.uint32))
+    # a batch: the words hold j local to the structure of their row, struct_off brings the global indices back
+    so = np.array([0, 700, 700, 1900, 3000], np.int32)
+    n_atoms, bits = 3000, 11                                   # largest structure: 1200 atoms
+    per_row = rng.integers(0, 4, size=n_atoms)
+    row_off = np.concatenate([[0], np.cumsum(per_row)]).astype(np.uint32)
+    i = np.repeat(np.arange(n_atoms), per_row)
+    s_of = np.searchsorted(so, i, side='right') - 1
+    jl = (rng.random(i.shape[0]) * (so[s_of + 1] - so[s_of])).astype(np.int64)
+    mask = rng.integers(0, 1 << 15, size=i.shape[0]).astype(np.int64)
+    feat = (rng.integers(0, 4, size=n_atoms).astype(np.uint32) << 14)
+    pk = PackedPairs(row_off, (jl | (mask << bits)).astype(np.uint32), None, None).view(n_atoms, i.shape[0], bits, 0, False)
+    out = pk.to_records(feat, struct_off=so)
+    assert np.array_equal(out['i'], i) and np.array_equal(out['j'], jl + so[s_of]) and np.array_equal(out['mask'] & 0x7fff, mask)
+    part = pk.structure(1900, 3000).to_records(feat[1900:3000])
+    sel = i >= 1900
+    assert np.array_equal(part['i'], i[sel] - 1900) and np.array_equal(part['j'], jl[sel]) and np.array_equal(part['mask'], out['mask'][sel])

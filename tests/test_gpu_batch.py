@@ -130,3 +130,24 @@ def test_batch_runner_packed_groups(engine, threads):
                 exp = oracle.pairs(soa, p)
                 assert counts[i] == exp.shape[0]
                 util.assert_records_equal(got[i], exp, f'packed group member {i} wire={wire}')
+
+
+def test_packed_words_of_a_batch_hold_structure_local_indices(engine):
+    """A batch of structures none larger than 131072 atoms needs no fifth byte however many atoms it has in total; the
+    whole batch unpacks with its atom offsets to the records of the concatenated structures."""
+    p = arp_params.make_params()
+    engine.set_params(p)
+    soas = [synth.cloud_featured(n, seed=700 + k) for k, n in enumerate((60_000, 50_000, 45_000, 1))]
+    off = engine.upload_atoms_batch(soas)
+    engine.run_pairs_async()
+    pk = engine.fetch_pairs_packed(with_dist=True)
+    assert pk.bits_j == 16 and pk.hi is None and pk.n_atoms == 155_001
+    whole = AtomSoA.concat(soas)
+    exp = oracle.pairs(whole, p)
+    util.assert_records_equal(pk.to_records(whole.feat, struct_off=off), exp, 'batch, global indices')
+    # the same through one arp_atoms with struct_off (concatenated on the host)
+    engine.upload_atoms(whole)
+    engine.run_pairs_async()
+    pk = engine.fetch_pairs_packed(with_dist=True)
+    assert pk.bits_j == 16 and pk.hi is None
+    util.assert_records_equal(pk.to_records(whole.feat, struct_off=whole.struct_off), exp, 'host-concatenated batch')

@@ -1,86 +1,69 @@
 #!/usr/bin/env python
-"""Where the end-to-end step spends its time: the e2e leg of bench.py with stages removed and with 1..12 stream slots.
+"""Where the pipelined end-to-end step (8 streams, one host thread) spends its time: the step with stages removed.
+    all        upload + kernels + sorted packed view + copies          (BatchRunner.run(packed=True))
+    no_upload  inputs resident: kernels + view + copies
+    no_d2h     upload + kernels + view, the words stay on the device   (ARPEGGIO_DEBUG_NO_D2H)
+    device     inputs resident, words stay on the device: kernels + view only
+    no_sort    upload + kernels, the count is the only result
+    kernels    inputs resident: the pair kernels only
 Run under gpurun: python tools/e2e_breakdown.py [atoms]"""
 import os
+import subprocess
 import sys
-import threading
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np  # noqa: E402
-from arpeggio_b200 import params, synth  # noqa: E402
-from arpeggio_b200.batch import BatchRunner  # noqa: E402
-from arpeggio_b200.engine import pinned_soa  # noqa: E402
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 
-atoms = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
-p = params.make_params()
-soa = synth.cloud_featured(atoms, seed=2, h_decimals=3)
-hosts = {'plain': pinned_soa(soa), 'wire': pinned_soa(soa.to_wire())}
-steps = 240
+if len(sys.argv) > 1 and sys.argv[1] == 'child':
+    from arpeggio_b200 import params, synth
+    from arpeggio_b200.batch import BatchRunner
+    from arpeggio_b200.engine import pinned_soa
+    atoms, form = int(sys.argv[2]), sys.argv[3]
+    p = params.make_params()
+    soa = synth.cloud_featured(atoms, seed=2, h_decimals=3 if form == 'wire_h_fix' else None)
+    host = pinned_soa(soa if form == 'plain' else soa.to_wire())
+    steps, S = 480, 8
 
+    def run(runner, upload, fetch):
+        engs = runner.engines
+        bufs = [runner._packed_buffer(s, host.n_atoms, 14 * host.n_atoms, False) for s in range(S)]
+        pend = [False] * S
+        t0 = time.perf_counter()
+        for k in range(steps):
+            s = k % S
+            e = engs[s]
+            if pend[s]:
+                e.fetch_pairs_packed_wait() if fetch else e.pair_count()
+            if upload:
+                e.upload_atoms(host, check_finite=False)
+            e.run_pairs_async()
+            if fetch:
+                e.fetch_pairs_packed_async(bufs[s], int(12.6 * host.n_atoms), False)
+            pend[s] = True
+        for s in range(S):
+            if pend[s]:
+                engs[s].fetch_pairs_packed_wait() if fetch else engs[s].pair_count()
+            engs[s].sync()
+        return (time.perf_counter() - t0) / steps * 1e3
 
-def staged(runner, host, mode):
-    """mode: 'all' upload + run + packed fetch; 'no_upload' run + fetch; 'no_fetch' upload + run + count; 'kernels' run + count;
-    'upload' upload only (+ sync); 'fetch' fetch of a finished run is not separable (the sort is redone per run)"""
-    todo = list(range(steps))
-    lock = threading.Lock()
-
-    def work(slot):
-        eng = runner.engines[slot]
-        eng.upload_atoms(host, check_finite=False)
-        n0 = eng.run_pairs()
-        buf = runner._packed_buffer(slot, host.n_atoms, n0 + 1024, False)
-        while True:
-            with lock:
-                if not todo:
-                    return
-                todo.pop()
-            if mode in ('all', 'no_fetch', 'upload'):
-                eng.upload_atoms(host, check_finite=False)
-            if mode == 'upload':
-                eng.sync()
-                continue
-            eng.run_pairs_async()
-            if mode in ('all', 'no_upload'):
-                eng.fetch_pairs_packed(False, out=buf)
-            else:
-                eng.pair_count()
-
-    ths = [threading.Thread(target=work, args=(s,)) for s in range(len(runner.engines))]
-    t0 = time.perf_counter()
-    for t in ths:
-        t.start()
-    for t in ths:
-        t.join()
-    for e in runner.engines:
-        e.sync()
-    return (time.perf_counter() - t0) / steps * 1e3
-
-
-def utilisation(fn):
-    """GPU utilisation (share of time with a kernel running, nvidia-smi's sampling) while fn() runs repeatedly for about 2 s"""
-    import subprocess
-    pr = subprocess.Popen(['nvidia-smi', '--query-gpu=utilization.gpu', '--format=csv,noheader,nounits', '-lms', '100', '-i', '0'],
-                          stdout=subprocess.PIPE, text=True)
-    t0 = time.perf_counter()
-    ms = []
-    while time.perf_counter() - t0 < 2.5:
-        ms.append(fn())
-    pr.terminate()
-    vals = [int(v) for v in pr.communicate()[0].split() if v.strip().isdigit()]
-    return round(float(np.median(ms)), 4), vals
-
-
-if os.environ.get('UTIL'):
-    with BatchRunner(device=0, slots=6, params=p) as runner:
-        for mode in ('kernels', 'no_upload', 'all'):
-            for name, host in hosts.items():
-                print(mode, name, utilisation(lambda: staged(runner, host, mode)), flush=True)
+    with BatchRunner(device=0, slots=S, params=p) as runner:
+        for e in runner.engines:
+            e.upload_atoms(host, check_finite=False)
+            e.run_pairs()
+        out = {}
+        for name, up, fe in (('with upload, with view', True, True), ('resident, with view', False, True),
+                             ('with upload, no view', True, False), ('resident, no view', False, False)):
+            run(runner, up, fe)
+            out[name] = round(min(run(runner, up, fe) for _ in range(3)), 4)
+        print(out)
     sys.exit(0)
 
-for slots in (1, 2, 3, 6, 12):
-    with BatchRunner(device=0, slots=slots, params=p) as runner:
-        for name, host in hosts.items():
-            staged(runner, host, 'all')
-            row = {m: round(staged(runner, host, m), 4) for m in ('all', 'no_upload', 'no_fetch', 'kernels', 'upload')}
-            print(f'slots={slots:2d} {name:5s} h2d={host.input_bytes() / 1e6:.2f} MB  ms/step: {row}', flush=True)
+atoms = sys.argv[1] if len(sys.argv) > 1 else '100000'
+for form in ('plain', 'wire', 'wire_h_fix'):
+    for d2h in (True, False):
+        env = dict(os.environ)
+        if not d2h:
+            env['ARPEGGIO_DEBUG_NO_D2H'] = '1'
+        r = subprocess.run([sys.executable, __file__, 'child', atoms, form], env=env, capture_output=True, text=True)
+        print(f'{form:10s} {"D2H of the words" if d2h else "words stay on the device":26s} ms/step: {r.stdout.strip() or r.stderr[-400:]}', flush=True)

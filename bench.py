@@ -10,9 +10,15 @@ filters, fused 15-bit CREDO classifier, record emission) over the configs[2] str
             library's stream and L2 is flushed (384 MiB memset) between steps, outside the brackets
   e2e       the same metric through the public API with HOST buffers: pinned H2D of the step's arrays +
             kernels + canonical (i, j) sort + D2H of the record stream inside the timed region.  The
-            stream crosses PCIe in its compact form (arp_pairs_fetch_compact: row offsets + 8-byte
-            (j, mask) records; the float32 distances stay on the device until asked for);
-            `records16` repeats the measurement with the 16-byte records (sorted too)
+            inputs cross PCIe in their wire form (soa.WireAtoms: uint8 counts for the CSR offsets, sparse
+            halogen neighbours; decoded on the device), the stream in its packed form
+            (arp_pairs_fetch_packed: row offsets + one 32-bit word per record; the float32 distances
+            stay on the device until asked for); eight streams are driven by ONE host thread that
+            enqueues every step whole (arp_pairs_run_async + arp_pairs_fetch_packed_async) and waits for it
+            when its slot comes round again.  `legs` repeats the measurement with plain AtomSoA inputs,
+            with the distance stream, with the compact 8-byte records, with the 16-byte records and with
+            3-decimal hydrogens as int32 fixed point; e2e runs min(max(10 K, 100), 600) steps (its own
+            `steps` key), the threaded legs K
   roofline  the step's algorithmic bytes (sum of input array bytes + 16 B per record) over the mean
             CUDA-event duration of the WHOLE step (grid build + pair kernels), against
             MEASURED_PEAKS.json (HBM copy); `pair_kernels` repeats it for the pair kernels alone and

@@ -34,5 +34,21 @@ with ContactEngine(0, p) as eng:
     big = synth.cloud_featured(24000, seed=77)                  # binding-site flags through the cell grid (>= 20 000 atoms)
     eng.upload_atoms(big)
     print('flag_within (grid)', int(eng.flag_within(6.0).sum()), 'atoms flagged')
+    # wire-form uploads (counts, sparse neighbours, fixed-point hydrogens), the packed view built behind the run
+    from arpeggio_b200.engine import PackedPairs  # noqa: E402
+    import numpy as np  # noqa: E402
+    for n, dec in ((9000, 3), (5000, None), (140_000, 3)):
+        src = synth.cloud_featured(n, seed=90 + n, h_decimals=dec)
+        eng.upload_atoms(src.to_wire())
+        eng.run_pairs_async()
+        out = PackedPairs(np.zeros(n + 2, np.uint32), np.zeros(16 * n, np.uint32), np.zeros(16 * n, np.uint8), np.zeros(16 * n, np.float32))
+        eng.fetch_pairs_packed_async(out, 5 * n, True)              # fewer words than the run has: the wait fetches the rest
+        pk = eng.fetch_pairs_packed_wait()
+        print('wire + packed', n, pk.n, 'records', pk.bits_j, 'bits,', pk.n_faults, 'fault records')
+    off = eng.upload_atoms_batch([q.to_wire() if k % 2 else q for k, q in enumerate(parts)])
+    eng.run_pairs_async()
+    out = PackedPairs(np.zeros(int(off[-1]) + 2, np.uint32), np.zeros(100_000, np.uint32), None, None)
+    eng.fetch_pairs_packed_async(out, 0, False)
+    print('device-packed batch, mixed forms, packed view', eng.fetch_pairs_packed_wait().n, 'records')
 if os.environ.get('ARPEGGIO_TILES'):
     print('the fused tile kernel (k_tiles) ran in place of k_search + k_classify')

@@ -9,13 +9,13 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np
 import util
 from arpeggio_b200 import abi, params as arp_params, synth
-from arpeggio_b200.engine import ContactEngine
+from arpeggio_b200.engine import ContactEngine, PackedPairs
 from oracle import oracle
 
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 t0 = time.time()
-checked = dict(pairs=0, records=0, batches=0, planes=0, within=0)
+checked = dict(pairs=0, records=0, batches=0, planes=0, within=0, wire_packed=0, h_fix=0)
 
 
 def make(rng, n, seed):
@@ -47,6 +47,20 @@ with ContactEngine(0) as eng:
         cp = eng.fetch_pairs_compact(with_dist=True)
         util.assert_records_equal(cp.to_records(), exp, f'case {c}: compact')
         checked['pairs'] += 1; checked['records'] += exp.shape[0]
+        # wire-form upload, packed view built behind the run, a blind copy of a random share of the words
+        if rng.random() < 0.5:
+            soa.h_xyz[:] = np.round(soa.h_xyz, 3)
+            exp = oracle.pairs(soa, p)
+        w = soa.to_wire()
+        checked['h_fix'] += w.h_fix is not None
+        eng.upload_atoms(w)
+        eng.run_pairs_async()
+        cap = exp.shape[0] + int(rng.integers(0, 50))
+        out = PackedPairs(np.zeros(n + 2, np.uint32), np.zeros(cap, np.uint32), np.zeros(cap, np.uint8), np.zeros(cap, np.float32))
+        eng.fetch_pairs_packed_async(out, int(rng.choice([0, 1, exp.shape[0] // 2, exp.shape[0], 10 ** 9])), True)
+        pk = eng.fetch_pairs_packed_wait()
+        util.assert_records_equal(pk.to_records(soa.feat), exp, f'case {c}: wire + packed')
+        checked['wire_packed'] += 1
         r = float(rng.choice([6.0, 2.0, 11.0]))
         assert np.array_equal(eng.flag_within(r), oracle.flag_within(soa, r)), f'case {c}: within {r}'
         checked['within'] += 1
@@ -63,12 +77,15 @@ with ContactEngine(0) as eng:
         if c % 3 == 0:
             parts = [make(rng, int(rng.choice([0, 1, 40, 700, 2500, 6000])), 80_000 + 10 * c + k) for k in range(int(rng.integers(2, 7)))]
             parts = [q for q in parts if q.n_atoms > 0] or [make(rng, 30, 81_000 + c)]
-            off = eng.upload_atoms_batch(parts)
+            off = eng.upload_atoms_batch([q.to_wire() if (k + c) % 2 else q for k, q in enumerate(parts)])
             eng.run_pairs_async()
             cb = eng.fetch_pairs_compact(with_dist=True)
+            pb = eng.fetch_pairs_packed(with_dist=True)
             for k, part in enumerate(parts):
                 rec = cb.structure(int(off[k]), int(off[k + 1])).to_records()
                 rec['j'] -= int(off[k])
-                util.assert_records_equal(rec, oracle.pairs(part, p), f'case {c}: packed structure {k}')
+                want = oracle.pairs(part, p)
+                util.assert_records_equal(rec, want, f'case {c}: packed structure {k}')
+                util.assert_records_equal(pb.structure(int(off[k]), int(off[k + 1])).to_records(part.feat), want, f'case {c}: packed words of structure {k}')
             checked['batches'] += 1
 print('stress ok:', checked, 'in %.0f s' % (time.time() - t0), '(tile kernel)' if os.environ.get('ARPEGGIO_TILES') else '')

@@ -6,7 +6,7 @@ import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(ROOT, 'arpeggio_b200', 'libarpeggio_cuda.so')
 out = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True).stdout
-want = ('k_grid_reg', 'k_search', 'k_classify', 'k_hscan', 'k_tiles', 'k_sort_', 'k_pl_', 'k_merge_', 'k_wg_', 'k_sift', 'k_grid_fused')
+want = ('k_grid_reg', 'k_search', 'k_classify', 'k_hscan', 'k_tiles', 'k_sort_', 'k_pl_', 'k_merge_', 'k_wg_', 'k_sift', 'k_grid_fused', 'k_cnt_', 'k_wire_')
 cur, hist = None, collections.OrderedDict()
 for line in out.splitlines():
     m = re.search(r'Function : (\S+)', line)

@@ -7,6 +7,9 @@
 #define _GNU_SOURCE
 #endif
 #include <math.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <sched.h>
 #include <stdlib.h>
 #include <new>
@@ -404,9 +407,15 @@ int wire_sizes(arp_ctx* c, const arp_atoms* a, WireSizes* w)
     ARP_REQUIRE(c, !(a->h_cnt && a->h_off), ARP_E_INVALID_ARG, "h_cnt and h_off are alternatives");
     ARP_REQUIRE(c, !(a->h_fix && a->h_xyz), ARP_E_INVALID_ARG, "h_fix and h_xyz are alternatives");
     ARP_REQUIRE(c, !a->h_fix || (a->h_fix_scale > 0.0 && a->h_fix_scale < 1e12), ARP_E_INVALID_ARG, "h_fix_scale out of range");
-    auto total = [&](const uint8_t* cnt) {         /* byte sum, eight at a time in four 16-bit lanes (flushed before a lane can overflow) */
+    auto total = [&](const uint8_t* cnt) {         /* byte sum: 16 at a time (psadbw) where SSE2 is there, else 8 in four 16-bit lanes */
         long long s = 0;
         int i = 0;
+#if defined(__SSE2__)
+        __m128i acc = _mm_setzero_si128();
+        const __m128i zero = _mm_setzero_si128();
+        for (; i + 16 <= N; i += 16) acc = _mm_add_epi64(acc, _mm_sad_epu8(_mm_loadu_si128((const __m128i*)(cnt + i)), zero));
+        s = (long long)_mm_cvtsi128_si64(acc) + (long long)_mm_cvtsi128_si64(_mm_unpackhi_epi64(acc, acc));
+#else
         const uint64_t M = 0x00ff00ff00ff00ffull;
         while (i + 8 <= N) {
             uint64_t acc = 0;
@@ -417,6 +426,7 @@ int wire_sizes(arp_ctx* c, const arp_atoms* a, WireSizes* w)
             }
             s += (long long)((acc & 0xffff) + ((acc >> 16) & 0xffff) + ((acc >> 32) & 0xffff) + (acc >> 48));
         }
+#endif
         for (; i < N; ++i) s += cnt[i];
         return s;
     };
@@ -670,7 +680,18 @@ int arp_upload_atoms(arp_ctx* c, const arp_atoms* a)
             ARP_REQUIRE(c, a->struct_off[s] <= a->struct_off[s + 1], ARP_E_INVALID_ARG, "struct_off must ascend");
     }
     ARP_TRY(arp_bind(c));
-    c->have_atoms = 0; pairs_invalidate(c); c->radtab_valid = 0;
+    c->have_atoms = 0; pairs_invalidate(c);
+    /* the radius-sum table depends on (vdw, cov, vdw_comp) only: a structure with the same radius tables keeps it */
+    {
+        const size_t kb = (size_t)a->n_rad_classes * sizeof(double);
+        const bool same = c->radtab_valid && N > 0 && c->rad_host.size() == 2 * (size_t)a->n_rad_classes &&
+                          memcmp(c->rad_host.data(), a->vdw, kb) == 0 && memcmp(c->rad_host.data() + a->n_rad_classes, a->cov, kb) == 0;
+        if (!same) {
+            c->radtab_valid = 0;
+            c->rad_host.clear();
+            if (N > 0) { c->rad_host.insert(c->rad_host.end(), a->vdw, a->vdw + a->n_rad_classes); c->rad_host.insert(c->rad_host.end(), a->cov, a->cov + a->n_rad_classes); }
+        }
+    }
     c->atom_ring.valid = 0;
     c->input_bytes = 0;
     c->N = N; c->Rs = a->n_residues; c->K = a->n_rad_classes; c->S = S;
@@ -875,7 +896,7 @@ int arp_upload_atoms_batch(arp_ctx* c, const arp_atoms* const* parts, int32_t n_
     }
     ARP_REQUIRE(c, N <= 500000000 && E < (1ll << 31) && H < (1ll << 31), ARP_E_INVALID_ARG, "batch too large");
     ARP_TRY(arp_bind(c));
-    c->have_atoms = 0; pairs_invalidate(c); c->radtab_valid = 0;
+    c->have_atoms = 0; pairs_invalidate(c); c->radtab_valid = 0; c->rad_host.clear();
     c->atom_ring.valid = 0;
     /* ---- host tables: part descriptors, struct_off, merged radius table + class maps (one pinned block) ---- */
     std::vector<double> vdw, cov;

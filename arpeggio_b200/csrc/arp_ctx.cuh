@@ -6,6 +6,7 @@
 #define ARP_CTX_CUH
 
 #include <cuda_runtime.h>
+#include <vector>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -146,6 +147,7 @@ struct arp_ctx {
     DBuf hreach;                  /* upload generation << 32 | float bits of the longest donor-hydrogen distance */
     unsigned upload_gen = 0;
     int radtab_valid = 0;
+    std::vector<double> rad_host;     /* vdw | cov of the upload the radius-sum table was built for (bitwise comparison at the next upload) */
     int cls_smem_set = 0;
     int hscan_blocks = 0;         /* co-resident blocks of k_hscan (probed once) */
     int coop_blocks = -1;         /* co-resident blocks of k_grid_fused (0: not available, -1: not probed) */

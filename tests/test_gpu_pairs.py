@@ -576,3 +576,19 @@ def test_async_packed_fetch_survives_an_overflowing_run():
         eng.fetch_pairs_packed_async(out, 0, False)
         pk = eng.fetch_pairs_packed_wait()
         util.assert_records_equal(pk.to_records(dense.feat, dist=eng.fetch_pairs_dist(pk.n)), exp, 'async packed after an overflow')
+
+
+def test_radius_table_follows_the_upload(engine):
+    """The K x K radius-sum table is kept across uploads whose vdw / cov tables are bitwise the same and rebuilt when a
+    value, the number of classes or vdw_comp changes."""
+    p = arp_params.make_params()
+    engine.set_params(p)
+    a = synth.cloud_featured(5000, seed=91)
+    b = dataclasses.replace(a, vdw=a.vdw * 1.07)
+    c = dataclasses.replace(a, cov=np.concatenate([a.cov * 0.9, [0.5]]), vdw=np.concatenate([a.vdw, [1.1]]))
+    for name, soa in (('a', a), ('a again', a), ('b: other vdw radii', b), ('a', a), ('c: one class more', c), ('b', b)):
+        util.assert_records_equal(engine.pairs(soa), oracle.pairs(soa, p), name)
+    p2 = arp_params.make_params(5.0, 0.35, False)
+    engine.set_params(p2)
+    util.assert_records_equal(engine.pairs(b), oracle.pairs(b, p2), 'b after vdw_comp changed')
+    assert not np.array_equal(oracle.pairs(a, p)['mask'], oracle.pairs(b, p)['mask'])

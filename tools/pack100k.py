@@ -1,5 +1,9 @@
+#!/usr/bin/env python
+"""End-to-end time per 100k-atom structure when several of them share one launch sequence (BatchRunner.run(packed=True, pack=k)):
+the merge kernels cost what the longer kernels save.  Run under gpurun."""
 import sys
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from arpeggio_b200 import params, synth
 from arpeggio_b200.batch import BatchRunner
 from arpeggio_b200.engine import pinned_soa

@@ -54,7 +54,7 @@ def lib():
         'arp_pairs_fetch_compact': (i32, [vp, vp, vp, u64, vp, u64p]),
         'arp_pairs_fetch_dist': (i32, [vp, vp, u64]),
         'arp_pairs_fetch_packed': (i32, [vp, vp, vp, vp, u64, vp, u64p, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]),
-        'arp_pairs_unpack_packed': (i32, [vp, vp, vp, vp, i32, i32, vp, vp, i32, vp, u64]),
+        'arp_pairs_unpack_packed': (i32, [vp, vp, vp, vp, i32, i32, vp, vp, i32, vp, u64, i32]),
         'arp_pairs_fetch_packed_async': (i32, [vp, vp, vp, vp, u64, vp, u64]),
         'arp_pairs_fetch_packed_wait': (i32, [vp, u64p, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]),
         'arp_pairs_unpack': (i32, [vp, vp, vp, i32, vp, u64]),

@@ -13,6 +13,7 @@
 #include <sched.h>
 #include <stdlib.h>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "arp_ctx.cuh"
@@ -1222,8 +1223,43 @@ int arp_pairs_fetch_packed_wait(arp_ctx* c, uint64_t* n_pairs, int32_t* bits_j, 
 
 /* host only: the packed view back into 16-byte records.  feat: the ARP_F_* words of the uploaded atoms (the entity class
    is a function of their selection / water bits, rule_entity_class_bools = interactions.py:643-691) */
+/* rows [r0, r1) of the packed view -> records */
+static int unpack_packed_rows(const uint32_t* row_off, const uint32_t* lo32, const uint8_t* hi8, const float* dist, int32_t n_atoms,
+                              int32_t bits_j, const uint32_t* feat, const int32_t* struct_off, int32_t n_structures, arp_pair* dst,
+                              uint64_t n, int32_t r0, int32_t r1)
+{
+    const uint64_t jmask = (1ull << bits_j) - 1ull;
+    uint32_t cls_of[16];                               /* branch-free: the six ifs as a table over (sel_i, sel_j, water_i, water_j) */
+    for (int k = 0; k < 16; ++k) cls_of[k] = rule_entity_class_bools(k & 1, (k >> 1) & 1, (k >> 2) & 1, (k >> 3) & 1) << ARP_CLASS_SHIFT;
+    int32_t s = 0, base = 0, end = n_atoms;            /* structure of row i: its first atom and the one behind its last */
+    if (struct_off) {
+        int lo = 0, hi = n_structures;                 /* last structure whose first atom is <= r0 */
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (struct_off[mid] <= r0) lo = mid; else hi = mid; }
+        s = lo; base = struct_off[s]; end = struct_off[s + 1];
+    }
+    for (int32_t i = r0; i < r1; ++i) {
+        while (struct_off && i >= end) { ++s; base = struct_off[s]; end = struct_off[s + 1]; if (end < base) return ARP_E_INVALID_ARG; }
+        if (row_off[i + 1] < row_off[i] || row_off[i + 1] > n) return ARP_E_INVALID_ARG;
+        const uint32_t fi = feat[i];
+        const uint32_t row_bits = ((fi & ARP_F_IN_SELECTION) ? 1u : 0u) | ((fi & ARP_F_IS_WATER) ? 4u : 0u);
+        const uint64_t k1 = row_off[i + 1];
+        for (uint64_t k = row_off[i]; k < k1; ++k) {
+            const uint64_t w = (uint64_t)lo32[k] | (hi8 ? (uint64_t)hi8[k] << 32 : 0ull);
+            const int64_t j = (int64_t)(w & jmask) + base;              /* the word holds j local to the structure */
+            if (j < base || j >= end) return ARP_E_INVALID_ARG;
+            const uint32_t fj = feat[j];
+            const uint32_t idx = row_bits | ((fj & ARP_F_IN_SELECTION) ? 2u : 0u) | ((fj & ARP_F_IS_WATER) ? 8u : 0u);
+            dst[k].i = i; dst[k].j = (int32_t)j;
+            dst[k].mask = (uint32_t)((w >> bits_j) & 0x7fffu) | cls_of[idx];
+            dst[k].dist = dist ? dist[k] : 0.f;
+        }
+    }
+    return ARP_OK;
+}
+
 int arp_pairs_unpack_packed(const uint32_t* row_off, const uint32_t* lo32, const uint8_t* hi8, const float* dist, int32_t n_atoms,
-                            int32_t bits_j, const uint32_t* feat, const int32_t* struct_off, int32_t n_structures, arp_pair* dst, uint64_t cap)
+                            int32_t bits_j, const uint32_t* feat, const int32_t* struct_off, int32_t n_structures, arp_pair* dst, uint64_t cap,
+                            int32_t threads)
 {
     if (n_atoms < 0 || (n_atoms > 0 && (!row_off || !feat)) || bits_j < 1 || bits_j > 31) return ARP_E_INVALID_ARG;
     if (struct_off && (n_structures < 1 || struct_off[0] != 0 || struct_off[n_structures] != n_atoms)) return ARP_E_INVALID_ARG;
@@ -1231,23 +1267,28 @@ int arp_pairs_unpack_packed(const uint32_t* row_off, const uint32_t* lo32, const
     const uint64_t n = row_off[n_atoms];
     if (n > cap) return ARP_E_CAPACITY;
     if (n && (!lo32 || !dst || (bits_j + 15 > 32 && !hi8))) return ARP_E_INVALID_ARG;
-    const uint64_t jmask = (1ull << bits_j) - 1ull;
-    int32_t s = 0, base = 0, end = n_atoms;            /* structure of row i: its first atom and the one behind its last */
-    if (struct_off) end = struct_off[1];
-    for (int32_t i = 0; i < n_atoms; ++i) {
-        while (struct_off && i >= end) { ++s; base = struct_off[s]; end = struct_off[s + 1]; if (end < base) return ARP_E_INVALID_ARG; }
-        if (row_off[i + 1] < row_off[i] || row_off[i + 1] > n) return ARP_E_INVALID_ARG;
-        const bool si = (feat[i] & ARP_F_IN_SELECTION) != 0, wi = (feat[i] & ARP_F_IS_WATER) != 0;
-        for (uint64_t k = row_off[i]; k < row_off[i + 1]; ++k) {
-            const uint64_t w = (uint64_t)lo32[k] | (hi8 ? (uint64_t)hi8[k] << 32 : 0ull);
-            const int64_t j = (int64_t)(w & jmask) + base;              /* the word holds j local to the structure */
-            if (j < base || j >= end) return ARP_E_INVALID_ARG;
-            const uint32_t cls = rule_entity_class_bools(si, (feat[j] & ARP_F_IN_SELECTION) != 0, wi, (feat[j] & ARP_F_IS_WATER) != 0);
-            dst[k].i = i; dst[k].j = (int32_t)j;
-            dst[k].mask = (uint32_t)((w >> bits_j) & 0x7fffu) | (cls << ARP_CLASS_SHIFT);
-            dst[k].dist = dist ? dist[k] : 0.f;
-        }
+    if (struct_off) for (int32_t s = 0; s < n_structures; ++s) if (struct_off[s + 1] < struct_off[s]) return ARP_E_INVALID_ARG;
+    int T = threads > 1 ? threads : 1;
+    if (T > 64) T = 64;
+    if (n < 200000 || n_atoms < 4 * T) T = 1;          /* not worth a thread start */
+    if (T == 1) return unpack_packed_rows(row_off, lo32, hi8, dist, n_atoms, bits_j, feat, struct_off, n_structures, dst, n, 0, n_atoms);
+    /* rows cut where the record count crosses k * n / T (row_off must ascend for the search to mean anything: each share checks its rows) */
+    std::vector<int32_t> cut((size_t)T + 1);
+    cut[0] = 0; cut[(size_t)T] = n_atoms;
+    for (int t = 1; t < T; ++t) {
+        const uint64_t want = n / (uint64_t)T * (uint64_t)t;
+        int32_t lo = 0, hi = n_atoms;
+        while (lo < hi) { const int32_t mid = lo + (hi - lo) / 2; if (row_off[mid] < want) lo = mid + 1; else hi = mid; }
+        cut[(size_t)t] = lo < cut[(size_t)t - 1] ? cut[(size_t)t - 1] : lo;
     }
+    std::vector<int> rc((size_t)T, ARP_OK);
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; ++t)
+        pool.emplace_back([&, t] { rc[(size_t)t] = unpack_packed_rows(row_off, lo32, hi8, dist, n_atoms, bits_j, feat, struct_off, n_structures, dst, n,
+                                                                       cut[(size_t)t], cut[(size_t)t + 1]); });
+    rc[0] = unpack_packed_rows(row_off, lo32, hi8, dist, n_atoms, bits_j, feat, struct_off, n_structures, dst, n, cut[0], cut[1]);
+    for (std::thread& th : pool) th.join();
+    for (int t = 0; t < T; ++t) if (rc[(size_t)t] != ARP_OK) return rc[(size_t)t];
     return ARP_OK;
 }
 

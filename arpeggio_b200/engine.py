@@ -163,10 +163,11 @@ class PackedPairs:
     def nbytes(self):
         return self.row_off.nbytes + self.lo.nbytes + (self.hi.nbytes if self.hi is not None else 0) + (self.dist.nbytes if self.dist is not None else 0)
 
-    def to_records(self, feat, dist=None, struct_off=None):
+    def to_records(self, feat, dist=None, struct_off=None, threads=0):
         """PAIR_DTYPE[n] through the library's host unpacker; feat: the uploaded atoms' feature words (uint32[n_atoms]).
         struct_off: the atom offsets of a batch (the words of a batch hold structure-local j; the records come out with
-        the batch-global indices).  A view made by structure() needs none: its records are local to the structure."""
+        the batch-global indices).  A view made by structure() needs none: its records are local to the structure.
+        threads > 1: host threads that share the rows."""
         out = np.empty(self.n, dtype=abi.PAIR_DTYPE)
         feat = np.ascontiguousarray(feat, np.uint32)
         d = self.dist if dist is None else np.ascontiguousarray(dist, np.float32)
@@ -175,7 +176,7 @@ class PackedPairs:
                                            self.hi.ctypes.data if self.hi is not None and self.n else None,
                                            d.ctypes.data if d is not None and self.n else None, self.n_atoms, self.bits_j,
                                            feat.ctypes.data if self.n_atoms else None, so.ctypes.data if so is not None else None,
-                                           0 if so is None else so.shape[0] - 1, out.ctypes.data if self.n else None, self.n)
+                                           0 if so is None else so.shape[0] - 1, out.ctypes.data if self.n else None, self.n, int(threads))
         if rc != abi.OK:
             raise ArpeggioCudaError(rc, 'arp_pairs_unpack_packed failed')
         return out

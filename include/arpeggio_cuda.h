@@ -341,10 +341,10 @@ int  arp_pairs_fetch_packed(arp_ctx* ctx, uint32_t* row_off, uint32_t* lo32, uin
    pair spans two structures -- so bits_j is that of the largest structure.  struct_off [n_structures + 1] (NULL: one
    structure) gives the structures' first atoms: the records come out with the run's global i and j.  To unpack ONE
    structure of a batch pass its rows (row_off rebased to start at 0), words and feat with struct_off = NULL: i and j
-   are then local to it. */
+   are then local to it.  threads > 1: that many host threads share the rows (1.25 M records: about 11 ms with one). */
 int  arp_pairs_unpack_packed(const uint32_t* row_off, const uint32_t* lo32, const uint8_t* hi8, const float* dist,
                              int32_t n_atoms, int32_t bits_j, const uint32_t* feat, const int32_t* struct_off, int32_t n_structures,
-                             arp_pair* dst, uint64_t cap);
+                             arp_pair* dst, uint64_t cap, int32_t threads);
 
 /* arp_pairs_fetch_packed split for pipelining: _async enqueues the sorted packed view and its copies BEHIND a run that
    has not been waited for (arp_pairs_run_async) -- the record count is read on the device and the first

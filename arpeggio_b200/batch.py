@@ -4,9 +4,12 @@ The reference processes one structure per process invocation (process_protein_cl
 structures share no state, so a batch shards with no collective on the data path:
   - across GPUs: `shard_indices` gives every rank (one process per GPU) its part of the list,
     greedy longest-first by atom count so that the ranks finish together;
-  - inside a GPU: `BatchRunner` keeps `slots` contexts (device buffers + stream each) busy from
-    `slots` host threads, so the H2D copy of one structure, the kernels of another and the D2H
-    copy of a third overlap (PCIe is full duplex; ctypes releases the GIL during the calls).
+  - inside a GPU: `BatchRunner` keeps `slots` contexts (device buffers + stream each) busy, so the
+    H2D copy of one structure, the kernels of another and the D2H copy of a third overlap (PCIe is
+    full duplex).  The packed stream (`run(packed=True)`) is pipelined from ONE host thread: a step is
+    enqueued whole (upload, kernels, sorted view, copies) and waited for when its slot comes round
+    again -- several submitting threads only contend for the driver's launch path.  The older stream
+    forms (16-byte records, compact) use one worker thread per slot (ctypes releases the GIL).
 """
 import queue
 import threading
@@ -36,9 +39,11 @@ def shard_indices(sizes, world_size, rank):
 
 
 class BatchRunner:
-    """`slots` ContactEngines on one device, driven by `slots` worker threads."""
+    """`slots` ContactEngines (contexts, one stream each) on one device.  run(packed=True) drives them from the calling
+    thread (submit_threads of them when asked for), every step enqueued whole; the other stream forms use one worker
+    thread per slot."""
 
-    def __init__(self, device=0, slots=6, params=None, submit_threads=1):
+    def __init__(self, device=0, slots=8, params=None, submit_threads=1):
         self.device = device
         self.submit_threads = submit_threads          # host threads that enqueue the pipelined packed stream (run(packed=True))
         self.engines = [ContactEngine(device, params) for _ in range(max(1, slots))]

@@ -518,6 +518,22 @@ def test_wire_forms_are_checked(engine):
     w.bond_off = soa.bond_off                           # both forms at once
     with pytest.raises(Exception, match='alternatives'):
         engine.upload_atoms(w)
+    w = soa.to_wire()
+    w.h_cnt = w.h_cnt.copy()
+    w.h_cnt[-1] += 2                                    # more hydrogens announced than h_xyz holds
+    with pytest.raises(Exception, match='h_cnt'):
+        engine.upload_atoms(w)
+    r = dataclasses.replace(soa, h_xyz=np.round(soa.h_xyz, 3)).to_wire()
+    assert r.h_fix is not None
+    r.h_fix_scale = 0.0
+    with pytest.raises(Exception, match='h_fix_scale'):
+        engine.upload_atoms(r)
+    w = soa.to_wire()
+    w.xnbr_idx = w.xnbr_idx.copy()
+    if w.xnbr_idx.shape[0]:
+        w.xnbr_idx[-1] = soa.n_atoms                    # out of range
+        with pytest.raises(Exception, match='xnbr_idx'):
+            engine.upload_atoms(w)
     engine.set_params(arp_params.make_params())
     util.assert_records_equal(engine.pairs(soa.to_wire()), oracle.pairs(soa, arp_params.make_params()), 'after the rejected uploads')
 

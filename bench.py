@@ -495,7 +495,9 @@ def run_ours(args):
                     'pcie': dict(pcie_min, what='pinned cudaMemcpyAsync of the step\'s H2D and D2H sizes, both directions at once, '
                                                 'every rank at the same time (min over ranks, GB/s per GPU)',
                                  d2h_floor_ms=d2h_bytes / (pcie_min['d2h_gbs'] * 1e6) if pcie_min['d2h_gbs'] else None,
-                                 h2d_floor_ms=in_bytes_wire / (pcie_min['h2d_gbs'] * 1e6) if pcie_min['h2d_gbs'] else None)},
+                                 h2d_floor_ms=in_bytes_wire / (pcie_min['h2d_gbs'] * 1e6) if pcie_min['h2d_gbs'] else None,
+                                 e2e_fraction_of_floor=(max(d2h_bytes / pcie_min['d2h_gbs'], in_bytes_wire / pcie_min['h2d_gbs']) / 1e6 / (e2e_max * 1e3)
+                                                        if pcie_min['d2h_gbs'] and pcie_min['h2d_gbs'] else None))},
             'resident_pipelined': pipelined,
             'gpu_launches': int(launches),
             'kernels_per_step': int(per_step),

@@ -75,6 +75,7 @@ def test_product_arm_prints_the_contract_line():
     assert 0 < legs['with_distances']['value'] <= e['value'] * 1.2 and d['resident_pipelined']['value'] > 0
     assert legs['wire_h_fix']['h2d_bytes_per_step'] < e['h2d_bytes_per_step'] and legs['wire_h_fix']['value'] > 0
     assert e['pcie']['h2d_gbs'] > 1 and e['pcie']['d2h_gbs'] > 1 and e['serial_value'] > 0
+    assert 0.05 < e['pcie']['e2e_fraction_of_floor'] < 1.3          # the end-to-end step against the slower copy direction alone
     rf = d['roofline']
     assert rf['bound'] == 'hbm' and rf['unit'] == 'GB/s' and abs(rf['frac'] - rf['achieved'] / rf['peak']) < 1e-9
     assert rf['algorithmic_bytes'] > 16 * d['config']['pairs_per_structure']
